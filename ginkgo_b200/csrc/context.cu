@@ -1,0 +1,158 @@
+// Executor glue behind include/ginkgo_b200.h: device/stream ownership, raw
+// memory, copies, synchronisation.  Mirrors what CudaExecutor provides to the
+// kernels in the reference (cuda/base/executor.cpp: raw_alloc/raw_free/
+// raw_copy_to/synchronize; stubs listed at core/device_hooks/cuda_hooks.cpp:19-250).
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace b200 {
+
+static thread_local char g_err[512] = {0};
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+}  // namespace b200
+
+void* b200_ctx::scratch(size_t bytes)
+{
+    if (bytes <= ws.bytes) return ws.ptr;
+    // grow: stream-ordered free + alloc keeps earlier kernels valid
+    size_t nb = bytes < (1u << 20) ? (1u << 20) : bytes * 2;
+    void* np = nullptr;
+    if (cudaMallocAsync(&np, nb, stream) != cudaSuccess) return nullptr;
+    if (ws.ptr) cudaFreeAsync(ws.ptr, stream);
+    ws.ptr = np;
+    ws.bytes = nb;
+    return np;
+}
+
+extern "C" {
+
+const char* b200_last_error(void) { return b200::g_err; }
+
+const char* b200_version(void)
+{
+    return "ginkgo_b200 0.1 (hand-written CUDA, sm_100a, CUDA " B200_STR(CUDART_VERSION) ")";
+}
+
+b200_status b200_ctx_create(int32_t device_id, void* cuda_stream, b200_ctx** out)
+{
+    B200_REQUIRE(out != nullptr, "out must not be null");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        b200::set_error("no CUDA device available (%s): this library has no CPU fallback",
+                        cudaGetErrorString(e));
+        return B200_ERR_CUDA;
+    }
+    B200_REQUIRE(device_id >= 0 && device_id < ndev, "device_id out of range");
+    B200_CUDA_CHECK(cudaSetDevice(device_id));
+    cudaDeviceProp prop;
+    B200_CUDA_CHECK(cudaGetDeviceProperties(&prop, device_id));
+    if (prop.major != 10) {
+        b200::set_error("device %d is sm_%d%d; this library contains sm_100a code only", device_id,
+                        prop.major, prop.minor);
+        return B200_ERR_UNSUPPORTED;
+    }
+    b200_ctx* c = new b200_ctx();
+    c->device = device_id;
+    c->num_sms = prop.multiProcessorCount;
+    c->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (cuda_stream) {
+        c->stream = (cudaStream_t)cuda_stream;
+    } else {
+        B200_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->owns_stream = true;
+    }
+    B200_CUDA_CHECK(cudaMalloc((void**)&c->counters, 256 * sizeof(unsigned int)));
+    B200_CUDA_CHECK(cudaMemsetAsync(c->counters, 0, 256 * sizeof(unsigned int), c->stream));
+    B200_CUDA_CHECK(cudaMallocHost((void**)&c->pinned, 4096));
+    memset(c->pinned, 0, 4096);
+    B200_CUDA_CHECK(cudaMalloc(&c->dev_mailbox, 4096));
+    B200_CUDA_CHECK(cudaMemsetAsync(c->dev_mailbox, 0, 4096, c->stream));
+    B200_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    *out = c;
+    return B200_OK;
+}
+
+void b200_ctx_destroy(b200_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->ws.ptr) cudaFree(ctx->ws.ptr);
+    if (ctx->counters) cudaFree(ctx->counters);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->dev_mailbox) cudaFree(ctx->dev_mailbox);
+    if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+void* b200_ctx_stream(const b200_ctx* ctx) { return (void*)ctx->stream; }
+int32_t b200_ctx_device(const b200_ctx* ctx) { return ctx->device; }
+int32_t b200_ctx_num_sms(const b200_ctx* ctx) { return ctx->num_sms; }
+int64_t b200_ctx_launch_count(const b200_ctx* ctx) { return ctx->launches; }
+
+b200_status b200_alloc(b200_ctx* ctx, size_t bytes, void** out)
+{
+    B200_REQUIRE(ctx && out, "null argument");
+    *out = nullptr;
+    if (bytes == 0) return B200_OK;
+    B200_CUDA_CHECK(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e != cudaSuccess) {
+        b200::set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        cudaGetLastError();
+        return B200_ERR_ALLOC;
+    }
+    return B200_OK;
+}
+
+b200_status b200_free(b200_ctx* ctx, void* ptr)
+{
+    // like CudaExecutor::raw_free this must not fail loudly
+    // (core/device_hooks/cuda_hooks.cpp:113-118)
+    if (!ptr) return B200_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ptr);
+    return B200_OK;
+}
+
+b200_status b200_copy_h2d(b200_ctx* ctx, void* dst, const void* src, size_t bytes)
+{
+    if (bytes == 0) return B200_OK;
+    B200_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    B200_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}
+
+b200_status b200_copy_d2h(b200_ctx* ctx, void* dst, const void* src, size_t bytes)
+{
+    if (bytes == 0) return B200_OK;
+    B200_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}
+
+b200_status b200_copy_d2d(b200_ctx* ctx, void* dst, const void* src, size_t bytes)
+{
+    if (bytes == 0) return B200_OK;
+    B200_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return B200_OK;
+}
+
+b200_status b200_synchronize(b200_ctx* ctx)
+{
+    B200_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,252 @@
+// Drop-in Krylov step kernels: CG, BiCGStab (element-wise, masked by the
+// per-column stopping_status) -- replaces gko::kernels::cuda::{cg,bicgstab}::*
+// (reference common/unified/solver/{cg,bicgstab}_kernels.cpp); arithmetic
+// contract reference/solver/cg_kernels.cpp:24-115 and
+// reference/solver/bicgstab_kernels.cpp:25-190.  Scalars (rho, beta, ...) are
+// read from device memory by every thread, no host round trip.
+#include "elementwise.cuh"
+
+namespace b200 {
+namespace steps {
+
+template <typename V>
+b200_status cg_initialize(b200_ctx* ctx, int64_t rows, int64_t cols, const V* b, int64_t bs, V* r,
+                          int64_t rs, V* z, int64_t zs, V* p, int64_t ps, V* q, int64_t qs,
+                          V* prev_rho, V* rho, uint8_t* stop)
+{
+    B200_REQUIRE(ctx != nullptr, "ctx is null");
+    // the scalar rows are initialised by the first `cols` threads of an extra row
+    return launch_ew(ctx, rows + 1, cols, [=] __device__(int64_t i, int64_t j) {
+        if (i == rows) {
+            rho[j] = V(0);
+            prev_rho[j] = V(1);
+            stop[j] = 0;
+        } else {
+            r[i * rs + j] = b[i * bs + j];
+            z[i * zs + j] = V(0);
+            p[i * ps + j] = V(0);
+            q[i * qs + j] = V(0);
+        }
+    });
+}
+
+template <typename V>
+b200_status cg_step_1(b200_ctx* ctx, int64_t rows, int64_t cols, V* p, int64_t ps, const V* z,
+                      int64_t zs, const V* rho, const V* prev_rho, const uint8_t* stop)
+{
+    return launch_ew(ctx, rows, cols, [=] __device__(int64_t i, int64_t j) {
+        if (has_stopped(stop[j])) return;
+        const V pr = prev_rho[j];
+        if (pr == V(0)) {
+            p[i * ps + j] = z[i * zs + j];
+        } else {
+            const V tmp = rho[j] / pr;
+            p[i * ps + j] = z[i * zs + j] + tmp * p[i * ps + j];
+        }
+    });
+}
+
+template <typename V>
+b200_status cg_step_2(b200_ctx* ctx, int64_t rows, int64_t cols, V* x, int64_t xs, V* r,
+                      int64_t rs, const V* p, int64_t ps, const V* q, int64_t qs, const V* beta,
+                      const V* rho, const uint8_t* stop)
+{
+    return launch_ew(ctx, rows, cols, [=] __device__(int64_t i, int64_t j) {
+        if (has_stopped(stop[j])) return;
+        const V bt = beta[j];
+        if (bt != V(0)) {
+            const V tmp = rho[j] / bt;
+            x[i * xs + j] += tmp * p[i * ps + j];
+            r[i * rs + j] -= tmp * q[i * qs + j];
+        }
+    });
+}
+
+template <typename V>
+b200_status bicgstab_initialize(b200_ctx* ctx, int64_t rows, int64_t cols, const V* b, int64_t bs,
+                                V* r, int64_t rs, V* rr, int64_t rrs, V* y, int64_t ys, V* s,
+                                int64_t ss, V* t, int64_t ts, V* z, int64_t zs, V* v, int64_t vs,
+                                V* p, int64_t ps, V* prev_rho, V* rho, V* alpha, V* beta,
+                                V* gamma, V* omega, uint8_t* stop)
+{
+    return launch_ew(ctx, rows + 1, cols, [=] __device__(int64_t i, int64_t j) {
+        if (i == rows) {
+            rho[j] = V(1);
+            prev_rho[j] = V(1);
+            alpha[j] = V(1);
+            beta[j] = V(1);
+            gamma[j] = V(1);
+            omega[j] = V(1);
+            stop[j] = 0;
+        } else {
+            r[i * rs + j] = b[i * bs + j];
+            rr[i * rrs + j] = V(0);
+            z[i * zs + j] = V(0);
+            v[i * vs + j] = V(0);
+            s[i * ss + j] = V(0);
+            t[i * ts + j] = V(0);
+            y[i * ys + j] = V(0);
+            p[i * ps + j] = V(0);
+        }
+    });
+}
+
+template <typename V>
+b200_status bicgstab_step_1(b200_ctx* ctx, int64_t rows, int64_t cols, const V* r, int64_t rs,
+                            V* p, int64_t ps, const V* v, int64_t vs, const V* rho,
+                            const V* prev_rho, const V* alpha, const V* omega,
+                            const uint8_t* stop)
+{
+    return launch_ew(ctx, rows, cols, [=] __device__(int64_t i, int64_t j) {
+        if (has_stopped(stop[j])) return;
+        const V pr = prev_rho[j], om = omega[j];
+        if (pr * om != V(0)) {
+            const V tmp = rho[j] / pr * alpha[j] / om;
+            p[i * ps + j] = r[i * rs + j] + tmp * (p[i * ps + j] - om * v[i * vs + j]);
+        } else {
+            p[i * ps + j] = r[i * rs + j];
+        }
+    });
+}
+
+// step_2 also WRITES alpha (1 x cols).  Every thread of a column computes the
+// same value; row 0's thread stores it after all reads of the old alpha are
+// irrelevant (alpha is not an input of this kernel).
+template <typename V>
+b200_status bicgstab_step_2(b200_ctx* ctx, int64_t rows, int64_t cols, const V* r, int64_t rs,
+                            V* s, int64_t ss, const V* v, int64_t vs, const V* rho, V* alpha,
+                            const V* beta, const uint8_t* stop)
+{
+    return launch_ew(ctx, rows, cols, [=] __device__(int64_t i, int64_t j) {
+        if (has_stopped(stop[j])) return;
+        const V bt = beta[j];
+        V a = V(0);
+        if (bt != V(0)) {
+            a = rho[j] / bt;
+            s[i * ss + j] = r[i * rs + j] - a * v[i * vs + j];
+        } else {
+            s[i * ss + j] = r[i * rs + j];
+        }
+        if (i == 0) alpha[j] = a;
+    });
+}
+
+// step_3 also WRITES omega, which is not read by this kernel's other threads
+// (they recompute it from gamma/beta).
+template <typename V>
+b200_status bicgstab_step_3(b200_ctx* ctx, int64_t rows, int64_t cols, V* x, int64_t xs, V* r,
+                            int64_t rs, const V* s, int64_t ss, const V* t, int64_t ts,
+                            const V* y, int64_t ys, const V* z, int64_t zs, const V* alpha,
+                            const V* beta, const V* gamma, V* omega, const uint8_t* stop)
+{
+    return launch_ew(ctx, rows + 1, cols, [=] __device__(int64_t i, int64_t j) {
+        if (has_stopped(stop[j])) return;
+        const V bt = beta[j];
+        const V om = bt != V(0) ? gamma[j] / bt : V(0);
+        if (i == rows) {
+            omega[j] = om;
+            return;
+        }
+        x[i * xs + j] += alpha[j] * y[i * ys + j] + om * z[i * zs + j];
+        r[i * rs + j] = s[i * ss + j] - om * t[i * ts + j];
+    });
+}
+
+template <typename V>
+__global__ void finalize_status_kernel(int64_t cols, uint8_t* stop)
+{
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j < cols && has_stopped(stop[j])) stop[j] |= kFinalizedMask;
+}
+
+template <typename V>
+b200_status bicgstab_finalize(b200_ctx* ctx, int64_t rows, int64_t cols, V* x, int64_t xs,
+                              const V* y, int64_t ys, const V* alpha, uint8_t* stop)
+{
+    b200_status st = launch_ew(ctx, rows, cols, [=] __device__(int64_t i, int64_t j) {
+        const uint8_t sj = stop[j];
+        if (has_stopped(sj) && !is_finalized(sj)) x[i * xs + j] += alpha[j] * y[i * ys + j];
+    });
+    if (st != B200_OK || cols == 0) return st;
+    // the status flip must come after every thread has read the old status
+    if (rows > 0) {
+        finalize_status_kernel<V><<<(unsigned)ceildiv(cols, 256), 256, 0, ctx->stream>>>(cols, stop);
+        B200_LAUNCH_CHECK(ctx);
+    }
+    return B200_OK;
+}
+
+}  // namespace steps
+}  // namespace b200
+
+extern "C" {
+
+#define B200_DEF_STEPS(V, VT)                                                                  \
+    b200_status b200_cg_initialize_##V(b200_ctx* ctx, int64_t rows, int64_t cols, const VT* b, \
+                                       int64_t bs, VT* r, int64_t rs, VT* z, int64_t zs,       \
+                                       VT* p, int64_t ps, VT* q, int64_t qs, VT* prev_rho,     \
+                                       VT* rho, uint8_t* stop)                                 \
+    {                                                                                          \
+        return b200::steps::cg_initialize<VT>(ctx, rows, cols, b, bs, r, rs, z, zs, p, ps, q, qs,     \
+                                       prev_rho, rho, stop);                                   \
+    }                                                                                          \
+    b200_status b200_cg_step_1_##V(b200_ctx* ctx, int64_t rows, int64_t cols, VT* p,           \
+                                   int64_t ps, const VT* z, int64_t zs, const VT* rho,         \
+                                   const VT* prev_rho, const uint8_t* stop)                    \
+    {                                                                                          \
+        return b200::steps::cg_step_1<VT>(ctx, rows, cols, p, ps, z, zs, rho, prev_rho, stop);        \
+    }                                                                                          \
+    b200_status b200_cg_step_2_##V(b200_ctx* ctx, int64_t rows, int64_t cols, VT* x,           \
+                                   int64_t xs, VT* r, int64_t rs, const VT* p, int64_t ps,     \
+                                   const VT* q, int64_t qs, const VT* beta, const VT* rho,     \
+                                   const uint8_t* stop)                                        \
+    {                                                                                          \
+        return b200::steps::cg_step_2<VT>(ctx, rows, cols, x, xs, r, rs, p, ps, q, qs, beta, rho,     \
+                                   stop);                                                      \
+    }                                                                                          \
+    b200_status b200_bicgstab_initialize_##V(                                                  \
+        b200_ctx* ctx, int64_t rows, int64_t cols, const VT* b, int64_t bs, VT* r, int64_t rs, \
+        VT* rr, int64_t rrs, VT* y, int64_t ys, VT* s, int64_t ss, VT* t, int64_t ts, VT* z,   \
+        int64_t zs, VT* v, int64_t vs, VT* p, int64_t ps, VT* prev_rho, VT* rho, VT* alpha,    \
+        VT* beta, VT* gamma, VT* omega, uint8_t* stop)                                         \
+    {                                                                                          \
+        return b200::steps::bicgstab_initialize<VT>(ctx, rows, cols, b, bs, r, rs, rr, rrs, y, ys, s, \
+                                             ss, t, ts, z, zs, v, vs, p, ps, prev_rho, rho,    \
+                                             alpha, beta, gamma, omega, stop);                 \
+    }                                                                                          \
+    b200_status b200_bicgstab_step_1_##V(                                                      \
+        b200_ctx* ctx, int64_t rows, int64_t cols, const VT* r, int64_t rs, VT* p, int64_t ps, \
+        const VT* v, int64_t vs, const VT* rho, const VT* prev_rho, const VT* alpha,           \
+        const VT* omega, const uint8_t* stop)                                                  \
+    {                                                                                          \
+        return b200::steps::bicgstab_step_1<VT>(ctx, rows, cols, r, rs, p, ps, v, vs, rho, prev_rho,  \
+                                         alpha, omega, stop);                                  \
+    }                                                                                          \
+    b200_status b200_bicgstab_step_2_##V(                                                      \
+        b200_ctx* ctx, int64_t rows, int64_t cols, const VT* r, int64_t rs, VT* s, int64_t ss, \
+        const VT* v, int64_t vs, const VT* rho, VT* alpha, const VT* beta,                     \
+        const uint8_t* stop)                                                                   \
+    {                                                                                          \
+        return b200::steps::bicgstab_step_2<VT>(ctx, rows, cols, r, rs, s, ss, v, vs, rho, alpha,     \
+                                         beta, stop);                                          \
+    }                                                                                          \
+    b200_status b200_bicgstab_step_3_##V(                                                      \
+        b200_ctx* ctx, int64_t rows, int64_t cols, VT* x, int64_t xs, VT* r, int64_t rs,       \
+        const VT* s, int64_t ss, const VT* t, int64_t ts, const VT* y, int64_t ys,             \
+        const VT* z, int64_t zs, const VT* alpha, const VT* beta, const VT* gamma, VT* omega,  \
+        const uint8_t* stop)                                                                   \
+    {                                                                                          \
+        return b200::steps::bicgstab_step_3<VT>(ctx, rows, cols, x, xs, r, rs, s, ss, t, ts, y, ys,   \
+                                         z, zs, alpha, beta, gamma, omega, stop);              \
+    }                                                                                          \
+    b200_status b200_bicgstab_finalize_##V(b200_ctx* ctx, int64_t rows, int64_t cols, VT* x,   \
+                                           int64_t xs, const VT* y, int64_t ys,                \
+                                           const VT* alpha, uint8_t* stop)                     \
+    {                                                                                          \
+        return b200::steps::bicgstab_finalize<VT>(ctx, rows, cols, x, xs, y, ys, alpha, stop);        \
+    }
+
+B200_DEF_STEPS(f64, double)
+B200_DEF_STEPS(f32, float)
+
+}  // extern "C"

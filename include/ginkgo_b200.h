@@ -1,0 +1,341 @@
+/*
+ * ginkgo_b200.h -- the C ABI of the B200-native SpMV + Krylov hot path.
+ *
+ * This is the drop-in boundary: every entry point below is what a
+ * `gko::kernels::cuda::<ns>::<kernel>` wrapper (the reference's link-time
+ * backend plug-in) would call after unpacking the
+ * Ginkgo objects (matrix::Csr / Dense / array<>) into raw device pointers,
+ * sizes and strides.  INTEGRATION.md shows that wrapper for each namespace.
+ *
+ * Conventions (all entry points):
+ *   - `extern "C"`, POD arguments only; every data pointer is a DEVICE pointer
+ *     owned by the caller (the Ginkgo object) and must stay valid until the
+ *     stream reaches the call.  Scalars alpha/beta/rho/... are 1x1 or 1xncols
+ *     Dense matrices IN DEVICE MEMORY, as in the reference.
+ *   - Dense operands are row-major with an explicit row stride (elements),
+ *     exactly `matrix::Dense::get_const_values()/get_stride()`
+ *     (reference include/ginkgo/core/matrix/dense.hpp:861-912).
+ *   - Every kernel is enqueued on the context's stream and returns without
+ *     synchronising, except the calls documented as blocking (host copies and
+ *     the two stopping-criterion checks that must hand a host `bool` back,
+ *     reference core/stop/residual_norm.cpp:197-204).
+ *   - Return value: B200_OK or an error code; no C++ exception crosses.
+ *   - There is no CPU fallback: without a usable sm_100 device
+ *     b200_ctx_create fails and nothing else can be called.
+ *
+ * Type suffixes: f32/f64 = value type (float/double), i32/i64 = index type.
+ * `size_type` arrays of the reference (SELL-P slice_sets/slice_lengths, GMRES
+ * final_iter_nums) are uint64_t here; `stopping_status` is one uint8_t per
+ * right-hand side (bit7 converged, bit6 finalized, bits0-5 stopping id;
+ * reference include/ginkgo/core/stop/stopping_status.hpp).
+ */
+#ifndef GINKGO_B200_H_
+#define GINKGO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int32_t b200_status;
+enum {
+    B200_OK = 0,
+    B200_ERR_CUDA = 1,        /* a CUDA runtime call failed (-> gko::CudaError) */
+    B200_ERR_INVALID = 2,     /* bad argument (-> gko::DimensionMismatch / BadDimension) */
+    B200_ERR_UNSUPPORTED = 3, /* not implemented on this path (-> gko::NotSupported) */
+    B200_ERR_ALLOC = 4,       /* device allocation failed (-> gko::AllocationError) */
+    B200_ERR_COMM = 5         /* NCCL failure on the multi-GPU path */
+};
+
+typedef struct b200_ctx b200_ctx;           /* one per (device, stream): the CudaExecutor analogue */
+typedef struct b200_csr_plan b200_csr_plan; /* cached row partition, the `srow` analogue */
+typedef struct b200_coo_plan b200_coo_plan; /* cached row_idxs -> row_ptrs + row partition */
+
+/* last error text of the calling thread ("" if none) */
+const char* b200_last_error(void);
+/* library version / build info string (contains "sm_100a") */
+const char* b200_version(void);
+
+/* ---------------------------------------------------------------------------
+ * Executor glue: replaces CudaExecutor::{create, raw_alloc, raw_free,
+ * raw_copy_to, synchronize, get_num_multiprocessor,...}
+ * (reference cuda/base/executor.cpp; stubs core/device_hooks/cuda_hooks.cpp:19-250)
+ * ------------------------------------------------------------------------- */
+/* stream == NULL: the context creates and owns a non-blocking stream (the
+ * legacy default stream is never used). */
+b200_status b200_ctx_create(int32_t device_id, void* cuda_stream, b200_ctx** out);
+void b200_ctx_destroy(b200_ctx* ctx);
+void* b200_ctx_stream(const b200_ctx* ctx);
+int32_t b200_ctx_device(const b200_ctx* ctx);
+int32_t b200_ctx_num_sms(const b200_ctx* ctx);
+int64_t b200_ctx_launch_count(const b200_ctx* ctx); /* kernels launched so far by this ctx */
+b200_status b200_alloc(b200_ctx* ctx, size_t bytes, void** out);
+b200_status b200_free(b200_ctx* ctx, void* ptr);
+b200_status b200_copy_h2d(b200_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes); /* blocking */
+b200_status b200_copy_d2h(b200_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes); /* blocking */
+b200_status b200_copy_d2d(b200_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes);  /* async */
+b200_status b200_synchronize(b200_ctx* ctx);
+
+/* ---------------------------------------------------------------------------
+ * CSR  (reference core/matrix/csr_kernels.hpp:28-43; oracle
+ * reference/matrix/csr_kernels.cpp:47-118; today's CUDA path
+ * common/cuda_hip/matrix/csr_kernels.template.cpp:2353-2468)
+ *   spmv:           c = A b
+ *   advanced_spmv:  c = alpha A b + beta c      (beta == 0 never reads c)
+ * `plan` may be NULL (the partition is then recomputed on the stream).
+ * ------------------------------------------------------------------------- */
+#define B200_DECL_CSR(V, VT, I, IT)                                                          \
+    b200_status b200_csr_plan_create_##V##_##I(b200_ctx* ctx, int64_t num_rows, int64_t nnz, \
+                                               const IT* row_ptrs, b200_csr_plan** out);     \
+    b200_status b200_csr_spmv_##V##_##I(                                                     \
+        b200_ctx* ctx, const b200_csr_plan* plan, int64_t num_rows, int64_t num_cols,        \
+        int64_t nnz, const IT* row_ptrs, const IT* col_idxs, const VT* values, const VT* b,  \
+        int64_t b_stride, int64_t num_rhs, VT* c, int64_t c_stride);                         \
+    b200_status b200_csr_advanced_spmv_##V##_##I(                                            \
+        b200_ctx* ctx, const b200_csr_plan* plan, int64_t num_rows, int64_t num_cols,        \
+        int64_t nnz, const IT* row_ptrs, const IT* col_idxs, const VT* values,               \
+        const VT* alpha, const VT* b, int64_t b_stride, int64_t num_rhs, const VT* beta,     \
+        VT* c, int64_t c_stride);
+void b200_csr_plan_destroy(b200_csr_plan* plan);
+
+/* ---------------------------------------------------------------------------
+ * ELL (core/matrix/ell_kernels.hpp:21-35; reference/matrix/ell_kernels.cpp:29-120)
+ * column-major storage: element (row, i) at values[row + i*ell_stride],
+ * padding column index == -1 (invalid_index).
+ * ------------------------------------------------------------------------- */
+#define B200_DECL_ELL(V, VT, I, IT)                                                           \
+    b200_status b200_ell_spmv_##V##_##I(                                                      \
+        b200_ctx* ctx, int64_t num_rows, int64_t num_cols, int64_t num_stored_per_row,        \
+        int64_t ell_stride, const IT* col_idxs, const VT* values, const VT* b,                \
+        int64_t b_stride, int64_t num_rhs, VT* c, int64_t c_stride);                          \
+    b200_status b200_ell_advanced_spmv_##V##_##I(                                             \
+        b200_ctx* ctx, int64_t num_rows, int64_t num_cols, int64_t num_stored_per_row,        \
+        int64_t ell_stride, const IT* col_idxs, const VT* values, const VT* alpha,            \
+        const VT* b, int64_t b_stride, int64_t num_rhs, const VT* beta, VT* c,                \
+        int64_t c_stride);
+
+/* ---------------------------------------------------------------------------
+ * SELL-P (core/matrix/sellp_kernels.hpp:21-32; reference/matrix/sellp_kernels.cpp:27-100)
+ * element (row r of slice s, i) at (slice_sets[s] + i) * slice_size + r.
+ * ------------------------------------------------------------------------- */
+#define B200_DECL_SELLP(V, VT, I, IT)                                                        \
+    b200_status b200_sellp_spmv_##V##_##I(                                                   \
+        b200_ctx* ctx, int64_t num_rows, int64_t num_cols, int64_t slice_size,               \
+        const uint64_t* slice_sets, const uint64_t* slice_lengths, const IT* col_idxs,       \
+        const VT* values, const VT* b, int64_t b_stride, int64_t num_rhs, VT* c,             \
+        int64_t c_stride);                                                                   \
+    b200_status b200_sellp_advanced_spmv_##V##_##I(                                          \
+        b200_ctx* ctx, int64_t num_rows, int64_t num_cols, int64_t slice_size,               \
+        const uint64_t* slice_sets, const uint64_t* slice_lengths, const IT* col_idxs,       \
+        const VT* values, const VT* alpha, const VT* b, int64_t b_stride, int64_t num_rhs,   \
+        const VT* beta, VT* c, int64_t c_stride);
+
+/* ---------------------------------------------------------------------------
+ * COO (core/matrix/coo_kernels.hpp:22-45; reference/matrix/coo_kernels.cpp:33-100)
+ *   spmv: c = A b;  advanced_spmv: c = alpha A b + beta c;
+ *   spmv2: c += A b;  advanced_spmv2: c += alpha A b.
+ * Entries must be sorted by row (the reference's invariant).  A row-sorted COO
+ * is a CSR whose row_ptrs have not been written down yet: the plan holds them
+ * (components::convert_idxs_to_ptrs, reference/components/
+ * format_conversion_kernels.cpp) plus the CSR row partition, so an apply streams
+ * 12 B/nnz instead of 16 and needs no atomics.  `plan` may be NULL (then the
+ * pointers are rebuilt on the stream for this call).
+ * Hybrid::apply = ell_spmv then coo_spmv2 (core/matrix/hybrid.cpp:175-201).
+ * ------------------------------------------------------------------------- */
+#define B200_DECL_COO(V, VT, I, IT)                                                          \
+    b200_status b200_coo_plan_create_##V##_##I(b200_ctx* ctx, int64_t num_rows, int64_t nnz, \
+                                               const IT* row_idxs, b200_coo_plan** out);     \
+    b200_status b200_coo_spmv_##V##_##I(                                                     \
+        b200_ctx* ctx, const b200_coo_plan* plan, int64_t num_rows, int64_t num_cols,        \
+        int64_t nnz, const IT* row_idxs, const IT* col_idxs, const VT* values, const VT* b,  \
+        int64_t b_stride, int64_t num_rhs, VT* c, int64_t c_stride);                         \
+    b200_status b200_coo_advanced_spmv_##V##_##I(                                            \
+        b200_ctx* ctx, const b200_coo_plan* plan, int64_t num_rows, int64_t num_cols,        \
+        int64_t nnz, const IT* row_idxs, const IT* col_idxs, const VT* values,               \
+        const VT* alpha, const VT* b, int64_t b_stride, int64_t num_rhs, const VT* beta,     \
+        VT* c, int64_t c_stride);                                                            \
+    b200_status b200_coo_spmv2_##V##_##I(                                                    \
+        b200_ctx* ctx, const b200_coo_plan* plan, int64_t num_rows, int64_t num_cols,        \
+        int64_t nnz, const IT* row_idxs, const IT* col_idxs, const VT* values, const VT* b,  \
+        int64_t b_stride, int64_t num_rhs, VT* c, int64_t c_stride);                         \
+    b200_status b200_coo_advanced_spmv2_##V##_##I(                                           \
+        b200_ctx* ctx, const b200_coo_plan* plan, int64_t num_rows, int64_t num_cols,        \
+        int64_t nnz, const IT* row_idxs, const IT* col_idxs, const VT* values,               \
+        const VT* alpha, const VT* b, int64_t b_stride, int64_t num_rhs, VT* c,              \
+        int64_t c_stride);
+void b200_coo_plan_destroy(b200_coo_plan* plan);
+
+/* ---------------------------------------------------------------------------
+ * Block-Jacobi apply (core/preconditioner/jacobi_kernels.hpp:47-74;
+ * reference/preconditioner/jacobi_kernels.cpp:419-520).  Inverted blocks in
+ * block_interleaved_storage_scheme (include/ginkgo/core/preconditioner/
+ * jacobi.hpp:37-141): element (r,c) of block k at
+ *   group_offset*(k >> group_power) + block_offset*(k & (2^group_power-1))
+ *   + r + c*(block_offset << group_power).
+ * Only full-precision storage (block_precisions == NULL in the reference).
+ * ------------------------------------------------------------------------- */
+#define B200_DECL_JACOBI_BLOCK(V, VT, I, IT)                                                  \
+    b200_status b200_jacobi_simple_apply_##V##_##I(                                           \
+        b200_ctx* ctx, int64_t num_blocks, int32_t max_block_size, int64_t block_offset,      \
+        int64_t group_offset, int32_t group_power, const IT* block_pointers,                  \
+        const VT* blocks, const VT* b, int64_t b_stride, int64_t num_rhs, VT* x,              \
+        int64_t x_stride);                                                                    \
+    b200_status b200_jacobi_apply_##V##_##I(                                                  \
+        b200_ctx* ctx, int64_t num_blocks, int32_t max_block_size, int64_t block_offset,      \
+        int64_t group_offset, int32_t group_power, const IT* block_pointers,                  \
+        const VT* blocks, const VT* alpha, const VT* b, int64_t b_stride, int64_t num_rhs,    \
+        const VT* beta, VT* x, int64_t x_stride);
+
+/* ---------------------------------------------------------------------------
+ * Dense BLAS-1 (core/matrix/dense_kernels.hpp:34-135;
+ * reference/matrix/dense_kernels.cpp:95-437).  `result` is a 1 x cols device
+ * row.  alpha is 1x1 (alpha_cols == 1) or 1 x cols (alpha_cols == cols).
+ * Reductions are deterministic (fixed tree, no floating-point atomics).
+ *
+ * CG (core/solver/cg_kernels.hpp:25-50; reference/solver/cg_kernels.cpp:24-115)
+ * BiCGStab (core/solver/bicgstab_kernels.hpp:25-74;
+ *           reference/solver/bicgstab_kernels.cpp:25-190)
+ * GMRES (core/solver/common_gmres_kernels.hpp:23-48, gmres_kernels.hpp:23-46;
+ *        reference/solver/common_gmres_kernels.cpp:112-195, gmres_kernels.cpp:27-100)
+ * Stopping criteria (core/stop/residual_norm_kernels.hpp:21-50;
+ *        reference/stop/residual_norm_kernels.cpp:27-92)
+ * Scalar Jacobi (core/preconditioner/jacobi_kernels.hpp:42-81;
+ *        reference/preconditioner/jacobi_kernels.cpp:522-592)
+ * ------------------------------------------------------------------------- */
+#define B200_DECL_VALUE(V, VT)                                                                \
+    b200_status b200_dense_compute_dot_##V(b200_ctx* ctx, int64_t rows, int64_t cols,         \
+                                           const VT* x, int64_t x_stride, const VT* y,        \
+                                           int64_t y_stride, VT* result);                     \
+    b200_status b200_dense_compute_conj_dot_##V(b200_ctx* ctx, int64_t rows, int64_t cols,    \
+                                                const VT* x, int64_t x_stride, const VT* y,   \
+                                                int64_t y_stride, VT* result);                \
+    b200_status b200_dense_compute_norm2_##V(b200_ctx* ctx, int64_t rows, int64_t cols,       \
+                                             const VT* x, int64_t x_stride, VT* result);      \
+    b200_status b200_dense_compute_squared_norm2_##V(b200_ctx* ctx, int64_t rows,             \
+                                                     int64_t cols, const VT* x,               \
+                                                     int64_t x_stride, VT* result);           \
+    b200_status b200_dense_add_scaled_##V(b200_ctx* ctx, int64_t rows, int64_t cols,          \
+                                          const VT* alpha, int64_t alpha_cols, const VT* x,   \
+                                          int64_t x_stride, VT* y, int64_t y_stride);         \
+    b200_status b200_dense_sub_scaled_##V(b200_ctx* ctx, int64_t rows, int64_t cols,          \
+                                          const VT* alpha, int64_t alpha_cols, const VT* x,   \
+                                          int64_t x_stride, VT* y, int64_t y_stride);         \
+    b200_status b200_dense_scale_##V(b200_ctx* ctx, int64_t rows, int64_t cols,               \
+                                     const VT* alpha, int64_t alpha_cols, VT* x,              \
+                                     int64_t x_stride);                                       \
+    b200_status b200_dense_inv_scale_##V(b200_ctx* ctx, int64_t rows, int64_t cols,           \
+                                         const VT* alpha, int64_t alpha_cols, VT* x,          \
+                                         int64_t x_stride);                                   \
+    b200_status b200_dense_copy_##V(b200_ctx* ctx, int64_t rows, int64_t cols, const VT* in,  \
+                                    int64_t in_stride, VT* out, int64_t out_stride);          \
+    b200_status b200_dense_fill_##V(b200_ctx* ctx, int64_t rows, int64_t cols, VT* x,         \
+                                    int64_t x_stride, VT value);                              \
+                                                                                              \
+    b200_status b200_cg_initialize_##V(                                                       \
+        b200_ctx* ctx, int64_t rows, int64_t cols, const VT* b, int64_t b_stride, VT* r,      \
+        int64_t r_stride, VT* z, int64_t z_stride, VT* p, int64_t p_stride, VT* q,            \
+        int64_t q_stride, VT* prev_rho, VT* rho, uint8_t* stop_status);                       \
+    b200_status b200_cg_step_1_##V(b200_ctx* ctx, int64_t rows, int64_t cols, VT* p,          \
+                                   int64_t p_stride, const VT* z, int64_t z_stride,           \
+                                   const VT* rho, const VT* prev_rho,                         \
+                                   const uint8_t* stop_status);                               \
+    b200_status b200_cg_step_2_##V(b200_ctx* ctx, int64_t rows, int64_t cols, VT* x,          \
+                                   int64_t x_stride, VT* r, int64_t r_stride, const VT* p,    \
+                                   int64_t p_stride, const VT* q, int64_t q_stride,           \
+                                   const VT* beta, const VT* rho,                             \
+                                   const uint8_t* stop_status);                               \
+                                                                                              \
+    b200_status b200_bicgstab_initialize_##V(                                                 \
+        b200_ctx* ctx, int64_t rows, int64_t cols, const VT* b, int64_t b_stride, VT* r,      \
+        int64_t r_stride, VT* rr, int64_t rr_stride, VT* y, int64_t y_stride, VT* s,          \
+        int64_t s_stride, VT* t, int64_t t_stride, VT* z, int64_t z_stride, VT* v,            \
+        int64_t v_stride, VT* p, int64_t p_stride, VT* prev_rho, VT* rho, VT* alpha,          \
+        VT* beta, VT* gamma, VT* omega, uint8_t* stop_status);                                \
+    b200_status b200_bicgstab_step_1_##V(                                                     \
+        b200_ctx* ctx, int64_t rows, int64_t cols, const VT* r, int64_t r_stride, VT* p,      \
+        int64_t p_stride, const VT* v, int64_t v_stride, const VT* rho, const VT* prev_rho,   \
+        const VT* alpha, const VT* omega, const uint8_t* stop_status);                        \
+    b200_status b200_bicgstab_step_2_##V(                                                     \
+        b200_ctx* ctx, int64_t rows, int64_t cols, const VT* r, int64_t r_stride, VT* s,      \
+        int64_t s_stride, const VT* v, int64_t v_stride, const VT* rho, VT* alpha,            \
+        const VT* beta, const uint8_t* stop_status);                                          \
+    b200_status b200_bicgstab_step_3_##V(                                                     \
+        b200_ctx* ctx, int64_t rows, int64_t cols, VT* x, int64_t x_stride, VT* r,            \
+        int64_t r_stride, const VT* s, int64_t s_stride, const VT* t, int64_t t_stride,       \
+        const VT* y, int64_t y_stride, const VT* z, int64_t z_stride, const VT* alpha,        \
+        const VT* beta, const VT* gamma, VT* omega, const uint8_t* stop_status);              \
+    b200_status b200_bicgstab_finalize_##V(b200_ctx* ctx, int64_t rows, int64_t cols, VT* x,  \
+                                           int64_t x_stride, const VT* y, int64_t y_stride,   \
+                                           const VT* alpha, uint8_t* stop_status);            \
+                                                                                              \
+    /* GMRES: krylov_bases is ((krylov_dim+1)*rows) x cols; hessenberg_iter is   */           \
+    /* (iter+2) x cols with stride hess_stride; givens are krylov_dim x cols.     */           \
+    b200_status b200_common_gmres_initialize_##V(                                             \
+        b200_ctx* ctx, int64_t rows, int64_t cols, int64_t krylov_dim, const VT* b,           \
+        int64_t b_stride, VT* residual, int64_t residual_stride, VT* givens_sin,              \
+        int64_t sin_stride, VT* givens_cos, int64_t cos_stride, uint8_t* stop_status);        \
+    b200_status b200_common_gmres_hessenberg_qr_##V(                                          \
+        b200_ctx* ctx, int64_t cols, VT* givens_sin, int64_t sin_stride, VT* givens_cos,      \
+        int64_t cos_stride, VT* residual_norm, VT* residual_norm_collection,                  \
+        int64_t rnc_stride, VT* hessenberg_iter, int64_t hess_stride, int64_t iter,           \
+        uint64_t* final_iter_nums, const uint8_t* stop_status);                               \
+    b200_status b200_common_gmres_solve_krylov_##V(                                           \
+        b200_ctx* ctx, int64_t cols, const VT* residual_norm_collection, int64_t rnc_stride,  \
+        const VT* hessenberg, int64_t hess_stride, VT* y, int64_t y_stride,                   \
+        const uint64_t* final_iter_nums, const uint8_t* stop_status);                         \
+    b200_status b200_gmres_restart_##V(                                                       \
+        b200_ctx* ctx, int64_t rows, int64_t cols, const VT* residual,                        \
+        int64_t residual_stride, const VT* residual_norm, VT* residual_norm_collection,       \
+        VT* krylov_bases, int64_t krylov_stride, uint64_t* final_iter_nums);                  \
+    b200_status b200_gmres_multi_axpy_##V(                                                    \
+        b200_ctx* ctx, int64_t rows, int64_t cols, const VT* krylov_bases,                    \
+        int64_t krylov_stride, const VT* y, int64_t y_stride, VT* before_preconditioner,      \
+        int64_t bp_stride, const uint64_t* final_iter_nums, uint8_t* stop_status);            \
+    b200_status b200_gmres_multi_dot_##V(                                                     \
+        b200_ctx* ctx, int64_t rows, int64_t cols, int64_t num_bases,                         \
+        const VT* krylov_bases, int64_t krylov_stride, const VT* next_krylov,                 \
+        int64_t next_stride, VT* hessenberg_col, int64_t hess_stride);                        \
+                                                                                              \
+    /* blocking: returns the two host bools of the reference signature */                     \
+    b200_status b200_residual_norm_##V(                                                       \
+        b200_ctx* ctx, int64_t cols, const VT* tau, const VT* orig_tau, VT rel_residual_goal, \
+        uint8_t stopping_id, int32_t set_finalized, uint8_t* stop_status,                     \
+        uint8_t* device_storage, int32_t* all_converged, int32_t* one_changed);               \
+    b200_status b200_implicit_residual_norm_##V(                                              \
+        b200_ctx* ctx, int64_t cols, const VT* tau, const VT* orig_tau, VT rel_residual_goal, \
+        uint8_t stopping_id, int32_t set_finalized, uint8_t* stop_status,                     \
+        uint8_t* device_storage, int32_t* all_converged, int32_t* one_changed);               \
+                                                                                              \
+    b200_status b200_jacobi_invert_diagonal_##V(b200_ctx* ctx, int64_t n, const VT* diag,     \
+                                                VT* inv_diag);                                \
+    b200_status b200_jacobi_simple_scalar_apply_##V(                                          \
+        b200_ctx* ctx, int64_t rows, int64_t cols, const VT* inv_diag, const VT* b,           \
+        int64_t b_stride, VT* x, int64_t x_stride);                                           \
+    b200_status b200_jacobi_scalar_apply_##V(                                                 \
+        b200_ctx* ctx, int64_t rows, int64_t cols, const VT* inv_diag, const VT* alpha,       \
+        const VT* b, int64_t b_stride, const VT* beta, VT* x, int64_t x_stride);
+
+/* set_all_statuses (core/stop/criterion_kernels.hpp:21; used by stop::Iteration) */
+b200_status b200_set_all_statuses(b200_ctx* ctx, int64_t cols, uint8_t stopping_id,
+                                  int32_t set_finalized, uint8_t* stop_status);
+
+#define B200_DECL_VALUE_INDEX(V, VT, I, IT) \
+    B200_DECL_CSR(V, VT, I, IT)             \
+    B200_DECL_ELL(V, VT, I, IT)             \
+    B200_DECL_SELLP(V, VT, I, IT)           \
+    B200_DECL_COO(V, VT, I, IT)             \
+    B200_DECL_JACOBI_BLOCK(V, VT, I, IT)
+
+B200_DECL_VALUE(f64, double)
+B200_DECL_VALUE(f32, float)
+B200_DECL_VALUE_INDEX(f64, double, i32, int32_t)
+B200_DECL_VALUE_INDEX(f64, double, i64, int64_t)
+B200_DECL_VALUE_INDEX(f32, float, i32, int32_t)
+B200_DECL_VALUE_INDEX(f32, float, i64, int64_t)
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GINKGO_B200_H_ */

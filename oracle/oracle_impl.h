@@ -1,0 +1,608 @@
+/*
+ * oracle_impl.h -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+ *
+ * CPU restatement of the reference executor's arithmetic for the SpMV + Krylov
+ * hot path, in plain C, one function per reference kernel, each citing the
+ * reference file:line it follows (paths relative to /root/reference).  Included
+ * once per value type from oracle.c with
+ *     #define V double / float,  #define VS f64 / f32
+ * and, for the index-typed part, I / IS.  Parity is PINNED: tests/
+ * test_oracle_golden.py checks every function against the literal known-answer
+ * vectors of the reference's own reference/test/ suites, and
+ * tests/test_oracle_vs_ref.py against the reference itself (oracle/_ref).
+ *
+ * Compiled with -ffp-contract=off: the reference build (x86-64 baseline) has no
+ * FMA contraction, every product is rounded before it is added.
+ */
+
+#define CAT_(a, b) a##_##b
+#define CAT(a, b) CAT_(a, b)
+#define FN(name) CAT(CAT(orc, name), VS)
+#define FNI(name) CAT(CAT(CAT(orc, name), VS), IS)
+
+#ifndef ORC_VALUE_PART_DONE
+/* ===================== value-typed kernels (no index type) ================= */
+
+/* reference/matrix/dense_kernels.cpp:262-279 (compute_dot), :295-311 (conj_dot) */
+void FN(dense_compute_dot)(int64_t rows, int64_t cols, const V* x, int64_t xs, const V* y,
+                           int64_t ys, V* result)
+{
+    for (int64_t j = 0; j < cols; ++j) result[j] = 0;
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) result[j] += x[i * xs + j] * y[i * ys + j];
+}
+
+void FN(dense_compute_conj_dot)(int64_t rows, int64_t cols, const V* x, int64_t xs, const V* y,
+                                int64_t ys, V* result)
+{
+    FN(dense_compute_dot)(rows, cols, x, xs, y, ys, result); /* real types: conj == identity */
+}
+
+/* reference/matrix/dense_kernels.cpp:328-346 (norm2), :420-435 (squared_norm2) */
+void FN(dense_compute_squared_norm2)(int64_t rows, int64_t cols, const V* x, int64_t xs, V* result)
+{
+    for (int64_t j = 0; j < cols; ++j) result[j] = 0;
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) result[j] += x[i * xs + j] * x[i * xs + j];
+}
+void FN(dense_compute_norm2)(int64_t rows, int64_t cols, const V* x, int64_t xs, V* result)
+{
+    FN(dense_compute_squared_norm2)(rows, cols, x, xs, result);
+    for (int64_t j = 0; j < cols; ++j) result[j] = SQRT(result[j]);
+}
+
+/* reference/matrix/dense_kernels.cpp:127-150 */
+void FN(dense_scale)(int64_t rows, int64_t cols, const V* alpha, int64_t alpha_cols, V* x,
+                     int64_t xs)
+{
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) {
+            if (alpha_cols == 1) {
+                if (alpha[0] == 0)
+                    x[i * xs + j] = 0;
+                else
+                    x[i * xs + j] *= alpha[0];
+            } else {
+                x[i * xs + j] *= alpha[j];
+            }
+        }
+}
+/* reference/matrix/dense_kernels.cpp:153-172 */
+void FN(dense_inv_scale)(int64_t rows, int64_t cols, const V* alpha, int64_t alpha_cols, V* x,
+                         int64_t xs)
+{
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) x[i * xs + j] /= alpha[alpha_cols == 1 ? 0 : j];
+}
+/* reference/matrix/dense_kernels.cpp:177-198 */
+void FN(dense_add_scaled)(int64_t rows, int64_t cols, const V* alpha, int64_t alpha_cols,
+                          const V* x, int64_t xs, V* y, int64_t ys)
+{
+    if (alpha_cols == 1 && alpha[0] == 0) return;
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j)
+            y[i * ys + j] += alpha[alpha_cols == 1 ? 0 : j] * x[i * xs + j];
+}
+/* reference/matrix/dense_kernels.cpp:203-224 */
+void FN(dense_sub_scaled)(int64_t rows, int64_t cols, const V* alpha, int64_t alpha_cols,
+                          const V* x, int64_t xs, V* y, int64_t ys)
+{
+    if (alpha_cols == 1 && alpha[0] == 0) return;
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j)
+            y[i * ys + j] -= alpha[alpha_cols == 1 ? 0 : j] * x[i * xs + j];
+}
+
+/* ---- stopping_status helpers: include/ginkgo/core/stop/stopping_status.hpp ---- */
+#ifndef ORC_STATUS_HELPERS
+#define ORC_STATUS_HELPERS
+static int st_has_stopped(uint8_t s) { return (s & 0x3f) != 0; }
+static int st_is_finalized(uint8_t s) { return (s & 0x40) != 0; }
+static uint8_t st_converge(uint8_t s, uint8_t id, int set_finalized)
+{
+    if (!st_has_stopped(s)) {
+        s |= 0x80 | (id & 0x3f);
+        if (set_finalized) s |= 0x40;
+    }
+    return s;
+}
+static uint8_t st_stop(uint8_t s, uint8_t id, int set_finalized)
+{
+    if (!st_has_stopped(s)) {
+        s |= (id & 0x3f);
+        if (set_finalized) s |= 0x40;
+    }
+    return s;
+}
+static uint8_t st_finalize(uint8_t s)
+{
+    if (st_has_stopped(s)) s |= 0x40;
+    return s;
+}
+/* reference/stop/criterion_kernels.cpp (set_all_statuses): stop(id, set_finalized) */
+void orc_set_all_statuses(int64_t cols, uint8_t id, int32_t set_finalized, uint8_t* stop)
+{
+    for (int64_t i = 0; i < cols; ++i) stop[i] = st_stop(stop[i], id, set_finalized);
+}
+
+#endif
+
+/* reference/solver/cg_kernels.cpp:24-45 */
+void FN(cg_initialize)(int64_t rows, int64_t cols, const V* b, int64_t bs, V* r, int64_t rs, V* z,
+                       int64_t zs, V* p, int64_t ps, V* q, int64_t qs, V* prev_rho, V* rho,
+                       uint8_t* stop)
+{
+    for (int64_t j = 0; j < cols; ++j) {
+        rho[j] = 0;
+        prev_rho[j] = 1;
+        stop[j] = 0;
+    }
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) {
+            r[i * rs + j] = b[i * bs + j];
+            z[i * zs + j] = p[i * ps + j] = q[i * qs + j] = 0;
+        }
+}
+/* reference/solver/cg_kernels.cpp:50-72 */
+void FN(cg_step_1)(int64_t rows, int64_t cols, V* p, int64_t ps, const V* z, int64_t zs,
+                   const V* rho, const V* prev_rho, const uint8_t* stop)
+{
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) {
+            if (st_has_stopped(stop[j])) continue;
+            if (prev_rho[j] == 0) {
+                p[i * ps + j] = z[i * zs + j];
+            } else {
+                V tmp = rho[j] / prev_rho[j];
+                p[i * ps + j] = z[i * zs + j] + tmp * p[i * ps + j];
+            }
+        }
+}
+/* reference/solver/cg_kernels.cpp:77-100 */
+void FN(cg_step_2)(int64_t rows, int64_t cols, V* x, int64_t xs, V* r, int64_t rs, const V* p,
+                   int64_t ps, const V* q, int64_t qs, const V* beta, const V* rho,
+                   const uint8_t* stop)
+{
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) {
+            if (st_has_stopped(stop[j])) continue;
+            if (beta[j] != 0) {
+                V tmp = rho[j] / beta[j];
+                x[i * xs + j] += tmp * p[i * ps + j];
+                r[i * rs + j] -= tmp * q[i * qs + j];
+            }
+        }
+}
+
+/* reference/solver/bicgstab_kernels.cpp:25-60 */
+void FN(bicgstab_initialize)(int64_t rows, int64_t cols, const V* b, int64_t bs, V* r, int64_t rs,
+                             V* rr, int64_t rrs, V* y, int64_t ys, V* s, int64_t ss, V* t,
+                             int64_t ts, V* z, int64_t zs, V* v, int64_t vs, V* p, int64_t ps,
+                             V* prev_rho, V* rho, V* alpha, V* beta, V* gamma, V* omega,
+                             uint8_t* stop)
+{
+    for (int64_t j = 0; j < cols; ++j) {
+        rho[j] = prev_rho[j] = alpha[j] = beta[j] = gamma[j] = omega[j] = 1;
+        stop[j] = 0;
+    }
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) {
+            r[i * rs + j] = b[i * bs + j];
+            rr[i * rrs + j] = z[i * zs + j] = v[i * vs + j] = s[i * ss + j] = t[i * ts + j] =
+                y[i * ys + j] = p[i * ps + j] = 0;
+        }
+}
+/* reference/solver/bicgstab_kernels.cpp:65-92 */
+void FN(bicgstab_step_1)(int64_t rows, int64_t cols, const V* r, int64_t rs, V* p, int64_t ps,
+                         const V* v, int64_t vs, const V* rho, const V* prev_rho, const V* alpha,
+                         const V* omega, const uint8_t* stop)
+{
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) {
+            if (st_has_stopped(stop[j])) continue;
+            if (prev_rho[j] * omega[j] != 0) {
+                V tmp = rho[j] / prev_rho[j] * alpha[j] / omega[j];
+                p[i * ps + j] = r[i * rs + j] + tmp * (p[i * ps + j] - omega[j] * v[i * vs + j]);
+            } else {
+                p[i * ps + j] = r[i * rs + j];
+            }
+        }
+}
+/* reference/solver/bicgstab_kernels.cpp:97-121 */
+void FN(bicgstab_step_2)(int64_t rows, int64_t cols, const V* r, int64_t rs, V* s, int64_t ss,
+                         const V* v, int64_t vs, const V* rho, V* alpha, const V* beta,
+                         const uint8_t* stop)
+{
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) {
+            if (st_has_stopped(stop[j])) continue;
+            if (beta[j] != 0) {
+                alpha[j] = rho[j] / beta[j];
+                s[i * ss + j] = r[i * rs + j] - alpha[j] * v[i * vs + j];
+            } else {
+                alpha[j] = 0;
+                s[i * ss + j] = r[i * rs + j];
+            }
+        }
+}
+/* reference/solver/bicgstab_kernels.cpp:126-158 */
+void FN(bicgstab_step_3)(int64_t rows, int64_t cols, V* x, int64_t xs, V* r, int64_t rs,
+                         const V* s, int64_t ss, const V* t, int64_t ts, const V* y, int64_t ys,
+                         const V* z, int64_t zs, const V* alpha, const V* beta, const V* gamma,
+                         V* omega, const uint8_t* stop)
+{
+    for (int64_t j = 0; j < cols; ++j) {
+        if (st_has_stopped(stop[j])) continue;
+        omega[j] = beta[j] != 0 ? gamma[j] / beta[j] : 0;
+    }
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) {
+            if (st_has_stopped(stop[j])) continue;
+            x[i * xs + j] += alpha[j] * y[i * ys + j] + omega[j] * z[i * zs + j];
+            r[i * rs + j] = s[i * ss + j] - omega[j] * t[i * ts + j];
+        }
+}
+/* reference/solver/bicgstab_kernels.cpp:163-178 */
+void FN(bicgstab_finalize)(int64_t rows, int64_t cols, V* x, int64_t xs, const V* y, int64_t ys,
+                           const V* alpha, uint8_t* stop)
+{
+    for (int64_t j = 0; j < cols; ++j)
+        if (st_has_stopped(stop[j]) && !st_is_finalized(stop[j]))
+            for (int64_t i = 0; i < rows; ++i) {
+                x[i * xs + j] += alpha[j] * y[i * ys + j];
+                stop[j] = st_finalize(stop[j]);
+            }
+}
+
+/* reference/solver/common_gmres_kernels.cpp:112-133 */
+void FN(common_gmres_initialize)(int64_t rows, int64_t cols, int64_t krylov_dim, const V* b,
+                                 int64_t bs, V* residual, int64_t rs, V* gsin, int64_t sins,
+                                 V* gcos, int64_t coss, uint8_t* stop)
+{
+    for (int64_t j = 0; j < cols; ++j) {
+        for (int64_t i = 0; i < rows; ++i) residual[i * rs + j] = b[i * bs + j];
+        for (int64_t i = 0; i < krylov_dim; ++i) gsin[i * sins + j] = gcos[i * coss + j] = 0;
+        stop[j] = 0;
+    }
+}
+/* reference/solver/common_gmres_kernels.cpp:27-107 (givens_rotation, calculate_sin_and_cos,
+ * calculate_next_residual_norm) and :138-157 (hessenberg_qr) */
+void FN(common_gmres_hessenberg_qr)(int64_t cols, V* gsin, int64_t sins, V* gcos, int64_t coss,
+                                    V* residual_norm, V* rnc, int64_t rncs, V* hess, int64_t hs,
+                                    int64_t iter, uint64_t* final_iter_nums, const uint8_t* stop)
+{
+    for (int64_t i = 0; i < cols; ++i)
+        if (!st_has_stopped(stop[i])) final_iter_nums[i]++;
+    for (int64_t i = 0; i < cols; ++i) {
+        if (st_has_stopped(stop[i])) continue;
+        for (int64_t j = 0; j < iter; ++j) {
+            V temp = gcos[j * coss + i] * hess[j * hs + i] + gsin[j * sins + i] * hess[(j + 1) * hs + i];
+            hess[(j + 1) * hs + i] =
+                -gsin[j * sins + i] * hess[j * hs + i] + gcos[j * coss + i] * hess[(j + 1) * hs + i];
+            hess[j * hs + i] = temp;
+        }
+        if (hess[iter * hs + i] == 0) {
+            gcos[iter * coss + i] = 0;
+            gsin[iter * sins + i] = 1;
+        } else {
+            V this_hess = hess[iter * hs + i];
+            V next_hess = hess[(iter + 1) * hs + i];
+            V scale = FABS(this_hess) + FABS(next_hess);
+            V hyp = scale * SQRT(FABS(this_hess / scale) * FABS(this_hess / scale) +
+                                 FABS(next_hess / scale) * FABS(next_hess / scale));
+            gcos[iter * coss + i] = this_hess / hyp;
+            gsin[iter * sins + i] = next_hess / hyp;
+        }
+        hess[iter * hs + i] =
+            gcos[iter * coss + i] * hess[iter * hs + i] + gsin[iter * sins + i] * hess[(iter + 1) * hs + i];
+        hess[(iter + 1) * hs + i] = 0;
+    }
+    for (int64_t i = 0; i < cols; ++i) {
+        if (st_has_stopped(stop[i])) continue;
+        rnc[(iter + 1) * rncs + i] = -gsin[iter * sins + i] * rnc[iter * rncs + i];
+        rnc[iter * rncs + i] = gcos[iter * coss + i] * rnc[iter * rncs + i];
+        residual_norm[i] = FABS(rnc[(iter + 1) * rncs + i]);
+    }
+}
+/* reference/solver/common_gmres_kernels.cpp:162-188; H(i,j) at hess[j*hs + i*cols + k] */
+void FN(common_gmres_solve_krylov)(int64_t cols, const V* rnc, int64_t rncs, const V* hess,
+                                   int64_t hs, V* y, int64_t ys, const uint64_t* final_iter_nums,
+                                   const uint8_t* stop)
+{
+    for (int64_t k = 0; k < cols; ++k) {
+        if (st_is_finalized(stop[k])) continue;
+        for (int64_t i = (int64_t)final_iter_nums[k] - 1; i >= 0; --i) {
+            V temp = rnc[i * rncs + k];
+            for (int64_t j = i + 1; j < (int64_t)final_iter_nums[k]; ++j)
+                temp -= hess[j * hs + i * cols + k] * y[j * ys + k];
+            y[i * ys + k] = temp / hess[i * hs + i * cols + k];
+        }
+    }
+}
+/* reference/solver/gmres_kernels.cpp:27-43 */
+void FN(gmres_restart)(int64_t rows, int64_t cols, const V* residual, int64_t rs,
+                       const V* residual_norm, V* rnc, V* krylov, int64_t ks,
+                       uint64_t* final_iter_nums)
+{
+    for (int64_t j = 0; j < cols; ++j) {
+        rnc[j] = residual_norm[j];
+        for (int64_t i = 0; i < rows; ++i) krylov[i * ks + j] = residual[i * rs + j] / residual_norm[j];
+        final_iter_nums[j] = 0;
+    }
+}
+/* reference/solver/gmres_kernels.cpp:48-74 */
+void FN(gmres_multi_axpy)(int64_t rows, int64_t cols, const V* krylov, int64_t ks, const V* y,
+                          int64_t ys, V* out, int64_t os, const uint64_t* final_iter_nums,
+                          uint8_t* stop)
+{
+    for (int64_t k = 0; k < cols; ++k) {
+        if (st_is_finalized(stop[k])) continue;
+        for (int64_t i = 0; i < rows; ++i) {
+            out[i * os + k] = 0;
+            for (int64_t j = 0; j < (int64_t)final_iter_nums[k]; ++j)
+                out[i * os + k] += krylov[(i + j * rows) * ks + k] * y[j * ys + k];
+        }
+        if (st_has_stopped(stop[k])) stop[k] = st_finalize(stop[k]);
+    }
+}
+/* reference/solver/gmres_kernels.cpp:79-98 */
+void FN(gmres_multi_dot)(int64_t rows, int64_t cols, int64_t num_bases, const V* krylov,
+                         int64_t ks, const V* next_krylov, int64_t ns, V* hcol, int64_t hs)
+{
+    for (int64_t i = 0; i < num_bases; ++i)
+        for (int64_t k = 0; k < cols; ++k) {
+            hcol[i * hs + k] = 0;
+            for (int64_t j = 0; j < rows; ++j)
+                hcol[i * hs + k] += krylov[(i * rows + j) * ks + k] * next_krylov[j * ns + k];
+        }
+}
+
+/* reference/stop/residual_norm_kernels.cpp:27-55 (implicit: :68-92) */
+void FN(residual_norm)(int64_t cols, const V* tau, const V* orig_tau, V goal, uint8_t id,
+                       int32_t set_finalized, uint8_t* stop, uint8_t* device_storage,
+                       int32_t* all_converged,
+                       int32_t* one_changed)
+{
+    *all_converged = 1;
+    *one_changed = 0;
+    for (int64_t i = 0; i < cols; ++i)
+        if (tau[i] <= goal * orig_tau[i]) {
+            stop[i] = st_converge(stop[i], id, set_finalized);
+            *one_changed = 1;
+        }
+    for (int64_t i = 0; i < cols; ++i)
+        if (!st_has_stopped(stop[i])) {
+            *all_converged = 0;
+            break;
+        }
+}
+void FN(implicit_residual_norm)(int64_t cols, const V* tau, const V* orig_tau, V goal, uint8_t id,
+                                int32_t set_finalized, uint8_t* stop, uint8_t* device_storage,
+                                int32_t* all_converged,
+                                int32_t* one_changed)
+{
+    *all_converged = 1;
+    *one_changed = 0;
+    for (int64_t i = 0; i < cols; ++i)
+        if (SQRT(FABS(tau[i])) <= goal * orig_tau[i]) {
+            stop[i] = st_converge(stop[i], id, set_finalized);
+            *one_changed = 1;
+        }
+    for (int64_t i = 0; i < cols; ++i)
+        if (!st_has_stopped(stop[i])) {
+            *all_converged = 0;
+            break;
+        }
+}
+
+/* reference/preconditioner/jacobi_kernels.cpp:577-592 */
+void FN(jacobi_invert_diagonal)(int64_t n, const V* diag, V* inv_diag)
+{
+    for (int64_t i = 0; i < n; ++i) {
+        V d = diag[i] == 0 ? (V)1 : diag[i];
+        inv_diag[i] = (V)1 / d;
+    }
+}
+/* reference/preconditioner/jacobi_kernels.cpp:541-555 */
+void FN(jacobi_simple_scalar_apply)(int64_t rows, int64_t cols, const V* inv_diag, const V* b,
+                                    int64_t bs, V* x, int64_t xs)
+{
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) x[i * xs + j] = b[i * bs + j] * inv_diag[i];
+}
+/* reference/preconditioner/jacobi_kernels.cpp:522-537 */
+void FN(jacobi_scalar_apply)(int64_t rows, int64_t cols, const V* inv_diag, const V* alpha,
+                             const V* b, int64_t bs, const V* beta, V* x, int64_t xs)
+{
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j)
+            x[i * xs + j] = beta[0] * x[i * xs + j] + alpha[0] * b[i * bs + j] * inv_diag[i];
+}
+
+#else /* ===================== (value, index)-typed kernels ===================== */
+
+/* reference/matrix/csr_kernels.cpp:47-78 */
+void FNI(csr_spmv)(int64_t num_rows, int64_t num_cols, int64_t nnz, const I* row_ptrs, const I* col_idxs, const V* values,
+                   const V* b, int64_t bs, int64_t num_rhs, V* c, int64_t cs)
+{
+    for (int64_t row = 0; row < num_rows; ++row)
+        for (int64_t j = 0; j < num_rhs; ++j) {
+            V sum = 0;
+            for (int64_t k = row_ptrs[row]; k < (int64_t)row_ptrs[row + 1]; ++k)
+                sum += values[k] * b[(int64_t)col_idxs[k] * bs + j];
+            c[row * cs + j] = sum;
+        }
+}
+/* reference/matrix/csr_kernels.cpp:84-118 */
+void FNI(csr_advanced_spmv)(int64_t num_rows, int64_t num_cols, int64_t nnz,
+                            const I* row_ptrs, const I* col_idxs,
+                            const V* values, const V* alpha, const V* b, int64_t bs,
+                            int64_t num_rhs, const V* beta, V* c, int64_t cs)
+{
+    const V valpha = alpha[0], vbeta = beta[0];
+    for (int64_t row = 0; row < num_rows; ++row)
+        for (int64_t j = 0; j < num_rhs; ++j) {
+            V sum = vbeta == 0 ? (V)0 : c[row * cs + j] * vbeta;
+            for (int64_t k = row_ptrs[row]; k < (int64_t)row_ptrs[row + 1]; ++k)
+                sum += valpha * values[k] * b[(int64_t)col_idxs[k] * bs + j];
+            c[row * cs + j] = sum;
+        }
+}
+
+/* reference/matrix/ell_kernels.cpp:29-72 */
+void FNI(ell_spmv)(int64_t num_rows, int64_t num_cols, int64_t width, int64_t stride, const I* col_idxs,
+                   const V* values, const V* b, int64_t bs, int64_t num_rhs, V* c, int64_t cs)
+{
+    for (int64_t j = 0; j < num_rhs; ++j)
+        for (int64_t row = 0; row < num_rows; ++row) {
+            V result = 0;
+            for (int64_t i = 0; i < width; ++i) {
+                I col = col_idxs[row + i * stride];
+                if (col != (I)-1) result += values[row + i * stride] * b[(int64_t)col * bs + j];
+            }
+            c[row * cs + j] = result;
+        }
+}
+/* reference/matrix/ell_kernels.cpp:77-120 */
+void FNI(ell_advanced_spmv)(int64_t num_rows, int64_t num_cols, int64_t width, int64_t stride, const I* col_idxs,
+                            const V* values, const V* alpha, const V* b, int64_t bs,
+                            int64_t num_rhs, const V* beta, V* c, int64_t cs)
+{
+    const V a = alpha[0], bt = beta[0];
+    for (int64_t j = 0; j < num_rhs; ++j)
+        for (int64_t row = 0; row < num_rows; ++row) {
+            V result = bt == 0 ? (V)0 : bt * c[row * cs + j];
+            for (int64_t i = 0; i < width; ++i) {
+                I col = col_idxs[row + i * stride];
+                if (col != (I)-1)
+                    result += a * values[row + i * stride] * b[(int64_t)col * bs + j];
+            }
+            c[row * cs + j] = result;
+        }
+}
+
+/* reference/matrix/sellp_kernels.cpp:27-58 */
+void FNI(sellp_spmv)(int64_t num_rows, int64_t num_cols, int64_t slice_size, const uint64_t* slice_sets,
+                     const uint64_t* slice_lengths, const I* col_idxs, const V* values,
+                     const V* b, int64_t bs, int64_t num_rhs, V* c, int64_t cs)
+{
+    int64_t slice_num = (num_rows + slice_size - 1) / slice_size;
+    for (int64_t slice = 0; slice < slice_num; ++slice)
+        for (int64_t row = 0; row < slice_size; ++row) {
+            int64_t g = slice * slice_size + row;
+            if (g >= num_rows) break;
+            for (int64_t j = 0; j < num_rhs; ++j) c[g * cs + j] = 0;
+            for (uint64_t i = 0; i < slice_lengths[slice]; ++i) {
+                int64_t idx = (int64_t)(slice_sets[slice] + i) * slice_size + row;
+                I col = col_idxs[idx];
+                if (col != (I)-1)
+                    for (int64_t j = 0; j < num_rhs; ++j)
+                        c[g * cs + j] += values[idx] * b[(int64_t)col * bs + j];
+            }
+        }
+}
+/* reference/matrix/sellp_kernels.cpp:63-105 */
+void FNI(sellp_advanced_spmv)(int64_t num_rows, int64_t num_cols, int64_t slice_size, const uint64_t* slice_sets,
+                              const uint64_t* slice_lengths, const I* col_idxs, const V* values,
+                              const V* alpha, const V* b, int64_t bs, int64_t num_rhs,
+                              const V* beta, V* c, int64_t cs)
+{
+    const V va = alpha[0], vb = beta[0];
+    int64_t slice_num = (num_rows + slice_size - 1) / slice_size;
+    for (int64_t slice = 0; slice < slice_num; ++slice)
+        for (int64_t row = 0; row < slice_size; ++row) {
+            int64_t g = slice * slice_size + row;
+            if (g >= num_rows) break;
+            for (int64_t j = 0; j < num_rhs; ++j) {
+                if (vb != 0)
+                    c[g * cs + j] *= vb;
+                else
+                    c[g * cs + j] = 0;
+            }
+            for (uint64_t i = 0; i < slice_lengths[slice]; ++i) {
+                int64_t idx = (int64_t)(slice_sets[slice] + i) * slice_size + row;
+                I col = col_idxs[idx];
+                if (col != (I)-1)
+                    for (int64_t j = 0; j < num_rhs; ++j)
+                        c[g * cs + j] += va * values[idx] * b[(int64_t)col * bs + j];
+            }
+        }
+}
+
+/* reference/matrix/coo_kernels.cpp:59-74 (spmv2), :81-97 (advanced_spmv2),
+ * :33-40 (spmv = fill 0 + spmv2), :46-55 (advanced_spmv = scale(beta) + advanced_spmv2) */
+void FNI(coo_spmv2)(int64_t num_rows, int64_t num_cols, int64_t nnz, const I* row_idxs, const I* col_idxs, const V* values,
+                    const V* b, int64_t bs, int64_t num_rhs, V* c, int64_t cs)
+{
+    for (int64_t i = 0; i < nnz; ++i)
+        for (int64_t j = 0; j < num_rhs; ++j)
+            c[(int64_t)row_idxs[i] * cs + j] += values[i] * b[(int64_t)col_idxs[i] * bs + j];
+}
+void FNI(coo_advanced_spmv2)(int64_t num_rows, int64_t num_cols, int64_t nnz,
+                             const I* row_idxs, const I* col_idxs, const V* values,
+                             const V* alpha, const V* b, int64_t bs, int64_t num_rhs, V* c,
+                             int64_t cs)
+{
+    const V a = alpha[0];
+    for (int64_t i = 0; i < nnz; ++i)
+        for (int64_t j = 0; j < num_rhs; ++j)
+            c[(int64_t)row_idxs[i] * cs + j] += a * values[i] * b[(int64_t)col_idxs[i] * bs + j];
+}
+void FNI(coo_spmv)(int64_t num_rows, int64_t num_cols, int64_t nnz, const I* row_idxs, const I* col_idxs,
+                   const V* values, const V* b, int64_t bs, int64_t num_rhs, V* c, int64_t cs)
+{
+    for (int64_t i = 0; i < num_rows; ++i)
+        for (int64_t j = 0; j < num_rhs; ++j) c[i * cs + j] = 0;
+    FNI(coo_spmv2)(num_rows, num_cols, nnz, row_idxs, col_idxs, values, b, bs, num_rhs, c, cs);
+}
+void FNI(coo_advanced_spmv)(int64_t num_rows, int64_t num_cols, int64_t nnz, const I* row_idxs, const I* col_idxs,
+                            const V* values, const V* alpha, const V* b, int64_t bs,
+                            int64_t num_rhs, const V* beta, V* c, int64_t cs)
+{
+    FN(dense_scale)(num_rows, num_rhs, beta, 1, c, cs);
+    FNI(coo_advanced_spmv2)(num_rows, num_cols, nnz, row_idxs, col_idxs, values, alpha, b, bs,
+                            num_rhs, c, cs);
+}
+
+/* reference/preconditioner/jacobi_kernels.cpp:419-447 (apply_block), :460-520 (apply /
+ * simple_apply); storage scheme include/ginkgo/core/preconditioner/jacobi.hpp:37-141 */
+void FNI(jacobi_apply)(int64_t num_blocks, int32_t max_block_size, int64_t block_offset, int64_t group_offset,
+                       int32_t group_power, const I* block_ptrs, const V* blocks, const V* alpha_p,
+                       const V* b, int64_t bs, int64_t num_rhs, const V* beta_p, V* x, int64_t xs)
+{
+    const V alpha = alpha_p ? alpha_p[0] : (V)1;
+    const V beta = beta_p ? beta_p[0] : (V)0;
+    const int64_t stride = block_offset << group_power;
+    for (int64_t k = 0; k < num_blocks; ++k) {
+        const V* blk = blocks + group_offset * (k >> group_power) +
+                       block_offset * (k & (((int64_t)1 << group_power) - 1));
+        const int64_t first = block_ptrs[k];
+        const int64_t n = (int64_t)block_ptrs[k + 1] - first;
+        V* xb = x + first * xs;
+        const V* bb = b + first * bs;
+        for (int64_t row = 0; row < n; ++row)
+            for (int64_t col = 0; col < num_rhs; ++col) {
+                if (beta != 0)
+                    xb[row * xs + col] *= beta;
+                else
+                    xb[row * xs + col] = 0;
+            }
+        for (int64_t inner = 0; inner < n; ++inner)
+            for (int64_t row = 0; row < n; ++row)
+                for (int64_t col = 0; col < num_rhs; ++col)
+                    xb[row * xs + col] += alpha * blk[row + inner * stride] * bb[inner * bs + col];
+    }
+}
+
+
+/* reference/preconditioner/jacobi_kernels.cpp:493-520 (simple_apply == alpha 1, beta 0) */
+void FNI(jacobi_simple_apply)(int64_t num_blocks, int32_t max_block_size, int64_t block_offset,
+                              int64_t group_offset, int32_t group_power, const I* block_ptrs,
+                              const V* blocks, const V* b, int64_t bs, int64_t num_rhs, V* x,
+                              int64_t xs)
+{
+    FNI(jacobi_apply)(num_blocks, max_block_size, block_offset, group_offset, group_power,
+                      block_ptrs, blocks, NULL, b, bs, num_rhs, NULL, x, xs);
+}
+
+#endif

@@ -1,0 +1,311 @@
+/*
+ * oracle_solvers.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU restatement of the reference's HOST solver loops (they live in
+ * libginkgo's core, not in a backend): core/solver/cg.cpp:93-181,
+ * core/solver/bicgstab.cpp:95-233, core/solver/gmres.cpp:321-626, with the
+ * stopping criteria of core/stop/{iteration,residual_norm,combined}.cpp, all
+ * built from the oracle kernels of oracle_impl.h.  Included once per value
+ * type; matrices are CSR with int32 indices.
+ */
+
+#ifndef ORC_SOLVER_COMMON
+#define ORC_SOLVER_COMMON
+typedef struct {
+    int32_t precond;        /* 0 identity, 1 scalar Jacobi (inv_diag), 2 block Jacobi */
+    int64_t num_blocks;     /* block Jacobi */
+    int64_t block_offset, group_offset;
+    int32_t group_power;
+    const int32_t* block_ptrs;
+    const void* blocks;     /* inverted blocks / inv_diag, value type */
+    int64_t max_iters;      /* <0: no Iteration criterion */
+    int32_t res_kind;       /* 0 none, 1 ResidualNorm, 2 ImplicitResidualNorm */
+    int32_t baseline;       /* 0 rhs_norm, 1 initial_resnorm, 2 absolute */
+    double reduction_factor;
+    int32_t iter_first;     /* order inside stop::Combined: Iteration before residual? */
+    int32_t krylov_dim;     /* GMRES */
+    int32_t ortho;          /* GMRES: 0 mgs, 1 cgs, 2 cgs2 */
+} orc_solver_cfg;
+#endif
+
+typedef struct {
+    int64_t n, cols;
+    const int32_t *rp, *ci;
+    const V* va;
+    const orc_solver_cfg* cfg;
+    V* starting_tau; /* 1 x cols */
+    V* u_tau;        /* 1 x cols */
+} FN(sctx);
+
+static void FN(s_apply_A)(const FN(sctx) * s, const V* alpha, const V* b, const V* beta, V* c)
+{
+    /* LinOp::apply(alpha, b, beta, x) -> csr::advanced_spmv; apply(b, x) -> csr::spmv */
+    if (alpha)
+        CAT(FN(csr_advanced_spmv), i32)(s->n, s->n, (int64_t)s->rp[s->n], s->rp, s->ci, s->va, alpha, b, s->cols, s->cols, beta,
+                                        c, s->cols);
+    else
+        CAT(FN(csr_spmv), i32)(s->n, s->n, (int64_t)s->rp[s->n], s->rp, s->ci, s->va, b, s->cols, s->cols, c, s->cols);
+}
+
+static void FN(s_apply_M)(const FN(sctx) * s, const V* r, V* z)
+{
+    const orc_solver_cfg* c = s->cfg;
+    if (c->precond == 0) { /* matrix::Identity::apply == copy */
+        memcpy(z, r, sizeof(V) * s->n * s->cols);
+    } else if (c->precond == 1) {
+        FN(jacobi_simple_scalar_apply)(s->n, s->cols, (const V*)c->blocks, r, s->cols, z, s->cols);
+    } else {
+        CAT(FN(jacobi_apply), i32)(c->num_blocks, 32, c->block_offset, c->group_offset, c->group_power,
+                                   c->block_ptrs, (const V*)c->blocks, NULL, r, s->cols, s->cols,
+                                   NULL, z, s->cols);
+    }
+}
+
+/* criterion generation: core/stop/residual_norm.cpp:91-160 */
+static void FN(s_criterion_generate)(FN(sctx) * s, const V* b, const V* initial_residual)
+{
+    const orc_solver_cfg* c = s->cfg;
+    if (c->res_kind == 0) return;
+    if (c->baseline == 0)
+        FN(dense_compute_norm2)(s->n, s->cols, b, s->cols, s->starting_tau);
+    else if (c->baseline == 1)
+        FN(dense_compute_norm2)(s->n, s->cols, initial_residual, s->cols, s->starting_tau);
+    else
+        for (int64_t j = 0; j < s->cols; ++j) s->starting_tau[j] = 1;
+}
+
+/* stop::Combined / Iteration / ResidualNorm check, core/stop/combined.cpp:33-52,
+ * core/stop/iteration.cpp:14-24, core/stop/residual_norm.cpp:165-228.
+ * residual may be NULL when residual_norm is given (GMRES). */
+static int FN(s_check)(FN(sctx) * s, int64_t iter, const V* residual, const V* residual_norm,
+                       const V* implicit_sq, int set_finalized, uint8_t* stop, int* one_changed)
+{
+    const orc_solver_cfg* c = s->cfg;
+    const int has_it = c->max_iters >= 0, has_res = c->res_kind != 0;
+    const int ncrit = has_it + has_res;
+    int converged = 0;
+    *one_changed = 0;
+    uint8_t id = 1;
+    for (int k = 0; k < ncrit && !converged; ++k, ++id) {
+        /* a single criterion is used directly with RelativeStoppingId == 1 */
+        const int is_it = has_it && (!has_res || (c->iter_first ? k == 0 : k == 1));
+        int local = 0;
+        if (is_it) {
+            if (iter >= c->max_iters) {
+                orc_set_all_statuses(s->cols, id, set_finalized, stop);
+                local = 1;
+                converged = 1;
+            }
+        } else {
+            int32_t all_conv = 0, ch = 0;
+            if (c->res_kind == 1) {
+                const V* tau = residual_norm;
+                if (!tau) {
+                    FN(dense_compute_norm2)(s->n, s->cols, residual, s->cols, s->u_tau);
+                    tau = s->u_tau;
+                }
+                FN(residual_norm)(s->cols, tau, s->starting_tau, (V)c->reduction_factor, id,
+                                  set_finalized, stop, NULL, &all_conv, &ch);
+            } else {
+                FN(implicit_residual_norm)(s->cols, implicit_sq, s->starting_tau,
+                                           (V)c->reduction_factor, id, set_finalized, stop,
+                                           NULL, &all_conv, &ch);
+            }
+            local = ch;
+            converged = all_conv;
+        }
+        *one_changed |= local;
+    }
+    return converged;
+}
+
+/* core/solver/cg.cpp:93-181.  Returns the iteration count at which the loop broke. */
+int64_t FN(cg_solve)(int64_t n, int64_t cols, const int32_t* rp, const int32_t* ci, const V* va,
+                     const V* b, V* x, const orc_solver_cfg* cfg, uint8_t* stop_out,
+                     V* resnorm_out)
+{
+    FN(sctx) s = {n, cols, rp, ci, va, cfg, NULL, NULL};
+    const size_t nb = sizeof(V) * n * cols;
+    V *r = malloc(nb), *z = malloc(nb), *p = malloc(nb), *q = malloc(nb);
+    V *beta = malloc(sizeof(V) * cols), *prev_rho = malloc(sizeof(V) * cols),
+      *rho = malloc(sizeof(V) * cols);
+    s.starting_tau = malloc(sizeof(V) * cols);
+    s.u_tau = malloc(sizeof(V) * cols);
+    uint8_t* stop = malloc(cols);
+    const V one = 1, neg_one = -1;
+    FN(cg_initialize)(n, cols, b, cols, r, cols, z, cols, p, cols, q, cols, prev_rho, rho, stop);
+    FN(s_apply_A)(&s, &neg_one, x, &one, r);
+    FN(s_criterion_generate)(&s, b, r);
+    int64_t iter = -1;
+    int one_changed;
+    while (1) {
+        FN(s_apply_M)(&s, r, z);
+        FN(dense_compute_dot)(n, cols, r, cols, z, cols, rho);
+        ++iter;
+        if (FN(s_check)(&s, iter, r, NULL, rho, 1, stop, &one_changed)) break;
+        FN(cg_step_1)(n, cols, p, cols, z, cols, rho, prev_rho, stop);
+        FN(s_apply_A)(&s, NULL, p, NULL, q);
+        FN(dense_compute_dot)(n, cols, p, cols, q, cols, beta);
+        FN(cg_step_2)(n, cols, x, cols, r, cols, p, cols, q, cols, beta, rho, stop);
+        V* t = prev_rho;
+        prev_rho = rho;
+        rho = t;
+    }
+    if (stop_out) memcpy(stop_out, stop, cols);
+    if (resnorm_out) FN(dense_compute_norm2)(n, cols, r, cols, resnorm_out);
+    free(r); free(z); free(p); free(q); free(beta); free(prev_rho); free(rho);
+    free(s.starting_tau); free(s.u_tau); free(stop);
+    return iter;
+}
+
+/* core/solver/bicgstab.cpp:95-233 */
+int64_t FN(bicgstab_solve)(int64_t n, int64_t cols, const int32_t* rp, const int32_t* ci,
+                           const V* va, const V* b, V* x, const orc_solver_cfg* cfg,
+                           uint8_t* stop_out, V* resnorm_out)
+{
+    FN(sctx) s = {n, cols, rp, ci, va, cfg, NULL, NULL};
+    const size_t nb = sizeof(V) * n * cols;
+    V *r = malloc(nb), *z = malloc(nb), *y = malloc(nb), *v = malloc(nb), *sv = malloc(nb),
+      *t = malloc(nb), *p = malloc(nb), *rr = malloc(nb);
+    V* sc = malloc(sizeof(V) * cols * 6);
+    V *alpha = sc, *beta = sc + cols, *gamma = sc + 2 * cols, *prev_rho = sc + 3 * cols,
+      *rho = sc + 4 * cols, *omega = sc + 5 * cols;
+    s.starting_tau = malloc(sizeof(V) * cols);
+    s.u_tau = malloc(sizeof(V) * cols);
+    uint8_t* stop = malloc(cols);
+    const V one = 1, neg_one = -1;
+    FN(bicgstab_initialize)(n, cols, b, cols, r, cols, rr, cols, y, cols, sv, cols, t, cols, z,
+                            cols, v, cols, p, cols, prev_rho, rho, alpha, beta, gamma, omega, stop);
+    FN(s_apply_A)(&s, &neg_one, x, &one, r);
+    FN(s_criterion_generate)(&s, b, r);
+    memcpy(rr, r, nb);
+    int64_t iter = -1;
+    int one_changed;
+    while (1) {
+        ++iter;
+        FN(dense_compute_dot)(n, cols, rr, cols, r, cols, rho);
+        if (FN(s_check)(&s, iter, r, NULL, rho, 1, stop, &one_changed)) break;
+        FN(bicgstab_step_1)(n, cols, r, cols, p, cols, v, cols, rho, prev_rho, alpha, omega, stop);
+        FN(s_apply_M)(&s, p, y);
+        FN(s_apply_A)(&s, NULL, y, NULL, v);
+        FN(dense_compute_dot)(n, cols, rr, cols, v, cols, beta);
+        FN(bicgstab_step_2)(n, cols, r, cols, sv, cols, v, cols, rho, alpha, beta, stop);
+        int all_stopped = FN(s_check)(&s, iter, sv, NULL, rho, 0, stop, &one_changed);
+        if (one_changed) FN(bicgstab_finalize)(n, cols, x, cols, y, cols, alpha, stop);
+        if (all_stopped) break;
+        FN(s_apply_M)(&s, sv, z);
+        FN(s_apply_A)(&s, NULL, z, NULL, t);
+        FN(dense_compute_dot)(n, cols, sv, cols, t, cols, gamma);
+        FN(dense_compute_dot)(n, cols, t, cols, t, cols, beta);
+        FN(bicgstab_step_3)(n, cols, x, cols, r, cols, sv, cols, t, cols, y, cols, z, cols, alpha,
+                            beta, gamma, omega, stop);
+        V* tmp = prev_rho;
+        prev_rho = rho;
+        rho = tmp;
+    }
+    if (stop_out) memcpy(stop_out, stop, cols);
+    if (resnorm_out) {
+        /* true residual b - A x */
+        memcpy(rr, b, nb);
+        FN(s_apply_A)(&s, &neg_one, x, &one, rr);
+        FN(dense_compute_norm2)(n, cols, rr, cols, resnorm_out);
+    }
+    free(r); free(z); free(y); free(v); free(sv); free(t); free(p); free(rr); free(sc);
+    free(s.starting_tau); free(s.u_tau); free(stop);
+    return iter;
+}
+
+/* core/solver/gmres.cpp:321-626 (non-flexible), orthogonalisation :156-307 */
+int64_t FN(gmres_solve)(int64_t n, int64_t cols, const int32_t* rp, const int32_t* ci, const V* va,
+                        const V* b, V* x, const orc_solver_cfg* cfg, uint8_t* stop_out,
+                        V* resnorm_out)
+{
+    FN(sctx) s = {n, cols, rp, ci, va, cfg, NULL, NULL};
+    const int64_t kd = cfg->krylov_dim;
+    const size_t nb = sizeof(V) * n * cols;
+    V *residual = malloc(nb), *precv = malloc(nb), *before = malloc(nb), *after = malloc(nb);
+    V* krylov = malloc(nb * (kd + 1));
+    const int64_t hstride = (kd + 1) * cols;
+    V* hess = calloc(kd * hstride, sizeof(V));
+    V* hess_aux = calloc((kd + 1) * cols, sizeof(V));
+    V *gsin = malloc(sizeof(V) * kd * cols), *gcos = malloc(sizeof(V) * kd * cols);
+    V* rnc = calloc((kd + 1) * cols, sizeof(V));
+    V* rnorm = malloc(sizeof(V) * cols);
+    V* y = calloc(kd * cols, sizeof(V));
+    uint64_t* fin = malloc(sizeof(uint64_t) * cols);
+    s.starting_tau = malloc(sizeof(V) * cols);
+    s.u_tau = malloc(sizeof(V) * cols);
+    uint8_t* stop = malloc(cols);
+    const V one = 1, neg_one = -1;
+    FN(common_gmres_initialize)(n, cols, kd, b, cols, residual, cols, gsin, cols, gcos, cols, stop);
+    FN(s_apply_A)(&s, &neg_one, x, &one, residual);
+    FN(dense_compute_norm2)(n, cols, residual, cols, rnorm);
+    FN(gmres_restart)(n, cols, residual, cols, rnorm, rnc, krylov, cols, fin);
+    FN(s_criterion_generate)(&s, b, residual);
+    int64_t total_iter = -1, restart_iter = 0;
+    int one_changed;
+    while (1) {
+        ++total_iter;
+        if (FN(s_check)(&s, total_iter, residual, rnorm, NULL, 0, stop, &one_changed)) break;
+        if (restart_iter == kd) {
+            FN(common_gmres_solve_krylov)(cols, rnc, cols, hess, hstride, y, cols, fin, stop);
+            FN(gmres_multi_axpy)(n, cols, krylov, cols, y, cols, before, cols, fin, stop);
+            FN(s_apply_M)(&s, before, after);
+            FN(dense_add_scaled)(n, cols, &one, 1, after, cols, x, cols);
+            memcpy(residual, b, nb);
+            FN(s_apply_A)(&s, &neg_one, x, &one, residual);
+            FN(dense_compute_norm2)(n, cols, residual, cols, rnorm);
+            FN(gmres_restart)(n, cols, residual, cols, rnorm, rnc, krylov, cols, fin);
+            restart_iter = 0;
+        }
+        V* this_k = krylov + n * cols * restart_iter;
+        V* next_k = krylov + n * cols * (restart_iter + 1);
+        FN(s_apply_M)(&s, this_k, precv);
+        V* hiter = hess + restart_iter * hstride; /* (restart_iter+2) x cols, stride cols */
+        FN(s_apply_A)(&s, NULL, precv, NULL, next_k);
+        if (cfg->ortho == 0) {
+            for (int64_t i = 0; i <= restart_iter; ++i) {
+                FN(dense_compute_dot)(n, cols, krylov + n * cols * i, cols, next_k, cols,
+                                      hiter + i * cols);
+                FN(dense_sub_scaled)(n, cols, hiter + i * cols, cols, krylov + n * cols * i, cols,
+                                     next_k, cols);
+            }
+        } else {
+            FN(gmres_multi_dot)(n, cols, restart_iter + 1, krylov, cols, next_k, cols, hiter, cols);
+            for (int64_t i = 0; i <= restart_iter; ++i)
+                FN(dense_sub_scaled)(n, cols, hiter + i * cols, cols, krylov + n * cols * i, cols,
+                                     next_k, cols);
+            if (cfg->ortho == 2) {
+                FN(gmres_multi_dot)(n, cols, restart_iter + 1, krylov, cols, next_k, cols, hess_aux,
+                                    cols);
+                for (int64_t i = 0; i <= restart_iter; ++i)
+                    FN(dense_sub_scaled)(n, cols, hess_aux + i * cols, cols,
+                                         krylov + n * cols * i, cols, next_k, cols);
+                /* hessenberg_iter->add_scaled(one, hessenberg_aux_iter): (restart_iter+2) rows;
+                 * the last row of aux is whatever it held -- the reference adds it too, and
+                 * then overwrites that entry with the norm below */
+                FN(dense_add_scaled)(restart_iter + 2, cols, &one, 1, hess_aux, cols, hiter, cols);
+            }
+        }
+        V* hnorm = hiter + (restart_iter + 1) * cols;
+        FN(dense_compute_norm2)(n, cols, next_k, cols, hnorm);
+        FN(dense_inv_scale)(n, cols, hnorm, cols, next_k, cols);
+        FN(common_gmres_hessenberg_qr)(cols, gsin, cols, gcos, cols, rnorm, rnc, cols, hiter, cols,
+                                       restart_iter, fin, stop);
+        restart_iter++;
+    }
+    FN(common_gmres_solve_krylov)(cols, rnc, cols, hess, hstride, y, cols, fin, stop);
+    FN(gmres_multi_axpy)(n, cols, krylov, cols, y, cols, before, cols, fin, stop);
+    FN(s_apply_M)(&s, before, after);
+    FN(dense_add_scaled)(n, cols, &one, 1, after, cols, x, cols);
+    if (stop_out) memcpy(stop_out, stop, cols);
+    if (resnorm_out) {
+        memcpy(residual, b, nb);
+        FN(s_apply_A)(&s, &neg_one, x, &one, residual);
+        FN(dense_compute_norm2)(n, cols, residual, cols, resnorm_out);
+    }
+    free(residual); free(precv); free(before); free(after); free(krylov); free(hess);
+    free(hess_aux); free(gsin); free(gcos); free(rnc); free(rnorm); free(y); free(fin);
+    free(s.starting_tau); free(s.u_tau); free(stop);
+    return total_iter;
+}

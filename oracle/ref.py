@@ -1,0 +1,93 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes loader for oracle/_ref/libgko_ref_shim.so -- the REAL
+reference (its core + Reference/OMP executors compiled from /root/reference by
+oracle/ref_build/Makefile) behind the small C ABI of oracle/ref_shim.cpp."""
+import ctypes
+import os
+
+import numpy as np
+
+from ginkgo_b200 import _cdecl
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libgko_ref_shim.so")
+_lib = None
+
+
+def available():
+    return os.path.exists(LIB_PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        l = ctypes.CDLL(LIB_PATH)
+        src = open(os.path.join(_HERE, "ref_shim.cpp")).read()
+        src = src[src.index('extern "C" {'):]
+        decls = _cdecl.parse(src, "refshim_")
+        _cdecl.bind(l, decls)
+        _lib = l
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data
+
+
+def _vt(a):
+    return 0 if a.dtype == np.float64 else 1
+
+
+def num_threads():
+    return lib().refshim_num_threads()
+
+
+def spmv(fmt, rp, ci, va, x, n_cols, alpha=None, beta=None, y=None, exec_kind=0, reps=0,
+         strategy="classical"):
+    """y = A x (or alpha A x + beta y) through the reference's LinOp::apply; returns (y, s/rep)"""
+    n = len(rp) - 1
+    x2 = np.ascontiguousarray(x).reshape(n_cols, -1)
+    nrhs = x2.shape[1]
+    if y is None:
+        y = np.zeros((n, nrhs), dtype=va.dtype)
+    sec = ctypes.c_double(0)
+    a = None if alpha is None else np.array([alpha], va.dtype)
+    b = None if beta is None else np.array([beta], va.dtype)
+    st = lib().refshim_spmv(exec_kind, fmt.encode(), _vt(va), n, n_cols, len(va), _p(rp), _p(ci),
+                            _p(va), _p(x2), nrhs, _p(y), _p(a), _p(b), reps, ctypes.byref(sec),
+                            strategy.encode())
+    assert st == 0, st
+    return y, sec.value
+
+
+def solve(kind, rp, ci, va, b, x0, precond_max_bs=0, block_ptrs=None, max_iters=-1, res_kind=1,
+          baseline=0, reduction=1e-8, iter_first=1, krylov_dim=30, ortho=0, exec_kind=0):
+    n = len(rp) - 1
+    b2 = np.ascontiguousarray(b).reshape(n, -1)
+    x = np.ascontiguousarray(x0).reshape(n, -1).copy()
+    nrhs = b2.shape[1]
+    iters = ctypes.c_int64(0)
+    sec = ctypes.c_double(0)
+    resn = np.zeros(nrhs, va.dtype)
+    nb = 0 if block_ptrs is None else len(block_ptrs) - 1
+    st = lib().refshim_solve(exec_kind, {"cg": 0, "bicgstab": 1, "gmres": 2}[kind], _vt(va), n,
+                             len(va), _p(rp), _p(ci), _p(va), _p(b2), _p(x), nrhs, precond_max_bs,
+                             _p(block_ptrs), nb, max_iters, res_kind, baseline, reduction,
+                             iter_first, krylov_dim, ortho, ctypes.byref(iters), _p(resn),
+                             ctypes.byref(sec))
+    assert st == 0, st
+    return x, iters.value, resn, sec.value
+
+
+def jacobi_generate(rp, ci, va, max_bs, block_ptrs=None):
+    n = len(rp) - 1
+    nb = 0 if block_ptrs is None else len(block_ptrs) - 1
+    cap = 32 * 32 * (n + 64) if max_bs > 1 else n
+    blocks = np.zeros(cap, va.dtype)
+    meta = np.zeros(5, np.int64)
+    ptrs = np.zeros(n + 2, np.int32)
+    st = lib().refshim_jacobi_generate(_vt(va), n, len(va), _p(rp), _p(ci), _p(va), max_bs,
+                                       _p(block_ptrs), nb, _p(blocks), cap, _p(meta), _p(ptrs))
+    assert st == 0, st
+    return dict(block_offset=int(meta[0]), group_offset=int(meta[1]), group_power=int(meta[2]),
+                num_blocks=int(meta[3]), blocks=blocks[:meta[4]].copy(),
+                block_ptrs=ptrs[:meta[3] + 1].copy())
