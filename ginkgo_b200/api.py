@@ -187,3 +187,140 @@ class Csr(_SparseBase):
                 self.exec._l.b200_csr_plan_destroy(self._plan)
         except Exception:
             pass
+
+
+# ---------------------------------------------------------------------------------------------
+# Solvers: thin Python handles over the C++ host layer (ginkgo_b200/host/gko_b200.hpp) -- the
+# loops, criteria and preconditioners run in C++; Python only passes device pointers.
+# ---------------------------------------------------------------------------------------------
+import os as _os
+
+_HOST_LIB = None
+
+
+def _host():
+    global _HOST_LIB
+    if _HOST_LIB is None:
+        _lib.lib()  # the C-ABI library first (RTLD_GLOBAL)
+        path = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "lib",
+                             "libgko_b200_host.so")
+        if not _os.path.exists(path):
+            raise _lib.B200Error("%s not found: run `make -C ginkgo_b200/host`" % path)
+        h = ctypes.CDLL(path)
+        vp, ll, i, d = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_double
+        h.gkob_last_error.restype = ctypes.c_char_p
+        h.gkob_exec_create.restype = vp
+        h.gkob_exec_create.argtypes = [i, vp]
+        h.gkob_destroy.argtypes = [vp]
+        h.gkob_launch_count.restype = ll
+        h.gkob_launch_count.argtypes = [vp]
+        for s in ("f64", "f32"):
+            f = getattr(h, "gkob_csr_view_%s_i32" % s)
+            f.restype, f.argtypes = vp, [vp, ll, ll, ll, vp, vp, vp]
+            f = getattr(h, "gkob_dense_view_" + s)
+            f.restype, f.argtypes = vp, [vp, ll, ll, ll, vp]
+            f = getattr(h, "gkob_solver_create_" + s)
+            f.restype = vp
+            f.argtypes = [vp, i, vp, i, vp, ll, ll, i, i, d, i, i, i, i, i]
+            f = getattr(h, "gkob_solver_info_" + s)
+            f.restype, f.argtypes = i, [vp, ctypes.POINTER(ll), ctypes.POINTER(ctypes.c_ubyte),
+                                        ctypes.POINTER(i)]
+        h.gkob_apply.restype, h.gkob_apply.argtypes = i, [vp, vp, vp]
+        h.gkob_apply4.restype, h.gkob_apply4.argtypes = i, [vp, vp, vp, vp, vp]
+        h.gkob_synchronize.restype, h.gkob_synchronize.argtypes = i, [vp]
+        _HOST_LIB = h
+    return _HOST_LIB
+
+
+def _hcheck(rc):
+    if rc != 0:
+        msg = _host().gkob_last_error().decode()
+        if rc == 2:
+            raise DimensionMismatch(msg)
+        if rc == 3:
+            raise NotSupported(msg)
+        raise _lib.B200Error(msg)
+
+
+class HostExecutor:
+    """gko_b200::B200Executor (C++) bound to a torch stream"""
+
+    def __init__(self, device_id=0, stream=None):
+        self.device = torch.device("cuda", device_id)
+        with torch.cuda.device(device_id):
+            self.stream = stream or torch.cuda.Stream(device_id)
+        self.h = _host().gkob_exec_create(device_id, self.stream.cuda_stream)
+        if not self.h:
+            raise _lib.B200Error(_host().gkob_last_error().decode())
+
+    def synchronize(self):
+        _hcheck(_host().gkob_synchronize(self.h))
+
+    def launch_count(self):
+        return _host().gkob_launch_count(self.h)
+
+
+class _HostObj:
+    def __init__(self, exec_, handle, keep=()):
+        if not handle:
+            raise _lib.B200Error(_host().gkob_last_error().decode())
+        self.exec, self.h, self._keep = exec_, handle, keep
+
+    def __del__(self):
+        try:
+            _host().gkob_destroy(self.h)
+        except Exception:
+            pass
+
+
+def host_csr(exec_, size, values, col_idxs, row_ptrs):
+    """gko_b200::matrix::Csr<V,int32> viewing torch device tensors"""
+    s = _VT[values.dtype]
+    fn = getattr(_host(), "gkob_csr_view_%s_i32" % s)
+    o = _HostObj(exec_, fn(exec_.h, size[0], size[1], values.numel(), row_ptrs.data_ptr(),
+                           col_idxs.data_ptr(), values.data_ptr()), (values, col_idxs, row_ptrs))
+    o.vt = s
+    return o
+
+
+def host_dense(exec_, t, cols=None, stride=None):
+    """gko_b200::matrix::Dense<V> viewing a torch device tensor (rows x stride, row-major)"""
+    if t.dim() == 1:
+        t = t.reshape(-1, 1)
+    rows, st = t.shape[0], (stride or t.shape[1])
+    cols = cols or t.shape[1]
+    fn = getattr(_host(), "gkob_dense_view_" + _VT[t.dtype])
+    return _HostObj(exec_, fn(exec_.h, rows, cols, st, t.data_ptr()), (t,))
+
+
+class HostSolver:
+    """solver::Cg / Bicgstab / Gmres of the C++ host layer.
+
+    kind: "cg" | "bicgstab" | "gmres";  criteria: max_iters (None = no Iteration criterion),
+    res_kind 0 none / 1 ResidualNorm / 2 ImplicitResidualNorm, baseline 0 rhs_norm /
+    1 initial_resnorm / 2 absolute, iter_first = order inside stop::Combined;
+    precond_max_bs 0 = none, 1 = scalar Jacobi, k > 1 = block Jacobi (block_ptrs required)."""
+
+    def __init__(self, exec_, kind, A, precond_max_bs=0, block_ptrs=None, max_iters=None,
+                 res_kind=1, baseline=0, reduction=1e-8, iter_first=True, krylov_dim=30, ortho=0,
+                 fused=True, check_every=16):
+        self.vt = A.vt
+        bp = None
+        nb = 0
+        if block_ptrs is not None:
+            import numpy as np
+            self._bp = np.ascontiguousarray(block_ptrs, dtype=np.int32)
+            bp, nb = self._bp.ctypes.data, len(self._bp) - 1
+        fn = getattr(_host(), "gkob_solver_create_" + self.vt)
+        self.obj = _HostObj(exec_, fn(exec_.h, {"cg": 0, "bicgstab": 1, "gmres": 2}[kind], A.h,
+                                      precond_max_bs, bp, nb, -1 if max_iters is None else max_iters,
+                                      res_kind, baseline, reduction, int(iter_first), krylov_dim,
+                                      ortho, int(fused), check_every), (A,))
+
+    def apply(self, b, x):
+        _hcheck(_host().gkob_apply(self.obj.h, b.h, x.h))
+        it, st, fu = ctypes.c_longlong(0), ctypes.c_ubyte(0), ctypes.c_int(0)
+        _hcheck(getattr(_host(), "gkob_solver_info_" + self.vt)(self.obj.h, ctypes.byref(it),
+                                                                ctypes.byref(st), ctypes.byref(fu)))
+        self.num_iterations, self.stop_status, self.used_fused = it.value, st.value, bool(fu.value)
+        return x

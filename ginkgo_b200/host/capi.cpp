@@ -1,0 +1,196 @@
+// capi.cpp -- a C handle API over the C++ host layer (gko_b200.hpp) so that the Python
+// harness (tests, bench.py) drives the SAME host code a C++ user links: executor, Csr, Dense
+// views, preconditioner::Jacobi, stop criteria, solver::{Cg,Bicgstab,Gmres}.
+#include <cstdio>
+#include <string>
+
+#include "gko_b200.hpp"
+
+using namespace gko_b200;
+
+namespace {
+thread_local std::string g_err;
+struct Handle {
+    std::shared_ptr<Executor> exec;
+    std::shared_ptr<LinOp> op;
+};
+template <typename F>
+int guarded(F f)
+{
+    try {
+        f();
+        return 0;
+    } catch (const DimensionMismatch& e) {
+        g_err = std::string("DimensionMismatch: ") + e.what();
+        return 2;
+    } catch (const NotSupported& e) {
+        g_err = std::string("NotSupported: ") + e.what();
+        return 3;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+template <typename V>
+std::unique_ptr<LinOp> make_solver(std::shared_ptr<Executor> exec, int kind,
+                                   std::shared_ptr<LinOp> A, int precond_max_bs,
+                                   const int32* block_ptrs, int64 nblocks, int64 max_iters,
+                                   int res_kind, int baseline, double reduction, int iter_first,
+                                   int krylov_dim, int ortho, int fused, int check_every)
+{
+    std::vector<std::shared_ptr<const stop::CriterionFactory>> crit;
+    std::shared_ptr<const stop::CriterionFactory> it_c, res_c;
+    if (max_iters >= 0) it_c = stop::Iteration::build().with_max_iters((size_type)max_iters).on(exec);
+    auto mode = baseline == 0   ? stop::mode::rhs_norm
+                : baseline == 1 ? stop::mode::initial_resnorm
+                                : stop::mode::absolute;
+    if (res_kind == 1)
+        res_c = stop::ResidualNorm<V>::build().with_baseline(mode).with_reduction_factor(reduction).on(exec);
+    else if (res_kind == 2)
+        res_c = stop::ImplicitResidualNorm<V>::build()
+                    .with_baseline(mode)
+                    .with_reduction_factor(reduction)
+                    .on(exec);
+    if (iter_first) {
+        if (it_c) crit.push_back(it_c);
+        if (res_c) crit.push_back(res_c);
+    } else {
+        if (res_c) crit.push_back(res_c);
+        if (it_c) crit.push_back(it_c);
+    }
+    std::shared_ptr<const LinOpFactory> pre;
+    if (precond_max_bs > 0) {
+        auto pb = preconditioner::Jacobi<V, int32>::build();
+        pb.with_max_block_size((uint32)precond_max_bs);
+        if (block_ptrs && precond_max_bs > 1)
+            pb.with_block_pointers(std::vector<int32>(block_ptrs, block_ptrs + nblocks + 1));
+        pre = pb.on(exec);
+    }
+    if (kind == 0) {
+        auto f = solver::Cg<V>::build();
+        f.with_criteria(crit).with_fused(fused != 0).with_check_every(check_every);
+        if (pre) f.with_preconditioner(pre);
+        return f.on(exec)->generate(A);
+    }
+    if (kind == 1) {
+        auto f = solver::Bicgstab<V>::build();
+        f.with_criteria(crit);
+        if (pre) f.with_preconditioner(pre);
+        return f.on(exec)->generate(A);
+    }
+    auto f = solver::Gmres<V>::build();
+    f.with_criteria(crit).with_krylov_dim((size_type)krylov_dim);
+    f.with_ortho_method(ortho == 0   ? solver::gmres::ortho_method::mgs
+                        : ortho == 1 ? solver::gmres::ortho_method::cgs
+                                     : solver::gmres::ortho_method::cgs2);
+    if (pre) f.with_preconditioner(pre);
+    return f.on(exec)->generate(A);
+}
+}  // namespace
+
+extern "C" {
+
+const char* gkob_last_error() { return g_err.c_str(); }
+
+void* gkob_exec_create(int device, void* stream)
+{
+    Handle* h = new Handle();
+    if (guarded([&] { h->exec = B200Executor::create(device, stream); })) {
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+
+void gkob_destroy(void* handle) { delete static_cast<Handle*>(handle); }
+
+long long gkob_launch_count(void* exec) { return static_cast<Handle*>(exec)->exec->launch_count(); }
+
+#define GKOB_DEF(V, S)                                                                          \
+    void* gkob_csr_view_##S##_i32(void* exec, long long n, long long m, long long nnz,         \
+                                  int32* rp, int32* ci, V* va)                                  \
+    {                                                                                           \
+        auto e = static_cast<Handle*>(exec)->exec;                                              \
+        Handle* h = new Handle{e, nullptr};                                                     \
+        if (guarded([&] {                                                                       \
+                h->op = matrix::Csr<V, int32>::create(                                          \
+                    e, dim2{(size_type)n, (size_type)m}, array<V>::view(e, nnz, va),            \
+                    array<int32>::view(e, nnz, ci), array<int32>::view(e, n + 1, rp));          \
+            })) {                                                                               \
+            delete h;                                                                           \
+            return nullptr;                                                                     \
+        }                                                                                       \
+        return h;                                                                               \
+    }                                                                                           \
+    void* gkob_dense_view_##S(void* exec, long long rows, long long cols, long long stride,     \
+                              V* ptr)                                                           \
+    {                                                                                           \
+        auto e = static_cast<Handle*>(exec)->exec;                                              \
+        Handle* h = new Handle{e, nullptr};                                                     \
+        if (guarded([&] {                                                                       \
+                h->op = matrix::Dense<V>::create_view(                                          \
+                    e, dim2{(size_type)rows, (size_type)cols}, ptr, (size_type)stride);         \
+            })) {                                                                               \
+            delete h;                                                                           \
+            return nullptr;                                                                     \
+        }                                                                                       \
+        return h;                                                                               \
+    }                                                                                           \
+    void* gkob_solver_create_##S(void* exec, int kind, void* matrix, int precond_max_bs,        \
+                                 const int32* block_ptrs, long long nblocks,                    \
+                                 long long max_iters, int res_kind, int baseline,               \
+                                 double reduction, int iter_first, int krylov_dim, int ortho,   \
+                                 int fused, int check_every)                                    \
+    {                                                                                           \
+        auto e = static_cast<Handle*>(exec)->exec;                                              \
+        Handle* h = new Handle{e, nullptr};                                                     \
+        if (guarded([&] {                                                                       \
+                h->op = make_solver<V>(e, kind, static_cast<Handle*>(matrix)->op,               \
+                                       precond_max_bs, block_ptrs, nblocks, max_iters,          \
+                                       res_kind, baseline, reduction, iter_first, krylov_dim,   \
+                                       ortho, fused, check_every);                              \
+            })) {                                                                               \
+            delete h;                                                                           \
+            return nullptr;                                                                     \
+        }                                                                                       \
+        return h;                                                                               \
+    }                                                                                           \
+    int gkob_solver_info_##S(void* solver, long long* iters, unsigned char* status,             \
+                             int* used_fused)                                                   \
+    {                                                                                           \
+        return guarded([&] {                                                                    \
+            auto op = static_cast<Handle*>(solver)->op.get();                                   \
+            auto sb = dynamic_cast<solver::SolverBase<V>*>(op);                                 \
+            if (!sb) throw NotSupported("not a solver");                                        \
+            *iters = (long long)sb->get_num_iterations();                                       \
+            *status = sb->get_stop_status(0);                                                   \
+            auto cg = dynamic_cast<solver::Cg<V>*>(op);                                         \
+            *used_fused = cg ? (int)cg->used_fused_path() : 0;                                  \
+        });                                                                                     \
+    }
+GKOB_DEF(double, f64)
+GKOB_DEF(float, f32)
+
+// x = op(b)   /   x = alpha op(b) + beta x  (alpha, beta: 1x1 Dense handles)
+int gkob_apply(void* op, void* b, void* x)
+{
+    return guarded([&] {
+        static_cast<Handle*>(op)->op->apply(static_cast<Handle*>(b)->op.get(),
+                                            static_cast<Handle*>(x)->op.get());
+    });
+}
+int gkob_apply4(void* op, void* alpha, void* b, void* beta, void* x)
+{
+    return guarded([&] {
+        static_cast<Handle*>(op)->op->apply(
+            static_cast<Handle*>(alpha)->op.get(), static_cast<Handle*>(b)->op.get(),
+            static_cast<Handle*>(beta)->op.get(), static_cast<Handle*>(x)->op.get());
+    });
+}
+int gkob_synchronize(void* exec)
+{
+    return guarded([&] { static_cast<Handle*>(exec)->exec->synchronize(); });
+}
+
+}  // extern "C"

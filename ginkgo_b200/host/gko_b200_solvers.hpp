@@ -1,0 +1,1011 @@
+// gko_b200_solvers.hpp -- preconditioner::Jacobi, stop::*, solver::{Cg,Bicgstab,Gmres}.
+// Included by gko_b200.hpp.
+#pragma once
+
+namespace gko_b200 {
+
+// =============================================================================================
+// stop:: criteria (include/ginkgo/core/stop/*.hpp, core/stop/*.cpp)
+// =============================================================================================
+namespace stop {
+
+enum class mode { absolute, initial_resnorm, rhs_norm };
+
+struct CriterionArgs {
+    std::shared_ptr<const LinOp> system_matrix;
+    const LinOp* b = nullptr;
+    const LinOp* x = nullptr;
+    const LinOp* initial_residual = nullptr;
+};
+
+// what Criterion::Updater carries (include/ginkgo/core/stop/criterion.hpp)
+struct Updater {
+    size_type num_iterations = 0;
+    const LinOp* residual = nullptr;
+    const LinOp* residual_norm = nullptr;
+    const LinOp* implicit_sq_residual_norm = nullptr;
+    const LinOp* solution = nullptr;
+};
+
+class Criterion {
+public:
+    virtual ~Criterion() = default;
+    // returns true if all right-hand sides have stopped
+    virtual bool check(uint8 stopping_id, bool set_finalized, array<uint8>* stop_status,
+                       bool* one_changed, const Updater& u) = 0;
+};
+
+class CriterionFactory {
+public:
+    virtual ~CriterionFactory() = default;
+    virtual std::unique_ptr<Criterion> generate(std::shared_ptr<const Executor> exec,
+                                                const CriterionArgs& args) const = 0;
+    // description used by the fused solver paths
+    virtual int kind() const = 0;  // 0 iteration, 1 residual norm, 2 implicit residual norm
+    virtual size_type max_iters() const { return 0; }
+    virtual double reduction_factor() const { return 0; }
+    virtual mode baseline() const { return mode::rhs_norm; }
+};
+
+// core/stop/iteration.cpp:14-24
+class Iteration : public Criterion {
+public:
+    struct Factory : CriterionFactory {
+        size_type max_iters_ = 0;
+        Factory& with_max_iters(size_type n)
+        {
+            max_iters_ = n;
+            return *this;
+        }
+        std::shared_ptr<const CriterionFactory> on(std::shared_ptr<const Executor>) const
+        {
+            return std::make_shared<Factory>(*this);
+        }
+        std::unique_ptr<Criterion> generate(std::shared_ptr<const Executor> exec,
+                                            const CriterionArgs&) const override
+        {
+            return std::unique_ptr<Criterion>(new Iteration(exec, max_iters_));
+        }
+        int kind() const override { return 0; }
+        size_type max_iters() const override { return max_iters_; }
+    };
+    static Factory build() { return Factory{}; }
+    bool check(uint8 id, bool set_finalized, array<uint8>* stop_status, bool* one_changed,
+               const Updater& u) override
+    {
+        const bool result = u.num_iterations >= max_iters_;
+        if (result) {
+            GKOB_CALL(b200_set_all_statuses(exec_->ctx(), stop_status->get_size(), id,
+                                            set_finalized, stop_status->get_data()));
+            *one_changed = true;
+        }
+        return result;
+    }
+
+private:
+    Iteration(std::shared_ptr<const Executor> exec, size_type n) : exec_(exec), max_iters_(n) {}
+    std::shared_ptr<const Executor> exec_;
+    size_type max_iters_;
+};
+
+// core/stop/residual_norm.cpp:91-228
+template <typename V, bool IMPLICIT>
+class ResidualNormBase : public Criterion {
+public:
+    struct Factory : CriterionFactory {
+        double factor_ = 5 * std::numeric_limits<V>::epsilon();
+        mode baseline_ = mode::rhs_norm;
+        Factory& with_reduction_factor(double f)
+        {
+            factor_ = f;
+            return *this;
+        }
+        Factory& with_baseline(mode m)
+        {
+            baseline_ = m;
+            return *this;
+        }
+        std::shared_ptr<const CriterionFactory> on(std::shared_ptr<const Executor>) const
+        {
+            return std::make_shared<Factory>(*this);
+        }
+        std::unique_ptr<Criterion> generate(std::shared_ptr<const Executor> exec,
+                                            const CriterionArgs& args) const override
+        {
+            return std::unique_ptr<Criterion>(new ResidualNormBase(exec, args, (V)factor_, baseline_));
+        }
+        int kind() const override { return IMPLICIT ? 2 : 1; }
+        double reduction_factor() const override { return factor_; }
+        mode baseline() const override { return baseline_; }
+    };
+    static Factory build() { return Factory{}; }
+
+    bool check(uint8 id, bool set_finalized, array<uint8>* stop_status, bool* one_changed,
+               const Updater& u) override
+    {
+        using Dense = matrix::Dense<V>;
+        const Dense* tau = nullptr;
+        if (IMPLICIT) {
+            if (!u.implicit_sq_residual_norm) throw NotSupported("ImplicitResidualNorm needs rho");
+            tau = as<Dense>(u.implicit_sq_residual_norm);
+        } else if (u.residual_norm) {
+            tau = as<Dense>(u.residual_norm);
+        } else if (u.residual) {
+            as<Dense>(u.residual)->compute_norm2(u_tau_.get());
+            tau = u_tau_.get();
+        } else if (u.solution && system_matrix_ && b_) {
+            auto r = as<Dense>(b_)->clone();
+            system_matrix_->apply(neg_one_.get(), u.solution, one_.get(), r.get());
+            r->compute_norm2(u_tau_.get());
+            tau = u_tau_.get();
+        } else {
+            throw NotSupported("ResidualNorm: no residual information");
+        }
+        int32 all_conv = 0, changed = 0;
+        auto fn = IMPLICIT ? vabi<V>::implicit_residual_norm : vabi<V>::residual_norm;
+        GKOB_CALL(fn(exec_->ctx(), tau->get_size().cols, tau->get_const_values(),
+                     starting_tau_->get_const_values(), factor_, id, set_finalized,
+                     stop_status->get_data(), device_storage_.get_data(), &all_conv, &changed));
+        *one_changed = changed != 0;
+        return all_conv != 0;
+    }
+
+private:
+    ResidualNormBase(std::shared_ptr<const Executor> exec, const CriterionArgs& args, V factor,
+                     mode baseline)
+        : exec_(exec), factor_(factor), device_storage_(exec, 2), system_matrix_(args.system_matrix),
+          b_(args.b)
+    {
+        using Dense = matrix::Dense<V>;
+        one_ = matrix::scalar<V>(V(1), exec);
+        neg_one_ = matrix::scalar<V>(V(-1), exec);
+        if (!args.b) throw NotSupported("ResidualNorm needs b");
+        const size_type cols = args.b->get_size().cols;
+        starting_tau_ = Dense::create(exec, dim2{1, cols});
+        u_tau_ = Dense::create(exec, dim2{1, cols});
+        switch (baseline) {
+        case mode::initial_resnorm:
+            if (args.initial_residual) {
+                as<Dense>(args.initial_residual)->compute_norm2(starting_tau_.get());
+            } else {
+                if (!args.system_matrix || !args.x) throw NotSupported("initial_resnorm needs A, x");
+                auto r = as<Dense>(args.b)->clone();
+                args.system_matrix->apply(neg_one_.get(), args.x, one_.get(), r.get());
+                r->compute_norm2(starting_tau_.get());
+            }
+            break;
+        case mode::rhs_norm:
+            as<Dense>(args.b)->compute_norm2(starting_tau_.get());
+            break;
+        case mode::absolute:
+            starting_tau_->fill(V(1));
+            break;
+        }
+    }
+    std::shared_ptr<const Executor> exec_;
+    V factor_;
+    array<uint8> device_storage_;
+    std::shared_ptr<const LinOp> system_matrix_;
+    const LinOp* b_;
+    std::unique_ptr<matrix::Dense<V>> starting_tau_, u_tau_, one_, neg_one_;
+};
+template <typename V>
+using ResidualNorm = ResidualNormBase<V, false>;
+template <typename V>
+using ImplicitResidualNorm = ResidualNormBase<V, true>;
+
+// core/stop/combined.cpp:33-52: ids 1, 2, ... in order, first converged criterion wins
+class Combined : public Criterion {
+public:
+    explicit Combined(std::vector<std::unique_ptr<Criterion>> c) : criteria_(std::move(c)) {}
+    bool check(uint8, bool set_finalized, array<uint8>* stop_status, bool* one_changed,
+               const Updater& u) override
+    {
+        bool one_converged = false;
+        uint8 ids = 1;
+        *one_changed = false;
+        for (auto& c : criteria_) {
+            bool local = false;
+            one_converged |= c->check(ids, set_finalized, stop_status, &local, u);
+            *one_changed |= local;
+            if (one_converged) break;
+            ids++;
+        }
+        return one_converged;
+    }
+
+private:
+    std::vector<std::unique_ptr<Criterion>> criteria_;
+};
+
+inline std::unique_ptr<Criterion> combine_and_generate(
+    const std::vector<std::shared_ptr<const CriterionFactory>>& factories,
+    std::shared_ptr<const Executor> exec, const CriterionArgs& args)
+{
+    if (factories.empty()) throw NotSupported("a solver needs at least one stopping criterion");
+    if (factories.size() == 1) return factories[0]->generate(exec, args);
+    std::vector<std::unique_ptr<Criterion>> c;
+    for (auto& f : factories) c.push_back(f->generate(exec, args));
+    return std::unique_ptr<Criterion>(new Combined(std::move(c)));
+}
+
+}  // namespace stop
+
+// =============================================================================================
+// preconditioner::Jacobi (include/ginkgo/core/preconditioner/jacobi.hpp, core/preconditioner/
+// jacobi.cpp).  apply runs on the device; generate: scalar = extract_diagonal +
+// invert_diagonal kernels; block = the reference's pivoted Gauss-Jordan
+// (reference/preconditioner/jacobi_kernels.cpp:150-415) run on the host at setup time with
+// user-supplied block pointers (natural-block detection is not part of this path).
+// =============================================================================================
+namespace preconditioner {
+
+template <typename I>
+struct block_interleaved_storage_scheme {
+    I block_offset = 0, group_offset = 0;
+    uint32 group_power = 0;
+    I get_group_size() const { return I(1) << group_power; }
+    I get_stride() const { return block_offset << group_power; }
+    I get_global_block_offset(I k) const
+    {
+        return group_offset * (k >> group_power) + block_offset * (k & (get_group_size() - 1));
+    }
+    size_type compute_storage_space(size_type num_blocks) const
+    {
+        const size_type gs = get_group_size();
+        return (num_blocks + gs - 1) / gs * group_offset;
+    }
+};
+
+template <typename V, typename I>
+class Jacobi : public LinOp {
+public:
+    struct Factory : LinOpFactory {
+        uint32 max_block_size_ = 32;
+        std::vector<I> block_pointers_;
+        std::shared_ptr<const Executor> exec_;
+        Factory& with_max_block_size(uint32 s)
+        {
+            max_block_size_ = s;
+            return *this;
+        }
+        Factory& with_block_pointers(std::vector<I> p)
+        {
+            block_pointers_ = std::move(p);
+            return *this;
+        }
+        std::shared_ptr<const LinOpFactory> on(std::shared_ptr<const Executor> exec) const
+        {
+            auto f = std::make_shared<Factory>(*this);
+            f->exec_ = exec;
+            return f;
+        }
+        std::unique_ptr<LinOp> generate(std::shared_ptr<const LinOp> op) const override
+        {
+            return std::unique_ptr<LinOp>(new Jacobi(exec_, *this, op));
+        }
+    };
+    static Factory build() { return Factory{}; }
+
+    uint32 get_max_block_size() const { return max_block_size_; }
+    size_type get_num_blocks() const { return num_blocks_; }
+    const V* get_blocks() const { return blocks_.get_const_data(); }
+    const block_interleaved_storage_scheme<I>& get_storage_scheme() const { return scheme_; }
+
+protected:
+    Jacobi(std::shared_ptr<const Executor> exec, const Factory& f, std::shared_ptr<const LinOp> op)
+        : LinOp(exec, op->get_size()), max_block_size_(f.max_block_size_)
+    {
+        if (max_block_size_ < 1 || max_block_size_ > 32)
+            throw NotSupported("Jacobi: max_block_size must be in [1, 32]");
+        auto csr = as<matrix::Csr<V, I>>(op.get());
+        const size_type n = size_.rows;
+        if (max_block_size_ == 1) {
+            auto diag = csr->extract_diagonal();
+            blocks_ = array<V>(exec, n);
+            GKOB_CALL(vabi<V>::invert_diagonal(exec->ctx(), n, diag->get_const_values(),
+                                               blocks_.get_data()));
+            num_blocks_ = n;
+            return;
+        }
+        if (f.block_pointers_.empty())
+            throw NotSupported("block Jacobi on this path needs explicit block_pointers");
+        std::vector<I> ptrs = f.block_pointers_;
+        num_blocks_ = ptrs.size() - 1;
+        // compute_storage_scheme (jacobi.hpp:589-625)
+        uint32 pow2 = 1;
+        while (pow2 < max_block_size_) pow2 *= 2;
+        const uint32 group_size = 32 / pow2;
+        scheme_.block_offset = (I)max_block_size_;
+        scheme_.group_offset = (I)(max_block_size_ * group_size * max_block_size_);
+        scheme_.group_power = 0;
+        while ((1u << scheme_.group_power) < group_size) ++scheme_.group_power;
+        // host copy of the matrix, extract + invert every diagonal block
+        const size_type nnz = csr->get_num_stored_elements();
+        std::vector<I> rp(n + 1), ci(nnz);
+        std::vector<V> va(nnz);
+        exec->copy_to_host(rp.data(), csr->get_const_row_ptrs(), n + 1);
+        exec->copy_to_host(ci.data(), csr->get_const_col_idxs(), nnz);
+        exec->copy_to_host(va.data(), csr->get_const_values(), nnz);
+        std::vector<V> store(scheme_.compute_storage_space(num_blocks_), V(0));
+        const size_type stride = scheme_.get_stride();
+        std::vector<V> blk;
+        std::vector<I> perm;
+        for (size_type k = 0; k < num_blocks_; ++k) {
+            const I start = ptrs[k];
+            const I bs = ptrs[k + 1] - start;
+            if (bs < 1 || (uint32)bs > max_block_size_)
+                throw BadDimension("Jacobi: block larger than max_block_size");
+            blk.assign((size_type)bs * bs, V(0));
+            perm.resize(bs);
+            for (I i = 0; i < bs; ++i) perm[i] = i;
+            // extract_block (reference jacobi_kernels.cpp:113-146)
+            for (I r = 0; r < bs; ++r)
+                for (I p = rp[start + r]; p < rp[start + r + 1]; ++p) {
+                    const I c = ci[p] - start;
+                    if (c >= 0 && c < bs) blk[(size_type)r * bs + c] = va[p];
+                }
+            invert_block(bs, perm.data(), blk.data(), (size_type)bs);
+            // permute_and_transpose_block (reference :243-258)
+            V* dst = store.data() + scheme_.get_global_block_offset((I)k);
+            for (I i = 0; i < bs; ++i)
+                for (I j = 0; j < bs; ++j) dst[i + perm[j] * stride] = blk[(size_type)i * bs + j];
+        }
+        blocks_ = array<V>(exec, store);
+        block_pointers_ = array<I>(exec, ptrs);
+    }
+
+    // reference/preconditioner/jacobi_kernels.cpp:150-278 (choose_pivot, swap_rows,
+    // apply_gauss_jordan_transform, invert_block), same operation order
+    static bool invert_block(I n, I* perm, V* block, size_type stride)
+    {
+        for (I k = 0; k < n; ++k) {
+            I cp = 0;
+            const V* col = block + k * stride + k;
+            for (I i = 1; i < n - k; ++i)
+                if (std::abs(col[cp * stride]) < std::abs(col[i * stride])) cp = i;
+            cp += k;
+            for (I i = 0; i < n; ++i) std::swap(block[k * stride + i], block[cp * stride + i]);
+            std::swap(perm[k], perm[cp]);
+            const V d = block[k * stride + k];
+            if (d == V(0)) return false;
+            for (I i = 0; i < n; ++i) block[i * stride + k] /= -d;
+            block[k * stride + k] = V(0);
+            for (I i = 0; i < n; ++i)
+                for (I j = 0; j < n; ++j)
+                    block[i * stride + j] += block[i * stride + k] * block[k * stride + j];
+            for (I j = 0; j < n; ++j) block[k * stride + j] /= d;
+            block[k * stride + k] = V(1) / d;
+        }
+        return true;
+    }
+
+    void apply_impl(const LinOp* b, LinOp* x) const override
+    {
+        auto db = as<matrix::Dense<V>>(b);
+        auto dx = as<matrix::Dense<V>>(x);
+        if (max_block_size_ == 1) {
+            GKOB_CALL(vabi<V>::simple_scalar_apply(exec_->ctx(), size_.rows, db->get_size().cols,
+                                                   blocks_.get_const_data(), db->get_const_values(),
+                                                   db->get_stride(), dx->get_values(),
+                                                   dx->get_stride()));
+        } else {
+            GKOB_CALL((viabi<V, I>::jacobi_simple_apply(
+                exec_->ctx(), num_blocks_, max_block_size_, scheme_.block_offset,
+                scheme_.group_offset, scheme_.group_power, block_pointers_.get_const_data(),
+                blocks_.get_const_data(), db->get_const_values(), db->get_stride(),
+                db->get_size().cols, dx->get_values(), dx->get_stride())));
+        }
+    }
+    void apply_impl(const LinOp* alpha, const LinOp* b, const LinOp* beta, LinOp* x) const override
+    {
+        auto db = as<matrix::Dense<V>>(b);
+        auto dx = as<matrix::Dense<V>>(x);
+        const V* al = as<matrix::Dense<V>>(alpha)->get_const_values();
+        const V* be = as<matrix::Dense<V>>(beta)->get_const_values();
+        if (max_block_size_ == 1) {
+            GKOB_CALL(vabi<V>::scalar_apply(exec_->ctx(), size_.rows, db->get_size().cols,
+                                            blocks_.get_const_data(), al, db->get_const_values(),
+                                            db->get_stride(), be, dx->get_values(),
+                                            dx->get_stride()));
+        } else {
+            GKOB_CALL((viabi<V, I>::jacobi_apply(
+                exec_->ctx(), num_blocks_, max_block_size_, scheme_.block_offset,
+                scheme_.group_offset, scheme_.group_power, block_pointers_.get_const_data(),
+                blocks_.get_const_data(), al, db->get_const_values(), db->get_stride(),
+                db->get_size().cols, be, dx->get_values(), dx->get_stride())));
+        }
+    }
+
+private:
+    uint32 max_block_size_;
+    size_type num_blocks_ = 0;
+    block_interleaved_storage_scheme<I> scheme_;
+    array<V> blocks_;
+    array<I> block_pointers_;
+};
+
+}  // namespace preconditioner
+
+// =============================================================================================
+// solver:: Cg / Bicgstab / Gmres (core/solver/{cg,bicgstab,gmres}.cpp)
+// =============================================================================================
+namespace solver {
+
+namespace gmres {
+enum class ortho_method { mgs, cgs, cgs2 };
+}
+
+template <typename V>
+class SolverBase : public LinOp {
+public:
+    // what log::Convergence reports in the reference
+    size_type get_num_iterations() const { return num_iterations_; }
+    uint8 get_stop_status(size_type col = 0) const { return col < status_.size() ? status_[col] : 0; }
+    bool has_converged() const
+    {
+        for (auto s : status_)
+            if (!(s & 0x80)) return false;
+        return !status_.empty();
+    }
+    std::shared_ptr<const LinOp> get_system_matrix() const { return system_matrix_; }
+    std::shared_ptr<const LinOp> get_preconditioner() const { return preconditioner_; }
+
+protected:
+    using Dense = matrix::Dense<V>;
+    template <typename FactoryT>
+    SolverBase(std::shared_ptr<const Executor> exec, const FactoryT& f,
+               std::shared_ptr<const LinOp> op)
+        : LinOp(exec, op->get_size()), system_matrix_(std::move(op)), criteria_(f.criteria_)
+    {
+        if (size_.rows != size_.cols) throw DimensionMismatch("solver needs a square operator");
+        if (f.generated_preconditioner_)
+            preconditioner_ = f.generated_preconditioner_;
+        else if (f.preconditioner_)
+            preconditioner_ = f.preconditioner_->generate(system_matrix_);
+        else
+            preconditioner_ = matrix::Identity<V>::create(exec, size_.rows);
+        one_ = matrix::scalar<V>(V(1), exec);
+        neg_one_ = matrix::scalar<V>(V(-1), exec);
+    }
+    void apply_impl(const LinOp* alpha, const LinOp* b, const LinOp* beta, LinOp* x) const override
+    {
+        // x = alpha * solve(b) + beta * x   (core/solver/cg.cpp:184-200)
+        auto dx = as<Dense>(x);
+        auto x_clone = dx->clone();
+        static_cast<const LinOp*>(this)->apply(b, static_cast<LinOp*>(x_clone.get()));
+        dx->scale(as<Dense>(beta));
+        dx->add_scaled(as<Dense>(alpha), x_clone.get());
+    }
+    void record(size_type iters, const array<uint8>& stop) const
+    {
+        num_iterations_ = iters;
+        status_ = stop.to_host();
+    }
+    std::shared_ptr<const LinOp> system_matrix_;
+    std::shared_ptr<const LinOp> preconditioner_;
+    std::vector<std::shared_ptr<const stop::CriterionFactory>> criteria_;
+    std::unique_ptr<Dense> one_, neg_one_;
+    mutable size_type num_iterations_ = 0;
+    mutable std::vector<uint8> status_;
+};
+
+// common factory parameters (GKO_CREATE_FACTORY_PARAMETERS idiom)
+template <typename Derived>
+struct SolverFactoryBase : LinOpFactory {
+    std::vector<std::shared_ptr<const stop::CriterionFactory>> criteria_;
+    std::shared_ptr<const LinOpFactory> preconditioner_;
+    std::shared_ptr<const LinOp> generated_preconditioner_;
+    std::shared_ptr<const Executor> exec_;
+    template <typename... F>
+    Derived& with_criteria(const F&... f)
+    {
+        criteria_.clear();
+        (criteria_.push_back(to_shared(f)), ...);
+        return static_cast<Derived&>(*this);
+    }
+    Derived& with_criteria(std::vector<std::shared_ptr<const stop::CriterionFactory>> v)
+    {
+        criteria_ = std::move(v);
+        return static_cast<Derived&>(*this);
+    }
+    template <typename PF>
+    Derived& with_preconditioner(const PF& pf)
+    {
+        preconditioner_ = to_shared_lo(pf);
+        return static_cast<Derived&>(*this);
+    }
+    Derived& with_generated_preconditioner(std::shared_ptr<const LinOp> p)
+    {
+        generated_preconditioner_ = std::move(p);
+        return static_cast<Derived&>(*this);
+    }
+    std::shared_ptr<const Derived> on(std::shared_ptr<const Executor> exec) const
+    {
+        auto f = std::make_shared<Derived>(static_cast<const Derived&>(*this));
+        f->exec_ = exec;
+        // deferred factories (criteria / preconditioner built without .on(exec))
+        return f;
+    }
+
+private:
+    static std::shared_ptr<const stop::CriterionFactory> to_shared(
+        std::shared_ptr<const stop::CriterionFactory> p)
+    {
+        return p;
+    }
+    template <typename F>
+    static std::shared_ptr<const stop::CriterionFactory> to_shared(const F& f)
+    {
+        return std::make_shared<F>(f);  // deferred_factory_parameter: no .on(exec) needed
+    }
+    static std::shared_ptr<const LinOpFactory> to_shared_lo(std::shared_ptr<const LinOpFactory> p)
+    {
+        return p;
+    }
+    template <typename F>
+    static std::shared_ptr<const LinOpFactory> to_shared_lo(const F& f)
+    {
+        return std::make_shared<F>(f);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Cg (core/solver/cg.cpp:93-181)
+// ---------------------------------------------------------------------------------------------
+template <typename V>
+class Cg : public SolverBase<V> {
+    using Base = SolverBase<V>;
+    using Dense = matrix::Dense<V>;
+
+public:
+    struct Factory : SolverFactoryBase<Factory> {
+        bool fused_ = true;
+        int check_every_ = 16;
+        // B200 extension: device-resident fused iteration (default on where applicable)
+        Factory& with_fused(bool f)
+        {
+            fused_ = f;
+            return *this;
+        }
+        Factory& with_check_every(int k)
+        {
+            check_every_ = k;
+            return *this;
+        }
+        std::unique_ptr<LinOp> generate(std::shared_ptr<const LinOp> op) const override
+        {
+            auto exec = this->exec_ ? this->exec_ : op->get_executor();
+            return std::unique_ptr<LinOp>(new Cg(exec, *this, op));
+        }
+    };
+    static Factory build() { return Factory{}; }
+    bool used_fused_path() const { return used_fused_; }
+    ~Cg() override { b200_graph_destroy(graph_); }
+
+protected:
+    Cg(std::shared_ptr<const Executor> exec, const Factory& f, std::shared_ptr<const LinOp> op)
+        : Base(exec, f, op), fused_(f.fused_), check_every_(std::max(1, f.check_every_))
+    {}
+    using Base::apply_impl;
+
+    void apply_impl(const LinOp* b, LinOp* x) const override
+    {
+        auto db = as<Dense>(b);
+        auto dx = as<Dense>(x);
+        if (fused_ && try_fused<int32>(db, dx)) return;
+        if (fused_ && try_fused<int64>(db, dx)) return;
+        used_fused_ = false;
+        apply_dense_impl(db, dx);
+    }
+
+    // the reference's loop, kernel for kernel
+    void apply_dense_impl(const Dense* b, Dense* x) const
+    {
+        auto exec = this->exec_;
+        const dim2 sz = b->get_size();
+        const size_type nrhs = sz.cols;
+        auto r = Dense::create(exec, sz), z = Dense::create(exec, sz), p = Dense::create(exec, sz),
+             q = Dense::create(exec, sz);
+        auto beta = Dense::create(exec, dim2{1, nrhs}), prev_rho = Dense::create(exec, dim2{1, nrhs}),
+             rho = Dense::create(exec, dim2{1, nrhs});
+        array<uint8> stop_status(exec, nrhs);
+        bool one_changed = false;
+        auto ctx = exec->ctx();
+        GKOB_CALL(vabi<V>::cg_initialize(ctx, sz.rows, nrhs, b->get_const_values(), b->get_stride(),
+                                         r->get_values(), r->get_stride(), z->get_values(),
+                                         z->get_stride(), p->get_values(), p->get_stride(),
+                                         q->get_values(), q->get_stride(), prev_rho->get_values(),
+                                         rho->get_values(), stop_status.get_data()));
+        this->system_matrix_->apply(this->neg_one_.get(), x, this->one_.get(), r.get());
+        stop::CriterionArgs args{this->system_matrix_, b, x, r.get()};
+        auto crit = stop::combine_and_generate(this->criteria_, exec, args);
+        int64 iter = -1;
+        while (true) {
+            this->preconditioner_->apply(r.get(), z.get());
+            r->compute_conj_dot(z.get(), rho.get());
+            ++iter;
+            stop::Updater u;
+            u.num_iterations = iter;
+            u.residual = r.get();
+            u.implicit_sq_residual_norm = rho.get();
+            u.solution = x;
+            if (crit->check(1, true, &stop_status, &one_changed, u)) break;
+            GKOB_CALL(vabi<V>::cg_step_1(ctx, sz.rows, nrhs, p->get_values(), p->get_stride(),
+                                         z->get_const_values(), z->get_stride(),
+                                         rho->get_const_values(), prev_rho->get_const_values(),
+                                         stop_status.get_const_data()));
+            this->system_matrix_->apply(p.get(), q.get());
+            p->compute_conj_dot(q.get(), beta.get());
+            GKOB_CALL(vabi<V>::cg_step_2(ctx, sz.rows, nrhs, x->get_values(), x->get_stride(),
+                                         r->get_values(), r->get_stride(), p->get_const_values(),
+                                         p->get_stride(), q->get_const_values(), q->get_stride(),
+                                         beta->get_const_values(), rho->get_const_values(),
+                                         stop_status.get_const_data()));
+            std::swap(prev_rho, rho);
+        }
+        this->record(iter, stop_status);
+    }
+
+    // Fused device-resident path: Csr matrix, one right-hand side, Identity or scalar-Jacobi
+    // preconditioner, criteria made of Iteration / (Implicit)ResidualNorm.
+    template <typename I>
+    bool try_fused(const Dense* b, Dense* x) const
+    {
+        using Csr = matrix::Csr<V, I>;
+        auto A = dynamic_cast<const Csr*>(this->system_matrix_.get());
+        if (!A || b->get_size().cols != 1 || b->get_stride() != 1 || x->get_stride() != 1) return false;
+        const V* inv_diag = nullptr;
+        if (auto J = dynamic_cast<const preconditioner::Jacobi<V, I>*>(this->preconditioner_.get())) {
+            if (J->get_max_block_size() != 1) return false;
+            inv_diag = J->get_blocks();
+        } else if (!dynamic_cast<const matrix::Identity<V>*>(this->preconditioner_.get())) {
+            return false;
+        }
+        int64 max_iters = -1;
+        int32 res_kind = 0, iter_first = 1, baseline = 0;
+        double factor = 0;
+        if (this->criteria_.empty() || this->criteria_.size() > 2) return false;
+        for (size_type k = 0; k < this->criteria_.size(); ++k) {
+            auto& c = this->criteria_[k];
+            if (c->kind() == 0) {
+                if (max_iters >= 0) return false;
+                max_iters = (int64)c->max_iters();
+                if (k == 1) iter_first = 0;
+            } else {
+                if (res_kind) return false;
+                res_kind = c->kind();
+                factor = c->reduction_factor();
+                baseline = c->baseline() == stop::mode::rhs_norm
+                               ? 0
+                               : c->baseline() == stop::mode::initial_resnorm ? 1 : 2;
+            }
+        }
+        auto exec = this->exec_;
+        auto ctx = exec->ctx();
+        const int64 n = this->size_.rows;
+        const int64 nnz = A->get_num_stored_elements();
+        if ((((std::uintptr_t)A->get_const_col_idxs()) | ((std::uintptr_t)A->get_const_values())) & 15)
+            return false;
+        // workspace (kept across applies: pointers are baked into the iteration graph)
+        if (!ws_ || ws_n_ != n) {
+            ws_ = Dense::create(exec, dim2{(size_type)(4 * n), 1});
+            sc_ = array<V>(exec, 8);
+            ctl_ = array<int32>(exec, 8);
+            work_ = array<V>(exec, (size_type)vabi<V>::fused_work_size(ctx));
+            ws_n_ = n;
+            b200_graph_destroy(graph_);
+            graph_ = nullptr;
+        }
+        V* r = ws_->get_values();
+        V* z = r + n;
+        V* p = z + n;
+        V* q = p + n;
+        V* xv = x->get_values();
+        // r = b - A x
+        exec->copy(r, b->get_const_values(), n);
+        auto rview = Dense::create_view(exec, dim2{(size_type)n, 1}, r, 1);
+        A->apply(this->neg_one_.get(), x, this->one_.get(), rview.get());
+        if (baseline == 0)  // ||b|| into sc[4]
+            GKOB_CALL(vabi<V>::norm2(ctx, n, 1, b->get_const_values(), 1, sc_.get_data() + 4));
+        GKOB_CALL(vabi<V>::fused_init(ctx, n, r, z, p, q, inv_diag, sc_.get_data(), ctl_.get_data(),
+                                      work_.get_data(), max_iters, res_kind, iter_first, baseline,
+                                      (V)factor, 1));
+        auto enqueue_iteration = [&]() {
+            GKOB_CALL(vabi<V>::fused_step_p(ctx, n, p, z, sc_.get_const_data(), ctl_.get_const_data()));
+            GKOB_CALL((viabi<V, I>::csr_spmv_dot(ctx, A->get_plan(), n, n, nnz, A->get_const_row_ptrs(),
+                                                 A->get_const_col_idxs(), A->get_const_values(), p, q,
+                                                 sc_.get_data() + 2, work_.get_data(),
+                                                 ctl_.get_const_data())));
+            GKOB_CALL(vabi<V>::fused_step_xr(ctx, n, xv, r, p, q, z, inv_diag, sc_.get_data(),
+                                             ctl_.get_data(), work_.get_data(), 1));
+        };
+        if (!graph_ || graph_x_ != xv || graph_diag_ != inv_diag) {
+            b200_graph_destroy(graph_);
+            graph_ = nullptr;
+            (void)A->get_plan();  // not inside the capture
+            GKOB_CALL(b200_graph_begin_capture(ctx));
+            for (int k = 0; k < check_every_; ++k) enqueue_iteration();
+            GKOB_CALL(b200_graph_end_capture(ctx, &graph_));
+            graph_x_ = xv;
+            graph_diag_ = inv_diag;
+        }
+        int32 h[8] = {0};
+        exec->copy_to_host(h, ctl_.get_const_data(), 8);
+        while (h[0] == 0) {
+            GKOB_CALL(b200_graph_launch(ctx, graph_));
+            exec->copy_to_host(h, ctl_.get_const_data(), 8);
+        }
+        this->num_iterations_ = (size_type)h[1];
+        this->status_.assign(1, (uint8)h[0]);
+        used_fused_ = true;
+        return true;
+    }
+
+private:
+    bool fused_;
+    int check_every_;
+    mutable bool used_fused_ = false;
+    mutable std::unique_ptr<Dense> ws_;
+    mutable array<V> sc_, work_;
+    mutable array<int32> ctl_;
+    mutable int64 ws_n_ = -1;
+    mutable b200_graph* graph_ = nullptr;
+    mutable const V* graph_x_ = nullptr;
+    mutable const V* graph_diag_ = nullptr;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Bicgstab (core/solver/bicgstab.cpp:95-233)
+// ---------------------------------------------------------------------------------------------
+template <typename V>
+class Bicgstab : public SolverBase<V> {
+    using Base = SolverBase<V>;
+    using Dense = matrix::Dense<V>;
+
+public:
+    struct Factory : SolverFactoryBase<Factory> {
+        std::unique_ptr<LinOp> generate(std::shared_ptr<const LinOp> op) const override
+        {
+            auto exec = this->exec_ ? this->exec_ : op->get_executor();
+            return std::unique_ptr<LinOp>(new Bicgstab(exec, *this, op));
+        }
+    };
+    static Factory build() { return Factory{}; }
+
+protected:
+    Bicgstab(std::shared_ptr<const Executor> exec, const Factory& f, std::shared_ptr<const LinOp> op)
+        : Base(exec, f, op)
+    {}
+    using Base::apply_impl;
+    void apply_impl(const LinOp* lb, LinOp* lx) const override
+    {
+        auto b = as<Dense>(lb);
+        auto x = as<Dense>(lx);
+        auto exec = this->exec_;
+        auto ctx = exec->ctx();
+        const dim2 sz = b->get_size();
+        const size_type nrhs = sz.cols;
+        auto mk = [&] { return Dense::create(exec, sz); };
+        auto sc = [&] { return Dense::create(exec, dim2{1, nrhs}); };
+        auto r = mk(), z = mk(), y = mk(), v = mk(), s = mk(), t = mk(), p = mk(), rr = mk();
+        auto alpha = sc(), beta = sc(), gamma = sc(), prev_rho = sc(), rho = sc(), omega = sc();
+        array<uint8> stop_status(exec, nrhs);
+        bool one_changed = false;
+#define GKOB_VS(d) (d)->get_values(), (d)->get_stride()
+#define GKOB_CVS(d) (d)->get_const_values(), (d)->get_stride()
+        GKOB_CALL(vabi<V>::bicgstab_initialize(
+            ctx, sz.rows, nrhs, GKOB_CVS(b), GKOB_VS(r), GKOB_VS(rr), GKOB_VS(y), GKOB_VS(s),
+            GKOB_VS(t), GKOB_VS(z), GKOB_VS(v), GKOB_VS(p), prev_rho->get_values(),
+            rho->get_values(), alpha->get_values(), beta->get_values(), gamma->get_values(),
+            omega->get_values(), stop_status.get_data()));
+        this->system_matrix_->apply(this->neg_one_.get(), x, this->one_.get(), r.get());
+        stop::CriterionArgs args{this->system_matrix_, b, x, r.get()};
+        auto crit = stop::combine_and_generate(this->criteria_, exec, args);
+        rr->copy_from(r.get());
+        int64 iter = -1;
+        while (true) {
+            ++iter;
+            rr->compute_conj_dot(r.get(), rho.get());
+            stop::Updater u;
+            u.num_iterations = iter;
+            u.residual = r.get();
+            u.implicit_sq_residual_norm = rho.get();
+            u.solution = x;
+            if (crit->check(1, true, &stop_status, &one_changed, u)) break;
+            GKOB_CALL(vabi<V>::bicgstab_step_1(ctx, sz.rows, nrhs, GKOB_CVS(r), GKOB_VS(p),
+                                               GKOB_CVS(v), rho->get_const_values(),
+                                               prev_rho->get_const_values(),
+                                               alpha->get_const_values(), omega->get_const_values(),
+                                               stop_status.get_const_data()));
+            this->preconditioner_->apply(p.get(), y.get());
+            this->system_matrix_->apply(y.get(), v.get());
+            rr->compute_conj_dot(v.get(), beta.get());
+            GKOB_CALL(vabi<V>::bicgstab_step_2(ctx, sz.rows, nrhs, GKOB_CVS(r), GKOB_VS(s),
+                                               GKOB_CVS(v), rho->get_const_values(),
+                                               alpha->get_values(), beta->get_const_values(),
+                                               stop_status.get_const_data()));
+            stop::Updater u2;
+            u2.num_iterations = iter;
+            u2.residual = s.get();
+            u2.implicit_sq_residual_norm = rho.get();
+            const bool all_stopped = crit->check(1, false, &stop_status, &one_changed, u2);
+            if (one_changed)
+                GKOB_CALL(vabi<V>::bicgstab_finalize(ctx, sz.rows, nrhs, GKOB_VS(x), GKOB_CVS(y),
+                                                     alpha->get_const_values(),
+                                                     stop_status.get_data()));
+            if (all_stopped) break;
+            this->preconditioner_->apply(s.get(), z.get());
+            this->system_matrix_->apply(z.get(), t.get());
+            s->compute_conj_dot(t.get(), gamma.get());
+            t->compute_conj_dot(t.get(), beta.get());
+            GKOB_CALL(vabi<V>::bicgstab_step_3(
+                ctx, sz.rows, nrhs, GKOB_VS(x), GKOB_VS(r), GKOB_CVS(s), GKOB_CVS(t), GKOB_CVS(y),
+                GKOB_CVS(z), alpha->get_const_values(), beta->get_const_values(),
+                gamma->get_const_values(), omega->get_values(), stop_status.get_const_data()));
+            std::swap(prev_rho, rho);
+        }
+        this->record(iter, stop_status);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Gmres (core/solver/gmres.cpp:321-626, non-flexible)
+// ---------------------------------------------------------------------------------------------
+template <typename V>
+class Gmres : public SolverBase<V> {
+    using Base = SolverBase<V>;
+    using Dense = matrix::Dense<V>;
+
+public:
+    struct Factory : SolverFactoryBase<Factory> {
+        size_type krylov_dim_ = 100;  // include/ginkgo/core/solver/gmres.hpp:32
+        gmres::ortho_method ortho_ = gmres::ortho_method::mgs;
+        Factory& with_krylov_dim(size_type d)
+        {
+            krylov_dim_ = d;
+            return *this;
+        }
+        Factory& with_ortho_method(gmres::ortho_method m)
+        {
+            ortho_ = m;
+            return *this;
+        }
+        std::unique_ptr<LinOp> generate(std::shared_ptr<const LinOp> op) const override
+        {
+            auto exec = this->exec_ ? this->exec_ : op->get_executor();
+            return std::unique_ptr<LinOp>(new Gmres(exec, *this, op));
+        }
+    };
+    static Factory build() { return Factory{}; }
+
+protected:
+    Gmres(std::shared_ptr<const Executor> exec, const Factory& f, std::shared_ptr<const LinOp> op)
+        : Base(exec, f, op), krylov_dim_(f.krylov_dim_), ortho_(f.ortho_)
+    {}
+    using Base::apply_impl;
+    void apply_impl(const LinOp* lb, LinOp* lx) const override
+    {
+        auto b = as<Dense>(lb);
+        auto x = as<Dense>(lx);
+        auto exec = this->exec_;
+        auto ctx = exec->ctx();
+        const dim2 sz = b->get_size();
+        const size_type n = sz.rows, nrhs = sz.cols, kd = krylov_dim_;
+        auto residual = Dense::create(exec, sz), precv = Dense::create(exec, sz),
+             before = Dense::create(exec, sz), after = Dense::create(exec, sz);
+        auto krylov = Dense::create(exec, dim2{n * (kd + 1), nrhs});
+        auto hess = Dense::create(exec, dim2{kd, (kd + 1) * nrhs});
+        hess->fill(V(0));
+        std::unique_ptr<Dense> hess_aux;
+        if (ortho_ == gmres::ortho_method::cgs2) {
+            hess_aux = Dense::create(exec, dim2{kd + 1, nrhs});
+            hess_aux->fill(V(0));
+        }
+        auto gsin = Dense::create(exec, dim2{kd, nrhs}), gcos = Dense::create(exec, dim2{kd, nrhs});
+        auto rnc = Dense::create(exec, dim2{kd + 1, nrhs});
+        rnc->fill(V(0));
+        auto rnorm = Dense::create(exec, dim2{1, nrhs});
+        auto y = Dense::create(exec, dim2{kd, nrhs});
+        y->fill(V(0));
+        array<std::uint64_t> fin(exec, nrhs);
+        array<uint8> stop_status(exec, nrhs);
+        bool one_changed = false;
+        GKOB_CALL(vabi<V>::gmres_initialize(ctx, n, nrhs, kd, GKOB_CVS(b), GKOB_VS(residual),
+                                            GKOB_VS(gsin), GKOB_VS(gcos), stop_status.get_data()));
+        this->system_matrix_->apply(this->neg_one_.get(), x, this->one_.get(), residual.get());
+        residual->compute_norm2(rnorm.get());
+        auto restart = [&] {
+            GKOB_CALL(vabi<V>::gmres_restart(ctx, n, nrhs, GKOB_CVS(residual),
+                                             rnorm->get_const_values(), rnc->get_values(),
+                                             GKOB_VS(krylov), fin.get_data()));
+        };
+        restart();
+        stop::CriterionArgs args{this->system_matrix_, b, x, residual.get()};
+        auto crit = stop::combine_and_generate(this->criteria_, exec, args);
+        auto solve_and_update = [&] {
+            GKOB_CALL(vabi<V>::gmres_solve_krylov(ctx, nrhs, GKOB_CVS(rnc), GKOB_CVS(hess),
+                                                  GKOB_VS(y), fin.get_const_data(),
+                                                  stop_status.get_const_data()));
+            GKOB_CALL(vabi<V>::gmres_multi_axpy(ctx, n, nrhs, GKOB_CVS(krylov), GKOB_CVS(y),
+                                                GKOB_VS(before), fin.get_const_data(),
+                                                stop_status.get_data()));
+            this->preconditioner_->apply(before.get(), after.get());
+            x->add_scaled(this->one_.get(), after.get());
+        };
+        int64 total_iter = -1;
+        size_type restart_iter = 0;
+        while (true) {
+            ++total_iter;
+            stop::Updater u;
+            u.num_iterations = total_iter;
+            u.residual = residual.get();
+            u.residual_norm = rnorm.get();
+            u.solution = x;
+            if (crit->check(1, false, &stop_status, &one_changed, u)) break;
+            if (restart_iter == kd) {
+                solve_and_update();
+                residual->copy_from(b);
+                this->system_matrix_->apply(this->neg_one_.get(), x, this->one_.get(),
+                                            residual.get());
+                residual->compute_norm2(rnorm.get());
+                restart();
+                restart_iter = 0;
+            }
+            auto this_k = krylov->create_submatrix_rows(n * restart_iter, n * (restart_iter + 1));
+            auto next_k = krylov->create_submatrix_rows(n * (restart_iter + 1), n * (restart_iter + 2));
+            this->preconditioner_->apply(this_k.get(), precv.get());
+            // hessenberg_iter = (restart_iter + 2) x nrhs view of row restart_iter
+            auto hiter = Dense::create_view(exec, dim2{restart_iter + 2, nrhs},
+                                            hess->get_values() + restart_iter * hess->get_stride(),
+                                            nrhs);
+            this->system_matrix_->apply(precv.get(), next_k.get());
+            auto sub_all = [&](Dense* h) {
+                for (size_type i = 0; i <= restart_iter; ++i) {
+                    auto hi = h->create_submatrix_rows(i, i + 1);
+                    auto ki = krylov->create_submatrix_rows(n * i, n * (i + 1));
+                    next_k->sub_scaled(hi.get(), ki.get());
+                }
+            };
+            if (ortho_ == gmres::ortho_method::mgs) {
+                for (size_type i = 0; i <= restart_iter; ++i) {
+                    auto hi = hiter->create_submatrix_rows(i, i + 1);
+                    auto ki = krylov->create_submatrix_rows(n * i, n * (i + 1));
+                    ki->compute_conj_dot(next_k.get(), hi.get());
+                    next_k->sub_scaled(hi.get(), ki.get());
+                }
+            } else {
+                GKOB_CALL(vabi<V>::gmres_multi_dot(ctx, n, nrhs, restart_iter + 1, GKOB_CVS(krylov),
+                                                   GKOB_CVS(next_k), GKOB_VS(hiter)));
+                sub_all(hiter.get());
+                if (ortho_ == gmres::ortho_method::cgs2) {
+                    auto haux = hess_aux->create_submatrix_rows(0, restart_iter + 2);
+                    GKOB_CALL(vabi<V>::gmres_multi_dot(ctx, n, nrhs, restart_iter + 1,
+                                                       GKOB_CVS(krylov), GKOB_CVS(next_k),
+                                                       GKOB_VS(haux)));
+                    sub_all(haux.get());
+                    hiter->add_scaled(this->one_.get(), haux.get());
+                }
+            }
+            auto hnorm = hiter->create_submatrix_rows(restart_iter + 1, restart_iter + 2);
+            next_k->compute_norm2(hnorm.get());
+            next_k->inv_scale(hnorm.get());
+            GKOB_CALL(vabi<V>::gmres_hessenberg_qr(ctx, nrhs, GKOB_VS(gsin), GKOB_VS(gcos),
+                                                   rnorm->get_values(), GKOB_VS(rnc), GKOB_VS(hiter),
+                                                   restart_iter, fin.get_data(),
+                                                   stop_status.get_const_data()));
+            restart_iter++;
+        }
+        solve_and_update();
+        this->record(total_iter, stop_status);
+#undef GKOB_VS
+#undef GKOB_CVS
+    }
+
+private:
+    size_type krylov_dim_;
+    gmres::ortho_method ortho_;
+};
+
+}  // namespace solver
+}  // namespace gko_b200

@@ -335,6 +335,78 @@ B200_DECL_VALUE_INDEX(f64, double, i64, int64_t)
 B200_DECL_VALUE_INDEX(f32, float, i32, int32_t)
 B200_DECL_VALUE_INDEX(f32, float, i64, int64_t)
 
+/* ---------------------------------------------------------------------------
+ * Fused CG iteration (B200 extension behind solver::Cg::apply; it regroups the
+ * loop body of core/solver/cg.cpp:142-180 into three launches per iteration with
+ * every scalar produced and consumed on the device):
+ *   step_p    p = z + (rho/prev_rho) p                        (cg::step_1)
+ *   spmv_dot  q = A p, pq = p.q in the SpMV epilogue          (Csr::apply + compute_conj_dot)
+ *   step_xr   x += (rho/pq) p; r -= (rho/pq) q; z = M^-1 r (scalar Jacobi or identity);
+ *             rho' = r.z; rr = r.r; Iteration / (Implicit)ResidualNorm check
+ *                                                             (cg::step_2 + jacobi apply + dot
+ *                                                              + norm2 + criterion check)
+ * sc:  VT[8]    0 rho, 1 prev_rho, 2 pq, 3 rr, 4 tau0, 5 threshold, 6/7 local partials
+ * ctl: int32[8] 0 stopping_status byte (0 = running), 1 iterations, 2 max_iters,
+ *               3 res_kind (0 none, 1 ResidualNorm, 2 ImplicitResidualNorm), 4 iter_first
+ * Once ctl[0] != 0 every fused kernel is a no-op, so graphs of k iterations can be
+ * replayed and the host polls ctl every k iterations.  finalize == 0 leaves the local
+ * sums in sc[6..7] for a multi-GPU all-reduce followed by b200_cg_fused_finish.
+ * baseline: 0 rhs_norm (caller stores ||b|| in sc[4] first), 1 initial_resnorm, 2 absolute.
+ * ------------------------------------------------------------------------- */
+typedef struct b200_graph b200_graph;
+b200_status b200_graph_begin_capture(b200_ctx* ctx);
+b200_status b200_graph_end_capture(b200_ctx* ctx, b200_graph** out);
+b200_status b200_graph_launch(b200_ctx* ctx, b200_graph* graph);
+void b200_graph_destroy(b200_graph* graph);
+
+#define B200_DECL_FCG(V, VT)                                                                   \
+    int64_t b200_cg_fused_work_size_##V(const b200_ctx* ctx);                                  \
+    b200_status b200_cg_fused_init_##V(                                                        \
+        b200_ctx* ctx, int64_t n, const VT* r, VT* z, VT* p, VT* q, const VT* inv_diag,        \
+        VT* sc, int32_t* ctl, VT* work, int64_t max_iters, int32_t res_kind,                   \
+        int32_t iter_first, int32_t baseline, VT reduction_factor, int32_t finalize);          \
+    b200_status b200_cg_fused_step_p_##V(b200_ctx* ctx, int64_t n, VT* p, const VT* z,         \
+                                         const VT* sc, const int32_t* ctl);                    \
+    b200_status b200_cg_fused_step_xr_##V(b200_ctx* ctx, int64_t n, VT* x, VT* r, const VT* p, \
+                                          const VT* q, VT* z, const VT* inv_diag, VT* sc,      \
+                                          int32_t* ctl, VT* work, int32_t finalize);           \
+    b200_status b200_cg_fused_finish_##V(b200_ctx* ctx, VT* sc, int32_t* ctl, int32_t init,    \
+                                         int32_t baseline, VT reduction_factor);
+#define B200_DECL_SPMV_DOT(V, VT, I, IT)                                                       \
+    b200_status b200_csr_spmv_dot_##V##_##I(                                                   \
+        b200_ctx* ctx, const b200_csr_plan* plan, int64_t num_rows, int64_t num_cols,          \
+        int64_t nnz, const IT* row_ptrs, const IT* col_idxs, const VT* values, const VT* b,    \
+        VT* c, VT* dot_out, VT* work, const int32_t* ctl);
+
+B200_DECL_FCG(f64, double)
+B200_DECL_FCG(f32, float)
+B200_DECL_SPMV_DOT(f64, double, i32, int32_t)
+B200_DECL_SPMV_DOT(f64, double, i64, int64_t)
+B200_DECL_SPMV_DOT(f32, float, i32, int32_t)
+B200_DECL_SPMV_DOT(f32, float, i64, int64_t)
+
+/* ---------------------------------------------------------------------------
+ * Integer-exact helpers either side of the SpMV path:
+ * components::convert_ptrs_to_idxs / convert_idxs_to_ptrs
+ * (reference/components/format_conversion_kernels.cpp) and csr::extract_diagonal
+ * (core/matrix/csr_kernels.hpp, reference/matrix/csr_kernels.cpp).
+ * ------------------------------------------------------------------------- */
+#define B200_DECL_CONVERT_I(I, IT)                                                             \
+    b200_status b200_convert_ptrs_to_idxs_##I(b200_ctx* ctx, const IT* ptrs, int64_t num_rows, \
+                                              IT* idxs);                                       \
+    b200_status b200_convert_idxs_to_ptrs_##I(b200_ctx* ctx, const IT* idxs, int64_t nnz,      \
+                                              int64_t num_rows, IT* ptrs);
+#define B200_DECL_EXTRACT_DIAG(V, VT, I, IT)                                                   \
+    b200_status b200_csr_extract_diagonal_##V##_##I(b200_ctx* ctx, int64_t n,                  \
+                                                    const IT* row_ptrs, const IT* col_idxs,    \
+                                                    const VT* values, VT* diag);
+B200_DECL_CONVERT_I(i32, int32_t)
+B200_DECL_CONVERT_I(i64, int64_t)
+B200_DECL_EXTRACT_DIAG(f64, double, i32, int32_t)
+B200_DECL_EXTRACT_DIAG(f64, double, i64, int64_t)
+B200_DECL_EXTRACT_DIAG(f32, float, i32, int32_t)
+B200_DECL_EXTRACT_DIAG(f32, float, i64, int64_t)
+
 #ifdef __cplusplus
 }
 #endif

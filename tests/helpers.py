@@ -197,3 +197,44 @@ def dense(rng, rows, cols, stride=None, vt="f64", fill=None):
     buf = np.full((rows, stride), 12345.0, dtype=VT[vt])
     buf[:, :cols] = rng.uniform(-1, 1, size=(rows, cols)) if fill is None else fill
     return buf
+
+
+# ---------------------------------------------------------------------------
+# oracle solver loops (oracle/oracle_solvers.h)
+# ---------------------------------------------------------------------------
+def _orc():
+    from oracle import oracle
+    return oracle
+
+
+def orc_solve(kind, vt, rp, ci, va, b, x0, precond=0, jac=None, **kw):
+    n = len(rp) - 1
+    cfg = _orc().SolverCfg()
+    cfg.precond = precond
+    cfg.max_iters = kw.get("max_iters", -1)
+    cfg.res_kind = kw.get("res_kind", 1)
+    cfg.baseline = kw.get("baseline", 0)
+    cfg.reduction_factor = kw.get("reduction", 1e-8)
+    cfg.iter_first = kw.get("iter_first", 1)
+    cfg.krylov_dim = kw.get("krylov_dim", 30)
+    cfg.ortho = kw.get("ortho", 0)
+    keep = []
+    if jac is not None:
+        keep.append(jac["blocks"])
+        cfg.blocks = jac["blocks"].ctypes.data
+        if precond == 2:
+            keep.append(jac["block_ptrs"])
+            cfg.num_blocks, cfg.block_offset = jac["num_blocks"], jac["block_offset"]
+            cfg.group_offset, cfg.group_power = jac["group_offset"], jac["group_power"]
+            cfg.block_ptrs = jac["block_ptrs"].ctypes.data
+    b2 = np.ascontiguousarray(b).reshape(n, -1)
+    x = np.ascontiguousarray(x0).reshape(n, -1).copy()
+    cols = b2.shape[1]
+    stop = np.zeros(cols, np.uint8)
+    rn = np.zeros(cols, VT[vt])
+    it = getattr(_orc().lib(), "orc_%s_solve_%s" % (kind, vt))(
+        n, cols, rp.ctypes.data, ci.ctypes.data, va.ctypes.data, b2.ctypes.data, x.ctypes.data,
+        ctypes.byref(cfg), stop.ctypes.data, rn.ctypes.data)
+    return x, it, stop
+
+

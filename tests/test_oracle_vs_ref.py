@@ -1,0 +1,117 @@
+"""Pins the oracle (oracle/liboracle.so, our C restatement) against the REAL reference:
+oracle/_ref is the reference's own core + ReferenceExecutor + OmpExecutor sources compiled
+in place (oracle/ref_build/Makefile) and driven through its public API (oracle/ref_shim.cpp).
+Runs wherever oracle/_ref exists (this container, and the GPU box via the shipped .so)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from tests import helpers as H
+from tests.helpers import VT
+
+ref = pytest.importorskip("oracle.ref")
+if not ref.available():
+    pytest.skip("oracle/_ref not built (needs /root/reference at build time)", allow_module_level=True)
+from oracle import oracle  # noqa: E402
+
+import workloads as W  # noqa: E402
+
+
+@pytest.mark.parametrize("vt", ["f64", "f32"])
+@pytest.mark.parametrize("fmt", ["csr", "ell", "sellp", "coo", "hybrid"])
+def test_spmv_bit_identical_to_reference(orc, vt, fmt):
+    rng = np.random.default_rng(21)
+    n, m = 1500, 1300
+    rp, ci, va = H.random_csr(rng, n, m, rng.integers(0, 40, n), vt, "i32")
+    for nrhs in (1, 3):
+        x = rng.uniform(-1, 1, (m, nrhs)).astype(VT[vt])
+        y_ref, _ = ref.spmv(fmt, rp, ci, va, x, m)
+        y = np.zeros((n, nrhs), VT[vt])
+        orc("csr_spmv_%s_i32" % vt, n, m, len(va), rp, ci, va, x, nrhs, nrhs, y, nrhs)
+        assert np.array_equal(y, y_ref)
+        y0 = rng.uniform(-1, 1, (n, nrhs)).astype(VT[vt])
+        y_ref, _ = ref.spmv(fmt, rp, ci, va, x, m, alpha=-1.5, beta=0.5, y=y0.copy())
+        y = y0.copy()
+        orc("csr_advanced_spmv_%s_i32" % vt, n, m, len(va), rp, ci, va, np.array([-1.5], VT[vt]), x,
+            nrhs, nrhs, np.array([0.5], VT[vt]), y, nrhs)
+        if fmt in ("csr", "ell", "sellp"):
+            assert np.array_equal(y, y_ref)
+        else:  # coo/hybrid scale y first, then accumulate: same values up to one rounding
+            assert H.rel_err(y, y_ref) <= H.R[vt]
+
+
+def test_omp_executor_matches_reference_executor():
+    rp, ci, va = W.build("cfg1")
+    x = W.vector(len(rp) - 1)
+    y0, _ = ref.spmv("csr", rp, ci, va, x, len(rp) - 1, exec_kind=0)
+    y1, _ = ref.spmv("csr", rp, ci, va, x, len(rp) - 1, exec_kind=1)
+    assert np.array_equal(y0, y1)
+
+
+from tests.helpers import orc_solve  # noqa: E402
+
+
+@pytest.mark.parametrize("kind", ["cg", "bicgstab", "gmres"])
+@pytest.mark.parametrize("precond", [0, 1, 2])
+@pytest.mark.parametrize("vt", ["f64", "f32"])
+def test_solver_loops_bit_identical_to_reference(kind, precond, vt):
+    rp, ci, va = W.laplace(24, 2, vdtype=VT[vt])
+    n = len(rp) - 1
+    b = np.ones((n, 1), VT[vt])
+    x0 = np.zeros((n, 1), VT[vt])
+    red = 1e-8 if vt == "f64" else 1e-4
+    bp = np.arange(0, n + 1, 8, dtype=np.int32) if precond == 2 else None
+    max_bs = {0: 0, 1: 1, 2: 8}[precond]
+    jac = ref.jacobi_generate(rp, ci, va, max_bs, bp) if precond else None
+    for iter_first in (1, 0):
+        xr, itr, _, _ = ref.solve(kind, rp, ci, va, b, x0, precond_max_bs=max_bs, block_ptrs=bp,
+                                  max_iters=300, reduction=red, iter_first=iter_first, krylov_dim=12)
+        xo, ito, stop = orc_solve(kind, vt, rp, ci, va, b, x0, precond, jac, max_iters=300,
+                                  reduction=red, iter_first=iter_first, krylov_dim=12)
+        assert itr == ito
+        assert np.array_equal(xr, xo)
+        assert stop[0] == (0x80 | 0x40 | (2 if iter_first else 1))
+
+
+@pytest.mark.parametrize("ortho", [0, 1, 2])
+def test_gmres_ortho_and_multi_rhs(ortho):
+    rng = np.random.default_rng(4)
+    rp, ci, va = W.laplace(12, 2)
+    n = len(rp) - 1
+    b = rng.uniform(-1, 1, (n, 3))
+    x0 = np.zeros((n, 3))
+    xr, itr, _, _ = ref.solve("gmres", rp, ci, va, b, x0, max_iters=60, reduction=1e-6,
+                              krylov_dim=7, ortho=ortho)
+    xo, ito, _ = orc_solve("gmres", "f64", rp, ci, va, b, x0, max_iters=60, reduction=1e-6,
+                           krylov_dim=7, ortho=ortho)
+    assert itr == ito and np.array_equal(xr, xo)
+
+
+@pytest.mark.parametrize("kind", ["cg", "bicgstab"])
+def test_implicit_residual_and_baselines(kind):
+    rng = np.random.default_rng(5)
+    rp, ci, va = W.laplace(16, 2)
+    n = len(rp) - 1
+    b = rng.uniform(-1, 1, (n, 2))
+    x0 = rng.uniform(-1, 1, (n, 2))
+    for res_kind, baseline in [(2, 0), (1, 1), (1, 2), (2, 1)]:
+        xr, itr, _, _ = ref.solve(kind, rp, ci, va, b, x0, max_iters=200, res_kind=res_kind,
+                                  baseline=baseline, reduction=1e-7)
+        xo, ito, _ = orc_solve(kind, "f64", rp, ci, va, b, x0, max_iters=200, res_kind=res_kind,
+                               baseline=baseline, reduction=1e-7)
+        assert itr == ito and np.array_equal(xr, xo), (res_kind, baseline)
+
+
+def test_cfg1_cg_jacobi_matches_survey_probe():
+    """SURVEY.md probe: 5-pt Laplacian 316^2, CG + scalar Jacobi, tol 1e-8 -> 579 iterations"""
+    rp, ci, va = W.build("cfg1")
+    n = len(rp) - 1
+    b, x0 = np.ones((n, 1)), np.zeros((n, 1))
+    jac = ref.jacobi_generate(rp, ci, va, 1)
+    xo, ito, _ = orc_solve("cg", "f64", rp, ci, va, b, x0, 1, jac, max_iters=5000, reduction=1e-8)
+    assert ito == 579
+    xr, itr, _, _ = ref.solve("cg", rp, ci, va, b, x0, precond_max_bs=1, max_iters=5000,
+                              reduction=1e-8, exec_kind=1)
+    assert itr == 579
+    assert H.rel_err(xo, xr) < 1e-12

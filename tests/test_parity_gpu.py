@@ -63,7 +63,7 @@ def csr_case(rng, kind, vt, it):
 
 CSR_KINDS = ["ref_common", "empty_rows", "laplace_like", "wide_rows", "long_rows", "one_row",
              "all_empty"]
-EXACT_KINDS = {"ref_common", "empty_rows", "laplace_like", "all_empty"}
+EXACT_KINDS = {"ref_common", "empty_rows", "laplace_like", "all_empty"}  # LANES == 1, rows fit
 
 
 @pytest.mark.parametrize("kind", CSR_KINDS)
@@ -160,13 +160,14 @@ def test_ell_spmv(orc, cuda, kind, vt, it):
         y0 = H.dense(rng, n, nrhs, nrhs + 2, vt)
         a, b = both(orc, cuda, "ell_spmv_%s_%s" % (vt, it),
                     lambda: [n, m, width, stride, cols, vals, x, nrhs + 1, nrhs, y0.copy(), nrhs + 2])
-        if kind != "wide_small":
+        exact = width < 16  # wider ELL with few rows splits rows over lanes (tree order)
+        if exact:
             assert np.array_equal(a[-2], b[-2])
         assert rel_err(a[-2], b[-2]) <= R[vt] * 15
         a, b = both(orc, cuda, "ell_advanced_spmv_%s_%s" % (vt, it),
                     lambda: [n, m, width, stride, cols, vals, np.array([-1.5], VT[vt]), x, nrhs + 1,
                              nrhs, np.array([0.5], VT[vt]), y0.copy(), nrhs + 2])
-        if kind != "wide_small":
+        if exact:
             assert np.array_equal(a[-2], b[-2])
         assert rel_err(a[-2], b[-2]) <= R[vt] * 15
 
@@ -232,7 +233,9 @@ def test_dense_reductions(orc, cuda, vt, rows, cols, stride):
     rng = np.random.default_rng(5)
     x = H.dense(rng, rows, cols, stride, vt)
     y = H.dense(rng, rows, cols, stride + 1, vt)
-    tol = R[vt] * max(1.0, np.sqrt(rows) / 4)
+    # the ORACLE sums sequentially (error grows ~ n eps); the device tree sum is the more
+    # accurate of the two, so the bound is the sequential one
+    tol = R[vt] * max(1.0, rows / 64.0)
     for fname, args in [
         ("dense_compute_dot", lambda: [rows, cols, x, stride, y, stride + 1, np.zeros(cols, VT[vt])]),
         ("dense_compute_conj_dot", lambda: [rows, cols, x, stride, y, stride + 1,
