@@ -31,6 +31,7 @@
 // thread-per-(row,rhs) kernel with the reference's summation order.
 #pragma once
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -48,11 +49,11 @@ constexpr int kGatherUnroll = (kCap + kThreads - 1) / kThreads;  // 11
 
 template <typename I>
 __global__ void plan_kernel(const I* __restrict__ row_ptrs, int64_t num_rows, int64_t num_tiles,
-                            int64_t* __restrict__ tiles)
+                            int64_t tile_items, int64_t* __restrict__ tiles)
 {
     const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (t > num_tiles) return;
-    const int64_t d = t * (int64_t)kTile;
+    const int64_t d = t * tile_items;
     int64_t lo = 0, hi = num_rows;
     while (lo < hi) {
         const int64_t mid = (lo + hi) >> 1;
@@ -387,6 +388,210 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 }
 
 // --------------------------------------------------------------------------
+// warp-stream kernel: no block barriers at all
+// --------------------------------------------------------------------------
+// Every WARP walks its own sequence of small tiles (kWTile merge items, the same
+// 2*row + row_ptrs[row] coordinate, so <= kWTile/2 rows and < kWTile nonzeros plus
+// the last row).  Per tile the 32 lanes stream the slab with 256-bit loads
+// (LDG.E.NA.EFL2.256), gather b for 8 nonzeros each, park the products in the
+// warp's private shared-memory strip and then sum whole rows (LANES lanes per row,
+// LANES == 1: left to right = reference order).  The slab and the extents of the
+// NEXT tile are loaded into registers before the current tile is consumed, so the
+// only exposed latency is the gather itself, and 24 independent warps per SM
+// keep thousands of gathers in flight.  Nothing but __syncwarp is needed.
+constexpr int kWTile = 256;
+constexpr int kWCap = kWTile + 64 + 8;   // staged nonzeros per warp tile
+constexpr int kWarpsPerCta = 8;
+constexpr int kWCtasPerSm = 3;
+
+template <typename V, typename I, int LANES, bool ADVANCED, bool DOT>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, kWCtasPerSm)
+    warp_stream_kernel(const int64_t* __restrict__ tiles, int64_t num_tiles, int64_t nnz,
+                       const I* __restrict__ row_ptrs, const I* __restrict__ col_idxs,
+                       const V* __restrict__ values, const V* __restrict__ alpha_p,
+                       const V* __restrict__ b, int64_t b_stride, const V* __restrict__ beta_p,
+                       V* __restrict__ c, int64_t c_stride, DotArgs<V> dot)
+{
+    __shared__ __align__(16) V prod_all[kWarpsPerCta][kWCap];
+    __shared__ V red[32];
+    __shared__ bool is_last;
+    if (DOT && dot.ctl && dot.ctl[0] != 0) return;
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    V* prod = prod_all[warp];
+    V alpha = V(1), beta = V(0);
+    if (ADVANCED) {
+        alpha = *alpha_p;
+        beta = *beta_p;
+    }
+    const uint64_t pol_last = policy_evict_last();
+    const uint64_t pol_first = policy_evict_first();
+    const int64_t W = (int64_t)gridDim.x * kWarpsPerCta;
+    int64_t t = (int64_t)blockIdx.x * kWarpsPerCta + warp;
+
+    // extents of a tile: r0, p0, r1, p1 (all lanes hold them; empty past the end)
+    auto load_ext = [&](int64_t tt, int64_t (&e)[4]) {
+        if (tt < num_tiles) {
+            const longlong2 a = *reinterpret_cast<const longlong2*>(tiles + 2 * tt);
+            const longlong2 bb = *reinterpret_cast<const longlong2*>(tiles + 2 * tt + 2);
+            e[0] = a.x;
+            e[1] = a.y;
+            e[2] = bb.x;
+            e[3] = bb.y;
+        } else {
+            e[0] = e[1] = e[2] = e[3] = 0;
+        }
+    };
+    // first 8-group of the lane: elements a0 + 8*lane .. +7 (streaming, coalesced)
+    auto load_group = [&](int64_t base, I (&cols)[8], V (&vals)[8]) {
+        if (base + 8 <= nnz) {
+            ld_stream_x8(col_idxs + base, cols);
+            ld_stream_x8(values + base, vals);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const bool ok = base + k < nnz;
+                cols[k] = ok ? ld_stream(col_idxs + base + k, pol_first) : I(0);
+                vals[k] = ok ? ld_stream(values + base + k, pol_first) : V(0);
+            }
+        }
+    };
+
+    int64_t cur[4], nxt[4];
+    I ncols[8];
+    V nvals[8];
+    I nrp = 0;  // row pointer of row r0 + lane (first pass of the row phase)
+    load_ext(t, cur);
+    load_ext(t + W, nxt);
+    {
+        const int64_t a0 = cur[1] & ~int64_t(7);
+        if (cur[2] > cur[0]) {
+            if (a0 + 8 * lane < cur[3]) load_group(a0 + 8 * lane, ncols, nvals);
+            if (lane <= cur[2] - cur[0]) nrp = row_ptrs[cur[0] + lane];
+        }
+    }
+    V dot_acc = V(0);
+    for (; t < num_tiles; t += W) {
+        const int64_t r0 = cur[0], p0 = cur[1], r1 = cur[2], p1 = cur[3];
+        I cols[8];
+        V vals[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            cols[k] = ncols[k];
+            vals[k] = nvals[k];
+        }
+        const I rp_first = nrp;
+        // ---- prefetch the next tile's slab, row pointers and the extents after it
+        int64_t nn[4];
+        load_ext(t + 2 * W, nn);
+        if (nxt[2] > nxt[0]) {
+            const int64_t na0 = nxt[1] & ~int64_t(7);
+            if (na0 + 8 * lane < nxt[3]) load_group(na0 + 8 * lane, ncols, nvals);
+            if (lane <= nxt[2] - nxt[0]) nrp = row_ptrs[nxt[0] + lane];
+        }
+        if (r1 > r0) {
+            const int64_t a0 = p0 & ~int64_t(7);
+            const bool long_last = (p1 - a0) > kWCap;
+            const int64_t rl = r1 - 1;
+            const int64_t sl = long_last ? (int64_t)row_ptrs[rl] : p1;
+            const int64_t pend = long_last ? sl : p1;
+            const int64_t rows_end = long_last ? rl : r1;
+            // ---- gather + products for group `lane`, then (rarely) groups lane + 32
+            {
+                const int64_t base = a0 + 8 * lane;
+                V xs[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int64_t idx = base + k;
+                    xs[k] = V(0);
+                    if (idx >= p0 && idx < pend)
+                        xs[k] = ld_gather(b + (int64_t)cols[k] * b_stride, pol_last);
+                }
+                if (base < pend) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        prod[8 * lane + k] = ADVANCED ? (alpha * vals[k]) * xs[k] : vals[k] * xs[k];
+                }
+            }
+            for (int64_t base = a0 + 8 * (lane + 32); base < pend; base += 256) {
+                I c2[8];
+                V v2[8], xs[8];
+                load_group(base, c2, v2);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int64_t idx = base + k;
+                    xs[k] = V(0);
+                    if (idx < pend) xs[k] = ld_gather(b + (int64_t)c2[k] * b_stride, pol_last);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    prod[base - a0 + k] = ADVANCED ? (alpha * v2[k]) * xs[k] : v2[k] * xs[k];
+            }
+            __syncwarp();
+            // ---- row phase: LANES lanes per row, rows_per_pass = 32 / LANES
+            constexpr int kRpp = 32 / LANES;
+            const int sub = lane % LANES;
+            const int nrows = (int)(rows_end - r0);
+            for (int ps = 0; ps * kRpp < nrows; ++ps) {
+                const int rloc = ps * kRpp + lane / LANES;
+                const bool rv = rloc < nrows;
+                int64_t s = 0, e = 0;
+                if (LANES == 1 && ps == 0) {
+                    // row pointers of the first 33 rows came with the prefetch
+                    const I nxt_rp = __shfl_down_sync(0xffffffffu, rp_first, 1);
+                    s = rp_first;
+                    e = (lane == 31) ? (rv ? (int64_t)row_ptrs[r0 + 32] : 0) : (int64_t)nxt_rp;
+                } else if (rv) {
+                    s = row_ptrs[r0 + rloc];
+                    e = row_ptrs[r0 + rloc + 1];
+                }
+                if (!rv) s = e = 0;
+                V acc = V(0);
+                if (LANES == 1) {
+                    if (ADVANCED && rv && beta != V(0)) acc = c[(r0 + rloc) * c_stride] * beta;
+                    for (int64_t i = s; i < e; ++i) acc += prod[i - a0];
+                } else {
+                    for (int64_t i = s + sub; i < e; i += LANES) acc += prod[i - a0];
+#pragma unroll
+                    for (int o = LANES / 2; o > 0; o >>= 1)
+                        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    if (ADVANCED && rv && sub == 0 && beta != V(0))
+                        acc = c[(r0 + rloc) * c_stride] * beta + acc;
+                }
+                if (rv && sub == 0) {
+                    c[(r0 + rloc) * c_stride] = acc;
+                    if (DOT) dot_acc += b[(r0 + rloc) * b_stride] * acc;
+                }
+            }
+            // ---- a last row that does not fit the strip: the whole warp sums it
+            if (long_last) {
+                V acc = V(0);
+                for (int64_t i = sl + lane; i < p1; i += 32) {
+                    const I col = ld_stream(col_idxs + i, pol_first);
+                    const V val = ld_stream(values + i, pol_first);
+                    const V x = ld_gather(b + (int64_t)col * b_stride, pol_last);
+                    acc += ADVANCED ? (alpha * val) * x : val * x;
+                }
+                acc = warp_sum(acc);
+                if (lane == 0) {
+                    if (ADVANCED && beta != V(0)) acc = c[rl * c_stride] * beta + acc;
+                    c[rl * c_stride] = acc;
+                    if (DOT) dot_acc += b[rl * b_stride] * acc;
+                }
+            }
+            __syncwarp();
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            cur[q] = nxt[q];
+            nxt[q] = nn[q];
+        }
+    }
+    if (DOT) dot_epilogue(dot_acc, dot, red, &is_last);
+}
+
+// --------------------------------------------------------------------------
 // fallback for unaligned base pointers: one tile per CTA, ordinary loads
 // --------------------------------------------------------------------------
 template <typename V, typename I, int LANES, bool ADVANCED, bool DOT>
@@ -481,6 +686,10 @@ inline int64_t num_tiles_for(int64_t num_rows, int64_t nnz)
 {
     return ceildiv(kRowW * num_rows + nnz, kTile);
 }
+inline int64_t num_wtiles_for(int64_t num_rows, int64_t nnz)
+{
+    return ceildiv(kRowW * num_rows + nnz, kWTile);
+}
 
 }  // namespace csr
 }  // namespace b200
@@ -490,6 +699,8 @@ struct b200_csr_plan {
     int64_t nnz = 0;
     int64_t num_tiles = 0;
     int64_t* tiles = nullptr;  // device, 2 * (num_tiles + 1): (first row, first nonzero)
+    int64_t num_wtiles = 0;
+    int64_t* wtiles = nullptr;  // same for the warp-stream kernel's kWTile-item tiles
     int lanes = 1;
     int device = 0;
 };
@@ -499,11 +710,12 @@ namespace csr {
 
 template <typename I>
 b200_status fill_plan(b200_ctx* ctx, int64_t num_rows, int64_t nnz, const I* row_ptrs,
-                      int64_t num_tiles, int64_t* tiles)
+                      int64_t num_tiles, int64_t* tiles, int64_t tile_items = kTile)
 {
     const int block = 256;
     const int grid = (int)ceildiv(num_tiles + 1, block);
-    plan_kernel<I><<<grid, block, 0, ctx->stream>>>(row_ptrs, num_rows, num_tiles, tiles);
+    plan_kernel<I><<<grid, block, 0, ctx->stream>>>(row_ptrs, num_rows, num_tiles, tile_items,
+                                                    tiles);
     B200_LAUNCH_CHECK(ctx);
     return B200_OK;
 }
@@ -522,27 +734,67 @@ b200_status set_smem(K kernel, size_t bytes)
     return B200_OK;
 }
 
+// kernel variants
+enum Variant { kSlab = 0, kTma = 1, kWarp = 2 };
+
+inline Variant pick_variant(const void* col_idxs, const void* values)
+{
+    const uintptr_t a = (uintptr_t)col_idxs | (uintptr_t)values;
+    static const char* env = getenv("B200_CSR_KERNEL");
+    Variant want = kWarp;
+    if (env && !strcmp(env, "tma")) want = kTma;
+    if (env && !strcmp(env, "slab")) want = kSlab;
+    if (want == kWarp && (a & 31u)) want = kSlab;  // 256-bit loads need 32-byte alignment
+    if (want == kTma && (a & 15u)) want = kSlab;   // bulk copies need 16-byte alignment
+    return want;
+}
+
+// tile array / tile count a variant works on
+inline int64_t variant_tiles(Variant v, int64_t num_rows, int64_t nnz)
+{
+    return v == kWarp ? num_wtiles_for(num_rows, nnz) : num_tiles_for(num_rows, nnz);
+}
+
+// number of CTAs a launch uses (the size of the fused-dot partials array)
+inline int grid_size(const b200_ctx* ctx, Variant v, int64_t num_tiles)
+{
+    if (v == kSlab) return (int)num_tiles;
+    if (v == kTma) {
+        const int64_t cap = (int64_t)ctx->num_sms * kCtasPerSm;
+        return (int)(num_tiles < cap ? num_tiles : cap);
+    }
+    const int64_t need = ceildiv(num_tiles, kWarpsPerCta);
+    const int64_t cap = (int64_t)ctx->num_sms * kWCtasPerSm;
+    return (int)(need < cap ? need : cap);
+}
+inline int max_grid_size(const b200_ctx* ctx) { return ctx->num_sms * 4; }
+
 template <typename V, typename I, int LANES, bool ADVANCED, bool DOT>
-b200_status launch_one(b200_ctx* ctx, bool tma, int64_t num_tiles, const int64_t* tiles,
+b200_status launch_one(b200_ctx* ctx, Variant v, int64_t num_tiles, const int64_t* tiles,
                        int64_t nnz, const I* row_ptrs, const I* col_idxs, const V* values,
                        const V* alpha, const V* b, int64_t b_stride, const V* beta, V* c,
                        int64_t c_stride, DotArgs<V> dot, int grid)
 {
-    if (tma) {
+    if (v == kTma) {
         constexpr size_t smem = StageLayout<V, I>::bytes * kStages;
         auto k = slab_tma_kernel<V, I, LANES, ADVANCED, DOT>;
         b200_status st = set_smem(k, smem);
         if (st != B200_OK) return st;
+        k<<<grid, kThreads, smem, ctx->stream>>>(tiles, num_tiles, nnz, row_ptrs, col_idxs, values,
+                                                 alpha, b, b_stride, beta, c, c_stride, dot);
+    } else if (v == kWarp) {
+        auto k = warp_stream_kernel<V, I, LANES, ADVANCED, DOT>;
         static bool dbg = getenv("B200_DEBUG") != nullptr;
         if (dbg) {
             int nb = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, kThreads, smem);
-            fprintf(stderr, "[b200] slab_tma_kernel: %d CTAs/SM, smem %zu B, grid %d, tiles %lld\n",
-                    nb, smem, grid, (long long)num_tiles);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, kWarpsPerCta * 32, 0);
+            fprintf(stderr, "[b200] warp_stream_kernel: %d CTAs/SM, grid %d, tiles %lld\n", nb, grid,
+                    (long long)num_tiles);
             dbg = false;
         }
-        k<<<grid, kThreads, smem, ctx->stream>>>(tiles, num_tiles, nnz, row_ptrs, col_idxs, values,
-                                                 alpha, b, b_stride, beta, c, c_stride, dot);
+        k<<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(tiles, num_tiles, nnz, row_ptrs, col_idxs,
+                                                       values, alpha, b, b_stride, beta, c, c_stride,
+                                                       dot);
     } else {
         slab_kernel<V, I, LANES, ADVANCED, DOT><<<(unsigned)num_tiles, kThreads, 0, ctx->stream>>>(
             tiles, nnz, row_ptrs, col_idxs, values, alpha, b, b_stride, beta, c, c_stride, dot);
@@ -551,24 +803,16 @@ b200_status launch_one(b200_ctx* ctx, bool tma, int64_t num_tiles, const int64_t
     return B200_OK;
 }
 
-// number of CTAs a launch will use (the size of the fused-dot partials array)
-inline int grid_size(const b200_ctx* ctx, bool tma, int64_t num_tiles)
-{
-    if (!tma) return (int)num_tiles;
-    const int64_t cap = (int64_t)ctx->num_sms * kCtasPerSm;
-    return (int)(num_tiles < cap ? num_tiles : cap);
-}
-
 template <typename V, typename I, bool ADVANCED, bool DOT>
-b200_status launch_slab(b200_ctx* ctx, int lanes, bool tma, int64_t num_tiles,
+b200_status launch_slab(b200_ctx* ctx, int lanes, Variant v, int64_t num_tiles,
                         const int64_t* tiles, int64_t nnz, const I* row_ptrs, const I* col_idxs,
                         const V* values, const V* alpha, const V* b, int64_t b_stride,
                         const V* beta, V* c, int64_t c_stride, DotArgs<V> dot = DotArgs<V>{})
 {
     if (num_tiles <= 0) return B200_OK;
-    const int grid = grid_size(ctx, tma, num_tiles);
+    const int grid = grid_size(ctx, v, num_tiles);
 #define B200_SLAB(L)                                                                           \
-    return launch_one<V, I, L, ADVANCED, DOT>(ctx, tma, num_tiles, tiles, nnz, row_ptrs,       \
+    return launch_one<V, I, L, ADVANCED, DOT>(ctx, v, num_tiles, tiles, nnz, row_ptrs,         \
                                               col_idxs, values, alpha, b, b_stride, beta, c,   \
                                               c_stride, dot, grid)
     switch (lanes) {
@@ -580,11 +824,6 @@ b200_status launch_slab(b200_ctx* ctx, int lanes, bool tma, int64_t num_tiles,
     default: B200_SLAB(32);
     }
 #undef B200_SLAB
-}
-
-inline bool can_tma(const void* col_idxs, const void* values)
-{
-    return ((((uintptr_t)col_idxs) | ((uintptr_t)values)) & 15u) == 0;
 }
 
 }  // namespace csr

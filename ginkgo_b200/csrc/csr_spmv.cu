@@ -50,13 +50,14 @@ b200_status spmv_impl(b200_ctx* ctx, const b200_csr_plan* plan, int64_t num_rows
             last = (const void*)b;
         }
     }
-    const int64_t num_tiles = num_tiles_for(num_rows, nnz);
+    const Variant variant = pick_variant(col_idxs, values);
+    const int64_t num_tiles = variant_tiles(variant, num_rows, nnz);
     const int64_t* tiles = nullptr;
     int lanes;
     if (plan) {
         B200_REQUIRE(plan->num_rows == num_rows && plan->nnz == nnz,
                      "plan does not match the matrix");
-        tiles = plan->tiles;
+        tiles = variant == kWarp ? plan->wtiles : plan->tiles;
         lanes = plan->lanes;
     } else {
         int64_t* tr = (int64_t*)ctx->scratch(2 * (num_tiles + 1) * sizeof(int64_t));
@@ -64,14 +65,15 @@ b200_status spmv_impl(b200_ctx* ctx, const b200_csr_plan* plan, int64_t num_rows
             set_error("scratch allocation failed");
             return B200_ERR_ALLOC;
         }
-        b200_status st = fill_plan<I>(ctx, num_rows, nnz, row_ptrs, num_tiles, tr);
+        b200_status st = fill_plan<I>(ctx, num_rows, nnz, row_ptrs, num_tiles, tr,
+                                      variant == kWarp ? kWTile : kTile);
         if (st != B200_OK) return st;
         tiles = tr;
         lanes = pick_lanes(num_rows, nnz);
     }
-    return launch_slab<V, I, ADVANCED, false>(ctx, lanes, can_tma(col_idxs, values), num_tiles,
-                                              tiles, nnz, row_ptrs, col_idxs, values, alpha, b,
-                                              b_stride, beta, c, c_stride);
+    return launch_slab<V, I, ADVANCED, false>(ctx, lanes, variant, num_tiles, tiles, nnz, row_ptrs,
+                                              col_idxs, values, alpha, b, b_stride, beta, c,
+                                              c_stride);
 }
 
 template <typename I>
@@ -84,16 +86,21 @@ b200_status plan_create(b200_ctx* ctx, int64_t num_rows, int64_t nnz, const I* r
     p->num_rows = num_rows;
     p->nnz = nnz;
     p->num_tiles = num_tiles_for(num_rows, nnz);
+    p->num_wtiles = num_wtiles_for(num_rows, nnz);
     p->lanes = pick_lanes(num_rows, nnz);
     p->device = ctx->device;
-    cudaError_t e = cudaMalloc((void**)&p->tiles, 2 * (p->num_tiles + 1) * sizeof(int64_t));
+    cudaError_t e = cudaMalloc((void**)&p->tiles,
+                               2 * (p->num_tiles + p->num_wtiles + 2) * sizeof(int64_t));
     if (e != cudaSuccess) {
         delete p;
         set_error("cudaMalloc failed for csr plan: %s", cudaGetErrorString(e));
         return B200_ERR_ALLOC;
     }
+    p->wtiles = p->tiles + 2 * (p->num_tiles + 1);
     if (num_rows > 0) {
-        b200_status st = fill_plan<I>(ctx, num_rows, nnz, row_ptrs, p->num_tiles, p->tiles);
+        b200_status st = fill_plan<I>(ctx, num_rows, nnz, row_ptrs, p->num_tiles, p->tiles, kTile);
+        if (st == B200_OK)
+            st = fill_plan<I>(ctx, num_rows, nnz, row_ptrs, p->num_wtiles, p->wtiles, kWTile);
         if (st != B200_OK) {
             cudaFree(p->tiles);
             delete p;
@@ -265,7 +272,8 @@ b200_status apply(b200_ctx* ctx, const b200_coo_plan* plan, int mode, int64_t nu
     } else {
         // one scratch block: [ones (16 B) | row_ptrs | csr tiles]; the CSR call below
         // must not re-use ctx->scratch, so the tile array is carved out here too
-        const int64_t num_tiles = csr::num_tiles_for(num_rows, nnz);
+        const csr::Variant variant = csr::pick_variant(col_idxs, values);
+        const int64_t num_tiles = csr::variant_tiles(variant, num_rows, nnz);
         const size_t off_ptrs = 16;
         const size_t off_tiles = (off_ptrs + (num_rows + 1) * sizeof(I) + 15) & ~size_t(15);
         const size_t total = off_tiles + 2 * (num_tiles + 1) * sizeof(int64_t);
@@ -279,9 +287,10 @@ b200_status apply(b200_ctx* ctx, const b200_coo_plan* plan, int mode, int64_t nu
         b200_status st = idxs_to_ptrs<I>(ctx, row_idxs, nnz, num_rows, rp);
         if (st != B200_OK) return st;
         if (num_rhs == 1) {
-            st = csr::fill_plan<I>(ctx, num_rows, nnz, rp, num_tiles, tiles);
+            st = csr::fill_plan<I>(ctx, num_rows, nnz, rp, num_tiles, tiles,
+                                   variant == csr::kWarp ? csr::kWTile : csr::kTile);
             if (st != B200_OK) return st;
-            const bool tma = csr::can_tma(col_idxs, values);
+            const csr::Variant tma = variant;
             const int lanes = csr::pick_lanes(num_rows, nnz);
             if (mode == 0)
                 return csr::launch_slab<V, I, false, false>(ctx, lanes, tma, num_tiles, tiles, nnz,

@@ -235,7 +235,7 @@ void b200_graph_destroy(b200_graph* graph)
     /* elements of `work` (value type) the fused kernels need for a matrix of this size */       \
     int64_t b200_cg_fused_work_size_##V(const b200_ctx* ctx)                                     \
     {                                                                                            \
-        return (int64_t)ctx->num_sms * 3 + 2 * (int64_t)ctx->num_sms * 4 + 64;                   \
+        return (int64_t)ctx->num_sms * 4 + 2 * (int64_t)ctx->num_sms * 4 + 64;                   \
     }                                                                                            \
     b200_status b200_cg_fused_init_##V(                                                          \
         b200_ctx* ctx, int64_t n, const VT* r, VT* z, VT* p, VT* q, const VT* inv_diag, VT* sc,  \
@@ -252,7 +252,7 @@ void b200_graph_destroy(b200_graph* graph)
         const int grid = b200::fcg::ew_grid(ctx, n);                                             \
         b200::fcg::step_xr_kernel<VT, true><<<grid, b200::fcg::kThreads, 0, ctx->stream>>>(      \
             n, nullptr, const_cast<VT*>(r), p, q, z, inv_diag, sc, ctl,                          \
-            work + (int64_t)ctx->num_sms * 3, ctx->counters + 2, finalize, baseline,             \
+            work + (int64_t)ctx->num_sms * 4, ctx->counters + 2, finalize, baseline,             \
             reduction_factor);                                                                   \
         B200_LAUNCH_CHECK(ctx);                                                                  \
         return B200_OK;                                                                          \
@@ -272,7 +272,7 @@ void b200_graph_destroy(b200_graph* graph)
     {                                                                                            \
         const int grid = b200::fcg::ew_grid(ctx, n);                                             \
         b200::fcg::step_xr_kernel<VT, false><<<grid, b200::fcg::kThreads, 0, ctx->stream>>>(     \
-            n, x, r, p, q, z, inv_diag, sc, ctl, work + (int64_t)ctx->num_sms * 3,               \
+            n, x, r, p, q, z, inv_diag, sc, ctl, work + (int64_t)ctx->num_sms * 4,               \
             ctx->counters + 2, finalize, 0, VT(0));                                              \
         B200_LAUNCH_CHECK(ctx);                                                                  \
         return B200_OK;                                                                          \
@@ -303,12 +303,14 @@ B200_DEF_FCG(f32, float)
     {                                                                                            \
         B200_REQUIRE(ctx && plan && dot_out && work, "null argument (a plan is required)");      \
         B200_REQUIRE(plan->num_rows == num_rows && plan->nnz == nnz, "plan does not match");     \
-        B200_REQUIRE(b200::csr::can_tma(col_idxs, values),                                       \
-                     "col_idxs/values must be 16-byte aligned");                                 \
+        const b200::csr::Variant v = b200::csr::pick_variant(col_idxs, values);                  \
+        B200_REQUIRE(v != b200::csr::kSlab, "col_idxs/values must be 32-byte aligned");          \
         b200::csr::DotArgs<VT> dot{work, ctx->counters + 1, dot_out, ctl};                       \
+        const bool w = v == b200::csr::kWarp;                                                    \
         return b200::csr::launch_slab<VT, IT, false, true>(                                      \
-            ctx, plan->lanes, true, plan->num_tiles, plan->tiles, nnz, row_ptrs, col_idxs,       \
-            values, nullptr, b, 1, nullptr, c, 1, dot);                                          \
+            ctx, plan->lanes, v, w ? plan->num_wtiles : plan->num_tiles,                         \
+            w ? plan->wtiles : plan->tiles, nnz, row_ptrs, col_idxs, values, nullptr, b, 1,      \
+            nullptr, c, 1, dot);                                                                 \
     }
 
 B200_DEF_SPMV_DOT(f64, double, i32, int32_t)

@@ -407,6 +407,38 @@ B200_DECL_EXTRACT_DIAG(f64, double, i64, int64_t)
 B200_DECL_EXTRACT_DIAG(f32, float, i32, int32_t)
 B200_DECL_EXTRACT_DIAG(f32, float, i64, int64_t)
 
+/* ---------------------------------------------------------------------------
+ * Multi-GPU (one process per GPU, 1-D row partition, NCCL over NVLink/NVSwitch):
+ * the B200 replacement of the reference's MPI layer on this path --
+ * experimental::distributed::Matrix::apply halo gather (core/distributed/matrix.cpp:450-509,
+ * row_gatherer.cpp) and distributed::Vector reductions (core/distributed/vector.cpp:510-534).
+ * All calls are enqueued on the context's stream and can be captured in CUDA graphs.
+ * Extended vectors: [n_local owned entries | n_ghost received entries].
+ * ------------------------------------------------------------------------- */
+typedef struct b200_comm b200_comm;
+typedef struct b200_halo b200_halo;
+b200_status b200_comm_get_unique_id(uint8_t* id128); /* rank 0, then broadcast the 128 bytes */
+b200_status b200_comm_create(b200_ctx* ctx, const uint8_t* id128, int32_t rank, int32_t nranks,
+                             b200_comm** out);
+void b200_comm_destroy(b200_comm* comm);
+int32_t b200_comm_rank(const b200_comm* comm);
+int32_t b200_comm_size(const b200_comm* comm);
+b200_status b200_halo_create(b200_ctx* ctx, int32_t nranks, int64_t n_local, int64_t n_ghost,
+                             const int64_t* send_counts, const int64_t* recv_counts,
+                             const int32_t* send_idx_dev, int32_t value_bytes, b200_halo** out);
+void b200_halo_destroy(b200_halo* halo);
+int64_t b200_halo_num_ghost(const b200_halo* halo);
+int64_t b200_halo_num_send(const b200_halo* halo);
+#define B200_DECL_COMM(V, VT)                                                                  \
+    b200_status b200_comm_allreduce_sum_##V(b200_ctx* ctx, b200_comm* comm, VT* buf,           \
+                                            int64_t count);                                    \
+    b200_status b200_comm_allgather_##V(b200_ctx* ctx, b200_comm* comm, const VT* send,        \
+                                        VT* recv, int64_t count_per_rank);                     \
+    b200_status b200_halo_exchange_##V(b200_ctx* ctx, b200_comm* comm, b200_halo* halo,        \
+                                       VT* x_ext, const int32_t* ctl);
+B200_DECL_COMM(f64, double)
+B200_DECL_COMM(f32, float)
+
 #ifdef __cplusplus
 }
 #endif
