@@ -142,32 +142,16 @@ def run_reference_arm(args, rank):
 def run_gpu_arm(args, rank, world):
     import torch
     import torch.distributed as dist
-    from ginkgo_b200.api import B200Executor, Csr, Dense
+    from ginkgo_b200 import api
+    from ginkgo_b200 import distributed as D
 
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    ex = B200Executor.create(local)
+    ex = api.HostExecutor(local)  # C++ host layer (gko_b200.hpp) over the C ABI
     dev = ex.device
-
-    r0, r1 = rank * N_ROWS // world, (rank + 1) * N_ROWS // world
-    with torch.cuda.stream(ex.stream):
-        rp, ci, va = W.build(CFG, r0, r1, xp="torch", device=dev)
-        x_full = W.vector(N_ROWS, xp="torch", device=dev)
-        x_loc = x_full[r0:r1].clone()
-    A = Csr(ex, (r1 - r0, N_ROWS), va, ci, rp)
-    A.plan()
-    nnz_loc = va.numel()
-    xg = Dense(ex, x_full.reshape(-1, 1))
-    y = Dense.create(ex, (r1 - r0, 1))
-    ex.synchronize()
-
-    def step():
-        if world > 1:
-            with torch.cuda.stream(ex.stream):
-                dist.all_gather_into_tensor(x_full, x_loc)
-        A.apply(xg, y)
+    hl = api._host()
 
     def timed(fn, n):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -186,57 +170,87 @@ def run_gpu_arm(args, rank, world):
             ms = float(t.item())
         return ms
 
+    # ---------------------------------------------------------------- SpMV, cfg2 (headline)
+    offs = D.uniform_offsets(N_ROWS, world)
+    r0, r1 = offs[rank], offs[rank + 1]
+    with torch.cuda.stream(ex.stream):
+        rp, ci, va = W.build(CFG, r0, r1, xp="torch", device=dev)
+        x_full = W.vector(N_ROWS, xp="torch", device=dev)
+    nnz_loc = va.numel()
+    nnz_total = N_ROWS * PER_ROW
+    if world == 1:
+        A = api.host_csr(ex, (N_ROWS, N_ROWS), va, ci, rp)
+        xg = api.host_dense(ex, x_full)
+        y_t = torch.empty(N_ROWS, dtype=torch.float64, device=dev)
+        yg = api.host_dense(ex, y_t)
+
+        def step():
+            api._hcheck(hl.gkob_apply(A.h, xg.h, yg.h))
+        kernel_step = step
+    else:
+        A = api.DistMatrix(ex, offs, rp, ci, va)
+        with torch.cuda.stream(ex.stream):
+            x_ext = torch.zeros(A.n_local + A.n_ghost, dtype=torch.float64, device=dev)
+            x_ext[:A.n_local] = x_full[r0:r1]
+            y_t = torch.empty(A.n_local, dtype=torch.float64, device=dev)
+        Aloc = api.host_csr(ex, (A.n_local, A.n_local + A.n_ghost), va, A.col_idxs, rp)
+        xe_h, y_h = api.host_dense(ex, x_ext), api.host_dense(ex, y_t)
+
+        def step():  # halo exchange (referenced remote entries only) + local SpMV
+            A.apply(x_ext, y_t)
+
+        def kernel_step():
+            api._hcheck(hl.gkob_apply(Aloc.h, xe_h.h, y_h.h))
+    ex.synchronize()
     for _ in range(max(args.warmup, 3)):
         step()
     with ClockSampler(local) as cs:
         l0 = ex.launch_count()
         ms_total = timed(step, args.steps)
         launches = ex.launch_count() - l0
-        # kernel-only time of the dominant kernel (no collective), same stream, CUDA events
         for _ in range(3):
-            A.apply(xg, y)
-        ms_kernel = timed(lambda: A.apply(xg, y), args.steps) / args.steps
+            kernel_step()
+        ms_kernel = timed(kernel_step, args.steps) / args.steps  # dominant kernel alone
     ms_step = ms_total / args.steps
-    nnz_total = N_ROWS * PER_ROW
     value = 2.0 * nnz_total / (ms_step * 1e-3) / 1e9
 
-    # end to end through the public API with host buffers: H2D x, SpMV, D2H y
-    xh = Dense(None, x_full.cpu().pin_memory().reshape(-1, 1))
-    yh = Dense(None, torch.empty((r1 - r0, 1), dtype=torch.float64).pin_memory())
+    # ----------------------------- end to end with HOST buffers: H2D x, SpMV, D2H y
+    n_e2e = max(5, min(args.steps, 50))
     if world == 1:
-        def e2e_step():
-            A.apply(xh, yh)
-        for _ in range(3):
-            e2e_step()
-        n_e2e = max(5, min(args.steps, 50))
-        ms_e2e = timed(e2e_step, n_e2e) / n_e2e
-        e2e = {"value": 2.0 * nnz_total / (ms_e2e * 1e-3) / 1e9, "unit": "GFLOP/s",
-               "h2d_bytes_per_step": N_ROWS * 8, "d2h_bytes_per_step": (r1 - r0) * 8,
-               "ms_per_step": ms_e2e}
-    else:
-        xl_h = Dense(None, x_loc.cpu().pin_memory().reshape(-1, 1))
+        xh = x_full.cpu().pin_memory()
+        yh = torch.empty(N_ROWS, dtype=torch.float64).pin_memory()
 
         def e2e_step():
             with torch.cuda.stream(ex.stream):
-                x_loc.copy_(xl_h.values.reshape(-1), non_blocking=True)
-                dist.all_gather_into_tensor(x_full, x_loc)
-            A.apply(xg, y)
+                x_full.copy_(xh, non_blocking=True)
+            step()
             with torch.cuda.stream(ex.stream):
-                yh.values.copy_(y.values, non_blocking=True)
-        for _ in range(3):
-            e2e_step()
-        n_e2e = max(5, min(args.steps, 50))
-        ms_e2e = timed(e2e_step, n_e2e) / n_e2e
-        e2e = {"value": 2.0 * nnz_total / (ms_e2e * 1e-3) / 1e9, "unit": "GFLOP/s",
-               "h2d_bytes_per_step": (r1 - r0) * 8 * world, "d2h_bytes_per_step": (r1 - r0) * 8 * world,
-               "ms_per_step": ms_e2e}
+                yh.copy_(y_t, non_blocking=True)
+        h2d, d2h = N_ROWS * 8, N_ROWS * 8
+    else:
+        xh = x_full[r0:r1].cpu().pin_memory()
+        yh = torch.empty(A.n_local, dtype=torch.float64).pin_memory()
+
+        def e2e_step():
+            with torch.cuda.stream(ex.stream):
+                x_ext[:A.n_local].copy_(xh, non_blocking=True)
+            step()
+            with torch.cuda.stream(ex.stream):
+                yh.copy_(y_t, non_blocking=True)
+        h2d, d2h = N_ROWS * 8, N_ROWS * 8  # summed over ranks
+    for _ in range(3):
+        e2e_step()
+    ms_e2e = timed(e2e_step, n_e2e) / n_e2e
+    e2e = {"value": 2.0 * nnz_total / (ms_e2e * 1e-3) / 1e9, "unit": "GFLOP/s",
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e}
 
     peak, peak_src = peaks()
-    alg_bytes = W.spmv_bytes(r1 - r0, N_ROWS, nnz_loc)
+    ncols_loc = N_ROWS if world == 1 else A.n_local + A.n_ghost
+    alg_bytes = W.spmv_bytes(r1 - r0, ncols_loc, nnz_loc)
     achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "kernel": "b200::csr::slab_kernel<double,int,1,false,true>",
+                "kernel": "b200::csr::warp_stream_kernel<double,int,1,false,false>",
                 "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_kernel}
     prof = os.path.join(ROOT, "profiles", "r01_csr_spmv_cfg2.json")
     if os.path.exists(prof):
@@ -244,6 +258,11 @@ def run_gpu_arm(args, rank, world):
             roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
         except Exception:
             pass
+    del A, rp, ci, va, x_full
+    torch.cuda.empty_cache()
+
+    # ------------------------------------------------------------------------------ CG
+    cg = run_cg(args, rank, world, ex, dev, timed_events=True)
 
     if rank != 0:
         return
@@ -256,14 +275,113 @@ def run_gpu_arm(args, rank, world):
         "config": {"workload": "%s: CSR SpMV fp64/int32, random n=%d nnz=%d (15 distinct uniform "
                                "cols/row), workloads.py seed 42" % (CFG, N_ROWS, nnz_total),
                    "parallelism": "1-D row split over %d GPU(s)%s" %
-                                  (world, ", NCCL all-gather of x per step" if world > 1 else ""),
+                                  (world, ", NCCL halo exchange of the referenced x entries per "
+                                          "step" if world > 1 else ""),
                    "l2": "inputs (2.0 GB/step) exceed the 126 MB L2; no flush between steps",
                    "gbs": alg_bytes * world / (ms_step * 1e-3) / 1e9},
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": cs.summary(),
+        "cg": cg,
     }
     if cpu:
         line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line))
+
+
+def run_cg(args, rank, world, ex, dev, timed_events=True):
+    """CG iterations/s: N == 1 -> BASELINE configs[2] (7-pt Laplacian 200^3 + scalar Jacobi, to
+    1e-8) AND configs[4] (400^3, 200 iterations); N > 1 -> configs[4] row-sharded (z-slabs)."""
+    import torch
+    import torch.distributed as dist
+    from ginkgo_b200 import api
+    from ginkgo_b200 import distributed as D
+    out = {}
+
+    def wall(fn):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ex.stream)
+        fn()
+        e1.record(ex.stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    if world == 1 and not args.no_cg:
+        g = W.CONFIGS["cfg3"]["grid"]
+        n = g ** 3
+        with torch.cuda.stream(ex.stream):
+            rp, ci, va = W.laplace(g, 3, xp="torch", device=dev)
+            b = torch.ones(n, dtype=torch.float64, device=dev)
+            x = torch.zeros(n, dtype=torch.float64, device=dev)
+        A = api.host_csr(ex, (n, n), va, ci, rp)
+        s = api.HostSolver(ex, "cg", A, precond_max_bs=1, max_iters=5000, reduction=1e-8, fused=True)
+        bd, xd = api.host_dense(ex, b), api.host_dense(ex, x)
+        s.apply(bd, xd)  # warm-up solve (builds the plan + graph)
+        x.zero_()
+        ms = wall(lambda: s.apply(bd, xd))
+        # true relative residual
+        r = b.clone()
+        rd = api.host_dense(ex, r)
+        one = api.host_dense(ex, torch.ones(1, dtype=torch.float64, device=dev))
+        neg = api.host_dense(ex, -torch.ones(1, dtype=torch.float64, device=dev))
+        api._hcheck(api._host().gkob_apply4(A.h, neg.h, xd.h, one.h, rd.h))
+        ex.synchronize()
+        nnz = va.numel()
+        bytes_it = nnz * 12 + (n + 1) * 4 + 13 * n * 8
+        out["cfg3"] = {"workload": "cfg3: CG + scalar Jacobi fp64, 7-pt Laplacian 200^3, b=1, "
+                                   "ResidualNorm(rhs_norm) 1e-8", "iterations": s.num_iterations,
+                       "ms": ms, "iters_per_s": s.num_iterations / (ms * 1e-3),
+                       "true_rel_residual": (r.norm() / b.norm()).item(),
+                       "fused": s.used_fused, "stop_status": s.stop_status,
+                       "algorithmic_gbs": bytes_it * s.num_iterations / (ms * 1e-3) / 1e9}
+        del A, s, rp, ci, va, b, x, r
+        torch.cuda.empty_cache()
+    if args.no_cg:
+        return out
+    # configs[4]: 400^3, fixed 200 iterations (reduction 0 never triggers), strong scaling
+    g = W.CONFIGS["cfg5"]["grid"] if not args.small_cg else 160
+    n = g ** 3
+    offs = [p * g // world * g * g for p in range(world + 1)]  # whole z-slabs per rank
+    r0, r1 = offs[rank], offs[rank + 1]
+    iters = 200
+    with torch.cuda.stream(ex.stream):
+        rp, ci, va = W.laplace(g, 3, r0, r1, xp="torch", device=dev)
+        b = torch.ones(r1 - r0, dtype=torch.float64, device=dev)
+        x = torch.zeros(r1 - r0, dtype=torch.float64, device=dev)
+    nnz_loc = va.numel()
+    if world == 1:
+        A = api.host_csr(ex, (n, n), va, ci, rp)
+        s = api.HostSolver(ex, "cg", A, max_iters=iters, reduction=1e-300, fused=True, check_every=20)
+        bd, xd = api.host_dense(ex, b), api.host_dense(ex, x)
+        s.apply(bd, xd)
+        x.zero_()
+        ms = wall(lambda: s.apply(bd, xd))
+        done, ghosts = s.num_iterations, 0
+    else:
+        A = api.DistMatrix(ex, offs, rp, ci, va)
+        A.make_cg(scalar_jacobi=False, max_iters=iters, reduction=1e-300, check_every=20)
+        A.cg_apply(b, x)
+        x.zero_()
+        res = {}
+        ms = wall(lambda: res.update(it=A.cg_apply(b, x)[0]))
+        done, ghosts = res["it"], A.n_ghost
+    nnz_t = torch.tensor([nnz_loc], device=dev, dtype=torch.int64)
+    if world > 1:
+        dist.all_reduce(nnz_t)
+    nnz = int(nnz_t.item())
+    bytes_it = nnz * 12 + (n + world) * 4 + 13 * n * 8
+    out["cfg5"] = {"workload": "cfg5: CG fp64 (unpreconditioned), 7-pt Laplacian %d^3 n=%d nnz=%d, "
+                               "b=1, %d iterations, rows split in z-slabs over %d GPU(s)"
+                               % (g, n, nnz, iters, world), "iterations": done, "ms": ms,
+                   "iters_per_s": done / (ms * 1e-3), "ghosts_per_rank": ghosts,
+                   "algorithmic_gbs": bytes_it * done / (ms * 1e-3) / 1e9}
+    return out
 
 
 def main():
@@ -273,6 +391,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cg", action="store_true", help="skip the CG legs")
+    ap.add_argument("--small-cg", action="store_true", help="160^3 instead of 400^3 for the cfg5 leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

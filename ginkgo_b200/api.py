@@ -324,3 +324,81 @@ class HostSolver:
                                                                 ctypes.byref(st), ctypes.byref(fu)))
         self.num_iterations, self.stop_status, self.used_fused = it.value, st.value, bool(fu.value)
         return x
+
+
+# ---------------------------------------------------------------------------------------------
+# Multi-GPU: row-partitioned Csr + fused distributed CG (C++: host/gko_b200_dist.hpp)
+# ---------------------------------------------------------------------------------------------
+class DistMatrix:
+    """experimental::distributed::Matrix analogue.  Each rank passes ITS rows (row_ptrs local,
+    col_idxs GLOBAL, values) and the partition offsets; set-up uses torch.distributed
+    (ginkgo_b200/distributed.py), the per-apply halo exchange uses the library's own NCCL
+    communicator on the executor's stream."""
+
+    def __init__(self, exec_, offsets, row_ptrs, col_idxs_global, values, group=None):
+        import torch.distributed as dist
+        from . import distributed as D
+        h = _host()
+        vp, ll, i = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int
+        h.gkob_dist_unique_id.restype, h.gkob_dist_unique_id.argtypes = i, [vp]
+        h.gkob_dist_matrix_create_f64_i32.restype = vp
+        h.gkob_dist_matrix_create_f64_i32.argtypes = [vp, vp, i, i, ll, ll, ll, vp, vp, vp, vp, vp, vp]
+        h.gkob_dist_spmv_f64.restype, h.gkob_dist_spmv_f64.argtypes = i, [vp, vp, vp]
+        h.gkob_dist_cg_create_f64.restype = i
+        h.gkob_dist_cg_create_f64.argtypes = [vp, i, ll, i, i, ctypes.c_double, i, i]
+        h.gkob_dist_cg_apply_f64.restype = i
+        h.gkob_dist_cg_apply_f64.argtypes = [vp, vp, vp, ctypes.POINTER(ll),
+                                             ctypes.POINTER(ctypes.c_ubyte)]
+        h.gkob_dist_destroy.argtypes = [vp]
+        self.exec = exec_
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        with torch.cuda.stream(exec_.stream):
+            part = D.build_partition(col_idxs_global, offsets, self.rank, group)
+            exec_.stream.synchronize()
+        self.part = part
+        self.n_local, self.n_ghost = part["n_local"], part["n_ghost"]
+        self.row_ptrs, self.values = row_ptrs, values
+        self.col_idxs = part["col_idxs_local"].contiguous()
+        self.send_idx = part["send_idx"].contiguous()
+        # NCCL unique id from rank 0
+        idt = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            buf = (ctypes.c_ubyte * 128)()
+            _hcheck(h.gkob_dist_unique_id(buf))
+            idt = torch.tensor(list(buf), dtype=torch.uint8)
+        if self.world > 1:
+            idt = idt.to(exec_.device)
+            dist.broadcast(idt, 0, group=group)
+            idt = idt.cpu()
+        idb = (ctypes.c_ubyte * 128)(*idt.tolist())
+        sc = (ctypes.c_longlong * self.world)(*part["send_counts"].tolist())
+        rc = (ctypes.c_longlong * self.world)(*part["recv_counts"].tolist())
+        self.h = h.gkob_dist_matrix_create_f64_i32(
+            exec_.h, idb, self.rank, self.world, self.n_local, self.n_ghost, values.numel(),
+            row_ptrs.data_ptr(), self.col_idxs.data_ptr(), values.data_ptr(), sc, rc,
+            self.send_idx.data_ptr() if self.send_idx.numel() else None)
+        if not self.h:
+            raise _lib.B200Error(h.gkob_last_error().decode())
+
+    def apply(self, x_ext, y_local):
+        """y_local = A x; x_ext is [n_local owned | n_ghost] (ghosts filled by the exchange)"""
+        _hcheck(_host().gkob_dist_spmv_f64(self.h, x_ext.data_ptr(), y_local.data_ptr()))
+
+    def make_cg(self, scalar_jacobi=False, max_iters=None, res_kind=1, baseline=0, reduction=1e-8,
+                iter_first=True, check_every=16):
+        _hcheck(_host().gkob_dist_cg_create_f64(self.h, int(scalar_jacobi),
+                                                -1 if max_iters is None else max_iters, res_kind,
+                                                baseline, reduction, int(iter_first), check_every))
+
+    def cg_apply(self, b_local, x_local):
+        it, st = ctypes.c_longlong(0), ctypes.c_ubyte(0)
+        _hcheck(_host().gkob_dist_cg_apply_f64(self.h, b_local.data_ptr(), x_local.data_ptr(),
+                                               ctypes.byref(it), ctypes.byref(st)))
+        return it.value, st.value
+
+    def __del__(self):
+        try:
+            _host().gkob_dist_destroy(self.h)
+        except Exception:
+            pass

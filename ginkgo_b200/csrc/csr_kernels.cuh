@@ -443,18 +443,16 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kWCtasPerSm)
             e[0] = e[1] = e[2] = e[3] = 0;
         }
     };
-    // first 8-group of the lane: elements a0 + 8*lane .. +7 (streaming, coalesced)
-    auto load_group = [&](int64_t base, I (&cols)[8], V (&vals)[8]) {
-        if (base + 8 <= nnz) {
-            ld_stream_x8(col_idxs + base, cols);
-            ld_stream_x8(values + base, vals);
-        } else {
+    // Lane l owns the nonzeros p0 + l + 32 k: consecutive lanes read consecutive entries, so
+    // the slab loads are coalesced AND the gathers of structured matrices (stencils, bands:
+    // neighbouring nonzeros reference neighbouring columns) fall into few cache lines.
+    auto load_slab = [&](const int64_t (&e)[4], I (&cols)[8], V (&vals)[8]) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const bool ok = base + k < nnz;
-                cols[k] = ok ? ld_stream(col_idxs + base + k, pol_first) : I(0);
-                vals[k] = ok ? ld_stream(values + base + k, pol_first) : V(0);
-            }
+        for (int k = 0; k < 8; ++k) {
+            const int64_t idx = e[1] + lane + 32 * k;
+            const bool ok = idx < e[3];
+            cols[k] = ok ? ld_stream(col_idxs + idx, pol_first) : I(0);
+            vals[k] = ok ? ld_stream(values + idx, pol_first) : V(0);
         }
     };
 
@@ -464,12 +462,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kWCtasPerSm)
     I nrp = 0;  // row pointer of row r0 + lane (first pass of the row phase)
     load_ext(t, cur);
     load_ext(t + W, nxt);
-    {
-        const int64_t a0 = cur[1] & ~int64_t(7);
-        if (cur[2] > cur[0]) {
-            if (a0 + 8 * lane < cur[3]) load_group(a0 + 8 * lane, ncols, nvals);
-            if (lane <= cur[2] - cur[0]) nrp = row_ptrs[cur[0] + lane];
-        }
+    if (cur[2] > cur[0]) {
+        load_slab(cur, ncols, nvals);
+        if (lane <= cur[2] - cur[0]) nrp = row_ptrs[cur[0] + lane];
     }
     V dot_acc = V(0);
     for (; t < num_tiles; t += W) {
@@ -486,47 +481,35 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kWCtasPerSm)
         int64_t nn[4];
         load_ext(t + 2 * W, nn);
         if (nxt[2] > nxt[0]) {
-            const int64_t na0 = nxt[1] & ~int64_t(7);
-            if (na0 + 8 * lane < nxt[3]) load_group(na0 + 8 * lane, ncols, nvals);
+            load_slab(nxt, ncols, nvals);
             if (lane <= nxt[2] - nxt[0]) nrp = row_ptrs[nxt[0] + lane];
         }
         if (r1 > r0) {
-            const int64_t a0 = p0 & ~int64_t(7);
-            const bool long_last = (p1 - a0) > kWCap;
+            const bool long_last = (p1 - p0) > kWCap;
             const int64_t rl = r1 - 1;
             const int64_t sl = long_last ? (int64_t)row_ptrs[rl] : p1;
             const int64_t pend = long_last ? sl : p1;
             const int64_t rows_end = long_last ? rl : r1;
-            // ---- gather + products for group `lane`, then (rarely) groups lane + 32
+            // ---- gather + products: first 256 nonzeros from the prefetched registers
             {
-                const int64_t base = a0 + 8 * lane;
                 V xs[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    const int64_t idx = base + k;
                     xs[k] = V(0);
-                    if (idx >= p0 && idx < pend)
+                    if (p0 + lane + 32 * k < pend)
                         xs[k] = ld_gather(b + (int64_t)cols[k] * b_stride, pol_last);
-                }
-                if (base < pend) {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        prod[8 * lane + k] = ADVANCED ? (alpha * vals[k]) * xs[k] : vals[k] * xs[k];
-                }
-            }
-            for (int64_t base = a0 + 8 * (lane + 32); base < pend; base += 256) {
-                I c2[8];
-                V v2[8], xs[8];
-                load_group(base, c2, v2);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int64_t idx = base + k;
-                    xs[k] = V(0);
-                    if (idx < pend) xs[k] = ld_gather(b + (int64_t)c2[k] * b_stride, pol_last);
                 }
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
-                    prod[base - a0 + k] = ADVANCED ? (alpha * v2[k]) * xs[k] : v2[k] * xs[k];
+                    if (p0 + lane + 32 * k < pend)
+                        prod[lane + 32 * k] = ADVANCED ? (alpha * vals[k]) * xs[k] : vals[k] * xs[k];
+            }
+            // ---- (rare) the part of the last row beyond 256 that still fits the strip
+            for (int64_t i = p0 + 256 + lane; i < pend; i += 32) {
+                const I col = ld_stream(col_idxs + i, pol_first);
+                const V val = ld_stream(values + i, pol_first);
+                const V x = ld_gather(b + (int64_t)col * b_stride, pol_last);
+                prod[i - p0] = ADVANCED ? (alpha * val) * x : val * x;
             }
             __syncwarp();
             // ---- row phase: LANES lanes per row, rows_per_pass = 32 / LANES
@@ -550,9 +533,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kWCtasPerSm)
                 V acc = V(0);
                 if (LANES == 1) {
                     if (ADVANCED && rv && beta != V(0)) acc = c[(r0 + rloc) * c_stride] * beta;
-                    for (int64_t i = s; i < e; ++i) acc += prod[i - a0];
+                    for (int64_t i = s; i < e; ++i) acc += prod[i - p0];
                 } else {
-                    for (int64_t i = s + sub; i < e; i += LANES) acc += prod[i - a0];
+                    for (int64_t i = s + sub; i < e; i += LANES) acc += prod[i - p0];
 #pragma unroll
                     for (int o = LANES / 2; o > 0; o >>= 1)
                         acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -744,7 +727,6 @@ inline Variant pick_variant(const void* col_idxs, const void* values)
     Variant want = kWarp;
     if (env && !strcmp(env, "tma")) want = kTma;
     if (env && !strcmp(env, "slab")) want = kSlab;
-    if (want == kWarp && (a & 31u)) want = kSlab;  // 256-bit loads need 32-byte alignment
     if (want == kTma && (a & 15u)) want = kSlab;   // bulk copies need 16-byte alignment
     return want;
 }

@@ -148,8 +148,11 @@ __global__ void finish_kernel(V* sc, int32_t* ctl, int baseline, V factor)
 {
     if (!INIT && ctl[0] != 0) return;
     if (INIT) {
+        // baseline: 1 initial_resnorm, 2 absolute, 3 rhs_norm with sc[4] = global ||b||^2,
+        // 0 rhs_norm with sc[4] = ||b|| already
         if (baseline == 1) sc[4] = sqrt(sc[7]);
         if (baseline == 2) sc[4] = V(1);
+        if (baseline == 3) sc[4] = sqrt(sc[4]);
         sc[5] = factor * sc[4];
     }
     finish_scalars(sc[6], sc[7], sc, ctl);

@@ -4,7 +4,7 @@
 #include <cstdio>
 #include <string>
 
-#include "gko_b200.hpp"
+#include "gko_b200_dist.hpp"
 
 using namespace gko_b200;
 
@@ -171,6 +171,89 @@ long long gkob_launch_count(void* exec) { return static_cast<Handle*>(exec)->exe
     }
 GKOB_DEF(double, f64)
 GKOB_DEF(float, f32)
+
+// ---- multi-GPU ------------------------------------------------------------------------------
+struct DistHandle {
+    std::shared_ptr<Executor> exec;
+    std::shared_ptr<distributed::communicator> comm;
+    std::shared_ptr<distributed::Matrix<double, int32>> A;
+    std::unique_ptr<distributed::Cg<double, int32>> cg;
+};
+
+int gkob_dist_unique_id(unsigned char* id128)
+{
+    return guarded([&] {
+        uint8 id[128];
+        distributed::communicator::get_unique_id(id);
+        std::memcpy(id128, id, 128);
+    });
+}
+
+// local rows (rp, ci_local, va device views), halo description from distributed.build_partition
+void* gkob_dist_matrix_create_f64_i32(void* exec, const unsigned char* id128, int rank, int nranks,
+                                      long long n_local, long long n_ghost, long long nnz,
+                                      int32* rp, int32* ci_local, double* va,
+                                      const long long* send_counts, const long long* recv_counts,
+                                      const int32* send_idx_dev)
+{
+    auto e = static_cast<Handle*>(exec)->exec;
+    auto h = new DistHandle();
+    h->exec = e;
+    if (guarded([&] {
+            h->comm = distributed::communicator::create(e, id128, rank, nranks);
+            auto local = matrix::Csr<double, int32>::create(
+                e, dim2{(size_type)n_local, (size_type)(n_local + n_ghost)},
+                array<double>::view(e, nnz, va), array<int32>::view(e, nnz, ci_local),
+                array<int32>::view(e, n_local + 1, rp));
+            std::vector<int64> sc(send_counts, send_counts + nranks), rc(recv_counts,
+                                                                         recv_counts + nranks);
+            h->A = std::make_shared<distributed::Matrix<double, int32>>(
+                e, h->comm, std::move(local), (size_type)n_ghost, sc, rc, send_idx_dev);
+        })) {
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+
+int gkob_dist_spmv_f64(void* dist, double* x_ext, double* y_local)
+{
+    return guarded([&] {
+        auto h = static_cast<DistHandle*>(dist);
+        auto n = h->A->n_local(), ng = h->A->n_ghost();
+        auto xe = matrix::Dense<double>::create_view(h->exec, dim2{n + ng, 1}, x_ext, 1);
+        auto y = matrix::Dense<double>::create_view(h->exec, dim2{n, 1}, y_local, 1);
+        h->A->apply(xe.get(), y.get());
+    });
+}
+
+int gkob_dist_cg_create_f64(void* dist, int scalar_jacobi, long long max_iters, int res_kind,
+                            int baseline, double reduction, int iter_first, int check_every)
+{
+    return guarded([&] {
+        auto h = static_cast<DistHandle*>(dist);
+        h->cg.reset(new distributed::Cg<double, int32>(h->exec, h->A, scalar_jacobi != 0, max_iters,
+                                                       res_kind, baseline, reduction,
+                                                       iter_first != 0, check_every));
+    });
+}
+
+int gkob_dist_cg_apply_f64(void* dist, const double* b_local, double* x_local, long long* iters,
+                           unsigned char* status)
+{
+    return guarded([&] {
+        auto h = static_cast<DistHandle*>(dist);
+        auto n = h->A->n_local();
+        auto b = matrix::Dense<double>::create_view(h->exec, dim2{n, 1},
+                                                    const_cast<double*>(b_local), 1);
+        auto x = matrix::Dense<double>::create_view(h->exec, dim2{n, 1}, x_local, 1);
+        h->cg->apply(b.get(), x.get());
+        *iters = h->cg->get_num_iterations();
+        *status = h->cg->get_stop_status();
+    });
+}
+
+void gkob_dist_destroy(void* dist) { delete static_cast<DistHandle*>(dist); }
 
 // x = op(b)   /   x = alpha op(b) + beta x  (alpha, beta: 1x1 Dense handles)
 int gkob_apply(void* op, void* b, void* x)

@@ -288,15 +288,20 @@ public:
             throw DimensionMismatch("apply: alpha and beta must be 1x1");
         apply_impl(alpha, b, beta, x);
     }
-    template <typename P1, typename P2>
+    // smart-pointer conveniences (std::unique_ptr / std::shared_ptr operands, as in the reference)
+    template <typename P1, typename P2, typename = typename P1::element_type,
+              typename = typename P2::element_type>
     void apply(const P1& b, const P2& x) const
     {
-        apply(&*b, &*x);
+        apply(static_cast<const LinOp*>(b.get()), static_cast<LinOp*>(x.get()));
     }
-    template <typename P0, typename P1, typename P2, typename P3>
+    template <typename P0, typename P1, typename P2, typename P3,
+              typename = typename P0::element_type, typename = typename P1::element_type,
+              typename = typename P2::element_type, typename = typename P3::element_type>
     void apply(const P0& a, const P1& b, const P2& bt, const P3& x) const
     {
-        apply(&*a, &*b, &*bt, &*x);
+        apply(static_cast<const LinOp*>(a.get()), static_cast<const LinOp*>(b.get()),
+              static_cast<const LinOp*>(bt.get()), static_cast<LinOp*>(x.get()));
     }
 
 protected:

@@ -733,8 +733,11 @@ protected:
         int32 h[8] = {0};
         exec->copy_to_host(h, ctl_.get_const_data(), 8);
         while (h[0] == 0) {
+            const int32 before = h[1];
             GKOB_CALL(b200_graph_launch(ctx, graph_));
             exec->copy_to_host(h, ctl_.get_const_data(), 8);
+            if (h[0] == 0 && h[1] == before)
+                throw Error("fused CG: the device iteration made no progress");
         }
         this->num_iterations_ = (size_type)h[1];
         this->status_.assign(1, (uint8)h[0]);

@@ -564,6 +564,19 @@ void FNI(coo_advanced_spmv)(int64_t num_rows, int64_t num_cols, int64_t nnz, con
                             num_rhs, c, cs);
 }
 
+/* reference/matrix/csr_kernels.cpp `extract_diagonal`: first stored entry with col == row */
+void FNI(csr_extract_diagonal)(int64_t n, const I* rp, const I* ci, const V* va, V* diag)
+{
+    for (int64_t row = 0; row < n; ++row) {
+        diag[row] = 0;
+        for (int64_t k = rp[row]; k < (int64_t)rp[row + 1]; ++k)
+            if ((int64_t)ci[k] == row) {
+                diag[row] = va[k];
+                break;
+            }
+    }
+}
+
 /* reference/preconditioner/jacobi_kernels.cpp:419-447 (apply_block), :460-520 (apply /
  * simple_apply); storage scheme include/ginkgo/core/preconditioner/jacobi.hpp:37-141 */
 void FNI(jacobi_apply)(int64_t num_blocks, int32_t max_block_size, int64_t block_offset, int64_t group_offset,

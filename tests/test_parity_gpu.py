@@ -479,3 +479,28 @@ def test_block_jacobi_apply(orc, cuda, vt, it, max_bs):
             nblocks, max_bs, bo, go, gp, ptrs, blocks, np.array([1.5], VT[vt]), b, bs, nrhs,
             np.array([-0.5], VT[vt]), x0.copy(), xs])
         assert np.array_equal(a[-2], c[-2])
+
+
+# ----------------------------------------------------------- integer-exact conversions
+@pytest.mark.parametrize("it", ITS)
+@pytest.mark.parametrize("kind", ["ref_common", "empty_rows", "all_empty", "long_rows"])
+def test_index_conversions_bit_exact(orc, cuda, it, kind):
+    rng = np.random.default_rng(19)
+    n, m, rp, ci, va = csr_case(rng, kind, "f64", it)
+    nnz = len(va)
+    a, b = both(orc, cuda, "convert_ptrs_to_idxs_" + it, lambda: [rp, n, np.full(nnz, -7, IT[it])])
+    assert np.array_equal(a[-1], b[-1])
+    rows = a[-1]
+    a, b = both(orc, cuda, "convert_idxs_to_ptrs_" + it,
+                lambda: [rows, nnz, n, np.full(n + 1, -7, IT[it])])
+    assert np.array_equal(a[-1], b[-1]) and np.array_equal(b[-1], rp)
+
+
+@pytest.mark.parametrize("vt", VTS)
+@pytest.mark.parametrize("it", ITS)
+def test_extract_diagonal(orc, cuda, vt, it):
+    rng = np.random.default_rng(20)
+    n, m, rp, ci, va = csr_case(rng, "empty_rows", vt, it)
+    a, b = both(orc, cuda, "csr_extract_diagonal_%s_%s" % (vt, it),
+                lambda: [n, rp, ci, va, np.full(n, np.nan, VT[vt])])
+    assert np.array_equal(a[-1], b[-1])
