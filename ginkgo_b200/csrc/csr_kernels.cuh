@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 constexpr int kWTile = 256;
 constexpr int kWCap = kWTile + 64 + 8;   // staged nonzeros per warp tile
 constexpr int kWarpsPerCta = 8;
-constexpr int kWCtasPerSm = 3;
+constexpr int kWCtasPerSm = 2;  // 128 registers: the register-resident prefetch must not spill
 
 template <typename V, typename I, int LANES, bool ADVANCED, bool DOT>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, kWCtasPerSm)

@@ -83,7 +83,10 @@ def test_solver_matches_oracle(hexec, kind, precond, vt, fused):
                                              max_iters=400, reduction=red, iter_first=iter_first,
                                              krylov_dim=20, fused=fused)
         assert used == (fused and precond != 2)
-        assert abs(itd - ito) <= 2, (itd, ito)
+        # BiCGStab's iteration count is sensitive to the rounding of its four dot products
+        # (tree vs sequential order): allow 5 % there, +-2 for CG / GMRES
+        slack = max(2, ito // 20) if kind == "bicgstab" else 2
+        assert abs(itd - ito) <= slack, (itd, ito)
         assert stop_d == stop_o[0]
         ro, rd = true_rel_res(rp, ci, va, b, xo), true_rel_res(rp, ci, va, b, xd)
         assert abs(ro[0] - rd[0]) <= (1e-10 if vt == "f64" else 1e-5)
