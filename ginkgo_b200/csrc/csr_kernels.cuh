@@ -607,11 +607,42 @@ __global__ void __launch_bounds__(kThreads, 3)
         const int64_t sl = long_last ? (int64_t)row_ptrs[rl] : p1;
         const int64_t pend = long_last ? sl : p1;
         const int64_t rows_end = long_last ? rl : r1;
-        for (int64_t i = p0 + tid; i < pend; i += kThreads) {
-            const I col = ld_stream(col_idxs + i, pol_first);
-            const V val = ld_stream(values + i, pol_first);
-            const V x = ld_gather(b + (int64_t)col * b_stride, pol_last);
-            prod[i - a0] = ADVANCED ? (alpha * val) * x : val * x;
+        if ((((uintptr_t)col_idxs | (uintptr_t)values) & 31u) == 0) {
+            // 8 consecutive nonzeros per thread, 256-bit streaming loads
+#pragma unroll 2
+            for (int64_t base = a0 + (int64_t)tid * 8; base < pend; base += (int64_t)kThreads * 8) {
+                I cols[8];
+                V vals[8];
+                if (base + 8 <= nnz) {
+                    ld_stream_x8(col_idxs + base, cols);
+                    ld_stream_x8(values + base, vals);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const bool ok = base + k < nnz;
+                        cols[k] = ok ? ld_stream(col_idxs + base + k, pol_first) : I(0);
+                        vals[k] = ok ? ld_stream(values + base + k, pol_first) : V(0);
+                    }
+                }
+                V xs[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int64_t idx = base + k;
+                    xs[k] = (idx >= p0 && idx < pend)
+                                ? ld_gather(b + (int64_t)cols[k] * b_stride, pol_last)
+                                : V(0);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    prod[base - a0 + k] = ADVANCED ? (alpha * vals[k]) * xs[k] : vals[k] * xs[k];
+            }
+        } else {
+            for (int64_t i = p0 + tid; i < pend; i += kThreads) {
+                const I col = ld_stream(col_idxs + i, pol_first);
+                const V val = ld_stream(values + i, pol_first);
+                const V x = ld_gather(b + (int64_t)col * b_stride, pol_last);
+                prod[i - a0] = ADVANCED ? (alpha * val) * x : val * x;
+            }
         }
         __syncthreads();
         row_phase<V, LANES, ADVANCED, DOT>(

@@ -35,7 +35,8 @@ for name, kw in [("lap3d_40", dict(grid=40, dims=3)), ("cfg2_small", dict(n=2000
         A1 = api.host_csr(ex, (n, n), va, ci, rp)
         y1 = torch.zeros(n, dtype=torch.float64, device=dev)
         _h = api._host()
-        api._hcheck(_h.gkob_apply(A1.h, api.host_dense(ex, x).h, api.host_dense(ex, y1).h))
+        xd1, yd1 = api.host_dense(ex, x), api.host_dense(ex, y1)  # keep the handles alive
+        api._hcheck(_h.gkob_apply(A1.h, xd1.h, yd1.h))
     A = api.DistMatrix(ex, offs, lrp, lci, lva)
     with torch.cuda.stream(ex.stream):
         x_ext = torch.zeros(A.n_local + A.n_ghost, dtype=torch.float64, device=dev)
@@ -50,7 +51,8 @@ for name, kw in [("lap3d_40", dict(grid=40, dims=3)), ("cfg2_small", dict(n=2000
         b = torch.ones(n, dtype=torch.float64, device=dev)
         s1 = api.HostSolver(ex, "cg", A1, precond_max_bs=1, max_iters=2000, reduction=1e-9, fused=True)
         x1 = torch.zeros(n, dtype=torch.float64, device=dev)
-        s1.apply(api.host_dense(ex, b), api.host_dense(ex, x1))
+        bd1, xd2 = api.host_dense(ex, b), api.host_dense(ex, x1)
+        s1.apply(bd1, xd2)
         A.make_cg(scalar_jacobi=True, max_iters=2000, reduction=1e-9)
         xd = torch.zeros(A.n_local, dtype=torch.float64, device=dev)
         it, st = A.cg_apply(b[r0:r1].contiguous(), xd)
