@@ -95,9 +95,11 @@ def cpu_reference_spmv(sample_rows, reps):
     rp, ci, va = W.build(CFG, 0, sample_rows, xp="np")
     x = W.vector(N_ROWS)
     nnz = len(va)
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
     from oracle import ref
     if ref.available():
-        cores = ref.num_threads()
+        cores = ref.use_physical_cores()
         _, sec = ref.spmv("csr", rp, ci, va, x, N_ROWS, exec_kind=1, reps=reps)
         kind = "reference"
     else:
@@ -344,6 +346,39 @@ def run_cg(args, rank, world, ex, dev, timed_events=True):
         torch.cuda.empty_cache()
     if args.no_cg:
         return out
+    if world == 1 and not args.no_gmres:
+        # configs[3]: GMRES(30, MGS) + block-Jacobi(16) fp32, random nonsymmetric diagonally
+        # dominant n=4M nnz=80M, uniform block pointers, rel. residual 1e-6
+        c4 = W.CONFIGS["cfg4"]
+        n = c4["n"]
+        with torch.cuda.stream(ex.stream):
+            rp, ci, va = W.build("cfg4", xp="torch", device=dev)
+            b = torch.ones(n, dtype=torch.float32, device=dev)
+            x = torch.zeros(n, dtype=torch.float32, device=dev)
+        A = api.host_csr(ex, (n, n), va, ci, rp)
+        bp = np.arange(0, n + 1, 16, dtype=np.int32)
+        t0 = time.perf_counter()
+        s = api.HostSolver(ex, "gmres", A, precond_max_bs=16, block_ptrs=bp, max_iters=1000,
+                           reduction=1e-6, krylov_dim=30, ortho=0)
+        bd, xd = api.host_dense(ex, b), api.host_dense(ex, x)
+        s.apply(bd, xd)  # warm-up (includes the host-side block inversion of the generate step)
+        setup_s = time.perf_counter() - t0
+        x.zero_()
+        ms = wall(lambda: s.apply(bd, xd))
+        r = b.clone()
+        rd = api.host_dense(ex, r)
+        one = api.host_dense(ex, torch.ones(1, dtype=torch.float32, device=dev))
+        neg = api.host_dense(ex, -torch.ones(1, dtype=torch.float32, device=dev))
+        api._hcheck(api._host().gkob_apply4(A.h, neg.h, xd.h, one.h, rd.h))
+        ex.synchronize()
+        out["cfg4"] = {"workload": "cfg4: GMRES(30, MGS) + block-Jacobi(16) fp32, random "
+                                   "nonsymmetric diag-dominant n=4M nnz=80M, b=1, 1e-6",
+                       "iterations": s.num_iterations, "ms": ms,
+                       "iters_per_s": s.num_iterations / (ms * 1e-3),
+                       "true_rel_residual": (r.double().norm() / b.double().norm()).item(),
+                       "stop_status": s.stop_status, "first_apply_incl_generate_s": setup_s}
+        del A, s, rp, ci, va, b, x, r
+        torch.cuda.empty_cache()
     # configs[4]: 400^3, fixed 200 iterations (reduction 0 never triggers), strong scaling
     g = W.CONFIGS["cfg5"]["grid"] if not args.small_cg else 160
     n = g ** 3
@@ -392,6 +427,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-cg", action="store_true", help="skip the CG legs")
+    ap.add_argument("--no-gmres", action="store_true", help="skip the GMRES + block-Jacobi leg")
     ap.add_argument("--small-cg", action="store_true", help="160^3 instead of 400^3 for the cfg5 leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

@@ -41,6 +41,18 @@ def num_threads():
     return lib().refshim_num_threads()
 
 
+def use_physical_cores():
+    """reference CPU-baseline methodology: one OpenMP thread per
+    physical core; returns the thread count in use"""
+    try:
+        import psutil
+        n = psutil.cpu_count(logical=False) or os.cpu_count()
+    except Exception:
+        n = os.cpu_count()
+    lib().refshim_set_num_threads(int(n))
+    return num_threads()
+
+
 def spmv(fmt, rp, ci, va, x, n_cols, alpha=None, beta=None, y=None, exec_kind=0, reps=0,
          strategy="classical"):
     """y = A x (or alpha A x + beta y) through the reference's LinOp::apply; returns (y, s/rep)"""
