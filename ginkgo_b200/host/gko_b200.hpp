@@ -373,7 +373,7 @@ public:
                                                    const V* host_row_major)
     {
         auto d = create(exec, size);
-        if (size.rows * size.cols)
+        if (size.rows * size.cols != 0)
             exec->copy_from_host(d->get_values(), host_row_major, size.rows * size.cols);
         return d;
     }

@@ -174,3 +174,15 @@ def test_errors_mirror_reference(hexec):
     s = api.HostSolver(hexec, "cg", A, max_iters=3)
     with pytest.raises(api.DimensionMismatch):
         s.apply(b, x)
+
+
+def test_cpp_example_simple_solver():
+    """examples/simple_solver.cpp: the reference's simple-solver flow written against
+    gko_b200.hpp (namespace gko = gko_b200), linked only against the C-ABI library"""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples",
+                       "simple_solver")
+    r = subprocess.run([exe, "40"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "converged=1" in r.stdout and "fused=1" in r.stdout
