@@ -504,3 +504,27 @@ def test_extract_diagonal(orc, cuda, vt, it):
     a, b = both(orc, cuda, "csr_extract_diagonal_%s_%s" % (vt, it),
                 lambda: [n, rp, ci, va, np.full(n, np.nan, VT[vt])])
     assert np.array_equal(a[-1], b[-1])
+
+
+@pytest.mark.parametrize("vt", VTS)
+def test_hybrid_is_ell_plus_coo(orc, cuda, vt):
+    """Hybrid::apply = ell->apply then coo->apply2 (core/matrix/hybrid.cpp:175-201): split every
+    row into its first k entries (ELL part) and the rest (COO part)"""
+    rng = np.random.default_rng(23)
+    n, m, rp, ci, va = csr_case(rng, "ref_common", vt, "i32")
+    k = 6
+    lens = np.diff(rp)
+    ell_mask = np.concatenate([np.arange(l) < k for l in lens])
+    erp = np.zeros(n + 1, np.int32)
+    erp[1:] = np.cumsum(np.minimum(lens, k))
+    width, stride, ecols, evals = H.csr_to_ell(erp, ci[ell_mask], va[ell_mask], n)
+    rows = H.csr_to_coo_rows(rp, n, "i32")[~ell_mask]
+    ccols, cvals = ci[~ell_mask], va[~ell_mask]
+    x = H.dense(rng, m, 1, vt=vt)
+    y = np.zeros((n, 1), VT[vt])
+    cuda("ell_spmv_%s_i32" % vt, n, m, width, stride, ecols, evals, x, 1, 1, y, 1)
+    cuda("coo_spmv2_%s_i32" % vt, n, m, len(cvals), rows, ccols, cvals, x, 1, 1, y, 1)
+    yo = np.zeros((n, 1), VT[vt])
+    orc("csr_spmv_%s_i32" % vt, n, m, len(va), rp, ci, va, x, 1, 1, yo, 1)
+    # same left-to-right order: ELL part first, COO part appended
+    assert np.array_equal(y, yo)
