@@ -575,6 +575,191 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kWCtasPerSm)
 }
 
 // --------------------------------------------------------------------------
+// warp-stream kernel, software pipelined: the row sums of tile k-1 (shared memory only)
+// run while the gathers of tile k and the slab loads of tile k+1 are in flight
+// --------------------------------------------------------------------------
+template <typename V, typename I, int LANES, bool ADVANCED, bool DOT>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, kWCtasPerSm)
+    warp_pipe_kernel(const int64_t* __restrict__ tiles, int64_t num_tiles, int64_t nnz,
+                     const I* __restrict__ row_ptrs, const I* __restrict__ col_idxs,
+                     const V* __restrict__ values, const V* __restrict__ alpha_p,
+                     const V* __restrict__ b, int64_t b_stride, const V* __restrict__ beta_p,
+                     V* __restrict__ c, int64_t c_stride, DotArgs<V> dot)
+{
+    __shared__ __align__(16) V prod_all[kWarpsPerCta][2][kWCap];
+    __shared__ V red[32];
+    __shared__ bool is_last;
+    if (DOT && dot.ctl && dot.ctl[0] != 0) return;
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    V alpha = V(1), beta = V(0);
+    if (ADVANCED) {
+        alpha = *alpha_p;
+        beta = *beta_p;
+    }
+    const uint64_t pol_last = policy_evict_last();
+    const uint64_t pol_first = policy_evict_first();
+    const int64_t W = (int64_t)gridDim.x * kWarpsPerCta;
+    int64_t t = (int64_t)blockIdx.x * kWarpsPerCta + warp;
+
+    auto load_ext = [&](int64_t tt, int64_t (&e)[4]) {
+        if (tt < num_tiles) {
+            const longlong2 a = *reinterpret_cast<const longlong2*>(tiles + 2 * tt);
+            const longlong2 bb = *reinterpret_cast<const longlong2*>(tiles + 2 * tt + 2);
+            e[0] = a.x;
+            e[1] = a.y;
+            e[2] = bb.x;
+            e[3] = bb.y;
+        } else {
+            e[0] = e[1] = e[2] = e[3] = 0;
+        }
+    };
+    auto load_slab = [&](const int64_t (&e)[4], I (&cols)[8], V (&vals)[8]) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int64_t idx = e[1] + lane + 32 * k;
+            const bool ok = idx < e[3];
+            cols[k] = ok ? ld_stream(col_idxs + idx, pol_first) : I(0);
+            vals[k] = ok ? ld_stream(values + idx, pol_first) : V(0);
+        }
+    };
+    // row sums of a finished tile from its strip (reads shared memory + a few row pointers)
+    auto row_phase = [&](const V* prod, int64_t r0, int64_t p0, int nrows, I rp_first, V& dot_acc) {
+        constexpr int kRpp = 32 / LANES;
+        const int sub = lane % LANES;
+        for (int ps = 0; ps * kRpp < nrows; ++ps) {
+            const int rloc = ps * kRpp + lane / LANES;
+            const bool rv = rloc < nrows;
+            int64_t s = 0, e = 0;
+            if (LANES == 1 && ps == 0) {
+                const I nxt_rp = __shfl_down_sync(0xffffffffu, rp_first, 1);
+                s = rp_first;
+                e = (lane == 31) ? (rv ? (int64_t)row_ptrs[r0 + 32] : 0) : (int64_t)nxt_rp;
+            } else if (rv) {
+                s = row_ptrs[r0 + rloc];
+                e = row_ptrs[r0 + rloc + 1];
+            }
+            if (!rv) s = e = 0;
+            V acc = V(0);
+            if (LANES == 1) {
+                if (ADVANCED && rv && beta != V(0)) acc = c[(r0 + rloc) * c_stride] * beta;
+                for (int64_t i = s; i < e; ++i) acc += prod[i - p0];
+            } else {
+                for (int64_t i = s + sub; i < e; i += LANES) acc += prod[i - p0];
+#pragma unroll
+                for (int o = LANES / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (ADVANCED && rv && sub == 0 && beta != V(0))
+                    acc = c[(r0 + rloc) * c_stride] * beta + acc;
+            }
+            if (rv && sub == 0) {
+                c[(r0 + rloc) * c_stride] = acc;
+                if (DOT) dot_acc += b[(r0 + rloc) * b_stride] * acc;
+            }
+        }
+    };
+
+    int64_t cur[4], nxt[4];
+    I cols[8];
+    V vals[8];
+    I rp_cur = 0;
+    load_ext(t, cur);
+    load_ext(t + W, nxt);
+    if (cur[2] > cur[0]) {
+        load_slab(cur, cols, vals);
+        if (lane <= cur[2] - cur[0]) rp_cur = row_ptrs[cur[0] + lane];
+    }
+    // the tile whose products are parked and still have to be summed
+    int64_t prev_r0 = 0, prev_p0 = 0;
+    int prev_nrows = 0;
+    I prev_rp = 0;
+    int par = 0;
+    V dot_acc = V(0);
+    for (; t < num_tiles; t += W) {
+        const int64_t r0 = cur[0], p0 = cur[1], r1 = cur[2], p1 = cur[3];
+        const bool have = r1 > r0;
+        bool long_last = false;
+        int64_t rl = 0, sl = p1, pend = p1, rows_end = r1;
+        V xs[8];
+        if (have) {
+            long_last = (p1 - p0) > kWCap;
+            rl = r1 - 1;
+            sl = long_last ? (int64_t)row_ptrs[rl] : p1;
+            pend = long_last ? sl : p1;
+            rows_end = long_last ? rl : r1;
+            // 1. gathers of this tile go out first
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                xs[k] = V(0);
+                if (p0 + lane + 32 * k < pend)
+                    xs[k] = ld_gather(b + (int64_t)cols[k] * b_stride, pol_last);
+            }
+        }
+        // 2. slab + row pointers of the next tile, extents of the one after it
+        I ncols[8];
+        V nvals[8];
+        I nrp = 0;
+        int64_t nn[4];
+        load_ext(t + 2 * W, nn);
+        if (nxt[2] > nxt[0]) {
+            load_slab(nxt, ncols, nvals);
+            if (lane <= nxt[2] - nxt[0]) nrp = row_ptrs[nxt[0] + lane];
+        }
+        // 3. row sums of the PREVIOUS tile while all of that is in flight
+        if (prev_nrows > 0) row_phase(prod_all[warp][par ^ 1], prev_r0, prev_p0, prev_nrows, prev_rp, dot_acc);
+        prev_nrows = 0;
+        // 4. products of this tile into the other strip
+        if (have) {
+            V* prod = prod_all[warp][par];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (p0 + lane + 32 * k < pend)
+                    prod[lane + 32 * k] = ADVANCED ? (alpha * vals[k]) * xs[k] : vals[k] * xs[k];
+            for (int64_t i = p0 + 256 + lane; i < pend; i += 32) {
+                const I col = ld_stream(col_idxs + i, pol_first);
+                const V val = ld_stream(values + i, pol_first);
+                const V x = ld_gather(b + (int64_t)col * b_stride, pol_last);
+                prod[i - p0] = ADVANCED ? (alpha * val) * x : val * x;
+            }
+            if (long_last) {
+                V acc = V(0);
+                for (int64_t i = sl + lane; i < p1; i += 32) {
+                    const I col = ld_stream(col_idxs + i, pol_first);
+                    const V val = ld_stream(values + i, pol_first);
+                    const V x = ld_gather(b + (int64_t)col * b_stride, pol_last);
+                    acc += ADVANCED ? (alpha * val) * x : val * x;
+                }
+                acc = warp_sum(acc);
+                if (lane == 0) {
+                    if (ADVANCED && beta != V(0)) acc = c[rl * c_stride] * beta + acc;
+                    c[rl * c_stride] = acc;
+                    if (DOT) dot_acc += b[rl * b_stride] * acc;
+                }
+            }
+            prev_r0 = r0;
+            prev_p0 = p0;
+            prev_nrows = (int)(rows_end - r0);
+            prev_rp = rp_cur;
+            par ^= 1;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            cols[k] = ncols[k];
+            vals[k] = nvals[k];
+        }
+        rp_cur = nrp;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            cur[q] = nxt[q];
+            nxt[q] = nn[q];
+        }
+    }
+    if (prev_nrows > 0) row_phase(prod_all[warp][par ^ 1], prev_r0, prev_p0, prev_nrows, prev_rp, dot_acc);
+    if (DOT) dot_epilogue(dot_acc, dot, red, &is_last);
+}
+
+// --------------------------------------------------------------------------
 // warp-ring kernel: the warp-stream algorithm with the slab prefetched by the
 // bulk-copy engine into a per-warp ring of shared-memory slots
 // --------------------------------------------------------------------------
@@ -969,7 +1154,7 @@ b200_status set_smem(K kernel, size_t bytes)
 }
 
 // kernel variants
-enum Variant { kSlab = 0, kTma = 1, kWarp = 2, kRingV = 3 };
+enum Variant { kSlab = 0, kTma = 1, kWarp = 2, kRingV = 3, kPipe = 4 };
 
 inline Variant pick_variant(const void* col_idxs, const void* values)
 {
@@ -979,6 +1164,7 @@ inline Variant pick_variant(const void* col_idxs, const void* values)
     if (env && !strcmp(env, "tma")) want = kTma;
     if (env && !strcmp(env, "slab")) want = kSlab;
     if (env && !strcmp(env, "ring")) want = kRingV;
+    if (env && !strcmp(env, "pipe")) want = kPipe;
     if (want == kRingV && (a & 15u)) want = kWarp;
     if (want == kTma && (a & 15u)) want = kSlab;   // bulk copies need 16-byte alignment
     return want;
@@ -987,7 +1173,7 @@ inline Variant pick_variant(const void* col_idxs, const void* values)
 // tile array / tile count a variant works on
 inline int64_t variant_tiles(Variant v, int64_t num_rows, int64_t nnz)
 {
-    return (v == kWarp || v == kRingV) ? num_wtiles_for(num_rows, nnz) : num_tiles_for(num_rows, nnz);
+    return (v == kWarp || v == kRingV || v == kPipe) ? num_wtiles_for(num_rows, nnz) : num_tiles_for(num_rows, nnz);
 }
 
 // number of CTAs a launch uses (the size of the fused-dot partials array)
@@ -1038,6 +1224,10 @@ b200_status launch_one(b200_ctx* ctx, Variant v, int64_t num_tiles, const int64_
         k<<<grid, kRingWarps * 32, smem, ctx->stream>>>(tiles, num_tiles, nnz, row_ptrs, col_idxs,
                                                         values, alpha, b, b_stride, beta, c,
                                                         c_stride, dot);
+    } else if (v == kPipe) {
+        warp_pipe_kernel<V, I, LANES, ADVANCED, DOT><<<grid, kWarpsPerCta * 32, 0, ctx->stream>>>(
+            tiles, num_tiles, nnz, row_ptrs, col_idxs, values, alpha, b, b_stride, beta, c, c_stride,
+            dot);
     } else if (v == kWarp) {
         auto k = warp_stream_kernel<V, I, LANES, ADVANCED, DOT>;
         static bool dbg = getenv("B200_DEBUG") != nullptr;

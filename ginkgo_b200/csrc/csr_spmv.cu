@@ -57,7 +57,7 @@ b200_status spmv_impl(b200_ctx* ctx, const b200_csr_plan* plan, int64_t num_rows
     if (plan) {
         B200_REQUIRE(plan->num_rows == num_rows && plan->nnz == nnz,
                      "plan does not match the matrix");
-        tiles = (variant == kWarp || variant == kRingV) ? plan->wtiles : plan->tiles;
+        tiles = (variant != kSlab && variant != kTma) ? plan->wtiles : plan->tiles;
         lanes = plan->lanes;
     } else {
         int64_t* tr = (int64_t*)ctx->scratch(2 * (num_tiles + 1) * sizeof(int64_t));
@@ -66,7 +66,7 @@ b200_status spmv_impl(b200_ctx* ctx, const b200_csr_plan* plan, int64_t num_rows
             return B200_ERR_ALLOC;
         }
         b200_status st = fill_plan<I>(ctx, num_rows, nnz, row_ptrs, num_tiles, tr,
-                                      (variant == kWarp || variant == kRingV) ? kWTile : kTile);
+                                      (variant != kSlab && variant != kTma) ? kWTile : kTile);
         if (st != B200_OK) return st;
         tiles = tr;
         lanes = pick_lanes(num_rows, nnz);
@@ -288,7 +288,7 @@ b200_status apply(b200_ctx* ctx, const b200_coo_plan* plan, int mode, int64_t nu
         if (st != B200_OK) return st;
         if (num_rhs == 1) {
             st = csr::fill_plan<I>(ctx, num_rows, nnz, rp, num_tiles, tiles,
-                                   (variant == csr::kWarp || variant == csr::kRingV) ? csr::kWTile : csr::kTile);
+                                   (variant != csr::kSlab && variant != csr::kTma) ? csr::kWTile : csr::kTile);
             if (st != B200_OK) return st;
             const csr::Variant tma = variant;
             const int lanes = csr::pick_lanes(num_rows, nnz);

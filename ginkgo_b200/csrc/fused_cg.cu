@@ -309,7 +309,7 @@ B200_DEF_FCG(f32, float)
         const b200::csr::Variant v = b200::csr::pick_variant(col_idxs, values);                  \
         B200_REQUIRE(v != b200::csr::kSlab, "col_idxs/values must be 32-byte aligned");          \
         b200::csr::DotArgs<VT> dot{work, ctx->counters + 1, dot_out, ctl};                       \
-        const bool w = v == b200::csr::kWarp || v == b200::csr::kRingV;                                                    \
+        const bool w = v != b200::csr::kTma;                                                    \
         return b200::csr::launch_slab<VT, IT, false, true>(                                      \
             ctx, plan->lanes, v, w ? plan->num_wtiles : plan->num_tiles,                         \
             w ? plan->wtiles : plan->tiles, nnz, row_ptrs, col_idxs, values, nullptr, b, 1,      \
