@@ -204,6 +204,8 @@ def run_gpu_arm(args, rank, world):
         def kernel_step():
             api._hcheck(hl.gkob_apply(Aloc.h, xe_h.h, y_h.h))
     ex.synchronize()
+    kernel_name = {2: "warp_stream_kernel", 4: "warp_pipe_kernel"}.get(
+        hl.gkob_csr_kernel_variant((A if world == 1 else Aloc).h), "warp_stream_kernel")
     for _ in range(max(args.warmup, 3)):
         step()
     with ClockSampler(local) as cs:
@@ -252,7 +254,7 @@ def run_gpu_arm(args, rank, world):
     achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "kernel": "b200::csr::warp_stream_kernel<double,int,1,false,false>",
+                "kernel": "b200::csr::%s<double,int,1,false,false>" % kernel_name,
                 "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_kernel}
     prof = os.path.join(ROOT, "profiles", "r01_csr_spmv_cfg2.json")
     if os.path.exists(prof):

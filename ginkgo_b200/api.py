@@ -168,6 +168,8 @@ class Csr(_SparseBase):
             _lib.check(fn(self.exec.ctx, self.size[0], self.nnz, self.row_ptrs.data_ptr(),
                           ctypes.byref(p)))
             self._plan = p
+            self.exec.run("b200_csr_plan_tune_%s_%s" % (self.vt, self.it), p, self.size[0],
+                          self.size[1], self.nnz, self.row_ptrs, self.col_idxs, self.values)
         return self._plan
 
     def _apply_impl(self, alpha, b, beta, x):
@@ -214,6 +216,7 @@ def _host():
         h.gkob_destroy.argtypes = [vp]
         h.gkob_launch_count.restype = ll
         h.gkob_launch_count.argtypes = [vp]
+        h.gkob_csr_kernel_variant.restype, h.gkob_csr_kernel_variant.argtypes = i, [vp]
         for s in ("f64", "f32"):
             f = getattr(h, "gkob_csr_view_%s_i32" % s)
             f.restype, f.argtypes = vp, [vp, ll, ll, ll, vp, vp, vp]

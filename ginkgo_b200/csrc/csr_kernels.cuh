@@ -1122,6 +1122,7 @@ struct b200_csr_plan {
     int64_t* wtiles = nullptr;  // same for the warp-stream kernel's kWTile-item tiles
     int lanes = 1;
     int device = 0;
+    int variant = -1;  // kernel variant chosen by b200_csr_plan_tune_*, -1 = not tuned
 };
 
 namespace b200 {
@@ -1156,11 +1157,12 @@ b200_status set_smem(K kernel, size_t bytes)
 // kernel variants
 enum Variant { kSlab = 0, kTma = 1, kWarp = 2, kRingV = 3, kPipe = 4 };
 
-inline Variant pick_variant(const void* col_idxs, const void* values)
+inline Variant pick_variant(const void* col_idxs, const void* values,
+                            const b200_csr_plan* plan = nullptr)
 {
     const uintptr_t a = (uintptr_t)col_idxs | (uintptr_t)values;
     static const char* env = getenv("B200_CSR_KERNEL");
-    Variant want = kWarp;
+    Variant want = (plan && plan->variant >= 0) ? (Variant)plan->variant : kWarp;
     if (env && !strcmp(env, "tma")) want = kTma;
     if (env && !strcmp(env, "slab")) want = kSlab;
     if (env && !strcmp(env, "ring")) want = kRingV;

@@ -50,7 +50,7 @@ b200_status spmv_impl(b200_ctx* ctx, const b200_csr_plan* plan, int64_t num_rows
             last = (const void*)b;
         }
     }
-    const Variant variant = pick_variant(col_idxs, values);
+    const Variant variant = pick_variant(col_idxs, values, plan);
     const int64_t num_tiles = variant_tiles(variant, num_rows, nnz);
     const int64_t* tiles = nullptr;
     int lanes;
@@ -111,10 +111,72 @@ b200_status plan_create(b200_ctx* ctx, int64_t num_rows, int64_t nnz, const I* r
     return B200_OK;
 }
 
+// Set-up time choice between the two warp kernels: the pipelined one wins where the gathers
+// of b are local (stencils, banded matrices: +10-14 %), the plain one where they are not
+// (uniformly random columns: +10 %) and on matrices too small to pipeline.  Both sum every
+// row in the same order, so the choice never changes a result bit.  Measured, not guessed:
+// each candidate runs `reps` times on the real matrix against a zero vector.
+template <typename V, typename I>
+b200_status plan_tune(b200_ctx* ctx, b200_csr_plan* plan, int64_t num_rows, int64_t num_cols,
+                      int64_t nnz, const I* row_ptrs, const I* col_idxs, const V* values)
+{
+    B200_REQUIRE(ctx && plan, "null argument");
+    B200_REQUIRE(plan->num_rows == num_rows && plan->nnz == nnz, "plan does not match the matrix");
+    plan->variant = kWarp;
+    const int64_t warps = (int64_t)ctx->num_sms * kWCtasPerSm * kWarpsPerCta;
+    if (num_rows == 0 || nnz == 0 || plan->num_wtiles < 4 * warps) return B200_OK;
+    B200_REQUIRE(row_ptrs && col_idxs && values, "null pointer");
+    V *b = nullptr, *c = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    b200_status st = B200_OK;
+    if (cudaMalloc((void**)&b, (size_t)num_cols * sizeof(V)) != cudaSuccess ||
+        cudaMalloc((void**)&c, (size_t)num_rows * sizeof(V)) != cudaSuccess ||
+        cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) {
+        cudaGetLastError();
+        cudaFree(b);
+        cudaFree(c);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+        return B200_OK;  // no room to measure: keep the default, this is only a tuning step
+    }
+    cudaMemsetAsync(b, 0, (size_t)num_cols * sizeof(V), ctx->stream);
+    const Variant cand[2] = {kWarp, kPipe};
+    float best = 0.f;
+    const int reps = 3;
+    for (int k = 0; k < 2 && st == B200_OK; ++k) {
+        float ms = 0.f;
+        for (int r = 0; r <= reps && st == B200_OK; ++r) {  // r == 0 warms up
+            if (r == 1) cudaEventRecord(e0, ctx->stream);
+            st = launch_slab<V, I, false, false>(ctx, plan->lanes, cand[k], plan->num_wtiles,
+                                                 plan->wtiles, nnz, row_ptrs, col_idxs, values,
+                                                 nullptr, b, 1, nullptr, c, 1);
+        }
+        cudaEventRecord(e1, ctx->stream);
+        if (cudaEventSynchronize(e1) != cudaSuccess) st = B200_ERR_CUDA;
+        if (st == B200_OK) cudaEventElapsedTime(&ms, e0, e1);
+        if (st == B200_OK && (k == 0 || ms < 0.97f * best)) {
+            best = ms;
+            plan->variant = cand[k];
+        }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(b);
+    cudaFree(c);
+    if (getenv("B200_DEBUG"))
+        fprintf(stderr, "[b200] csr plan tuned: rows %lld nnz %lld -> %s (%.3f ms / %d launches)\n",
+                (long long)num_rows, (long long)nnz,
+                plan->variant == kPipe ? "warp_pipe" : "warp_stream", best, reps);
+    if (st != B200_OK) set_error("csr plan tuning failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return st;
+}
+
 }  // namespace csr
 }  // namespace b200
 
 extern "C" {
+
+int b200_csr_plan_variant(const b200_csr_plan* plan) { return plan ? plan->variant : -1; }
 
 void b200_csr_plan_destroy(b200_csr_plan* plan)
 {
@@ -130,6 +192,14 @@ void b200_csr_plan_destroy(b200_csr_plan* plan)
                                                const IT* row_ptrs, b200_csr_plan** out)        \
     {                                                                                          \
         return b200::csr::plan_create<IT>(ctx, num_rows, nnz, row_ptrs, out);                  \
+    }                                                                                          \
+    b200_status b200_csr_plan_tune_##V##_##I(b200_ctx* ctx, b200_csr_plan* plan,               \
+                                             int64_t num_rows, int64_t num_cols, int64_t nnz,  \
+                                             const IT* row_ptrs, const IT* col_idxs,           \
+                                             const VT* values)                                 \
+    {                                                                                          \
+        return b200::csr::plan_tune<VT, IT>(ctx, plan, num_rows, num_cols, nnz, row_ptrs,      \
+                                            col_idxs, values);                                 \
     }                                                                                          \
     b200_status b200_csr_spmv_##V##_##I(                                                       \
         b200_ctx* ctx, const b200_csr_plan* plan, int64_t num_rows, int64_t num_cols,          \

@@ -306,7 +306,7 @@ B200_DEF_FCG(f32, float)
     {                                                                                            \
         B200_REQUIRE(ctx && plan && dot_out && work, "null argument (a plan is required)");      \
         B200_REQUIRE(plan->num_rows == num_rows && plan->nnz == nnz, "plan does not match");     \
-        const b200::csr::Variant v = b200::csr::pick_variant(col_idxs, values);                  \
+        const b200::csr::Variant v = b200::csr::pick_variant(col_idxs, values, plan);            \
         B200_REQUIRE(v != b200::csr::kSlab, "col_idxs/values must be 32-byte aligned");          \
         b200::csr::DotArgs<VT> dot{work, ctx->counters + 1, dot_out, ctl};                       \
         const bool w = v != b200::csr::kTma;                                                    \

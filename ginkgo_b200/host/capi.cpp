@@ -107,6 +107,21 @@ void gkob_destroy(void* handle) { delete static_cast<Handle*>(handle); }
 
 long long gkob_launch_count(void* exec) { return static_cast<Handle*>(exec)->exec->launch_count(); }
 
+// kernel variant the tuned plan of a Csr handle uses (2 = warp_stream, 4 = warp_pipe); -1 if
+// the handle is not a double/int32 or float/int32 Csr
+int gkob_csr_kernel_variant(void* csr)
+{
+    int v = -1;
+    guarded([&] {
+        auto op = static_cast<Handle*>(csr)->op.get();
+        if (auto a = dynamic_cast<const matrix::Csr<double, int32>*>(op))
+            v = b200_csr_plan_variant(a->get_plan());
+        else if (auto a = dynamic_cast<const matrix::Csr<float, int32>*>(op))
+            v = b200_csr_plan_variant(a->get_plan());
+    });
+    return v;
+}
+
 #define GKOB_DEF(V, S)                                                                          \
     void* gkob_csr_view_##S##_i32(void* exec, long long n, long long m, long long nnz,         \
                                   int32* rp, int32* ci, V* va)                                  \

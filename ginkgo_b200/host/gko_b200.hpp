@@ -136,6 +136,7 @@ GKOB_V(float, f32)
     template <>                                                                                 \
     struct viabi<V, I> {                                                                        \
         static constexpr auto csr_plan_create = b200_csr_plan_create_##S##_##T;                 \
+        static constexpr auto csr_plan_tune = b200_csr_plan_tune_##S##_##T;                     \
         static constexpr auto csr_spmv = b200_csr_spmv_##S##_##T;                               \
         static constexpr auto csr_advanced_spmv = b200_csr_advanced_spmv_##S##_##T;             \
         static constexpr auto csr_spmv_dot = b200_csr_spmv_dot_##S##_##T;                       \
@@ -545,9 +546,14 @@ public:
     // the cached row partition (the reference's srow / strategy->process())
     const b200_csr_plan* get_plan() const
     {
-        if (!plan_)
+        if (!plan_) {
             GKOB_CALL((viabi<V, I>::csr_plan_create(exec_->ctx(), size_.rows, values_.get_size(),
                                                     row_ptrs_.get_const_data(), &plan_)));
+            // strategy selection (reference: csr.hpp `automatical`), measured on the matrix
+            GKOB_CALL((viabi<V, I>::csr_plan_tune(
+                exec_->ctx(), plan_, size_.rows, size_.cols, values_.get_size(),
+                row_ptrs_.get_const_data(), col_idxs_.get_const_data(), values_.get_const_data())));
+        }
         return plan_;
     }
     std::unique_ptr<Dense<V>> extract_diagonal() const

@@ -85,10 +85,19 @@ b200_status b200_synchronize(b200_ctx* ctx);
  *   spmv:           c = A b
  *   advanced_spmv:  c = alpha A b + beta c      (beta == 0 never reads c)
  * `plan` may be NULL (the partition is then recomputed on the stream).
+ * plan_tune (optional, set-up phase, synchronises, not capturable) times the kernel
+ * variants on the matrix itself and records the faster one in the plan -- the analogue
+ * of the reference's strategy selection (include/ginkgo/core/matrix/csr.hpp `automatical`,
+ * which picks from nnz statistics); every variant sums rows in the same order, so the
+ * choice never changes a result.  plan_variant returns the recorded choice (-1 untuned).
  * ------------------------------------------------------------------------- */
 #define B200_DECL_CSR(V, VT, I, IT)                                                          \
     b200_status b200_csr_plan_create_##V##_##I(b200_ctx* ctx, int64_t num_rows, int64_t nnz, \
                                                const IT* row_ptrs, b200_csr_plan** out);     \
+    b200_status b200_csr_plan_tune_##V##_##I(b200_ctx* ctx, b200_csr_plan* plan,             \
+                                             int64_t num_rows, int64_t num_cols,             \
+                                             int64_t nnz, const IT* row_ptrs,                \
+                                             const IT* col_idxs, const VT* values);          \
     b200_status b200_csr_spmv_##V##_##I(                                                     \
         b200_ctx* ctx, const b200_csr_plan* plan, int64_t num_rows, int64_t num_cols,        \
         int64_t nnz, const IT* row_ptrs, const IT* col_idxs, const VT* values, const VT* b,  \
@@ -99,6 +108,7 @@ b200_status b200_synchronize(b200_ctx* ctx);
         const VT* alpha, const VT* b, int64_t b_stride, int64_t num_rhs, const VT* beta,     \
         VT* c, int64_t c_stride);
 void b200_csr_plan_destroy(b200_csr_plan* plan);
+int b200_csr_plan_variant(const b200_csr_plan* plan);
 
 /* ---------------------------------------------------------------------------
  * ELL (core/matrix/ell_kernels.hpp:21-35; reference/matrix/ell_kernels.cpp:29-120)

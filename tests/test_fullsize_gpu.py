@@ -55,7 +55,8 @@ def test_cfg2_full_size_properties(hexec, orc):
         y2 = torch.empty_like(y)
         y3 = torch.empty_like(y)
         x3 = 2 * x - 3 * x2
-    api._hcheck(h.gkob_apply(A.h, api.host_dense(hexec, x2).h, (d2 := api.host_dense(hexec, y2)).h))
+    d2i = api.host_dense(hexec, x2)  # handles must outlive the call
+    api._hcheck(h.gkob_apply(A.h, d2i.h, (d2 := api.host_dense(hexec, y2)).h))
     api._hcheck(h.gkob_apply(A.h, (d3i := api.host_dense(hexec, x3)).h,
                              (d3 := api.host_dense(hexec, y3)).h))
     hexec.synchronize()
@@ -102,3 +103,31 @@ def test_cfg3_full_size_operator_and_cg(hexec):
     hexec.synchronize()
     assert (r.norm() / ones.norm()).item() <= 1.05e-8
     assert 400 <= s.num_iterations <= 600
+
+
+@pytest.mark.parametrize("kind", ["stencil", "random"])
+def test_plan_tune_keeps_results_bit_identical(kind):
+    """b200_csr_plan_tune_* may pick either warp kernel; the result must not change by a bit
+    against the untuned (plan = NULL) launch, and the recorded choice must be a warp variant."""
+    import ctypes
+    import torch
+    from ginkgo_b200 import api, _lib
+    ex = api.B200Executor(0)
+    dev = ex.device
+    with torch.cuda.stream(ex.stream):
+        if kind == "stencil":
+            rp, ci, va = W.laplace(100, 3, xp="torch", device=dev)
+            n = 100 ** 3
+        else:
+            n = 1 << 20
+            rp, ci, va = W.random_csr(n, 8, xp="torch", device=dev, stream=5)
+        x = W.vector(n, xp="torch", device=dev)
+        y0 = torch.zeros(n, dtype=torch.float64, device=dev)
+    A = api.Csr(ex, (n, n), va, ci, rp)
+    X, Y = api.Dense(ex, x), api.Dense(ex, torch.zeros_like(y0))
+    A.apply(X, Y)
+    ex.run("b200_csr_spmv_f64_i32", None, n, n, A.nnz, rp, ci, va, x, 1, 1, y0, 1)
+    ex.synchronize()
+    variant = _lib.lib().b200_csr_plan_variant(A.plan())
+    assert variant in (2, 4)
+    assert torch.equal(Y.values.reshape(-1), y0)
