@@ -347,6 +347,7 @@ class DistMatrix:
         h.gkob_dist_matrix_create_f64_i32.restype = vp
         h.gkob_dist_matrix_create_f64_i32.argtypes = [vp, vp, i, i, ll, ll, ll, vp, vp, vp, vp, vp, vp]
         h.gkob_dist_spmv_f64.restype, h.gkob_dist_spmv_f64.argtypes = i, [vp, vp, vp]
+        h.gkob_dist_p2p.restype, h.gkob_dist_p2p.argtypes = i, [vp]
         h.gkob_dist_cg_create_f64.restype = i
         h.gkob_dist_cg_create_f64.argtypes = [vp, i, ll, i, i, ctypes.c_double, i, i]
         h.gkob_dist_cg_apply_f64.restype = i
@@ -383,6 +384,11 @@ class DistMatrix:
             self.send_idx.data_ptr() if self.send_idx.numel() else None)
         if not self.h:
             raise _lib.B200Error(h.gkob_last_error().decode())
+
+    @property
+    def p2p(self):
+        """bit 0: scalar all-reduces on peer memory, bit 1: halo exchange on peer memory"""
+        return _host().gkob_dist_p2p(self.h)
 
     def apply(self, x_ext, y_local):
         """y_local = A x; x_ext is [n_local owned | n_ghost] (ghosts filled by the exchange)"""

@@ -111,9 +111,29 @@ struct dtype<int64_t> {
         }                                                                                   \
     } while (0)
 
+// A peer window: one cudaMalloc'd block per rank, exported with cudaIpcGetMemHandle and
+// mapped by every other rank of the box, so kernels can store straight into a peer's HBM
+// through NVLink / NVSwitch.
+struct b200_peer_window {
+    void* local = nullptr;
+    size_t bytes = 0;
+    std::vector<void*> mapped;  // per rank, mapped[rank] == local
+};
+
 struct b200_comm {
     b200::nccl::ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
+    // peer-memory all-reduce of a few scalars (b200_comm_enable_p2p)
+    bool p2p = false;
+    b200_peer_window win;           // [flags 2 x nranks u64 | mailbox 2 x nranks x 8 cells of 8 B]
+    void** peer_base_dev = nullptr;  // device: nranks window base pointers
+    uint64_t* epoch_dev = nullptr;   // device: number of completed all-reduces
+    int* err_dev = nullptr;          // device: set by a kernel whose wait timed out (sticky)
+    int device = 0;
+    b200_ctx* ctx = nullptr;         // the context enable_p2p ran on (must outlive the comm)
+    // exported blocks of destroyed halos: freed in b200_comm_destroy after a barrier, because
+    // an exported block must not be freed while a peer still has it mapped
+    std::vector<void*> retired;
 };
 
 // halo plan: which owned entries go to which peer, where received entries land
@@ -125,6 +145,19 @@ struct b200_halo {
     void* send_buf = nullptr;     // device: n_send values
     size_t elem = 0;
     int device = 0;
+    // peer-memory exchange (b200_halo_enable_p2p): entries are stored straight into the
+    // owner-side landing slots of the peers, no NCCL call on the data path
+    bool p2p = false;
+    int rank = 0;
+    b200_peer_window win;           // [flags 2 x nranks u64 | landing slot 0 | landing slot 1]
+    size_t slot_off[2] = {0, 0};
+    int64_t* meta_dev = nullptr;    // device: send_off[nranks+1] | send_cnt[nranks] | recv_cnt[nranks]
+    void** peer_slot_dev = nullptr;  // device: [2][nranks] where my segment starts on peer p
+    uint64_t** peer_flag_dev = nullptr;  // device: [nranks] &flags[0][rank] on peer p
+    uint64_t* epoch_dev = nullptr;
+    unsigned* ticket_dev = nullptr;  // 2 self-resetting counters
+    int* err_dev = nullptr;          // the communicator's error word
+    b200_comm* comm = nullptr;       // owner of the retired-block list (must outlive the halo)
 };
 
 namespace b200 {
@@ -139,10 +172,306 @@ __global__ void pack_kernel(int64_t n, const int32_t* __restrict__ idx, const V*
     if (i < n) out[i] = x[idx[i]];
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Peer-memory collectives.  Synchronisation is by epoch-stamped flags in the receiver's
+// window: a sender stores its data, fences at system scope and releases flag[parity][sender]
+// = epoch on the receiver; the receiver acquires the flag before it reads.  Two parities:
+// a rank can only start epoch e+2 after every peer it talks to has finished reading epoch e
+// (it had to receive their epoch e+1 first), so slot e & 1 is free again.  The epoch lives
+// in device memory and is advanced by the kernels themselves, which keeps every call
+// capturable in a CUDA graph.  A wait that exceeds kSpinLimit cycles sets a sticky error
+// word instead of hanging the GPU.
+// ---------------------------------------------------------------------------------------
+constexpr long long kSpinLimit = 20000000000ll;  // ~10 s of SM clock
+
+__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p)
+{
+    uint64_t v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void wait_flag(const uint64_t* p, uint64_t epoch, int* err)
+{
+    if (*(volatile int*)err) return;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(p) < epoch) {
+        if (clock64() - t0 > kSpinLimit) {
+            *(volatile int*)err = 1;
+            return;
+        }
+        __nanosleep(40);
+    }
+}
+
+struct HaloDev {
+    int nranks, rank;
+    int64_t n_local, n_ghost, n_send;
+    const int32_t* send_idx;
+    const int64_t* meta;       // send_off[nranks+1] | send_cnt[nranks] | recv_cnt[nranks]
+    void* const* peer_slot;    // [2][nranks]
+    uint64_t* const* peer_flag;  // [nranks]
+    uint64_t* my_flags;        // [2][nranks]
+    const void* my_slot[2];
+    uint64_t* epoch;
+    unsigned* ticket;
+    int* err;
+};
+
+// pack + send in one kernel: every owned entry a peer references is stored directly into
+// that peer's landing slot (remote store over NVLink); the last CTA to finish releases the
+// epoch flag on every peer that receives from this rank.
+template <typename V>
+__global__ void __launch_bounds__(256) halo_push_kernel(HaloDev h, const V* __restrict__ x)
+{
+    const uint64_t e = *(volatile uint64_t*)h.epoch + 1;
+    const int par = (int)(e & 1);
+    const int64_t* send_off = h.meta;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < h.n_send; i += stride) {
+        int p = 0;
+        while (i >= send_off[p + 1]) ++p;
+        V* dst = (V*)h.peer_slot[par * h.nranks + p];
+        dst[i - send_off[p]] = x[h.send_idx[i]];
+    }
+    __threadfence_system();
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(h.ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last) {
+        if (threadIdx.x == 0) *h.ticket = 0;
+        const int64_t* send_cnt = h.meta + h.nranks + 1;
+        if ((int)threadIdx.x < h.nranks && send_cnt[threadIdx.x] > 0) {
+            __threadfence_system();
+            st_release_sys(h.peer_flag[threadIdx.x] + par * h.nranks, e);
+        }
+    }
+}
+
+// wait + unpack: acquire the epoch flag of every rank this one receives from, then move the
+// landing slot into the ghost tail of the extended vector.  The last CTA advances the epoch.
+template <typename V>
+__global__ void __launch_bounds__(256) halo_wait_kernel(HaloDev h, V* __restrict__ x_ext)
+{
+    const uint64_t e = *(volatile uint64_t*)h.epoch + 1;
+    const int par = (int)(e & 1);
+    const int64_t* recv_cnt = h.meta + 2 * h.nranks + 1;
+    if ((int)threadIdx.x < h.nranks && recv_cnt[threadIdx.x] > 0)
+        wait_flag(h.my_flags + par * h.nranks + threadIdx.x, e, h.err);
+    __syncthreads();
+    const V* src = (const V*)h.my_slot[par];
+    V* dst = x_ext + h.n_local;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < h.n_ghost; i += stride)
+        dst[i] = __ldcg(src + i);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(h.ticket + 1, 1u) == gridDim.x - 1) {
+            h.ticket[1] = 0;
+            *(volatile uint64_t*)h.epoch = e;
+        }
+    }
+}
+
+struct CommDev {
+    int nranks, rank;
+    void* const* peer_base;  // [nranks] window bases
+    uint64_t* epoch;
+    int* err;
+};
+constexpr int kMailCells = 8;  // values per all-reduce, 8-byte cells
+
+// sum all-reduce of <= 8 scalars in ONE single-CTA kernel: thread p stores this rank's values
+// into rank p's mailbox and releases its flag there, thread q waits for rank q's flag here,
+// then the values are added in rank order -- every rank computes the same bits, and the
+// result does not depend on a ring / tree schedule.
+template <typename V>
+__global__ void __launch_bounds__(64) p2p_allreduce_kernel(CommDev c, V* __restrict__ buf, int count)
+{
+    const uint64_t e = *(volatile uint64_t*)c.epoch + 1;
+    const int par = (int)(e & 1);
+    const int t = threadIdx.x;
+    const size_t flag_bytes = 2 * (size_t)c.nranks * sizeof(uint64_t);
+    __shared__ V mine[kMailCells];
+    if (t < count) mine[t] = buf[t];
+    __syncthreads();
+    if (t < c.nranks) {
+        char* base = (char*)c.peer_base[t];
+        V* cell = (V*)(base + flag_bytes + ((size_t)(par * c.nranks + c.rank) * kMailCells) * 8);
+        for (int k = 0; k < count; ++k) cell[k] = mine[k];
+        __threadfence_system();
+        st_release_sys((uint64_t*)base + par * c.nranks + c.rank, e);
+    }
+    char* my = (char*)c.peer_base[c.rank];
+    if (t < c.nranks) wait_flag((const uint64_t*)my + par * c.nranks + t, e, c.err);
+    __syncthreads();
+    if (t < count) {
+        V s = V(0);
+        for (int q = 0; q < c.nranks; ++q) {
+            const V* cell =
+                (const V*)(my + flag_bytes + ((size_t)(par * c.nranks + q) * kMailCells) * 8);
+            const V v = __ldcg(cell + t);
+            s = q == 0 ? v : s + v;
+        }
+        buf[t] = s;
+    }
+    __syncthreads();
+    if (t == 0) *(volatile uint64_t*)c.epoch = e;
+}
+
 }  // namespace dist
 }  // namespace b200
 
+namespace {
+
+using b200::nccl::api;
+
+inline size_t round256(size_t b) { return (b + 255) & ~size_t(255); }
+
+// all-gather of `bytes` host bytes per rank through the NCCL communicator (set-up only)
+b200_status allgather_host(b200_ctx* ctx, b200_comm* comm, const void* mine, size_t bytes,
+                           void* all)
+{
+    auto& a = api();
+    uint8_t* dev = nullptr;
+    B200_CUDA_CHECK(cudaMalloc((void**)&dev, bytes * (comm->nranks + 1)));
+    B200_CUDA_CHECK(cudaMemcpyAsync(dev, mine, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    int r = a.AllGather(dev, dev + bytes, bytes, b200::nccl::ncclUint8, comm->comm, ctx->stream);
+    if (r != b200::nccl::ncclSuccess) {
+        cudaFree(dev);
+        b200::set_error("ncclAllGather (set-up): %s", a.GetErrorString(r));
+        return B200_ERR_COMM;
+    }
+    B200_CUDA_CHECK(cudaMemcpyAsync(all, dev + bytes, bytes * comm->nranks, cudaMemcpyDeviceToHost,
+                                    ctx->stream));
+    B200_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(dev);
+    return B200_OK;
+}
+
+// unmap the peers' blocks; the own block is either freed (set-up failure: nobody uses it
+// any more, all ranks fail alike) or handed to `retire`
+void window_close(b200_peer_window* w, int rank, std::vector<void*>* retire = nullptr)
+{
+    for (size_t p = 0; p < w->mapped.size(); ++p)
+        if ((int)p != rank && w->mapped[p]) cudaIpcCloseMemHandle(w->mapped[p]);
+    w->mapped.clear();
+    if (w->local) {
+        if (retire)
+            retire->push_back(w->local);
+        else
+            cudaFree(w->local);
+    }
+    w->local = nullptr;
+}
+
+// Collective: allocate `bytes` (zeroed), exchange IPC handles, map every peer's block.
+// Every rank learns whether ALL ranks succeeded; on any failure nothing stays mapped.
+b200_status window_open(b200_ctx* ctx, b200_comm* comm, size_t bytes, b200_peer_window* w)
+{
+    const int n = comm->nranks;
+    struct Msg {
+        cudaIpcMemHandle_t handle;
+        int32_t ok;
+        int32_t pad[3];
+    };
+    static_assert(sizeof(Msg) % 16 == 0, "message layout");
+    Msg mine;
+    memset(&mine, 0, sizeof(mine));
+    w->bytes = bytes;
+    mine.ok = cudaMalloc(&w->local, bytes) == cudaSuccess &&
+              cudaMemsetAsync(w->local, 0, bytes, ctx->stream) == cudaSuccess &&
+              cudaStreamSynchronize(ctx->stream) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine.handle, w->local) == cudaSuccess;
+    if (!mine.ok) cudaGetLastError();
+    std::vector<Msg> all(n);
+    b200_status st = allgather_host(ctx, comm, &mine, sizeof(Msg), all.data());
+    if (st != B200_OK) return st;
+    bool ok = true;
+    for (int p = 0; p < n; ++p) ok = ok && all[p].ok;
+    int32_t opened = ok;
+    w->mapped.assign(n, nullptr);
+    if (ok) {
+        for (int p = 0; p < n && opened; ++p) {
+            if (p == comm->rank) {
+                w->mapped[p] = w->local;
+                continue;
+            }
+            cudaError_t e = cudaIpcOpenMemHandle(&w->mapped[p], all[p].handle,
+                                                 cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                b200::set_error("cudaIpcOpenMemHandle(rank %d): %s", p, cudaGetErrorString(e));
+                cudaGetLastError();
+                w->mapped[p] = nullptr;
+                opened = 0;
+            }
+        }
+    }
+    std::vector<int32_t> flags(n);
+    st = allgather_host(ctx, comm, &opened, sizeof(int32_t), flags.data());
+    if (st != B200_OK) return st;
+    for (int p = 0; p < n; ++p) ok = ok && flags[p];
+    if (!ok) {
+        window_close(w, comm->rank, &comm->retired);
+        if (!mine.ok || opened) b200::set_error("peer window: a rank could not export or map its block");
+        return B200_ERR_COMM;
+    }
+    return B200_OK;
+}
+
+}  // namespace
+
 extern "C" {
+
+// Collective over the communicator: switch the <= 8-value all-reduces to the peer-memory
+// kernel.  Returns B200_ERR_COMM (on every rank alike) if CUDA IPC is not available between
+// the processes; the NCCL path then stays in place.
+b200_status b200_comm_enable_p2p(b200_ctx* ctx, b200_comm* comm)
+{
+    B200_REQUIRE(ctx && comm, "null argument");
+    if (comm->p2p || comm->nranks == 1) return B200_OK;
+    B200_REQUIRE(comm->nranks <= 64, "peer-memory all-reduce supports up to 64 ranks");
+    B200_CUDA_CHECK(cudaSetDevice(ctx->device));
+    comm->device = ctx->device;
+    comm->ctx = ctx;
+    const size_t bytes =
+        2 * (size_t)comm->nranks * 8 + 2 * (size_t)comm->nranks * b200::dist::kMailCells * 8;
+    b200_status st = window_open(ctx, comm, bytes, &comm->win);
+    if (st != B200_OK) return st;
+    if (!comm->err_dev) {
+        B200_CUDA_CHECK(cudaMalloc((void**)&comm->err_dev, sizeof(int)));
+        B200_CUDA_CHECK(cudaMemsetAsync(comm->err_dev, 0, sizeof(int), ctx->stream));
+    }
+    B200_CUDA_CHECK(cudaMalloc((void**)&comm->peer_base_dev, sizeof(void*) * comm->nranks));
+    B200_CUDA_CHECK(cudaMalloc((void**)&comm->epoch_dev, sizeof(uint64_t)));
+    B200_CUDA_CHECK(cudaMemsetAsync(comm->epoch_dev, 0, sizeof(uint64_t), ctx->stream));
+    B200_CUDA_CHECK(cudaMemcpyAsync(comm->peer_base_dev, comm->win.mapped.data(),
+                                    sizeof(void*) * comm->nranks, cudaMemcpyHostToDevice,
+                                    ctx->stream));
+    B200_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    comm->p2p = true;
+    return B200_OK;
+}
+int32_t b200_comm_p2p_enabled(const b200_comm* comm) { return comm && comm->p2p; }
+/* 1 once a peer-memory wait timed out (a rank died or the call sequences diverged);  */
+/* synchronises the context's stream                                                   */
+int32_t b200_comm_p2p_error(b200_ctx* ctx, const b200_comm* comm)
+{
+    if (!ctx || !comm || !comm->err_dev) return 0;
+    int v = 0;
+    if (cudaMemcpyAsync(&v, comm->err_dev, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream) !=
+            cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+        return 1;
+    return v;
+}
+int32_t b200_halo_p2p_enabled(const b200_halo* h) { return h && h->p2p; }
 
 b200_status b200_comm_get_unique_id(uint8_t* id128)
 {
@@ -179,6 +508,23 @@ b200_status b200_comm_create(b200_ctx* ctx, const uint8_t* id128, int32_t rank, 
 void b200_comm_destroy(b200_comm* comm)
 {
     if (!comm) return;
+    if (comm->ctx || !comm->retired.empty()) {
+        cudaSetDevice(comm->device);
+        cudaDeviceSynchronize();
+        window_close(&comm->win, comm->rank, &comm->retired);
+        // barrier: every rank has unmapped its peers before anybody frees an exported block
+        if (comm->ctx && comm->comm && comm->err_dev &&
+            b200::nccl::api().AllReduce(comm->err_dev, comm->err_dev, 1, b200::nccl::ncclInt32,
+                                        b200::nccl::ncclSum, comm->comm,
+                                        comm->ctx->stream) == b200::nccl::ncclSuccess)
+            cudaStreamSynchronize(comm->ctx->stream);
+        else
+            cudaDeviceSynchronize();
+        for (void* blk : comm->retired) cudaFree(blk);
+        cudaFree(comm->peer_base_dev);
+        cudaFree(comm->epoch_dev);
+    }
+    if (comm->err_dev) cudaFree(comm->err_dev);
     if (comm->comm) b200::nccl::api().CommDestroy(comm->comm);
     delete comm;
 }
@@ -192,6 +538,15 @@ void b200_halo_destroy(b200_halo* h)
     cudaSetDevice(h->device);
     cudaFree(h->send_idx);
     cudaFree(h->send_buf);
+    if (h->p2p) {
+        cudaDeviceSynchronize();
+        window_close(&h->win, h->rank, h->comm ? &h->comm->retired : nullptr);
+        cudaFree(h->meta_dev);
+        cudaFree(h->peer_slot_dev);
+        cudaFree(h->peer_flag_dev);
+        cudaFree(h->epoch_dev);
+        cudaFree(h->ticket_dev);
+    }
     delete h;
 }
 int64_t b200_halo_num_ghost(const b200_halo* h) { return h->n_ghost; }
@@ -204,6 +559,13 @@ int64_t b200_halo_num_send(const b200_halo* h) { return h->n_send; }
     {                                                                                          \
         auto& a = b200::nccl::api();                                                           \
         if (comm->nranks == 1) return B200_OK;                                                 \
+        if (comm->p2p && count <= b200::dist::kMailCells) {                                    \
+            b200::dist::CommDev c{comm->nranks, comm->rank, comm->peer_base_dev,               \
+                                  comm->epoch_dev, comm->err_dev};                             \
+            b200::dist::p2p_allreduce_kernel<VT><<<1, 64, 0, ctx->stream>>>(c, buf, (int)count);\
+            B200_LAUNCH_CHECK(ctx);                                                            \
+            return B200_OK;                                                                    \
+        }                                                                                      \
         B200_NCCL_CHECK(a.AllReduce(buf, buf, (size_t)count, b200::nccl::dtype<VT>::v,         \
                                     b200::nccl::ncclSum, comm->comm, ctx->stream));            \
         return B200_OK;                                                                        \
@@ -224,6 +586,24 @@ int64_t b200_halo_num_send(const b200_halo* h) { return h->n_send; }
     {                                                                                          \
         auto& a = b200::nccl::api();                                                           \
         if (h->nranks == 1 || (h->n_send == 0 && h->n_ghost == 0)) return B200_OK;             \
+        if (h->p2p) {                                                                          \
+            b200::dist::HaloDev d{h->nranks, h->rank, h->n_local, h->n_ghost, h->n_send,       \
+                                  h->send_idx, h->meta_dev, h->peer_slot_dev,                  \
+                                  h->peer_flag_dev, (uint64_t*)h->win.local,                   \
+                                  {(char*)h->win.local + h->slot_off[0],                       \
+                                   (char*)h->win.local + h->slot_off[1]},                      \
+                                  h->epoch_dev, h->ticket_dev, h->err_dev};                    \
+            const int64_t cap = (int64_t)ctx->num_sms * 4;                                     \
+            int64_t gs = b200::ceildiv(h->n_send, 256 * 4);                                    \
+            gs = gs < 1 ? 1 : (gs > cap ? cap : gs);                                           \
+            b200::dist::halo_push_kernel<VT><<<(unsigned)gs, 256, 0, ctx->stream>>>(d, x_ext); \
+            B200_LAUNCH_CHECK(ctx);                                                            \
+            int64_t gr = b200::ceildiv(h->n_ghost, 256 * 4);                                   \
+            gr = gr < 1 ? 1 : (gr > cap ? cap : gr);                                           \
+            b200::dist::halo_wait_kernel<VT><<<(unsigned)gr, 256, 0, ctx->stream>>>(d, x_ext); \
+            B200_LAUNCH_CHECK(ctx);                                                            \
+            return B200_OK;                                                                    \
+        }                                                                                      \
         VT* sb = (VT*)h->send_buf;                                                             \
         if (h->n_send > 0) {                                                                   \
             b200::dist::pack_kernel<VT>                                                        \
@@ -286,6 +666,89 @@ b200_status b200_halo_create(b200_ctx* ctx, int32_t nranks, int64_t n_local, int
         B200_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     }
     *out = h;
+    return B200_OK;
+}
+
+
+// Collective over the communicator: move this halo plan onto peer memory.  Every rank
+// learns from the all-gathered send counts where its segment starts in each peer's landing
+// slot and how large each peer's window is.
+b200_status b200_halo_enable_p2p(b200_ctx* ctx, b200_comm* comm, b200_halo* h)
+{
+    B200_REQUIRE(ctx && comm && h, "null argument");
+    if (h->p2p || h->nranks == 1) return B200_OK;
+    B200_REQUIRE(h->nranks == comm->nranks, "halo and communicator differ in size");
+    B200_REQUIRE(h->nranks <= 256, "peer-memory halo supports up to 256 ranks");
+    B200_CUDA_CHECK(cudaSetDevice(ctx->device));
+    const int n = h->nranks, me = comm->rank;
+    h->rank = me;
+    h->comm = comm;
+    comm->device = ctx->device;
+    comm->ctx = ctx;
+    if (!comm->err_dev) {
+        B200_CUDA_CHECK(cudaMalloc((void**)&comm->err_dev, sizeof(int)));
+        B200_CUDA_CHECK(cudaMemsetAsync(comm->err_dev, 0, sizeof(int), ctx->stream));
+    }
+    h->err_dev = comm->err_dev;
+    // S[q][p] = number of entries rank q sends to rank p
+    std::vector<int64_t> S((size_t)n * n);
+    b200_status st = allgather_host(ctx, comm, h->send_count.data(), sizeof(int64_t) * n, S.data());
+    if (st != B200_OK) return st;
+    int32_t consistent = 1;
+    for (int q = 0; q < n; ++q)
+        if (S[(size_t)q * n + me] != h->recv_count[q]) consistent = 0;
+    std::vector<int32_t> cons(n);
+    st = allgather_host(ctx, comm, &consistent, sizeof(int32_t), cons.data());
+    if (st != B200_OK) return st;
+    for (int p = 0; p < n; ++p)
+        if (!cons[p]) {
+            b200::set_error("halo: send and receive counts of the ranks do not match");
+            return B200_ERR_INVALID;
+        }
+    const size_t flag_bytes = round256(2 * (size_t)n * sizeof(uint64_t));
+    auto ghosts_of = [&](int p) {
+        int64_t g = 0;
+        for (int q = 0; q < n; ++q) g += S[(size_t)q * n + p];
+        return g;
+    };
+    auto slot_bytes_of = [&](int p) { return round256((size_t)ghosts_of(p) * h->elem + 16); };
+    h->slot_off[0] = flag_bytes;
+    h->slot_off[1] = flag_bytes + slot_bytes_of(me);
+    st = window_open(ctx, comm, flag_bytes + 2 * slot_bytes_of(me), &h->win);
+    if (st != B200_OK) return st;
+    std::vector<void*> peer_slot(2 * (size_t)n);
+    std::vector<uint64_t*> peer_flag(n);
+    for (int p = 0; p < n; ++p) {
+        int64_t off = 0;  // where my segment starts in p's ghost numbering
+        for (int q = 0; q < me; ++q) off += S[(size_t)q * n + p];
+        char* base = (char*)h->win.mapped[p];
+        peer_slot[p] = base + flag_bytes + (size_t)off * h->elem;
+        peer_slot[n + p] = base + flag_bytes + slot_bytes_of(p) + (size_t)off * h->elem;
+        peer_flag[p] = (uint64_t*)base + me;
+    }
+    std::vector<int64_t> meta(3 * (size_t)n + 1);
+    for (int p = 0; p < n; ++p) {
+        meta[p] = h->send_off[p];
+        meta[n + 1 + p] = h->send_count[p];
+        meta[2 * n + 1 + p] = h->recv_count[p];
+    }
+    meta[n] = h->n_send;
+    B200_CUDA_CHECK(cudaMalloc((void**)&h->meta_dev, sizeof(int64_t) * meta.size()));
+    B200_CUDA_CHECK(cudaMalloc((void**)&h->peer_slot_dev, sizeof(void*) * peer_slot.size()));
+    B200_CUDA_CHECK(cudaMalloc((void**)&h->peer_flag_dev, sizeof(uint64_t*) * n));
+    B200_CUDA_CHECK(cudaMalloc((void**)&h->epoch_dev, sizeof(uint64_t)));
+    B200_CUDA_CHECK(cudaMalloc((void**)&h->ticket_dev, 2 * sizeof(unsigned)));
+    B200_CUDA_CHECK(cudaMemsetAsync(h->epoch_dev, 0, sizeof(uint64_t), ctx->stream));
+    B200_CUDA_CHECK(cudaMemsetAsync(h->ticket_dev, 0, 2 * sizeof(unsigned), ctx->stream));
+    B200_CUDA_CHECK(cudaMemcpyAsync(h->meta_dev, meta.data(), sizeof(int64_t) * meta.size(),
+                                    cudaMemcpyHostToDevice, ctx->stream));
+    B200_CUDA_CHECK(cudaMemcpyAsync(h->peer_slot_dev, peer_slot.data(),
+                                    sizeof(void*) * peer_slot.size(), cudaMemcpyHostToDevice,
+                                    ctx->stream));
+    B200_CUDA_CHECK(cudaMemcpyAsync(h->peer_flag_dev, peer_flag.data(), sizeof(uint64_t*) * n,
+                                    cudaMemcpyHostToDevice, ctx->stream));
+    B200_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    h->p2p = true;
     return B200_OK;
 }
 

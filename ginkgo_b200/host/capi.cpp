@@ -270,6 +270,14 @@ int gkob_dist_cg_apply_f64(void* dist, const double* b_local, double* x_local, l
 
 void gkob_dist_destroy(void* dist) { delete static_cast<DistHandle*>(dist); }
 
+// bit 0: all-reduces run on peer memory, bit 1: the halo exchange does
+int gkob_dist_p2p(void* dist)
+{
+    auto h = static_cast<DistHandle*>(dist);
+    return (b200_comm_p2p_enabled(h->comm->get()) ? 1 : 0) |
+           (b200_halo_p2p_enabled(h->A->get_halo()) ? 2 : 0);
+}
+
 // x = op(b)   /   x = alpha op(b) + beta x  (alpha, beta: 1x1 Dense handles)
 int gkob_apply(void* op, void* b, void* x)
 {

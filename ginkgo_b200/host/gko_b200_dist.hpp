@@ -5,6 +5,9 @@
 // One process per GPU; rank p owns rows [offsets[p], offsets[p+1]).
 #pragma once
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "gko_b200.hpp"
 
 namespace gko_b200 {
@@ -20,7 +23,24 @@ public:
         auto c = std::shared_ptr<communicator>(new communicator());
         c->exec_ = exec;
         GKOB_CALL(b200_comm_create(exec->ctx(), id128, rank, size, &c->comm_));
+        // peer-memory collectives over NVLink/NVSwitch unless B200_P2P=0; when CUDA IPC is not
+        // available between the ranks every rank gets the same error and NCCL stays in use
+        const char* env = std::getenv("B200_P2P");
+        c->want_p2p_ = !(env && env[0] == '0');
+        if (c->want_p2p_ && size > 1 &&
+            b200_comm_enable_p2p(exec->ctx(), c->comm_) != B200_OK) {
+            std::fprintf(stderr, "[gko_b200] rank %d: peer-memory collectives unavailable (%s), using NCCL\n",
+                         rank, b200_last_error());
+            c->want_p2p_ = false;
+        }
         return c;
+    }
+    bool use_p2p() const { return want_p2p_ && b200_comm_p2p_enabled(comm_); }
+    // throws if a peer-memory wait timed out (synchronises the stream)
+    void check() const
+    {
+        if (b200_comm_p2p_error(exec_->ctx(), comm_))
+            throw Error("peer-memory collective timed out: a rank stopped or the call sequences diverged");
     }
     ~communicator() { b200_comm_destroy(comm_); }
     int rank() const { return b200_comm_rank(comm_); }
@@ -31,6 +51,7 @@ private:
     communicator() = default;
     std::shared_ptr<const Executor> exec_;
     b200_comm* comm_ = nullptr;
+    bool want_p2p_ = true;
 };
 
 template <typename V>
@@ -62,6 +83,10 @@ public:
         GKOB_CALL(b200_halo_create(exec->ctx(), comm->size(), local_->get_size().rows, n_ghost,
                                    send_counts.data(), recv_counts.data(), send_idx_dev,
                                    (int32)sizeof(V), &halo_));
+        if (comm->use_p2p() &&
+            b200_halo_enable_p2p(exec->ctx(), comm->get(), halo_) != B200_OK)
+            std::fprintf(stderr, "[gko_b200] rank %d: peer-memory halo unavailable (%s), using NCCL\n",
+                         comm->rank(), b200_last_error());
     }
     ~Matrix() { b200_halo_destroy(halo_); }
     size_type n_local() const { return local_->get_size().rows; }
@@ -181,6 +206,7 @@ public:
         }
         num_iterations_ = h[1];
         status_ = (uint8)h[0];
+        A_->get_communicator()->check();
     }
     int64 get_num_iterations() const { return num_iterations_; }
     uint8 get_stop_status() const { return status_; }

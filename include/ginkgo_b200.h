@@ -439,6 +439,21 @@ b200_status b200_halo_create(b200_ctx* ctx, int32_t nranks, int64_t n_local, int
 void b200_halo_destroy(b200_halo* halo);
 int64_t b200_halo_num_ghost(const b200_halo* halo);
 int64_t b200_halo_num_send(const b200_halo* halo);
+/* Peer-memory data path (collective calls, set-up phase).  After enable_p2p the halo
+ * exchange is two kernels -- pack+remote-store into the peers' landing slots over NVLink /
+ * NVSwitch, and wait+unpack -- and all-reduces of <= 8 values are ONE single-CTA kernel that
+ * stores into every peer's mailbox and sums in rank order (deterministic, identical bits on
+ * every rank).  Windows are cudaMalloc blocks shared with cudaIpc*; synchronisation is by
+ * epoch flags (st.release.sys / ld.acquire.sys), so everything stays CUDA-graph capturable.
+ * Both return B200_ERR_COMM on EVERY rank alike when CUDA IPC is unavailable; the NCCL
+ * send/recv + all-reduce path then remains in use.  p2p_error: 1 after a wait timed out.
+ * Lifetime: the context outlives the communicator, the communicator outlives its halos
+ * (exported blocks are only freed in b200_comm_destroy, after a barrier). */
+b200_status b200_comm_enable_p2p(b200_ctx* ctx, b200_comm* comm);
+b200_status b200_halo_enable_p2p(b200_ctx* ctx, b200_comm* comm, b200_halo* halo);
+int32_t b200_comm_p2p_enabled(const b200_comm* comm);
+int32_t b200_halo_p2p_enabled(const b200_halo* halo);
+int32_t b200_comm_p2p_error(b200_ctx* ctx, const b200_comm* comm);
 #define B200_DECL_COMM(V, VT)                                                                  \
     b200_status b200_comm_allreduce_sum_##V(b200_ctx* ctx, b200_comm* comm, VT* buf,           \
                                             int64_t count);                                    \

@@ -45,8 +45,29 @@ for name, kw in [("lap3d_40", dict(grid=40, dims=3)), ("cfg2_small", dict(n=2000
     A.apply(x_ext, y)
     ex.synchronize()
     same = torch.equal(y, y1[r0:r1])
+    # repeated exchanges with changing data (epochs / double-buffered landing slots)
+    for k in range(1, 6):
+        with torch.cuda.stream(ex.stream):
+            xk = W.vector(n, stream=20 + k, xp="torch", device=dev)
+            x_ext[:A.n_local] = xk[r0:r1]
+            xdk = api.host_dense(ex, xk)
+        api._hcheck(_h.gkob_apply(A1.h, xdk.h, yd1.h))
+        A.apply(x_ext, y)
+        ex.synchronize()
+        same = same and torch.equal(y, y1[r0:r1])
     ok &= same
-    print("rank %d %s: n_local=%d n_ghost=%d spmv bit-equal=%s" % (rank, name, A.n_local, A.n_ghost, same), flush=True)
+    with torch.cuda.stream(ex.stream):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(5):
+            A.apply(x_ext, y)
+        dist.barrier()
+        e0.record(ex.stream)
+        for _ in range(100):
+            A.apply(x_ext, y)
+        e1.record(ex.stream)
+    ex.synchronize()
+    print("rank %d %s: n_local=%d n_ghost=%d p2p=%d spmv bit-equal=%s  %.1f us/apply"
+          % (rank, name, A.n_local, A.n_ghost, A.p2p, same, e0.elapsed_time(e1) * 10), flush=True)
     if name.startswith("lap"):
         b = torch.ones(n, dtype=torch.float64, device=dev)
         s1 = api.HostSolver(ex, "cg", A1, precond_max_bs=1, max_iters=2000, reduction=1e-9, fused=True)

@@ -112,7 +112,7 @@ def test_plan_tune_keeps_results_bit_identical(kind):
     import ctypes
     import torch
     from ginkgo_b200 import api, _lib
-    ex = api.B200Executor(0)
+    ex = api.B200Executor.create(0)
     dev = ex.device
     with torch.cuda.stream(ex.stream):
         if kind == "stencil":
