@@ -199,12 +199,15 @@ __device__ __forceinline__ void wait_flag(const uint64_t* p, uint64_t epoch, int
 {
     if (*(volatile int*)err) return;
     const long long t0 = clock64();
+    int polls = 0;
     while (ld_acquire_sys(p) < epoch) {
-        if (clock64() - t0 > kSpinLimit) {
-            *(volatile int*)err = 1;
-            return;
+        if (++polls > 4096) {  // back off only once the wait is clearly not a short one
+            if (clock64() - t0 > kSpinLimit) {
+                *(volatile int*)err = 1;
+                return;
+            }
+            __nanosleep(100);
         }
-        __nanosleep(40);
     }
 }
 
@@ -232,16 +235,37 @@ __global__ void __launch_bounds__(256) halo_push_kernel(HaloDev h, const V* __re
     const int par = (int)(e & 1);
     const int64_t* send_off = h.meta;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < h.n_send; i += stride) {
-        int p = 0;
-        while (i >= send_off[p + 1]) ++p;
-        V* dst = (V*)h.peer_slot[par * h.nranks + p];
-        dst[i - send_off[p]] = x[h.send_idx[i]];
+    constexpr int U = 4;  // independent gather -> remote-store chains per thread
+    for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < h.n_send;
+         i0 += U * stride) {
+        int32_t idx[U];
+        V v[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int64_t i = i0 + k * stride;
+            idx[k] = i < h.n_send ? h.send_idx[i] : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) v[k] = x[idx[k]];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int64_t i = i0 + k * stride;
+            if (i < h.n_send) {
+                int p = 0;
+                while (i >= send_off[p + 1]) ++p;
+                V* dst = (V*)h.peer_slot[par * h.nranks + p];
+                dst[i - send_off[p]] = v[k];
+            }
+        }
     }
-    __threadfence_system();
+    // one system-scope fence per CTA: the barrier orders every thread's stores before
+    // thread 0's fence, which is cumulative (the cooperative-groups grid-sync idiom)
     __shared__ bool last;
     __syncthreads();
-    if (threadIdx.x == 0) last = atomicAdd(h.ticket, 1u) == gridDim.x - 1;
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        last = atomicAdd(h.ticket, 1u) == gridDim.x - 1;
+    }
     __syncthreads();
     if (last) {
         if (threadIdx.x == 0) *h.ticket = 0;

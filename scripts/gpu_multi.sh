@@ -8,7 +8,7 @@ B200_P2P=$P2P timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per
 done
 for P2P in 1 0; do
 echo "== bench $N GPUs B200_P2P=$P2P"
-B200_P2P=$P2P timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2952$P2P bench.py --gpus $N --steps 100 --warmup 5 --no-gmres 2>gpurun_out/bench${N}_p2p$P2P.err | tee gpurun_out/bench${N}_p2p$P2P.json | python -c "
+B200_P2P=$P2P timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2952$P2P bench.py --gpus $N --steps 50 --warmup 5 --no-gmres 2>gpurun_out/bench${N}_p2p$P2P.err | tee gpurun_out/bench${N}_p2p$P2P.json | python -c "
 import sys,json
 for l in sys.stdin:
     try: d=json.loads(l)
