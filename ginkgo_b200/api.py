@@ -217,6 +217,10 @@ def _host():
         h.gkob_launch_count.restype = ll
         h.gkob_launch_count.argtypes = [vp]
         h.gkob_csr_kernel_variant.restype, h.gkob_csr_kernel_variant.argtypes = i, [vp]
+        h.gkob_csr_convert.restype = vp
+        h.gkob_csr_convert.argtypes = [vp, ctypes.c_char_p, ll, ll, d, d]
+        h.gkob_csr_sort_by_column_index.restype = i
+        h.gkob_csr_sort_by_column_index.argtypes = [vp]
         for s in ("f64", "f32"):
             f = getattr(h, "gkob_csr_view_%s_i32" % s)
             f.restype, f.argtypes = vp, [vp, ll, ll, ll, vp, vp, vp]
@@ -284,6 +288,25 @@ def host_csr(exec_, size, values, col_idxs, row_ptrs):
                            col_idxs.data_ptr(), values.data_ptr()), (values, col_idxs, row_ptrs))
     o.vt = s
     return o
+
+
+_HYB = {"automatic": 0, "column_limit": 1, "imbalance_limit": 2, "imbalance_bounded_limit": 3,
+        "minimal_storage_limit": 4}
+
+
+def host_convert(A, fmt, slice_size=64, stride_factor=1, strategy="automatic", columns=0,
+                 percent=0.8, ratio=0.0001):
+    """Csr::convert_to(Ell | Sellp | Coo | Hybrid) on the device; returns the new LinOp"""
+    p0, p1 = (slice_size, stride_factor) if fmt == "sellp" else (_HYB[strategy], columns)
+    o = _HostObj(A.exec, _host().gkob_csr_convert(A.h, fmt.encode(), p0, p1, float(percent),
+                                                  float(ratio)))
+    o.vt = A.vt
+    return o
+
+
+def host_sort_by_column_index(A):
+    """Csr::sort_by_column_index in place (on the tensors the handle views)"""
+    _hcheck(_host().gkob_csr_sort_by_column_index(A.h))
 
 
 def host_dense(exec_, t, cols=None, stride=None):

@@ -89,6 +89,44 @@ std::unique_ptr<LinOp> make_solver(std::shared_ptr<Executor> exec, int kind,
 }
 }  // namespace
 
+// Csr::convert_to on the device: fmt = "ell" | "sellp" (p0 slice_size, p1 stride_factor) |
+// "coo" | "hybrid" (p0: 0 automatic, 1 column_limit(p1), 2 imbalance_limit(pd),
+// 3 imbalance_bounded_limit(pd, pd2), 4 minimal_storage_limit).  Returns a new LinOp handle.
+template <typename V>
+static std::shared_ptr<LinOp> convert_csr(const matrix::Csr<V, int32>* a, const std::string& f,
+                                          long long p0, long long p1, double pd, double pd2)
+{
+    auto e = a->get_executor();
+    if (f == "ell") {
+        auto t = matrix::Ell<V, int32>::create(e);
+        a->convert_to(t.get());
+        return std::shared_ptr<LinOp>(std::move(t));
+    }
+    if (f == "sellp") {
+        auto t = matrix::Sellp<V, int32>::create(e, (size_type)p0, (size_type)p1);
+        a->convert_to(t.get());
+        return std::shared_ptr<LinOp>(std::move(t));
+    }
+    if (f == "coo") {
+        auto t = matrix::Coo<V, int32>::create(e);
+        a->convert_to(t.get());
+        return std::shared_ptr<LinOp>(std::move(t));
+    }
+    if (f == "hybrid") {
+        using H = matrix::Hybrid<V, int32>;
+        auto st = p0 == 1   ? H::column_limit((size_type)p1)
+                  : p0 == 2 ? H::imbalance_limit(pd)
+                  : p0 == 3 ? H::imbalance_bounded_limit(pd, pd2)
+                  : p0 == 4 ? H::minimal_storage_limit()
+                            : H::automatic();
+        auto t = H::create(e, st);
+        a->convert_to(t.get());
+        return std::shared_ptr<LinOp>(std::move(t));
+    }
+    throw NotSupported("gkob_csr_convert: unknown format");
+}
+
+
 extern "C" {
 
 const char* gkob_last_error() { return g_err.c_str(); }
@@ -106,6 +144,39 @@ void* gkob_exec_create(int device, void* stream)
 void gkob_destroy(void* handle) { delete static_cast<Handle*>(handle); }
 
 long long gkob_launch_count(void* exec) { return static_cast<Handle*>(exec)->exec->launch_count(); }
+
+void* gkob_csr_convert(void* csr, const char* fmt, long long p0, long long p1, double pd, double pd2)
+{
+    auto src = static_cast<Handle*>(csr);
+    Handle* h = new Handle{src->exec, nullptr};
+    if (guarded([&] {
+            auto op = src->op.get();
+            if (auto a = dynamic_cast<const matrix::Csr<double, int32>*>(op))
+                h->op = convert_csr<double>(a, fmt, p0, p1, pd, pd2);
+            else if (auto a = dynamic_cast<const matrix::Csr<float, int32>*>(op))
+                h->op = convert_csr<float>(a, fmt, p0, p1, pd, pd2);
+            else
+                throw NotSupported("gkob_csr_convert: handle is not a Csr<double|float, int32>");
+        })) {
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+
+// Csr::sort_by_column_index in place (the handle's arrays, i.e. the caller's views)
+int gkob_csr_sort_by_column_index(void* csr)
+{
+    return guarded([&] {
+        auto op = static_cast<Handle*>(csr)->op.get();
+        if (auto a = dynamic_cast<matrix::Csr<double, int32>*>(op))
+            a->sort_by_column_index();
+        else if (auto a = dynamic_cast<matrix::Csr<float, int32>*>(op))
+            a->sort_by_column_index();
+        else
+            throw NotSupported("gkob_csr_sort_by_column_index: not a Csr<double|float, int32>");
+    });
+}
 
 // kernel variant the tuned plan of a Csr handle uses (2 = warp_stream, 4 = warp_pipe); -1 if
 // the handle is not a double/int32 or float/int32 Csr

@@ -141,6 +141,16 @@ GKOB_V(float, f32)
         static constexpr auto csr_advanced_spmv = b200_csr_advanced_spmv_##S##_##T;             \
         static constexpr auto csr_spmv_dot = b200_csr_spmv_dot_##S##_##T;                       \
         static constexpr auto csr_extract_diagonal = b200_csr_extract_diagonal_##S##_##T;       \
+        static constexpr auto csr_convert_to_ell = b200_csr_convert_to_ell_##S##_##T;           \
+        static constexpr auto csr_convert_to_sellp = b200_csr_convert_to_sellp_##S##_##T;       \
+        static constexpr auto csr_convert_to_hybrid = b200_csr_convert_to_hybrid_##S##_##T;     \
+        static constexpr auto csr_sort_by_column_index = b200_csr_sort_by_column_index_##S##_##T; \
+        static constexpr auto ell_compute_max_row_nnz = b200_ell_compute_max_row_nnz_##T;       \
+        static constexpr auto sellp_compute_slice_sets = b200_sellp_compute_slice_sets_##T;     \
+        static constexpr auto csr_compute_hybrid_coo_row_ptrs =                                 \
+            b200_csr_compute_hybrid_coo_row_ptrs_##T;                                           \
+        static constexpr auto csr_row_nnz_order_statistic = b200_csr_row_nnz_order_statistic_##T; \
+        static constexpr auto convert_ptrs_to_idxs = b200_convert_ptrs_to_idxs_##T;             \
         static constexpr auto ell_spmv = b200_ell_spmv_##S##_##T;                               \
         static constexpr auto ell_advanced_spmv = b200_ell_advanced_spmv_##S##_##T;             \
         static constexpr auto sellp_spmv = b200_sellp_spmv_##S##_##T;                           \
@@ -520,6 +530,15 @@ std::unique_ptr<Dense<V>> scalar(V v, std::shared_ptr<const Executor> exec)
 
 // ---- Csr (include/ginkgo/core/matrix/csr.hpp) ------------------------------------------------
 template <typename V, typename I>
+class Ell;
+template <typename V, typename I>
+class Sellp;
+template <typename V, typename I>
+class Coo;
+template <typename V, typename I>
+class Hybrid;
+
+template <typename V, typename I>
 class Csr : public LinOp {
 public:
     using value_type = V;
@@ -556,6 +575,13 @@ public:
         }
         return plan_;
     }
+    // Csr::convert_to(Ell|Sellp|Coo|Hybrid) and sort_by_column_index on the device
+    // (core/matrix/csr.cpp:285-300, :419-530, :1402); defined in gko_b200_convert.hpp
+    void convert_to(Ell<V, I>* result) const;
+    void convert_to(Sellp<V, I>* result) const;
+    void convert_to(Coo<V, I>* result) const;
+    void convert_to(Hybrid<V, I>* result) const;
+    void sort_by_column_index();
     std::unique_ptr<Dense<V>> extract_diagonal() const
     {
         auto d = Dense<V>::create(exec_, dim2{std::min(size_.rows, size_.cols), 1});
@@ -616,10 +642,20 @@ public:
         return std::unique_ptr<Ell>(new Ell(exec, size, num_stored_per_row, stride,
                                             std::move(values), std::move(col_idxs)));
     }
+    // empty matrix, to be filled by Csr::convert_to
+    static std::unique_ptr<Ell> create(std::shared_ptr<const Executor> exec)
+    {
+        return std::unique_ptr<Ell>(new Ell(exec, dim2{}, 0, 0, array<V>(exec, 0), array<I>(exec, 0)));
+    }
     size_type get_num_stored_elements_per_row() const { return width_; }
     size_type get_stride() const { return stride_; }
+    const V* get_const_values() const { return values_.get_const_data(); }
+    const I* get_const_col_idxs() const { return col_idxs_.get_const_data(); }
+    size_type get_num_stored_elements() const { return values_.get_size(); }
 
 protected:
+    friend class Csr<V, I>;
+    friend class Hybrid<V, I>;
     Ell(std::shared_ptr<const Executor> exec, dim2 size, size_type w, size_type stride, array<V> v,
         array<I> c)
         : LinOp(std::move(exec), size), width_(w), stride_(stride), values_(std::move(v)),
@@ -663,8 +699,28 @@ public:
                                                 std::move(slice_lengths), std::move(values),
                                                 std::move(col_idxs)));
     }
+    // empty matrix with the reference's defaults (slice_size 64, stride_factor 1:
+    // include/ginkgo/core/matrix/sellp.hpp), to be filled by Csr::convert_to
+    static std::unique_ptr<Sellp> create(std::shared_ptr<const Executor> exec,
+                                         size_type slice_size = 64, size_type stride_factor = 1)
+    {
+        auto r = std::unique_ptr<Sellp>(new Sellp(exec, dim2{}, slice_size,
+                                                  array<std::uint64_t>(exec, 1),
+                                                  array<std::uint64_t>(exec, 0), array<V>(exec, 0),
+                                                  array<I>(exec, 0)));
+        r->stride_factor_ = stride_factor;
+        return r;
+    }
+    size_type get_slice_size() const { return slice_size_; }
+    size_type get_stride_factor() const { return stride_factor_; }
+    const std::uint64_t* get_const_slice_sets() const { return sets_.get_const_data(); }
+    const std::uint64_t* get_const_slice_lengths() const { return lens_.get_const_data(); }
+    const V* get_const_values() const { return values_.get_const_data(); }
+    const I* get_const_col_idxs() const { return col_idxs_.get_const_data(); }
+    size_type get_num_stored_elements() const { return values_.get_size(); }
 
 protected:
+    friend class Csr<V, I>;
     Sellp(std::shared_ptr<const Executor> exec, dim2 size, size_type ss, array<std::uint64_t> sets,
           array<std::uint64_t> lens, array<V> v, array<I> c)
         : LinOp(std::move(exec), size), slice_size_(ss), sets_(std::move(sets)),
@@ -694,6 +750,7 @@ protected:
 
 private:
     size_type slice_size_;
+    size_type stride_factor_ = 1;
     array<std::uint64_t> sets_, lens_;
     array<V> values_;
     array<I> col_idxs_;
@@ -708,12 +765,23 @@ public:
         return std::unique_ptr<Coo>(
             new Coo(exec, size, std::move(values), std::move(col_idxs), std::move(row_idxs)));
     }
+    static std::unique_ptr<Coo> create(std::shared_ptr<const Executor> exec)
+    {
+        return std::unique_ptr<Coo>(
+            new Coo(exec, dim2{}, array<V>(exec, 0), array<I>(exec, 0), array<I>(exec, 0)));
+    }
     ~Coo() override { b200_coo_plan_destroy(plan_); }
+    const V* get_const_values() const { return values_.get_const_data(); }
+    const I* get_const_col_idxs() const { return col_idxs_.get_const_data(); }
+    const I* get_const_row_idxs() const { return row_idxs_.get_const_data(); }
+    size_type get_num_stored_elements() const { return values_.get_size(); }
     // x += A b   /   x += alpha A b   (Coo::apply2, used by Hybrid)
     void apply2(const LinOp* b, LinOp* x) const { run(2, nullptr, b, nullptr, x); }
     void apply2(const LinOp* alpha, const LinOp* b, LinOp* x) const { run(3, alpha, b, nullptr, x); }
 
 protected:
+    friend class Csr<V, I>;
+    friend class Hybrid<V, I>;
     Coo(std::shared_ptr<const Executor> exec, dim2 size, array<V> v, array<I> c, array<I> r)
         : LinOp(std::move(exec), size), values_(std::move(v)), col_idxs_(std::move(c)),
           row_idxs_(std::move(r))
@@ -779,8 +847,61 @@ public:
     {
         return std::unique_ptr<Hybrid>(new Hybrid(exec, std::move(ell), std::move(coo)));
     }
+    // How many entries per row go into the ELL part (include/ginkgo/core/matrix/
+    // hybrid.hpp:188-352).  The sorted-row-length lookup of imbalance_limit is one device
+    // order statistic instead of the reference's host std::sort.
+    struct strategy_type {
+        enum kind_t { column_limit_k, imbalance_limit_k, imbalance_bounded_limit_k } kind;
+        size_type columns;
+        double percent, ratio;
+        size_type compute_ell_num_stored_elements_per_row(const Executor* exec, const I* row_ptrs,
+                                                          size_type num_rows) const
+        {
+            if (kind == column_limit_k) return columns;
+            if (num_rows == 0) return 0;
+            const double pct = std::min(std::max(percent, 0.0), 1.0);
+            const int64 k = pct < 1 ? (int64)(size_type)(num_rows * pct) : (int64)num_rows - 1;
+            int64 v = 0;
+            GKOB_CALL((viabi<V, I>::csr_row_nnz_order_statistic(exec->ctx(), row_ptrs, num_rows, k, &v)));
+            if (kind == imbalance_bounded_limit_k)
+                return std::min((size_type)v, (size_type)(num_rows * ratio));
+            return (size_type)v;
+        }
+    };
+    static strategy_type column_limit(size_type num_columns = 0)
+    {
+        return {strategy_type::column_limit_k, num_columns, 0.0, 0.0};
+    }
+    static strategy_type imbalance_limit(double percent = 0.8)
+    {
+        return {strategy_type::imbalance_limit_k, 0, percent, 0.0};
+    }
+    static strategy_type imbalance_bounded_limit(double percent = 0.8, double ratio = 0.0001)
+    {
+        return {strategy_type::imbalance_bounded_limit_k, 0, percent, ratio};
+    }
+    static strategy_type minimal_storage_limit()
+    {
+        return imbalance_limit(static_cast<double>(sizeof(I)) / (sizeof(V) + 2 * sizeof(I)));
+    }
+    static strategy_type automatic() { return imbalance_bounded_limit(1.0 / 3.0, 0.001); }
+    // empty matrix, to be filled by Csr::convert_to
+    static std::unique_ptr<Hybrid> create(std::shared_ptr<const Executor> exec,
+                                          strategy_type strategy = automatic())
+    {
+        auto r = std::unique_ptr<Hybrid>(new Hybrid(exec, Ell<V, I>::create(exec), Coo<V, I>::create(exec)));
+        r->strategy_ = strategy;
+        return r;
+    }
+    const Ell<V, I>* get_ell() const { return ell_.get(); }
+    const Coo<V, I>* get_coo() const { return coo_.get(); }
+    size_type get_ell_num_stored_elements_per_row() const { return ell_->get_num_stored_elements_per_row(); }
+    size_type get_ell_stride() const { return ell_->get_stride(); }
+    size_type get_coo_num_stored_elements() const { return coo_->get_num_stored_elements(); }
+    const strategy_type& get_strategy() const { return strategy_; }
 
 protected:
+    friend class Csr<V, I>;
     Hybrid(std::shared_ptr<const Executor> exec, std::unique_ptr<Ell<V, I>> ell,
            std::unique_ptr<Coo<V, I>> coo)
         : LinOp(std::move(exec), ell->get_size()), ell_(std::move(ell)), coo_(std::move(coo))
@@ -799,6 +920,7 @@ protected:
 private:
     std::unique_ptr<Ell<V, I>> ell_;
     std::unique_ptr<Coo<V, I>> coo_;
+    strategy_type strategy_ = automatic();
 };
 
 // matrix::Identity: apply == copy (default preconditioner of the solvers)
@@ -831,4 +953,5 @@ using Vec = matrix::Dense<V>;
 
 }  // namespace gko_b200
 
+#include "gko_b200_convert.hpp"
 #include "gko_b200_solvers.hpp"

@@ -418,6 +418,59 @@ B200_DECL_EXTRACT_DIAG(f32, float, i32, int32_t)
 B200_DECL_EXTRACT_DIAG(f32, float, i64, int64_t)
 
 /* ---------------------------------------------------------------------------
+ * CSR -> ELL / SELL-P / Hybrid on the device, and the in-row column sort.
+ * Bit-exact against the reference kernels:
+ *   ell::compute_max_row_nnz (reference/matrix/ell_kernels.cpp:130-140; result on the host),
+ *   csr::convert_to_ell (reference/matrix/csr_kernels.cpp:573-598),
+ *   sellp::compute_slice_sets (reference/matrix/sellp_kernels.cpp:107-130; slice_sets has
+ *   num_slices + 1 entries, slice_lengths num_slices, both size_type = uint64),
+ *   csr::convert_to_sellp (reference/matrix/csr_kernels.cpp:528-567),
+ *   csr::compute_hybrid_coo_row_ptrs + csr::convert_to_hybrid
+ *   (core/matrix/csr.cpp:419-441, reference/matrix/csr_kernels.cpp:910-953; the ELL part is
+ *   initialised for all ell_stride rows like the reference does),
+ *   row_nnz_order_statistic: the sorted-row-length lookup of Hybrid's imbalance_limit
+ *   strategy (include/ginkgo/core/matrix/hybrid.hpp:222-243),
+ *   csr::sort_by_column_index (reference/matrix/csr_kernels.cpp:1272-1290; stable, i.e.
+ *   identical to the reference for rows with distinct columns, which is all its unstable
+ *   std::sort defines).
+ * ------------------------------------------------------------------------- */
+#define B200_DECL_CONVERT_FMT_I(I, IT)                                                         \
+    b200_status b200_ell_compute_max_row_nnz_##I(b200_ctx* ctx, const IT* row_ptrs,            \
+                                                 int64_t num_rows, int64_t* max_nnz_host);     \
+    b200_status b200_sellp_compute_slice_sets_##I(                                             \
+        b200_ctx* ctx, const IT* row_ptrs, int64_t num_rows, int64_t slice_size,               \
+        int64_t stride_factor, uint64_t* slice_sets, uint64_t* slice_lengths);                 \
+    b200_status b200_csr_compute_hybrid_coo_row_ptrs_##I(b200_ctx* ctx, const IT* row_ptrs,    \
+                                                         int64_t num_rows, int64_t ell_lim,    \
+                                                         int64_t* coo_row_ptrs);               \
+    b200_status b200_csr_row_nnz_order_statistic_##I(b200_ctx* ctx, const IT* row_ptrs,        \
+                                                     int64_t num_rows, int64_t k,              \
+                                                     int64_t* value_host);
+#define B200_DECL_CONVERT_FMT(V, VT, I, IT)                                                    \
+    b200_status b200_csr_convert_to_ell_##V##_##I(                                             \
+        b200_ctx* ctx, int64_t num_rows, const IT* row_ptrs, const IT* col_idxs,               \
+        const VT* values, int64_t num_stored_per_row, int64_t ell_stride, IT* ell_col_idxs,    \
+        VT* ell_values);                                                                       \
+    b200_status b200_csr_convert_to_sellp_##V##_##I(                                           \
+        b200_ctx* ctx, int64_t num_rows, int64_t slice_size, const uint64_t* slice_sets,       \
+        const uint64_t* slice_lengths, const IT* row_ptrs, const IT* col_idxs,                 \
+        const VT* values, IT* sellp_col_idxs, VT* sellp_values);                               \
+    b200_status b200_csr_convert_to_hybrid_##V##_##I(                                          \
+        b200_ctx* ctx, int64_t num_rows, const IT* row_ptrs, const IT* col_idxs,               \
+        const VT* values, int64_t ell_lim, int64_t ell_stride, IT* ell_col_idxs,               \
+        VT* ell_values, const int64_t* coo_row_ptrs, IT* coo_row_idxs, IT* coo_col_idxs,       \
+        VT* coo_values);                                                                       \
+    b200_status b200_csr_sort_by_column_index_##V##_##I(b200_ctx* ctx, int64_t num_rows,       \
+                                                        const IT* row_ptrs, IT* col_idxs,      \
+                                                        VT* values);
+B200_DECL_CONVERT_FMT_I(i32, int32_t)
+B200_DECL_CONVERT_FMT_I(i64, int64_t)
+B200_DECL_CONVERT_FMT(f64, double, i32, int32_t)
+B200_DECL_CONVERT_FMT(f64, double, i64, int64_t)
+B200_DECL_CONVERT_FMT(f32, float, i32, int32_t)
+B200_DECL_CONVERT_FMT(f32, float, i64, int64_t)
+
+/* ---------------------------------------------------------------------------
  * Multi-GPU (one process per GPU, 1-D row partition, NCCL over NVLink/NVSwitch):
  * the B200 replacement of the reference's MPI layer on this path --
  * experimental::distributed::Matrix::apply halo gather (core/distributed/matrix.cpp:450-509,

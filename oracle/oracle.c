@@ -25,6 +25,74 @@
 ORC_CONVERT(i32, int32_t)
 ORC_CONVERT(i64, int64_t)
 
+static int orc_cmp_i64(const void* a, const void* b)
+{
+    const int64_t x = *(const int64_t*)a, y = *(const int64_t*)b;
+    return (x > y) - (x < y);
+}
+
+/* reference/matrix/ell_kernels.cpp:130-140 compute_max_row_nnz;
+ * reference/matrix/sellp_kernels.cpp:107-130 compute_slice_sets (per-slice maximum rounded up
+ * to stride_factor, then prefix_sum_nonnegative over num_slices + 1 entries);
+ * core/matrix/csr.cpp:419-441 + reference `compute_hybrid_coo_row_ptrs`: prefix sum of
+ * max(row_nnz - ell_lim, 0);
+ * include/ginkgo/core/matrix/hybrid.hpp:222-243 imbalance_limit: std::sort of the row
+ * lengths, value at position k. */
+#define ORC_CONVERT_FMT(IS, I)                                                              \
+    void orc_ell_compute_max_row_nnz_##IS(const I* ptrs, int64_t num_rows, int64_t* max_nnz) \
+    {                                                                                       \
+        *max_nnz = 0;                                                                       \
+        for (int64_t i = 1; i <= num_rows; ++i) {                                           \
+            const int64_t len = (int64_t)ptrs[i] - (int64_t)ptrs[i - 1];                    \
+            if (len > *max_nnz) *max_nnz = len;                                             \
+        }                                                                                   \
+    }                                                                                       \
+    void orc_sellp_compute_slice_sets_##IS(const I* ptrs, int64_t num_rows,                 \
+                                           int64_t slice_size, int64_t stride_factor,       \
+                                           uint64_t* slice_sets, uint64_t* slice_lengths)   \
+    {                                                                                       \
+        const int64_t num_slices = (num_rows + slice_size - 1) / slice_size;                \
+        for (int64_t slice = 0; slice < num_slices; ++slice) {                              \
+            uint64_t slice_length = 0;                                                      \
+            for (int64_t lr = 0; lr < slice_size; ++lr) {                                   \
+                const int64_t row = slice * slice_size + lr;                                \
+                const int64_t len = row < num_rows ? (int64_t)ptrs[row + 1] - ptrs[row] : 0;\
+                const uint64_t padded =                                                     \
+                    (uint64_t)((len + stride_factor - 1) / stride_factor * stride_factor);  \
+                if (padded > slice_length) slice_length = padded;                           \
+            }                                                                               \
+            slice_lengths[slice] = slice_length;                                            \
+        }                                                                                   \
+        uint64_t run = 0;                                                                   \
+        for (int64_t slice = 0; slice < num_slices; ++slice) {                              \
+            slice_sets[slice] = run;                                                        \
+            run += slice_lengths[slice];                                                    \
+        }                                                                                   \
+        slice_sets[num_slices] = run;                                                       \
+    }                                                                                       \
+    void orc_csr_compute_hybrid_coo_row_ptrs_##IS(const I* ptrs, int64_t num_rows,          \
+                                                  int64_t ell_lim, int64_t* coo_row_ptrs)   \
+    {                                                                                       \
+        int64_t run = 0;                                                                    \
+        for (int64_t r = 0; r < num_rows; ++r) {                                            \
+            const int64_t len = (int64_t)ptrs[r + 1] - (int64_t)ptrs[r];                    \
+            coo_row_ptrs[r] = run;                                                          \
+            run += len > ell_lim ? len - ell_lim : 0;                                       \
+        }                                                                                   \
+        coo_row_ptrs[num_rows] = run;                                                       \
+    }                                                                                       \
+    void orc_csr_row_nnz_order_statistic_##IS(const I* ptrs, int64_t num_rows, int64_t k,   \
+                                              int64_t* value)                               \
+    {                                                                                       \
+        int64_t* len = (int64_t*)malloc(sizeof(int64_t) * (size_t)(num_rows > 0 ? num_rows : 1)); \
+        for (int64_t r = 0; r < num_rows; ++r) len[r] = (int64_t)ptrs[r + 1] - (int64_t)ptrs[r]; \
+        qsort(len, (size_t)num_rows, sizeof(int64_t), orc_cmp_i64);                         \
+        *value = len[k];                                                                    \
+        free(len);                                                                          \
+    }
+ORC_CONVERT_FMT(i32, int32_t)
+ORC_CONVERT_FMT(i64, int64_t)
+
 /* ---- double ---- */
 #define V double
 #define VS f64

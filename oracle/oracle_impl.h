@@ -577,6 +577,103 @@ void FNI(csr_extract_diagonal)(int64_t n, const I* rp, const I* ci, const V* va,
     }
 }
 
+/* reference/matrix/csr_kernels.cpp:573-598 convert_to_ell: every (row, i < width) slot is
+ * reset to (0, -1) and the row's entries copied in order; rows >= num_rows of a padded
+ * stride are not touched. */
+void FNI(csr_convert_to_ell)(int64_t num_rows, const I* rp, const I* ci, const V* va,
+                             int64_t width, int64_t stride, I* ecols, V* evals)
+{
+    for (int64_t row = 0; row < num_rows; ++row) {
+        for (int64_t i = 0; i < width; ++i) {
+            evals[row + i * stride] = 0;
+            ecols[row + i * stride] = (I)-1;
+        }
+        for (int64_t i = 0; i < (int64_t)rp[row + 1] - (int64_t)rp[row]; ++i) {
+            evals[row + i * stride] = va[rp[row] + i];
+            ecols[row + i * stride] = ci[rp[row] + i];
+        }
+    }
+}
+
+/* reference/matrix/csr_kernels.cpp:528-567 convert_to_sellp */
+void FNI(csr_convert_to_sellp)(int64_t num_rows, int64_t slice_size, const uint64_t* slice_sets,
+                               const uint64_t* slice_lengths, const I* rp, const I* ci,
+                               const V* va, I* scols, V* svals)
+{
+    const int64_t slice_num = (num_rows + slice_size - 1) / slice_size;
+    for (int64_t slice = 0; slice < slice_num; ++slice) {
+        for (int64_t row = 0; row < slice_size; ++row) {
+            const int64_t global_row = slice * slice_size + row;
+            if (global_row >= num_rows) break;
+            int64_t ind = (int64_t)slice_sets[slice] * slice_size + row;
+            for (int64_t k = rp[global_row]; k < (int64_t)rp[global_row + 1]; ++k) {
+                svals[ind] = va[k];
+                scols[ind] = ci[k];
+                ind += slice_size;
+            }
+            for (int64_t i = ind;
+                 i < (int64_t)(slice_sets[slice] + slice_lengths[slice]) * slice_size + row;
+                 i += slice_size) {
+                scols[i] = (I)-1;
+                svals[i] = 0;
+            }
+        }
+    }
+}
+
+/* reference/matrix/csr_kernels.cpp:910-953 convert_to_hybrid: the whole ELL part
+ * (ell_stride rows x ell_lim) is reset, then each row fills ELL first and spills into COO */
+void FNI(csr_convert_to_hybrid)(int64_t num_rows, const I* rp, const I* ci, const V* va,
+                                int64_t ell_lim, int64_t ell_stride, I* ecols, V* evals,
+                                const int64_t* coo_row_ptrs, I* crows, I* ccols, V* cvals)
+{
+    (void)coo_row_ptrs; /* the reference kernel ignores them as well (sequential counter) */
+    for (int64_t i = 0; i < ell_lim; ++i)
+        for (int64_t j = 0; j < ell_stride; ++j) {
+            evals[j + i * ell_stride] = 0;
+            ecols[j + i * ell_stride] = (I)-1;
+        }
+    int64_t csr_idx = 0, coo_idx = 0;
+    for (int64_t row = 0; row < num_rows; ++row) {
+        int64_t ell_idx = 0;
+        while (csr_idx < (int64_t)rp[row + 1]) {
+            if (ell_idx < ell_lim) {
+                evals[row + ell_idx * ell_stride] = va[csr_idx];
+                ecols[row + ell_idx * ell_stride] = ci[csr_idx];
+                ++ell_idx;
+            } else {
+                cvals[coo_idx] = va[csr_idx];
+                ccols[coo_idx] = ci[csr_idx];
+                crows[coo_idx] = (I)row;
+                ++coo_idx;
+            }
+            ++csr_idx;
+        }
+    }
+}
+
+/* reference/matrix/csr_kernels.cpp:1272-1290 sort_by_column_index: std::sort of the
+ * (col, value) pairs of each row by column.  Restated as a stable insertion sort; identical
+ * for rows with distinct columns (all that an unstable sort defines). */
+void FNI(csr_sort_by_column_index)(int64_t num_rows, const I* rp, I* ci, V* va)
+{
+    for (int64_t row = 0; row < num_rows; ++row) {
+        const int64_t s = rp[row], e = rp[row + 1];
+        for (int64_t i = s + 1; i < e; ++i) {
+            const I c = ci[i];
+            const V v = va[i];
+            int64_t j = i - 1;
+            while (j >= s && ci[j] > c) {
+                ci[j + 1] = ci[j];
+                va[j + 1] = va[j];
+                --j;
+            }
+            ci[j + 1] = c;
+            va[j + 1] = v;
+        }
+    }
+}
+
 /* reference/preconditioner/jacobi_kernels.cpp:419-447 (apply_block), :460-520 (apply /
  * simple_apply); storage scheme include/ginkgo/core/preconditioner/jacobi.hpp:37-141 */
 void FNI(jacobi_apply)(int64_t num_blocks, int32_t max_block_size, int64_t block_offset, int64_t group_offset,

@@ -103,3 +103,40 @@ def jacobi_generate(rp, ci, va, max_bs, block_ptrs=None):
     return dict(block_offset=int(meta[0]), group_offset=int(meta[1]), group_power=int(meta[2]),
                 num_blocks=int(meta[3]), blocks=blocks[:meta[4]].copy(),
                 block_ptrs=ptrs[:meta[3] + 1].copy())
+
+
+def convert(fmt, rp, ci, va, n_cols, slice_size=64, stride_factor=1, strategy=0, columns=0,
+            percent=0.8, ratio=0.0001):
+    """Csr::convert_to(Ell|Sellp|Hybrid) / Csr::sort_by_column_index of the real reference.
+    Returns a dict of the result arrays (see oracle/ref_shim.cpp `convert_impl`)."""
+    n, nnz = len(rp) - 1, len(va)
+    lens = np.diff(rp.astype(np.int64)) if n else np.zeros(0, np.int64)
+    width = int(lens.max()) if n else 0
+    pad = (width + stride_factor) if fmt == "sellp" else max(width, int(columns))
+    rows_pad = (n + slice_size) if fmt == "sellp" else n
+    cap = max(1, pad * rows_pad, nnz)
+    vals = np.zeros(cap, va.dtype)
+    cols = np.zeros(cap, np.int32)
+    ns = (n + slice_size - 1) // slice_size
+    aux0, aux1 = np.zeros(ns + 2, np.uint64), np.zeros(ns + 1, np.uint64)
+    crows, ccols, cvals = np.zeros(nnz + 1, np.int32), np.zeros(nnz + 1, np.int32), np.zeros(nnz + 1, va.dtype)
+    meta = np.zeros(4, np.int64)
+    if fmt == "sellp":
+        p0, p1 = slice_size, stride_factor
+    else:
+        p0, p1 = strategy, columns
+    st = lib().refshim_convert(fmt.encode(), _vt(va), n, n_cols, nnz, _p(rp), _p(ci), _p(va), p0, p1,
+                               float(percent), float(ratio), _p(meta), _p(vals), _p(cols), cap,
+                               _p(aux0), _p(aux1), _p(crows), _p(ccols), _p(cvals), nnz + 1)
+    assert st == 0, st
+    if fmt == "sort":
+        return dict(cols=cols[:nnz], vals=vals[:nnz])
+    if fmt == "ell":
+        w, stride = int(meta[0]), int(meta[1])
+        return dict(width=w, stride=stride, cols=cols[:w * stride], vals=vals[:w * stride])
+    if fmt == "sellp":
+        tot = int(meta[1])
+        return dict(slice_sets=aux0[:ns + 1], slice_lengths=aux1[:ns], cols=cols[:tot], vals=vals[:tot])
+    w, stride, cn = int(meta[0]), int(meta[1]), int(meta[2])
+    return dict(ell_lim=w, ell_stride=stride, coo_nnz=cn, cols=cols[:w * stride],
+                vals=vals[:w * stride], coo_rows=crows[:cn], coo_cols=ccols[:cn], coo_vals=cvals[:cn])

@@ -25,9 +25,15 @@ def rel_err(a, b):
 
 class OutInt:
     """int32 out-parameter (all_converged / one_changed)"""
+    ctype = ctypes.c_int32
 
     def __init__(self):
         self.value = None
+
+
+class OutI64(OutInt):
+    """int64 out-parameter in HOST memory (max_row_nnz, order statistic)"""
+    ctype = ctypes.c_int64
 
 
 class Oracle:
@@ -42,7 +48,7 @@ class Oracle:
         boxes, conv = [], []
         for a in args:
             if isinstance(a, OutInt):
-                b = ctypes.c_int32(0)
+                b = a.ctype(0)
                 boxes.append((a, b))
                 conv.append(ctypes.byref(b))
             elif isinstance(a, np.ndarray):
@@ -86,7 +92,7 @@ class Cuda:
         with torch.cuda.stream(self.stream):
             for a in args:
                 if isinstance(a, OutInt):
-                    b = ctypes.c_int32(0)
+                    b = a.ctype(0)
                     boxes.append((a, b))
                     conv.append(ctypes.byref(b))
                 elif isinstance(a, np.ndarray):
@@ -238,3 +244,29 @@ def orc_solve(kind, vt, rp, ci, va, b, x0, precond=0, jac=None, **kw):
     return x, it, stop
 
 
+
+
+def hybrid_ell_lim(be, rp, n, m, strategy, columns, percent, ratio, vbytes, ibytes):
+    """Hybrid strategy -> ELL width through the backend's order statistic, following
+    include/ginkgo/core/matrix/hybrid.hpp:188-352 (column_limit, imbalance_limit,
+    imbalance_bounded_limit, minimal_storage_limit, automatic) and the `ell_lim > num_cols`
+    clamp of core/matrix/csr.cpp:428-431."""
+    def imbalance(pct):
+        pct = min(max(pct, 0.0), 1.0)
+        if n == 0:
+            return 0
+        k = int(n * pct) if pct < 1 else n - 1
+        out = OutI64()
+        be("csr_row_nnz_order_statistic_i32", rp, n, k, out)
+        return int(out.value)
+    if strategy == 1:
+        lim = columns
+    elif strategy == 2:
+        lim = imbalance(percent)
+    elif strategy == 3:
+        lim = min(imbalance(percent), int(n * ratio))
+    elif strategy == 4:
+        lim = imbalance(ibytes / (vbytes + 2 * ibytes))
+    else:
+        lim = min(imbalance(1.0 / 3.0), int(n * 0.001))
+    return min(lim, m)

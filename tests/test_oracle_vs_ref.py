@@ -115,3 +115,96 @@ def test_cfg1_cg_jacobi_matches_survey_probe():
                               reduction=1e-8, exec_kind=1)
     assert itr == 579
     assert H.rel_err(xo, xr) < 1e-12
+
+
+# ---------------------------------------------------------------- conversions
+def _conv_matrix(rng, vt, kind):
+    n, m = 777, 650
+    if kind == "empty_rows":
+        lens = rng.integers(0, 3, n) * rng.integers(0, 2, n)
+    elif kind == "skewed":
+        lens = rng.integers(0, 12, n)
+        lens[rng.integers(0, n, 5)] = rng.integers(100, 300, 5)
+    else:
+        lens = rng.integers(0, 40, n)
+    return (n, m) + H.random_csr(rng, n, m, lens, vt, "i32")
+
+
+@pytest.mark.parametrize("kind", ["uniform", "skewed", "empty_rows"])
+@pytest.mark.parametrize("vt", ["f64", "f32"])
+def test_convert_to_ell_matches_reference(orc, vt, kind):
+    n, m, rp, ci, va = _conv_matrix(np.random.default_rng(5), vt, kind)
+    r = ref.convert("ell", rp, ci, va, m)
+    mx = H.OutI64()
+    orc("ell_compute_max_row_nnz_i32", rp, n, mx)
+    assert mx.value == r["width"] and r["stride"] == n
+    cols = np.full(r["width"] * n, 77, np.int32)
+    vals = np.full(r["width"] * n, 7, VT[vt])
+    orc("csr_convert_to_ell_%s_i32" % vt, n, rp, ci, va, r["width"], n, cols, vals)
+    assert np.array_equal(cols, r["cols"]) and np.array_equal(vals, r["vals"])
+
+
+@pytest.mark.parametrize("kind", ["uniform", "skewed", "empty_rows"])
+@pytest.mark.parametrize("slice_size,stride_factor", [(64, 1), (32, 4), (8, 3)])
+def test_convert_to_sellp_matches_reference(orc, kind, slice_size, stride_factor):
+    vt = "f64"
+    n, m, rp, ci, va = _conv_matrix(np.random.default_rng(6), vt, kind)
+    r = ref.convert("sellp", rp, ci, va, m, slice_size=slice_size, stride_factor=stride_factor)
+    ns = (n + slice_size - 1) // slice_size
+    ss, sl = np.zeros(ns + 1, np.uint64), np.zeros(ns, np.uint64)
+    orc("sellp_compute_slice_sets_i32", rp, n, slice_size, stride_factor, ss, sl)
+    assert np.array_equal(ss, r["slice_sets"]) and np.array_equal(sl, r["slice_lengths"])
+    tot = int(ss[-1]) * slice_size
+    assert tot == len(r["cols"])
+    # slots of rows past num_rows in the last slice are never written by the reference:
+    # compare only what it defines (start from its own buffer for those)
+    cols, vals = r["cols"].copy(), r["vals"].copy()
+    keep_c, keep_v = cols.copy(), vals.copy()
+    cols[:] = 77
+    vals[:] = 7
+    orc("csr_convert_to_sellp_%s_i32" % vt, n, slice_size, ss, sl, rp, ci, va, cols, vals)
+    defined = np.ones(tot, bool)
+    for s in range(ns):
+        for lr in range(slice_size):
+            if s * slice_size + lr >= n:
+                idx = (int(ss[s]) + np.arange(int(sl[s]))) * slice_size + lr
+                defined[idx] = False
+    assert np.array_equal(cols[defined], keep_c[defined])
+    assert np.array_equal(vals[defined], keep_v[defined])
+    assert np.all(cols[~defined] == 77)
+
+
+@pytest.mark.parametrize("kind", ["uniform", "skewed", "empty_rows"])
+@pytest.mark.parametrize("strategy", [(0, 0, 0, 0), (1, 3, 0, 0), (2, 0, 0.8, 0), (3, 0, 0.5, 0.01), (4, 0, 0, 0)])
+def test_convert_to_hybrid_matches_reference(orc, kind, strategy):
+    vt = "f64"
+    n, m, rp, ci, va = _conv_matrix(np.random.default_rng(7), vt, kind)
+    sk, columns, percent, ratio = strategy
+    r = ref.convert("hybrid", rp, ci, va, m, strategy=sk, columns=columns, percent=percent, ratio=ratio)
+    ell_lim = H.hybrid_ell_lim(orc, rp, n, m, sk, columns, percent, ratio, vbytes=8, ibytes=4)
+    assert ell_lim == r["ell_lim"] and r["ell_stride"] == n
+    crp = np.zeros(n + 1, np.int64)
+    orc("csr_compute_hybrid_coo_row_ptrs_i32", rp, n, ell_lim, crp)
+    assert crp[-1] == r["coo_nnz"]
+    ec, ev = np.full(ell_lim * n, 77, np.int32), np.full(ell_lim * n, 7, VT[vt])
+    cn = int(crp[-1])
+    cr, cc, cv = np.zeros(cn, np.int32), np.zeros(cn, np.int32), np.zeros(cn, VT[vt])
+    orc("csr_convert_to_hybrid_%s_i32" % vt, n, rp, ci, va, ell_lim, n, ec, ev, crp, cr, cc, cv)
+    for a, b in ((ec, r["cols"]), (ev, r["vals"]), (cr, r["coo_rows"]), (cc, r["coo_cols"]),
+                 (cv, r["coo_vals"])):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("vt", ["f64", "f32"])
+def test_sort_by_column_index_matches_reference(orc, vt):
+    rng = np.random.default_rng(8)
+    n, m, rp, ci, va = _conv_matrix(rng, vt, "skewed")
+    ci2, va2 = ci.copy(), va.copy()
+    for r_ in range(n):  # shuffle inside the rows (columns stay distinct)
+        s, e = rp[r_], rp[r_ + 1]
+        perm = rng.permutation(e - s)
+        ci2[s:e], va2[s:e] = ci[s:e][perm], va[s:e][perm]
+    r = ref.convert("sort", rp, ci2, va2, m)
+    orc("csr_sort_by_column_index_%s_i32" % vt, n, rp, ci2, va2)
+    assert np.array_equal(ci2, r["cols"]) and np.array_equal(va2, r["vals"])
+    assert np.array_equal(ci2, ci) and np.array_equal(va2, va)

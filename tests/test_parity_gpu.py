@@ -528,3 +528,94 @@ def test_hybrid_is_ell_plus_coo(orc, cuda, vt):
     orc("csr_spmv_%s_i32" % vt, n, m, len(va), rp, ci, va, x, 1, 1, yo, 1)
     # same left-to-right order: ELL part first, COO part appended
     assert np.array_equal(y, yo)
+
+
+# ------------------------------------------- CSR -> ELL / SELL-P / Hybrid, sort (8f-1)
+@pytest.mark.parametrize("vt", VTS)
+@pytest.mark.parametrize("it", ITS)
+@pytest.mark.parametrize("kind", ["ref_common", "empty_rows", "all_empty", "long_rows"])
+def test_convert_to_ell_bit_exact(orc, cuda, vt, it, kind):
+    rng = np.random.default_rng(31)
+    n, m, rp, ci, va = csr_case(rng, kind, vt, it)
+    mo, mc = H.OutI64(), H.OutI64()
+    orc("ell_compute_max_row_nnz_" + it, rp, n, mo)
+    cuda("ell_compute_max_row_nnz_" + it, rp, n, mc)
+    assert mo.value == mc.value == (int(np.diff(rp).max()) if n else 0)
+    width, stride = mo.value, n + 3  # padded stride: rows >= n must stay untouched
+    a, b = both(orc, cuda, "csr_convert_to_ell_%s_%s" % (vt, it),
+                lambda: [n, rp, ci, va, width, stride, np.full(width * stride, 77, IT[it]),
+                         np.full(width * stride, 7, VT[vt])])
+    assert np.array_equal(a[-1], b[-1]) and np.array_equal(a[-2], b[-2])
+
+
+@pytest.mark.parametrize("it", ITS)
+@pytest.mark.parametrize("kind", ["ref_common", "empty_rows", "all_empty", "long_rows"])
+@pytest.mark.parametrize("slice_size,stride_factor", [(64, 1), (32, 4), (8, 3)])
+def test_convert_to_sellp_bit_exact(orc, cuda, it, kind, slice_size, stride_factor):
+    vt = "f64"
+    rng = np.random.default_rng(32)
+    n, m, rp, ci, va = csr_case(rng, kind, vt, it)
+    ns = (n + slice_size - 1) // slice_size
+    a, b = both(orc, cuda, "sellp_compute_slice_sets_" + it,
+                lambda: [rp, n, slice_size, stride_factor, np.full(ns + 1, 9, np.uint64),
+                         np.full(max(ns, 1), 9, np.uint64)])
+    assert np.array_equal(a[-2], b[-2]) and np.array_equal(a[-1][:ns], b[-1][:ns])
+    ss, sl = a[-2], a[-1]
+    tot = int(ss[-1]) * slice_size
+    a, b = both(orc, cuda, "csr_convert_to_sellp_%s_%s" % (vt, it),
+                lambda: [n, slice_size, ss, sl, rp, ci, va, np.full(max(tot, 1), 77, IT[it]),
+                         np.full(max(tot, 1), 7, VT[vt])])
+    assert np.array_equal(a[-1], b[-1]) and np.array_equal(a[-2], b[-2])
+
+
+@pytest.mark.parametrize("it", ITS)
+@pytest.mark.parametrize("kind", ["ref_common", "empty_rows", "long_rows"])
+@pytest.mark.parametrize("strategy", [(0, 0, 0, 0), (1, 3, 0, 0), (2, 0, 0.8, 0), (3, 0, 0.5, 0.01),
+                                      (4, 0, 0, 0)])
+def test_convert_to_hybrid_bit_exact(orc, cuda, it, kind, strategy):
+    vt = "f64"
+    rng = np.random.default_rng(33)
+    n, m, rp, ci, va = csr_case(rng, kind, vt, it)
+    if it == "i64":
+        pytest.skip("order statistic helper is exercised with i32 row pointers")
+    lim_o = H.hybrid_ell_lim(orc, rp, n, m, *strategy, vbytes=8, ibytes=4)
+    lim_c = H.hybrid_ell_lim(cuda, rp, n, m, *strategy, vbytes=8, ibytes=4)
+    assert lim_o == lim_c
+    a, b = both(orc, cuda, "csr_compute_hybrid_coo_row_ptrs_" + it,
+                lambda: [rp, n, lim_o, np.full(n + 1, -5, np.int64)])
+    assert np.array_equal(a[-1], b[-1])
+    crp = a[-1]
+    cn, stride = int(crp[-1]), n + 2
+    a, b = both(orc, cuda, "csr_convert_to_hybrid_%s_%s" % (vt, it),
+                lambda: [n, rp, ci, va, lim_o, stride, np.full(max(lim_o * stride, 1), 77, IT[it]),
+                         np.full(max(lim_o * stride, 1), 7, VT[vt]), crp,
+                         np.full(max(cn, 1), -3, IT[it]), np.full(max(cn, 1), -3, IT[it]),
+                         np.full(max(cn, 1), 5, VT[vt])])
+    for i in (6, 7, 9, 10, 11):  # ell cols / vals, coo rows / cols / vals
+        assert np.array_equal(a[i], b[i])
+
+
+@pytest.mark.parametrize("vt", VTS)
+@pytest.mark.parametrize("it", ITS)
+@pytest.mark.parametrize("kind", ["ref_common", "empty_rows", "long_rows", "very_long"])
+def test_sort_by_column_index_bit_exact(orc, cuda, vt, it, kind):
+    rng = np.random.default_rng(34)
+    if kind == "very_long":  # rows beyond the shared-memory path (> 2048 entries)
+        n, m = 40, 9000
+        lens = rng.integers(0, 50, n)
+        lens[[3, 17]] = [2500, 5000]
+        rp, ci, va = H.random_csr(rng, n, m, lens, vt, it)
+    else:
+        n, m, rp, ci, va = csr_case(rng, kind, vt, it)
+    ci2, va2 = ci.copy(), va.copy()
+    for r in range(n):
+        s, e = int(rp[r]), int(rp[r + 1])
+        perm = rng.permutation(e - s)
+        ci2[s:e], va2[s:e] = ci[s:e][perm], va[s:e][perm]
+    a, b = both(orc, cuda, "csr_sort_by_column_index_%s_%s" % (vt, it),
+                lambda: [n, rp, ci2.copy(), va2.copy()])
+    assert np.array_equal(a[-2], b[-2]) and np.array_equal(a[-1], b[-1])
+    for r in range(n):  # independent truth: columns are distinct, so the order is unique
+        s, e = int(rp[r]), int(rp[r + 1])
+        o = np.argsort(ci2[s:e], kind="stable")
+        assert np.array_equal(b[-2][s:e], ci2[s:e][o]) and np.array_equal(b[-1][s:e], va2[s:e][o])

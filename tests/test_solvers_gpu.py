@@ -176,6 +176,56 @@ def test_errors_mirror_reference(hexec):
         s.apply(b, x)
 
 
+@pytest.mark.parametrize("vt", ["f64", "f32"])
+@pytest.mark.parametrize("fmt,kw", [("ell", {}), ("sellp", {}), ("sellp", dict(slice_size=32, stride_factor=4)),
+                                    ("coo", {}), ("hybrid", {}),
+                                    ("hybrid", dict(strategy="column_limit", columns=3)),
+                                    ("hybrid", dict(strategy="imbalance_limit", percent=0.5))])
+def test_host_convert_then_apply_bit_equal(hexec, orc, vt, fmt, kw):
+    """Csr::convert_to(...) on the device, then the converted operator's apply: every format
+    keeps the row entries in CSR order, so y is bit-identical to the oracle's CSR SpMV."""
+    import torch
+    from ginkgo_b200 import api
+    rng = np.random.default_rng(41)
+    n, m = 5000, 4000
+    rp, ci, va = H.random_csr(rng, n, m, rng.integers(0, 13, n), vt, "i32")
+    x = rng.uniform(-1, 1, m).astype(VT[vt])
+    dev = hexec.device
+    with torch.cuda.stream(hexec.stream):
+        t = [torch.from_numpy(a).to(dev) for a in (va, ci, rp)]
+        tx = torch.from_numpy(x).to(dev)
+        ty = torch.zeros(n, dtype=tx.dtype, device=dev)
+    A = api.host_csr(hexec, (n, m), *t)
+    B = api.host_convert(A, fmt, **kw)
+    xd, yd = api.host_dense(hexec, tx), api.host_dense(hexec, ty)
+    api._hcheck(api._host().gkob_apply(B.h, xd.h, yd.h))
+    hexec.synchronize()
+    yo = np.zeros(n, VT[vt])
+    orc("csr_spmv_%s_i32" % vt, n, m, len(va), rp, ci, va, x, 1, 1, yo, 1)
+    assert np.array_equal(ty.cpu().numpy(), yo)
+
+
+def test_host_sort_by_column_index(hexec):
+    import torch
+    from ginkgo_b200 import api
+    rng = np.random.default_rng(42)
+    n, m = 3000, 3000
+    lens = rng.integers(0, 40, n)
+    lens[[5, 900]] = [100, 2500]
+    rp, ci, va = H.random_csr(rng, n, m, lens, "f64", "i32")
+    ci2, va2 = ci.copy(), va.copy()
+    for r in range(n):
+        s, e = rp[r], rp[r + 1]
+        perm = rng.permutation(e - s)
+        ci2[s:e], va2[s:e] = ci[s:e][perm], va[s:e][perm]
+    with torch.cuda.stream(hexec.stream):
+        t = [torch.from_numpy(a).to(hexec.device) for a in (va2, ci2, rp)]
+    A = api.host_csr(hexec, (n, m), *t)
+    api.host_sort_by_column_index(A)
+    hexec.synchronize()
+    assert np.array_equal(t[1].cpu().numpy(), ci) and np.array_equal(t[0].cpu().numpy(), va)
+
+
 def test_cpp_example_simple_solver():
     """examples/simple_solver.cpp: the reference's simple-solver flow written against
     gko_b200.hpp (namespace gko = gko_b200), linked only against the C-ABI library"""
