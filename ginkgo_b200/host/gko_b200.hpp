@@ -162,6 +162,7 @@ GKOB_V(float, f32)
         static constexpr auto coo_advanced_spmv2 = b200_coo_advanced_spmv2_##S##_##T;           \
         static constexpr auto jacobi_simple_apply = b200_jacobi_simple_apply_##S##_##T;         \
         static constexpr auto jacobi_apply = b200_jacobi_apply_##S##_##T;                       \
+        static constexpr auto jacobi_generate = b200_jacobi_generate_##S##_##T;                 \
     };
 GKOB_VI(double, f64, int32, i32)
 GKOB_VI(double, f64, int64, i64)

@@ -233,10 +233,11 @@ inline std::unique_ptr<Criterion> combine_and_generate(
 
 // =============================================================================================
 // preconditioner::Jacobi (include/ginkgo/core/preconditioner/jacobi.hpp, core/preconditioner/
-// jacobi.cpp).  apply runs on the device; generate: scalar = extract_diagonal +
-// invert_diagonal kernels; block = the reference's pivoted Gauss-Jordan
-// (reference/preconditioner/jacobi_kernels.cpp:150-415) run on the host at setup time with
-// user-supplied block pointers (natural-block detection is not part of this path).
+// jacobi.cpp).  apply and generate run on the device; generate: scalar = extract_diagonal +
+// invert_diagonal kernels; block = b200_jacobi_generate_* (the reference's pivoted
+// Gauss-Jordan, reference/preconditioner/jacobi_kernels.cpp:113-410, in the reference's
+// operation order) with user-supplied block pointers (natural-block detection is not part
+// of this path).
 // =============================================================================================
 namespace preconditioner {
 
@@ -320,64 +321,22 @@ protected:
         scheme_.group_offset = (I)(max_block_size_ * group_size * max_block_size_);
         scheme_.group_power = 0;
         while ((1u << scheme_.group_power) < group_size) ++scheme_.group_power;
-        // host copy of the matrix, extract + invert every diagonal block
-        const size_type nnz = csr->get_num_stored_elements();
-        std::vector<I> rp(n + 1), ci(nnz);
-        std::vector<V> va(nnz);
-        exec->copy_to_host(rp.data(), csr->get_const_row_ptrs(), n + 1);
-        exec->copy_to_host(ci.data(), csr->get_const_col_idxs(), nnz);
-        exec->copy_to_host(va.data(), csr->get_const_values(), nnz);
-        std::vector<V> store(scheme_.compute_storage_space(num_blocks_), V(0));
-        const size_type stride = scheme_.get_stride();
-        std::vector<V> blk;
-        std::vector<I> perm;
+        // extract + invert every diagonal block on the device (jacobi::generate)
         for (size_type k = 0; k < num_blocks_; ++k) {
-            const I start = ptrs[k];
-            const I bs = ptrs[k + 1] - start;
+            const I bs = ptrs[k + 1] - ptrs[k];
             if (bs < 1 || (uint32)bs > max_block_size_)
                 throw BadDimension("Jacobi: block larger than max_block_size");
-            blk.assign((size_type)bs * bs, V(0));
-            perm.resize(bs);
-            for (I i = 0; i < bs; ++i) perm[i] = i;
-            // extract_block (reference jacobi_kernels.cpp:113-146)
-            for (I r = 0; r < bs; ++r)
-                for (I p = rp[start + r]; p < rp[start + r + 1]; ++p) {
-                    const I c = ci[p] - start;
-                    if (c >= 0 && c < bs) blk[(size_type)r * bs + c] = va[p];
-                }
-            invert_block(bs, perm.data(), blk.data(), (size_type)bs);
-            // permute_and_transpose_block (reference :243-258)
-            V* dst = store.data() + scheme_.get_global_block_offset((I)k);
-            for (I i = 0; i < bs; ++i)
-                for (I j = 0; j < bs; ++j) dst[i + perm[j] * stride] = blk[(size_type)i * bs + j];
         }
-        blocks_ = array<V>(exec, store);
+        if ((size_type)ptrs.back() != n) throw BadDimension("Jacobi: block pointers do not cover the rows");
+        const size_type space = scheme_.compute_storage_space(num_blocks_);
+        blocks_ = array<V>(exec, space);
+        GKOB_CALL(vabi<V>::fill(exec->ctx(), space, 1, blocks_.get_data(), 1, V(0)));
         block_pointers_ = array<I>(exec, ptrs);
-    }
-
-    // reference/preconditioner/jacobi_kernels.cpp:150-278 (choose_pivot, swap_rows,
-    // apply_gauss_jordan_transform, invert_block), same operation order
-    static bool invert_block(I n, I* perm, V* block, size_type stride)
-    {
-        for (I k = 0; k < n; ++k) {
-            I cp = 0;
-            const V* col = block + k * stride + k;
-            for (I i = 1; i < n - k; ++i)
-                if (std::abs(col[cp * stride]) < std::abs(col[i * stride])) cp = i;
-            cp += k;
-            for (I i = 0; i < n; ++i) std::swap(block[k * stride + i], block[cp * stride + i]);
-            std::swap(perm[k], perm[cp]);
-            const V d = block[k * stride + k];
-            if (d == V(0)) return false;
-            for (I i = 0; i < n; ++i) block[i * stride + k] /= -d;
-            block[k * stride + k] = V(0);
-            for (I i = 0; i < n; ++i)
-                for (I j = 0; j < n; ++j)
-                    block[i * stride + j] += block[i * stride + k] * block[k * stride + j];
-            for (I j = 0; j < n; ++j) block[k * stride + j] /= d;
-            block[k * stride + k] = V(1) / d;
-        }
-        return true;
+        GKOB_CALL((viabi<V, I>::jacobi_generate(
+            exec->ctx(), n, csr->get_const_row_ptrs(), csr->get_const_col_idxs(),
+            csr->get_const_values(), num_blocks_, max_block_size_, scheme_.block_offset,
+            scheme_.group_offset, scheme_.group_power, block_pointers_.get_const_data(),
+            blocks_.get_data())));
     }
 
     void apply_impl(const LinOp* b, LinOp* x) const override

@@ -196,7 +196,16 @@ void b200_coo_plan_destroy(b200_coo_plan* plan);
         b200_ctx* ctx, int64_t num_blocks, int32_t max_block_size, int64_t block_offset,      \
         int64_t group_offset, int32_t group_power, const IT* block_pointers,                  \
         const VT* blocks, const VT* alpha, const VT* b, int64_t b_stride, int64_t num_rhs,    \
-        const VT* beta, VT* x, int64_t x_stride);
+        const VT* beta, VT* x, int64_t x_stride);                                             \
+    /* jacobi::generate, full precision (reference/preconditioner/jacobi_kernels.cpp:        \
+     * 113-278, 320-410): extract each diagonal block, invert it with the reference's         \
+     * pivoted Gauss-Jordan in the reference's operation order (bit-identical inverse), store \
+     * it transposed + column-permuted.  Entries of a slot outside the bs x bs block are not  \
+     * written.  A zero pivot leaves the block as the reference leaves it. */                 \
+    b200_status b200_jacobi_generate_##V##_##I(                                               \
+        b200_ctx* ctx, int64_t num_rows, const IT* row_ptrs, const IT* col_idxs,              \
+        const VT* values, int64_t num_blocks, int32_t max_block_size, int64_t block_offset,   \
+        int64_t group_offset, int32_t group_power, const IT* block_pointers, VT* blocks);
 
 /* ---------------------------------------------------------------------------
  * Dense BLAS-1 (core/matrix/dense_kernels.hpp:34-135;

@@ -705,6 +705,61 @@ void FNI(jacobi_apply)(int64_t num_blocks, int32_t max_block_size, int64_t block
 }
 
 
+/* reference/preconditioner/jacobi_kernels.cpp:113-147 extract_block, :150-205 choose_pivot /
+ * swap_rows / apply_gauss_jordan_transform, :262-278 invert_block, :243-258
+ * permute_and_transpose_block, :320-410 generate (full-precision branch, no conditioning) */
+void FNI(jacobi_generate)(int64_t num_rows, const I* rp, const I* ci, const V* va, int64_t num_blocks,
+                          int32_t max_block_size, int64_t block_offset, int64_t group_offset,
+                          int32_t group_power, const I* block_ptrs, V* blocks)
+{
+    (void)num_rows;
+    (void)max_block_size;
+    const int64_t stride = block_offset << group_power;
+    V blk[32 * 32];
+    int perm[32];
+    for (int64_t g = 0; g < num_blocks; ++g) {
+        const int64_t start = block_ptrs[g];
+        const int bs = (int)((int64_t)block_ptrs[g + 1] - start);
+        for (int i = 0; i < bs; ++i)
+            for (int j = 0; j < bs; ++j) blk[i * bs + j] = 0;
+        for (int i = 0; i < bs; ++i) perm[i] = i;
+        for (int row = 0; row < bs; ++row)
+            for (int64_t p = rp[start + row]; p < (int64_t)rp[start + row + 1]; ++p) {
+                const int64_t col = (int64_t)ci[p] - start;
+                if (0 <= col && col < bs) blk[row * bs + col] = va[p];
+            }
+        for (int k = 0; k < bs; ++k) {
+            int cp = 0;
+            const V* colk = blk + k * bs + k;
+            for (int i = 1; i < bs - k; ++i)
+                if (FABS(colk[cp * bs]) < FABS(colk[i * bs])) cp = i;
+            cp += k;
+            for (int i = 0; i < bs; ++i) {
+                const V t = blk[k * bs + i];
+                blk[k * bs + i] = blk[cp * bs + i];
+                blk[cp * bs + i] = t;
+            }
+            {
+                const int t = perm[k];
+                perm[k] = perm[cp];
+                perm[cp] = t;
+            }
+            const V d = blk[k * bs + k];
+            if (d == 0) break;
+            for (int i = 0; i < bs; ++i) blk[i * bs + k] /= -d;
+            blk[k * bs + k] = 0;
+            for (int i = 0; i < bs; ++i)
+                for (int j = 0; j < bs; ++j) blk[i * bs + j] += blk[i * bs + k] * blk[k * bs + j];
+            for (int j = 0; j < bs; ++j) blk[k * bs + j] /= d;
+            blk[k * bs + k] = (V)1 / d;
+        }
+        V* dst = blocks + group_offset * (g >> group_power) +
+                 block_offset * (g & (((int64_t)1 << group_power) - 1));
+        for (int i = 0; i < bs; ++i)
+            for (int j = 0; j < bs; ++j) dst[i + perm[j] * stride] = blk[i * bs + j];
+    }
+}
+
 /* reference/preconditioner/jacobi_kernels.cpp:493-520 (simple_apply == alpha 1, beta 0) */
 void FNI(jacobi_simple_apply)(int64_t num_blocks, int32_t max_block_size, int64_t block_offset,
                               int64_t group_offset, int32_t group_power, const I* block_ptrs,

@@ -208,3 +208,43 @@ def test_sort_by_column_index_matches_reference(orc, vt):
     orc("csr_sort_by_column_index_%s_i32" % vt, n, rp, ci2, va2)
     assert np.array_equal(ci2, r["cols"]) and np.array_equal(va2, r["vals"])
     assert np.array_equal(ci2, ci) and np.array_equal(va2, va)
+
+
+# ------------------------------------------------------- block-Jacobi generate (8f-2)
+def _jacobi_case(rng, vt, max_bs, singular=False):
+    n = 600
+    sizes = []
+    while sum(sizes) < n:
+        sizes.append(int(rng.integers(1, max_bs + 1)))
+    sizes[-1] -= sum(sizes) - n
+    if sizes[-1] == 0:
+        sizes.pop()
+    bp = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    lens = rng.integers(3, 40, n)
+    rp, ci, va = H.random_csr(rng, n, n, lens, vt, "i32")
+    if singular:  # wipe the rows of one block inside the block -> zero pivot
+        b0, b1 = int(bp[3]), int(bp[4])
+        for r in range(b0, b1):
+            s, e = rp[r], rp[r + 1]
+            va[s:e][(ci[s:e] >= b0) & (ci[s:e] < b1)] = 0
+    return n, rp, ci, va, bp
+
+
+@pytest.mark.parametrize("vt", ["f64", "f32"])
+@pytest.mark.parametrize("max_bs", [2, 7, 16, 32])
+def test_jacobi_generate_bit_identical_to_reference(orc, vt, max_bs):
+    rng = np.random.default_rng(50 + max_bs)
+    n, rp, ci, va, bp = _jacobi_case(rng, vt, max_bs)
+    r = ref.jacobi_generate(rp, ci, va, max_bs, bp)
+    assert np.array_equal(r["block_ptrs"], bp)
+    blocks = np.zeros_like(r["blocks"])
+    orc("jacobi_generate_%s_i32" % vt, n, rp, ci, va, len(bp) - 1, max_bs, r["block_offset"],
+        r["group_offset"], r["group_power"], bp, blocks)
+    # compare what the reference defines: the bs x bs part of every slot
+    stride = r["block_offset"] << r["group_power"]
+    for k in range(len(bp) - 1):
+        bs = int(bp[k + 1] - bp[k])
+        off = r["group_offset"] * (k >> r["group_power"]) + r["block_offset"] * (
+            k & ((1 << r["group_power"]) - 1))
+        idx = off + (np.arange(bs)[:, None] + np.arange(bs)[None, :] * stride)
+        assert np.array_equal(blocks[idx], r["blocks"][idx]), k

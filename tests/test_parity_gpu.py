@@ -619,3 +619,52 @@ def test_sort_by_column_index_bit_exact(orc, cuda, vt, it, kind):
         s, e = int(rp[r]), int(rp[r + 1])
         o = np.argsort(ci2[s:e], kind="stable")
         assert np.array_equal(b[-2][s:e], ci2[s:e][o]) and np.array_equal(b[-1][s:e], va2[s:e][o])
+
+
+# ------------------------------------------------- block-Jacobi generate on the device (8f-2)
+@pytest.mark.parametrize("vt", VTS)
+@pytest.mark.parametrize("it", ITS)
+@pytest.mark.parametrize("max_bs,singular", [(1, False), (2, False), (7, False), (16, False),
+                                            (32, False), (13, True)])
+def test_jacobi_generate_bit_exact(orc, cuda, vt, it, max_bs, singular):
+    rng = np.random.default_rng(60 + max_bs)
+    n = 700
+    sizes = []
+    while sum(sizes) < n:
+        sizes.append(int(rng.integers(1, max_bs + 1)))
+    sizes[-1] -= sum(sizes) - n
+    if sizes[-1] == 0:
+        sizes.pop()
+    bp = np.concatenate([[0], np.cumsum(sizes)]).astype(IT[it])
+    rp, ci, va = H.random_csr(rng, n, n, rng.integers(3, 40, n), vt, it)
+    if singular:
+        b0, b1 = int(bp[3]), int(bp[4])
+        for r in range(b0, b1):
+            s, e = int(rp[r]), int(rp[r + 1])
+            va[s:e][(ci[s:e] >= b0) & (ci[s:e] < b1)] = 0
+    pow2 = 1
+    while pow2 < max_bs:
+        pow2 *= 2
+    group_size = 32 // pow2
+    gp = group_size.bit_length() - 1
+    block_offset, group_offset = max_bs, max_bs * group_size * max_bs
+    nb = len(bp) - 1
+    space = (nb + group_size - 1) // group_size * group_offset
+    a, b = both(orc, cuda, "jacobi_generate_%s_%s" % (vt, it),
+                lambda: [n, rp, ci, va, nb, max_bs, block_offset, group_offset, gp, bp,
+                         np.zeros(space, VT[vt])])
+    assert np.array_equal(a[-1], b[-1], equal_nan=True)
+    if not singular:  # and it is an inverse: apply to A_block * e
+        k = nb // 2
+        bs, st = int(bp[k + 1] - bp[k]), int(bp[k])
+        off = group_offset * (k >> gp) + block_offset * (k & ((1 << gp) - 1))
+        stride = block_offset << gp
+        inv = b[-1][off + np.arange(bs)[:, None] + np.arange(bs)[None, :] * stride].astype(np.float64)
+        blk = np.zeros((bs, bs))
+        for r in range(bs):
+            for p in range(int(rp[st + r]), int(rp[st + r + 1])):
+                c = int(ci[p]) - st
+                if 0 <= c < bs:
+                    blk[r, c] = va[p]
+        err = np.abs(inv @ blk - np.eye(bs)).max()
+        assert err < (1e-9 if vt == "f64" else 1e-2) * max(1.0, np.linalg.cond(blk))
