@@ -71,6 +71,15 @@ b200_status b200_ctx_create(int32_t device_id, void* cuda_stream, b200_ctx** out
         B200_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->owns_stream = true;
     }
+    {
+        // keep released blocks in the device pool instead of returning them to the driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     B200_CUDA_CHECK(cudaMalloc((void**)&c->counters, 256 * sizeof(unsigned int)));
     B200_CUDA_CHECK(cudaMemsetAsync(c->counters, 0, 256 * sizeof(unsigned int), c->stream));
     B200_CUDA_CHECK(cudaMallocHost((void**)&c->pinned, 4096));
@@ -106,9 +115,12 @@ b200_status b200_alloc(b200_ctx* ctx, size_t bytes, void** out)
     *out = nullptr;
     if (bytes == 0) return B200_OK;
     B200_CUDA_CHECK(cudaSetDevice(ctx->device));
-    cudaError_t e = cudaMalloc(out, bytes);
+    // stream-ordered allocation (the reference's CudaAsyncAllocator, cuda/base/memory.cpp):
+    // solver workspaces are allocated and released on every apply; with the pool they are
+    // re-used without a device synchronisation or a page-mapping cost
+    cudaError_t e = cudaMallocAsync(out, bytes, ctx->stream);
     if (e != cudaSuccess) {
-        b200::set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        b200::set_error("cudaMallocAsync(%zu) failed: %s", bytes, cudaGetErrorString(e));
         cudaGetLastError();
         return B200_ERR_ALLOC;
     }
@@ -121,8 +133,7 @@ b200_status b200_free(b200_ctx* ctx, void* ptr)
     // (core/device_hooks/cuda_hooks.cpp:113-118)
     if (!ptr) return B200_OK;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
-    cudaFree(ptr);
+    if (cudaFreeAsync(ptr, ctx->stream) != cudaSuccess) cudaGetLastError();
     return B200_OK;
 }
 

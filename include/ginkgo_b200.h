@@ -71,6 +71,9 @@ void* b200_ctx_stream(const b200_ctx* ctx);
 int32_t b200_ctx_device(const b200_ctx* ctx);
 int32_t b200_ctx_num_sms(const b200_ctx* ctx);
 int64_t b200_ctx_launch_count(const b200_ctx* ctx); /* kernels launched so far by this ctx */
+/* stream-ordered on the context's stream (cudaMallocAsync / cudaFreeAsync, the reference's
+ * CudaAsyncAllocator): memory may be used by work enqueued on that stream after the call;
+ * free never synchronises and never fails loudly (cuda_hooks.cpp:113-118). */
 b200_status b200_alloc(b200_ctx* ctx, size_t bytes, void** out);
 b200_status b200_free(b200_ctx* ctx, void* ptr);
 b200_status b200_copy_h2d(b200_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes); /* blocking */
