@@ -217,6 +217,11 @@ def _host():
         h.gkob_launch_count.restype = ll
         h.gkob_launch_count.argtypes = [vp]
         h.gkob_csr_kernel_variant.restype, h.gkob_csr_kernel_variant.argtypes = i, [vp]
+        h.gkob_staged_create.restype, h.gkob_staged_create.argtypes = vp, [vp, i, ll]
+        h.gkob_staged_apply.restype, h.gkob_staged_apply.argtypes = i, [vp, vp, vp]
+        h.gkob_staged_join.restype, h.gkob_staged_join.argtypes = i, [vp]
+        h.gkob_staged_wait.restype, h.gkob_staged_wait.argtypes = i, [vp]
+        h.gkob_staged_destroy.argtypes = [vp]
         h.gkob_csr_convert.restype = vp
         h.gkob_csr_convert.argtypes = [vp, ctypes.c_char_p, ll, ll, d, d]
         h.gkob_csr_sort_by_column_index.restype = i
@@ -307,6 +312,33 @@ def host_convert(A, fmt, slice_size=64, stride_factor=1, strategy="automatic", c
 def host_sort_by_column_index(A):
     """Csr::sort_by_column_index in place (on the tensors the handle views)"""
     _hcheck(_host().gkob_csr_sort_by_column_index(A.h))
+
+
+class StagedApply:
+    """gko_b200::staged_apply<V>: x_host = op(b_host) with HOST tensors (pinned to overlap),
+    pipelined over two copy streams; apply() is asynchronous, wait() makes x_host valid."""
+
+    def __init__(self, A, nrhs=1):
+        self.A = A
+        self.h = _host().gkob_staged_create(A.h, 0 if A.vt == "f64" else 1, nrhs)
+        if not self.h:
+            raise _lib.B200Error(_host().gkob_last_error().decode())
+
+    def apply(self, b_host, x_host):
+        assert not b_host.is_cuda and not x_host.is_cuda
+        _hcheck(_host().gkob_staged_apply(self.h, b_host.data_ptr(), x_host.data_ptr()))
+
+    def join(self):
+        _hcheck(_host().gkob_staged_join(self.h))
+
+    def wait(self):
+        _hcheck(_host().gkob_staged_wait(self.h))
+
+    def __del__(self):
+        try:
+            _host().gkob_staged_destroy(self.h)
+        except Exception:
+            pass
 
 
 def host_dense(exec_, t, cols=None, stride=None):

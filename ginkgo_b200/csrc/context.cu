@@ -166,4 +166,108 @@ b200_status b200_synchronize(b200_ctx* ctx)
     return B200_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Staging pipe: host-resident operands of an apply (the reference clones them onto the
+// device inside LinOp::apply, include/ginkgo/core/base/lin_op.hpp:129-215 +
+// make_temporary_clone) move over two extra streams, so that the upload of call k+1, the
+// kernel of call k and the download of call k-1 overlap (PCIe is full duplex).  `slot`
+// selects one of kPipeSlots staging-buffer pairs the caller owns; the events enforce
+//   upload(slot)   after the compute that last read the slot's input buffer,
+//   compute(slot)  after upload(slot) and after the download that last read its output,
+//   download(slot) after compute(slot).
+// ---------------------------------------------------------------------------------------
+struct b200_pipe {
+    static constexpr int kSlots = 2;
+    b200_ctx* ctx = nullptr;
+    cudaStream_t in = nullptr, out = nullptr;
+    cudaEvent_t uploaded[kSlots], computed[kSlots], downloaded[kSlots];
+};
+
+b200_status b200_pipe_create(b200_ctx* ctx, b200_pipe** out)
+{
+    B200_REQUIRE(ctx && out, "null argument");
+    B200_CUDA_CHECK(cudaSetDevice(ctx->device));
+    b200_pipe* p = new b200_pipe();
+    p->ctx = ctx;
+    B200_CUDA_CHECK(cudaStreamCreateWithFlags(&p->in, cudaStreamNonBlocking));
+    B200_CUDA_CHECK(cudaStreamCreateWithFlags(&p->out, cudaStreamNonBlocking));
+    for (int i = 0; i < b200_pipe::kSlots; ++i) {
+        B200_CUDA_CHECK(cudaEventCreateWithFlags(&p->uploaded[i], cudaEventDisableTiming));
+        B200_CUDA_CHECK(cudaEventCreateWithFlags(&p->computed[i], cudaEventDisableTiming));
+        B200_CUDA_CHECK(cudaEventCreateWithFlags(&p->downloaded[i], cudaEventDisableTiming));
+    }
+    *out = p;
+    return B200_OK;
+}
+
+void b200_pipe_destroy(b200_pipe* p)
+{
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    cudaStreamSynchronize(p->in);
+    cudaStreamSynchronize(p->out);
+    for (int i = 0; i < b200_pipe::kSlots; ++i) {
+        cudaEventDestroy(p->uploaded[i]);
+        cudaEventDestroy(p->computed[i]);
+        cudaEventDestroy(p->downloaded[i]);
+    }
+    cudaStreamDestroy(p->in);
+    cudaStreamDestroy(p->out);
+    delete p;
+}
+
+int32_t b200_pipe_num_slots(void) { return b200_pipe::kSlots; }
+
+/* host -> device on the upload stream (src_host should be pinned to overlap) */
+b200_status b200_pipe_upload(b200_pipe* p, int32_t slot, void* dst_dev, const void* src_host,
+                             size_t bytes)
+{
+    B200_REQUIRE(p && slot >= 0 && slot < b200_pipe::kSlots, "bad pipe slot");
+    B200_CUDA_CHECK(cudaStreamWaitEvent(p->in, p->computed[slot], 0));
+    if (bytes)
+        B200_CUDA_CHECK(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, p->in));
+    B200_CUDA_CHECK(cudaEventRecord(p->uploaded[slot], p->in));
+    return B200_OK;
+}
+
+/* bracket the kernels of one call on the context's stream */
+b200_status b200_pipe_begin_compute(b200_pipe* p, int32_t slot)
+{
+    B200_REQUIRE(p && slot >= 0 && slot < b200_pipe::kSlots, "bad pipe slot");
+    B200_CUDA_CHECK(cudaStreamWaitEvent(p->ctx->stream, p->uploaded[slot], 0));
+    B200_CUDA_CHECK(cudaStreamWaitEvent(p->ctx->stream, p->downloaded[slot], 0));
+    return B200_OK;
+}
+b200_status b200_pipe_end_compute(b200_pipe* p, int32_t slot)
+{
+    B200_REQUIRE(p && slot >= 0 && slot < b200_pipe::kSlots, "bad pipe slot");
+    B200_CUDA_CHECK(cudaEventRecord(p->computed[slot], p->ctx->stream));
+    return B200_OK;
+}
+
+/* device -> host on the download stream */
+b200_status b200_pipe_download(b200_pipe* p, int32_t slot, void* dst_host, const void* src_dev,
+                               size_t bytes)
+{
+    B200_REQUIRE(p && slot >= 0 && slot < b200_pipe::kSlots, "bad pipe slot");
+    B200_CUDA_CHECK(cudaStreamWaitEvent(p->out, p->computed[slot], 0));
+    if (bytes)
+        B200_CUDA_CHECK(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, p->out));
+    B200_CUDA_CHECK(cudaEventRecord(p->downloaded[slot], p->out));
+    return B200_OK;
+}
+
+/* the context's stream waits for every outstanding transfer (then b200_synchronize, or an
+ * event recorded on that stream, covers the whole pipeline) */
+b200_status b200_pipe_join(b200_pipe* p)
+{
+    B200_REQUIRE(p != nullptr, "null pipe");
+    for (int i = 0; i < b200_pipe::kSlots; ++i) {
+        B200_CUDA_CHECK(cudaStreamWaitEvent(p->ctx->stream, p->uploaded[i], 0));
+        B200_CUDA_CHECK(cudaStreamWaitEvent(p->ctx->stream, p->downloaded[i], 0));
+    }
+    return B200_OK;
+}
+
 }  // extern "C"

@@ -178,6 +178,54 @@ int gkob_csr_sort_by_column_index(void* csr)
     });
 }
 
+// staged_apply<V> over a LinOp handle: apply with HOST vectors, pipelined (gko_b200_staging.hpp)
+struct StagedHandle {
+    std::shared_ptr<Executor> exec;
+    std::unique_ptr<staged_apply<double>> f64;
+    std::unique_ptr<staged_apply<float>> f32;
+};
+void* gkob_staged_create(void* op, int vt, long long nrhs)
+{
+    auto src = static_cast<Handle*>(op);
+    auto h = new StagedHandle();
+    h->exec = src->exec;
+    if (guarded([&] {
+            if (vt == 0)
+                h->f64.reset(new staged_apply<double>(src->op, (size_type)nrhs));
+            else
+                h->f32.reset(new staged_apply<float>(src->op, (size_type)nrhs));
+        })) {
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+int gkob_staged_apply(void* staged, const void* b_host, void* x_host)
+{
+    return guarded([&] {
+        auto h = static_cast<StagedHandle*>(staged);
+        if (h->f64)
+            h->f64->apply((const double*)b_host, (double*)x_host);
+        else
+            h->f32->apply((const float*)b_host, (float*)x_host);
+    });
+}
+int gkob_staged_join(void* staged)
+{
+    return guarded([&] {
+        auto h = static_cast<StagedHandle*>(staged);
+        h->f64 ? h->f64->join() : h->f32->join();
+    });
+}
+int gkob_staged_wait(void* staged)
+{
+    return guarded([&] {
+        auto h = static_cast<StagedHandle*>(staged);
+        h->f64 ? h->f64->wait() : h->f32->wait();
+    });
+}
+void gkob_staged_destroy(void* staged) { delete static_cast<StagedHandle*>(staged); }
+
 // kernel variant the tuned plan of a Csr handle uses (2 = warp_stream, 4 = warp_pipe); -1 if
 // the handle is not a double/int32 or float/int32 Csr
 int gkob_csr_kernel_variant(void* csr)

@@ -955,4 +955,5 @@ using Vec = matrix::Dense<V>;
 }  // namespace gko_b200
 
 #include "gko_b200_convert.hpp"
+#include "gko_b200_staging.hpp"
 #include "gko_b200_solvers.hpp"

@@ -81,6 +81,27 @@ b200_status b200_copy_d2h(b200_ctx* ctx, void* dst_host, const void* src_dev, si
 b200_status b200_copy_d2d(b200_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes);  /* async */
 b200_status b200_synchronize(b200_ctx* ctx);
 
+/* Staging pipe for HOST-resident operands (the reference clones them onto the device inside
+ * LinOp::apply: include/ginkgo/core/base/lin_op.hpp:129-215, make_temporary_clone).  Two
+ * extra streams + events: the upload of call k+1, the kernels of call k and the download of
+ * call k-1 overlap (PCIe is full duplex).  The caller owns b200_pipe_num_slots() pairs of
+ * device staging buffers and cycles through the slots; host buffers should be pinned.
+ *   upload(slot): after the compute that last read the slot's input
+ *   begin_compute(slot) ... kernels on the context's stream ... end_compute(slot)
+ *   download(slot): after end_compute(slot)
+ *   join: the context's stream waits for all outstanding transfers. */
+typedef struct b200_pipe b200_pipe;
+b200_status b200_pipe_create(b200_ctx* ctx, b200_pipe** out);
+void b200_pipe_destroy(b200_pipe* pipe);
+int32_t b200_pipe_num_slots(void);
+b200_status b200_pipe_upload(b200_pipe* pipe, int32_t slot, void* dst_dev, const void* src_host,
+                             size_t bytes);
+b200_status b200_pipe_begin_compute(b200_pipe* pipe, int32_t slot);
+b200_status b200_pipe_end_compute(b200_pipe* pipe, int32_t slot);
+b200_status b200_pipe_download(b200_pipe* pipe, int32_t slot, void* dst_host, const void* src_dev,
+                               size_t bytes);
+b200_status b200_pipe_join(b200_pipe* pipe);
+
 /* ---------------------------------------------------------------------------
  * CSR  (reference core/matrix/csr_kernels.hpp:28-43; oracle
  * reference/matrix/csr_kernels.cpp:47-118; today's CUDA path

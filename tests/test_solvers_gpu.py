@@ -226,6 +226,35 @@ def test_host_sort_by_column_index(hexec):
     assert np.array_equal(t[1].cpu().numpy(), ci) and np.array_equal(t[0].cpu().numpy(), va)
 
 
+def test_staged_apply_pipeline_matches_device_apply(hexec, orc):
+    """staged_apply: HOST vectors, upload / kernel / download of consecutive calls overlap;
+    every call's result must be the plain SpMV of that call's input."""
+    import torch
+    from ginkgo_b200 import api
+    rng = np.random.default_rng(43)
+    n, m = 200000, 150000
+    rp, ci, va = H.random_csr(rng, n, m, rng.integers(0, 12, n), "f64", "i32")
+    with torch.cuda.stream(hexec.stream):
+        t = [torch.from_numpy(a).to(hexec.device) for a in (va, ci, rp)]
+    A = api.host_csr(hexec, (n, m), *t)
+    st = api.StagedApply(A)
+    xs = [torch.from_numpy(rng.uniform(-1, 1, m)).pin_memory() for _ in range(7)]
+    ys = [torch.full((n,), float("nan"), dtype=torch.float64).pin_memory() for _ in range(7)]
+    for x, y in zip(xs, ys):
+        st.apply(x, y)
+    st.wait()
+    for x, y in zip(xs, ys):
+        yo = np.zeros(n)
+        orc("csr_spmv_f64_i32", n, m, len(va), rp, ci, va, x.numpy(), 1, 1, yo, 1)
+        assert np.array_equal(y.numpy(), yo)
+    # re-using ONE output buffer keeps the last result
+    y1 = torch.empty(n, dtype=torch.float64).pin_memory()
+    for x in xs:
+        st.apply(x, y1)
+    st.wait()
+    assert torch.equal(y1, ys[-1])
+
+
 def test_cpp_example_simple_solver():
     """examples/simple_solver.cpp: the reference's simple-solver flow written against
     gko_b200.hpp (namespace gko = gko_b200), linked only against the C-ABI library"""
