@@ -207,6 +207,7 @@ def run_gpu_arm(args, rank, world):
     ex.synchronize()
     kernel_name = {2: "warp_stream_kernel", 4: "warp_pipe_kernel"}.get(
         hl.gkob_csr_kernel_variant((A if world == 1 else Aloc).h), "warp_stream_kernel")
+    plan_parts = hl.gkob_csr_plan_parts((A if world == 1 else Aloc).h)
     for _ in range(max(args.warmup, 3)):
         step()
     with ClockSampler(local) as cs:
@@ -267,7 +268,10 @@ def run_gpu_arm(args, rank, world):
     achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "kernel": "b200::csr::%s<double,int,1,false,false>" % kernel_name,
+                "kernel": "b200::csr::%s<double,int,1,...>" % kernel_name + (
+                    " x %d launches (column-blocked copy, parts applied in order)" % plan_parts
+                    if plan_parts > 1 else ""),
+                "launches_per_step": max(plan_parts, 1),
                 "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_kernel}
     prof = os.path.join(ROOT, "profiles", "r01_csr_spmv_cfg2.json")
     if os.path.exists(prof):

@@ -217,6 +217,7 @@ def _host():
         h.gkob_launch_count.restype = ll
         h.gkob_launch_count.argtypes = [vp]
         h.gkob_csr_kernel_variant.restype, h.gkob_csr_kernel_variant.argtypes = i, [vp]
+        h.gkob_csr_plan_parts.restype, h.gkob_csr_plan_parts.argtypes = i, [vp]
         h.gkob_staged_create.restype, h.gkob_staged_create.argtypes = vp, [vp, i, ll]
         h.gkob_staged_apply.restype, h.gkob_staged_apply.argtypes = i, [vp, vp, vp]
         h.gkob_staged_join.restype, h.gkob_staged_join.argtypes = i, [vp]

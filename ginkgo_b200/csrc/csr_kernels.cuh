@@ -1123,6 +1123,21 @@ struct b200_csr_plan {
     int lanes = 1;
     int device = 0;
     int variant = -1;  // kernel variant chosen by b200_csr_plan_tune_*, -1 = not tuned
+    // Column-blocked copy of the matrix (b200_csr_plan_tune_* builds it when it wins): part p
+    // holds, row by row, the entries with column in [col_split[p], col_split[p+1]).  Rows are
+    // column-sorted (checked), so applying the parts in order -- part 0 as c = A0 b, part p
+    // as c = 1*Ap b + 1*c -- adds every row's products in exactly the original order: same
+    // bits, but the gathers of one launch stay inside a slice of b that fits in L2.
+    static constexpr int kMaxParts = 4;
+    int parts = 0;
+    const void* src_cols = nullptr;  // the arrays the copy was made from (identity check)
+    const void* src_vals = nullptr;
+    void* part_row_ptrs[kMaxParts] = {nullptr, nullptr, nullptr, nullptr};
+    void* part_cols[kMaxParts] = {nullptr, nullptr, nullptr, nullptr};
+    void* part_vals[kMaxParts] = {nullptr, nullptr, nullptr, nullptr};
+    int64_t part_nnz[kMaxParts] = {0, 0, 0, 0};
+    b200_csr_plan* part_plan[kMaxParts] = {nullptr, nullptr, nullptr, nullptr};
+    void* ones = nullptr;  // device {1, 1} in the value type
 };
 
 namespace b200 {

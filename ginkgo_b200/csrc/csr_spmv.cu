@@ -1,5 +1,6 @@
 // C-ABI entry points of the CSR (and COO-on-CSR) SpMV; kernels in csr_kernels.cuh.
 #include "csr_kernels.cuh"
+#include "scan.cuh"
 
 namespace b200 {
 namespace csr {
@@ -49,6 +50,32 @@ b200_status spmv_impl(b200_ctx* ctx, const b200_csr_plan* plan, int64_t num_rows
                     bytes, ratio, prop.persistingL2CacheMaxSize, prop.accessPolicyMaxWindowSize);
             last = (const void*)b;
         }
+    }
+    if (plan && plan->parts > 1 && plan->src_cols == (const void*)col_idxs &&
+        plan->src_vals == (const void*)values && !getenv("B200_CSR_NO_REBLOCK")) {
+        // column-blocked copy: part 0 starts the row sums, the others continue them
+        const V* ones = (const V*)plan->ones;
+        for (int p = 0; p < plan->parts; ++p) {
+            const b200_csr_plan* sub = plan->part_plan[p];
+            const Variant v = pick_variant(plan->part_cols[p], plan->part_vals[p], sub);
+            const bool w = v != kSlab && v != kTma;
+            b200_status st;
+            if (p == 0 && !ADVANCED)
+                st = launch_slab<V, I, false, false>(
+                    ctx, sub->lanes, v, w ? sub->num_wtiles : sub->num_tiles,
+                    w ? sub->wtiles : sub->tiles, plan->part_nnz[p], (const I*)plan->part_row_ptrs[p],
+                    (const I*)plan->part_cols[p], (const V*)plan->part_vals[p], nullptr, b, b_stride,
+                    nullptr, c, c_stride);
+            else
+                st = launch_slab<V, I, true, false>(
+                    ctx, sub->lanes, v, w ? sub->num_wtiles : sub->num_tiles,
+                    w ? sub->wtiles : sub->tiles, plan->part_nnz[p], (const I*)plan->part_row_ptrs[p],
+                    (const I*)plan->part_cols[p], (const V*)plan->part_vals[p],
+                    ADVANCED ? alpha : ones, b, b_stride, (ADVANCED && p == 0) ? beta : ones + 1, c,
+                    c_stride);
+            if (st != B200_OK) return st;
+        }
+        return B200_OK;
     }
     const Variant variant = pick_variant(col_idxs, values, plan);
     const int64_t num_tiles = variant_tiles(variant, num_rows, nnz);
@@ -111,6 +138,160 @@ b200_status plan_create(b200_ctx* ctx, int64_t num_rows, int64_t nnz, const I* r
     return B200_OK;
 }
 
+// ---- column-blocked copy (see b200_csr_plan) ------------------------------------------
+template <typename I>
+__global__ void unsorted_rows_kernel(int64_t num_rows, const I* __restrict__ rp,
+                                     const I* __restrict__ ci, int* __restrict__ flag)
+{
+    const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (row >= num_rows) return;
+    for (int64_t k = rp[row]; k + 1 < (int64_t)rp[row + 1]; ++k)
+        if (ci[k] > ci[k + 1]) {
+            *flag = 1;
+            return;
+        }
+}
+
+// pos[(p - 1) * num_rows + row] = first entry of `row` with column >= bounds[p], p = 1..parts-1
+template <typename I>
+__global__ void split_positions_kernel(int64_t num_rows, const I* __restrict__ rp,
+                                       const I* __restrict__ ci, int parts, int64_t col_block,
+                                       I* __restrict__ pos)
+{
+    const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (row >= num_rows) return;
+    const int64_t s = rp[row], e = rp[row + 1];
+    int64_t k = s;
+    for (int p = 1; p < parts; ++p) {
+        const int64_t bound = p * col_block;
+        while (k < e && (int64_t)ci[k] < bound) ++k;
+        pos[(int64_t)(p - 1) * num_rows + row] = (I)k;
+    }
+}
+
+template <typename V, typename I>
+__global__ void split_copy_kernel(int64_t num_rows, const I* __restrict__ rp,
+                                  const I* __restrict__ ci, const V* __restrict__ va, int parts,
+                                  const I* __restrict__ pos, int part,
+                                  const I* __restrict__ prp, I* __restrict__ pci,
+                                  V* __restrict__ pva)
+{
+    const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (row >= num_rows) return;
+    const int64_t s = part == 0 ? (int64_t)rp[row] : (int64_t)pos[(int64_t)(part - 1) * num_rows + row];
+    const int64_t e = part == parts - 1 ? (int64_t)rp[row + 1] : (int64_t)pos[(int64_t)part * num_rows + row];
+    int64_t out = prp[row];
+    for (int64_t k = s; k < e; ++k, ++out) {
+        pci[out] = ci[k];
+        pva[out] = va[k];
+    }
+}
+
+template <typename V>
+__global__ void plan_ones_kernel(V* p)
+{
+    p[0] = V(1);
+    p[1] = V(1);
+}
+
+inline void plan_drop_parts(b200_csr_plan* plan)
+{
+    for (int p = 0; p < b200_csr_plan::kMaxParts; ++p) {
+        cudaFree(plan->part_row_ptrs[p]);
+        cudaFree(plan->part_cols[p]);
+        cudaFree(plan->part_vals[p]);
+        plan->part_row_ptrs[p] = plan->part_cols[p] = plan->part_vals[p] = nullptr;
+        if (plan->part_plan[p]) {
+            cudaFree(plan->part_plan[p]->tiles);
+            delete plan->part_plan[p];
+            plan->part_plan[p] = nullptr;
+        }
+    }
+    cudaFree(plan->ones);
+    plan->ones = nullptr;
+    plan->parts = 0;
+}
+
+template <typename I>
+b200_status plan_create(b200_ctx* ctx, int64_t num_rows, int64_t nnz, const I* row_ptrs,
+                        b200_csr_plan** out);
+
+// Builds the copy; returns B200_OK with plan->parts == 0 when the matrix does not qualify
+// (unsorted rows, no memory): the caller then simply keeps the original arrays.
+template <typename V, typename I>
+b200_status plan_reblock(b200_ctx* ctx, b200_csr_plan* plan, int64_t num_rows, int64_t num_cols,
+                         int64_t nnz, const I* rp, const I* ci, const V* va, int parts)
+{
+    plan_drop_parts(plan);
+    if (parts < 2 || num_rows == 0 || nnz == 0) return B200_OK;
+    if (parts > b200_csr_plan::kMaxParts) parts = b200_csr_plan::kMaxParts;
+    const unsigned grid = (unsigned)ceildiv(num_rows, 256);
+    int* flag = (int*)ctx->scratch(sizeof(int));
+    if (!flag) return B200_OK;
+    cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream);
+    unsorted_rows_kernel<I><<<grid, 256, 0, ctx->stream>>>(num_rows, rp, ci, flag);
+    B200_LAUNCH_CHECK(ctx);
+    int unsorted = 0;
+    B200_CUDA_CHECK(cudaMemcpyAsync(&unsorted, flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (unsorted) return B200_OK;
+    I* pos = nullptr;
+    I* sums = nullptr;
+    bool ok = cudaMalloc((void**)&pos, sizeof(I) * (size_t)(parts - 1) * num_rows) == cudaSuccess &&
+              cudaMalloc((void**)&sums, sizeof(I) * (size_t)scan::num_tiles(num_rows + 1)) == cudaSuccess &&
+              cudaMalloc(&plan->ones, 2 * sizeof(V)) == cudaSuccess;
+    const int64_t col_block = ceildiv(num_cols, (int64_t)parts);
+    b200_status st = B200_OK;
+    if (ok) {
+        plan_ones_kernel<V><<<1, 1, 0, ctx->stream>>>((V*)plan->ones);
+        ctx->launches++;
+        split_positions_kernel<I><<<grid, 256, 0, ctx->stream>>>(num_rows, rp, ci, parts, col_block, pos);
+        ctx->launches++;
+    }
+    for (int p = 0; p < parts && ok && st == B200_OK; ++p) {
+        ok = cudaMalloc(&plan->part_row_ptrs[p], sizeof(I) * (size_t)(num_rows + 1)) == cudaSuccess;
+        if (!ok) break;
+        I* prp = (I*)plan->part_row_ptrs[p];
+        const I* cpos = pos;
+        const int np = parts;
+        st = scan::exclusive<I>(
+            ctx, num_rows + 1,
+            [=] __device__(int64_t r) -> I {
+                if (r >= num_rows) return I(0);
+                const I s = p == 0 ? rp[r] : cpos[(int64_t)(p - 1) * num_rows + r];
+                const I e = p == np - 1 ? rp[r + 1] : cpos[(int64_t)p * num_rows + r];
+                return e - s;
+            },
+            prp, sums);
+        if (st != B200_OK) break;
+        I last = 0;
+        B200_CUDA_CHECK(cudaMemcpyAsync(&last, prp + num_rows, sizeof(I), cudaMemcpyDeviceToHost, ctx->stream));
+        B200_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        plan->part_nnz[p] = (int64_t)last;
+        const size_t cnt = (size_t)(last > 0 ? last : 1);
+        ok = cudaMalloc(&plan->part_cols[p], sizeof(I) * cnt) == cudaSuccess &&
+             cudaMalloc(&plan->part_vals[p], sizeof(V) * cnt) == cudaSuccess;
+        if (!ok) break;
+        split_copy_kernel<V, I><<<grid, 256, 0, ctx->stream>>>(num_rows, rp, ci, va, parts, pos, p, prp,
+                                                               (I*)plan->part_cols[p],
+                                                               (V*)plan->part_vals[p]);
+        ctx->launches++;
+        st = plan_create<I>(ctx, num_rows, plan->part_nnz[p], prp, &plan->part_plan[p]);
+    }
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(pos);
+    cudaFree(sums);
+    if (!ok || st != B200_OK) {
+        cudaGetLastError();
+        plan_drop_parts(plan);
+        return st;
+    }
+    plan->parts = parts;
+    plan->src_cols = ci;
+    plan->src_vals = va;
+    return B200_OK;
+}
+
 // Set-up time choice between the two warp kernels: the pipelined one wins where the gathers
 // of b are local (stencils, banded matrices: +10-14 %), the plain one where they are not
 // (uniformly random columns: +10 %) and on matrices too small to pipeline.  Both sum every
@@ -159,14 +340,42 @@ b200_status plan_tune(b200_ctx* ctx, b200_csr_plan* plan, int64_t num_rows, int6
             plan->variant = cand[k];
         }
     }
+    // third candidate: the column-blocked copy, when b is too large to stay in L2 next to
+    // the matrix stream (B200: 126 MB L2 on two dies; gathers of a 40 MB slice stay resident)
+    const size_t b_bytes = (size_t)num_cols * sizeof(V);
+    const char* rb = getenv("B200_CSR_REBLOCK");  // "0" never, "N" force N parts
+    int parts = 0;
+    if (rb)
+        parts = atoi(rb);
+    else if (b_bytes > (size_t)48 << 20 && nnz >= 4 * num_rows)
+        parts = (int)((b_bytes + ((size_t)40 << 20) - 1) / ((size_t)40 << 20));
+    if (parts > b200_csr_plan::kMaxParts) parts = b200_csr_plan::kMaxParts;
+    float t_parts = 0.f;
+    if (st == B200_OK && parts >= 2) {
+        st = plan_reblock<V, I>(ctx, plan, num_rows, num_cols, nnz, row_ptrs, col_idxs, values, parts);
+        if (st == B200_OK && plan->parts > 1) {
+            for (int r = 0; r <= reps && st == B200_OK; ++r) {
+                if (r == 1) cudaEventRecord(e0, ctx->stream);
+                st = spmv_impl<V, I, false>(ctx, plan, num_rows, num_cols, nnz, row_ptrs, col_idxs,
+                                            values, nullptr, b, 1, 1, nullptr, c, 1);
+            }
+            cudaEventRecord(e1, ctx->stream);
+            if (cudaEventSynchronize(e1) != cudaSuccess) st = B200_ERR_CUDA;
+            if (st == B200_OK) cudaEventElapsedTime(&t_parts, e0, e1);
+            if (st != B200_OK || (!rb && t_parts > 0.92f * best)) plan_drop_parts(plan);
+        }
+    }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFree(b);
     cudaFree(c);
     if (getenv("B200_DEBUG"))
-        fprintf(stderr, "[b200] csr plan tuned: rows %lld nnz %lld -> %s (%.3f ms / %d launches)\n",
+        fprintf(stderr,
+                "[b200] csr plan tuned: rows %lld nnz %lld -> %s (%.3f ms / %d launches)%s parts=%d "
+                "(%.3f ms)\n",
                 (long long)num_rows, (long long)nnz,
-                plan->variant == kPipe ? "warp_pipe" : "warp_stream", best, reps);
+                plan->variant == kPipe ? "warp_pipe" : "warp_stream", best, reps,
+                plan->parts > 1 ? ", column-blocked copy kept" : "", plan->parts, t_parts);
     if (st != B200_OK) set_error("csr plan tuning failed: %s", cudaGetErrorString(cudaGetLastError()));
     return st;
 }
@@ -177,12 +386,14 @@ b200_status plan_tune(b200_ctx* ctx, b200_csr_plan* plan, int64_t num_rows, int6
 extern "C" {
 
 int b200_csr_plan_variant(const b200_csr_plan* plan) { return plan ? plan->variant : -1; }
+int b200_csr_plan_parts(const b200_csr_plan* plan) { return plan ? plan->parts : 0; }
 
 void b200_csr_plan_destroy(b200_csr_plan* plan)
 {
     if (!plan) return;
     cudaSetDevice(plan->device);
     cudaDeviceSynchronize();
+    b200::csr::plan_drop_parts(plan);
     cudaFree(plan->tiles);
     delete plan;
 }

@@ -226,6 +226,20 @@ int gkob_staged_wait(void* staged)
 }
 void gkob_staged_destroy(void* staged) { delete static_cast<StagedHandle*>(staged); }
 
+// number of column blocks the tuned plan of a Csr handle applies (0 / 1: the original arrays)
+int gkob_csr_plan_parts(void* csr)
+{
+    int v = 0;
+    guarded([&] {
+        auto op = static_cast<Handle*>(csr)->op.get();
+        if (auto a = dynamic_cast<const matrix::Csr<double, int32>*>(op))
+            v = b200_csr_plan_parts(a->get_plan());
+        else if (auto a = dynamic_cast<const matrix::Csr<float, int32>*>(op))
+            v = b200_csr_plan_parts(a->get_plan());
+    });
+    return v;
+}
+
 // kernel variant the tuned plan of a Csr handle uses (2 = warp_stream, 4 = warp_pipe); -1 if
 // the handle is not a double/int32 or float/int32 Csr
 int gkob_csr_kernel_variant(void* csr)

@@ -114,6 +114,13 @@ b200_status b200_pipe_join(b200_pipe* pipe);
  * of the reference's strategy selection (include/ginkgo/core/matrix/csr.hpp `automatical`,
  * which picks from nnz statistics); every variant sums rows in the same order, so the
  * choice never changes a result.  plan_variant returns the recorded choice (-1 untuned).
+ * When b is larger than L2 can hold next to the matrix stream (> 48 MB) and the rows are
+ * column-sorted, tune also tries a COLUMN-BLOCKED COPY of col_idxs/values held by the plan
+ * (2-4 parts of <= 40 MB of b each, applied in order: the row sums keep their exact
+ * left-to-right order, so the bits do not change) and keeps it if it is >= 8 % faster.
+ * The copy is only used for calls that pass the same col_idxs / values pointers; after
+ * changing the values in place, tune again (the reference's `srow` has the same contract
+ * for structural changes, csr.hpp `make_srow`).  B200_CSR_REBLOCK=0 disables it.
  * ------------------------------------------------------------------------- */
 #define B200_DECL_CSR(V, VT, I, IT)                                                          \
     b200_status b200_csr_plan_create_##V##_##I(b200_ctx* ctx, int64_t num_rows, int64_t nnz, \
@@ -133,6 +140,7 @@ b200_status b200_pipe_join(b200_pipe* pipe);
         VT* c, int64_t c_stride);
 void b200_csr_plan_destroy(b200_csr_plan* plan);
 int b200_csr_plan_variant(const b200_csr_plan* plan);
+int b200_csr_plan_parts(const b200_csr_plan* plan); /* > 1: a column-blocked copy is in use */
 
 /* ---------------------------------------------------------------------------
  * ELL (core/matrix/ell_kernels.hpp:21-35; reference/matrix/ell_kernels.cpp:29-120)

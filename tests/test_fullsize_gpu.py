@@ -131,3 +131,42 @@ def test_plan_tune_keeps_results_bit_identical(kind):
     variant = _lib.lib().b200_csr_plan_variant(A.plan())
     assert variant in (2, 4)
     assert torch.equal(Y.values.reshape(-1), y0)
+
+
+@pytest.mark.parametrize("parts", [2, 3, 4])
+def test_column_blocked_copy_keeps_results_bit_identical(parts, monkeypatch):
+    """b200_csr_plan_tune_* with a forced column-blocked copy: the parts are applied in order
+    (c = A0 b, then c = 1*Ap b + 1*c), which must reproduce the single-pass row sums bit for
+    bit, for spmv and advanced_spmv; unsorted rows must refuse the copy."""
+    import torch
+    from ginkgo_b200 import api, _lib
+    monkeypatch.setenv("B200_CSR_REBLOCK", str(parts))
+    ex = api.B200Executor.create(0)
+    dev = ex.device
+    n = 400_000
+    with torch.cuda.stream(ex.stream):
+        rp, ci, va = W.random_csr(n, 9, xp="torch", device=dev, stream=11)
+        x = W.vector(n, xp="torch", device=dev)
+        y0 = torch.zeros(n, dtype=torch.float64, device=dev)
+        y1 = W.vector(n, stream=13, xp="torch", device=dev)
+        y1b = y1.clone()
+        alpha = torch.tensor([-1.5], dtype=torch.float64, device=dev)
+        beta = torch.tensor([0.25], dtype=torch.float64, device=dev)
+    A = api.Csr(ex, (n, n), va, ci, rp)
+    assert _lib.lib().b200_csr_plan_parts(A.plan()) == parts
+    Y = api.Dense(ex, torch.zeros_like(y0))
+    A.apply(api.Dense(ex, x), Y)
+    ex.run("b200_csr_spmv_f64_i32", None, n, n, A.nnz, rp, ci, va, x, 1, 1, y0, 1)
+    Y1 = api.Dense(ex, y1)
+    A.apply(api.Dense(ex, alpha), api.Dense(ex, x), api.Dense(ex, beta), Y1)
+    ex.run("b200_csr_advanced_spmv_f64_i32", None, n, n, A.nnz, rp, ci, va, alpha, x, 1, 1, beta,
+           y1b, 1)
+    ex.synchronize()
+    assert torch.equal(Y.values.reshape(-1), y0)
+    assert torch.equal(y1, y1b)
+    # unsorted rows: the copy is refused, the plan still works
+    with torch.cuda.stream(ex.stream):
+        ci2 = ci.clone()
+        ci2[0], ci2[1] = ci[1], ci[0]
+    B = api.Csr(ex, (n, n), va, ci2, rp)
+    assert _lib.lib().b200_csr_plan_parts(B.plan()) == 0
