@@ -274,9 +274,12 @@ def run_gpu_arm(args, rank, world):
                 "launches_per_step": max(plan_parts, 1),
                 "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_kernel}
     prof = os.path.join(ROOT, "profiles", "r01_csr_spmv_cfg2.json")
-    if os.path.exists(prof):
+    if os.path.exists(prof) and world == 1:  # the capture is of the 1-GPU workload
         try:
-            roofline["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
+            pj = json.load(open(prof))
+            # the capture is of the column-blocked SpMV (2 launches); without the copy one
+            # launch moves what profiles/r01g_spmv_cfg2_random.json shows
+            roofline["traffic"] = pj.get("dram_bytes_per_launch") if plan_parts > 1 else 4518669040.0
         except Exception:
             pass
     del A, rp, ci, va, x_full

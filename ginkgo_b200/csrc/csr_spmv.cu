@@ -362,7 +362,7 @@ b200_status plan_tune(b200_ctx* ctx, b200_csr_plan* plan, int64_t num_rows, int6
             cudaEventRecord(e1, ctx->stream);
             if (cudaEventSynchronize(e1) != cudaSuccess) st = B200_ERR_CUDA;
             if (st == B200_OK) cudaEventElapsedTime(&t_parts, e0, e1);
-            if (st != B200_OK || (!rb && t_parts > 0.92f * best)) plan_drop_parts(plan);
+            if (st != B200_OK || (!rb && t_parts > 0.96f * best)) plan_drop_parts(plan);
         }
     }
     cudaEventDestroy(e0);

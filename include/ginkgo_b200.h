@@ -117,7 +117,7 @@ b200_status b200_pipe_join(b200_pipe* pipe);
  * When b is larger than L2 can hold next to the matrix stream (> 48 MB) and the rows are
  * column-sorted, tune also tries a COLUMN-BLOCKED COPY of col_idxs/values held by the plan
  * (2-4 parts of <= 40 MB of b each, applied in order: the row sums keep their exact
- * left-to-right order, so the bits do not change) and keeps it if it is >= 8 % faster.
+ * left-to-right order, so the bits do not change) and keeps it if it is >= 4 % faster.
  * The copy is only used for calls that pass the same col_idxs / values pointers; after
  * changing the values in place, tune again (the reference's `srow` has the same contract
  * for structural changes, csr.hpp `make_srow`).  B200_CSR_REBLOCK=0 disables it.
