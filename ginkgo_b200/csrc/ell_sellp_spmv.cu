@@ -19,6 +19,44 @@
 #include "common.cuh"
 
 namespace b200 {
+
+// acc += sum_i val_i * b[col_i] over `len` stored entries spaced `step` apart, in storage
+// order, skipping padding (col == -1) exactly like the reference loops.  The loads of four
+// entries are issued together (padding reads b[0] and is discarded), so a row is not a chain
+// of dependent memory latencies.
+template <typename V, typename I, bool ADVANCED>
+__device__ __forceinline__ V strided_row_sum(V acc, const I* __restrict__ cols,
+                                             const V* __restrict__ vals, int64_t step, int64_t len,
+                                             int64_t lane_first, int64_t lane_step, V alpha,
+                                             const V* __restrict__ b, int64_t b_stride,
+                                             uint64_t pol_first, uint64_t pol_last)
+{
+    int64_t i = lane_first;
+    for (; i + 3 * lane_step < len; i += 4 * lane_step) {
+        I c[4];
+        V v[4], x[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) c[k] = ld_stream(cols + (i + k * lane_step) * step, pol_first);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = ld_stream(vals + (i + k * lane_step) * step, pol_first);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            x[k] = ld_gather(b + (int64_t)(c[k] < I(0) ? I(0) : c[k]) * b_stride, pol_last);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (c[k] != I(-1)) acc += ADVANCED ? (alpha * v[k]) * x[k] : v[k] * x[k];
+    }
+    for (; i < len; i += lane_step) {
+        const I c = ld_stream(cols + i * step, pol_first);
+        if (c != I(-1)) {
+            const V v = ld_stream(vals + i * step, pol_first);
+            const V x = ld_gather(b + (int64_t)c * b_stride, pol_last);
+            acc += ADVANCED ? (alpha * v) * x : v * x;
+        }
+    }
+    return acc;
+}
+
 namespace ell {
 
 constexpr int kThreads = 256;
@@ -47,14 +85,9 @@ __global__ void __launch_bounds__(kThreads)
     const bool rv = row < num_rows;
     if (rv) {
         if (LANES == 1 && ADVANCED && beta != V(0)) acc = beta * c[row * c_stride + j];
-        for (int64_t i = lane; i < width; i += LANES) {
-            const I col = ld_stream(col_idxs + row + i * stride, pol_first);
-            if (col != I(-1)) {
-                const V val = ld_stream(values + row + i * stride, pol_first);
-                const V x = ld_gather(b + (int64_t)col * b_stride + j, pol_last);
-                acc += ADVANCED ? (alpha * val) * x : val * x;
-            }
-        }
+        acc = strided_row_sum<V, I, ADVANCED>(acc, col_idxs + row, values + row, stride, width,
+                                              lane, LANES, alpha, b + j, b_stride, pol_first,
+                                              pol_last);
     }
     if (LANES == 1) {
         if (rv) c[row * c_stride + j] = acc;
@@ -123,7 +156,10 @@ __global__ void __launch_bounds__(256)
     if (row >= num_rows) return;
     const uint64_t pol_first = policy_evict_first();
     const uint64_t pol_last = policy_evict_last();
-    const int64_t slice = row / slice_size;
+    // 32-bit division when it fits (a 64-bit one costs as much as a 7-entry row)
+    const int64_t slice = (num_rows >> 31) == 0 && (slice_size >> 31) == 0
+                              ? (int64_t)((uint32_t)row / (uint32_t)slice_size)
+                              : row / slice_size;
     const int64_t rin = row - slice * slice_size;
     const int64_t base = (int64_t)slice_sets[slice];
     const int64_t len = (int64_t)slice_lengths[slice];
@@ -134,15 +170,9 @@ __global__ void __launch_bounds__(256)
     }
     V acc = V(0);
     if (ADVANCED && beta != V(0)) acc = c[row * c_stride + j] * beta;
-    for (int64_t i = 0; i < len; ++i) {
-        const int64_t idx = (base + i) * slice_size + rin;
-        const I col = ld_stream(col_idxs + idx, pol_first);
-        if (col != I(-1)) {
-            const V val = ld_stream(values + idx, pol_first);
-            const V x = ld_gather(b + (int64_t)col * b_stride + j, pol_last);
-            acc += ADVANCED ? (alpha * val) * x : val * x;
-        }
-    }
+    const int64_t first = base * slice_size + rin;
+    acc = strided_row_sum<V, I, ADVANCED>(acc, col_idxs + first, values + first, slice_size, len, 0, 1,
+                                          alpha, b + j, b_stride, pol_first, pol_last);
     c[row * c_stride + j] = acc;
 }
 

@@ -181,11 +181,17 @@ __global__ void __launch_bounds__(kMdThreads)
     __syncthreads();
     if (is_last) {
         __threadfence();
-        for (int64_t e = tid; e < num_bases * cols; e += kMdThreads) {
+        // one warp per (basis, column): lanes stride over the per-CTA partials, fixed shuffle
+        // tree -- deterministic, and not a serial chain of gridDim.x dependent L2 reads
+        const int lane = tid & 31, wrp = tid >> 5;
+        for (int64_t e = wrp; e < num_bases * cols; e += kMdThreads / 32) {
             V s = V(0);
-            for (int g = 0; g < (int)gridDim.x; ++g) s += __ldcg(partials + e * gridDim.x + g);
-            const int64_t i = e / cols, k = e - i * cols;
-            hcol[i * hs + k] = s;
+            for (int g = lane; g < (int)gridDim.x; g += 32) s += __ldcg(partials + e * gridDim.x + g);
+            s = warp_sum(s);
+            if (lane == 0) {
+                const int64_t i = e / cols, k = e - i * cols;
+                hcol[i * hs + k] = s;
+            }
         }
         if (tid == 0) *counter = 0u;
     }

@@ -96,7 +96,12 @@ namespace jacobi {
 // single right-hand side this is a batch of tiny GEMVs at ~0.5 flop/byte:
 // HBM-bound, so no tensor cores (SURVEY.md section 7 "Block-Jacobi layout").
 // Summation order per row: inner = 0..bs-1, as the reference's apply_block.
-template <typename V, typename I, bool ADVANCED>
+// One warp per storage GROUP (32 / pow2(max_block_size) blocks interleaved so that column c
+// of all of them is one contiguous run): lane l holds row l % block_offset of sub-block
+// l / block_offset, so every load of a block column is a single coalesced run for the whole
+// warp.  All MBS columns are fetched before the first multiply (no chain of dependent
+// latencies) and stay in registers for every right-hand side.
+template <typename V, typename I, int MBS, bool ADVANCED>
 __global__ void __launch_bounds__(256)
     block_apply_kernel(int64_t num_blocks, int64_t block_offset, int64_t group_offset,
                        int32_t group_power, const I* __restrict__ block_ptrs,
@@ -105,31 +110,42 @@ __global__ void __launch_bounds__(256)
                        const V* __restrict__ beta_p, V* __restrict__ x, int64_t xs)
 {
     const int lane = threadIdx.x & 31;
-    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    if (warp >= num_blocks) return;
-    const int64_t k = warp;
-    const int64_t first = block_ptrs[k];
-    const int bsz = (int)((int64_t)block_ptrs[k + 1] - first);
+    const int64_t group = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int group_size = 1 << group_power;
+    if (group * group_size >= num_blocks) return;
+    const int bo = (int)block_offset;
+    const int sub = lane / bo;
+    const int r = lane - sub * bo;
+    const int64_t k = group * group_size + sub;
+    int64_t first = 0;
+    int bsz = 0;
+    if (sub < group_size && k < num_blocks) {
+        first = block_ptrs[k];
+        bsz = (int)((int64_t)block_ptrs[k + 1] - first);
+    }
+    const bool valid = r < bsz;
     const int64_t stride = block_offset << group_power;
-    const V* blk = blocks + group_offset * (k >> group_power) +
-                   block_offset * (k & ((int64_t(1) << group_power) - 1));
+    const V* col0 = blocks + group_offset * group + lane;
+    V a[MBS];
+#pragma unroll
+    for (int inner = 0; inner < MBS; ++inner)
+        a[inner] = (valid && inner < bsz) ? col0[inner * stride] : V(0);
     V alpha = V(1), beta = V(0);
     if (ADVANCED) {
         alpha = *alpha_p;
         beta = *beta_p;
     }
+    const int src0 = sub * bo;
     for (int64_t j = 0; j < num_rhs; ++j) {
-        const V bv = lane < bsz ? b[(first + lane) * bs_ + j] : V(0);
+        const V bv = valid ? b[(first + r) * bs_ + j] : V(0);
         V acc = V(0);
-        if (ADVANCED && lane < bsz && beta != V(0)) acc = x[(first + lane) * xs + j] * beta;
-        for (int inner = 0; inner < bsz; ++inner) {
-            const V bi = __shfl_sync(0xffffffffu, bv, inner);
-            if (lane < bsz) {
-                const V a = blk[lane + inner * stride];
-                acc += ADVANCED ? (alpha * a) * bi : a * bi;
-            }
+        if (ADVANCED && valid && beta != V(0)) acc = x[(first + r) * xs + j] * beta;
+#pragma unroll
+        for (int inner = 0; inner < MBS; ++inner) {
+            const V bi = __shfl_sync(0xffffffffu, bv, (src0 + inner) & 31);
+            if (valid && inner < bsz) acc += ADVANCED ? (alpha * a[inner]) * bi : a[inner] * bi;
         }
-        if (lane < bsz) x[(first + lane) * xs + j] = acc;
+        if (valid) x[(first + r) * xs + j] = acc;
     }
 }
 
@@ -141,11 +157,24 @@ b200_status block_apply(b200_ctx* ctx, int64_t num_blocks, int32_t max_block_siz
 {
     B200_REQUIRE(ctx != nullptr, "ctx is null");
     B200_REQUIRE(max_block_size >= 1 && max_block_size <= 32, "max_block_size must be in [1,32]");
+    B200_REQUIRE(block_offset >= 1 && (block_offset << group_power) <= 32 && group_power >= 0,
+                 "storage scheme does not fit a warp");
     if (num_blocks <= 0 || num_rhs <= 0) return B200_OK;
-    const int64_t grid = ceildiv(num_blocks * 32, 256);
-    block_apply_kernel<V, I, ADVANCED><<<(unsigned)grid, 256, 0, ctx->stream>>>(
-        num_blocks, block_offset, group_offset, group_power, block_ptrs, blocks, alpha, b, bs,
-        num_rhs, beta, x, xs);
+    const int64_t groups = ceildiv(num_blocks, int64_t(1) << group_power);
+    const unsigned grid = (unsigned)ceildiv(groups * 32, (int64_t)256);
+#define B200_BJ(M)                                                                              \
+    block_apply_kernel<V, I, M, ADVANCED><<<grid, 256, 0, ctx->stream>>>(                       \
+        num_blocks, block_offset, group_offset, group_power, block_ptrs, blocks, alpha, b, bs,  \
+        num_rhs, beta, x, xs)
+    if (block_offset <= 4)
+        B200_BJ(4);
+    else if (block_offset <= 8)
+        B200_BJ(8);
+    else if (block_offset <= 16)
+        B200_BJ(16);
+    else
+        B200_BJ(32);
+#undef B200_BJ
     B200_LAUNCH_CHECK(ctx);
     return B200_OK;
 }

@@ -163,6 +163,7 @@ GKOB_V(float, f32)
         static constexpr auto jacobi_simple_apply = b200_jacobi_simple_apply_##S##_##T;         \
         static constexpr auto jacobi_apply = b200_jacobi_apply_##S##_##T;                       \
         static constexpr auto jacobi_generate = b200_jacobi_generate_##S##_##T;                 \
+        static constexpr auto jacobi_find_blocks = b200_jacobi_find_blocks_##T;                 \
     };
 GKOB_VI(double, f64, int32, i32)
 GKOB_VI(double, f64, int64, i64)

@@ -236,8 +236,8 @@ inline std::unique_ptr<Criterion> combine_and_generate(
 // jacobi.cpp).  apply and generate run on the device; generate: scalar = extract_diagonal +
 // invert_diagonal kernels; block = b200_jacobi_generate_* (the reference's pivoted
 // Gauss-Jordan, reference/preconditioner/jacobi_kernels.cpp:113-410, in the reference's
-// operation order) with user-supplied block pointers (natural-block detection is not part
-// of this path).
+// operation order); block pointers are user-supplied or detected by b200_jacobi_find_blocks_*
+// (reference/preconditioner/jacobi_kernels.cpp:36-123).
 // =============================================================================================
 namespace preconditioner {
 
@@ -291,6 +291,7 @@ public:
     uint32 get_max_block_size() const { return max_block_size_; }
     size_type get_num_blocks() const { return num_blocks_; }
     const V* get_blocks() const { return blocks_.get_const_data(); }
+    const I* get_const_block_pointers() const { return block_pointers_.get_const_data(); }
     const block_interleaved_storage_scheme<I>& get_storage_scheme() const { return scheme_; }
 
 protected:
@@ -309,9 +310,18 @@ protected:
             num_blocks_ = n;
             return;
         }
-        if (f.block_pointers_.empty())
-            throw NotSupported("block Jacobi on this path needs explicit block_pointers");
         std::vector<I> ptrs = f.block_pointers_;
+        if (ptrs.empty()) {
+            // jacobi::find_blocks on the device (natural blocks + agglomeration)
+            array<I> dev_ptrs(exec, n + 1);
+            int64 nb = 0;
+            GKOB_CALL((viabi<V, I>::jacobi_find_blocks(exec->ctx(), n, csr->get_const_row_ptrs(),
+                                                       csr->get_const_col_idxs(),
+                                                       (int32)max_block_size_, dev_ptrs.get_data(),
+                                                       &nb)));
+            ptrs.resize(nb + 1);
+            exec->copy_to_host(ptrs.data(), dev_ptrs.get_const_data(), nb + 1);
+        }
         num_blocks_ = ptrs.size() - 1;
         // compute_storage_scheme (jacobi.hpp:589-625)
         uint32 pow2 = 1;

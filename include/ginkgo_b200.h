@@ -239,6 +239,18 @@ void b200_coo_plan_destroy(b200_coo_plan* plan);
         const VT* values, int64_t num_blocks, int32_t max_block_size, int64_t block_offset,   \
         int64_t group_offset, int32_t group_power, const IT* block_pointers, VT* blocks);
 
+/* jacobi::find_blocks (core/preconditioner/jacobi_kernels.hpp:19-26; reference/preconditioner/
+ * jacobi_kernels.cpp:36-123): natural blocks = maximal runs of rows with identical column
+ * patterns, cut at max_block_size, then greedy agglomeration of neighbours while the sum
+ * stays <= max_block_size.  block_pointers needs num_rows + 1 entries; the number of blocks
+ * comes back on the host (the call synchronises).  Integer-exact. */
+b200_status b200_jacobi_find_blocks_i32(b200_ctx* ctx, int64_t num_rows, const int32_t* row_ptrs,
+                                        const int32_t* col_idxs, int32_t max_block_size,
+                                        int32_t* block_pointers, int64_t* num_blocks_host);
+b200_status b200_jacobi_find_blocks_i64(b200_ctx* ctx, int64_t num_rows, const int64_t* row_ptrs,
+                                        const int64_t* col_idxs, int32_t max_block_size,
+                                        int64_t* block_pointers, int64_t* num_blocks_host);
+
 /* ---------------------------------------------------------------------------
  * Dense BLAS-1 (core/matrix/dense_kernels.hpp:34-135;
  * reference/matrix/dense_kernels.cpp:95-437).  `result` is a 1 x cols device

@@ -93,6 +93,52 @@ static int orc_cmp_i64(const void* a, const void* b)
 ORC_CONVERT_FMT(i32, int32_t)
 ORC_CONVERT_FMT(i64, int64_t)
 
+/* reference/preconditioner/jacobi_kernels.cpp:36-123: has_same_nonzero_pattern,
+ * find_natural_blocks, agglomerate_supervariables, find_blocks */
+#define ORC_FIND_BLOCKS(IS, I)                                                              \
+    void orc_jacobi_find_blocks_##IS(int64_t rows, const I* row_ptrs, const I* col_idx,     \
+                                     int32_t max_block_size, I* block_ptrs,                 \
+                                     int64_t* num_blocks_out)                               \
+    {                                                                                       \
+        block_ptrs[0] = 0;                                                                  \
+        *num_blocks_out = 0;                                                                \
+        if (rows == 0) return;                                                              \
+        int64_t num_blocks = 1;                                                             \
+        int32_t current = 1;                                                                \
+        for (int64_t i = 1; i < rows; ++i) {                                                \
+            const I* prev = col_idx + row_ptrs[i - 1];                                      \
+            const I* curr = col_idx + row_ptrs[i];                                          \
+            const I* next = col_idx + row_ptrs[i + 1];                                      \
+            int same = (next - curr) == (curr - prev);                                      \
+            for (int64_t k = 0; same && k < next - curr; ++k) same = curr[k] == prev[k];    \
+            if (current < max_block_size && same) {                                         \
+                ++current;                                                                  \
+            } else {                                                                        \
+                block_ptrs[num_blocks] = block_ptrs[num_blocks - 1] + current;              \
+                ++num_blocks;                                                               \
+                current = 1;                                                                \
+            }                                                                               \
+        }                                                                                   \
+        block_ptrs[num_blocks] = block_ptrs[num_blocks - 1] + current;                      \
+        const int64_t num_natural = num_blocks;                                             \
+        num_blocks = 1;                                                                     \
+        I cur = block_ptrs[1] - block_ptrs[0];                                              \
+        for (int64_t i = 1; i < num_natural; ++i) {                                         \
+            const I size = block_ptrs[i + 1] - block_ptrs[i];                               \
+            if (cur + size <= max_block_size) {                                             \
+                cur += size;                                                                \
+            } else {                                                                        \
+                block_ptrs[num_blocks] = block_ptrs[i];                                     \
+                ++num_blocks;                                                               \
+                cur = size;                                                                 \
+            }                                                                               \
+        }                                                                                   \
+        block_ptrs[num_blocks] = block_ptrs[num_natural];                                   \
+        *num_blocks_out = num_blocks;                                                       \
+    }
+ORC_FIND_BLOCKS(i32, int32_t)
+ORC_FIND_BLOCKS(i64, int64_t)
+
 /* ---- double ---- */
 #define V double
 #define VS f64

@@ -248,3 +248,40 @@ def test_jacobi_generate_bit_identical_to_reference(orc, vt, max_bs):
             k & ((1 << r["group_power"]) - 1))
         idx = off + (np.arange(bs)[:, None] + np.arange(bs)[None, :] * stride)
         assert np.array_equal(blocks[idx], r["blocks"][idx]), k
+
+
+def _blocky_matrix(rng, n, max_run, vt="f64"):
+    """rows come in runs sharing one column pattern (natural blocks), run lengths 1..max_run"""
+    rows_cols = []
+    r = 0
+    while r < n:
+        run = int(rng.integers(1, max_run + 1))
+        k = int(rng.integers(1, 9))
+        cols = np.sort(rng.choice(n, size=k, replace=False))
+        for _ in range(min(run, n - r)):
+            rows_cols.append(cols)
+            r += 1
+    rp = np.zeros(n + 1, np.int32)
+    rp[1:] = np.cumsum([len(c) for c in rows_cols])
+    ci = np.concatenate(rows_cols).astype(np.int32)
+    va = rng.uniform(-1, 1, len(ci)).astype(VT[vt])
+    # make the diagonal blocks invertible enough: not needed for find_blocks itself
+    return rp, ci, va
+
+
+@pytest.mark.parametrize("max_bs", [1, 2, 5, 16, 32])
+@pytest.mark.parametrize("max_run", [1, 3, 40])
+def test_find_blocks_matches_reference(orc, max_bs, max_run):
+    rng = np.random.default_rng(70 + max_bs + max_run)
+    n = 3000
+    rp, ci, va = _blocky_matrix(rng, n, max_run)
+    # put a strong diagonal so the reference's generate does not hit singular blocks
+    r = ref.jacobi_generate(rp, ci, va, max_bs, None)
+    bp = np.full(n + 1, -1, np.int32)
+    nb = H.OutI64()
+    orc("jacobi_find_blocks_i32", n, rp, ci, max_bs, bp, nb)
+    if max_bs == 1:
+        assert nb.value == n and np.array_equal(bp[:n + 1], np.arange(n + 1))
+    else:
+        assert nb.value == r["num_blocks"]
+        assert np.array_equal(bp[:nb.value + 1], r["block_ptrs"])

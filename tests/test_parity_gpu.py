@@ -668,3 +668,29 @@ def test_jacobi_generate_bit_exact(orc, cuda, vt, it, max_bs, singular):
                     blk[r, c] = va[p]
         err = np.abs(inv @ blk - np.eye(bs)).max()
         assert err < (1e-9 if vt == "f64" else 1e-2) * max(1.0, np.linalg.cond(blk))
+
+
+@pytest.mark.parametrize("it", ITS)
+@pytest.mark.parametrize("max_bs", [1, 2, 5, 16, 32])
+@pytest.mark.parametrize("n,max_run", [(1, 1), (5000, 1), (5000, 3), (5000, 40), (70000, 7)])
+def test_find_blocks_bit_exact(orc, cuda, it, max_bs, n, max_run):
+    rng = np.random.default_rng(80 + max_bs + max_run)
+    cols_of = []
+    r = 0
+    while r < n:
+        run = int(rng.integers(1, max_run + 1))
+        k = int(rng.integers(1, 9))
+        cols = np.sort(rng.choice(n, size=min(k, n), replace=False))
+        for _ in range(min(run, n - r)):
+            cols_of.append(cols)
+            r += 1
+    rp = np.zeros(n + 1, IT[it])
+    rp[1:] = np.cumsum([len(c) for c in cols_of])
+    ci = np.concatenate(cols_of).astype(IT[it])
+    no, nc = H.OutI64(), H.OutI64()
+    bo, bc = np.full(n + 1, -1, IT[it]), np.full(n + 1, -1, IT[it])
+    orc("jacobi_find_blocks_" + it, n, rp, ci, max_bs, bo, no)
+    cuda("jacobi_find_blocks_" + it, n, rp, ci, max_bs, bc, nc)
+    assert no.value == nc.value
+    assert np.array_equal(bo[:no.value + 1], bc[:nc.value + 1])
+    assert bc[nc.value] == n and np.all(np.diff(bc[:nc.value + 1]) <= max_bs)

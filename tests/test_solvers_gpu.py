@@ -101,6 +101,36 @@ def test_solver_matches_oracle(hexec, kind, precond, vt, fused):
         assert H.rel_err(xo, xd) <= (1e-8 if vt == "f64" else 1e-3)
 
 
+def test_block_jacobi_with_detected_blocks(hexec):
+    """Jacobi::build().with_max_block_size(4) WITHOUT block pointers: find_blocks on the device
+    must reproduce the reference's blocks, so CG + block Jacobi takes the oracle's path."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("needs oracle/_ref")
+    vt = "f64"
+    # 2x2 block structure: a 2-D Laplacian expanded by kron(A, [[2,1],[1,2]]) has row pairs
+    # with identical patterns
+    rp0, ci0, va0 = W.laplace(24, 2)
+    n0 = len(rp0) - 1
+    import scipy.sparse as sp
+    A = sp.kron(sp.csr_matrix((va0, ci0, rp0), shape=(n0, n0)), np.array([[2.0, 1.0], [1.0, 2.0]]),
+                format="csr")
+    A.sort_indices()
+    rp, ci, va = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.astype(np.float64)
+    n = A.shape[0]
+    jac = ref.jacobi_generate(rp, ci, va, 4, None)
+    assert jac["num_blocks"] < n  # blocks were found
+    rng = np.random.default_rng(3)
+    b = rng.uniform(-1, 1, (n, 1))
+    x0 = np.zeros((n, 1))
+    xo, ito, stop_o = H.orc_solve("cg", vt, rp, ci, va, b, x0, 2, jac, max_iters=500, reduction=1e-9,
+                                  iter_first=1, krylov_dim=20)
+    xd, itd, stop_d, _ = device_solve(hexec, "cg", vt, rp, ci, va, b, x0, 4, None, max_iters=500,
+                                      reduction=1e-9, iter_first=True, krylov_dim=20, fused=False)
+    assert abs(itd - ito) <= 2 and stop_d == stop_o[0]
+    assert H.rel_err(xo, xd) <= 1e-8
+
+
 def test_iteration_limit_and_status(hexec):
     rp, ci, va = W.laplace(30, 2)
     n = len(rp) - 1
