@@ -542,6 +542,7 @@ b200_status apply(b200_ctx* ctx, const b200_coo_plan* plan, int mode, int64_t nu
     B200_REQUIRE(ctx != nullptr, "ctx is null");
     B200_REQUIRE(num_rows >= 0 && nnz >= 0, "negative size");
     if (num_rows == 0 || num_rhs == 0) return B200_OK;
+    if (nnz == 0 && mode >= 2) return B200_OK;  // c += (nothing): the reference loop is empty
     const I* row_ptrs;
     const b200_csr_plan* cplan = nullptr;
     const V* ones;

@@ -22,8 +22,8 @@ namespace b200 {
 
 // acc += sum_i val_i * b[col_i] over `len` stored entries spaced `step` apart, in storage
 // order, skipping padding (col == -1) exactly like the reference loops.  The loads of four
-// entries are issued together (padding reads b[0] and is discarded), so a row is not a chain
-// of dependent memory latencies.
+// entries are issued together (predicated off for padding and for positions past `len`), so
+// a row of 7 entries costs two memory latencies instead of seven.
 template <typename V, typename I, bool ADVANCED>
 __device__ __forceinline__ V strided_row_sum(V acc, const I* __restrict__ cols,
                                              const V* __restrict__ vals, int64_t step, int64_t len,
@@ -31,28 +31,25 @@ __device__ __forceinline__ V strided_row_sum(V acc, const I* __restrict__ cols,
                                              const V* __restrict__ b, int64_t b_stride,
                                              uint64_t pol_first, uint64_t pol_last)
 {
-    int64_t i = lane_first;
-    for (; i + 3 * lane_step < len; i += 4 * lane_step) {
+    for (int64_t i = lane_first; i < len; i += 4 * lane_step) {
         I c[4];
         V v[4], x[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) c[k] = ld_stream(cols + (i + k * lane_step) * step, pol_first);
+        for (int k = 0; k < 4; ++k) {
+            const int64_t ik = i + k * lane_step;
+            c[k] = ik < len ? ld_stream(cols + ik * step, pol_first) : I(-1);
+        }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) v[k] = ld_stream(vals + (i + k * lane_step) * step, pol_first);
+        for (int k = 0; k < 4; ++k) {
+            const int64_t ik = i + k * lane_step;
+            v[k] = ik < len ? ld_stream(vals + ik * step, pol_first) : V(0);
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            x[k] = ld_gather(b + (int64_t)(c[k] < I(0) ? I(0) : c[k]) * b_stride, pol_last);
+            x[k] = c[k] >= I(0) ? ld_gather(b + (int64_t)c[k] * b_stride, pol_last) : V(0);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
             if (c[k] != I(-1)) acc += ADVANCED ? (alpha * v[k]) * x[k] : v[k] * x[k];
-    }
-    for (; i < len; i += lane_step) {
-        const I c = ld_stream(cols + i * step, pol_first);
-        if (c != I(-1)) {
-            const V v = ld_stream(vals + i * step, pol_first);
-            const V x = ld_gather(b + (int64_t)c * b_stride, pol_last);
-            acc += ADVANCED ? (alpha * v) * x : v * x;
-        }
     }
     return acc;
 }

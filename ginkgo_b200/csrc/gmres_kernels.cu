@@ -136,9 +136,17 @@ b200_status multi_axpy(b200_ctx* ctx, int64_t rows, int64_t cols, const V* krylo
 // grid.x CTAs each own a strided set of row chunks; a thread keeps w(r) in a
 // register and walks the bases, so w is read once and every basis once.
 constexpr int kMdThreads = 256;
-constexpr int kMdMaxBases = 8;  // bases handled per sweep (register accumulators)
+constexpr int kMdMaxBases = 16;  // bases handled per sweep (register accumulators)
 
-template <typename V>
+// VW consecutive rows per thread (one 16-byte load per basis when VW * sizeof(V) == 16):
+// 17 x 16 B in flight per thread, enough memory-level parallelism to stream HBM -- with one
+// 4-byte element per load the kernel sat at 20 % of the HBM roofline.
+template <typename V, int VW>
+struct alignas(sizeof(V) * VW) md_vec {
+    V v[VW];
+};
+
+template <typename V, int VW>
 __global__ void __launch_bounds__(kMdThreads)
     multi_dot_kernel(int64_t rows, int64_t cols, int64_t num_bases, const V* __restrict__ krylov,
                      int64_t ks, const V* __restrict__ w, int64_t wstride, V* __restrict__ partials,
@@ -147,20 +155,35 @@ __global__ void __launch_bounds__(kMdThreads)
     __shared__ V red[32];
     __shared__ bool is_last;
     const int tid = threadIdx.x;
-    // work item = (row, rhs column), columns fastest
-    const int64_t total = rows * cols;
+    using vec = md_vec<V, VW>;
     for (int64_t i0 = 0; i0 < num_bases; i0 += kMdMaxBases) {
         const int nb = (int)((num_bases - i0) < kMdMaxBases ? (num_bases - i0) : kMdMaxBases);
         for (int64_t k = 0; k < cols; ++k) {
             V acc[kMdMaxBases];
 #pragma unroll
             for (int q = 0; q < kMdMaxBases; ++q) acc[q] = V(0);
-            for (int64_t r = blockIdx.x * (int64_t)kMdThreads + tid; r < rows;
-                 r += (int64_t)gridDim.x * kMdThreads) {
-                const V wv = w[r * wstride + k];
+            for (int64_t r = (blockIdx.x * (int64_t)kMdThreads + tid) * VW; r < rows;
+                 r += (int64_t)gridDim.x * kMdThreads * VW) {
+                vec wv, kv[kMdMaxBases];
+                if (VW == 1) {
+                    wv.v[0] = w[r * wstride + k];
+#pragma unroll
+                    for (int q = 0; q < kMdMaxBases; ++q)
+                        kv[q].v[0] = q < nb ? krylov[((i0 + q) * rows + r) * ks + k] : V(0);
+                } else {  // ks == wstride == 1, cols == 1, rows % VW == 0, aligned (host checks)
+                    wv = *reinterpret_cast<const vec*>(w + r);
+#pragma unroll
+                    for (int q = 0; q < kMdMaxBases; ++q) {
+                        if (q < nb)
+                            kv[q] = *reinterpret_cast<const vec*>(krylov + (i0 + q) * rows + r);
+                    }
+                }
 #pragma unroll
                 for (int q = 0; q < kMdMaxBases; ++q) {
-                    if (q < nb) acc[q] += krylov[((i0 + q) * rows + r) * ks + k] * wv;
+                    if (q < nb) {
+#pragma unroll
+                        for (int e = 0; e < VW; ++e) acc[q] += kv[q].v[e] * wv.v[e];
+                    }
                 }
             }
 #pragma unroll
@@ -172,7 +195,6 @@ __global__ void __launch_bounds__(kMdThreads)
             }
         }
     }
-    (void)total;
     if (tid == 0) {
         __threadfence();
         const unsigned int ticket = atomicAdd(counter, 1u);
@@ -203,13 +225,20 @@ b200_status multi_dot(b200_ctx* ctx, int64_t rows, int64_t cols, int64_t num_bas
 {
     B200_REQUIRE(ctx != nullptr, "ctx is null");
     if (num_bases <= 0 || cols <= 0) return B200_OK;
-    int grid = (int)ceildiv(rows, kMdThreads * 4);
-    if (grid > ctx->num_sms * 4) grid = ctx->num_sms * 4;
+    constexpr int kVW = 16 / (int)sizeof(V);
+    const bool vec_ok = cols == 1 && ks == 1 && ws == 1 && rows % kVW == 0 &&
+                        ((uintptr_t)krylov % 16) == 0 && ((uintptr_t)w % 16) == 0;
+    int grid = (int)ceildiv(rows, (int64_t)kMdThreads * (vec_ok ? kVW : 1) * 2);
+    if (grid > ctx->num_sms * 3) grid = ctx->num_sms * 3;
     if (grid < 1) grid = 1;
     V* partials = (V*)ctx->scratch(sizeof(V) * grid * num_bases * cols);
     if (!partials) return B200_ERR_ALLOC;
-    multi_dot_kernel<V><<<grid, kMdThreads, 0, ctx->stream>>>(rows, cols, num_bases, krylov, ks, w, ws,
-                                                              partials, ctx->counters, hcol, hs);
+    if (vec_ok)
+        multi_dot_kernel<V, kVW><<<grid, kMdThreads, 0, ctx->stream>>>(
+            rows, cols, num_bases, krylov, ks, w, ws, partials, ctx->counters, hcol, hs);
+    else
+        multi_dot_kernel<V, 1><<<grid, kMdThreads, 0, ctx->stream>>>(
+            rows, cols, num_bases, krylov, ks, w, ws, partials, ctx->counters, hcol, hs);
     B200_LAUNCH_CHECK(ctx);
     return B200_OK;
 }
