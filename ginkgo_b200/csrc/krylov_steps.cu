@@ -62,6 +62,151 @@ b200_status cg_step_2(b200_ctx* ctx, int64_t rows, int64_t cols, V* x, int64_t x
     });
 }
 
+// ---- FCG (reference/solver/fcg_kernels.cpp:22-100) and CGS (reference/solver/
+// cgs_kernels.cpp:22-140): siblings of CG with the same element-wise + device-scalar pattern
+template <typename V>
+b200_status fcg_initialize(b200_ctx* ctx, int64_t rows, int64_t cols, const V* b, int64_t bs, V* r,
+                           int64_t rs, V* z, int64_t zs, V* p, int64_t ps, V* q, int64_t qs, V* t,
+                           int64_t ts, V* prev_rho, V* rho, V* rho_t, uint8_t* stop)
+{
+    B200_REQUIRE(ctx != nullptr, "ctx is null");
+    return launch_ew(ctx, rows + 1, cols, [=] __device__(int64_t i, int64_t j) {
+        if (i == rows) {
+            rho[j] = V(0);
+            prev_rho[j] = V(1);
+            rho_t[j] = V(1);
+            stop[j] = 0;
+        } else {
+            const V v = b[i * bs + j];
+            t[i * ts + j] = v;
+            r[i * rs + j] = v;
+            z[i * zs + j] = V(0);
+            p[i * ps + j] = V(0);
+            q[i * qs + j] = V(0);
+        }
+    });
+}
+
+template <typename V>
+b200_status fcg_step_1(b200_ctx* ctx, int64_t rows, int64_t cols, V* p, int64_t ps, const V* z,
+                       int64_t zs, const V* rho_t, const V* prev_rho, const uint8_t* stop)
+{
+    return launch_ew(ctx, rows, cols, [=] __device__(int64_t i, int64_t j) {
+        if (has_stopped(stop[j])) return;
+        const V pr = prev_rho[j];
+        if (pr == V(0)) {
+            p[i * ps + j] = z[i * zs + j];
+        } else {
+            const V tmp = rho_t[j] / pr;
+            p[i * ps + j] = z[i * zs + j] + tmp * p[i * ps + j];
+        }
+    });
+}
+
+template <typename V>
+b200_status fcg_step_2(b200_ctx* ctx, int64_t rows, int64_t cols, V* x, int64_t xs, V* r,
+                       int64_t rs, V* t, int64_t ts, const V* p, int64_t ps, const V* q,
+                       int64_t qs, const V* beta, const V* rho, const uint8_t* stop)
+{
+    return launch_ew(ctx, rows, cols, [=] __device__(int64_t i, int64_t j) {
+        if (has_stopped(stop[j])) return;
+        const V bt = beta[j];
+        if (bt != V(0)) {
+            const V tmp = rho[j] / bt;
+            const V prev_r = r[i * rs + j];
+            x[i * xs + j] += tmp * p[i * ps + j];
+            const V nr = prev_r - tmp * q[i * qs + j];
+            r[i * rs + j] = nr;
+            t[i * ts + j] = nr - prev_r;
+        }
+    });
+}
+
+template <typename V>
+b200_status cgs_initialize(b200_ctx* ctx, int64_t rows, int64_t cols, const V* b, int64_t bs, V* r,
+                           int64_t rs, V* r_tld, int64_t rts, V* p, int64_t ps, V* q, int64_t qs,
+                           V* u, int64_t us, V* u_hat, int64_t uhs, V* v_hat, int64_t vhs, V* t,
+                           int64_t ts, V* alpha, V* beta, V* gamma, V* prev_rho, V* rho,
+                           uint8_t* stop)
+{
+    B200_REQUIRE(ctx != nullptr, "ctx is null");
+    return launch_ew(ctx, rows + 1, cols, [=] __device__(int64_t i, int64_t j) {
+        if (i == rows) {
+            rho[j] = V(0);
+            prev_rho[j] = V(1);
+            alpha[j] = V(1);
+            beta[j] = V(1);
+            gamma[j] = V(1);
+            stop[j] = 0;
+        } else {
+            const V v = b[i * bs + j];
+            r[i * rs + j] = v;
+            r_tld[i * rts + j] = v;
+            u[i * us + j] = V(0);
+            u_hat[i * uhs + j] = V(0);
+            p[i * ps + j] = V(0);
+            q[i * qs + j] = V(0);
+            v_hat[i * vhs + j] = V(0);
+            t[i * ts + j] = V(0);
+        }
+    });
+}
+
+// step_1 and step_2 also WRITE a 1 x cols scalar (beta resp. alpha) that every thread of the
+// column needs: each thread recomputes it from the inputs, and the store is done by a
+// separate tiny launch BEFORE the vector update, exactly the reference's two loops.
+template <typename V>
+b200_status cgs_step_1(b200_ctx* ctx, int64_t rows, int64_t cols, const V* r, int64_t rs, V* u,
+                       int64_t us, V* p, int64_t ps, const V* q, int64_t qs, V* beta,
+                       const V* rho, const V* prev_rho, const uint8_t* stop)
+{
+    b200_status st = launch_ew(ctx, 1, cols, [=] __device__(int64_t, int64_t j) {
+        if (has_stopped(stop[j])) return;
+        if (prev_rho[j] != V(0)) beta[j] = rho[j] / prev_rho[j];
+    });
+    if (st != B200_OK) return st;
+    return launch_ew(ctx, rows, cols, [=] __device__(int64_t i, int64_t j) {
+        if (has_stopped(stop[j])) return;
+        const V bt = beta[j];
+        const V qv = q[i * qs + j];
+        const V uv = r[i * rs + j] + bt * qv;
+        u[i * us + j] = uv;
+        p[i * ps + j] = uv + bt * (qv + bt * p[i * ps + j]);
+    });
+}
+
+template <typename V>
+b200_status cgs_step_2(b200_ctx* ctx, int64_t rows, int64_t cols, const V* u, int64_t us,
+                       const V* v_hat, int64_t vhs, V* q, int64_t qs, V* t, int64_t ts, V* alpha,
+                       const V* rho, const V* gamma, const uint8_t* stop)
+{
+    b200_status st = launch_ew(ctx, 1, cols, [=] __device__(int64_t, int64_t j) {
+        if (has_stopped(stop[j])) return;
+        if (gamma[j] != V(0)) alpha[j] = rho[j] / gamma[j];
+    });
+    if (st != B200_OK) return st;
+    return launch_ew(ctx, rows, cols, [=] __device__(int64_t i, int64_t j) {
+        if (has_stopped(stop[j])) return;
+        const V uv = u[i * us + j];
+        const V qv = uv - alpha[j] * v_hat[i * vhs + j];
+        q[i * qs + j] = qv;
+        t[i * ts + j] = uv + qv;
+    });
+}
+
+template <typename V>
+b200_status cgs_step_3(b200_ctx* ctx, int64_t rows, int64_t cols, const V* t, int64_t ts,
+                       const V* u_hat, int64_t uhs, V* r, int64_t rs, V* x, int64_t xs,
+                       const V* alpha, const uint8_t* stop)
+{
+    return launch_ew(ctx, rows, cols, [=] __device__(int64_t i, int64_t j) {
+        if (has_stopped(stop[j])) return;
+        const V a = alpha[j];
+        x[i * xs + j] += a * u_hat[i * uhs + j];
+        r[i * rs + j] -= a * t[i * ts + j];
+    });
+}
+
 template <typename V>
 b200_status bicgstab_initialize(b200_ctx* ctx, int64_t rows, int64_t cols, const V* b, int64_t bs,
                                 V* r, int64_t rs, V* rr, int64_t rrs, V* y, int64_t ys, V* s,
@@ -203,6 +348,63 @@ extern "C" {
     {                                                                                          \
         return b200::steps::cg_step_2<VT>(ctx, rows, cols, x, xs, r, rs, p, ps, q, qs, beta, rho,     \
                                    stop);                                                      \
+    }                                                                                          \
+    b200_status b200_fcg_initialize_##V(                                                       \
+        b200_ctx* ctx, int64_t rows, int64_t cols, const VT* b, int64_t bs, VT* r, int64_t rs, \
+        VT* z, int64_t zs, VT* p, int64_t ps, VT* q, int64_t qs, VT* t, int64_t ts,            \
+        VT* prev_rho, VT* rho, VT* rho_t, uint8_t* stop)                                       \
+    {                                                                                          \
+        return b200::steps::fcg_initialize<VT>(ctx, rows, cols, b, bs, r, rs, z, zs, p, ps, q, \
+                                               qs, t, ts, prev_rho, rho, rho_t, stop);         \
+    }                                                                                          \
+    b200_status b200_fcg_step_1_##V(b200_ctx* ctx, int64_t rows, int64_t cols, VT* p,          \
+                                    int64_t ps, const VT* z, int64_t zs, const VT* rho_t,      \
+                                    const VT* prev_rho, const uint8_t* stop)                   \
+    {                                                                                          \
+        return b200::steps::fcg_step_1<VT>(ctx, rows, cols, p, ps, z, zs, rho_t, prev_rho,     \
+                                           stop);                                              \
+    }                                                                                          \
+    b200_status b200_fcg_step_2_##V(b200_ctx* ctx, int64_t rows, int64_t cols, VT* x,          \
+                                    int64_t xs, VT* r, int64_t rs, VT* t, int64_t ts,          \
+                                    const VT* p, int64_t ps, const VT* q, int64_t qs,          \
+                                    const VT* beta, const VT* rho, const uint8_t* stop)        \
+    {                                                                                          \
+        return b200::steps::fcg_step_2<VT>(ctx, rows, cols, x, xs, r, rs, t, ts, p, ps, q, qs, \
+                                           beta, rho, stop);                                   \
+    }                                                                                          \
+    b200_status b200_cgs_initialize_##V(                                                       \
+        b200_ctx* ctx, int64_t rows, int64_t cols, const VT* b, int64_t bs, VT* r, int64_t rs, \
+        VT* r_tld, int64_t rts, VT* p, int64_t ps, VT* q, int64_t qs, VT* u, int64_t us,       \
+        VT* u_hat, int64_t uhs, VT* v_hat, int64_t vhs, VT* t, int64_t ts, VT* alpha,          \
+        VT* beta, VT* gamma, VT* prev_rho, VT* rho, uint8_t* stop)                             \
+    {                                                                                          \
+        return b200::steps::cgs_initialize<VT>(ctx, rows, cols, b, bs, r, rs, r_tld, rts, p,   \
+                                               ps, q, qs, u, us, u_hat, uhs, v_hat, vhs, t,    \
+                                               ts, alpha, beta, gamma, prev_rho, rho, stop);   \
+    }                                                                                          \
+    b200_status b200_cgs_step_1_##V(b200_ctx* ctx, int64_t rows, int64_t cols, const VT* r,    \
+                                    int64_t rs, VT* u, int64_t us, VT* p, int64_t ps,          \
+                                    const VT* q, int64_t qs, VT* beta, const VT* rho,          \
+                                    const VT* prev_rho, const uint8_t* stop)                   \
+    {                                                                                          \
+        return b200::steps::cgs_step_1<VT>(ctx, rows, cols, r, rs, u, us, p, ps, q, qs, beta,  \
+                                           rho, prev_rho, stop);                               \
+    }                                                                                          \
+    b200_status b200_cgs_step_2_##V(b200_ctx* ctx, int64_t rows, int64_t cols, const VT* u,    \
+                                    int64_t us, const VT* v_hat, int64_t vhs, VT* q,           \
+                                    int64_t qs, VT* t, int64_t ts, VT* alpha, const VT* rho,   \
+                                    const VT* gamma, const uint8_t* stop)                      \
+    {                                                                                          \
+        return b200::steps::cgs_step_2<VT>(ctx, rows, cols, u, us, v_hat, vhs, q, qs, t, ts,   \
+                                           alpha, rho, gamma, stop);                           \
+    }                                                                                          \
+    b200_status b200_cgs_step_3_##V(b200_ctx* ctx, int64_t rows, int64_t cols, const VT* t,    \
+                                    int64_t ts, const VT* u_hat, int64_t uhs, VT* r,           \
+                                    int64_t rs, VT* x, int64_t xs, const VT* alpha,            \
+                                    const uint8_t* stop)                                       \
+    {                                                                                          \
+        return b200::steps::cgs_step_3<VT>(ctx, rows, cols, t, ts, u_hat, uhs, r, rs, x, xs,   \
+                                           alpha, stop);                                       \
     }                                                                                          \
     b200_status b200_bicgstab_initialize_##V(                                                  \
         b200_ctx* ctx, int64_t rows, int64_t cols, const VT* b, int64_t bs, VT* r, int64_t rs, \

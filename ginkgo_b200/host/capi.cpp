@@ -79,6 +79,18 @@ std::unique_ptr<LinOp> make_solver(std::shared_ptr<Executor> exec, int kind,
         if (pre) f.with_preconditioner(pre);
         return f.on(exec)->generate(A);
     }
+    if (kind == 3) {
+        auto f = solver::Fcg<V>::build();
+        f.with_criteria(crit);
+        if (pre) f.with_preconditioner(pre);
+        return f.on(exec)->generate(A);
+    }
+    if (kind == 4) {
+        auto f = solver::Cgs<V>::build();
+        f.with_criteria(crit);
+        if (pre) f.with_preconditioner(pre);
+        return f.on(exec)->generate(A);
+    }
     auto f = solver::Gmres<V>::build();
     f.with_criteria(crit).with_krylov_dim((size_type)krylov_dim);
     f.with_ortho_method(ortho == 0   ? solver::gmres::ortho_method::mgs

@@ -108,6 +108,13 @@ struct viabi;
         static constexpr auto cg_initialize = b200_cg_initialize_##S;                           \
         static constexpr auto cg_step_1 = b200_cg_step_1_##S;                                   \
         static constexpr auto cg_step_2 = b200_cg_step_2_##S;                                   \
+        static constexpr auto fcg_initialize = b200_fcg_initialize_##S;                         \
+        static constexpr auto fcg_step_1 = b200_fcg_step_1_##S;                                 \
+        static constexpr auto fcg_step_2 = b200_fcg_step_2_##S;                                 \
+        static constexpr auto cgs_initialize = b200_cgs_initialize_##S;                         \
+        static constexpr auto cgs_step_1 = b200_cgs_step_1_##S;                                 \
+        static constexpr auto cgs_step_2 = b200_cgs_step_2_##S;                                 \
+        static constexpr auto cgs_step_3 = b200_cgs_step_3_##S;                                 \
         static constexpr auto bicgstab_initialize = b200_bicgstab_initialize_##S;               \
         static constexpr auto bicgstab_step_1 = b200_bicgstab_step_1_##S;                       \
         static constexpr auto bicgstab_step_2 = b200_bicgstab_step_2_##S;                       \

@@ -730,6 +730,161 @@ private:
 // ---------------------------------------------------------------------------------------------
 // Bicgstab (core/solver/bicgstab.cpp:95-233)
 // ---------------------------------------------------------------------------------------------
+// solver::Fcg (core/solver/fcg.cpp:93-188): flexible CG, one more vector (t = r_new - r_old)
+// and one more dot per iteration than CG.  SURVEY.md 8f-3.
+// ---------------------------------------------------------------------------------------------
+#define GKOB_VS(d) (d)->get_values(), (d)->get_stride()
+#define GKOB_CVS(d) (d)->get_const_values(), (d)->get_stride()
+template <typename V>
+class Fcg : public SolverBase<V> {
+    using Base = SolverBase<V>;
+    using Dense = matrix::Dense<V>;
+
+public:
+    struct Factory : SolverFactoryBase<Factory> {
+        std::unique_ptr<LinOp> generate(std::shared_ptr<const LinOp> op) const override
+        {
+            auto exec = this->exec_ ? this->exec_ : op->get_executor();
+            return std::unique_ptr<LinOp>(new Fcg(exec, *this, op));
+        }
+    };
+    static Factory build() { return Factory{}; }
+
+protected:
+    Fcg(std::shared_ptr<const Executor> exec, const Factory& f, std::shared_ptr<const LinOp> op)
+        : Base(exec, f, op)
+    {}
+    using Base::apply_impl;
+    void apply_impl(const LinOp* lb, LinOp* lx) const override
+    {
+        auto b = as<Dense>(lb);
+        auto x = as<Dense>(lx);
+        auto exec = this->exec_;
+        auto ctx = exec->ctx();
+        const dim2 sz = b->get_size();
+        const size_type nrhs = sz.cols;
+        auto mk = [&] { return Dense::create(exec, sz); };
+        auto sc = [&] { return Dense::create(exec, dim2{1, nrhs}); };
+        auto r = mk(), z = mk(), p = mk(), q = mk(), t = mk();
+        auto beta = sc(), prev_rho = sc(), rho = sc(), rho_t = sc();
+        array<uint8> stop_status(exec, nrhs);
+        bool one_changed = false;
+        GKOB_CALL(vabi<V>::fcg_initialize(ctx, sz.rows, nrhs, GKOB_CVS(b), GKOB_VS(r), GKOB_VS(z),
+                                          GKOB_VS(p), GKOB_VS(q), GKOB_VS(t), prev_rho->get_values(),
+                                          rho->get_values(), rho_t->get_values(),
+                                          stop_status.get_data()));
+        this->system_matrix_->apply(this->neg_one_.get(), x, this->one_.get(), r.get());
+        stop::CriterionArgs args{this->system_matrix_, b, x, r.get()};
+        auto crit = stop::combine_and_generate(this->criteria_, exec, args);
+        int64 iter = -1;
+        while (true) {
+            this->preconditioner_->apply(r.get(), z.get());
+            r->compute_conj_dot(z.get(), rho.get());
+            t->compute_conj_dot(z.get(), rho_t.get());
+            ++iter;
+            stop::Updater u;
+            u.num_iterations = iter;
+            u.residual = r.get();
+            u.implicit_sq_residual_norm = rho.get();
+            u.solution = x;
+            if (crit->check(1, true, &stop_status, &one_changed, u)) break;
+            GKOB_CALL(vabi<V>::fcg_step_1(ctx, sz.rows, nrhs, GKOB_VS(p), GKOB_CVS(z),
+                                          rho_t->get_const_values(), prev_rho->get_const_values(),
+                                          stop_status.get_const_data()));
+            this->system_matrix_->apply(p.get(), q.get());
+            p->compute_conj_dot(q.get(), beta.get());
+            GKOB_CALL(vabi<V>::fcg_step_2(ctx, sz.rows, nrhs, GKOB_VS(x), GKOB_VS(r), GKOB_VS(t),
+                                          GKOB_CVS(p), GKOB_CVS(q), beta->get_const_values(),
+                                          rho->get_const_values(), stop_status.get_const_data()));
+            std::swap(prev_rho, rho);
+        }
+        this->record(iter, stop_status);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// solver::Cgs (core/solver/cgs.cpp:93-205): two SpMVs and two preconditioner applications per
+// iteration, no transpose.  SURVEY.md 8f-3.
+// ---------------------------------------------------------------------------------------------
+template <typename V>
+class Cgs : public SolverBase<V> {
+    using Base = SolverBase<V>;
+    using Dense = matrix::Dense<V>;
+
+public:
+    struct Factory : SolverFactoryBase<Factory> {
+        std::unique_ptr<LinOp> generate(std::shared_ptr<const LinOp> op) const override
+        {
+            auto exec = this->exec_ ? this->exec_ : op->get_executor();
+            return std::unique_ptr<LinOp>(new Cgs(exec, *this, op));
+        }
+    };
+    static Factory build() { return Factory{}; }
+
+protected:
+    Cgs(std::shared_ptr<const Executor> exec, const Factory& f, std::shared_ptr<const LinOp> op)
+        : Base(exec, f, op)
+    {}
+    using Base::apply_impl;
+    void apply_impl(const LinOp* lb, LinOp* lx) const override
+    {
+        auto b = as<Dense>(lb);
+        auto x = as<Dense>(lx);
+        auto exec = this->exec_;
+        auto ctx = exec->ctx();
+        const dim2 sz = b->get_size();
+        const size_type nrhs = sz.cols;
+        auto mk = [&] { return Dense::create(exec, sz); };
+        auto sc = [&] { return Dense::create(exec, dim2{1, nrhs}); };
+        auto r = mk(), r_tld = mk(), p = mk(), q = mk(), u = mk(), u_hat = mk(), v_hat = mk(),
+             t = mk();
+        auto alpha = sc(), beta = sc(), gamma = sc(), prev_rho = sc(), rho = sc();
+        array<uint8> stop_status(exec, nrhs);
+        bool one_changed = false;
+        GKOB_CALL(vabi<V>::cgs_initialize(
+            ctx, sz.rows, nrhs, GKOB_CVS(b), GKOB_VS(r), GKOB_VS(r_tld), GKOB_VS(p), GKOB_VS(q),
+            GKOB_VS(u), GKOB_VS(u_hat), GKOB_VS(v_hat), GKOB_VS(t), alpha->get_values(),
+            beta->get_values(), gamma->get_values(), prev_rho->get_values(), rho->get_values(),
+            stop_status.get_data()));
+        this->system_matrix_->apply(this->neg_one_.get(), x, this->one_.get(), r.get());
+        stop::CriterionArgs args{this->system_matrix_, b, x, r.get()};
+        auto crit = stop::combine_and_generate(this->criteria_, exec, args);
+        r_tld->copy_from(r.get());
+        int64 iter = -1;
+        while (true) {
+            r->compute_conj_dot(r_tld.get(), rho.get());
+            ++iter;
+            stop::Updater up;
+            up.num_iterations = iter;
+            up.residual = r.get();
+            up.implicit_sq_residual_norm = rho.get();
+            up.solution = x;
+            if (crit->check(1, true, &stop_status, &one_changed, up)) break;
+            GKOB_CALL(vabi<V>::cgs_step_1(ctx, sz.rows, nrhs, GKOB_CVS(r), GKOB_VS(u), GKOB_VS(p),
+                                          GKOB_CVS(q), beta->get_values(), rho->get_const_values(),
+                                          prev_rho->get_const_values(),
+                                          stop_status.get_const_data()));
+            this->preconditioner_->apply(p.get(), t.get());
+            this->system_matrix_->apply(t.get(), v_hat.get());
+            r_tld->compute_conj_dot(v_hat.get(), gamma.get());
+            GKOB_CALL(vabi<V>::cgs_step_2(ctx, sz.rows, nrhs, GKOB_CVS(u), GKOB_CVS(v_hat),
+                                          GKOB_VS(q), GKOB_VS(t), alpha->get_values(),
+                                          rho->get_const_values(), gamma->get_const_values(),
+                                          stop_status.get_const_data()));
+            this->preconditioner_->apply(t.get(), u_hat.get());
+            this->system_matrix_->apply(u_hat.get(), t.get());
+            GKOB_CALL(vabi<V>::cgs_step_3(ctx, sz.rows, nrhs, GKOB_CVS(t), GKOB_CVS(u_hat),
+                                          GKOB_VS(r), GKOB_VS(x), alpha->get_const_values(),
+                                          stop_status.get_const_data()));
+            std::swap(prev_rho, rho);
+        }
+        this->record(iter, stop_status);
+    }
+};
+#undef GKOB_VS
+#undef GKOB_CVS
+
+// ---------------------------------------------------------------------------------------------
 template <typename V>
 class Bicgstab : public SolverBase<V> {
     using Base = SolverBase<V>;

@@ -310,6 +310,43 @@ b200_status b200_jacobi_find_blocks_i64(b200_ctx* ctx, int64_t num_rows, const i
                                    const VT* beta, const VT* rho,                             \
                                    const uint8_t* stop_status);                               \
                                                                                               \
+    /* FCG (core/solver/fcg_kernels.hpp; reference/solver/fcg_kernels.cpp:22-100) and CGS    \
+     * (core/solver/cgs_kernels.hpp; reference/solver/cgs_kernels.cpp:22-140), SURVEY 8f-3 */ \
+    b200_status b200_fcg_initialize_##V(                                                      \
+        b200_ctx* ctx, int64_t rows, int64_t cols, const VT* b, int64_t b_stride, VT* r,      \
+        int64_t r_stride, VT* z, int64_t z_stride, VT* p, int64_t p_stride, VT* q,            \
+        int64_t q_stride, VT* t, int64_t t_stride, VT* prev_rho, VT* rho, VT* rho_t,          \
+        uint8_t* stop_status);                                                                \
+    b200_status b200_fcg_step_1_##V(b200_ctx* ctx, int64_t rows, int64_t cols, VT* p,         \
+                                    int64_t p_stride, const VT* z, int64_t z_stride,          \
+                                    const VT* rho_t, const VT* prev_rho,                      \
+                                    const uint8_t* stop_status);                              \
+    b200_status b200_fcg_step_2_##V(b200_ctx* ctx, int64_t rows, int64_t cols, VT* x,         \
+                                    int64_t x_stride, VT* r, int64_t r_stride, VT* t,         \
+                                    int64_t t_stride, const VT* p, int64_t p_stride,          \
+                                    const VT* q, int64_t q_stride, const VT* beta,            \
+                                    const VT* rho, const uint8_t* stop_status);               \
+    b200_status b200_cgs_initialize_##V(                                                      \
+        b200_ctx* ctx, int64_t rows, int64_t cols, const VT* b, int64_t b_stride, VT* r,      \
+        int64_t r_stride, VT* r_tld, int64_t r_tld_stride, VT* p, int64_t p_stride, VT* q,    \
+        int64_t q_stride, VT* u, int64_t u_stride, VT* u_hat, int64_t u_hat_stride,           \
+        VT* v_hat, int64_t v_hat_stride, VT* t, int64_t t_stride, VT* alpha, VT* beta,        \
+        VT* gamma, VT* prev_rho, VT* rho, uint8_t* stop_status);                              \
+    b200_status b200_cgs_step_1_##V(b200_ctx* ctx, int64_t rows, int64_t cols, const VT* r,   \
+                                    int64_t r_stride, VT* u, int64_t u_stride, VT* p,         \
+                                    int64_t p_stride, const VT* q, int64_t q_stride,          \
+                                    VT* beta, const VT* rho, const VT* prev_rho,              \
+                                    const uint8_t* stop_status);                              \
+    b200_status b200_cgs_step_2_##V(b200_ctx* ctx, int64_t rows, int64_t cols, const VT* u,   \
+                                    int64_t u_stride, const VT* v_hat, int64_t v_hat_stride,  \
+                                    VT* q, int64_t q_stride, VT* t, int64_t t_stride,         \
+                                    VT* alpha, const VT* rho, const VT* gamma,                \
+                                    const uint8_t* stop_status);                              \
+    b200_status b200_cgs_step_3_##V(b200_ctx* ctx, int64_t rows, int64_t cols, const VT* t,   \
+                                    int64_t t_stride, const VT* u_hat, int64_t u_hat_stride,  \
+                                    VT* r, int64_t r_stride, VT* x, int64_t x_stride,         \
+                                    const VT* alpha, const uint8_t* stop_status);             \
+                                                                                              \
     b200_status b200_bicgstab_initialize_##V(                                                 \
         b200_ctx* ctx, int64_t rows, int64_t cols, const VT* b, int64_t b_stride, VT* r,      \
         int64_t r_stride, VT* rr, int64_t rr_stride, VT* y, int64_t y_stride, VT* s,          \

@@ -174,6 +174,114 @@ void FN(cg_step_2)(int64_t rows, int64_t cols, V* x, int64_t xs, V* r, int64_t r
         }
 }
 
+/* reference/solver/fcg_kernels.cpp:22-100 */
+void FN(fcg_initialize)(int64_t rows, int64_t cols, const V* b, int64_t bs, V* r, int64_t rs, V* z,
+                        int64_t zs, V* p, int64_t ps, V* q, int64_t qs, V* t, int64_t ts,
+                        V* prev_rho, V* rho, V* rho_t, uint8_t* stop)
+{
+    for (int64_t j = 0; j < cols; ++j) {
+        rho[j] = 0;
+        prev_rho[j] = 1;
+        rho_t[j] = 1;
+        stop[j] = 0;
+    }
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) {
+            t[i * ts + j] = r[i * rs + j] = b[i * bs + j];
+            z[i * zs + j] = p[i * ps + j] = q[i * qs + j] = 0;
+        }
+}
+void FN(fcg_step_1)(int64_t rows, int64_t cols, V* p, int64_t ps, const V* z, int64_t zs,
+                    const V* rho_t, const V* prev_rho, const uint8_t* stop)
+{
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) {
+            if (st_has_stopped(stop[j])) continue;
+            if (prev_rho[j] == 0) {
+                p[i * ps + j] = z[i * zs + j];
+            } else {
+                V tmp = rho_t[j] / prev_rho[j];
+                p[i * ps + j] = z[i * zs + j] + tmp * p[i * ps + j];
+            }
+        }
+}
+void FN(fcg_step_2)(int64_t rows, int64_t cols, V* x, int64_t xs, V* r, int64_t rs, V* t,
+                    int64_t ts, const V* p, int64_t ps, const V* q, int64_t qs, const V* beta,
+                    const V* rho, const uint8_t* stop)
+{
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) {
+            if (st_has_stopped(stop[j])) continue;
+            if (beta[j] != 0) {
+                V tmp = rho[j] / beta[j];
+                V prev_r = r[i * rs + j];
+                x[i * xs + j] += tmp * p[i * ps + j];
+                r[i * rs + j] -= tmp * q[i * qs + j];
+                t[i * ts + j] = r[i * rs + j] - prev_r;
+            }
+        }
+}
+
+/* reference/solver/cgs_kernels.cpp:22-140 */
+void FN(cgs_initialize)(int64_t rows, int64_t cols, const V* b, int64_t bs, V* r, int64_t rs,
+                        V* r_tld, int64_t rts, V* p, int64_t ps, V* q, int64_t qs, V* u,
+                        int64_t us, V* u_hat, int64_t uhs, V* v_hat, int64_t vhs, V* t, int64_t ts,
+                        V* alpha, V* beta, V* gamma, V* prev_rho, V* rho, uint8_t* stop)
+{
+    for (int64_t j = 0; j < cols; ++j) {
+        rho[j] = 0;
+        prev_rho[j] = alpha[j] = beta[j] = gamma[j] = 1;
+        stop[j] = 0;
+    }
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) {
+            r[i * rs + j] = b[i * bs + j];
+            r_tld[i * rts + j] = b[i * bs + j];
+            u[i * us + j] = u_hat[i * uhs + j] = p[i * ps + j] = q[i * qs + j] =
+                v_hat[i * vhs + j] = t[i * ts + j] = 0;
+        }
+}
+void FN(cgs_step_1)(int64_t rows, int64_t cols, const V* r, int64_t rs, V* u, int64_t us, V* p,
+                    int64_t ps, const V* q, int64_t qs, V* beta, const V* rho, const V* prev_rho,
+                    const uint8_t* stop)
+{
+    for (int64_t j = 0; j < cols; ++j) {
+        if (st_has_stopped(stop[j])) continue;
+        if (prev_rho[j] != 0) beta[j] = rho[j] / prev_rho[j];
+    }
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) {
+            if (st_has_stopped(stop[j])) continue;
+            u[i * us + j] = r[i * rs + j] + beta[j] * q[i * qs + j];
+            p[i * ps + j] = u[i * us + j] + beta[j] * (q[i * qs + j] + beta[j] * p[i * ps + j]);
+        }
+}
+void FN(cgs_step_2)(int64_t rows, int64_t cols, const V* u, int64_t us, const V* v_hat, int64_t vhs,
+                    V* q, int64_t qs, V* t, int64_t ts, V* alpha, const V* rho, const V* gamma,
+                    const uint8_t* stop)
+{
+    for (int64_t j = 0; j < cols; ++j) {
+        if (st_has_stopped(stop[j])) continue;
+        if (gamma[j] != 0) alpha[j] = rho[j] / gamma[j];
+    }
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) {
+            if (st_has_stopped(stop[j])) continue;
+            q[i * qs + j] = u[i * us + j] - alpha[j] * v_hat[i * vhs + j];
+            t[i * ts + j] = u[i * us + j] + q[i * qs + j];
+        }
+}
+void FN(cgs_step_3)(int64_t rows, int64_t cols, const V* t, int64_t ts, const V* u_hat, int64_t uhs,
+                    V* r, int64_t rs, V* x, int64_t xs, const V* alpha, const uint8_t* stop)
+{
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) {
+            if (st_has_stopped(stop[j])) continue;
+            x[i * xs + j] += alpha[j] * u_hat[i * uhs + j];
+            r[i * rs + j] -= alpha[j] * t[i * ts + j];
+        }
+}
+
 /* reference/solver/bicgstab_kernels.cpp:25-60 */
 void FN(bicgstab_initialize)(int64_t rows, int64_t cols, const V* b, int64_t bs, V* r, int64_t rs,
                              V* rr, int64_t rrs, V* y, int64_t ys, V* s, int64_t ss, V* t,

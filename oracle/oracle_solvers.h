@@ -158,6 +158,93 @@ int64_t FN(cg_solve)(int64_t n, int64_t cols, const int32_t* rp, const int32_t* 
     return iter;
 }
 
+/* core/solver/fcg.cpp:93-188 */
+int64_t FN(fcg_solve)(int64_t n, int64_t cols, const int32_t* rp, const int32_t* ci, const V* va,
+                      const V* b, V* x, const orc_solver_cfg* cfg, uint8_t* stop_out,
+                      V* resnorm_out)
+{
+    FN(sctx) s = {n, cols, rp, ci, va, cfg, NULL, NULL};
+    const size_t nb = sizeof(V) * n * cols;
+    V *r = malloc(nb), *z = malloc(nb), *p = malloc(nb), *q = malloc(nb), *t = malloc(nb);
+    V *beta = malloc(sizeof(V) * cols), *prev_rho = malloc(sizeof(V) * cols),
+      *rho = malloc(sizeof(V) * cols), *rho_t = malloc(sizeof(V) * cols);
+    s.starting_tau = malloc(sizeof(V) * cols);
+    s.u_tau = malloc(sizeof(V) * cols);
+    uint8_t* stop = malloc(cols);
+    const V one = 1, neg_one = -1;
+    FN(fcg_initialize)(n, cols, b, cols, r, cols, z, cols, p, cols, q, cols, t, cols, prev_rho, rho,
+                       rho_t, stop);
+    FN(s_apply_A)(&s, &neg_one, x, &one, r);
+    FN(s_criterion_generate)(&s, b, r);
+    int64_t iter = -1;
+    int one_changed;
+    while (1) {
+        FN(s_apply_M)(&s, r, z);
+        FN(dense_compute_dot)(n, cols, r, cols, z, cols, rho);
+        FN(dense_compute_dot)(n, cols, t, cols, z, cols, rho_t);
+        ++iter;
+        if (FN(s_check)(&s, iter, r, NULL, rho, 1, stop, &one_changed)) break;
+        FN(fcg_step_1)(n, cols, p, cols, z, cols, rho_t, prev_rho, stop);
+        FN(s_apply_A)(&s, NULL, p, NULL, q);
+        FN(dense_compute_dot)(n, cols, p, cols, q, cols, beta);
+        FN(fcg_step_2)(n, cols, x, cols, r, cols, t, cols, p, cols, q, cols, beta, rho, stop);
+        V* sw = prev_rho;
+        prev_rho = rho;
+        rho = sw;
+    }
+    if (stop_out) memcpy(stop_out, stop, cols);
+    if (resnorm_out) FN(dense_compute_norm2)(n, cols, r, cols, resnorm_out);
+    free(r); free(z); free(p); free(q); free(t); free(beta); free(prev_rho); free(rho); free(rho_t);
+    free(s.starting_tau); free(s.u_tau); free(stop);
+    return iter;
+}
+
+/* core/solver/cgs.cpp:93-205 */
+int64_t FN(cgs_solve)(int64_t n, int64_t cols, const int32_t* rp, const int32_t* ci, const V* va,
+                      const V* b, V* x, const orc_solver_cfg* cfg, uint8_t* stop_out,
+                      V* resnorm_out)
+{
+    FN(sctx) s = {n, cols, rp, ci, va, cfg, NULL, NULL};
+    const size_t nb = sizeof(V) * n * cols;
+    V *r = malloc(nb), *r_tld = malloc(nb), *p = malloc(nb), *q = malloc(nb), *u = malloc(nb),
+      *u_hat = malloc(nb), *v_hat = malloc(nb), *t = malloc(nb);
+    V* sc = malloc(sizeof(V) * cols * 5);
+    V *alpha = sc, *beta = sc + cols, *gamma = sc + 2 * cols, *prev_rho = sc + 3 * cols,
+      *rho = sc + 4 * cols;
+    s.starting_tau = malloc(sizeof(V) * cols);
+    s.u_tau = malloc(sizeof(V) * cols);
+    uint8_t* stop = malloc(cols);
+    const V one = 1, neg_one = -1;
+    FN(cgs_initialize)(n, cols, b, cols, r, cols, r_tld, cols, p, cols, q, cols, u, cols, u_hat,
+                       cols, v_hat, cols, t, cols, alpha, beta, gamma, prev_rho, rho, stop);
+    FN(s_apply_A)(&s, &neg_one, x, &one, r);
+    FN(s_criterion_generate)(&s, b, r);
+    memcpy(r_tld, r, nb);
+    int64_t iter = -1;
+    int one_changed;
+    while (1) {
+        FN(dense_compute_dot)(n, cols, r, cols, r_tld, cols, rho);
+        ++iter;
+        if (FN(s_check)(&s, iter, r, NULL, rho, 1, stop, &one_changed)) break;
+        FN(cgs_step_1)(n, cols, r, cols, u, cols, p, cols, q, cols, beta, rho, prev_rho, stop);
+        FN(s_apply_M)(&s, p, t);
+        FN(s_apply_A)(&s, NULL, t, NULL, v_hat);
+        FN(dense_compute_dot)(n, cols, r_tld, cols, v_hat, cols, gamma);
+        FN(cgs_step_2)(n, cols, u, cols, v_hat, cols, q, cols, t, cols, alpha, rho, gamma, stop);
+        FN(s_apply_M)(&s, t, u_hat);
+        FN(s_apply_A)(&s, NULL, u_hat, NULL, t);
+        FN(cgs_step_3)(n, cols, t, cols, u_hat, cols, r, cols, x, cols, alpha, stop);
+        V* sw = prev_rho;
+        prev_rho = rho;
+        rho = sw;
+    }
+    if (stop_out) memcpy(stop_out, stop, cols);
+    if (resnorm_out) FN(dense_compute_norm2)(n, cols, r, cols, resnorm_out);
+    free(r); free(r_tld); free(p); free(q); free(u); free(u_hat); free(v_hat); free(t); free(sc);
+    free(s.starting_tau); free(s.u_tau); free(stop);
+    return iter;
+}
+
 /* core/solver/bicgstab.cpp:95-233 */
 int64_t FN(bicgstab_solve)(int64_t n, int64_t cols, const int32_t* rp, const int32_t* ci,
                            const V* va, const V* b, V* x, const orc_solver_cfg* cfg,

@@ -694,3 +694,72 @@ def test_find_blocks_bit_exact(orc, cuda, it, max_bs, n, max_run):
     assert no.value == nc.value
     assert np.array_equal(bo[:no.value + 1], bc[:nc.value + 1])
     assert bc[nc.value] == n and np.all(np.diff(bc[:nc.value + 1]) <= max_bs)
+
+
+# ------------------------------------------------------- sibling Krylov kernels (8f-3)
+def _all_equal(a, b):
+    for i in range(len(a)):
+        if isinstance(a[i], np.ndarray):
+            assert np.array_equal(a[i], b[i]), i
+
+
+@pytest.mark.parametrize("vt", VTS)
+@pytest.mark.parametrize("rows,cols", [(597, 43), (100001, 1), (0, 2)])
+def test_fcg_steps(orc, cuda, vt, rows, cols):
+    rng = np.random.default_rng(90)
+    st = dict(b=cols + 1, r=cols + 2, z=cols + 3, p=cols + 2, q=cols + 1, t=cols + 4, x=cols)
+    v = {k: H.dense(rng, rows, cols, s, vt) for k, s in st.items()}
+    sc = {k: rng.uniform(0.5, 1, cols).astype(VT[vt]) for k in ("rho", "prev_rho", "rho_t", "beta")}
+    stop = np.zeros(cols, dtype=np.uint8)
+    if cols > 3:
+        sc["prev_rho"][2] = 0
+        sc["beta"][3] = 0
+        stop[1] = 1 | 0x40
+    a, b = both(orc, cuda, "fcg_initialize_" + vt,
+                lambda: [rows, cols, v["b"], st["b"], v["r"].copy(), st["r"], v["z"].copy(), st["z"],
+                         v["p"].copy(), st["p"], v["q"].copy(), st["q"], v["t"].copy(), st["t"],
+                         sc["prev_rho"].copy(), sc["rho"].copy(), sc["rho_t"].copy(),
+                         np.full(cols, 0x81, np.uint8)])
+    _all_equal(a, b)
+    a, b = both(orc, cuda, "fcg_step_1_" + vt,
+                lambda: [rows, cols, v["p"].copy(), st["p"], v["z"], st["z"], sc["rho_t"],
+                         sc["prev_rho"], stop])
+    _all_equal(a, b)
+    a, b = both(orc, cuda, "fcg_step_2_" + vt,
+                lambda: [rows, cols, v["x"].copy(), st["x"], v["r"].copy(), st["r"], v["t"].copy(),
+                         st["t"], v["p"], st["p"], v["q"], st["q"], sc["beta"], sc["rho"], stop])
+    _all_equal(a, b)
+
+
+@pytest.mark.parametrize("vt", VTS)
+@pytest.mark.parametrize("rows,cols", [(597, 43), (100001, 1), (0, 2)])
+def test_cgs_steps(orc, cuda, vt, rows, cols):
+    rng = np.random.default_rng(91)
+    names = ("b", "r", "r_tld", "p", "q", "u", "u_hat", "v_hat", "t", "x")
+    st = {k: cols + (i % 4) for i, k in enumerate(names)}
+    v = {k: H.dense(rng, rows, cols, s, vt) for k, s in st.items()}
+    sc = {k: rng.uniform(0.5, 1, cols).astype(VT[vt])
+          for k in ("alpha", "beta", "gamma", "prev_rho", "rho")}
+    stop = np.zeros(cols, dtype=np.uint8)
+    if cols > 3:
+        sc["prev_rho"][2] = 0
+        sc["gamma"][3] = 0
+        stop[1] = 1 | 0x40
+    a, b = both(orc, cuda, "cgs_initialize_" + vt,
+                lambda: [rows, cols, v["b"], st["b"]] + sum(
+                    [[v[k].copy(), st[k]] for k in ("r", "r_tld", "p", "q", "u", "u_hat", "v_hat", "t")],
+                    []) + [sc[k].copy() for k in ("alpha", "beta", "gamma", "prev_rho", "rho")] +
+                [np.full(cols, 0x81, np.uint8)])
+    _all_equal(a, b)
+    a, b = both(orc, cuda, "cgs_step_1_" + vt,
+                lambda: [rows, cols, v["r"], st["r"], v["u"].copy(), st["u"], v["p"].copy(), st["p"],
+                         v["q"], st["q"], sc["beta"].copy(), sc["rho"], sc["prev_rho"], stop])
+    _all_equal(a, b)
+    a, b = both(orc, cuda, "cgs_step_2_" + vt,
+                lambda: [rows, cols, v["u"], st["u"], v["v_hat"], st["v_hat"], v["q"].copy(), st["q"],
+                         v["t"].copy(), st["t"], sc["alpha"].copy(), sc["rho"], sc["gamma"], stop])
+    _all_equal(a, b)
+    a, b = both(orc, cuda, "cgs_step_3_" + vt,
+                lambda: [rows, cols, v["t"], st["t"], v["u_hat"], st["u_hat"], v["r"].copy(), st["r"],
+                         v["x"].copy(), st["x"], sc["alpha"], stop])
+    _all_equal(a, b)
