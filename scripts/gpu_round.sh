@@ -14,7 +14,8 @@ echo "== ncu launches (bench, no cpu leg, small cg)"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'warp_stream|warp_pipe|slab|step_|plan_kernel|ew_kernel|reduce_c|init_scalars|extract_diag|multi_|hessenberg|solve_krylov|block_apply|residual_norm|pack_kernel' -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 20 --warmup 3 --no-cpu --small-cg > gpurun_out/ncu_bench.log 2>&1
 tail -2 gpurun_out/ncu_bench.log | cut -c1-300
 echo "== ncu full: spmv cfg2"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'warp_stream|warp_pipe' -s 14 -c 1 -f -o gpurun_out/prof_spmv_cfg2 python bench.py --steps 10 --warmup 3 --no-cpu --no-cg > gpurun_out/ncu_full1.log 2>&1; tail -1 gpurun_out/ncu_full1.log | cut -c1-200
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'warp_stream|warp_pipe' -s 22 -c 2 -f -o gpurun_out/prof_spmv_cfg2 python bench.py --steps 10 --warmup 3 --no-cpu --no-cg > gpurun_out/ncu_full1.log 2>&1; tail -1 gpurun_out/ncu_full1.log | cut -c1-200
 echo "== ncu full: CG kernels (cfg3)"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'warp_stream|warp_pipe|step_xr|step_p' -s 338 -c 3 -f -o gpurun_out/prof_cg_cfg3 python scripts/cg_probe.py > gpurun_out/ncu_full2.log 2>&1; tail -2 gpurun_out/ncu_full2.log | cut -c1-200
-ls -la gpurun_out | tail -20
+echo "== exp kernels"; timeout 300 python scripts/exp_kernels.py > gpurun_out/exp_kernels.log 2>&1; tail -3 gpurun_out/exp_kernels.log | cut -c1-200
+ls -la gpurun_out | tail -24
