@@ -12,8 +12,8 @@
 // i.e. finite-state machines.  They are evaluated in parallel the classic way: per chunk of
 // items and per possible entry state (one thread each) the exit state; a serial composition
 // over the (few thousand) chunks; then every chunk replays from its true entry state and
-// marks the block starts.  The reference's own CUDA backend runs these two loops in
-// single-thread kernels (common/cuda_hip/preconditioner/jacobi_kernels.cpp).
+// marks the block starts.  The reference's own CUDA backend runs these two loops as
+// <<<1, 1>>> kernels (common/cuda_hip/preconditioner/jacobi_kernels.cpp:246, :261).
 #include "scan.cuh"
 
 namespace b200 {
