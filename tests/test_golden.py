@@ -5,7 +5,7 @@ C ABI.  Citations are relative to /root/reference."""
 import numpy as np
 import pytest
 
-from tests.helpers import IT, R, VT, OutInt, rel_err
+from tests.helpers import IT, R, VT, OutI64, OutInt, rel_err
 
 BACKENDS = ["oracle", pytest.param("cuda", marks=pytest.mark.gpu)]
 VTS = ["f64", "f32"]
@@ -335,3 +335,124 @@ class TestJacobi:
         x = arr([1, -1, 2, -2, 3], vt)
         be("jacobi_scalar_apply_" + vt, 5, 1, inv, arr([2], vt), b, 1, arr([-1], vt), x, 1)
         assert x.tolist() == [1.0, 0.5, -3.0, 4.0, -3.5]
+
+
+    # ---- set-up kernels -------------------------------------------------------
+    def _fixture(self, vt, it):
+        # reference/test/preconditioner/jacobi_kernels.cpp:58-71: the 5x5 test matrix
+        rp = np.array([0, 3, 5, 7, 10, 13], dtype=IT[it])
+        ci = np.array([0, 1, 4, 0, 1, 2, 3, 2, 3, 4, 0, 3, 4], dtype=IT[it])
+        va = arr([4, -2, -2, -1, 4, 4, -2, -1, 4, -2, -1, -1, 4], vt)
+        return rp, ci, va
+
+    def test_generate_inverts_diagonal_blocks(self, be, vt, it):
+        # reference/test/preconditioner/jacobi_kernels.cpp:244-268 (InvertsDiagonalBlocks)
+        bo, go, gp, expect = self._blocks(vt)
+        rp, ci, va = self._fixture(vt, it)
+        ptrs = np.array([0, 2, 5], dtype=IT[it])
+        blocks = np.zeros_like(expect)
+        be("jacobi_generate_%s_%s" % (vt, it), 5, rp, ci, va, 2, 3, bo, go, gp, ptrs, blocks)
+        assert rel_err(blocks, expect) <= R[vt]
+
+    def test_generate_pivots(self, be, vt, it):
+        # reference/test/preconditioner/jacobi_kernels.cpp:452-490 (PivotsWhenInvertingBlocks)
+        rp = np.array([0, 3, 6, 9], dtype=IT[it])
+        ci = np.array([0, 1, 2, 0, 1, 2, 0, 1, 2], dtype=IT[it])
+        va = arr([0, 2, 0, 0, 0, 4, 1, 0, 0], vt)
+        bo, gp = 3, 3
+        stride = bo << gp
+        blocks = np.zeros(3 * stride, VT[vt])
+        be("jacobi_generate_%s_%s" % (vt, it), 3, rp, ci, va, 1, 3, bo, 3 * stride, gp,
+           np.array([0, 3], dtype=IT[it]), blocks)
+        inv = np.array([[blocks[r + c * stride] for c in range(3)] for r in range(3)])
+        assert rel_err(inv, np.array([[0, 0, 4], [2, 0, 0], [0, 1, 0]]) / 4.0) <= R[vt]
+
+    @pytest.mark.parametrize("case", ["natural", "agglomeration", "size_bound", "fixture"])
+    def test_find_blocks(self, be, vt, it, case):
+        # reference/test/preconditioner/jacobi_kernels.cpp:129-241 (FindsNaturalBlocks,
+        # ExecutesSupervariableAgglomeration, AdheresToBlockSizeBound,
+        # CanBeGeneratedWithUnknownBlockSizes), all with max_block_size 3
+        if vt == "f32":
+            pytest.skip("index-only kernel")
+        if case == "natural":
+            rp, ci, expect = [0, 2, 4, 6, 8], [0, 1, 0, 1, 0, 2, 0, 2], [0, 2, 4]
+        elif case == "agglomeration":
+            rp, ci, expect = [0, 2, 4, 6, 8, 9], [0, 1, 0, 1, 2, 3, 2, 3, 4], [0, 2, 5]
+        elif case == "size_bound":
+            rp, ci, expect = list(range(8)), list(range(7)), [0, 3, 6, 7]
+        else:
+            rp, ci, _ = self._fixture(vt, it)
+            rp, ci, expect = rp.tolist(), ci.tolist(), [0, 3, 5]
+        n = len(rp) - 1
+        ptrs = np.full(n + 1, -1, dtype=IT[it])
+        nb = OutI64()
+        be("jacobi_find_blocks_" + it, n, np.array(rp, dtype=IT[it]), np.array(ci, dtype=IT[it]), 3,
+           ptrs, nb)
+        assert nb.value == len(expect) - 1
+        assert ptrs[:len(expect)].tolist() == expect
+
+
+@pytest.mark.parametrize("vt", VTS)
+@pytest.mark.parametrize("it", ITS)
+class TestConversions:
+    """reference/test/matrix/csr_kernels.cpp: ConvertsToEll (:1585), ConvertsToSellp (:1251),
+    ConvertsToHybridAutomatically (:1301), ConvertsToHybridByColumn2 (:1326), SortUnsortedMatrix
+    (:2335) with the expectations of assert_equal_to_mtx (:190-332)."""
+
+    def test_converts_to_ell(self, be, vt, it):
+        rp, ci, va = csr_fix(vt, it)
+        mx = OutI64()
+        be("ell_compute_max_row_nnz_" + it, rp, 2, mx)
+        assert mx.value == 3
+        cols, vals = np.full(6, 9, IT[it]), np.full(6, 9, VT[vt])
+        be("csr_convert_to_ell_%s_%s" % (vt, it), 2, rp, ci, va, 3, 2, cols, vals)
+        assert cols.tolist() == [0, 1, 1, -1, 2, -1]
+        assert vals.tolist() == [1.0, 5.0, 3.0, 0.0, 2.0, 0.0]
+
+    def test_converts_to_sellp(self, be, vt, it):
+        rp, ci, va = csr_fix(vt, it)
+        ss, sl = np.full(2, 9, np.uint64), np.full(1, 9, np.uint64)
+        be("sellp_compute_slice_sets_" + it, rp, 2, 64, 1, ss, sl)
+        assert ss.tolist() == [0, 3] and sl.tolist() == [3]
+        cols, vals = np.full(192, 9, IT[it]), np.full(192, 9, VT[vt])
+        be("csr_convert_to_sellp_%s_%s" % (vt, it), 2, 64, ss, sl, rp, ci, va, cols, vals)
+        assert [cols[i] for i in (0, 1, 64, 65, 128, 129)] == [0, 1, 1, -1, 2, -1]
+        assert [vals[i] for i in (0, 1, 64, 65, 128, 129)] == [1.0, 5.0, 3.0, 0.0, 2.0, 0.0]
+
+    def test_converts_to_hybrid_automatically(self, be, vt, it):
+        # automatic = imbalance_bounded_limit(1/3, 0.001): min(sorted_nnz[0], 2 * 0.001) = 0
+        rp, ci, va = csr_fix(vt, it)
+        k = OutI64()
+        be("csr_row_nnz_order_statistic_" + it, rp, 2, int(2 * (1.0 / 3.0)), k)
+        ell_lim = min(k.value, int(2 * 0.001))
+        assert ell_lim == 0
+        crp = np.full(3, -1, np.int64)
+        be("csr_compute_hybrid_coo_row_ptrs_" + it, rp, 2, ell_lim, crp)
+        assert crp.tolist() == [0, 3, 4]
+        ec, ev = np.zeros(1, IT[it]), np.zeros(1, VT[vt])
+        cr, cc, cv = np.full(4, 9, IT[it]), np.full(4, 9, IT[it]), np.full(4, 9, VT[vt])
+        be("csr_convert_to_hybrid_%s_%s" % (vt, it), 2, rp, ci, va, 0, 2, ec, ev, crp, cr, cc, cv)
+        assert (cr.tolist(), cc.tolist(), cv.tolist()) == ([0, 0, 0, 1], [0, 1, 2, 1],
+                                                           [1.0, 3.0, 2.0, 5.0])
+
+    def test_converts_to_hybrid_by_column_2(self, be, vt, it):
+        # mtx2 keeps an explicit zero: [[1,3,2],[{0},5,0]]
+        rp = np.array([0, 3, 5], dtype=IT[it])
+        ci = np.array([0, 1, 2, 0, 1], dtype=IT[it])
+        va = arr([1, 3, 2, 0, 5], vt)
+        crp = np.full(3, -1, np.int64)
+        be("csr_compute_hybrid_coo_row_ptrs_" + it, rp, 2, 2, crp)
+        assert crp.tolist() == [0, 1, 1]
+        ec, ev = np.full(4, 9, IT[it]), np.full(4, 9, VT[vt])
+        cr, cc, cv = np.full(1, 9, IT[it]), np.full(1, 9, IT[it]), np.full(1, 9, VT[vt])
+        be("csr_convert_to_hybrid_%s_%s" % (vt, it), 2, rp, ci, va, 2, 2, ec, ev, crp, cr, cc, cv)
+        assert (cr.tolist(), cc.tolist(), cv.tolist()) == ([0], [2], [2.0])
+        assert ev.tolist() == [1.0, 0.0, 3.0, 5.0] and ec.tolist() == [0, 0, 1, 1]
+
+    def test_sort_unsorted_matrix(self, be, vt, it):
+        rp = np.array([0, 2, 5, 7], dtype=IT[it])
+        cols = np.array([2, 1, 1, 2, 0, 2, 0], dtype=IT[it])
+        vals = arr([1, 2, 1, 8, 3, 3, 2], vt)
+        be("csr_sort_by_column_index_%s_%s" % (vt, it), 3, rp, cols, vals)
+        assert cols.tolist() == [1, 2, 0, 1, 2, 0, 2]
+        assert vals.tolist() == [2.0, 1.0, 3.0, 1.0, 8.0, 2.0, 3.0]
