@@ -223,6 +223,11 @@ def _host():
         h.gkob_staged_join.restype, h.gkob_staged_join.argtypes = i, [vp]
         h.gkob_staged_wait.restype, h.gkob_staged_wait.argtypes = i, [vp]
         h.gkob_staged_destroy.argtypes = [vp]
+        h.gkob_csr_read_f64_i32.restype, h.gkob_csr_read_f64_i32.argtypes = vp, [vp, ctypes.c_char_p]
+        h.gkob_csr_write_f64_i32.restype = i
+        h.gkob_csr_write_f64_i32.argtypes = [vp, ctypes.c_char_p, i]
+        h.gkob_num_rows.restype, h.gkob_num_rows.argtypes = ll, [vp]
+        h.gkob_num_cols.restype, h.gkob_num_cols.argtypes = ll, [vp]
         h.gkob_csr_convert.restype = vp
         h.gkob_csr_convert.argtypes = [vp, ctypes.c_char_p, ll, ll, d, d]
         h.gkob_csr_sort_by_column_index.restype = i
@@ -340,6 +345,20 @@ class StagedApply:
             _host().gkob_staged_destroy(self.h)
         except Exception:
             pass
+
+
+def host_read_csr(exec_, path):
+    """gko::read_generic<Csr<double,int32>>: MatrixMarket or Ginkgo-binary file -> device Csr"""
+    o = _HostObj(exec_, _host().gkob_csr_read_f64_i32(exec_.h, str(path).encode()))
+    o.vt = "f64"
+    o.size = (_host().gkob_num_rows(o.h), _host().gkob_num_cols(o.h))
+    return o
+
+
+def host_write_csr(A, path, layout="coordinate"):
+    """gko::write / gko::write_binary of a device Csr<double,int32>"""
+    _hcheck(_host().gkob_csr_write_f64_i32(A.h, str(path).encode(),
+                                           {"coordinate": 0, "array": 1, "binary": 2}[layout]))
 
 
 def host_dense(exec_, t, cols=None, stride=None):

@@ -2,6 +2,8 @@
 // harness (tests, bench.py) drives the SAME host code a C++ user links: executor, Csr, Dense
 // views, preconditioner::Jacobi, stop criteria, solver::{Cg,Bicgstab,Gmres}.
 #include <cstdio>
+#include <fstream>
+#include <iomanip>
 #include <string>
 
 #include "gko_b200_dist.hpp"
@@ -251,6 +253,39 @@ int gkob_csr_plan_parts(void* csr)
     });
     return v;
 }
+
+// gko::read_generic<Csr<double, int32>>(file) / gko::write(file, csr) / write_binary
+void* gkob_csr_read_f64_i32(void* exec, const char* path)
+{
+    auto e = static_cast<Handle*>(exec)->exec;
+    Handle* h = new Handle{e, nullptr};
+    if (guarded([&] {
+            std::ifstream is(path, std::ios::binary);
+            if (!is) throw StreamError(std::string("cannot open ") + path);
+            h->op = read_generic<matrix::Csr<double, int32>>(is, e);
+        })) {
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+// layout: 0 coordinate, 1 array, 2 binary
+int gkob_csr_write_f64_i32(void* csr, const char* path, int layout)
+{
+    return guarded([&] {
+        auto a = dynamic_cast<const matrix::Csr<double, int32>*>(static_cast<Handle*>(csr)->op.get());
+        if (!a) throw NotSupported("gkob_csr_write: not a Csr<double, int32>");
+        std::ofstream os(path, std::ios::binary);
+        if (!os) throw StreamError(std::string("cannot open ") + path);
+        os << std::setprecision(17);
+        if (layout == 2)
+            write_binary(os, a);
+        else
+            write(os, a, layout == 1 ? layout_type::array : layout_type::coordinate);
+    });
+}
+long long gkob_num_rows(void* op) { return (long long)static_cast<Handle*>(op)->op->get_size().rows; }
+long long gkob_num_cols(void* op) { return (long long)static_cast<Handle*>(op)->op->get_size().cols; }
 
 // kernel variant the tuned plan of a Csr handle uses (2 = warp_stream, 4 = warp_pipe); -1 if
 // the handle is not a double/int32 or float/int32 Csr

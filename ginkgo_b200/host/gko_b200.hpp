@@ -36,43 +36,10 @@
 
 #include "../../include/ginkgo_b200.h"
 
+#include "gko_b200_types.hpp"
+#include "gko_b200_io.hpp"
+
 namespace gko_b200 {
-
-using size_type = std::size_t;
-using uint8 = std::uint8_t;
-using uint32 = std::uint32_t;
-using int32 = std::int32_t;
-using int64 = std::int64_t;
-
-struct dim2 {
-    size_type rows = 0, cols = 0;
-    dim2() = default;
-    dim2(size_type r, size_type c) : rows(r), cols(c) {}
-    explicit dim2(size_type n) : rows(n), cols(n) {}
-    size_type operator[](int i) const { return i == 0 ? rows : cols; }
-    bool operator==(const dim2& o) const { return rows == o.rows && cols == o.cols; }
-};
-
-// ---- exceptions (include/ginkgo/core/base/exception.hpp) -------------------------------
-class Error : public std::runtime_error {
-public:
-    using std::runtime_error::runtime_error;
-};
-class CudaError : public Error {
-    using Error::Error;
-};
-class AllocationError : public Error {
-    using Error::Error;
-};
-class DimensionMismatch : public Error {
-    using Error::Error;
-};
-class NotSupported : public Error {
-    using Error::Error;
-};
-class BadDimension : public Error {
-    using Error::Error;
-};
 
 inline void check(b200_status st, const char* where)
 {
@@ -584,6 +551,48 @@ public:
         }
         return plan_;
     }
+    // empty matrix, to be filled by read()
+    static std::unique_ptr<Csr> create(std::shared_ptr<const Executor> exec)
+    {
+        return create(exec, dim2{}, array<V>(exec, 0), array<I>(exec, 0),
+                      array<I>(exec, std::vector<I>{I(0)}));
+    }
+    // ReadableFromMatrixData / WritableToMatrixData (core/matrix/csr.cpp:558-582, :633-650):
+    // `data` must be in row-major order (read_raw and friends deliver it that way)
+    void read(const matrix_data<V, I>& data)
+    {
+        const size_type nnz = data.nonzeros.size();
+        std::vector<V> va(nnz);
+        std::vector<I> ci(nnz), rp(data.size.rows + 1, I(0));
+        for (size_type k = 0; k < nnz; ++k) {
+            const auto& e = data.nonzeros[k];
+            if (e.row < 0 || (size_type)e.row >= data.size.rows || e.column < 0 ||
+                (size_type)e.column >= data.size.cols)
+                throw BadDimension("Csr::read: entry outside the matrix");
+            if (k > 0 && e.row < data.nonzeros[k - 1].row)
+                throw BadDimension("Csr::read: matrix_data is not in row-major order");
+            va[k] = e.value;
+            ci[k] = e.column;
+            ++rp[e.row + 1];
+        }
+        for (size_type r = 0; r < data.size.rows; ++r) rp[r + 1] += rp[r];
+        b200_csr_plan_destroy(plan_);
+        plan_ = nullptr;
+        size_ = data.size;
+        values_ = array<V>(exec_, va);
+        col_idxs_ = array<I>(exec_, ci);
+        row_ptrs_ = array<I>(exec_, rp);
+    }
+    void write(matrix_data<V, I>& data) const
+    {
+        const auto rp = row_ptrs_.to_host();
+        const auto ci = col_idxs_.to_host();
+        const auto va = values_.to_host();
+        data = matrix_data<V, I>(size_);
+        data.nonzeros.reserve(va.size());
+        for (size_type row = 0; row < size_.rows; ++row)
+            for (auto k = rp[row]; k < rp[row + 1]; ++k) data.nonzeros.push_back({(I)row, ci[k], va[k]});
+    }
     // Csr::convert_to(Ell|Sellp|Coo|Hybrid) and sort_by_column_index on the device
     // (core/matrix/csr.cpp:285-300, :419-530, :1402); defined in gko_b200_convert.hpp
     void convert_to(Ell<V, I>* result) const;
@@ -959,6 +968,44 @@ protected:
 
 template <typename V>
 using Vec = matrix::Dense<V>;
+
+// gko::read / read_binary / read_generic / write / write_binary
+// (include/ginkgo/core/base/mtx_io.hpp:150-320) for matrix::Csr
+template <typename MatrixType, typename StreamType>
+std::unique_ptr<MatrixType> read(StreamType&& is, std::shared_ptr<const Executor> exec)
+{
+    auto mtx = MatrixType::create(std::move(exec));
+    mtx->read(read_raw<typename MatrixType::value_type, typename MatrixType::index_type>(is));
+    return mtx;
+}
+template <typename MatrixType, typename StreamType>
+std::unique_ptr<MatrixType> read_binary(StreamType&& is, std::shared_ptr<const Executor> exec)
+{
+    auto mtx = MatrixType::create(std::move(exec));
+    mtx->read(read_binary_raw<typename MatrixType::value_type, typename MatrixType::index_type>(is));
+    return mtx;
+}
+template <typename MatrixType, typename StreamType>
+std::unique_ptr<MatrixType> read_generic(StreamType&& is, std::shared_ptr<const Executor> exec)
+{
+    auto mtx = MatrixType::create(std::move(exec));
+    mtx->read(read_generic_raw<typename MatrixType::value_type, typename MatrixType::index_type>(is));
+    return mtx;
+}
+template <typename MatrixType, typename StreamType>
+void write(StreamType&& os, const MatrixType* mtx, layout_type layout = layout_type::coordinate)
+{
+    matrix_data<typename MatrixType::value_type, typename MatrixType::index_type> data;
+    mtx->write(data);
+    write_raw(os, data, layout);
+}
+template <typename MatrixType, typename StreamType>
+void write_binary(StreamType&& os, const MatrixType* mtx)
+{
+    matrix_data<typename MatrixType::value_type, typename MatrixType::index_type> data;
+    mtx->write(data);
+    write_binary_raw(os, data);
+}
 
 }  // namespace gko_b200
 

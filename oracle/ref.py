@@ -140,3 +140,24 @@ def convert(fmt, rp, ci, va, n_cols, slice_size=64, stride_factor=1, strategy=0,
     w, stride, cn = int(meta[0]), int(meta[1]), int(meta[2])
     return dict(ell_lim=w, ell_stride=stride, coo_nnz=cn, cols=cols[:w * stride],
                 vals=vals[:w * stride], coo_rows=crows[:cn], coo_cols=ccols[:cn], coo_vals=cvals[:cn])
+
+
+def read_mtx(path, cap=1 << 20):
+    """gko::read_generic_raw<double,int32>: (rows, cols, [(r, c, v) ...]) in the reference's order"""
+    meta = np.zeros(3, np.int64)
+    r, c, v = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.float64)
+    st = lib().refshim_read_mtx(str(path).encode(), _p(meta), _p(r), _p(c), _p(v), cap)
+    if st != 0:
+        raise RuntimeError("reference could not read %s (status %d)" % (path, st))
+    n = int(meta[2])
+    return int(meta[0]), int(meta[1]), r[:n].copy(), c[:n].copy(), v[:n].copy()
+
+
+def write_mtx(path, layout, nrows, ncols, rows, cols, vals):
+    """gko::write_raw (layout 'coordinate' | 'array') / write_binary_raw ('binary')"""
+    rows = np.ascontiguousarray(rows, np.int32)
+    cols = np.ascontiguousarray(cols, np.int32)
+    vals = np.ascontiguousarray(vals, np.float64)
+    st = lib().refshim_write_mtx(str(path).encode(), {"coordinate": 0, "array": 1, "binary": 2}[layout],
+                                 nrows, ncols, len(vals), _p(rows), _p(cols), _p(vals))
+    assert st == 0, st

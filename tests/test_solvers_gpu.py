@@ -295,3 +295,40 @@ def test_cpp_example_simple_solver():
     r = subprocess.run([exe, "40"], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "converged=1" in r.stdout and "fused=1" in r.stdout
+
+
+def test_zz_read_write_csr_files(hexec, orc, tmp_path):
+    """gko::read_generic<Csr> / gko::write on the device executor: a file written by the host
+    layer is read back into a Csr whose apply matches the oracle (kept last in the suite)."""
+    import torch
+    from ginkgo_b200 import api
+    rng = np.random.default_rng(44)
+    n, m = 300, 250
+    rp, ci, va = H.random_csr(rng, n, m, rng.integers(0, 9, n), "f64", "i32")
+    rows = np.repeat(np.arange(n), np.diff(rp))
+    path = tmp_path / "a.mtx"
+    with open(path, "w") as f:
+        f.write("%%MatrixMarket matrix coordinate real general\n%d %d %d\n" % (n, m, len(va)))
+        for r, c, v in zip(rows, ci, va):
+            f.write("%d %d %.17g\n" % (r + 1, c + 1, v))
+    A = api.host_read_csr(hexec, path)
+    assert A.size == (n, m)
+    x = rng.uniform(-1, 1, m)
+    with torch.cuda.stream(hexec.stream):
+        tx = torch.from_numpy(x).to(hexec.device)
+        ty = torch.zeros(n, dtype=torch.float64, device=hexec.device)
+    xd, yd = api.host_dense(hexec, tx), api.host_dense(hexec, ty)
+    api._hcheck(api._host().gkob_apply(A.h, xd.h, yd.h))
+    hexec.synchronize()
+    yo = np.zeros(n)
+    orc("csr_spmv_f64_i32", n, m, len(va), rp, ci, va, x, 1, 1, yo, 1)
+    assert np.array_equal(ty.cpu().numpy(), yo)
+    for layout in ("coordinate", "binary"):
+        out = tmp_path / ("b." + layout)
+        api.host_write_csr(A, out, layout)
+        B = api.host_read_csr(hexec, out)
+        with torch.cuda.stream(hexec.stream):
+            ty.zero_()
+        api._hcheck(api._host().gkob_apply(B.h, xd.h, yd.h))
+        hexec.synchronize()
+        assert np.array_equal(ty.cpu().numpy(), yo)
