@@ -27,32 +27,8 @@ b200_status spmv_impl(b200_ctx* ctx, const b200_csr_plan* plan, int64_t num_rows
         return B200_OK;
     }
 
-    {
-        // experiment knob: pin b in L2 with a stream access-policy window
-        static const char* env = getenv("B200_L2_PERSIST");
-        static const void* last = nullptr;
-        if (env && last != (const void*)b) {
-            const double ratio = atof(env);
-            cudaDeviceProp prop;
-            cudaGetDeviceProperties(&prop, ctx->device);
-            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, prop.persistingL2CacheMaxSize);
-            cudaStreamAttrValue at;
-            memset(&at, 0, sizeof(at));
-            size_t bytes = (size_t)num_cols * sizeof(V);
-            if (bytes > (size_t)prop.accessPolicyMaxWindowSize) bytes = prop.accessPolicyMaxWindowSize;
-            at.accessPolicyWindow.base_ptr = (void*)b;
-            at.accessPolicyWindow.num_bytes = bytes;
-            at.accessPolicyWindow.hitRatio = (float)ratio;
-            at.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-            at.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-            cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &at);
-            fprintf(stderr, "[b200] L2 persist window %zu B ratio %.2f (max persisting %d B, max window %d B)\n",
-                    bytes, ratio, prop.persistingL2CacheMaxSize, prop.accessPolicyMaxWindowSize);
-            last = (const void*)b;
-        }
-    }
     if (plan && plan->parts > 1 && plan->src_cols == (const void*)col_idxs &&
-        plan->src_vals == (const void*)values && !getenv("B200_CSR_NO_REBLOCK")) {
+        plan->src_vals == (const void*)values) {
         // column-blocked copy: part 0 starts the row sums, the others continue them
         const V* ones = (const V*)plan->ones;
         for (int p = 0; p < plan->parts; ++p) {
