@@ -561,21 +561,9 @@ public:
     // `data` must be in row-major order (read_raw and friends deliver it that way)
     void read(const matrix_data<V, I>& data)
     {
-        const size_type nnz = data.nonzeros.size();
-        std::vector<V> va(nnz);
-        std::vector<I> ci(nnz), rp(data.size.rows + 1, I(0));
-        for (size_type k = 0; k < nnz; ++k) {
-            const auto& e = data.nonzeros[k];
-            if (e.row < 0 || (size_type)e.row >= data.size.rows || e.column < 0 ||
-                (size_type)e.column >= data.size.cols)
-                throw BadDimension("Csr::read: entry outside the matrix");
-            if (k > 0 && e.row < data.nonzeros[k - 1].row)
-                throw BadDimension("Csr::read: matrix_data is not in row-major order");
-            va[k] = e.value;
-            ci[k] = e.column;
-            ++rp[e.row + 1];
-        }
-        for (size_type r = 0; r < data.size.rows; ++r) rp[r + 1] += rp[r];
+        std::vector<V> va;
+        std::vector<I> ci, rp;
+        csr_arrays_from_matrix_data(data, rp, ci, va);
         b200_csr_plan_destroy(plan_);
         plan_ = nullptr;
         size_ = data.size;
@@ -585,13 +573,8 @@ public:
     }
     void write(matrix_data<V, I>& data) const
     {
-        const auto rp = row_ptrs_.to_host();
-        const auto ci = col_idxs_.to_host();
-        const auto va = values_.to_host();
-        data = matrix_data<V, I>(size_);
-        data.nonzeros.reserve(va.size());
-        for (size_type row = 0; row < size_.rows; ++row)
-            for (auto k = rp[row]; k < rp[row + 1]; ++k) data.nonzeros.push_back({(I)row, ci[k], va[k]});
+        data = matrix_data_from_csr_arrays(size_, row_ptrs_.to_host(), col_idxs_.to_host(),
+                                           values_.to_host());
     }
     // Csr::convert_to(Ell|Sellp|Coo|Hybrid) and sort_by_column_index on the device
     // (core/matrix/csr.cpp:285-300, :419-530, :1402); defined in gko_b200_convert.hpp

@@ -316,4 +316,41 @@ void write_binary_raw(std::ostream& os, const matrix_data<V, I>& data)
     os.flush();
 }
 
+// matrix_data (row-major sorted) <-> CSR host arrays: the host half of Csr::read / Csr::write
+// (core/matrix/csr.cpp:558-582 aos_to_soa + convert_idxs_to_ptrs, :633-650)
+template <typename V, typename I>
+void csr_arrays_from_matrix_data(const matrix_data<V, I>& data, std::vector<I>& row_ptrs,
+                                 std::vector<I>& col_idxs, std::vector<V>& values)
+{
+    const size_type nnz = data.nonzeros.size();
+    values.assign(nnz, V(0));
+    col_idxs.assign(nnz, I(0));
+    row_ptrs.assign(data.size.rows + 1, I(0));
+    for (size_type k = 0; k < nnz; ++k) {
+        const auto& e = data.nonzeros[k];
+        if (e.row < 0 || (size_type)e.row >= data.size.rows || e.column < 0 ||
+            (size_type)e.column >= data.size.cols)
+            throw BadDimension("Csr::read: entry outside the matrix");
+        if (k > 0 && e.row < data.nonzeros[k - 1].row)
+            throw BadDimension("Csr::read: matrix_data is not in row-major order");
+        values[k] = e.value;
+        col_idxs[k] = e.column;
+        ++row_ptrs[e.row + 1];
+    }
+    for (size_type r = 0; r < data.size.rows; ++r) row_ptrs[r + 1] += row_ptrs[r];
+}
+
+template <typename V, typename I>
+matrix_data<V, I> matrix_data_from_csr_arrays(dim2 size, const std::vector<I>& row_ptrs,
+                                              const std::vector<I>& col_idxs,
+                                              const std::vector<V>& values)
+{
+    matrix_data<V, I> data(size);
+    data.nonzeros.reserve(values.size());
+    for (size_type row = 0; row < size.rows; ++row)
+        for (auto k = row_ptrs[row]; k < row_ptrs[row + 1]; ++k)
+            data.nonzeros.push_back({(I)row, col_idxs[k], values[k]});
+    return data;
+}
+
 }  // namespace gko_b200

@@ -1,6 +1,7 @@
 // CPU-only harness for ginkgo_b200/host/gko_b200_io.hpp (no CUDA, no library to link):
 //   io_check read   <in>  <f64|f32> <i32|i64>          print "rows cols nnz" + "r c value" lines
 //   io_check write  <in>  <out> <coordinate|array|binary>   read (generic) and write back
+//   io_check csr    <in>  <out>                          through CSR arrays, written as binary
 #include <fstream>
 #include <iomanip>
 #include <iostream>
@@ -41,6 +42,20 @@ int main(int argc, char** argv)
                 write_binary_raw(os, d);
             else
                 write_raw(os, d, layout == "array" ? layout_type::array : layout_type::coordinate);
+            return 0;
+        }
+        if (mode == "csr" && argc == 4) {
+            // file -> matrix_data -> CSR arrays -> matrix_data -> binary file (the host half of
+            // Csr::read / Csr::write)
+            std::ifstream is(argv[2], std::ios::binary);
+            auto d = read_generic_raw<double, int32>(is);
+            std::vector<double> va;
+            std::vector<int32> ci, rp;
+            csr_arrays_from_matrix_data(d, rp, ci, va);
+            auto back = matrix_data_from_csr_arrays(d.size, rp, ci, va);
+            if (!(back.nonzeros == d.nonzeros)) return 4;
+            std::ofstream os(argv[3], std::ios::binary);
+            write_binary_raw(os, back);
             return 0;
         }
         std::cerr << "usage: io_check read <in> <f64|f32> <i32|i64> | write <in> <out> <layout>\n";

@@ -115,3 +115,16 @@ def test_errors(io_check, tmp_path, text, code):
     path.write_text(text)
     out = subprocess.run([io_check, "read", str(path), "f64", "i32"], capture_output=True, text=True)
     assert out.returncode == code, (out.returncode, out.stderr)
+
+
+@pytest.mark.parametrize("name", ["coordinate_general", "coordinate_symmetric", "array_general", "empty"])
+def test_csr_array_round_trip(io_check, tmp_path, name):
+    """the host half of Csr::read / Csr::write: matrix_data -> (row_ptrs, col_idxs, values) ->
+    matrix_data reproduces the data, and the written binary file reads back identically"""
+    path = tmp_path / (name + ".mtx")
+    path.write_text(FILES[name])
+    out = tmp_path / "out.bin"
+    res = subprocess.run([io_check, "csr", str(path), str(out)], capture_output=True, text=True)
+    assert res.returncode == 0, (res.returncode, res.stderr)
+    a, b = ref.read_mtx(path), ref.read_mtx(out)
+    assert a[:2] == b[:2] and all(np.array_equal(x, y) for x, y in zip(a[2:], b[2:]))

@@ -308,7 +308,8 @@ def test_zz_read_write_csr_files(hexec, orc, tmp_path):
     rows = np.repeat(np.arange(n), np.diff(rp))
     path = tmp_path / "a.mtx"
     with open(path, "w") as f:
-        f.write("%%MatrixMarket matrix coordinate real general\n%d %d %d\n" % (n, m, len(va)))
+        f.write("%%MatrixMarket matrix coordinate real general\n")  # no %-formatting here
+        f.write("%d %d %d\n" % (n, m, len(va)))
         for r, c, v in zip(rows, ci, va):
             f.write("%d %d %.17g\n" % (r + 1, c + 1, v))
     A = api.host_read_csr(hexec, path)
