@@ -2,7 +2,7 @@
 // (reference common/unified/solver/common_gmres_kernels.cpp:25-160 and
 // common/unified/solver/gmres_kernels.cpp:25-120); arithmetic contract
 // reference/solver/common_gmres_kernels.cpp:27-195 and
-// reference/solver/gmres_kernels.cpp:27-100.
+// reference/solver/gmres_kernels.cpp:27-99.
 //
 // Layouts (core/solver/gmres.cpp:342-362): krylov_bases is a tall
 // ((krylov_dim+1)*rows) x cols Dense, basis i = rows [i*rows, (i+1)*rows);

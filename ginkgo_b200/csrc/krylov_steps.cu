@@ -1,8 +1,8 @@
 // Drop-in Krylov step kernels: CG, BiCGStab (element-wise, masked by the
 // per-column stopping_status) -- replaces gko::kernels::cuda::{cg,bicgstab}::*
 // (reference common/unified/solver/{cg,bicgstab}_kernels.cpp); arithmetic
-// contract reference/solver/cg_kernels.cpp:24-115 and
-// reference/solver/bicgstab_kernels.cpp:25-190.  Scalars (rho, beta, ...) are
+// contract reference/solver/cg_kernels.cpp:24-102 and
+// reference/solver/bicgstab_kernels.cpp:25-178.  Scalars (rho, beta, ...) are
 // read from device memory by every thread, no host round trip.
 #include "elementwise.cuh"
 

@@ -257,11 +257,11 @@ b200_status b200_jacobi_find_blocks_i64(b200_ctx* ctx, int64_t num_rows, const i
  * row.  alpha is 1x1 (alpha_cols == 1) or 1 x cols (alpha_cols == cols).
  * Reductions are deterministic (fixed tree, no floating-point atomics).
  *
- * CG (core/solver/cg_kernels.hpp:25-50; reference/solver/cg_kernels.cpp:24-115)
+ * CG (core/solver/cg_kernels.hpp:25-50; reference/solver/cg_kernels.cpp:24-102)
  * BiCGStab (core/solver/bicgstab_kernels.hpp:25-74;
- *           reference/solver/bicgstab_kernels.cpp:25-190)
+ *           reference/solver/bicgstab_kernels.cpp:25-178)
  * GMRES (core/solver/common_gmres_kernels.hpp:23-48, gmres_kernels.hpp:23-46;
- *        reference/solver/common_gmres_kernels.cpp:112-195, gmres_kernels.cpp:27-100)
+ *        reference/solver/common_gmres_kernels.cpp:112-195, gmres_kernels.cpp:27-99)
  * Stopping criteria (core/stop/residual_norm_kernels.hpp:21-50;
  *        reference/stop/residual_norm_kernels.cpp:27-92)
  * Scalar Jacobi (core/preconditioner/jacobi_kernels.hpp:42-81;
