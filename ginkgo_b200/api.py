@@ -200,6 +200,48 @@ import os as _os
 _HOST_LIB = None
 
 
+def _configure_host_lib(h):
+    """ctypes signatures of the gkob_* C handles (ginkgo_b200/host/capi.cpp)"""
+    vp, ll, i, d = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_double
+    h.gkob_last_error.restype = ctypes.c_char_p
+    h.gkob_exec_create.restype = vp
+    h.gkob_exec_create.argtypes = [i, vp]
+    h.gkob_destroy.argtypes = [vp]
+    h.gkob_launch_count.restype = ll
+    h.gkob_launch_count.argtypes = [vp]
+    h.gkob_csr_kernel_variant.restype, h.gkob_csr_kernel_variant.argtypes = i, [vp]
+    h.gkob_csr_plan_parts.restype, h.gkob_csr_plan_parts.argtypes = i, [vp]
+    h.gkob_staged_create.restype, h.gkob_staged_create.argtypes = vp, [vp, i, ll]
+    h.gkob_staged_apply.restype, h.gkob_staged_apply.argtypes = i, [vp, vp, vp]
+    h.gkob_staged_join.restype, h.gkob_staged_join.argtypes = i, [vp]
+    h.gkob_staged_wait.restype, h.gkob_staged_wait.argtypes = i, [vp]
+    h.gkob_staged_destroy.argtypes = [vp]
+    h.gkob_csr_read_f64_i32.restype, h.gkob_csr_read_f64_i32.argtypes = vp, [vp, ctypes.c_char_p]
+    h.gkob_csr_write_f64_i32.restype = i
+    h.gkob_csr_write_f64_i32.argtypes = [vp, ctypes.c_char_p, i]
+    h.gkob_num_rows.restype, h.gkob_num_rows.argtypes = ll, [vp]
+    h.gkob_num_cols.restype, h.gkob_num_cols.argtypes = ll, [vp]
+    h.gkob_csr_convert.restype = vp
+    h.gkob_csr_convert.argtypes = [vp, ctypes.c_char_p, ll, ll, d, d]
+    h.gkob_csr_sort_by_column_index.restype = i
+    h.gkob_csr_sort_by_column_index.argtypes = [vp]
+    for s in ("f64", "f32"):
+        f = getattr(h, "gkob_csr_view_%s_i32" % s)
+        f.restype, f.argtypes = vp, [vp, ll, ll, ll, vp, vp, vp]
+        f = getattr(h, "gkob_dense_view_" + s)
+        f.restype, f.argtypes = vp, [vp, ll, ll, ll, vp]
+        f = getattr(h, "gkob_solver_create_" + s)
+        f.restype = vp
+        f.argtypes = [vp, i, vp, i, vp, ll, ll, i, i, d, i, i, i, i, i]
+        f = getattr(h, "gkob_solver_info_" + s)
+        f.restype, f.argtypes = i, [vp, ctypes.POINTER(ll), ctypes.POINTER(ctypes.c_ubyte),
+                                    ctypes.POINTER(i)]
+    h.gkob_apply.restype, h.gkob_apply.argtypes = i, [vp, vp, vp]
+    h.gkob_apply4.restype, h.gkob_apply4.argtypes = i, [vp, vp, vp, vp, vp]
+    h.gkob_synchronize.restype, h.gkob_synchronize.argtypes = i, [vp]
+    return h
+
+
 def _host():
     global _HOST_LIB
     if _HOST_LIB is None:
@@ -208,45 +250,7 @@ def _host():
                              "libgko_b200_host.so")
         if not _os.path.exists(path):
             raise _lib.B200Error("%s not found: run `make -C ginkgo_b200/host`" % path)
-        h = ctypes.CDLL(path)
-        vp, ll, i, d = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_double
-        h.gkob_last_error.restype = ctypes.c_char_p
-        h.gkob_exec_create.restype = vp
-        h.gkob_exec_create.argtypes = [i, vp]
-        h.gkob_destroy.argtypes = [vp]
-        h.gkob_launch_count.restype = ll
-        h.gkob_launch_count.argtypes = [vp]
-        h.gkob_csr_kernel_variant.restype, h.gkob_csr_kernel_variant.argtypes = i, [vp]
-        h.gkob_csr_plan_parts.restype, h.gkob_csr_plan_parts.argtypes = i, [vp]
-        h.gkob_staged_create.restype, h.gkob_staged_create.argtypes = vp, [vp, i, ll]
-        h.gkob_staged_apply.restype, h.gkob_staged_apply.argtypes = i, [vp, vp, vp]
-        h.gkob_staged_join.restype, h.gkob_staged_join.argtypes = i, [vp]
-        h.gkob_staged_wait.restype, h.gkob_staged_wait.argtypes = i, [vp]
-        h.gkob_staged_destroy.argtypes = [vp]
-        h.gkob_csr_read_f64_i32.restype, h.gkob_csr_read_f64_i32.argtypes = vp, [vp, ctypes.c_char_p]
-        h.gkob_csr_write_f64_i32.restype = i
-        h.gkob_csr_write_f64_i32.argtypes = [vp, ctypes.c_char_p, i]
-        h.gkob_num_rows.restype, h.gkob_num_rows.argtypes = ll, [vp]
-        h.gkob_num_cols.restype, h.gkob_num_cols.argtypes = ll, [vp]
-        h.gkob_csr_convert.restype = vp
-        h.gkob_csr_convert.argtypes = [vp, ctypes.c_char_p, ll, ll, d, d]
-        h.gkob_csr_sort_by_column_index.restype = i
-        h.gkob_csr_sort_by_column_index.argtypes = [vp]
-        for s in ("f64", "f32"):
-            f = getattr(h, "gkob_csr_view_%s_i32" % s)
-            f.restype, f.argtypes = vp, [vp, ll, ll, ll, vp, vp, vp]
-            f = getattr(h, "gkob_dense_view_" + s)
-            f.restype, f.argtypes = vp, [vp, ll, ll, ll, vp]
-            f = getattr(h, "gkob_solver_create_" + s)
-            f.restype = vp
-            f.argtypes = [vp, i, vp, i, vp, ll, ll, i, i, d, i, i, i, i, i]
-            f = getattr(h, "gkob_solver_info_" + s)
-            f.restype, f.argtypes = i, [vp, ctypes.POINTER(ll), ctypes.POINTER(ctypes.c_ubyte),
-                                        ctypes.POINTER(i)]
-        h.gkob_apply.restype, h.gkob_apply.argtypes = i, [vp, vp, vp]
-        h.gkob_apply4.restype, h.gkob_apply4.argtypes = i, [vp, vp, vp, vp, vp]
-        h.gkob_synchronize.restype, h.gkob_synchronize.argtypes = i, [vp]
-        _HOST_LIB = h
+        _HOST_LIB = _configure_host_lib(ctypes.CDLL(path))
     return _HOST_LIB
 
 
