@@ -221,6 +221,7 @@ def _configure_host_lib(h):
     h.gkob_csr_write_f64_i32.argtypes = [vp, ctypes.c_char_p, i]
     h.gkob_num_rows.restype, h.gkob_num_rows.argtypes = ll, [vp]
     h.gkob_num_cols.restype, h.gkob_num_cols.argtypes = ll, [vp]
+    h.gkob_solver_params.restype, h.gkob_solver_params.argtypes = None, [d, d, d]
     h.gkob_csr_convert.restype = vp
     h.gkob_csr_convert.argtypes = [vp, ctypes.c_char_p, ll, ll, d, d]
     h.gkob_csr_sort_by_column_index.restype = i
@@ -378,15 +379,17 @@ def host_dense(exec_, t, cols=None, stride=None):
 class HostSolver:
     """solver::Cg / Bicgstab / Gmres of the C++ host layer.
 
-    kind: "cg" | "bicgstab" | "gmres" | "fcg" | "cgs";  criteria: max_iters (None = no Iteration criterion),
+    kind: "cg" | "bicgstab" | "gmres" | "fcg" | "cgs" | "ir" (relaxation_factor) | "chebyshev" (foci);  criteria: max_iters (None = no Iteration criterion),
     res_kind 0 none / 1 ResidualNorm / 2 ImplicitResidualNorm, baseline 0 rhs_norm /
     1 initial_resnorm / 2 absolute, iter_first = order inside stop::Combined;
-    precond_max_bs 0 = none, 1 = scalar Jacobi, k > 1 = block Jacobi (block_ptrs required)."""
+    precond_max_bs 0 = none, 1 = scalar Jacobi, k > 1 = block Jacobi (block_ptrs given, or
+    detected by find_blocks); for "ir" the preconditioner slot is the inner solver."""
 
     def __init__(self, exec_, kind, A, precond_max_bs=0, block_ptrs=None, max_iters=None,
                  res_kind=1, baseline=0, reduction=1e-8, iter_first=True, krylov_dim=30, ortho=0,
-                 fused=True, check_every=16):
+                 fused=True, check_every=16, relaxation_factor=1.0, foci=(0.0, 1.0)):
         self.vt = A.vt
+        _host().gkob_solver_params(float(relaxation_factor), float(foci[0]), float(foci[1]))
         bp = None
         nb = 0
         if block_ptrs is not None:
@@ -394,7 +397,7 @@ class HostSolver:
             self._bp = np.ascontiguousarray(block_ptrs, dtype=np.int32)
             bp, nb = self._bp.ctypes.data, len(self._bp) - 1
         fn = getattr(_host(), "gkob_solver_create_" + self.vt)
-        self.obj = _HostObj(exec_, fn(exec_.h, {"cg": 0, "bicgstab": 1, "gmres": 2, "fcg": 3, "cgs": 4}[kind], A.h,
+        self.obj = _HostObj(exec_, fn(exec_.h, {"cg": 0, "bicgstab": 1, "gmres": 2, "fcg": 3, "cgs": 4, "ir": 5, "chebyshev": 6}[kind], A.h,
                                       precond_max_bs, bp, nb, -1 if max_iters is None else max_iters,
                                       res_kind, baseline, reduction, int(iter_first), krylov_dim,
                                       ortho, int(fused), check_every), (A,))

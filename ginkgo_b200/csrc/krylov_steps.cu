@@ -207,6 +207,39 @@ b200_status cgs_step_3(b200_ctx* ctx, int64_t rows, int64_t cols, const V* t, in
     });
 }
 
+// ---- IR / Chebyshev (reference/solver/ir_kernels.cpp:17-24, chebyshev_kernels.cpp:15-66).
+// The Chebyshev coefficients arrive by value and the arithmetic is done in double whatever V
+// is (solver::detail::coeff_type, include/ginkgo/core/solver/chebyshev.hpp:29-31).
+template <typename V>
+b200_status chebyshev_init_update(b200_ctx* ctx, int64_t rows, int64_t cols, double alpha,
+                                  const V* inner_sol, int64_t is, V* update_sol, int64_t us,
+                                  V* output, int64_t os)
+{
+    B200_REQUIRE(ctx != nullptr, "ctx is null");
+    return launch_ew(ctx, rows, cols, [=] __device__(int64_t i, int64_t j) {
+        const double inner_val = (double)inner_sol[i * is + j];
+        update_sol[i * us + j] = (V)inner_val;
+        const double prod = alpha * inner_val;
+        output[i * os + j] = (V)((double)output[i * os + j] + prod);
+    });
+}
+
+template <typename V>
+b200_status chebyshev_update(b200_ctx* ctx, int64_t rows, int64_t cols, double alpha, double beta,
+                             V* inner_sol, int64_t is, V* update_sol, int64_t us, V* output,
+                             int64_t os)
+{
+    B200_REQUIRE(ctx != nullptr, "ctx is null");
+    return launch_ew(ctx, rows, cols, [=] __device__(int64_t i, int64_t j) {
+        const double bu = beta * (double)update_sol[i * us + j];
+        const double val = (double)inner_sol[i * is + j] + bu;
+        inner_sol[i * is + j] = (V)val;
+        update_sol[i * us + j] = (V)val;
+        const double prod = alpha * val;
+        output[i * os + j] = (V)((double)output[i * os + j] + prod);
+    });
+}
+
 template <typename V>
 b200_status bicgstab_initialize(b200_ctx* ctx, int64_t rows, int64_t cols, const V* b, int64_t bs,
                                 V* r, int64_t rs, V* rr, int64_t rrs, V* y, int64_t ys, V* s,
@@ -326,6 +359,13 @@ b200_status bicgstab_finalize(b200_ctx* ctx, int64_t rows, int64_t cols, V* x, i
 
 extern "C" {
 
+/* ir::initialize (reference/solver/ir_kernels.cpp:17-24): reset every stopping status */
+b200_status b200_ir_initialize(b200_ctx* ctx, int64_t cols, uint8_t* stop_status)
+{
+    B200_REQUIRE(ctx != nullptr, "ctx is null");
+    return b200::launch_ew(ctx, 1, cols, [=] __device__(int64_t, int64_t j) { stop_status[j] = 0; });
+}
+
 #define B200_DEF_STEPS(V, VT)                                                                  \
     b200_status b200_cg_initialize_##V(b200_ctx* ctx, int64_t rows, int64_t cols, const VT* b, \
                                        int64_t bs, VT* r, int64_t rs, VT* z, int64_t zs,       \
@@ -405,6 +445,22 @@ extern "C" {
     {                                                                                          \
         return b200::steps::cgs_step_3<VT>(ctx, rows, cols, t, ts, u_hat, uhs, r, rs, x, xs,   \
                                            alpha, stop);                                       \
+    }                                                                                          \
+    b200_status b200_chebyshev_init_update_##V(b200_ctx* ctx, int64_t rows, int64_t cols,      \
+                                               double alpha, const VT* inner_sol, int64_t is,  \
+                                               VT* update_sol, int64_t us, VT* output,         \
+                                               int64_t os)                                     \
+    {                                                                                          \
+        return b200::steps::chebyshev_init_update<VT>(ctx, rows, cols, alpha, inner_sol, is,   \
+                                                      update_sol, us, output, os);             \
+    }                                                                                          \
+    b200_status b200_chebyshev_update_##V(b200_ctx* ctx, int64_t rows, int64_t cols,           \
+                                          double alpha, double beta, VT* inner_sol,            \
+                                          int64_t is, VT* update_sol, int64_t us, VT* output,  \
+                                          int64_t os)                                          \
+    {                                                                                          \
+        return b200::steps::chebyshev_update<VT>(ctx, rows, cols, alpha, beta, inner_sol, is,  \
+                                                 update_sol, us, output, os);                  \
     }                                                                                          \
     b200_status b200_bicgstab_initialize_##V(                                                  \
         b200_ctx* ctx, int64_t rows, int64_t cols, const VT* b, int64_t bs, VT* r, int64_t rs, \

@@ -34,6 +34,9 @@ int guarded(F f)
     }
 }
 
+// extra parameters of solver kinds 5 (Ir) and 6 (Chebyshev), set by gkob_solver_params
+double g_relaxation = 1.0, g_foci_lo = 0.0, g_foci_hi = 1.0;
+
 template <typename V>
 std::unique_ptr<LinOp> make_solver(std::shared_ptr<Executor> exec, int kind,
                                    std::shared_ptr<LinOp> A, int precond_max_bs,
@@ -78,6 +81,18 @@ std::unique_ptr<LinOp> make_solver(std::shared_ptr<Executor> exec, int kind,
     if (kind == 1) {
         auto f = solver::Bicgstab<V>::build();
         f.with_criteria(crit);
+        if (pre) f.with_preconditioner(pre);
+        return f.on(exec)->generate(A);
+    }
+    if (kind == 5) {
+        auto f = solver::Ir<V>::build();
+        f.with_criteria(crit).with_relaxation_factor((V)g_relaxation);
+        if (pre) f.with_solver(pre);
+        return f.on(exec)->generate(A);
+    }
+    if (kind == 6) {
+        auto f = solver::Chebyshev<V>::build();
+        f.with_criteria(crit).with_foci(g_foci_lo, g_foci_hi);
         if (pre) f.with_preconditioner(pre);
         return f.on(exec)->generate(A);
     }
@@ -286,6 +301,15 @@ int gkob_csr_write_f64_i32(void* csr, const char* path, int layout)
 }
 long long gkob_num_rows(void* op) { return (long long)static_cast<Handle*>(op)->op->get_size().rows; }
 long long gkob_num_cols(void* op) { return (long long)static_cast<Handle*>(op)->op->get_size().cols; }
+
+// parameters for the next gkob_solver_create_* of kind 5 (Ir: relaxation_factor) or 6
+// (Chebyshev: foci)
+void gkob_solver_params(double relaxation_factor, double foci_lo, double foci_hi)
+{
+    g_relaxation = relaxation_factor;
+    g_foci_lo = foci_lo;
+    g_foci_hi = foci_hi;
+}
 
 // kernel variant the tuned plan of a Csr handle uses (2 = warp_stream, 4 = warp_pipe); -1 if
 // the handle is not a double/int32 or float/int32 Csr

@@ -82,6 +82,8 @@ struct viabi;
         static constexpr auto cgs_step_1 = b200_cgs_step_1_##S;                                 \
         static constexpr auto cgs_step_2 = b200_cgs_step_2_##S;                                 \
         static constexpr auto cgs_step_3 = b200_cgs_step_3_##S;                                 \
+        static constexpr auto chebyshev_init_update = b200_chebyshev_init_update_##S;           \
+        static constexpr auto chebyshev_update = b200_chebyshev_update_##S;                     \
         static constexpr auto bicgstab_initialize = b200_bicgstab_initialize_##S;               \
         static constexpr auto bicgstab_step_1 = b200_bicgstab_step_1_##S;                       \
         static constexpr auto bicgstab_step_2 = b200_bicgstab_step_2_##S;                       \
@@ -260,6 +262,9 @@ public:
     virtual ~LinOp() = default;
     const dim2& get_size() const { return size_; }
     std::shared_ptr<const Executor> get_executor() const { return exec_; }
+    // include/ginkgo/core/base/lin_op.hpp `apply_uses_initial_guess`: true for the iterative
+    // solvers (x is read as the starting point), false for matrices and preconditioners
+    virtual bool apply_uses_initial_guess() const { return false; }
     // x = op(b)
     void apply(const LinOp* b, LinOp* x) const
     {

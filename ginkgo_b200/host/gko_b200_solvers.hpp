@@ -25,6 +25,9 @@ struct Updater {
     const LinOp* residual_norm = nullptr;
     const LinOp* implicit_sq_residual_norm = nullptr;
     const LinOp* solution = nullptr;
+    // core/stop/criterion.hpp `ignore_residual_check`: a ResidualNorm criterion that is handed
+    // no residual norm reports "not converged" instead of computing one
+    bool ignore_residual_check = false;
 };
 
 class Criterion {
@@ -130,6 +133,8 @@ public:
             tau = as<Dense>(u.implicit_sq_residual_norm);
         } else if (u.residual_norm) {
             tau = as<Dense>(u.residual_norm);
+        } else if (u.ignore_residual_check) {
+            return false;  // core/stop/residual_norm.cpp:172-175
         } else if (u.residual) {
             as<Dense>(u.residual)->compute_norm2(u_tau_.get());
             tau = u_tau_.get();
@@ -419,9 +424,35 @@ public:
     }
     std::shared_ptr<const LinOp> get_system_matrix() const { return system_matrix_; }
     std::shared_ptr<const LinOp> get_preconditioner() const { return preconditioner_; }
+    bool apply_uses_initial_guess() const override { return true; }
 
 protected:
     using Dense = matrix::Dense<V>;
+    // core/solver/update_residual.hpp:20-73 (IR, Chebyshev): iteration 0 checks the residual it
+    // is given; later iterations first ask the criteria with the residual check switched off,
+    // then recompute residual = b - A x and check again
+    bool update_residual(stop::Criterion* crit, int64 iter, const Dense* b, Dense* x, Dense* residual,
+                         const Dense*& residual_ptr, array<uint8>* stop_status) const
+    {
+        bool one_changed = false;
+        stop::Updater u;
+        u.num_iterations = iter;
+        u.solution = x;
+        if (iter == 0) {
+            u.residual = residual_ptr;
+            return crit->check(1, true, stop_status, &one_changed, u);
+        }
+        u.ignore_residual_check = true;
+        if (crit->check(1, false, stop_status, &one_changed, u)) return true;
+        residual_ptr = residual;
+        residual->copy_from(b);
+        system_matrix_->apply(neg_one_.get(), x, one_.get(), residual);
+        stop::Updater u2;
+        u2.num_iterations = iter;
+        u2.solution = x;
+        u2.residual = residual_ptr;
+        return crit->check(1, true, stop_status, &one_changed, u2);
+    }
     template <typename FactoryT>
     SolverBase(std::shared_ptr<const Executor> exec, const FactoryT& f,
                std::shared_ptr<const LinOp> op)
@@ -880,6 +911,165 @@ protected:
         }
         this->record(iter, stop_status);
     }
+};
+// ---------------------------------------------------------------------------------------------
+// solver::Ir (core/solver/ir.cpp:192-258): x += relaxation_factor * inner_solver(b - A x).
+// The inner solver is the `with_solver` / preconditioner slot of the factory (Identity by
+// default, which gives Richardson iteration).  default_initial_guess = provided.
+// ---------------------------------------------------------------------------------------------
+template <typename V>
+class Ir : public SolverBase<V> {
+    using Base = SolverBase<V>;
+    using Dense = matrix::Dense<V>;
+
+public:
+    struct Factory : SolverFactoryBase<Factory> {
+        V relaxation_factor_ = V(1);
+        Factory& with_relaxation_factor(V w)
+        {
+            relaxation_factor_ = w;
+            return *this;
+        }
+        // the reference's name for the inner-solver slot
+        Factory& with_solver(std::shared_ptr<const LinOpFactory> f) { return this->with_preconditioner(std::move(f)); }
+        Factory& with_generated_solver(std::shared_ptr<const LinOp> s)
+        {
+            return this->with_generated_preconditioner(std::move(s));
+        }
+        std::unique_ptr<LinOp> generate(std::shared_ptr<const LinOp> op) const override
+        {
+            auto exec = this->exec_ ? this->exec_ : op->get_executor();
+            return std::unique_ptr<LinOp>(new Ir(exec, *this, op));
+        }
+    };
+    static Factory build() { return Factory{}; }
+    std::shared_ptr<const LinOp> get_solver() const { return this->preconditioner_; }
+
+protected:
+    Ir(std::shared_ptr<const Executor> exec, const Factory& f, std::shared_ptr<const LinOp> op)
+        : Base(exec, f, op), relaxation_(matrix::scalar<V>(f.relaxation_factor_, exec))
+    {}
+    using Base::apply_impl;
+    void apply_impl(const LinOp* lb, LinOp* lx) const override
+    {
+        auto b = as<Dense>(lb);
+        auto x = as<Dense>(lx);
+        auto exec = this->exec_;
+        const dim2 sz = b->get_size();
+        auto residual = Dense::create(exec, sz);
+        std::unique_ptr<Dense> inner_solution;
+        array<uint8> stop_status(exec, sz.cols);
+        GKOB_CALL(b200_ir_initialize(exec->ctx(), sz.cols, stop_status.get_data()));
+        residual->copy_from(b);
+        this->system_matrix_->apply(this->neg_one_.get(), x, this->one_.get(), residual.get());
+        const Dense* residual_ptr = residual.get();
+        stop::CriterionArgs args{this->system_matrix_, b, x, residual_ptr};
+        auto crit = stop::combine_and_generate(this->criteria_, exec, args);
+        auto inner = this->preconditioner_.get();
+        int64 iter = -1;
+        while (true) {
+            ++iter;
+            if (this->update_residual(crit.get(), iter, b, x, residual.get(), residual_ptr, &stop_status))
+                break;
+            if (inner->apply_uses_initial_guess()) {
+                if (!inner_solution) inner_solution = Dense::create(exec, sz);
+                inner_solution->copy_from(residual_ptr);
+                inner->apply(residual_ptr, inner_solution.get());
+                x->add_scaled(relaxation_.get(), inner_solution.get());
+            } else {
+                inner->apply(relaxation_.get(), residual_ptr, this->one_.get(), x);
+            }
+        }
+        this->record(iter, stop_status);
+    }
+
+private:
+    std::unique_ptr<Dense> relaxation_;
+};
+
+// ---------------------------------------------------------------------------------------------
+// solver::Chebyshev (core/solver/chebyshev.cpp:85-97, :201-296): no inner products; `foci` =
+// the interval that contains the spectrum of the preconditioned operator.
+// ---------------------------------------------------------------------------------------------
+template <typename V>
+class Chebyshev : public SolverBase<V> {
+    using Base = SolverBase<V>;
+    using Dense = matrix::Dense<V>;
+
+public:
+    struct Factory : SolverFactoryBase<Factory> {
+        std::pair<double, double> foci_{0.0, 1.0};
+        Factory& with_foci(double lo, double hi)
+        {
+            foci_ = {lo, hi};
+            return *this;
+        }
+        Factory& with_foci(std::pair<double, double> f)
+        {
+            foci_ = f;
+            return *this;
+        }
+        std::unique_ptr<LinOp> generate(std::shared_ptr<const LinOp> op) const override
+        {
+            auto exec = this->exec_ ? this->exec_ : op->get_executor();
+            return std::unique_ptr<LinOp>(new Chebyshev(exec, *this, op));
+        }
+    };
+    static Factory build() { return Factory{}; }
+
+protected:
+    Chebyshev(std::shared_ptr<const Executor> exec, const Factory& f, std::shared_ptr<const LinOp> op)
+        : Base(exec, f, op),
+          center_((f.foci_.first + f.foci_.second) / 2.0),
+          foci_direction_((f.foci_.second - f.foci_.first) / 2.0)
+    {
+        if (!(f.foci_.first <= f.foci_.second) || center_ == 0.0)
+            throw BadDimension("Chebyshev: foci must satisfy lo <= hi and lo + hi != 0");
+    }
+    using Base::apply_impl;
+    void apply_impl(const LinOp* lb, LinOp* lx) const override
+    {
+        auto b = as<Dense>(lb);
+        auto x = as<Dense>(lx);
+        auto exec = this->exec_;
+        auto ctx = exec->ctx();
+        const dim2 sz = b->get_size();
+        auto residual = Dense::create(exec, sz), inner_solution = Dense::create(exec, sz),
+             update_solution = Dense::create(exec, sz);
+        double alpha_host = 1.0 / center_;
+        double beta_host = 0.5 * (foci_direction_ * alpha_host) * (foci_direction_ * alpha_host);
+        array<uint8> stop_status(exec, sz.cols);
+        GKOB_CALL(b200_ir_initialize(ctx, sz.cols, stop_status.get_data()));
+        residual->copy_from(b);
+        this->system_matrix_->apply(this->neg_one_.get(), x, this->one_.get(), residual.get());
+        const Dense* residual_ptr = residual.get();
+        stop::CriterionArgs args{this->system_matrix_, b, x, residual_ptr};
+        auto crit = stop::combine_and_generate(this->criteria_, exec, args);
+        int64 iter = -1;
+        while (true) {
+            ++iter;
+            if (this->update_residual(crit.get(), iter, b, x, residual.get(), residual_ptr, &stop_status))
+                break;
+            if (this->preconditioner_->apply_uses_initial_guess()) inner_solution->copy_from(residual_ptr);
+            this->preconditioner_->apply(residual_ptr, inner_solution.get());
+            if (iter == 0) {
+                GKOB_CALL(vabi<V>::chebyshev_init_update(
+                    ctx, sz.rows, sz.cols, alpha_host, GKOB_CVS(inner_solution), GKOB_VS(update_solution),
+                    GKOB_VS(x)));
+                continue;
+            }
+            if (iter > 1)
+                beta_host = (foci_direction_ * alpha_host / 2.0) * (foci_direction_ * alpha_host / 2.0);
+            alpha_host = 1.0 / (center_ - beta_host / alpha_host);
+            GKOB_CALL(vabi<V>::chebyshev_update(ctx, sz.rows, sz.cols, alpha_host, beta_host,
+                                                GKOB_VS(inner_solution), GKOB_VS(update_solution),
+                                                GKOB_VS(x)));
+        }
+        this->record(iter, stop_status);
+    }
+
+private:
+    double center_, foci_direction_;
 };
 #undef GKOB_VS
 #undef GKOB_CVS

@@ -347,6 +347,19 @@ b200_status b200_jacobi_find_blocks_i64(b200_ctx* ctx, int64_t num_rows, const i
                                     VT* r, int64_t r_stride, VT* x, int64_t x_stride,         \
                                     const VT* alpha, const uint8_t* stop_status);             \
                                                                                               \
+    /* Chebyshev (core/solver/chebyshev_kernels.hpp; reference/solver/chebyshev_kernels.cpp:   \
+     * 15-66): alpha / beta by value, arithmetic in double for every value type */            \
+    b200_status b200_chebyshev_init_update_##V(b200_ctx* ctx, int64_t rows, int64_t cols,     \
+                                               double alpha, const VT* inner_sol,             \
+                                               int64_t inner_stride, VT* update_sol,          \
+                                               int64_t update_stride, VT* output,             \
+                                               int64_t output_stride);                        \
+    b200_status b200_chebyshev_update_##V(b200_ctx* ctx, int64_t rows, int64_t cols,          \
+                                          double alpha, double beta, VT* inner_sol,           \
+                                          int64_t inner_stride, VT* update_sol,               \
+                                          int64_t update_stride, VT* output,                  \
+                                          int64_t output_stride);                             \
+                                                                                              \
     b200_status b200_bicgstab_initialize_##V(                                                 \
         b200_ctx* ctx, int64_t rows, int64_t cols, const VT* b, int64_t b_stride, VT* r,      \
         int64_t r_stride, VT* rr, int64_t rr_stride, VT* y, int64_t y_stride, VT* s,          \
@@ -416,6 +429,9 @@ b200_status b200_jacobi_find_blocks_i64(b200_ctx* ctx, int64_t num_rows, const i
     b200_status b200_jacobi_scalar_apply_##V(                                                 \
         b200_ctx* ctx, int64_t rows, int64_t cols, const VT* inv_diag, const VT* alpha,       \
         const VT* b, int64_t b_stride, const VT* beta, VT* x, int64_t x_stride);
+
+/* ir::initialize (core/solver/ir_kernels.hpp; reference/solver/ir_kernels.cpp:17-24): reset */
+b200_status b200_ir_initialize(b200_ctx* ctx, int64_t cols, uint8_t* stop_status);
 
 /* set_all_statuses (core/stop/criterion_kernels.hpp:21; used by stop::Iteration) */
 b200_status b200_set_all_statuses(b200_ctx* ctx, int64_t cols, uint8_t stopping_id,

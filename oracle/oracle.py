@@ -22,6 +22,8 @@ class SolverCfg(ctypes.Structure):
         ("res_kind", ctypes.c_int32), ("baseline", ctypes.c_int32),
         ("reduction_factor", ctypes.c_double), ("iter_first", ctypes.c_int32),
         ("krylov_dim", ctypes.c_int32), ("ortho", ctypes.c_int32),
+        ("relaxation_factor", ctypes.c_double), ("foci_lo", ctypes.c_double),
+        ("foci_hi", ctypes.c_double),
     ]
 
 

@@ -282,6 +282,38 @@ void FN(cgs_step_3)(int64_t rows, int64_t cols, const V* t, int64_t ts, const V*
         }
 }
 
+/* reference/solver/ir_kernels.cpp:17-24: reset every stopping status */
+#ifndef ORC_IR_INITIALIZE
+#define ORC_IR_INITIALIZE
+void orc_ir_initialize(int64_t cols, uint8_t* stop)
+{
+    for (int64_t j = 0; j < cols; ++j) stop[j] = 0;
+}
+#endif
+/* reference/solver/chebyshev_kernels.cpp:15-66; coefficients and arithmetic in double
+ * (solver::detail::coeff_type, include/ginkgo/core/solver/chebyshev.hpp:29-31) */
+void FN(chebyshev_init_update)(int64_t rows, int64_t cols, double alpha, const V* inner_sol, int64_t is,
+                               V* update_sol, int64_t us, V* output, int64_t os)
+{
+    for (int64_t row = 0; row < rows; ++row)
+        for (int64_t col = 0; col < cols; ++col) {
+            const double inner_val = (double)inner_sol[row * is + col];
+            update_sol[row * us + col] = (V)inner_val;
+            output[row * os + col] = (V)((double)output[row * os + col] + alpha * inner_val);
+        }
+}
+void FN(chebyshev_update)(int64_t rows, int64_t cols, double alpha, double beta, V* inner_sol, int64_t is,
+                          V* update_sol, int64_t us, V* output, int64_t os)
+{
+    for (int64_t row = 0; row < rows; ++row)
+        for (int64_t col = 0; col < cols; ++col) {
+            const double val = (double)inner_sol[row * is + col] + beta * (double)update_sol[row * us + col];
+            inner_sol[row * is + col] = (V)val;
+            update_sol[row * us + col] = (V)val;
+            output[row * os + col] = (V)((double)output[row * os + col] + alpha * val);
+        }
+}
+
 /* reference/solver/bicgstab_kernels.cpp:25-60 */
 void FN(bicgstab_initialize)(int64_t rows, int64_t cols, const V* b, int64_t bs, V* r, int64_t rs,
                              V* rr, int64_t rrs, V* y, int64_t ys, V* s, int64_t ss, V* t,

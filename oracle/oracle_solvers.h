@@ -25,6 +25,8 @@ typedef struct {
     int32_t iter_first;     /* order inside stop::Combined: Iteration before residual? */
     int32_t krylov_dim;     /* GMRES */
     int32_t ortho;          /* GMRES: 0 mgs, 1 cgs, 2 cgs2 */
+    double relaxation_factor; /* IR */
+    double foci_lo, foci_hi;  /* Chebyshev */
 } orc_solver_cfg;
 #endif
 
@@ -77,8 +79,20 @@ static void FN(s_criterion_generate)(FN(sctx) * s, const V* b, const V* initial_
 /* stop::Combined / Iteration / ResidualNorm check, core/stop/combined.cpp:33-52,
  * core/stop/iteration.cpp:14-24, core/stop/residual_norm.cpp:165-228.
  * residual may be NULL when residual_norm is given (GMRES). */
+static int FN(s_check_ex)(FN(sctx) * s, int64_t iter, const V* residual, const V* residual_norm,
+                          const V* implicit_sq, int set_finalized, uint8_t* stop, int* one_changed,
+                          int ignore_residual_check);
 static int FN(s_check)(FN(sctx) * s, int64_t iter, const V* residual, const V* residual_norm,
                        const V* implicit_sq, int set_finalized, uint8_t* stop, int* one_changed)
+{
+    return FN(s_check_ex)(s, iter, residual, residual_norm, implicit_sq, set_finalized, stop,
+                          one_changed, 0);
+}
+/* ignore_residual_check: core/stop/residual_norm.cpp:172-175 (a ResidualNorm criterion that is
+ * given no residual norm returns "not converged" without touching anything) */
+static int FN(s_check_ex)(FN(sctx) * s, int64_t iter, const V* residual, const V* residual_norm,
+                          const V* implicit_sq, int set_finalized, uint8_t* stop, int* one_changed,
+                          int ignore_residual_check)
 {
     const orc_solver_cfg* c = s->cfg;
     const int has_it = c->max_iters >= 0, has_res = c->res_kind != 0;
@@ -98,7 +112,9 @@ static int FN(s_check)(FN(sctx) * s, int64_t iter, const V* residual, const V* r
             }
         } else {
             int32_t all_conv = 0, ch = 0;
-            if (c->res_kind == 1) {
+            if (c->res_kind == 1 && !residual_norm && ignore_residual_check) {
+                /* skipped */
+            } else if (c->res_kind == 1) {
                 const V* tau = residual_norm;
                 if (!tau) {
                     FN(dense_compute_norm2)(s->n, s->cols, residual, s->cols, s->u_tau);
@@ -242,6 +258,108 @@ int64_t FN(cgs_solve)(int64_t n, int64_t cols, const int32_t* rp, const int32_t*
     if (resnorm_out) FN(dense_compute_norm2)(n, cols, r, cols, resnorm_out);
     free(r); free(r_tld); free(p); free(q); free(u); free(u_hat); free(v_hat); free(t); free(sc);
     free(s.starting_tau); free(s.u_tau); free(stop);
+    return iter;
+}
+
+/* core/solver/update_residual.hpp:20-73 */
+static int FN(s_update_residual)(FN(sctx) * s, int64_t iter, const V* b, const V* x, V* residual,
+                                 const V** residual_ptr, uint8_t* stop)
+{
+    int one_changed;
+    const V one = 1, neg_one = -1;
+    if (iter == 0) return FN(s_check)(s, iter, *residual_ptr, NULL, NULL, 1, stop, &one_changed);
+    if (FN(s_check_ex)(s, iter, NULL, NULL, NULL, 0, stop, &one_changed, 1)) return 1;
+    *residual_ptr = residual;
+    memcpy(residual, b, sizeof(V) * s->n * s->cols);
+    FN(s_apply_A)(s, &neg_one, x, &one, residual);
+    return FN(s_check)(s, iter, *residual_ptr, NULL, NULL, 1, stop, &one_changed);
+}
+
+/* x = alpha M^-1 r + beta x: LinOp::apply(alpha, b, beta, x) of the inner solver / preconditioner
+ * (matrix::Identity: scale + add_scaled; Jacobi: scalar_apply / apply) */
+static void FN(s_apply_M_adv)(const FN(sctx) * s, const V* alpha, const V* r, const V* beta, V* x)
+{
+    const orc_solver_cfg* c = s->cfg;
+    if (c->precond == 0) {
+        FN(dense_scale)(s->n, s->cols, beta, 1, x, s->cols);
+        FN(dense_add_scaled)(s->n, s->cols, alpha, 1, r, s->cols, x, s->cols);
+    } else if (c->precond == 1) {
+        FN(jacobi_scalar_apply)(s->n, s->cols, (const V*)c->blocks, alpha, r, s->cols, beta, x, s->cols);
+    } else {
+        CAT(FN(jacobi_apply), i32)(c->num_blocks, 32, c->block_offset, c->group_offset, c->group_power,
+                                   c->block_ptrs, (const V*)c->blocks, alpha, r, s->cols, s->cols,
+                                   beta, x, s->cols);
+    }
+}
+
+/* core/solver/ir.cpp:192-258 with default_initial_guess = provided; the inner solver is the
+ * configured preconditioner (Identity by default), which does not use an initial guess */
+int64_t FN(ir_solve)(int64_t n, int64_t cols, const int32_t* rp, const int32_t* ci, const V* va,
+                     const V* b, V* x, const orc_solver_cfg* cfg, uint8_t* stop_out,
+                     V* resnorm_out)
+{
+    FN(sctx) s = {n, cols, rp, ci, va, cfg, NULL, NULL};
+    const size_t nb = sizeof(V) * n * cols;
+    V* residual = malloc(nb);
+    s.starting_tau = malloc(sizeof(V) * cols);
+    s.u_tau = malloc(sizeof(V) * cols);
+    uint8_t* stop = malloc(cols);
+    const V one = 1, neg_one = -1, relax = (V)cfg->relaxation_factor;
+    orc_ir_initialize(cols, stop);
+    memcpy(residual, b, nb);
+    FN(s_apply_A)(&s, &neg_one, x, &one, residual);
+    const V* residual_ptr = residual;
+    FN(s_criterion_generate)(&s, b, residual_ptr);
+    int64_t iter = -1;
+    while (1) {
+        ++iter;
+        if (FN(s_update_residual)(&s, iter, b, x, residual, &residual_ptr, stop)) break;
+        FN(s_apply_M_adv)(&s, &relax, residual_ptr, &one, x);
+    }
+    if (stop_out) memcpy(stop_out, stop, cols);
+    if (resnorm_out) FN(dense_compute_norm2)(n, cols, residual, cols, resnorm_out);
+    free(residual); free(s.starting_tau); free(s.u_tau); free(stop);
+    return iter;
+}
+
+/* core/solver/chebyshev.cpp:85-97 (center, foci direction) and :201-296 */
+int64_t FN(chebyshev_solve)(int64_t n, int64_t cols, const int32_t* rp, const int32_t* ci, const V* va,
+                            const V* b, V* x, const orc_solver_cfg* cfg, uint8_t* stop_out,
+                            V* resnorm_out)
+{
+    FN(sctx) s = {n, cols, rp, ci, va, cfg, NULL, NULL};
+    const size_t nb = sizeof(V) * n * cols;
+    V *residual = malloc(nb), *inner = malloc(nb), *update = malloc(nb);
+    s.starting_tau = malloc(sizeof(V) * cols);
+    s.u_tau = malloc(sizeof(V) * cols);
+    uint8_t* stop = malloc(cols);
+    const V one = 1, neg_one = -1;
+    const double center = (cfg->foci_lo + cfg->foci_hi) / 2.0;
+    const double foci_direction = (cfg->foci_hi - cfg->foci_lo) / 2.0;
+    double alpha_host = 1.0 / center;
+    double beta_host = 0.5 * (foci_direction * alpha_host) * (foci_direction * alpha_host);
+    orc_ir_initialize(cols, stop);
+    memcpy(residual, b, nb);
+    FN(s_apply_A)(&s, &neg_one, x, &one, residual);
+    const V* residual_ptr = residual;
+    FN(s_criterion_generate)(&s, b, residual_ptr);
+    int64_t iter = -1;
+    while (1) {
+        ++iter;
+        if (FN(s_update_residual)(&s, iter, b, x, residual, &residual_ptr, stop)) break;
+        FN(s_apply_M)(&s, residual_ptr, inner);
+        if (iter == 0) {
+            FN(chebyshev_init_update)(n, cols, alpha_host, inner, cols, update, cols, x, cols);
+            continue;
+        }
+        if (iter > 1)
+            beta_host = (foci_direction * alpha_host / 2.0) * (foci_direction * alpha_host / 2.0);
+        alpha_host = 1.0 / (center - beta_host / alpha_host);
+        FN(chebyshev_update)(n, cols, alpha_host, beta_host, inner, cols, update, cols, x, cols);
+    }
+    if (stop_out) memcpy(stop_out, stop, cols);
+    if (resnorm_out) FN(dense_compute_norm2)(n, cols, residual, cols, resnorm_out);
+    free(residual); free(inner); free(update); free(s.starting_tau); free(s.u_tau); free(stop);
     return iter;
 }
 

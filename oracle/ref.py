@@ -72,7 +72,8 @@ def spmv(fmt, rp, ci, va, x, n_cols, alpha=None, beta=None, y=None, exec_kind=0,
 
 
 def solve(kind, rp, ci, va, b, x0, precond_max_bs=0, block_ptrs=None, max_iters=-1, res_kind=1,
-          baseline=0, reduction=1e-8, iter_first=1, krylov_dim=30, ortho=0, exec_kind=0):
+          baseline=0, reduction=1e-8, iter_first=1, krylov_dim=30, ortho=0, exec_kind=0,
+          relaxation_factor=1.0, foci=(0.0, 1.0)):
     n = len(rp) - 1
     b2 = np.ascontiguousarray(b).reshape(n, -1)
     x = np.ascontiguousarray(x0).reshape(n, -1).copy()
@@ -81,7 +82,9 @@ def solve(kind, rp, ci, va, b, x0, precond_max_bs=0, block_ptrs=None, max_iters=
     sec = ctypes.c_double(0)
     resn = np.zeros(nrhs, va.dtype)
     nb = 0 if block_ptrs is None else len(block_ptrs) - 1
-    st = lib().refshim_solve(exec_kind, {"cg": 0, "bicgstab": 1, "gmres": 2, "fcg": 3, "cgs": 4}[kind], _vt(va), n,
+    lib().refshim_solve_params(float(relaxation_factor), float(foci[0]), float(foci[1]))
+    st = lib().refshim_solve(exec_kind, {"cg": 0, "bicgstab": 1, "gmres": 2, "fcg": 3, "cgs": 4, "ir": 5,
+                                         "chebyshev": 6}[kind], _vt(va), n,
                              len(va), _p(rp), _p(ci), _p(va), _p(b2), _p(x), nrhs, precond_max_bs,
                              _p(block_ptrs), nb, max_iters, res_kind, baseline, reduction,
                              iter_first, krylov_dim, ortho, ctypes.byref(iters), _p(resn),

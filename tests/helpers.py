@@ -224,6 +224,8 @@ def orc_solve(kind, vt, rp, ci, va, b, x0, precond=0, jac=None, **kw):
     cfg.iter_first = kw.get("iter_first", 1)
     cfg.krylov_dim = kw.get("krylov_dim", 30)
     cfg.ortho = kw.get("ortho", 0)
+    cfg.relaxation_factor = kw.get("relaxation_factor", 1.0)
+    cfg.foci_lo, cfg.foci_hi = kw.get("foci", (0.0, 1.0))
     keep = []
     if jac is not None:
         keep.append(jac["blocks"])

@@ -218,3 +218,37 @@ def test_host_errors(host):
     with pytest.raises(Exception):  # block larger than max_block_size
         api.HostSolver(host, "cg", A, precond_max_bs=2, block_ptrs=np.array([0, 5, n], np.int32),
                        max_iters=5, fused=False)
+
+
+@pytest.mark.parametrize("kind,extra", [("ir", dict(relaxation_factor=1.0)), ("ir", dict(relaxation_factor=0.3)),
+                                        ("chebyshev", dict(foci=(0.3, 7.9))),
+                                        ("chebyshev", dict(foci=(0.4, 1.7)))])
+@pytest.mark.parametrize("precond", [0, 1, 2])
+@pytest.mark.parametrize("vt", ["f64", "f32"])
+def test_host_ir_and_chebyshev(host, kind, extra, precond, vt):
+    """update_residual.hpp semantics (ignore_residual_check) + the Ir / Chebyshev host loops"""
+    from oracle import ref
+    rp, ci, va = W.laplace(14, 2, vdtype=VT[vt])
+    n = len(rp) - 1
+    rng = np.random.default_rng(11)
+    b = rng.uniform(-1, 1, (n, 2)).astype(VT[vt])
+    x0 = rng.uniform(-1, 1, (n, 2)).astype(VT[vt])
+    if kind == "ir" and precond == 0:
+        extra = dict(relaxation_factor=extra["relaxation_factor"] * 0.2)
+    max_bs = {0: 0, 1: 1, 2: 8}[precond]
+    bp = np.arange(0, n + 1, 8, dtype=np.int32)[: n // 8 + 1] if precond == 2 else None
+    if precond == 2 and bp[-1] != n:
+        bp = np.append(bp, n).astype(np.int32)
+    jac = None
+    if precond:
+        if not ref.available():
+            pytest.skip("needs oracle/_ref for the inverted blocks")
+        jac = ref.jacobi_generate(rp, ci, va, max_bs, bp)
+    for iter_first in (1, 0):
+        for res_kind in (1, 0):
+            kw = dict(max_iters=40, reduction=1e-3, res_kind=res_kind, krylov_dim=10, **extra)
+            xo, ito, stop_o = H.orc_solve(kind, vt, rp, ci, va, b, x0, precond, jac, iter_first=iter_first, **kw)
+            xh, ith, stop_h = host_solve(host, kind, vt, rp, ci, va, b, x0, max_bs, bp,
+                                         iter_first=bool(iter_first), **kw)
+            assert (ith, stop_h) == (ito, stop_o[0])
+            assert np.array_equal(xh, xo, equal_nan=True)

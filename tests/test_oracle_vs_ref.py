@@ -285,3 +285,31 @@ def test_find_blocks_matches_reference(orc, max_bs, max_run):
     else:
         assert nb.value == r["num_blocks"]
         assert np.array_equal(bp[:nb.value + 1], r["block_ptrs"])
+
+
+@pytest.mark.parametrize("kind,extra", [("ir", dict(relaxation_factor=1.0)), ("ir", dict(relaxation_factor=0.2)),
+                                        ("chebyshev", dict(foci=(0.3, 7.9))),
+                                        ("chebyshev", dict(foci=(1.0, 1.0)))])
+@pytest.mark.parametrize("precond", [0, 1, 2])
+@pytest.mark.parametrize("vt", ["f64", "f32"])
+def test_ir_and_chebyshev_loops_bit_identical_to_reference(kind, extra, precond, vt):
+    """core/solver/ir.cpp, chebyshev.cpp with update_residual.hpp (residual check ignored in the
+    first criterion pass of every iteration > 0)"""
+    rp, ci, va = W.laplace(16, 2, vdtype=VT[vt])
+    n = len(rp) - 1
+    rng = np.random.default_rng(9)
+    b = rng.uniform(-1, 1, (n, 2)).astype(VT[vt])
+    x0 = rng.uniform(-1, 1, (n, 2)).astype(VT[vt])
+    if kind == "ir" and precond == 0:
+        extra = dict(relaxation_factor=extra["relaxation_factor"] * 0.2)  # keep plain Richardson stable
+    bp = np.arange(0, n + 1, 8, dtype=np.int32) if precond == 2 else None
+    max_bs = {0: 0, 1: 1, 2: 8}[precond]
+    jac = ref.jacobi_generate(rp, ci, va, max_bs, bp) if precond else None
+    red = 1e-3
+    for iter_first in (1, 0):
+        xr, itr, _, _ = ref.solve(kind, rp, ci, va, b, x0, precond_max_bs=max_bs, block_ptrs=bp,
+                                  max_iters=60, reduction=red, iter_first=iter_first, **extra)
+        xo, ito, stop = orc_solve(kind, vt, rp, ci, va, b, x0, precond, jac, max_iters=60,
+                                  reduction=red, iter_first=iter_first, **extra)
+        assert itr == ito
+        assert np.array_equal(xr, xo, equal_nan=True)  # a diverging run must diverge alike

@@ -763,3 +763,23 @@ def test_cgs_steps(orc, cuda, vt, rows, cols):
                 lambda: [rows, cols, v["t"], st["t"], v["u_hat"], st["u_hat"], v["r"].copy(), st["r"],
                          v["x"].copy(), st["x"], sc["alpha"], stop])
     _all_equal(a, b)
+
+
+@pytest.mark.parametrize("vt", VTS)
+@pytest.mark.parametrize("rows,cols", [(597, 43), (100001, 1), (0, 2)])
+def test_ir_and_chebyshev_kernels(orc, cuda, vt, rows, cols):
+    rng = np.random.default_rng(92)
+    st = dict(inner=cols + 1, update=cols + 2, out=cols)
+    v = {k: H.dense(rng, rows, cols, s, vt) for k, s in st.items()}
+    a, b = both(orc, cuda, "chebyshev_init_update_" + vt,
+                lambda: [rows, cols, 0.37, v["inner"], st["inner"], v["update"].copy(), st["update"],
+                         v["out"].copy(), st["out"]])
+    _all_equal(a, b)
+    a, b = both(orc, cuda, "chebyshev_update_" + vt,
+                lambda: [rows, cols, 0.41, 0.0625, v["inner"].copy(), st["inner"], v["update"].copy(),
+                         st["update"], v["out"].copy(), st["out"]])
+    _all_equal(a, b)
+    so, sc = np.full(max(cols, 1), 0xC1, np.uint8), np.full(max(cols, 1), 0xC1, np.uint8)
+    orc("ir_initialize", cols, so)
+    cuda("ir_initialize", cols, sc)
+    assert np.array_equal(so, sc) and not so[:cols].any()

@@ -297,6 +297,26 @@ def test_cpp_example_simple_solver():
     assert "converged=1" in r.stdout and "fused=1" in r.stdout
 
 
+@pytest.mark.parametrize("kind,extra", [("ir", dict(relaxation_factor=0.9)), ("chebyshev", dict(foci=(0.4, 1.7)))])
+@pytest.mark.parametrize("vt", ["f64", "f32"])
+def test_zy_ir_and_chebyshev_match_oracle(hexec, kind, extra, vt):
+    """Jacobi-preconditioned Richardson / Chebyshev iteration: no inner products, so the device
+    run follows the oracle (= reference) loop to rounding of the residual norms only"""
+    rp, ci, va = W.laplace(30, 2, vdtype=VT[vt])
+    n = len(rp) - 1
+    rng = np.random.default_rng(6)
+    b = rng.uniform(-1, 1, (n, 1)).astype(VT[vt])
+    x0 = np.zeros((n, 1), VT[vt])
+    jac = ref_jacobi(vt, rp, ci, va, 1, None)
+    red = 1e-4 if vt == "f64" else 1e-3
+    xo, ito, stop_o = H.orc_solve(kind, vt, rp, ci, va, b, x0, 1, jac, max_iters=3000, reduction=red,
+                                  iter_first=1, **extra)
+    xd, itd, stop_d, _ = device_solve(hexec, kind, vt, rp, ci, va, b, x0, 1, None, max_iters=3000,
+                                      reduction=red, iter_first=True, fused=False, **extra)
+    assert abs(itd - ito) <= 2 and stop_d == stop_o[0]
+    assert H.rel_err(xo, xd) <= (1e-10 if vt == "f64" else 1e-4)
+
+
 def test_zz_read_write_csr_files(hexec, orc, tmp_path):
     """gko::read_generic<Csr> / gko::write on the device executor: a file written by the host
     layer is read back into a Csr whose apply matches the oracle (kept last in the suite)."""
