@@ -240,6 +240,103 @@ b200_status chebyshev_update(b200_ctx* ctx, int64_t rows, int64_t cols, double a
     });
 }
 
+// ---- PipeCG (reference/solver/pipe_cg_kernels.cpp:24-160)
+template <typename V>
+b200_status pipe_cg_initialize_1(b200_ctx* ctx, int64_t rows, int64_t cols, const V* b, int64_t bs,
+                                 V* r, int64_t rs, V* prev_rho, uint8_t* stop)
+{
+    B200_REQUIRE(ctx != nullptr, "ctx is null");
+    return launch_ew(ctx, rows + 1, cols, [=] __device__(int64_t i, int64_t j) {
+        if (i == rows) {
+            prev_rho[j] = V(1);
+            stop[j] = 0;
+        } else {
+            r[i * rs + j] = b[i * bs + j];
+        }
+    });
+}
+
+template <typename V>
+b200_status pipe_cg_initialize_2(b200_ctx* ctx, int64_t rows, int64_t cols, V* p, int64_t ps, V* q,
+                                 int64_t qs, V* f, int64_t fs, V* g, int64_t gs, V* beta, const V* z,
+                                 int64_t zs, const V* w, int64_t ws, const V* m, int64_t ms,
+                                 const V* n, int64_t ns, const V* delta)
+{
+    B200_REQUIRE(ctx != nullptr, "ctx is null");
+    return launch_ew(ctx, rows + 1, cols, [=] __device__(int64_t i, int64_t j) {
+        if (i == rows) {
+            beta[j] = delta[j];
+        } else {
+            p[i * ps + j] = z[i * zs + j];
+            q[i * qs + j] = w[i * ws + j];
+            f[i * fs + j] = m[i * ms + j];
+            g[i * gs + j] = n[i * ns + j];
+        }
+    });
+}
+
+template <typename V>
+b200_status pipe_cg_step_1(b200_ctx* ctx, int64_t rows, int64_t cols, V* x, int64_t xs, V* r,
+                           int64_t rs, V* z1, int64_t z1s, V* z2, int64_t z2s, V* w, int64_t ws,
+                           const V* p, int64_t ps, const V* q, int64_t qs, const V* f, int64_t fs,
+                           const V* g, int64_t gs, const V* rho, const V* beta, const uint8_t* stop)
+{
+    return launch_ew(ctx, rows, cols, [=] __device__(int64_t i, int64_t j) {
+        if (has_stopped(stop[j])) return;
+        const V bt = beta[j];
+        if (bt != V(0)) {
+            const V tmp = rho[j] / bt;
+            x[i * xs + j] += tmp * p[i * ps + j];
+            r[i * rs + j] -= tmp * q[i * qs + j];
+            const V z = z1[i * z1s + j] - tmp * f[i * fs + j];
+            z1[i * z1s + j] = z;
+            z2[i * z2s + j] = z;
+            w[i * ws + j] -= tmp * g[i * gs + j];
+        }
+    });
+}
+
+// step_2 rewrites beta (1 x cols) from its own old value, so the scalar update runs first in a
+// tiny launch that also leaves tmp = rho / prev_rho (or the "restart" flag) for the vector pass
+template <typename V>
+b200_status pipe_cg_step_2(b200_ctx* ctx, int64_t rows, int64_t cols, V* beta, V* p, int64_t ps, V* q,
+                           int64_t qs, V* f, int64_t fs, V* g, int64_t gs, const V* z, int64_t zs,
+                           const V* w, int64_t ws, const V* m, int64_t ms, const V* n, int64_t ns,
+                           const V* prev_rho, const V* rho, const V* delta, const uint8_t* stop)
+{
+    B200_REQUIRE(ctx != nullptr, "ctx is null");
+    b200_status st = launch_ew(ctx, 1, cols, [=] __device__(int64_t, int64_t j) {
+        if (has_stopped(stop[j])) return;
+        if (prev_rho[j] != V(0)) {
+            const V tmp = rho[j] / prev_rho[j];
+            const V abs_tmp = tmp < V(0) ? -tmp : tmp;
+            const V sq = abs_tmp * abs_tmp;
+            V bt = delta[j] - sq * beta[j];
+            if (bt == V(0)) bt = delta[j];
+            beta[j] = bt;
+        } else {
+            beta[j] = delta[j];
+        }
+    });
+    if (st != B200_OK) return st;
+    return launch_ew(ctx, rows, cols, [=] __device__(int64_t i, int64_t j) {
+        if (has_stopped(stop[j])) return;
+        const V pr = prev_rho[j];
+        if (pr != V(0)) {
+            const V tmp = rho[j] / pr;
+            p[i * ps + j] = z[i * zs + j] + tmp * p[i * ps + j];
+            q[i * qs + j] = w[i * ws + j] + tmp * q[i * qs + j];
+            f[i * fs + j] = m[i * ms + j] + tmp * f[i * fs + j];
+            g[i * gs + j] = n[i * ns + j] + tmp * g[i * gs + j];
+        } else {
+            p[i * ps + j] = z[i * zs + j];
+            q[i * qs + j] = w[i * ws + j];
+            f[i * fs + j] = m[i * ms + j];
+            g[i * gs + j] = n[i * ns + j];
+        }
+    });
+}
+
 template <typename V>
 b200_status bicgstab_initialize(b200_ctx* ctx, int64_t rows, int64_t cols, const V* b, int64_t bs,
                                 V* r, int64_t rs, V* rr, int64_t rrs, V* y, int64_t ys, V* s,
@@ -461,6 +558,42 @@ b200_status b200_ir_initialize(b200_ctx* ctx, int64_t cols, uint8_t* stop_status
     {                                                                                          \
         return b200::steps::chebyshev_update<VT>(ctx, rows, cols, alpha, beta, inner_sol, is,  \
                                                  update_sol, us, output, os);                  \
+    }                                                                                          \
+    b200_status b200_pipe_cg_initialize_1_##V(b200_ctx* ctx, int64_t rows, int64_t cols,       \
+                                              const VT* b, int64_t bs, VT* r, int64_t rs,      \
+                                              VT* prev_rho, uint8_t* stop)                     \
+    {                                                                                          \
+        return b200::steps::pipe_cg_initialize_1<VT>(ctx, rows, cols, b, bs, r, rs, prev_rho,  \
+                                                     stop);                                    \
+    }                                                                                          \
+    b200_status b200_pipe_cg_initialize_2_##V(                                                 \
+        b200_ctx* ctx, int64_t rows, int64_t cols, VT* p, int64_t ps, VT* q, int64_t qs,       \
+        VT* f, int64_t fs, VT* g, int64_t gs, VT* beta, const VT* z, int64_t zs, const VT* w,  \
+        int64_t ws, const VT* m, int64_t ms, const VT* n, int64_t ns, const VT* delta)         \
+    {                                                                                          \
+        return b200::steps::pipe_cg_initialize_2<VT>(ctx, rows, cols, p, ps, q, qs, f, fs, g,  \
+                                                     gs, beta, z, zs, w, ws, m, ms, n, ns,     \
+                                                     delta);                                   \
+    }                                                                                          \
+    b200_status b200_pipe_cg_step_1_##V(                                                       \
+        b200_ctx* ctx, int64_t rows, int64_t cols, VT* x, int64_t xs, VT* r, int64_t rs,       \
+        VT* z1, int64_t z1s, VT* z2, int64_t z2s, VT* w, int64_t ws, const VT* p, int64_t ps,  \
+        const VT* q, int64_t qs, const VT* f, int64_t fs, const VT* g, int64_t gs,             \
+        const VT* rho, const VT* beta, const uint8_t* stop)                                    \
+    {                                                                                          \
+        return b200::steps::pipe_cg_step_1<VT>(ctx, rows, cols, x, xs, r, rs, z1, z1s, z2,     \
+                                               z2s, w, ws, p, ps, q, qs, f, fs, g, gs, rho,    \
+                                               beta, stop);                                    \
+    }                                                                                          \
+    b200_status b200_pipe_cg_step_2_##V(                                                       \
+        b200_ctx* ctx, int64_t rows, int64_t cols, VT* beta, VT* p, int64_t ps, VT* q,         \
+        int64_t qs, VT* f, int64_t fs, VT* g, int64_t gs, const VT* z, int64_t zs,             \
+        const VT* w, int64_t ws, const VT* m, int64_t ms, const VT* n, int64_t ns,             \
+        const VT* prev_rho, const VT* rho, const VT* delta, const uint8_t* stop)               \
+    {                                                                                          \
+        return b200::steps::pipe_cg_step_2<VT>(ctx, rows, cols, beta, p, ps, q, qs, f, fs, g,  \
+                                               gs, z, zs, w, ws, m, ms, n, ns, prev_rho, rho,  \
+                                               delta, stop);                                   \
     }                                                                                          \
     b200_status b200_bicgstab_initialize_##V(                                                  \
         b200_ctx* ctx, int64_t rows, int64_t cols, const VT* b, int64_t bs, VT* r, int64_t rs, \

@@ -84,6 +84,12 @@ std::unique_ptr<LinOp> make_solver(std::shared_ptr<Executor> exec, int kind,
         if (pre) f.with_preconditioner(pre);
         return f.on(exec)->generate(A);
     }
+    if (kind == 7) {
+        auto f = solver::PipeCg<V>::build();
+        f.with_criteria(crit);
+        if (pre) f.with_preconditioner(pre);
+        return f.on(exec)->generate(A);
+    }
     if (kind == 5) {
         auto f = solver::Ir<V>::build();
         f.with_criteria(crit).with_relaxation_factor((V)g_relaxation);

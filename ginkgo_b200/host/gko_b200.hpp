@@ -82,6 +82,10 @@ struct viabi;
         static constexpr auto cgs_step_1 = b200_cgs_step_1_##S;                                 \
         static constexpr auto cgs_step_2 = b200_cgs_step_2_##S;                                 \
         static constexpr auto cgs_step_3 = b200_cgs_step_3_##S;                                 \
+        static constexpr auto pipe_cg_initialize_1 = b200_pipe_cg_initialize_1_##S;             \
+        static constexpr auto pipe_cg_initialize_2 = b200_pipe_cg_initialize_2_##S;             \
+        static constexpr auto pipe_cg_step_1 = b200_pipe_cg_step_1_##S;                         \
+        static constexpr auto pipe_cg_step_2 = b200_pipe_cg_step_2_##S;                         \
         static constexpr auto chebyshev_init_update = b200_chebyshev_init_update_##S;           \
         static constexpr auto chebyshev_update = b200_chebyshev_update_##S;                     \
         static constexpr auto bicgstab_initialize = b200_bicgstab_initialize_##S;               \

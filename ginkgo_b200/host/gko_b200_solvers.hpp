@@ -913,6 +913,95 @@ protected:
     }
 };
 // ---------------------------------------------------------------------------------------------
+// solver::PipeCg (core/solver/pipe_cg.cpp:95-285): pipelined CG, one reduction point per
+// iteration (rho = r.z and delta = w.z together).  The reference stores (r | w), (z1 | z2)
+// side by side to get both with ONE compute_conj_dot; every column of that dot is an
+// independent sum, so the two dots issued here return the same values.
+// ---------------------------------------------------------------------------------------------
+template <typename V>
+class PipeCg : public SolverBase<V> {
+    using Base = SolverBase<V>;
+    using Dense = matrix::Dense<V>;
+
+public:
+    struct Factory : SolverFactoryBase<Factory> {
+        std::unique_ptr<LinOp> generate(std::shared_ptr<const LinOp> op) const override
+        {
+            auto exec = this->exec_ ? this->exec_ : op->get_executor();
+            return std::unique_ptr<LinOp>(new PipeCg(exec, *this, op));
+        }
+    };
+    static Factory build() { return Factory{}; }
+
+protected:
+    PipeCg(std::shared_ptr<const Executor> exec, const Factory& f, std::shared_ptr<const LinOp> op)
+        : Base(exec, f, op)
+    {}
+    using Base::apply_impl;
+    void apply_impl(const LinOp* lb, LinOp* lx) const override
+    {
+        auto b = as<Dense>(lb);
+        auto x = as<Dense>(lx);
+        auto exec = this->exec_;
+        auto ctx = exec->ctx();
+        const dim2 sz = b->get_size();
+        const size_type nrhs = sz.cols;
+        auto mk = [&] { return Dense::create(exec, sz); };
+        auto sc = [&] { return Dense::create(exec, dim2{1, nrhs}); };
+        auto r = mk(), w = mk(), z1 = mk(), z2 = mk(), p = mk(), m = mk(), n = mk(), q = mk(), f = mk(),
+             g = mk();
+        auto rho = sc(), delta = sc(), beta = sc(), prev_rho = sc();
+        array<uint8> stop_status(exec, nrhs);
+        bool one_changed = false;
+        GKOB_CALL(vabi<V>::pipe_cg_initialize_1(ctx, sz.rows, nrhs, GKOB_CVS(b), GKOB_VS(r),
+                                                prev_rho->get_values(), stop_status.get_data()));
+        this->system_matrix_->apply(this->neg_one_.get(), x, this->one_.get(), r.get());
+        this->preconditioner_->apply(r.get(), z1.get());
+        z2->copy_from(z1.get());
+        this->system_matrix_->apply(z1.get(), w.get());
+        this->preconditioner_->apply(w.get(), m.get());
+        this->system_matrix_->apply(m.get(), n.get());
+        r->compute_conj_dot(z1.get(), rho.get());
+        w->compute_conj_dot(z2.get(), delta.get());
+        stop::CriterionArgs args{this->system_matrix_, b, x, r.get()};
+        auto crit = stop::combine_and_generate(this->criteria_, exec, args);
+        int64 iter = 0;
+        auto check = [&] {
+            stop::Updater u;
+            u.num_iterations = iter;
+            u.residual = r.get();
+            u.implicit_sq_residual_norm = rho.get();
+            u.solution = x;
+            return crit->check(1, true, &stop_status, &one_changed, u);
+        };
+        if (!check()) {
+            GKOB_CALL(vabi<V>::pipe_cg_initialize_2(
+                ctx, sz.rows, nrhs, GKOB_VS(p), GKOB_VS(q), GKOB_VS(f), GKOB_VS(g), beta->get_values(),
+                GKOB_CVS(z1), GKOB_CVS(w), GKOB_CVS(m), GKOB_CVS(n), delta->get_const_values()));
+            while (true) {
+                GKOB_CALL(vabi<V>::pipe_cg_step_1(
+                    ctx, sz.rows, nrhs, GKOB_VS(x), GKOB_VS(r), GKOB_VS(z1), GKOB_VS(z2), GKOB_VS(w),
+                    GKOB_CVS(p), GKOB_CVS(q), GKOB_CVS(f), GKOB_CVS(g), rho->get_const_values(),
+                    beta->get_const_values(), stop_status.get_const_data()));
+                this->preconditioner_->apply(w.get(), m.get());
+                this->system_matrix_->apply(m.get(), n.get());
+                prev_rho->copy_from(rho.get());
+                r->compute_conj_dot(z1.get(), rho.get());
+                w->compute_conj_dot(z2.get(), delta.get());
+                ++iter;
+                if (check()) break;
+                GKOB_CALL(vabi<V>::pipe_cg_step_2(
+                    ctx, sz.rows, nrhs, beta->get_values(), GKOB_VS(p), GKOB_VS(q), GKOB_VS(f),
+                    GKOB_VS(g), GKOB_CVS(z1), GKOB_CVS(w), GKOB_CVS(m), GKOB_CVS(n),
+                    prev_rho->get_const_values(), rho->get_const_values(),
+                    delta->get_const_values(), stop_status.get_const_data()));
+            }
+        }
+        this->record(iter, stop_status);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
 // solver::Ir (core/solver/ir.cpp:192-258): x += relaxation_factor * inner_solver(b - A x).
 // The inner solver is the `with_solver` / preconditioner slot of the factory (Identity by
 // default, which gives Richardson iteration).  default_initial_guess = provided.

@@ -360,6 +360,29 @@ b200_status b200_jacobi_find_blocks_i64(b200_ctx* ctx, int64_t num_rows, const i
                                           int64_t update_stride, VT* output,                  \
                                           int64_t output_stride);                             \
                                                                                               \
+    /* PipeCG (core/solver/pipe_cg_kernels.hpp; reference/solver/pipe_cg_kernels.cpp:24-160) */ \
+    b200_status b200_pipe_cg_initialize_1_##V(b200_ctx* ctx, int64_t rows, int64_t cols,      \
+                                              const VT* b, int64_t b_stride, VT* r,           \
+                                              int64_t r_stride, VT* prev_rho,                 \
+                                              uint8_t* stop_status);                          \
+    b200_status b200_pipe_cg_initialize_2_##V(                                                \
+        b200_ctx* ctx, int64_t rows, int64_t cols, VT* p, int64_t p_stride, VT* q,            \
+        int64_t q_stride, VT* f, int64_t f_stride, VT* g, int64_t g_stride, VT* beta,         \
+        const VT* z, int64_t z_stride, const VT* w, int64_t w_stride, const VT* m,            \
+        int64_t m_stride, const VT* n, int64_t n_stride, const VT* delta);                    \
+    b200_status b200_pipe_cg_step_1_##V(                                                      \
+        b200_ctx* ctx, int64_t rows, int64_t cols, VT* x, int64_t x_stride, VT* r,            \
+        int64_t r_stride, VT* z1, int64_t z1_stride, VT* z2, int64_t z2_stride, VT* w,        \
+        int64_t w_stride, const VT* p, int64_t p_stride, const VT* q, int64_t q_stride,       \
+        const VT* f, int64_t f_stride, const VT* g, int64_t g_stride, const VT* rho,          \
+        const VT* beta, const uint8_t* stop_status);                                          \
+    b200_status b200_pipe_cg_step_2_##V(                                                      \
+        b200_ctx* ctx, int64_t rows, int64_t cols, VT* beta, VT* p, int64_t p_stride, VT* q,  \
+        int64_t q_stride, VT* f, int64_t f_stride, VT* g, int64_t g_stride, const VT* z,      \
+        int64_t z_stride, const VT* w, int64_t w_stride, const VT* m, int64_t m_stride,       \
+        const VT* n, int64_t n_stride, const VT* prev_rho, const VT* rho, const VT* delta,    \
+        const uint8_t* stop_status);                                                          \
+                                                                                              \
     b200_status b200_bicgstab_initialize_##V(                                                 \
         b200_ctx* ctx, int64_t rows, int64_t cols, const VT* b, int64_t b_stride, VT* r,      \
         int64_t r_stride, VT* rr, int64_t rr_stride, VT* y, int64_t y_stride, VT* s,          \

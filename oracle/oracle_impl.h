@@ -314,6 +314,79 @@ void FN(chebyshev_update)(int64_t rows, int64_t cols, double alpha, double beta,
         }
 }
 
+/* reference/solver/pipe_cg_kernels.cpp:24-160 */
+void FN(pipe_cg_initialize_1)(int64_t rows, int64_t cols, const V* b, int64_t bs, V* r, int64_t rs,
+                              V* prev_rho, uint8_t* stop)
+{
+    for (int64_t j = 0; j < cols; ++j) {
+        prev_rho[j] = 1;
+        stop[j] = 0;
+    }
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) r[i * rs + j] = b[i * bs + j];
+}
+void FN(pipe_cg_initialize_2)(int64_t rows, int64_t cols, V* p, int64_t ps, V* q, int64_t qs, V* f,
+                              int64_t fs, V* g, int64_t gs, V* beta, const V* z, int64_t zs,
+                              const V* w, int64_t ws, const V* m, int64_t ms, const V* n, int64_t ns,
+                              const V* delta)
+{
+    for (int64_t j = 0; j < cols; ++j) beta[j] = delta[j];
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) {
+            p[i * ps + j] = z[i * zs + j];
+            q[i * qs + j] = w[i * ws + j];
+            f[i * fs + j] = m[i * ms + j];
+            g[i * gs + j] = n[i * ns + j];
+        }
+}
+void FN(pipe_cg_step_1)(int64_t rows, int64_t cols, V* x, int64_t xs, V* r, int64_t rs, V* z1,
+                        int64_t z1s, V* z2, int64_t z2s, V* w, int64_t ws, const V* p, int64_t ps,
+                        const V* q, int64_t qs, const V* f, int64_t fs, const V* g, int64_t gs,
+                        const V* rho, const V* beta, const uint8_t* stop)
+{
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) {
+            if (st_has_stopped(stop[j])) continue;
+            if (beta[j] != 0) {
+                V tmp = rho[j] / beta[j];
+                x[i * xs + j] += tmp * p[i * ps + j];
+                r[i * rs + j] -= tmp * q[i * qs + j];
+                z1[i * z1s + j] -= tmp * f[i * fs + j];
+                z2[i * z2s + j] = z1[i * z1s + j];
+                w[i * ws + j] -= tmp * g[i * gs + j];
+            }
+        }
+}
+void FN(pipe_cg_step_2)(int64_t rows, int64_t cols, V* beta, V* p, int64_t ps, V* q, int64_t qs, V* f,
+                        int64_t fs, V* g, int64_t gs, const V* z, int64_t zs, const V* w, int64_t ws,
+                        const V* m, int64_t ms, const V* n, int64_t ns, const V* prev_rho,
+                        const V* rho, const V* delta, const uint8_t* stop)
+{
+    for (int64_t j = 0; j < cols; ++j) {
+        if (st_has_stopped(stop[j])) continue;
+        if (prev_rho[j] != 0) {
+            V tmp = rho[j] / prev_rho[j];
+            V abs_tmp = FABS(tmp);
+            beta[j] = delta[j] - abs_tmp * abs_tmp * beta[j];
+            if (beta[j] == 0) beta[j] = delta[j];
+            for (int64_t i = 0; i < rows; ++i) {
+                p[i * ps + j] = z[i * zs + j] + tmp * p[i * ps + j];
+                q[i * qs + j] = w[i * ws + j] + tmp * q[i * qs + j];
+                f[i * fs + j] = m[i * ms + j] + tmp * f[i * fs + j];
+                g[i * gs + j] = n[i * ns + j] + tmp * g[i * gs + j];
+            }
+        } else {
+            beta[j] = delta[j];
+            for (int64_t i = 0; i < rows; ++i) {
+                p[i * ps + j] = z[i * zs + j];
+                q[i * qs + j] = w[i * ws + j];
+                f[i * fs + j] = m[i * ms + j];
+                g[i * gs + j] = n[i * ns + j];
+            }
+        }
+    }
+}
+
 /* reference/solver/bicgstab_kernels.cpp:25-60 */
 void FN(bicgstab_initialize)(int64_t rows, int64_t cols, const V* b, int64_t bs, V* r, int64_t rs,
                              V* rr, int64_t rrs, V* y, int64_t ys, V* s, int64_t ss, V* t,

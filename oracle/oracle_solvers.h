@@ -363,6 +363,59 @@ int64_t FN(chebyshev_solve)(int64_t n, int64_t cols, const int32_t* rp, const in
     return iter;
 }
 
+/* core/solver/pipe_cg.cpp:95-285.  The reference stores (r | w), (z1 | z2) and (rho | delta) side
+ * by side so that ONE compute_conj_dot yields rho = r.z1 and delta = w.z2; every column of that
+ * dot is an independent row-ordered sum, so two separate dots give the same bits. */
+int64_t FN(pipe_cg_solve)(int64_t n, int64_t cols, const int32_t* rp, const int32_t* ci, const V* va,
+                          const V* b, V* x, const orc_solver_cfg* cfg, uint8_t* stop_out,
+                          V* resnorm_out)
+{
+    FN(sctx) s = {n, cols, rp, ci, va, cfg, NULL, NULL};
+    const size_t nb = sizeof(V) * n * cols;
+    V *r = malloc(nb), *w = malloc(nb), *z1 = malloc(nb), *z2 = malloc(nb), *p = malloc(nb),
+      *m = malloc(nb), *nn = malloc(nb), *q = malloc(nb), *f = malloc(nb), *g = malloc(nb);
+    V* sc = malloc(sizeof(V) * cols * 4);
+    V *rho = sc, *delta = sc + cols, *beta = sc + 2 * cols, *prev_rho = sc + 3 * cols;
+    s.starting_tau = malloc(sizeof(V) * cols);
+    s.u_tau = malloc(sizeof(V) * cols);
+    uint8_t* stop = malloc(cols);
+    const V one = 1, neg_one = -1;
+    int one_changed;
+    FN(pipe_cg_initialize_1)(n, cols, b, cols, r, cols, prev_rho, stop);
+    FN(s_apply_A)(&s, &neg_one, x, &one, r);
+    FN(s_apply_M)(&s, r, z1);
+    memcpy(z2, z1, nb);
+    FN(s_apply_A)(&s, NULL, z1, NULL, w);
+    FN(s_apply_M)(&s, w, m);
+    FN(s_apply_A)(&s, NULL, m, NULL, nn);
+    FN(dense_compute_dot)(n, cols, r, cols, z1, cols, rho);
+    FN(dense_compute_dot)(n, cols, w, cols, z2, cols, delta);
+    FN(s_criterion_generate)(&s, b, r);
+    int64_t iter = 0;
+    if (!FN(s_check)(&s, iter, r, NULL, rho, 1, stop, &one_changed)) {
+        FN(pipe_cg_initialize_2)(n, cols, p, cols, q, cols, f, cols, g, cols, beta, z1, cols, w, cols, m,
+                                 cols, nn, cols, delta);
+        while (1) {
+            FN(pipe_cg_step_1)(n, cols, x, cols, r, cols, z1, cols, z2, cols, w, cols, p, cols, q, cols,
+                               f, cols, g, cols, rho, beta, stop);
+            FN(s_apply_M)(&s, w, m);
+            FN(s_apply_A)(&s, NULL, m, NULL, nn);
+            memcpy(prev_rho, rho, sizeof(V) * cols);
+            FN(dense_compute_dot)(n, cols, r, cols, z1, cols, rho);
+            FN(dense_compute_dot)(n, cols, w, cols, z2, cols, delta);
+            ++iter;
+            if (FN(s_check)(&s, iter, r, NULL, rho, 1, stop, &one_changed)) break;
+            FN(pipe_cg_step_2)(n, cols, beta, p, cols, q, cols, f, cols, g, cols, z1, cols, w, cols, m,
+                               cols, nn, cols, prev_rho, rho, delta, stop);
+        }
+    }
+    if (stop_out) memcpy(stop_out, stop, cols);
+    if (resnorm_out) FN(dense_compute_norm2)(n, cols, r, cols, resnorm_out);
+    free(r); free(w); free(z1); free(z2); free(p); free(m); free(nn); free(q); free(f); free(g);
+    free(sc); free(s.starting_tau); free(s.u_tau); free(stop);
+    return iter;
+}
+
 /* core/solver/bicgstab.cpp:95-233 */
 int64_t FN(bicgstab_solve)(int64_t n, int64_t cols, const int32_t* rp, const int32_t* ci,
                            const V* va, const V* b, V* x, const orc_solver_cfg* cfg,

@@ -783,3 +783,37 @@ def test_ir_and_chebyshev_kernels(orc, cuda, vt, rows, cols):
     orc("ir_initialize", cols, so)
     cuda("ir_initialize", cols, sc)
     assert np.array_equal(so, sc) and not so[:cols].any()
+
+
+@pytest.mark.parametrize("vt", VTS)
+@pytest.mark.parametrize("rows,cols", [(597, 43), (100001, 1), (0, 2)])
+def test_pipe_cg_steps(orc, cuda, vt, rows, cols):
+    rng = np.random.default_rng(93)
+    names = ("b", "r", "z1", "z2", "w", "p", "q", "f", "g", "m", "n", "x")
+    st = {k: cols + (i % 3) for i, k in enumerate(names)}
+    v = {k: H.dense(rng, rows, cols, s, vt) for k, s in st.items()}
+    sc = {k: rng.uniform(0.5, 1, cols).astype(VT[vt]) for k in ("rho", "prev_rho", "beta", "delta")}
+    stop = np.zeros(cols, dtype=np.uint8)
+    if cols > 4:
+        sc["prev_rho"][2] = 0
+        sc["beta"][3] = 0
+        stop[1] = 1 | 0x40
+        # a column whose updated beta is exactly zero: beta = delta - |rho/prev_rho|^2 * beta
+        sc["rho"][4], sc["prev_rho"][4], sc["beta"][4], sc["delta"][4] = 2.0, 1.0, 0.25, 1.0
+    a, b = both(orc, cuda, "pipe_cg_initialize_1_" + vt,
+                lambda: [rows, cols, v["b"], st["b"], v["r"].copy(), st["r"], sc["prev_rho"].copy(),
+                         np.full(cols, 0x81, np.uint8)])
+    _all_equal(a, b)
+    a, b = both(orc, cuda, "pipe_cg_initialize_2_" + vt,
+                lambda: [rows, cols] + sum([[v[k].copy(), st[k]] for k in ("p", "q", "f", "g")], []) +
+                [sc["beta"].copy()] + sum([[v[k], st[k]] for k in ("z1", "w", "m", "n")], []) + [sc["delta"]])
+    _all_equal(a, b)
+    a, b = both(orc, cuda, "pipe_cg_step_1_" + vt,
+                lambda: [rows, cols] + sum([[v[k].copy(), st[k]] for k in ("x", "r", "z1", "z2", "w")], []) +
+                sum([[v[k], st[k]] for k in ("p", "q", "f", "g")], []) + [sc["rho"], sc["beta"], stop])
+    _all_equal(a, b)
+    a, b = both(orc, cuda, "pipe_cg_step_2_" + vt,
+                lambda: [rows, cols, sc["beta"].copy()] + sum([[v[k].copy(), st[k]] for k in ("p", "q", "f", "g")], []) +
+                sum([[v[k], st[k]] for k in ("z1", "w", "m", "n")], []) +
+                [sc["prev_rho"], sc["rho"], sc["delta"], stop])
+    _all_equal(a, b)
