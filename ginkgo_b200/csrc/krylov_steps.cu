@@ -337,6 +337,53 @@ b200_status pipe_cg_step_2(b200_ctx* ctx, int64_t rows, int64_t cols, V* beta, V
     });
 }
 
+// ---- GCR (reference/solver/gcr_kernels.cpp:26-84); the orthogonalisation itself is built from
+// the Dense kernels (dot, squared_norm2, inv_scale, sub_scaled) by the host loop, as in the reference
+template <typename V>
+b200_status gcr_initialize(b200_ctx* ctx, int64_t rows, int64_t cols, const V* b, int64_t bs,
+                           V* residual, int64_t rs, uint8_t* stop)
+{
+    B200_REQUIRE(ctx != nullptr, "ctx is null");
+    return launch_ew(ctx, rows + 1, cols, [=] __device__(int64_t i, int64_t j) {
+        if (i == rows)
+            stop[j] = 0;
+        else
+            residual[i * rs + j] = b[i * bs + j];
+    });
+}
+
+template <typename V>
+b200_status gcr_restart(b200_ctx* ctx, int64_t rows, int64_t cols, const V* residual, int64_t rs,
+                        const V* a_residual, int64_t ars, V* p_bases, int64_t ps, V* ap_bases,
+                        int64_t aps, uint64_t* final_iter_nums)
+{
+    B200_REQUIRE(ctx != nullptr, "ctx is null");
+    return launch_ew(ctx, rows + 1, cols, [=] __device__(int64_t i, int64_t j) {
+        if (i == rows) {
+            final_iter_nums[j] = 0;
+        } else {
+            p_bases[i * ps + j] = residual[i * rs + j];
+            ap_bases[i * aps + j] = a_residual[i * ars + j];
+        }
+    });
+}
+
+template <typename V>
+b200_status gcr_step_1(b200_ctx* ctx, int64_t rows, int64_t cols, V* x, int64_t xs, V* residual,
+                       int64_t rs, const V* p, int64_t ps, const V* ap, int64_t aps,
+                       const V* ap_norm, const V* rap, const uint8_t* stop)
+{
+    return launch_ew(ctx, rows, cols, [=] __device__(int64_t i, int64_t j) {
+        if (has_stopped(stop[j])) return;
+        const V an = ap_norm[j];
+        if (an != V(0)) {
+            const V tmp = rap[j] / an;
+            x[i * xs + j] += tmp * p[i * ps + j];
+            residual[i * rs + j] -= tmp * ap[i * aps + j];
+        }
+    });
+}
+
 template <typename V>
 b200_status bicgstab_initialize(b200_ctx* ctx, int64_t rows, int64_t cols, const V* b, int64_t bs,
                                 V* r, int64_t rs, V* rr, int64_t rrs, V* y, int64_t ys, V* s,
@@ -594,6 +641,28 @@ b200_status b200_ir_initialize(b200_ctx* ctx, int64_t cols, uint8_t* stop_status
         return b200::steps::pipe_cg_step_2<VT>(ctx, rows, cols, beta, p, ps, q, qs, f, fs, g,  \
                                                gs, z, zs, w, ws, m, ms, n, ns, prev_rho, rho,  \
                                                delta, stop);                                   \
+    }                                                                                          \
+    b200_status b200_gcr_initialize_##V(b200_ctx* ctx, int64_t rows, int64_t cols,             \
+                                        const VT* b, int64_t bs, VT* residual, int64_t rs,     \
+                                        uint8_t* stop)                                         \
+    {                                                                                          \
+        return b200::steps::gcr_initialize<VT>(ctx, rows, cols, b, bs, residual, rs, stop);    \
+    }                                                                                          \
+    b200_status b200_gcr_restart_##V(b200_ctx* ctx, int64_t rows, int64_t cols,                \
+                                     const VT* residual, int64_t rs, const VT* a_residual,     \
+                                     int64_t ars, VT* p_bases, int64_t ps, VT* ap_bases,       \
+                                     int64_t aps, uint64_t* final_iter_nums)                   \
+    {                                                                                          \
+        return b200::steps::gcr_restart<VT>(ctx, rows, cols, residual, rs, a_residual, ars,    \
+                                            p_bases, ps, ap_bases, aps, final_iter_nums);      \
+    }                                                                                          \
+    b200_status b200_gcr_step_1_##V(b200_ctx* ctx, int64_t rows, int64_t cols, VT* x,          \
+                                    int64_t xs, VT* residual, int64_t rs, const VT* p,         \
+                                    int64_t ps, const VT* ap, int64_t aps, const VT* ap_norm,  \
+                                    const VT* rap, const uint8_t* stop)                        \
+    {                                                                                          \
+        return b200::steps::gcr_step_1<VT>(ctx, rows, cols, x, xs, residual, rs, p, ps, ap,    \
+                                           aps, ap_norm, rap, stop);                           \
     }                                                                                          \
     b200_status b200_bicgstab_initialize_##V(                                                  \
         b200_ctx* ctx, int64_t rows, int64_t cols, const VT* b, int64_t bs, VT* r, int64_t rs, \

@@ -1002,6 +1002,115 @@ protected:
 };
 
 // ---------------------------------------------------------------------------------------------
+// solver::Gcr (core/solver/gcr.cpp:99-292): generalised conjugate residual with restarts; the
+// modified Gram-Schmidt on the A p_i bases is built from the Dense kernels as in the reference.
+// ---------------------------------------------------------------------------------------------
+template <typename V>
+class Gcr : public SolverBase<V> {
+    using Base = SolverBase<V>;
+    using Dense = matrix::Dense<V>;
+
+public:
+    struct Factory : SolverFactoryBase<Factory> {
+        size_type krylov_dim_ = 100;  // gcr_default_krylov_dim (include/ginkgo/core/solver/gcr.hpp)
+        Factory& with_krylov_dim(size_type k)
+        {
+            krylov_dim_ = k;
+            return *this;
+        }
+        std::unique_ptr<LinOp> generate(std::shared_ptr<const LinOp> op) const override
+        {
+            auto exec = this->exec_ ? this->exec_ : op->get_executor();
+            return std::unique_ptr<LinOp>(new Gcr(exec, *this, op));
+        }
+    };
+    static Factory build() { return Factory{}; }
+    size_type get_krylov_dim() const { return krylov_dim_; }
+
+protected:
+    Gcr(std::shared_ptr<const Executor> exec, const Factory& f, std::shared_ptr<const LinOp> op)
+        : Base(exec, f, op), krylov_dim_(f.krylov_dim_ ? f.krylov_dim_ : 100)
+    {}
+    using Base::apply_impl;
+    void apply_impl(const LinOp* lb, LinOp* lx) const override
+    {
+        auto b = as<Dense>(lb);
+        auto x = as<Dense>(lx);
+        auto exec = this->exec_;
+        auto ctx = exec->ctx();
+        const dim2 sz = b->get_size();
+        const size_type n = sz.rows, nrhs = sz.cols, kd = krylov_dim_;
+        auto residual = Dense::create(exec, sz), precon_residual = Dense::create(exec, sz),
+             a_precon_residual = Dense::create(exec, sz);
+        auto p_bases = Dense::create(exec, dim2{n * (kd + 1), nrhs});
+        auto ap_bases = Dense::create(exec, dim2{n * (kd + 1), nrhs});
+        auto tmp_rap = Dense::create(exec, dim2{1, nrhs}), tmp_minus_beta = Dense::create(exec, dim2{1, nrhs}),
+             residual_norm = Dense::create(exec, dim2{1, nrhs});
+        auto ap_norms = Dense::create(exec, dim2{kd + 1, nrhs});
+        array<std::uint64_t> final_iter_nums(exec, nrhs);
+        array<uint8> stop_status(exec, nrhs);
+        bool one_changed = false;
+        GKOB_CALL(vabi<V>::gcr_initialize(ctx, n, nrhs, GKOB_CVS(b), GKOB_VS(residual),
+                                          stop_status.get_data()));
+        this->system_matrix_->apply(this->neg_one_.get(), x, this->one_.get(), residual.get());
+        this->preconditioner_->apply(residual.get(), precon_residual.get());
+        this->system_matrix_->apply(precon_residual.get(), a_precon_residual.get());
+        auto restart = [&] {
+            GKOB_CALL(vabi<V>::gcr_restart(ctx, n, nrhs, GKOB_CVS(precon_residual),
+                                           GKOB_CVS(a_precon_residual), GKOB_VS(p_bases),
+                                           GKOB_VS(ap_bases), final_iter_nums.get_data()));
+        };
+        restart();
+        stop::CriterionArgs args{this->system_matrix_, b, x, residual.get()};
+        auto crit = stop::combine_and_generate(this->criteria_, exec, args);
+        int64 total_iter = -1;
+        size_type restart_iter = 0;
+        while (true) {
+            ++total_iter;
+            residual->compute_norm2(residual_norm.get());
+            stop::Updater u;
+            u.num_iterations = total_iter;
+            u.residual = residual.get();
+            u.residual_norm = residual_norm.get();
+            u.solution = x;
+            if (crit->check(1, true, &stop_status, &one_changed, u)) break;
+            if (restart_iter == kd) {
+                restart();
+                restart_iter = 0;
+            }
+            auto ap = ap_bases->create_submatrix_rows(n * restart_iter, n * (restart_iter + 1));
+            auto p = p_bases->create_submatrix_rows(n * restart_iter, n * (restart_iter + 1));
+            residual->compute_conj_dot(ap.get(), tmp_rap.get());
+            auto ap_norm = ap_norms->create_submatrix_rows(restart_iter, restart_iter + 1);
+            ap->compute_squared_norm2(ap_norm.get());
+            GKOB_CALL(vabi<V>::gcr_step_1(ctx, n, nrhs, GKOB_VS(x), GKOB_VS(residual), GKOB_CVS(p),
+                                          GKOB_CVS(ap), ap_norm->get_const_values(),
+                                          tmp_rap->get_const_values(), stop_status.get_const_data()));
+            this->preconditioner_->apply(residual.get(), precon_residual.get());
+            this->system_matrix_->apply(precon_residual.get(), a_precon_residual.get());
+            auto next_ap = ap_bases->create_submatrix_rows(n * (restart_iter + 1), n * (restart_iter + 2));
+            auto next_p = p_bases->create_submatrix_rows(n * (restart_iter + 1), n * (restart_iter + 2));
+            next_ap->copy_from(a_precon_residual.get());
+            next_p->copy_from(precon_residual.get());
+            for (size_type i = 0; i <= restart_iter; ++i) {
+                auto api = ap_bases->create_submatrix_rows(n * i, n * (i + 1));
+                auto pi = p_bases->create_submatrix_rows(n * i, n * (i + 1));
+                auto ni = ap_norms->create_submatrix_rows(i, i + 1);
+                a_precon_residual->compute_conj_dot(api.get(), tmp_minus_beta.get());
+                tmp_minus_beta->inv_scale(ni.get());
+                next_ap->sub_scaled(tmp_minus_beta.get(), api.get());
+                next_p->sub_scaled(tmp_minus_beta.get(), pi.get());
+            }
+            ++restart_iter;
+        }
+        this->record(total_iter, stop_status);
+    }
+
+private:
+    size_type krylov_dim_;
+};
+
+// ---------------------------------------------------------------------------------------------
 // solver::Ir (core/solver/ir.cpp:192-258): x += relaxation_factor * inner_solver(b - A x).
 // The inner solver is the `with_solver` / preconditioner slot of the factory (Identity by
 // default, which gives Richardson iteration).  default_initial_guess = provided.

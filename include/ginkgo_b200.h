@@ -383,6 +383,21 @@ b200_status b200_jacobi_find_blocks_i64(b200_ctx* ctx, int64_t num_rows, const i
         const VT* n, int64_t n_stride, const VT* prev_rho, const VT* rho, const VT* delta,    \
         const uint8_t* stop_status);                                                          \
                                                                                               \
+    /* GCR (core/solver/gcr_kernels.hpp; reference/solver/gcr_kernels.cpp:26-84) */           \
+    b200_status b200_gcr_initialize_##V(b200_ctx* ctx, int64_t rows, int64_t cols,            \
+                                        const VT* b, int64_t b_stride, VT* residual,          \
+                                        int64_t residual_stride, uint8_t* stop_status);       \
+    b200_status b200_gcr_restart_##V(b200_ctx* ctx, int64_t rows, int64_t cols,               \
+                                     const VT* residual, int64_t residual_stride,             \
+                                     const VT* a_residual, int64_t a_residual_stride,         \
+                                     VT* p_bases, int64_t p_stride, VT* ap_bases,             \
+                                     int64_t ap_stride, uint64_t* final_iter_nums);           \
+    b200_status b200_gcr_step_1_##V(b200_ctx* ctx, int64_t rows, int64_t cols, VT* x,         \
+                                    int64_t x_stride, VT* residual, int64_t residual_stride,  \
+                                    const VT* p, int64_t p_stride, const VT* ap,              \
+                                    int64_t ap_stride, const VT* ap_norm, const VT* rap,      \
+                                    const uint8_t* stop_status);                              \
+                                                                                              \
     b200_status b200_bicgstab_initialize_##V(                                                 \
         b200_ctx* ctx, int64_t rows, int64_t cols, const VT* b, int64_t b_stride, VT* r,      \
         int64_t r_stride, VT* rr, int64_t rr_stride, VT* y, int64_t y_stride, VT* s,          \

@@ -387,6 +387,42 @@ void FN(pipe_cg_step_2)(int64_t rows, int64_t cols, V* beta, V* p, int64_t ps, V
     }
 }
 
+/* reference/solver/gcr_kernels.cpp:26-84 */
+void FN(gcr_initialize)(int64_t rows, int64_t cols, const V* b, int64_t bs, V* residual, int64_t rs,
+                        uint8_t* stop)
+{
+    for (int64_t j = 0; j < cols; ++j) {
+        for (int64_t i = 0; i < rows; ++i) residual[i * rs + j] = b[i * bs + j];
+        stop[j] = 0;
+    }
+}
+void FN(gcr_restart)(int64_t rows, int64_t cols, const V* residual, int64_t rs, const V* a_residual,
+                     int64_t ars, V* p_bases, int64_t ps, V* ap_bases, int64_t aps,
+                     uint64_t* final_iter_nums)
+{
+    for (int64_t j = 0; j < cols; ++j) {
+        for (int64_t i = 0; i < rows; ++i) {
+            p_bases[i * ps + j] = residual[i * rs + j];
+            ap_bases[i * aps + j] = a_residual[i * ars + j];
+        }
+        final_iter_nums[j] = 0;
+    }
+}
+void FN(gcr_step_1)(int64_t rows, int64_t cols, V* x, int64_t xs, V* residual, int64_t rs, const V* p,
+                    int64_t ps, const V* ap, int64_t aps, const V* ap_norm, const V* rap,
+                    const uint8_t* stop)
+{
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) {
+            if (st_has_stopped(stop[j])) continue;
+            if (ap_norm[j] != 0) {
+                V tmp = rap[j] / ap_norm[j];
+                x[i * xs + j] += tmp * p[i * ps + j];
+                residual[i * rs + j] -= tmp * ap[i * aps + j];
+            }
+        }
+}
+
 /* reference/solver/bicgstab_kernels.cpp:25-60 */
 void FN(bicgstab_initialize)(int64_t rows, int64_t cols, const V* b, int64_t bs, V* r, int64_t rs,
                              V* rr, int64_t rrs, V* y, int64_t ys, V* s, int64_t ss, V* t,

@@ -416,6 +416,70 @@ int64_t FN(pipe_cg_solve)(int64_t n, int64_t cols, const int32_t* rp, const int3
     return iter;
 }
 
+/* core/solver/gcr.cpp:99-292 */
+int64_t FN(gcr_solve)(int64_t n, int64_t cols, const int32_t* rp, const int32_t* ci, const V* va,
+                      const V* b, V* x, const orc_solver_cfg* cfg, uint8_t* stop_out,
+                      V* resnorm_out)
+{
+    FN(sctx) s = {n, cols, rp, ci, va, cfg, NULL, NULL};
+    const int64_t kd = cfg->krylov_dim;
+    const size_t nb = sizeof(V) * n * cols;
+    V *residual = malloc(nb), *precon = malloc(nb), *a_precon = malloc(nb);
+    V *pb = malloc(nb * (kd + 1)), *apb = malloc(nb * (kd + 1));
+    V *rap = malloc(sizeof(V) * cols), *minus_beta = malloc(sizeof(V) * cols),
+      *resnorm = malloc(sizeof(V) * cols), *ap_norms = malloc(sizeof(V) * cols * (kd + 1));
+    uint64_t* fin = malloc(sizeof(uint64_t) * cols);
+    s.starting_tau = malloc(sizeof(V) * cols);
+    s.u_tau = malloc(sizeof(V) * cols);
+    uint8_t* stop = malloc(cols);
+    const V one = 1, neg_one = -1;
+    const int64_t blk = n * cols; /* elements of one basis vector block */
+    FN(gcr_initialize)(n, cols, b, cols, residual, cols, stop);
+    FN(s_apply_A)(&s, &neg_one, x, &one, residual);
+    FN(s_apply_M)(&s, residual, precon);
+    FN(s_apply_A)(&s, NULL, precon, NULL, a_precon);
+    FN(gcr_restart)(n, cols, precon, cols, a_precon, cols, pb, cols, apb, cols, fin);
+    FN(s_criterion_generate)(&s, b, residual);
+    int64_t total_iter = -1, restart_iter = 0;
+    int one_changed;
+    while (1) {
+        ++total_iter;
+        FN(dense_compute_norm2)(n, cols, residual, cols, resnorm);
+        if (FN(s_check)(&s, total_iter, residual, resnorm, NULL, 1, stop, &one_changed)) break;
+        if (restart_iter == kd) {
+            FN(gcr_restart)(n, cols, precon, cols, a_precon, cols, pb, cols, apb, cols, fin);
+            restart_iter = 0;
+        }
+        V* ap = apb + blk * restart_iter;
+        V* p = pb + blk * restart_iter;
+        FN(dense_compute_dot)(n, cols, residual, cols, ap, cols, rap);
+        V* ap_norm = ap_norms + cols * restart_iter;
+        FN(dense_compute_squared_norm2)(n, cols, ap, cols, ap_norm);
+        FN(gcr_step_1)(n, cols, x, cols, residual, cols, p, cols, ap, cols, ap_norm, rap, stop);
+        FN(s_apply_M)(&s, residual, precon);
+        FN(s_apply_A)(&s, NULL, precon, NULL, a_precon);
+        V* next_ap = apb + blk * (restart_iter + 1);
+        V* next_p = pb + blk * (restart_iter + 1);
+        memcpy(next_ap, a_precon, nb);
+        memcpy(next_p, precon, nb);
+        for (int64_t i = 0; i <= restart_iter; ++i) {
+            ap = apb + blk * i;
+            p = pb + blk * i;
+            ap_norm = ap_norms + cols * i;
+            FN(dense_compute_dot)(n, cols, a_precon, cols, ap, cols, minus_beta);
+            FN(dense_inv_scale)(1, cols, ap_norm, cols, minus_beta, cols);
+            FN(dense_sub_scaled)(n, cols, minus_beta, cols, ap, cols, next_ap, cols);
+            FN(dense_sub_scaled)(n, cols, minus_beta, cols, p, cols, next_p, cols);
+        }
+        restart_iter++;
+    }
+    if (stop_out) memcpy(stop_out, stop, cols);
+    if (resnorm_out) FN(dense_compute_norm2)(n, cols, residual, cols, resnorm_out);
+    free(residual); free(precon); free(a_precon); free(pb); free(apb); free(rap); free(minus_beta);
+    free(resnorm); free(ap_norms); free(fin); free(s.starting_tau); free(s.u_tau); free(stop);
+    return total_iter;
+}
+
 /* core/solver/bicgstab.cpp:95-233 */
 int64_t FN(bicgstab_solve)(int64_t n, int64_t cols, const int32_t* rp, const int32_t* ci,
                            const V* va, const V* b, V* x, const orc_solver_cfg* cfg,

@@ -817,3 +817,29 @@ def test_pipe_cg_steps(orc, cuda, vt, rows, cols):
                 sum([[v[k], st[k]] for k in ("z1", "w", "m", "n")], []) +
                 [sc["prev_rho"], sc["rho"], sc["delta"], stop])
     _all_equal(a, b)
+
+
+@pytest.mark.parametrize("vt", VTS)
+@pytest.mark.parametrize("rows,cols", [(597, 43), (100001, 1), (0, 2)])
+def test_gcr_kernels(orc, cuda, vt, rows, cols):
+    rng = np.random.default_rng(94)
+    names = ("b", "res", "ares", "p", "ap", "x")
+    st = {k: cols + (i % 3) for i, k in enumerate(names)}
+    v = {k: H.dense(rng, rows, cols, s, vt) for k, s in st.items()}
+    ap_norm = rng.uniform(0.5, 1, cols).astype(VT[vt])
+    rap = rng.uniform(-1, 1, cols).astype(VT[vt])
+    stop = np.zeros(cols, dtype=np.uint8)
+    if cols > 3:
+        ap_norm[2] = 0
+        stop[1] = 1 | 0x40
+    a, b = both(orc, cuda, "gcr_initialize_" + vt,
+                lambda: [rows, cols, v["b"], st["b"], v["res"].copy(), st["res"], np.full(cols, 0x81, np.uint8)])
+    _all_equal(a, b)
+    a, b = both(orc, cuda, "gcr_restart_" + vt,
+                lambda: [rows, cols, v["res"], st["res"], v["ares"], st["ares"], v["p"].copy(), st["p"],
+                         v["ap"].copy(), st["ap"], np.full(cols, 7, np.uint64)])
+    _all_equal(a, b)
+    a, b = both(orc, cuda, "gcr_step_1_" + vt,
+                lambda: [rows, cols, v["x"].copy(), st["x"], v["res"].copy(), st["res"], v["p"], st["p"],
+                         v["ap"], st["ap"], ap_norm, rap, stop])
+    _all_equal(a, b)

@@ -298,7 +298,7 @@ def test_cpp_example_simple_solver():
 
 
 @pytest.mark.parametrize("kind,extra", [("ir", dict(relaxation_factor=0.9)), ("chebyshev", dict(foci=(0.4, 1.7))),
-                                        ("pipe_cg", {})])
+                                        ("pipe_cg", {}), ("gcr", dict(krylov_dim=20))])
 @pytest.mark.parametrize("vt", ["f64", "f32"])
 def test_zy_ir_and_chebyshev_match_oracle(hexec, kind, extra, vt):
     """Jacobi-preconditioned Richardson / Chebyshev iteration: no inner products, so the device
@@ -314,13 +314,16 @@ def test_zy_ir_and_chebyshev_match_oracle(hexec, kind, extra, vt):
                                   iter_first=1, **extra)
     xd, itd, stop_d, _ = device_solve(hexec, kind, vt, rp, ci, va, b, x0, 1, None, max_iters=3000,
                                       reduction=red, iter_first=True, fused=False, **extra)
-    if kind == "pipe_cg":  # dot products: tree vs sequential order, and PipeCG amplifies rounding
+    if kind in ("pipe_cg", "gcr"):  # dot products: tree vs sequential order (PipeCG amplifies it)
         assert abs(itd - ito) <= max(3, 0.2 * ito) and stop_d == stop_o[0]
         rd = true_rel_res(rp, ci, va, b, xd)
         assert rd[0] <= 20 * red, rd
         return
     assert abs(itd - ito) <= 2 and stop_d == stop_o[0]
-    assert H.rel_err(xo, xd) <= (1e-10 if vt == "f64" else 1e-4)
+    if itd == ito:  # same number of steps: the iterates agree to rounding
+        assert H.rel_err(xo, xd) <= (1e-10 if vt == "f64" else 1e-4)
+    else:  # the residual norm crossed the threshold one step apart
+        assert true_rel_res(rp, ci, va, b, xd)[0] <= 2 * red
 
 
 def test_zz_read_write_csr_files(hexec, orc, tmp_path):
