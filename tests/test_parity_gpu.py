@@ -763,83 +763,3 @@ def test_cgs_steps(orc, cuda, vt, rows, cols):
                 lambda: [rows, cols, v["t"], st["t"], v["u_hat"], st["u_hat"], v["r"].copy(), st["r"],
                          v["x"].copy(), st["x"], sc["alpha"], stop])
     _all_equal(a, b)
-
-
-@pytest.mark.parametrize("vt", VTS)
-@pytest.mark.parametrize("rows,cols", [(597, 43), (100001, 1), (0, 2)])
-def test_ir_and_chebyshev_kernels(orc, cuda, vt, rows, cols):
-    rng = np.random.default_rng(92)
-    st = dict(inner=cols + 1, update=cols + 2, out=cols)
-    v = {k: H.dense(rng, rows, cols, s, vt) for k, s in st.items()}
-    a, b = both(orc, cuda, "chebyshev_init_update_" + vt,
-                lambda: [rows, cols, 0.37, v["inner"], st["inner"], v["update"].copy(), st["update"],
-                         v["out"].copy(), st["out"]])
-    _all_equal(a, b)
-    a, b = both(orc, cuda, "chebyshev_update_" + vt,
-                lambda: [rows, cols, 0.41, 0.0625, v["inner"].copy(), st["inner"], v["update"].copy(),
-                         st["update"], v["out"].copy(), st["out"]])
-    _all_equal(a, b)
-    so, sc = np.full(max(cols, 1), 0xC1, np.uint8), np.full(max(cols, 1), 0xC1, np.uint8)
-    orc("ir_initialize", cols, so)
-    cuda("ir_initialize", cols, sc)
-    assert np.array_equal(so, sc) and not so[:cols].any()
-
-
-@pytest.mark.parametrize("vt", VTS)
-@pytest.mark.parametrize("rows,cols", [(597, 43), (100001, 1), (0, 2)])
-def test_pipe_cg_steps(orc, cuda, vt, rows, cols):
-    rng = np.random.default_rng(93)
-    names = ("b", "r", "z1", "z2", "w", "p", "q", "f", "g", "m", "n", "x")
-    st = {k: cols + (i % 3) for i, k in enumerate(names)}
-    v = {k: H.dense(rng, rows, cols, s, vt) for k, s in st.items()}
-    sc = {k: rng.uniform(0.5, 1, cols).astype(VT[vt]) for k in ("rho", "prev_rho", "beta", "delta")}
-    stop = np.zeros(cols, dtype=np.uint8)
-    if cols > 4:
-        sc["prev_rho"][2] = 0
-        sc["beta"][3] = 0
-        stop[1] = 1 | 0x40
-        # a column whose updated beta is exactly zero: beta = delta - |rho/prev_rho|^2 * beta
-        sc["rho"][4], sc["prev_rho"][4], sc["beta"][4], sc["delta"][4] = 2.0, 1.0, 0.25, 1.0
-    a, b = both(orc, cuda, "pipe_cg_initialize_1_" + vt,
-                lambda: [rows, cols, v["b"], st["b"], v["r"].copy(), st["r"], sc["prev_rho"].copy(),
-                         np.full(cols, 0x81, np.uint8)])
-    _all_equal(a, b)
-    a, b = both(orc, cuda, "pipe_cg_initialize_2_" + vt,
-                lambda: [rows, cols] + sum([[v[k].copy(), st[k]] for k in ("p", "q", "f", "g")], []) +
-                [sc["beta"].copy()] + sum([[v[k], st[k]] for k in ("z1", "w", "m", "n")], []) + [sc["delta"]])
-    _all_equal(a, b)
-    a, b = both(orc, cuda, "pipe_cg_step_1_" + vt,
-                lambda: [rows, cols] + sum([[v[k].copy(), st[k]] for k in ("x", "r", "z1", "z2", "w")], []) +
-                sum([[v[k], st[k]] for k in ("p", "q", "f", "g")], []) + [sc["rho"], sc["beta"], stop])
-    _all_equal(a, b)
-    a, b = both(orc, cuda, "pipe_cg_step_2_" + vt,
-                lambda: [rows, cols, sc["beta"].copy()] + sum([[v[k].copy(), st[k]] for k in ("p", "q", "f", "g")], []) +
-                sum([[v[k], st[k]] for k in ("z1", "w", "m", "n")], []) +
-                [sc["prev_rho"], sc["rho"], sc["delta"], stop])
-    _all_equal(a, b)
-
-
-@pytest.mark.parametrize("vt", VTS)
-@pytest.mark.parametrize("rows,cols", [(597, 43), (100001, 1), (0, 2)])
-def test_gcr_kernels(orc, cuda, vt, rows, cols):
-    rng = np.random.default_rng(94)
-    names = ("b", "res", "ares", "p", "ap", "x")
-    st = {k: cols + (i % 3) for i, k in enumerate(names)}
-    v = {k: H.dense(rng, rows, cols, s, vt) for k, s in st.items()}
-    ap_norm = rng.uniform(0.5, 1, cols).astype(VT[vt])
-    rap = rng.uniform(-1, 1, cols).astype(VT[vt])
-    stop = np.zeros(cols, dtype=np.uint8)
-    if cols > 3:
-        ap_norm[2] = 0
-        stop[1] = 1 | 0x40
-    a, b = both(orc, cuda, "gcr_initialize_" + vt,
-                lambda: [rows, cols, v["b"], st["b"], v["res"].copy(), st["res"], np.full(cols, 0x81, np.uint8)])
-    _all_equal(a, b)
-    a, b = both(orc, cuda, "gcr_restart_" + vt,
-                lambda: [rows, cols, v["res"], st["res"], v["ares"], st["ares"], v["p"].copy(), st["p"],
-                         v["ap"].copy(), st["ap"], np.full(cols, 7, np.uint64)])
-    _all_equal(a, b)
-    a, b = both(orc, cuda, "gcr_step_1_" + vt,
-                lambda: [rows, cols, v["x"].copy(), st["x"], v["res"].copy(), st["res"], v["p"], st["p"],
-                         v["ap"], st["ap"], ap_norm, rap, stop])
-    _all_equal(a, b)

@@ -295,70 +295,3 @@ def test_cpp_example_simple_solver():
     r = subprocess.run([exe, "40"], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "converged=1" in r.stdout and "fused=1" in r.stdout
-
-
-@pytest.mark.parametrize("kind,extra", [("ir", dict(relaxation_factor=0.9)), ("chebyshev", dict(foci=(0.4, 1.7))),
-                                        ("pipe_cg", {}), ("gcr", dict(krylov_dim=20))])
-@pytest.mark.parametrize("vt", ["f64", "f32"])
-def test_zy_ir_and_chebyshev_match_oracle(hexec, kind, extra, vt):
-    """Jacobi-preconditioned Richardson / Chebyshev iteration: no inner products, so the device
-    run follows the oracle (= reference) loop to rounding of the residual norms only"""
-    rp, ci, va = W.laplace(30, 2, vdtype=VT[vt])
-    n = len(rp) - 1
-    rng = np.random.default_rng(6)
-    b = rng.uniform(-1, 1, (n, 1)).astype(VT[vt])
-    x0 = np.zeros((n, 1), VT[vt])
-    jac = ref_jacobi(vt, rp, ci, va, 1, None)
-    red = 1e-4 if vt == "f64" else 1e-3
-    xo, ito, stop_o = H.orc_solve(kind, vt, rp, ci, va, b, x0, 1, jac, max_iters=3000, reduction=red,
-                                  iter_first=1, **extra)
-    xd, itd, stop_d, _ = device_solve(hexec, kind, vt, rp, ci, va, b, x0, 1, None, max_iters=3000,
-                                      reduction=red, iter_first=True, fused=False, **extra)
-    if kind in ("pipe_cg", "gcr"):  # dot products: tree vs sequential order (PipeCG amplifies it)
-        assert abs(itd - ito) <= max(3, 0.2 * ito) and stop_d == stop_o[0]
-        rd = true_rel_res(rp, ci, va, b, xd)
-        assert rd[0] <= 20 * red, rd
-        return
-    assert abs(itd - ito) <= 2 and stop_d == stop_o[0]
-    if itd == ito:  # same number of steps: the iterates agree to rounding
-        assert H.rel_err(xo, xd) <= (1e-10 if vt == "f64" else 1e-4)
-    else:  # the residual norm crossed the threshold one step apart
-        assert true_rel_res(rp, ci, va, b, xd)[0] <= 2 * red
-
-
-def test_zz_read_write_csr_files(hexec, orc, tmp_path):
-    """gko::read_generic<Csr> / gko::write on the device executor: a file written by the host
-    layer is read back into a Csr whose apply matches the oracle (kept last in the suite)."""
-    import torch
-    from ginkgo_b200 import api
-    rng = np.random.default_rng(44)
-    n, m = 300, 250
-    rp, ci, va = H.random_csr(rng, n, m, rng.integers(0, 9, n), "f64", "i32")
-    rows = np.repeat(np.arange(n), np.diff(rp))
-    path = tmp_path / "a.mtx"
-    with open(path, "w") as f:
-        f.write("%%MatrixMarket matrix coordinate real general\n")  # no %-formatting here
-        f.write("%d %d %d\n" % (n, m, len(va)))
-        for r, c, v in zip(rows, ci, va):
-            f.write("%d %d %.17g\n" % (r + 1, c + 1, v))
-    A = api.host_read_csr(hexec, path)
-    assert A.size == (n, m)
-    x = rng.uniform(-1, 1, m)
-    with torch.cuda.stream(hexec.stream):
-        tx = torch.from_numpy(x).to(hexec.device)
-        ty = torch.zeros(n, dtype=torch.float64, device=hexec.device)
-    xd, yd = api.host_dense(hexec, tx), api.host_dense(hexec, ty)
-    api._hcheck(api._host().gkob_apply(A.h, xd.h, yd.h))
-    hexec.synchronize()
-    yo = np.zeros(n)
-    orc("csr_spmv_f64_i32", n, m, len(va), rp, ci, va, x, 1, 1, yo, 1)
-    assert np.array_equal(ty.cpu().numpy(), yo)
-    for layout in ("coordinate", "binary"):
-        out = tmp_path / ("b." + layout)
-        api.host_write_csr(A, out, layout)
-        B = api.host_read_csr(hexec, out)
-        with torch.cuda.stream(hexec.stream):
-            ty.zero_()
-        api._hcheck(api._host().gkob_apply(B.h, xd.h, yd.h))
-        hexec.synchronize()
-        assert np.array_equal(ty.cpu().numpy(), yo)
