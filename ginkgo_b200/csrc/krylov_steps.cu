@@ -384,6 +384,133 @@ b200_status gcr_step_1(b200_ctx* ctx, int64_t rows, int64_t cols, V* x, int64_t 
     });
 }
 
+// ---- MINRES (reference/solver/minres_kernels.cpp:26-150).  safe_divide(a, b) = b == 0 ? 0 : a / b
+// (include/ginkgo/core/base/math.hpp); sqrt and division are IEEE on the device, products and
+// sums are rounded separately (-fmad=false), so the scalar recurrences match the reference.
+template <typename V>
+__device__ __forceinline__ V safe_divide(V a, V b)
+{
+    return b == V(0) ? V(0) : a / b;
+}
+template <typename V>
+__device__ __forceinline__ V dev_abs(V a)
+{
+    return a < V(0) ? -a : a;
+}
+
+template <typename V>
+b200_status minres_initialize(b200_ctx* ctx, int64_t rows, int64_t cols, const V* r, int64_t rs, V* z,
+                              int64_t zs, V* p, int64_t ps, V* p_prev, int64_t pps, V* q, int64_t qs,
+                              V* q_prev, int64_t qps, V* q_tilde, int64_t qts, V* beta, V* gamma,
+                              V* delta, V* cos_prev, V* cos_, V* sin_prev, V* sin_, V* eta_next, V* eta,
+                              uint8_t* stop)
+{
+    B200_REQUIRE(ctx != nullptr, "ctx is null");
+    // scalars first (beta <- sqrt(beta)), then the vectors read the new beta
+    b200_status st = launch_ew(ctx, 1, cols, [=] __device__(int64_t, int64_t j) {
+        delta[j] = V(0);
+        gamma[j] = V(0);
+        cos_prev[j] = V(0);
+        sin_prev[j] = V(0);
+        sin_[j] = V(0);
+        cos_[j] = V(1);
+        const V sb = sqrt(beta[j]);
+        beta[j] = sb;
+        eta[j] = sb;
+        eta_next[j] = sb;
+        stop[j] = 0;
+    });
+    if (st != B200_OK) return st;
+    return launch_ew(ctx, rows, cols, [=] __device__(int64_t i, int64_t j) {
+        const V bt = beta[j];
+        q[i * qs + j] = safe_divide(r[i * rs + j], bt);
+        z[i * zs + j] = safe_divide(z[i * zs + j], bt);
+        p[i * ps + j] = V(0);
+        p_prev[i * pps + j] = V(0);
+        q_prev[i * qps + j] = V(0);
+        q_tilde[i * qts + j] = V(0);
+    });
+}
+
+template <typename V>
+b200_status minres_step_1(b200_ctx* ctx, int64_t cols, V* alpha, V* beta, V* gamma, V* delta,
+                          V* cos_prev, V* cos_, V* sin_prev, V* sin_, V* eta, V* eta_next, V* tau,
+                          const uint8_t* stop)
+{
+    B200_REQUIRE(ctx != nullptr, "ctx is null");
+    return launch_ew(ctx, 1, cols, [=] __device__(int64_t, int64_t j) {
+        if (has_stopped(stop[j])) return;
+        const V bt = sqrt(beta[j]);
+        beta[j] = bt;
+        const V tmp_d = gamma[j];
+        const V tmp_a = alpha[j];
+        delta[j] = sin_prev[j] * tmp_d;
+        const V c_old = cos_[j], s_old = sin_[j], cp_old = cos_prev[j];
+        const V g1 = cp_old * c_old;
+        const V g2 = g1 * tmp_d;
+        const V g3 = s_old * tmp_a;
+        gamma[j] = g2 + g3;
+        const V a1 = (-s_old) * cp_old;
+        const V a2 = a1 * tmp_d;
+        const V a3 = c_old * tmp_a;
+        V al = a2 + a3;
+        // swap(cos, cos_prev), swap(sin, sin_prev): the old pair moves to *_prev
+        cos_prev[j] = c_old;
+        sin_prev[j] = s_old;
+        V c, sn;
+        if (al == V(0)) {
+            c = V(0);
+            sn = V(1);
+        } else {
+            const V scale = dev_abs(al) + dev_abs(bt);
+            const V ra = dev_abs(al / scale), rb = dev_abs(bt / scale);
+            const V h1 = ra * ra;
+            const V h2 = rb * rb;
+            const V hyp = scale * sqrt(h1 + h2);
+            c = al / hyp;
+            sn = bt / hyp;
+        }
+        const V n1 = c * al;
+        const V n2 = sn * bt;
+        al = n1 + n2;
+        alpha[j] = al;
+        cos_[j] = c;
+        sin_[j] = sn;
+        const V t1 = sn * sn;
+        tau[j] = t1 * tau[j];
+        const V e = eta_next[j];
+        eta[j] = e;
+        eta_next[j] = (-sn) * e;
+    });
+}
+
+template <typename V>
+b200_status minres_step_2(b200_ctx* ctx, int64_t rows, int64_t cols, V* x, int64_t xs, V* p, int64_t ps,
+                          const V* p_prev, int64_t pps, V* z, int64_t zs, const V* z_tilde, int64_t zts,
+                          V* q, int64_t qs, V* q_prev, int64_t qps, V* v, int64_t vs, const V* alpha,
+                          const V* beta, const V* gamma, const V* delta, const V* cos_, const V* eta,
+                          const uint8_t* stop)
+{
+    return launch_ew(ctx, rows, cols, [=] __device__(int64_t i, int64_t j) {
+        if (has_stopped(stop[j])) return;
+        const V gp = gamma[j] * p_prev[i * pps + j];
+        const V dp = delta[j] * p[i * ps + j];
+        const V num = (z[i * zs + j] - gp) - dp;
+        const V pn = safe_divide(num, alpha[j]);
+        p[i * ps + j] = pn;
+        const V ce = cos_[j] * eta[j];
+        const V cep = ce * pn;
+        x[i * xs + j] = x[i * xs + j] + cep;
+        const V vv = v[i * vs + j];
+        q_prev[i * qps + j] = vv;
+        const V tmp = q[i * qs + j];
+        const V bt = beta[j];
+        q[i * qs + j] = safe_divide(vv, bt);
+        v[i * vs + j] = tmp * bt;
+        z[i * zs + j] = safe_divide(z_tilde[i * zts + j], bt);
+    });
+}
+
 template <typename V>
 b200_status bicgstab_initialize(b200_ctx* ctx, int64_t rows, int64_t cols, const V* b, int64_t bs,
                                 V* r, int64_t rs, V* rr, int64_t rrs, V* y, int64_t ys, V* s,
@@ -663,6 +790,36 @@ b200_status b200_ir_initialize(b200_ctx* ctx, int64_t cols, uint8_t* stop_status
     {                                                                                          \
         return b200::steps::gcr_step_1<VT>(ctx, rows, cols, x, xs, residual, rs, p, ps, ap,    \
                                            aps, ap_norm, rap, stop);                           \
+    }                                                                                          \
+    b200_status b200_minres_initialize_##V(                                                    \
+        b200_ctx* ctx, int64_t rows, int64_t cols, const VT* r, int64_t rs, VT* z, int64_t zs, \
+        VT* p, int64_t ps, VT* p_prev, int64_t pps, VT* q, int64_t qs, VT* q_prev,             \
+        int64_t qps, VT* q_tilde, int64_t qts, VT* beta, VT* gamma, VT* delta, VT* cos_prev,   \
+        VT* cos_, VT* sin_prev, VT* sin_, VT* eta_next, VT* eta, uint8_t* stop)                \
+    {                                                                                          \
+        return b200::steps::minres_initialize<VT>(ctx, rows, cols, r, rs, z, zs, p, ps,        \
+                                                  p_prev, pps, q, qs, q_prev, qps, q_tilde,    \
+                                                  qts, beta, gamma, delta, cos_prev, cos_,     \
+                                                  sin_prev, sin_, eta_next, eta, stop);        \
+    }                                                                                          \
+    b200_status b200_minres_step_1_##V(b200_ctx* ctx, int64_t cols, VT* alpha, VT* beta,       \
+                                       VT* gamma, VT* delta, VT* cos_prev, VT* cos_,           \
+                                       VT* sin_prev, VT* sin_, VT* eta, VT* eta_next,          \
+                                       VT* tau, const uint8_t* stop)                           \
+    {                                                                                          \
+        return b200::steps::minres_step_1<VT>(ctx, cols, alpha, beta, gamma, delta, cos_prev,  \
+                                              cos_, sin_prev, sin_, eta, eta_next, tau, stop); \
+    }                                                                                          \
+    b200_status b200_minres_step_2_##V(                                                        \
+        b200_ctx* ctx, int64_t rows, int64_t cols, VT* x, int64_t xs, VT* p, int64_t ps,       \
+        const VT* p_prev, int64_t pps, VT* z, int64_t zs, const VT* z_tilde, int64_t zts,      \
+        VT* q, int64_t qs, VT* q_prev, int64_t qps, VT* v, int64_t vs, const VT* alpha,        \
+        const VT* beta, const VT* gamma, const VT* delta, const VT* cos_, const VT* eta,       \
+        const uint8_t* stop)                                                                   \
+    {                                                                                          \
+        return b200::steps::minres_step_2<VT>(ctx, rows, cols, x, xs, p, ps, p_prev, pps, z,   \
+                                              zs, z_tilde, zts, q, qs, q_prev, qps, v, vs,     \
+                                              alpha, beta, gamma, delta, cos_, eta, stop);     \
     }                                                                                          \
     b200_status b200_bicgstab_initialize_##V(                                                  \
         b200_ctx* ctx, int64_t rows, int64_t cols, const VT* b, int64_t bs, VT* r, int64_t rs, \

@@ -84,6 +84,12 @@ std::unique_ptr<LinOp> make_solver(std::shared_ptr<Executor> exec, int kind,
         if (pre) f.with_preconditioner(pre);
         return f.on(exec)->generate(A);
     }
+    if (kind == 9) {
+        auto f = solver::Minres<V>::build();
+        f.with_criteria(crit);
+        if (pre) f.with_preconditioner(pre);
+        return f.on(exec)->generate(A);
+    }
     if (kind == 8) {
         auto f = solver::Gcr<V>::build();
         f.with_criteria(crit).with_krylov_dim((size_type)krylov_dim);

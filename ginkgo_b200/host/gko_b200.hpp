@@ -89,6 +89,9 @@ struct viabi;
         static constexpr auto gcr_initialize = b200_gcr_initialize_##S;                         \
         static constexpr auto gcr_restart = b200_gcr_restart_##S;                               \
         static constexpr auto gcr_step_1 = b200_gcr_step_1_##S;                                 \
+        static constexpr auto minres_initialize = b200_minres_initialize_##S;                   \
+        static constexpr auto minres_step_1 = b200_minres_step_1_##S;                           \
+        static constexpr auto minres_step_2 = b200_minres_step_2_##S;                           \
         static constexpr auto chebyshev_init_update = b200_chebyshev_init_update_##S;           \
         static constexpr auto chebyshev_update = b200_chebyshev_update_##S;                     \
         static constexpr auto bicgstab_initialize = b200_bicgstab_initialize_##S;               \

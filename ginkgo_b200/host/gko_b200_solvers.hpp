@@ -1111,6 +1111,88 @@ private:
 };
 
 // ---------------------------------------------------------------------------------------------
+// solver::Minres (core/solver/minres.cpp:114-286): symmetric (possibly indefinite) systems; the
+// residual norm is tracked by a recurrence (tau), the criteria receive it as the implicit
+// squared norm and no residual vector.
+// ---------------------------------------------------------------------------------------------
+template <typename V>
+class Minres : public SolverBase<V> {
+    using Base = SolverBase<V>;
+    using Dense = matrix::Dense<V>;
+
+public:
+    struct Factory : SolverFactoryBase<Factory> {
+        std::unique_ptr<LinOp> generate(std::shared_ptr<const LinOp> op) const override
+        {
+            auto exec = this->exec_ ? this->exec_ : op->get_executor();
+            return std::unique_ptr<LinOp>(new Minres(exec, *this, op));
+        }
+    };
+    static Factory build() { return Factory{}; }
+
+protected:
+    Minres(std::shared_ptr<const Executor> exec, const Factory& f, std::shared_ptr<const LinOp> op)
+        : Base(exec, f, op)
+    {}
+    using Base::apply_impl;
+    void apply_impl(const LinOp* lb, LinOp* lx) const override
+    {
+        auto b = as<Dense>(lb);
+        auto x = as<Dense>(lx);
+        auto exec = this->exec_;
+        auto ctx = exec->ctx();
+        const dim2 sz = b->get_size();
+        const size_type nrhs = sz.cols;
+        auto mk = [&] { return Dense::create(exec, sz); };
+        auto sc = [&] { return Dense::create(exec, dim2{1, nrhs}); };
+        auto r = mk(), z = mk(), p = mk(), q = mk(), v = mk(), z_tilde = mk(), p_prev = mk(), q_prev = mk();
+        auto alpha = sc(), beta = sc(), gamma = sc(), delta = sc(), eta_next = sc(), eta = sc(), tau = sc(),
+             cos_prev = sc(), cos = sc(), sin_prev = sc(), sin = sc();
+        array<uint8> stop_status(exec, nrhs);
+        bool one_changed = false;
+        r->copy_from(b);
+        this->system_matrix_->apply(this->neg_one_.get(), x, this->one_.get(), r.get());
+        stop::CriterionArgs args{this->system_matrix_, b, x, r.get()};
+        auto crit = stop::combine_and_generate(this->criteria_, exec, args);
+        this->preconditioner_->apply(r.get(), z.get());
+        r->compute_conj_dot(z.get(), beta.get());
+        z->compute_conj_dot(z.get(), tau.get());
+        GKOB_CALL(vabi<V>::minres_initialize(
+            ctx, sz.rows, nrhs, GKOB_CVS(r), GKOB_VS(z), GKOB_VS(p), GKOB_VS(p_prev), GKOB_VS(q),
+            GKOB_VS(q_prev), GKOB_VS(v), beta->get_values(), gamma->get_values(), delta->get_values(),
+            cos_prev->get_values(), cos->get_values(), sin_prev->get_values(), sin->get_values(),
+            eta_next->get_values(), eta->get_values(), stop_status.get_data()));
+        int64 iter = -1;
+        while (true) {
+            ++iter;
+            stop::Updater u;
+            u.num_iterations = iter;
+            u.implicit_sq_residual_norm = tau.get();
+            u.solution = x;
+            if (crit->check(1, true, &stop_status, &one_changed, u)) break;
+            this->system_matrix_->apply(this->one_.get(), z.get(), this->neg_one_.get(), v.get());
+            v->compute_conj_dot(z.get(), alpha.get());
+            v->sub_scaled(alpha.get(), q.get());
+            this->preconditioner_->apply(v.get(), z_tilde.get());
+            v->compute_conj_dot(z_tilde.get(), beta.get());
+            GKOB_CALL(vabi<V>::minres_step_1(
+                ctx, nrhs, alpha->get_values(), beta->get_values(), gamma->get_values(),
+                delta->get_values(), cos_prev->get_values(), cos->get_values(), sin_prev->get_values(),
+                sin->get_values(), eta->get_values(), eta_next->get_values(), tau->get_values(),
+                stop_status.get_const_data()));
+            std::swap(p, p_prev);
+            GKOB_CALL(vabi<V>::minres_step_2(
+                ctx, sz.rows, nrhs, GKOB_VS(x), GKOB_VS(p), GKOB_CVS(p_prev), GKOB_VS(z),
+                GKOB_CVS(z_tilde), GKOB_VS(q), GKOB_VS(q_prev), GKOB_VS(v), alpha->get_const_values(),
+                beta->get_const_values(), gamma->get_const_values(), delta->get_const_values(),
+                cos->get_const_values(), eta->get_const_values(), stop_status.get_const_data()));
+            std::swap(gamma, beta);
+        }
+        this->record(iter, stop_status);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
 // solver::Ir (core/solver/ir.cpp:192-258): x += relaxation_factor * inner_solver(b - A x).
 // The inner solver is the `with_solver` / preconditioner slot of the factory (Identity by
 // default, which gives Richardson iteration).  default_initial_guess = provided.

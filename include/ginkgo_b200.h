@@ -398,6 +398,25 @@ b200_status b200_jacobi_find_blocks_i64(b200_ctx* ctx, int64_t num_rows, const i
                                     int64_t ap_stride, const VT* ap_norm, const VT* rap,      \
                                     const uint8_t* stop_status);                              \
                                                                                               \
+    /* MINRES (core/solver/minres_kernels.hpp; reference/solver/minres_kernels.cpp:26-150) */ \
+    b200_status b200_minres_initialize_##V(                                                   \
+        b200_ctx* ctx, int64_t rows, int64_t cols, const VT* r, int64_t r_stride, VT* z,      \
+        int64_t z_stride, VT* p, int64_t p_stride, VT* p_prev, int64_t p_prev_stride, VT* q,  \
+        int64_t q_stride, VT* q_prev, int64_t q_prev_stride, VT* q_tilde,                     \
+        int64_t q_tilde_stride, VT* beta, VT* gamma, VT* delta, VT* cos_prev, VT* cos_,       \
+        VT* sin_prev, VT* sin_, VT* eta_next, VT* eta, uint8_t* stop_status);                 \
+    b200_status b200_minres_step_1_##V(b200_ctx* ctx, int64_t cols, VT* alpha, VT* beta,      \
+                                       VT* gamma, VT* delta, VT* cos_prev, VT* cos_,          \
+                                       VT* sin_prev, VT* sin_, VT* eta, VT* eta_next,         \
+                                       VT* tau, const uint8_t* stop_status);                  \
+    b200_status b200_minres_step_2_##V(                                                       \
+        b200_ctx* ctx, int64_t rows, int64_t cols, VT* x, int64_t x_stride, VT* p,            \
+        int64_t p_stride, const VT* p_prev, int64_t p_prev_stride, VT* z, int64_t z_stride,   \
+        const VT* z_tilde, int64_t z_tilde_stride, VT* q, int64_t q_stride, VT* q_prev,       \
+        int64_t q_prev_stride, VT* v, int64_t v_stride, const VT* alpha, const VT* beta,      \
+        const VT* gamma, const VT* delta, const VT* cos_, const VT* eta,                      \
+        const uint8_t* stop_status);                                                          \
+                                                                                              \
     b200_status b200_bicgstab_initialize_##V(                                                 \
         b200_ctx* ctx, int64_t rows, int64_t cols, const VT* b, int64_t b_stride, VT* r,      \
         int64_t r_stride, VT* rr, int64_t rr_stride, VT* y, int64_t y_stride, VT* s,          \

@@ -423,6 +423,80 @@ void FN(gcr_step_1)(int64_t rows, int64_t cols, V* x, int64_t xs, V* residual, i
         }
 }
 
+/* reference/solver/minres_kernels.cpp:26-150 (safe_divide: include/ginkgo/core/base/math.hpp) */
+static V FN(safe_divide)(V a, V b) { return b == 0 ? (V)0 : a / b; }
+void FN(minres_initialize)(int64_t rows, int64_t cols, const V* r, int64_t rs, V* z, int64_t zs, V* p,
+                           int64_t ps, V* p_prev, int64_t pps, V* q, int64_t qs, V* q_prev,
+                           int64_t qps, V* q_tilde, int64_t qts, V* beta, V* gamma, V* delta,
+                           V* cos_prev, V* cos_, V* sin_prev, V* sin_, V* eta_next, V* eta,
+                           uint8_t* stop)
+{
+    for (int64_t j = 0; j < cols; ++j) {
+        delta[j] = gamma[j] = cos_prev[j] = sin_prev[j] = sin_[j] = 0;
+        cos_[j] = 1;
+        eta_next[j] = eta[j] = beta[j] = SQRT(beta[j]);
+        stop[j] = 0;
+    }
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) {
+            q[i * qs + j] = FN(safe_divide)(r[i * rs + j], beta[j]);
+            z[i * zs + j] = FN(safe_divide)(z[i * zs + j], beta[j]);
+            p[i * ps + j] = p_prev[i * pps + j] = q_prev[i * qps + j] = q_tilde[i * qts + j] = 0;
+        }
+}
+void FN(minres_step_1)(int64_t cols, V* alpha, V* beta, V* gamma, V* delta, V* cos_prev, V* cos_,
+                       V* sin_prev, V* sin_, V* eta, V* eta_next, V* tau, const uint8_t* stop)
+{
+    for (int64_t j = 0; j < cols; ++j) {
+        if (st_has_stopped(stop[j])) continue;
+        beta[j] = SQRT(beta[j]);
+        delta[j] = sin_prev[j] * gamma[j];
+        const V tmp_d = gamma[j];
+        const V tmp_a = alpha[j];
+        gamma[j] = cos_prev[j] * cos_[j] * tmp_d + sin_[j] * tmp_a;
+        alpha[j] = -sin_[j] * cos_prev[j] * tmp_d + cos_[j] * tmp_a;
+        V t = cos_[j];
+        cos_[j] = cos_prev[j];
+        cos_prev[j] = t;
+        t = sin_[j];
+        sin_[j] = sin_prev[j];
+        sin_prev[j] = t;
+        /* update_givens_rotation(alpha, beta, cos, sin) */
+        if (alpha[j] == 0) {
+            cos_[j] = 0;
+            sin_[j] = 1;
+        } else {
+            const V scale = FABS(alpha[j]) + FABS(beta[j]);
+            const V hyp = scale * SQRT(FABS(alpha[j] / scale) * FABS(alpha[j] / scale) +
+                                       FABS(beta[j] / scale) * FABS(beta[j] / scale));
+            cos_[j] = alpha[j] / hyp;
+            sin_[j] = beta[j] / hyp;
+        }
+        alpha[j] = cos_[j] * alpha[j] + sin_[j] * beta[j];
+        tau[j] = sin_[j] * sin_[j] * tau[j];
+        eta[j] = eta_next[j];
+        eta_next[j] = -sin_[j] * eta[j];
+    }
+}
+void FN(minres_step_2)(int64_t rows, int64_t cols, V* x, int64_t xs, V* p, int64_t ps, const V* p_prev,
+                       int64_t pps, V* z, int64_t zs, const V* z_tilde, int64_t zts, V* q, int64_t qs,
+                       V* q_prev, int64_t qps, V* v, int64_t vs, const V* alpha, const V* beta,
+                       const V* gamma, const V* delta, const V* cos_, const V* eta, const uint8_t* stop)
+{
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) {
+            if (st_has_stopped(stop[j])) continue;
+            p[i * ps + j] = FN(safe_divide)(
+                z[i * zs + j] - gamma[j] * p_prev[i * pps + j] - delta[j] * p[i * ps + j], alpha[j]);
+            x[i * xs + j] = x[i * xs + j] + cos_[j] * eta[j] * p[i * ps + j];
+            q_prev[i * qps + j] = v[i * vs + j];
+            const V tmp = q[i * qs + j];
+            q[i * qs + j] = FN(safe_divide)(v[i * vs + j], beta[j]);
+            v[i * vs + j] = tmp * beta[j];
+            z[i * zs + j] = FN(safe_divide)(z_tilde[i * zts + j], beta[j]);
+        }
+}
+
 /* reference/solver/bicgstab_kernels.cpp:25-60 */
 void FN(bicgstab_initialize)(int64_t rows, int64_t cols, const V* b, int64_t bs, V* r, int64_t rs,
                              V* rr, int64_t rrs, V* y, int64_t ys, V* s, int64_t ss, V* t,

@@ -37,6 +37,8 @@ typedef struct {
     const orc_solver_cfg* cfg;
     V* starting_tau; /* 1 x cols */
     V* u_tau;        /* 1 x cols */
+    const V* cur_b;  /* for criteria that are only given the solution (MINRES) */
+    const V* cur_x;
 } FN(sctx);
 
 static void FN(s_apply_A)(const FN(sctx) * s, const V* alpha, const V* b, const V* beta, V* c)
@@ -116,8 +118,17 @@ static int FN(s_check_ex)(FN(sctx) * s, int64_t iter, const V* residual, const V
                 /* skipped */
             } else if (c->res_kind == 1) {
                 const V* tau = residual_norm;
-                if (!tau) {
+                if (!tau && residual) {
                     FN(dense_compute_norm2)(s->n, s->cols, residual, s->cols, s->u_tau);
+                    tau = s->u_tau;
+                } else if (!tau) {
+                    /* core/stop/residual_norm.cpp:183-196: r = b - A x from the solution */
+                    const V one_ = 1, neg_one_ = -1;
+                    V* tmp_r = malloc(sizeof(V) * s->n * s->cols);
+                    memcpy(tmp_r, s->cur_b, sizeof(V) * s->n * s->cols);
+                    FN(s_apply_A)(s, &neg_one_, s->cur_x, &one_, tmp_r);
+                    FN(dense_compute_norm2)(s->n, s->cols, tmp_r, s->cols, s->u_tau);
+                    free(tmp_r);
                     tau = s->u_tau;
                 }
                 FN(residual_norm)(s->cols, tau, s->starting_tau, (V)c->reduction_factor, id,
@@ -478,6 +489,59 @@ int64_t FN(gcr_solve)(int64_t n, int64_t cols, const int32_t* rp, const int32_t*
     free(residual); free(precon); free(a_precon); free(pb); free(apb); free(rap); free(minus_beta);
     free(resnorm); free(ap_norms); free(fin); free(s.starting_tau); free(s.u_tau); free(stop);
     return total_iter;
+}
+
+/* core/solver/minres.cpp:114-286 */
+int64_t FN(minres_solve)(int64_t n, int64_t cols, const int32_t* rp, const int32_t* ci, const V* va,
+                         const V* b, V* x, const orc_solver_cfg* cfg, uint8_t* stop_out,
+                         V* resnorm_out)
+{
+    FN(sctx) s = {n, cols, rp, ci, va, cfg, NULL, NULL, b, x};
+    const size_t nb = sizeof(V) * n * cols;
+    V *r = malloc(nb), *z = malloc(nb), *p = malloc(nb), *q = malloc(nb), *v = malloc(nb),
+      *z_tilde = malloc(nb), *p_prev = malloc(nb), *q_prev = malloc(nb);
+    V* sc = calloc(cols * 11, sizeof(V));
+    V *alpha = sc, *beta = sc + cols, *gamma = sc + 2 * cols, *delta = sc + 3 * cols,
+      *eta_next = sc + 4 * cols, *eta = sc + 5 * cols, *tau = sc + 6 * cols, *cos_prev = sc + 7 * cols,
+      *cos_ = sc + 8 * cols, *sin_prev = sc + 9 * cols, *sin_ = sc + 10 * cols;
+    s.starting_tau = malloc(sizeof(V) * cols);
+    s.u_tau = malloc(sizeof(V) * cols);
+    uint8_t* stop = malloc(cols);
+    const V one = 1, neg_one = -1;
+    int one_changed;
+    memcpy(r, b, nb);
+    FN(s_apply_A)(&s, &neg_one, x, &one, r);
+    FN(s_criterion_generate)(&s, b, r);
+    FN(s_apply_M)(&s, r, z);
+    FN(dense_compute_dot)(n, cols, r, cols, z, cols, beta);
+    FN(dense_compute_dot)(n, cols, z, cols, z, cols, tau);
+    FN(minres_initialize)(n, cols, r, cols, z, cols, p, cols, p_prev, cols, q, cols, q_prev, cols, v,
+                          cols, beta, gamma, delta, cos_prev, cos_, sin_prev, sin_, eta_next, eta, stop);
+    int64_t iter = -1;
+    while (1) {
+        ++iter;
+        if (FN(s_check)(&s, iter, NULL, NULL, tau, 1, stop, &one_changed)) break;
+        FN(s_apply_A)(&s, &one, z, &neg_one, v);
+        FN(dense_compute_dot)(n, cols, v, cols, z, cols, alpha);
+        FN(dense_sub_scaled)(n, cols, alpha, cols, q, cols, v, cols);
+        FN(s_apply_M)(&s, v, z_tilde);
+        FN(dense_compute_dot)(n, cols, v, cols, z_tilde, cols, beta);
+        FN(minres_step_1)(cols, alpha, beta, gamma, delta, cos_prev, cos_, sin_prev, sin_, eta, eta_next,
+                          tau, stop);
+        V* sw = p;
+        p = p_prev;
+        p_prev = sw;
+        FN(minres_step_2)(n, cols, x, cols, p, cols, p_prev, cols, z, cols, z_tilde, cols, q, cols, q_prev,
+                          cols, v, cols, alpha, beta, gamma, delta, cos_, eta, stop);
+        sw = gamma;
+        gamma = beta;
+        beta = sw;
+    }
+    if (stop_out) memcpy(stop_out, stop, cols);
+    if (resnorm_out) FN(dense_compute_norm2)(n, cols, r, cols, resnorm_out);
+    free(r); free(z); free(p); free(q); free(v); free(z_tilde); free(p_prev); free(q_prev); free(sc);
+    free(s.starting_tau); free(s.u_tau); free(stop);
+    return iter;
 }
 
 /* core/solver/bicgstab.cpp:95-233 */

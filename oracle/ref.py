@@ -84,7 +84,7 @@ def solve(kind, rp, ci, va, b, x0, precond_max_bs=0, block_ptrs=None, max_iters=
     nb = 0 if block_ptrs is None else len(block_ptrs) - 1
     lib().refshim_solve_params(float(relaxation_factor), float(foci[0]), float(foci[1]))
     st = lib().refshim_solve(exec_kind, {"cg": 0, "bicgstab": 1, "gmres": 2, "fcg": 3, "cgs": 4, "ir": 5,
-                                         "chebyshev": 6, "pipe_cg": 7, "gcr": 8}[kind], _vt(va), n,
+                                         "chebyshev": 6, "pipe_cg": 7, "gcr": 8, "minres": 9}[kind], _vt(va), n,
                              len(va), _p(rp), _p(ci), _p(va), _p(b2), _p(x), nrhs, precond_max_bs,
                              _p(block_ptrs), nb, max_iters, res_kind, baseline, reduction,
                              iter_first, krylov_dim, ortho, ctypes.byref(iters), _p(resn),

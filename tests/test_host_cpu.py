@@ -79,7 +79,7 @@ def host_solve(host, kind, vt, rp, ci, va, b, x0, precond_max_bs=0, block_ptrs=N
     return tx.numpy(), s.num_iterations, s.stop_status
 
 
-@pytest.mark.parametrize("kind", ["cg", "fcg", "cgs", "pipe_cg", "bicgstab", "gmres", "gcr"])
+@pytest.mark.parametrize("kind", ["cg", "fcg", "cgs", "pipe_cg", "minres", "bicgstab", "gmres", "gcr"])
 @pytest.mark.parametrize("precond", [0, 1, 2, 3])
 @pytest.mark.parametrize("vt", ["f64", "f32"])
 def test_host_solver_loops_are_the_oracle_loops(host, kind, precond, vt):

@@ -52,7 +52,7 @@ def test_omp_executor_matches_reference_executor():
 from tests.helpers import orc_solve  # noqa: E402
 
 
-@pytest.mark.parametrize("kind", ["cg", "bicgstab", "gmres", "fcg", "cgs", "pipe_cg", "gcr"])
+@pytest.mark.parametrize("kind", ["cg", "bicgstab", "gmres", "fcg", "cgs", "pipe_cg", "gcr", "minres"])
 @pytest.mark.parametrize("precond", [0, 1, 2])
 @pytest.mark.parametrize("vt", ["f64", "f32"])
 def test_solver_loops_bit_identical_to_reference(kind, precond, vt):

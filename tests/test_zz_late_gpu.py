@@ -95,8 +95,52 @@ def test_gcr_kernels(orc, cuda, vt, rows, cols):
     _all_equal(a, b)
 
 
+@pytest.mark.parametrize("vt", VTS)
+@pytest.mark.parametrize("rows,cols", [(597, 43), (100001, 1), (0, 2)])
+def test_minres_kernels(orc, cuda, vt, rows, cols):
+    rng = np.random.default_rng(95)
+    names = ("r", "z", "p", "p_prev", "q", "q_prev", "v", "z_tilde", "x")
+    st = {k: cols + (i % 3) for i, k in enumerate(names)}
+    v = {k: H.dense(rng, rows, cols, s, vt) for k, s in st.items()}
+    sc = {k: rng.uniform(0.3, 1, cols).astype(VT[vt])
+          for k in ("alpha", "beta", "gamma", "delta", "cos_prev", "cos", "sin_prev", "sin", "eta_next",
+                    "eta", "tau")}
+    stop = np.zeros(cols, dtype=np.uint8)
+    if cols > 4:
+        stop[1] = 1 | 0x40
+        sc["beta"][2] = 0    # safe_divide by zero
+        sc["alpha"][3] = 0
+    a, b = both(orc, cuda, "minres_initialize_" + vt,
+                lambda: [rows, cols, v["r"], st["r"]] +
+                sum([[v[k].copy(), st[k]] for k in ("z", "p", "p_prev", "q", "q_prev", "v")], []) +
+                [sc[k].copy() for k in ("beta", "gamma", "delta", "cos_prev", "cos", "sin_prev", "sin",
+                                        "eta_next", "eta")] + [np.full(cols, 0x81, np.uint8)])
+    _all_equal(a, b)
+    a, b = both(orc, cuda, "minres_step_1_" + vt,
+                lambda: [cols] + [sc[k].copy() for k in ("alpha", "beta", "gamma", "delta", "cos_prev",
+                                                        "cos", "sin_prev", "sin", "eta", "eta_next",
+                                                        "tau")] + [stop])
+    _all_equal(a, b)
+    # a column whose rotated alpha is exactly zero: gamma = 0, alpha = 0 -> cos = 0, sin = 1
+    if cols > 4:
+        z = {k: sc[k].copy() for k in sc}
+        z["alpha"][4] = 0
+        z["gamma"][4] = 0
+        a, b = both(orc, cuda, "minres_step_1_" + vt,
+                    lambda: [cols] + [z[k].copy() for k in ("alpha", "beta", "gamma", "delta", "cos_prev",
+                                                           "cos", "sin_prev", "sin", "eta", "eta_next",
+                                                           "tau")] + [stop])
+        _all_equal(a, b)
+    a, b = both(orc, cuda, "minres_step_2_" + vt,
+                lambda: [rows, cols, v["x"].copy(), st["x"], v["p"].copy(), st["p"], v["p_prev"], st["p_prev"],
+                         v["z"].copy(), st["z"], v["z_tilde"], st["z_tilde"], v["q"].copy(), st["q"],
+                         v["q_prev"].copy(), st["q_prev"], v["v"].copy(), st["v"], sc["alpha"], sc["beta"],
+                         sc["gamma"], sc["delta"], sc["cos"], sc["eta"], stop])
+    _all_equal(a, b)
+
+
 @pytest.mark.parametrize("kind,extra", [("ir", dict(relaxation_factor=0.9)), ("chebyshev", dict(foci=(0.4, 1.7))),
-                                        ("pipe_cg", {}), ("gcr", dict(krylov_dim=20))])
+                                        ("pipe_cg", {}), ("gcr", dict(krylov_dim=20)), ("minres", {})])
 @pytest.mark.parametrize("vt", ["f64", "f32"])
 def test_zy_ir_and_chebyshev_match_oracle(hexec, kind, extra, vt):
     """Jacobi-preconditioned Richardson / Chebyshev iteration: no inner products, so the device
@@ -112,7 +156,7 @@ def test_zy_ir_and_chebyshev_match_oracle(hexec, kind, extra, vt):
                                   iter_first=1, **extra)
     xd, itd, stop_d, _ = device_solve(hexec, kind, vt, rp, ci, va, b, x0, 1, None, max_iters=3000,
                                       reduction=red, iter_first=True, fused=False, **extra)
-    if kind in ("pipe_cg", "gcr"):  # dot products: tree vs sequential order (PipeCG amplifies it)
+    if kind in ("pipe_cg", "gcr", "minres"):  # dot products: tree vs sequential order (PipeCG amplifies it)
         assert abs(itd - ito) <= max(3, 0.2 * ito) and stop_d == stop_o[0]
         rd = true_rel_res(rp, ci, va, b, xd)
         assert rd[0] <= 20 * red, rd
