@@ -252,3 +252,38 @@ def test_host_ir_and_chebyshev(host, kind, extra, precond, vt):
                                          iter_first=bool(iter_first), **kw)
             assert (ith, stop_h) == (ito, stop_o[0])
             assert np.array_equal(xh, xo, equal_nan=True)
+
+
+@pytest.mark.parametrize("ortho", [0, 1, 2])
+@pytest.mark.parametrize("krylov_dim", [5, 30])
+def test_host_gmres_ortho_and_restart(host, ortho, krylov_dim):
+    """GMRES orthogonalisation variants (mgs / cgs / cgs2) and restarts through the C++ host loop"""
+    rp, ci, va = W.laplace(12, 2)
+    n = len(rp) - 1
+    rng = np.random.default_rng(4)
+    b = rng.uniform(-1, 1, (n, 3))
+    x0 = rng.uniform(-1, 1, (n, 3))
+    kw = dict(max_iters=80, reduction=1e-10, krylov_dim=krylov_dim, ortho=ortho)
+    xo, ito, stop_o = H.orc_solve("gmres", "f64", rp, ci, va, b, x0, 0, None, iter_first=1, **kw)
+    xh, ith, stop_h = host_solve(host, "gmres", "f64", rp, ci, va, b, x0, iter_first=True, **kw)
+    assert (ith, stop_h) == (ito, stop_o[0]) and np.array_equal(xh, xo)
+
+
+def test_host_advanced_solver_apply(host):
+    """x = alpha * solve(b) + beta * x  (core/solver/cg.cpp:184-200: clone, solve, scale, add_scaled)"""
+    from ginkgo_b200 import api
+    rp, ci, va = W.laplace(10, 2)
+    n = len(rp) - 1
+    rng = np.random.default_rng(8)
+    b = rng.uniform(-1, 1, (n, 1))
+    x0 = rng.uniform(-1, 1, (n, 1))
+    A = api.host_csr(host, (n, n), _t(va), _t(ci), _t(rp))
+    s = api.HostSolver(host, "cg", A, max_iters=200, reduction=1e-10, fused=False)
+    tx = _t(x0).clone()
+    al, be = torch.tensor([2.0], dtype=torch.float64), torch.tensor([-0.5], dtype=torch.float64)
+    ald, bed, bd, xd = (api.host_dense(host, t) for t in (al, be, _t(b), tx))
+    api._hcheck(api._host().gkob_apply4(s.obj.h, ald.h, bd.h, bed.h, xd.h))
+    xs, _, _ = host_solve(host, "cg", "f64", rp, ci, va, b, x0, max_iters=200, reduction=1e-10)
+    expect = x0 * -0.5
+    expect = expect + 2.0 * xs
+    assert np.array_equal(tx.numpy(), expect)
