@@ -684,6 +684,108 @@ int32_t b200_comm_p2p_error(b200_ctx* ctx, const b200_comm* comm);
 B200_DECL_COMM(f64, double)
 B200_DECL_COMM(f32, float)
 
+/* ---------------------------------------------------------------------------
+ * Distributed set-up on the device: what
+ * experimental::distributed::Matrix::read_distributed runs before the first apply
+ * (core/distributed/matrix.cpp:300-380).  G = global index type, L = local index type; the
+ * (L, G) pairs are the reference's (int32, int32), (int32, int64), (int64, int64).  A partition
+ * is passed as its arrays: range_bounds[num_ranges + 1], part_ids[num_ranges],
+ * range_starting_indices[num_ranges], part_sizes[num_parts]
+ * (include/ginkgo/core/distributed/partition.hpp:101-200).  `*_host` arguments are host
+ * pointers, written after a stream synchronisation.  All results are bit-exact against the
+ * reference kernels named below.
+ *
+ * partition:: (reference/distributed/partition_kernels.cpp)
+ *   build_ranges_from_global_size :75-92   ranges[num_parts + 1], uniform split
+ *   build_from_contiguous        :32-47   part_id_mapping may be NULL (part i owns range i)
+ *   count_ranges / build_from_mapping :18-29, :52-70   one range per run of equal owners
+ *   build_starting_indices       :97-113  local index of each range's first row + part sizes
+ *   has_ordered_parts            :138-153
+ * ------------------------------------------------------------------------- */
+b200_status b200_partition_count_ranges(b200_ctx* ctx, int64_t n, const int32_t* mapping,
+                                        int64_t* num_ranges_host);
+b200_status b200_partition_has_ordered_parts(b200_ctx* ctx, int64_t num_ranges, const int32_t* part_ids,
+                                             int32_t* result_host);
+/* distributed_matrix::separate_local_nonlocal (reference/distributed/matrix_kernels.cpp:18-90)
+ * in two steps.  classify_entries: cls[i] = 0 (row not owned by local_part), 1 (local column),
+ * 2 (non-local column); local_rank / non_local_rank [nnz + 1] = exclusive counts, i.e. the
+ * position of entry i in its output list (input order is kept, as in the reference);
+ * num_local_host / num_non_local_host = their lengths.  separate_fill writes the reference's six arrays (rows
+ * and local columns in local numbering, non-local columns still global); kept_fill writes all
+ * entries of the owned rows in input order with global columns -- the input of a matrix in the
+ * combined index space [local columns | remote columns].
+ *
+ * index_map (reference/distributed/index_map_kernels.cpp:20-105 build_mapping, :108-212
+ * map_to_local).  The set of remote indices is a bitmap over the global index space
+ * (global_size / 32 + 2 words) plus word_rank[words + 1], the number of set bits before each
+ * word; the reference's "sort + unique by (part id, global index)" position of a connected
+ * index g of range r is range_offsets[r] + (set bits of r below g).
+ *   mark:  bit g set for every global_idxs[i]; skip_part >= 0 ignores indices that part owns
+ *   rank:  word_rank, range_offsets[num_ranges], remote_sizes[num_parts] (entries received
+ *          from each part), num_remote_host
+ *   fill:  remote_global_idxs / remote_local_idxs (/ remote_part_ids, may be NULL), each
+ *          num_remote long, ordered by (part id, global index)
+ *   map_to_local: index_space 0 local, 1 non_local, 2 combined (non-local + local_size);
+ *          -1 (invalid_index) where the reference returns it */
+#define B200_DECL_DIST_G(G, GT)                                                                          \
+    b200_status b200_partition_build_ranges_from_global_size_##G(b200_ctx* ctx, int32_t num_parts,       \
+                                                                 int64_t global_size, GT* ranges);       \
+    b200_status b200_partition_build_from_contiguous_##G(b200_ctx* ctx, int64_t num_ranges,              \
+                                                         const GT* ranges,                               \
+                                                         const int32_t* part_id_mapping,                 \
+                                                         GT* range_bounds, int32_t* part_ids);           \
+    b200_status b200_partition_build_from_mapping_##G(b200_ctx* ctx, int64_t n, const int32_t* mapping,  \
+                                                      GT* range_bounds, int32_t* part_ids);              \
+    b200_status b200_dist_classify_entries_##G(                                                          \
+        b200_ctx* ctx, int64_t nnz, const GT* row_idxs, const GT* col_idxs, int64_t row_num_ranges,      \
+        const GT* row_bounds, const int32_t* row_part_ids, int64_t col_num_ranges, const GT* col_bounds, \
+        const int32_t* col_part_ids, int32_t local_part, uint8_t* cls, int64_t* local_rank,              \
+        int64_t* non_local_rank, int64_t* num_local_host, int64_t* num_non_local_host);                  \
+    b200_status b200_index_map_mark_##G(b200_ctx* ctx, int64_t global_size, int64_t num_ranges,          \
+                                        const GT* bounds, const int32_t* part_ids, int32_t skip_part,    \
+                                        int64_t m, const GT* global_idxs, uint32_t* bitmap);             \
+    b200_status b200_index_map_rank_##G(b200_ctx* ctx, int64_t global_size, int64_t num_ranges,          \
+                                        int32_t num_parts, const GT* bounds, const int32_t* part_ids,    \
+                                        const uint32_t* bitmap, int64_t* word_rank,                      \
+                                        int64_t* range_offsets, int64_t* remote_sizes,                   \
+                                        int64_t* num_remote_host);
+B200_DECL_DIST_G(i32, int32_t)
+B200_DECL_DIST_G(i64, int64_t)
+#define B200_DECL_DIST_LG(L, LT, G, GT)                                                                  \
+    b200_status b200_partition_build_starting_indices_##L##_##G(                                         \
+        b200_ctx* ctx, int64_t num_ranges, int32_t num_parts, const GT* range_bounds,                    \
+        const int32_t* part_ids, LT* starting_indices, LT* part_sizes, int32_t* num_empty_parts_host);   \
+    b200_status b200_index_map_fill_##L##_##G(                                                           \
+        b200_ctx* ctx, int64_t global_size, int64_t num_ranges, const GT* bounds,                        \
+        const int32_t* part_ids, const LT* starting, const uint32_t* bitmap, const int64_t* word_rank,   \
+        const int64_t* range_offsets, GT* remote_global_idxs, LT* remote_local_idxs,                     \
+        int32_t* remote_part_ids);                                                                       \
+    b200_status b200_index_map_map_to_local_##L##_##G(                                                   \
+        b200_ctx* ctx, int64_t global_size, int64_t num_ranges, const GT* bounds,                        \
+        const int32_t* part_ids, const LT* starting, const uint32_t* bitmap, const int64_t* word_rank,   \
+        const int64_t* range_offsets, int32_t rank, LT local_size, int32_t index_space, int64_t m,       \
+        const GT* global_ids, LT* local_ids);
+B200_DECL_DIST_LG(i32, int32_t, i32, int32_t)
+B200_DECL_DIST_LG(i32, int32_t, i64, int64_t)
+B200_DECL_DIST_LG(i64, int64_t, i64, int64_t)
+#define B200_DECL_DIST_VLG(V, VT, L, LT, G, GT)                                                          \
+    b200_status b200_dist_separate_fill_##V##_##L##_##G(                                                 \
+        b200_ctx* ctx, int64_t nnz, const GT* row_idxs, const GT* col_idxs, const VT* values,            \
+        int64_t row_num_ranges, const GT* row_bounds, const LT* row_starting, int64_t col_num_ranges,    \
+        const GT* col_bounds, const LT* col_starting, const uint8_t* cls, const int64_t* local_rank,     \
+        const int64_t* non_local_rank, LT* local_rows, LT* local_cols, VT* local_vals,                   \
+        LT* non_local_rows, GT* non_local_cols, VT* non_local_vals);                                     \
+    b200_status b200_dist_kept_fill_##V##_##L##_##G(                                                     \
+        b200_ctx* ctx, int64_t nnz, const GT* row_idxs, const GT* col_idxs, const VT* values,            \
+        int64_t row_num_ranges, const GT* row_bounds, const LT* row_starting, const uint8_t* cls,        \
+        const int64_t* local_rank, const int64_t* non_local_rank, LT* rows, GT* cols, VT* vals);
+#define B200_DECL_DIST_VLG_ALL(V, VT)                     \
+    B200_DECL_DIST_VLG(V, VT, i32, int32_t, i32, int32_t) \
+    B200_DECL_DIST_VLG(V, VT, i32, int32_t, i64, int64_t) \
+    B200_DECL_DIST_VLG(V, VT, i64, int64_t, i64, int64_t)
+B200_DECL_DIST_VLG_ALL(f64, double)
+B200_DECL_DIST_VLG_ALL(f32, float)
+
 #ifdef __cplusplus
 }
 #endif

@@ -139,6 +139,63 @@ ORC_CONVERT_FMT(i64, int64_t)
 ORC_FIND_BLOCKS(i32, int32_t)
 ORC_FIND_BLOCKS(i64, int64_t)
 
+/* ---- distributed set-up (partition, separate_local_nonlocal, index_map) ---- */
+#define G int32_t
+#define GS i32
+#include "oracle_dist.h"
+#define L int32_t
+#define LS i32
+#include "oracle_dist.h"
+#define V double
+#define VS f64
+#include "oracle_dist.h"
+#undef V
+#undef VS
+#define V float
+#define VS f32
+#include "oracle_dist.h"
+#undef V
+#undef VS
+#undef L
+#undef LS
+#undef G
+#undef GS
+#define G int64_t
+#define GS i64
+#include "oracle_dist.h"
+#define L int32_t
+#define LS i32
+#include "oracle_dist.h"
+#define V double
+#define VS f64
+#include "oracle_dist.h"
+#undef V
+#undef VS
+#define V float
+#define VS f32
+#include "oracle_dist.h"
+#undef V
+#undef VS
+#undef L
+#undef LS
+#define L int64_t
+#define LS i64
+#include "oracle_dist.h"
+#define V double
+#define VS f64
+#include "oracle_dist.h"
+#undef V
+#undef VS
+#define V float
+#define VS f32
+#include "oracle_dist.h"
+#undef V
+#undef VS
+#undef L
+#undef LS
+#undef G
+#undef GS
+
 /* ---- double ---- */
 #define V double
 #define VS f64

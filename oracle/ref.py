@@ -164,3 +164,72 @@ def write_mtx(path, layout, nrows, ncols, rows, cols, vals):
     st = lib().refshim_write_mtx(str(path).encode(), {"coordinate": 0, "array": 1, "binary": 2}[layout],
                                  nrows, ncols, len(vals), _p(rows), _p(cols), _p(vals))
     assert st == 0, st
+
+
+# ---- distributed set-up (reference Partition / separate_local_nonlocal / index_map) ----
+def partition(kind, mapping_or_ids=None, ranges=None, num_parts=0, global_size=0):
+    """kind 0: build_from_mapping(mapping, num_parts); 1: build_from_contiguous(ranges[, ids]);
+    2: build_from_global_size_uniform(num_parts, global_size).  Returns a dict."""
+    ids = None if mapping_or_ids is None else np.ascontiguousarray(mapping_or_ids, np.int32)
+    rg = None if ranges is None else np.ascontiguousarray(ranges, np.int64)
+    if kind == 0:
+        n = len(ids)
+        cap_r, cap_p = n + 1, num_parts
+    elif kind == 1:
+        n = len(rg) - 1
+        cap_r, cap_p = n + 1, n
+    else:
+        n = 0
+        cap_r, cap_p = num_parts + 1, num_parts
+    meta = np.zeros(6, np.int64)
+    bounds = np.zeros(cap_r + 1, np.int64)
+    pid = np.zeros(max(cap_r, 1), np.int32)
+    start = np.zeros(max(cap_r, 1), np.int32)
+    sizes = np.zeros(max(cap_p, 1), np.int32)
+    st = lib().refshim_partition(kind, n, _p(ids), _p(rg), num_parts, global_size, _p(meta), _p(bounds),
+                                 _p(pid), _p(start), _p(sizes))
+    assert st == 0, st
+    nr, npart = int(meta[1]), int(meta[2])
+    return dict(size=int(meta[0]), num_ranges=nr, num_parts=npart, num_empty_parts=int(meta[3]),
+                connected=bool(meta[4]), ordered=bool(meta[5]), range_bounds=bounds[:nr + 1].copy(),
+                part_ids=pid[:nr].copy(), starting_indices=start[:nr].copy(), part_sizes=sizes[:npart].copy())
+
+
+def separate_local_nonlocal(shape, rows, cols, vals, row_mapping, col_mapping, num_parts, local_part):
+    rows = np.ascontiguousarray(rows, np.int64)
+    cols = np.ascontiguousarray(cols, np.int64)
+    vals = np.ascontiguousarray(vals, np.float64)
+    rm = np.ascontiguousarray(row_mapping, np.int32)
+    cm = np.ascontiguousarray(col_mapping, np.int32)
+    nnz = len(rows)
+    cap = max(nnz, 1)
+    counts = np.zeros(2, np.int64)
+    lr, lc, nlr = (np.zeros(cap, np.int32) for _ in range(3))
+    nlc = np.zeros(cap, np.int64)
+    lv, nlv = np.zeros(cap), np.zeros(cap)
+    st = lib().refshim_separate_local_nonlocal(shape[0], shape[1], nnz, _p(rows), _p(cols), _p(vals), _p(rm),
+                                               _p(cm), num_parts, local_part, _p(counts), _p(lr), _p(lc),
+                                               _p(lv), _p(nlr), _p(nlc), _p(nlv))
+    assert st == 0, st
+    a, b = int(counts[0]), int(counts[1])
+    return (lr[:a], lc[:a], lv[:a]), (nlr[:b], nlc[:b], nlv[:b])
+
+
+def index_map(mapping, num_parts, rank, conns, index_space=0, query=None):
+    mp = np.ascontiguousarray(mapping, np.int32)
+    cn = np.ascontiguousarray(conns, np.int64)
+    m = len(cn)
+    meta = np.zeros(2, np.int64)
+    rg = np.zeros(max(m, 1), np.int64)
+    rl = np.zeros(max(m, 1), np.int32)
+    ids = np.zeros(max(num_parts, 1), np.int32)
+    sizes = np.zeros(max(num_parts, 1), np.int64)
+    q = None if query is None else np.ascontiguousarray(query, np.int64)
+    k = 0 if q is None else len(q)
+    ql = np.zeros(max(k, 1), np.int32)
+    st = lib().refshim_index_map(_p(mp), len(mp), num_parts, rank, m, _p(cn), _p(meta), _p(rg), _p(rl),
+                                 _p(ids), _p(sizes), index_space, k, _p(q), _p(ql))
+    assert st == 0, st
+    a, b = int(meta[0]), int(meta[1])
+    return dict(remote_global=rg[:a].copy(), remote_local=rl[:a].copy(), target_ids=ids[:b].copy(),
+                remote_sizes=sizes[:b].copy(), query_local=ql[:k].copy())

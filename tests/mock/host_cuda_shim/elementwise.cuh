@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE ONLY -- stands in for ginkgo_b200/csrc/elementwise.cuh (+ common.cuh) when
-// tests/test_kernel_sources_cpu.py compiles a COPY of an element-wise .cu file (krylov_steps.cu)
-// with plain g++: the extended lambdas of the kernels become ordinary lambdas and launch_ew runs
+// tests/test_kernel_sources_cpu.py / tests/test_dist_assembly_cpu.py compile a COPY of an
+// element-wise .cu file (krylov_steps.cu, dist_assembly.cu) with plain g++: the extended lambdas of the kernels become ordinary lambdas and launch_ew runs
 // them in a host loop over (row, col).  This checks the arithmetic written in the kernel bodies
 // against the oracle without a GPU; the launch mechanics themselves are exercised by the GPU
 // tests.  Compiled with -ffp-contract=off, the counterpart of nvcc's -fmad=false.
@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "ginkgo_b200.h"
@@ -19,9 +20,49 @@
 #define __forceinline__ inline
 #define __restrict__
 
+// the tests hand in a zero-filled 64-byte buffer as the context
 struct b200_ctx {
-    int64_t launches = 0;
+    int64_t launches;
+    void* scratch_buf;
+    size_t scratch_cap;
+    int stream;
+    void* scratch(size_t bytes)
+    {
+        if (bytes > scratch_cap) {
+            std::free(scratch_buf);
+            scratch_buf = std::malloc(bytes);
+            scratch_cap = bytes;
+        }
+        return scratch_buf;
+    }
 };
+
+// the few CUDA runtime / device names an element-wise file may use, on host memory
+enum cudaMemcpyKind { cudaMemcpyDeviceToHost = 2 };
+inline int cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind, int)
+{
+    std::memcpy(dst, src, bytes);
+    return 0;
+}
+inline int cudaStreamSynchronize(int) { return 0; }
+#define B200_CUDA_CHECK(expr) \
+    do {                      \
+        if ((expr) != 0) return B200_ERR_CUDA; \
+    } while (0)
+inline int __popc(unsigned int w) { return __builtin_popcount(w); }
+inline int __ffs(unsigned int w) { return __builtin_ffs((int)w); }
+inline unsigned int atomicOr(unsigned int* p, unsigned int v)
+{
+    const unsigned int old = *p;
+    *p = old | v;
+    return old;
+}
+inline int atomicAdd(int* p, int v)
+{
+    const int old = *p;
+    *p = old + v;
+    return old;
+}
 
 namespace b200 {
 
