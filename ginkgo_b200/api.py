@@ -240,6 +240,24 @@ def _configure_host_lib(h):
     h.gkob_apply.restype, h.gkob_apply.argtypes = i, [vp, vp, vp]
     h.gkob_apply4.restype, h.gkob_apply4.argtypes = i, [vp, vp, vp, vp, vp]
     h.gkob_synchronize.restype, h.gkob_synchronize.argtypes = i, [vp]
+    # distributed set-up
+    h.gkob_partition_from_mapping.restype, h.gkob_partition_from_mapping.argtypes = vp, [vp, vp, ll, i]
+    h.gkob_partition_from_contiguous.restype = vp
+    h.gkob_partition_from_contiguous.argtypes = [vp, vp, ll, vp]
+    h.gkob_partition_uniform.restype, h.gkob_partition_uniform.argtypes = vp, [vp, i, ll]
+    h.gkob_partition_info.restype, h.gkob_partition_info.argtypes = i, [vp, vp, vp, vp, vp, vp]
+    h.gkob_partition_destroy.restype, h.gkob_partition_destroy.argtypes = None, [vp]
+    h.gkob_dist_assemble_f64_i32.restype = vp
+    h.gkob_dist_assemble_f64_i32.argtypes = [vp, vp, vp, i, ll, ll, ll, vp, vp, vp]
+    h.gkob_dist_assembly_sizes.restype, h.gkob_dist_assembly_sizes.argtypes = i, [vp, vp]
+    h.gkob_dist_assembly_get.restype, h.gkob_dist_assembly_get.argtypes = i, [vp, vp, vp, vp, vp, vp, vp]
+    h.gkob_dist_assembly_map_to_local.restype = i
+    h.gkob_dist_assembly_map_to_local.argtypes = [vp, i, ll, vp, vp]
+    h.gkob_dist_assembly_destroy.restype, h.gkob_dist_assembly_destroy.argtypes = None, [vp]
+    h.gkob_dist_send_layout.restype, h.gkob_dist_send_layout.argtypes = i, [i, i, vp, vp, vp]
+    h.gkob_dist_matrix_read_f64_i32.restype = vp
+    h.gkob_dist_matrix_read_f64_i32.argtypes = [vp, vp, i, i, vp, ll, ll, ll, vp, vp, vp]
+    h.gkob_dist_matrix_sizes.restype, h.gkob_dist_matrix_sizes.argtypes = i, [vp, vp, vp]
     return h
 
 
@@ -414,16 +432,120 @@ class HostSolver:
 # ---------------------------------------------------------------------------------------------
 # Multi-GPU: row-partitioned Csr + fused distributed CG (C++: host/gko_b200_dist.hpp)
 # ---------------------------------------------------------------------------------------------
+def _np(a, dtype):
+    import numpy as np
+    return np.ascontiguousarray(a, dtype)
+
+
+class HostPartition:
+    """gko_b200::distributed::Partition<int32, int64> (experimental::distributed::Partition):
+    built on the device from host descriptions"""
+
+    def __init__(self, exec_, handle):
+        if not handle:
+            raise _lib.B200Error(_host().gkob_last_error().decode())
+        self.exec, self.h = exec_, handle
+
+    @classmethod
+    def from_mapping(cls, exec_, mapping, num_parts):
+        m = _np(mapping, "int32")
+        return cls(exec_, _host().gkob_partition_from_mapping(exec_.h, m.ctypes.data, len(m), num_parts))
+
+    @classmethod
+    def from_contiguous(cls, exec_, ranges, part_ids=None):
+        r = _np(ranges, "int64")
+        ids = None if part_ids is None else _np(part_ids, "int32")
+        if len(r) == 0 or (ids is not None and len(ids) != len(r) - 1):
+            raise DimensionMismatch("Partition: ranges needs num_ranges + 1 entries, part_ids num_ranges")
+        return cls(exec_, _host().gkob_partition_from_contiguous(
+            exec_.h, r.ctypes.data, len(r) - 1, None if ids is None else ids.ctypes.data))
+
+    @classmethod
+    def uniform(cls, exec_, num_parts, global_size):
+        return cls(exec_, _host().gkob_partition_uniform(exec_.h, num_parts, global_size))
+
+    def info(self):
+        import numpy as np
+        meta = np.zeros(6, np.int64)
+        _hcheck(_host().gkob_partition_info(self.h, meta.ctypes.data, None, None, None, None))
+        nr, npart = int(meta[1]), int(meta[2])
+        bounds = np.zeros(nr + 1, np.int64)
+        ids, start = np.zeros(max(nr, 1), np.int32), np.zeros(max(nr, 1), np.int32)
+        sizes = np.zeros(max(npart, 1), np.int32)
+        _hcheck(_host().gkob_partition_info(self.h, meta.ctypes.data, bounds.ctypes.data, ids.ctypes.data,
+                                            start.ctypes.data, sizes.ctypes.data))
+        return dict(size=int(meta[0]), num_ranges=nr, num_parts=npart, num_empty_parts=int(meta[3]),
+                    connected=bool(meta[4]), ordered=bool(meta[5]), range_bounds=bounds, part_ids=ids[:nr],
+                    starting_indices=start[:nr], part_sizes=sizes[:npart])
+
+    def __del__(self):
+        try:
+            _host().gkob_partition_destroy(self.h)
+        except Exception:
+            pass
+
+
+class HostAssembly:
+    """gko_b200::distributed::assemble_local<double, int32, int64>: what part `rank` owns of the
+    global (row-major sorted) triplets, columns in the combined index space"""
+
+    def __init__(self, exec_, row_part, rank, shape, rows, cols, vals, col_part=None):
+        import numpy as np
+        r, c, v = _np(rows, "int64"), _np(cols, "int64"), _np(vals, "float64")
+        self.h = _host().gkob_dist_assemble_f64_i32(
+            exec_.h, row_part.h, None if col_part is None else col_part.h, rank, shape[0], shape[1], len(r),
+            r.ctypes.data, c.ctypes.data, v.ctypes.data)
+        if not self.h:
+            msg = _host().gkob_last_error().decode()
+            raise (DimensionMismatch if msg.startswith("DimensionMismatch") else _lib.B200Error)(msg)
+        sz = np.zeros(5, np.int64)
+        _hcheck(_host().gkob_dist_assembly_sizes(self.h, sz.ctypes.data))
+        self.n_local_rows, self.n_local_cols, self.n_ghost, self.nnz, nparts = (int(x) for x in sz)
+        self.row_ptrs = np.zeros(self.n_local_rows + 1, np.int32)
+        self.col_idxs = np.zeros(max(self.nnz, 1), np.int32)
+        self.values = np.zeros(max(self.nnz, 1))
+        self.recv_counts = np.zeros(max(nparts, 1), np.int64)
+        self.remote_global = np.zeros(max(self.n_ghost, 1), np.int64)
+        self.remote_local = np.zeros(max(self.n_ghost, 1), np.int32)
+        _hcheck(_host().gkob_dist_assembly_get(self.h, self.row_ptrs.ctypes.data, self.col_idxs.ctypes.data,
+                                               self.values.ctypes.data, self.recv_counts.ctypes.data,
+                                               self.remote_global.ctypes.data, self.remote_local.ctypes.data))
+        self.col_idxs, self.values = self.col_idxs[:self.nnz], self.values[:self.nnz]
+        self.recv_counts = self.recv_counts[:nparts]
+        self.remote_global, self.remote_local = self.remote_global[:self.n_ghost], self.remote_local[:self.n_ghost]
+
+    def map_to_local(self, global_ids, index_space):
+        import numpy as np
+        g = _np(global_ids, "int64")
+        out = np.zeros(max(len(g), 1), np.int32)
+        _hcheck(_host().gkob_dist_assembly_map_to_local(self.h, index_space, len(g), g.ctypes.data,
+                                                        out.ctypes.data))
+        return out[:len(g)]
+
+    def __del__(self):
+        try:
+            _host().gkob_dist_assembly_destroy(self.h)
+        except Exception:
+            pass
+
+
+def host_send_layout(num_parts, rank, S):
+    """S[q][p] = entries rank q receives from p -> (send_counts, source_offsets) of `rank`"""
+    import numpy as np
+    S = _np(S, "int64")
+    sc, so = np.zeros(num_parts, np.int64), np.zeros(num_parts, np.int64)
+    _hcheck(_host().gkob_dist_send_layout(num_parts, rank, S.ctypes.data, sc.ctypes.data, so.ctypes.data))
+    return sc, so
+
+
 class DistMatrix:
     """experimental::distributed::Matrix analogue.  Each rank passes ITS rows (row_ptrs local,
     col_idxs GLOBAL, values) and the partition offsets; set-up uses torch.distributed
     (ginkgo_b200/distributed.py), the per-apply halo exchange uses the library's own NCCL
     communicator on the executor's stream."""
 
-    def __init__(self, exec_, offsets, row_ptrs, col_idxs_global, values, group=None):
-        import torch.distributed as dist
-        from . import distributed as D
-        h = _host()
+    @staticmethod
+    def _bind(h):
         vp, ll, i = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int
         h.gkob_dist_unique_id.restype, h.gkob_dist_unique_id.argtypes = i, [vp]
         h.gkob_dist_matrix_create_f64_i32.restype = vp
@@ -436,6 +558,28 @@ class DistMatrix:
         h.gkob_dist_cg_apply_f64.argtypes = [vp, vp, vp, ctypes.POINTER(ll),
                                              ctypes.POINTER(ctypes.c_ubyte)]
         h.gkob_dist_destroy.argtypes = [vp]
+
+    @staticmethod
+    def _unique_id(exec_, rank, world, group):
+        """NCCL unique id from rank 0, broadcast over torch.distributed"""
+        import torch.distributed as dist
+        h = _host()
+        idt = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (ctypes.c_ubyte * 128)()
+            _hcheck(h.gkob_dist_unique_id(buf))
+            idt = torch.tensor(list(buf), dtype=torch.uint8)
+        if world > 1:
+            idt = idt.to(exec_.device)
+            dist.broadcast(idt, 0, group=group)
+            idt = idt.cpu()
+        return (ctypes.c_ubyte * 128)(*idt.tolist())
+
+    def __init__(self, exec_, offsets, row_ptrs, col_idxs_global, values, group=None):
+        import torch.distributed as dist
+        from . import distributed as D
+        h = _host()
+        self._bind(h)
         self.exec = exec_
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -447,17 +591,7 @@ class DistMatrix:
         self.row_ptrs, self.values = row_ptrs, values
         self.col_idxs = part["col_idxs_local"].contiguous()
         self.send_idx = part["send_idx"].contiguous()
-        # NCCL unique id from rank 0
-        idt = torch.zeros(128, dtype=torch.uint8)
-        if self.rank == 0:
-            buf = (ctypes.c_ubyte * 128)()
-            _hcheck(h.gkob_dist_unique_id(buf))
-            idt = torch.tensor(list(buf), dtype=torch.uint8)
-        if self.world > 1:
-            idt = idt.to(exec_.device)
-            dist.broadcast(idt, 0, group=group)
-            idt = idt.cpu()
-        idb = (ctypes.c_ubyte * 128)(*idt.tolist())
+        idb = self._unique_id(exec_, self.rank, self.world, group)
         sc = (ctypes.c_longlong * self.world)(*part["send_counts"].tolist())
         rc = (ctypes.c_longlong * self.world)(*part["recv_counts"].tolist())
         self.h = h.gkob_dist_matrix_create_f64_i32(
@@ -466,6 +600,34 @@ class DistMatrix:
             self.send_idx.data_ptr() if self.send_idx.numel() else None)
         if not self.h:
             raise _lib.B200Error(h.gkob_last_error().decode())
+
+    @classmethod
+    def read(cls, exec_, partition, shape, rows, cols, vals, group=None):
+        """experimental::distributed::Matrix::read_distributed: every rank passes the global
+        (row-major sorted) triplets -- or at least its own rows -- and a HostPartition with one
+        part per rank; the split, the column renumbering and the exchange of the send lists run
+        in the library (device kernels + its own communicator).  Collective."""
+        import torch.distributed as dist
+        h = _host()
+        cls._bind(h)
+        self = cls.__new__(cls)
+        self.exec = exec_
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        idb = cls._unique_id(exec_, self.rank, self.world, group)
+        r, c, v = _np(rows, "int64"), _np(cols, "int64"), _np(vals, "float64")
+        self.h = h.gkob_dist_matrix_read_f64_i32(exec_.h, idb, self.rank, self.world, partition.h, shape[0],
+                                                 shape[1], len(r), r.ctypes.data, c.ctypes.data, v.ctypes.data)
+        if not self.h:
+            raise _lib.B200Error(h.gkob_last_error().decode())
+        import numpy as np
+        sz = np.zeros(3, np.int64)
+        _hcheck(h.gkob_dist_matrix_sizes(self.h, sz.ctypes.data, None))
+        self.n_local, self.n_local_cols, self.n_ghost = (int(x) for x in sz)
+        self.ghost_globals = np.zeros(max(self.n_ghost, 1), np.int64)
+        _hcheck(h.gkob_dist_matrix_sizes(self.h, sz.ctypes.data, self.ghost_globals.ctypes.data))
+        self.ghost_globals = self.ghost_globals[:self.n_ghost]
+        return self
 
     @property
     def p2p(self):

@@ -651,6 +651,20 @@ int64_t b200_halo_num_send(const b200_halo* h) { return h->n_send; }
 B200_DEF_COMM(f64, double)
 B200_DEF_COMM(f32, float)
 
+// all-gather of `bytes_per_rank` raw device bytes per rank (set-up exchanges of index lists
+// and counts: distributed::Matrix::read_distributed)
+b200_status b200_comm_allgather_bytes(b200_ctx* ctx, b200_comm* comm, const void* send, void* recv,
+                                      int64_t bytes_per_rank)
+{
+    B200_REQUIRE(ctx && comm && (bytes_per_rank == 0 || (send && recv)), "null argument");
+    B200_REQUIRE(bytes_per_rank >= 0, "negative size");
+    if (bytes_per_rank == 0) return B200_OK;
+    auto& a = b200::nccl::api();
+    B200_NCCL_CHECK(a.AllGather(send, recv, (size_t)bytes_per_rank, b200::nccl::ncclUint8, comm->comm,
+                                ctx->stream));
+    return B200_OK;
+}
+
 // Halo plan from the partition set-up (done by the host side with torch.distributed, see
 // ginkgo_b200/distributed.py): per-peer counts (host arrays of nranks entries) and the
 // device list of owned entries to pack, grouped by destination rank.

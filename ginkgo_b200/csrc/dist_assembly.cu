@@ -17,7 +17,7 @@
 //     rank(g) = offset of g's range in (part, range) order + set bits of that range below g.
 //     1/8 byte + 1/4 byte per global column instead of a sort of the non-local entries.
 // Element-wise lambdas only, so a copy of this file also compiles for the host and is checked
-// against the oracle without a GPU (tests/test_dist_assembly_cpu.py).
+// there without a GPU (tests/test_dist_assembly_cpu.py).
 #include "elementwise.cuh"
 #include "scan.cuh"
 

@@ -492,6 +492,215 @@ int gkob_dist_cg_apply_f64(void* dist, const double* b_local, double* x_local, l
 
 void gkob_dist_destroy(void* dist) { delete static_cast<DistHandle*>(dist); }
 
+// ---- distributed set-up: Partition<int32, int64>, assemble_local, read_distributed ---------
+using part_t = distributed::Partition<int32, int64>;
+struct PartHandle {
+    std::shared_ptr<Executor> exec;
+    std::shared_ptr<const part_t> part;
+};
+struct AssemblyHandle {
+    std::shared_ptr<Executor> exec;
+    distributed::local_assembly<double, int32, int64> a;
+};
+
+void* gkob_partition_from_mapping(void* exec, const int* mapping_host, long long n, int num_parts)
+{
+    auto e = static_cast<Handle*>(exec)->exec;
+    auto h = new PartHandle{e, nullptr};
+    if (guarded([&] {
+            array<int32> m(e, std::vector<int32>(mapping_host, mapping_host + n));
+            h->part = part_t::build_from_mapping(e, m, num_parts);
+        })) {
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+
+void* gkob_partition_from_contiguous(void* exec, const long long* ranges_host, long long num_ranges,
+                                     const int* part_ids_host)
+{
+    auto e = static_cast<Handle*>(exec)->exec;
+    auto h = new PartHandle{e, nullptr};
+    if (guarded([&] {
+            array<int64> r(e, std::vector<int64>(ranges_host, ranges_host + num_ranges + 1));
+            if (part_ids_host) {
+                array<int32> ids(e, std::vector<int32>(part_ids_host, part_ids_host + num_ranges));
+                h->part = part_t::build_from_contiguous(e, r, ids);
+            } else {
+                h->part = part_t::build_from_contiguous(e, r);
+            }
+        })) {
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+
+void* gkob_partition_uniform(void* exec, int num_parts, long long global_size)
+{
+    auto e = static_cast<Handle*>(exec)->exec;
+    auto h = new PartHandle{e, nullptr};
+    if (guarded([&] { h->part = part_t::build_from_global_size_uniform(e, num_parts, global_size); })) {
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+
+// meta = {size, num_ranges, num_parts, num_empty_parts, has_connected_parts, has_ordered_parts};
+// the arrays (may be NULL) are copied to the host
+int gkob_partition_info(void* part, long long* meta, long long* bounds, int* part_ids, int* starting,
+                        int* sizes)
+{
+    return guarded([&] {
+        auto h = static_cast<PartHandle*>(part);
+        auto& p = *h->part;
+        const size_type nr = p.get_num_ranges();
+        meta[0] = (long long)p.get_size();
+        meta[1] = (long long)nr;
+        meta[2] = p.get_num_parts();
+        meta[3] = p.get_num_empty_parts();
+        meta[4] = p.has_connected_parts();
+        meta[5] = p.has_ordered_parts();
+        if (bounds) {
+            std::vector<int64> b(nr + 1);
+            h->exec->copy_to_host(b.data(), p.get_range_bounds(), nr + 1);
+            std::copy(b.begin(), b.end(), bounds);
+        }
+        if (part_ids && nr) h->exec->copy_to_host(part_ids, p.get_part_ids(), nr);
+        if (starting && nr) h->exec->copy_to_host(starting, p.get_range_starting_indices(), nr);
+        if (sizes && p.get_num_parts())
+            h->exec->copy_to_host(sizes, p.get_part_sizes(), (size_type)p.get_num_parts());
+    });
+}
+
+void gkob_partition_destroy(void* part) { delete static_cast<PartHandle*>(part); }
+
+static matrix_data<double, int64> triplets(long long nrows, long long ncols, long long nnz, const long long* rows,
+                                           const long long* cols, const double* vals)
+{
+    matrix_data<double, int64> d(dim2{(size_type)nrows, (size_type)ncols});
+    d.nonzeros.reserve((size_t)nnz);
+    for (long long i = 0; i < nnz; ++i) d.nonzeros.push_back({(int64)rows[i], (int64)cols[i], vals[i]});
+    return d;
+}
+
+// the communication-free part of read_distributed for part `rank` (col_part may be NULL)
+void* gkob_dist_assemble_f64_i32(void* exec, void* row_part, void* col_part, int rank, long long nrows,
+                                 long long ncols, long long nnz, const long long* rows, const long long* cols,
+                                 const double* vals)
+{
+    auto e = static_cast<Handle*>(exec)->exec;
+    auto h = new AssemblyHandle{e, {}};
+    if (guarded([&] {
+            auto rp = static_cast<PartHandle*>(row_part)->part;
+            auto cp = col_part ? static_cast<PartHandle*>(col_part)->part : rp;
+            h->a = distributed::assemble_local<double, int32, int64>(
+                e, triplets(nrows, ncols, nnz, rows, cols, vals), rp, cp, rank);
+        })) {
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+
+// out = {n_local_rows, n_local_cols, n_ghost, nnz of the local block, num_parts}
+int gkob_dist_assembly_sizes(void* assembly, long long* out)
+{
+    return guarded([&] {
+        auto& a = static_cast<AssemblyHandle*>(assembly)->a;
+        out[0] = (long long)a.n_local_rows;
+        out[1] = (long long)a.n_local_cols;
+        out[2] = (long long)a.n_ghost;
+        out[3] = (long long)a.local->get_num_stored_elements();
+        out[4] = (long long)a.imap->get_remote_sizes().size();
+    });
+}
+
+int gkob_dist_assembly_get(void* assembly, int* row_ptrs, int* col_idxs, double* values,
+                           long long* recv_counts, long long* remote_global, int* remote_local)
+{
+    return guarded([&] {
+        auto h = static_cast<AssemblyHandle*>(assembly);
+        auto& a = h->a;
+        const size_type nnz = a.local->get_num_stored_elements();
+        h->exec->copy_to_host(row_ptrs, a.local->get_const_row_ptrs(), a.n_local_rows + 1);
+        if (nnz) {
+            h->exec->copy_to_host(col_idxs, a.local->get_const_col_idxs(), nnz);
+            h->exec->copy_to_host(values, a.local->get_const_values(), nnz);
+        }
+        const auto& rs = a.imap->get_remote_sizes();
+        std::copy(rs.begin(), rs.end(), recv_counts);
+        if (a.n_ghost) {
+            const auto rg = a.imap->get_remote_global_idxs().to_host();
+            std::copy(rg.begin(), rg.end(), remote_global);
+            h->exec->copy_to_host(remote_local, a.imap->get_remote_local_idxs().get_const_data(), a.n_ghost);
+        }
+    });
+}
+
+int gkob_dist_assembly_map_to_local(void* assembly, int index_space, long long m, const long long* gids_host,
+                                    int* out_host)
+{
+    return guarded([&] {
+        auto h = static_cast<AssemblyHandle*>(assembly);
+        array<int64> g(h->exec, std::vector<int64>(gids_host, gids_host + m));
+        auto res = h->a.imap->map_to_local(g, (distributed::index_space)index_space).to_host();
+        std::copy(res.begin(), res.end(), out_host);
+    });
+}
+
+void gkob_dist_assembly_destroy(void* assembly) { delete static_cast<AssemblyHandle*>(assembly); }
+
+// S[q * P + p] = entries rank q receives from p  ->  what `rank` sends to every q and where
+// those entries start in q's remote list
+int gkob_dist_send_layout(int P, int rank, const long long* S, long long* send_counts,
+                          long long* source_offsets)
+{
+    return guarded([&] {
+        const auto l = distributed::compute_send_layout(std::vector<int64>(S, S + (size_t)P * P), P, rank);
+        std::copy(l.send_counts.begin(), l.send_counts.end(), send_counts);
+        std::copy(l.source_offsets.begin(), l.source_offsets.end(), source_offsets);
+    });
+}
+
+// collective: distributed::Matrix::read_distributed of the global triplets (row-major sorted)
+void* gkob_dist_matrix_read_f64_i32(void* exec, const unsigned char* id128, int rank, int nranks,
+                                    void* row_part, long long nrows, long long ncols, long long nnz,
+                                    const long long* rows, const long long* cols, const double* vals)
+{
+    auto e = static_cast<Handle*>(exec)->exec;
+    auto h = new DistHandle();
+    h->exec = e;
+    if (guarded([&] {
+            h->comm = distributed::communicator::create(e, id128, rank, nranks);
+            h->A = distributed::Matrix<double, int32>::read_distributed<int64>(
+                e, h->comm, triplets(nrows, ncols, nnz, rows, cols, vals),
+                static_cast<PartHandle*>(row_part)->part);
+        })) {
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+
+// out = {n_local rows, n_local columns, n_ghost}; ghost_globals (may be NULL): n_ghost entries
+int gkob_dist_matrix_sizes(void* dist, long long* out, long long* ghost_globals)
+{
+    return guarded([&] {
+        auto h = static_cast<DistHandle*>(dist);
+        out[0] = (long long)h->A->n_local();
+        out[1] = (long long)h->A->n_local_cols();
+        out[2] = (long long)h->A->n_ghost();
+        if (ghost_globals) {
+            const auto& g = h->A->get_non_local_to_global();
+            std::copy(g.begin(), g.end(), ghost_globals);
+        }
+    });
+}
+
+
 // bit 0: all-reduces run on peer memory, bit 1: the halo exchange does
 int gkob_dist_p2p(void* dist)
 {

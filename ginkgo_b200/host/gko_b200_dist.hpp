@@ -5,10 +5,13 @@
 // One process per GPU; rank p owns rows [offsets[p], offsets[p+1]).
 #pragma once
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <numeric>
 
 #include "gko_b200.hpp"
+#include "gko_b200_io.hpp"
 
 namespace gko_b200 {
 namespace distributed {
@@ -67,6 +70,337 @@ struct cabi<float> {
     static constexpr auto halo_exchange = b200_halo_exchange_f32;
 };
 
+// C-ABI tables of the distributed set-up kernels, by global / (local, global) / (value, local,
+// global) types
+template <typename I>
+struct iabi;
+template <>
+struct iabi<int32> {
+    static constexpr auto convert_idxs_to_ptrs = b200_convert_idxs_to_ptrs_i32;
+};
+template <>
+struct iabi<int64> {
+    static constexpr auto convert_idxs_to_ptrs = b200_convert_idxs_to_ptrs_i64;
+};
+template <typename G>
+struct gabi;
+template <typename L, typename G>
+struct lgabi;
+template <typename V, typename L, typename G>
+struct vlgabi;
+#define GKOB_G(G, S)                                                                                  \
+    template <>                                                                                       \
+    struct gabi<G> {                                                                                  \
+        static constexpr auto build_ranges_from_global_size =                                         \
+            b200_partition_build_ranges_from_global_size_##S;                                         \
+        static constexpr auto build_from_contiguous = b200_partition_build_from_contiguous_##S;       \
+        static constexpr auto build_from_mapping = b200_partition_build_from_mapping_##S;             \
+        static constexpr auto classify_entries = b200_dist_classify_entries_##S;                      \
+        static constexpr auto index_map_mark = b200_index_map_mark_##S;                               \
+        static constexpr auto index_map_rank = b200_index_map_rank_##S;                               \
+    };
+GKOB_G(int32, i32)
+GKOB_G(int64, i64)
+#define GKOB_LG(L, LS, G, GS)                                                                         \
+    template <>                                                                                       \
+    struct lgabi<L, G> {                                                                              \
+        static constexpr auto build_starting_indices = b200_partition_build_starting_indices_##LS##_##GS; \
+        static constexpr auto index_map_fill = b200_index_map_fill_##LS##_##GS;                       \
+        static constexpr auto index_map_map_to_local = b200_index_map_map_to_local_##LS##_##GS;       \
+    };
+GKOB_LG(int32, i32, int32, i32)
+GKOB_LG(int32, i32, int64, i64)
+GKOB_LG(int64, i64, int64, i64)
+#define GKOB_VLG(V, VS, L, LS, G, GS)                                                                 \
+    template <>                                                                                       \
+    struct vlgabi<V, L, G> {                                                                          \
+        static constexpr auto separate_fill = b200_dist_separate_fill_##VS##_##LS##_##GS;             \
+        static constexpr auto kept_fill = b200_dist_kept_fill_##VS##_##LS##_##GS;                     \
+    };
+GKOB_VLG(double, f64, int32, i32, int32, i32)
+GKOB_VLG(double, f64, int32, i32, int64, i64)
+GKOB_VLG(double, f64, int64, i64, int64, i64)
+GKOB_VLG(float, f32, int32, i32, int32, i32)
+GKOB_VLG(float, f32, int32, i32, int64, i64)
+GKOB_VLG(float, f32, int64, i64, int64, i64)
+
+using comm_index_type = int32;
+enum class index_space { local = 0, non_local = 1, combined = 2 };
+
+// experimental::distributed::Partition (include/ginkgo/core/distributed/partition.hpp:83-290,
+// core/distributed/partition.cpp): ranges of global indices, each owned by one part; all
+// arrays live on the device and are built by device kernels.
+template <typename L = int32, typename G = int64>
+class Partition {
+public:
+    using local_index_type = L;
+    using global_index_type = G;
+
+    // one range per run of equal owners in `mapping` (device array of part ids)
+    static std::unique_ptr<Partition> build_from_mapping(std::shared_ptr<const Executor> exec,
+                                                         const array<comm_index_type>& mapping,
+                                                         comm_index_type num_parts)
+    {
+        int64 num_ranges = 0;
+        GKOB_CALL(b200_partition_count_ranges(exec->ctx(), (int64)mapping.get_size(),
+                                              mapping.get_const_data(), &num_ranges));
+        auto p = std::unique_ptr<Partition>(new Partition(exec, num_parts, (size_type)num_ranges));
+        GKOB_CALL(gabi<G>::build_from_mapping(exec->ctx(), (int64)mapping.get_size(),
+                                              mapping.get_const_data(), p->offsets_.get_data(),
+                                              p->part_ids_.get_data()));
+        p->finalize_construction();
+        return p;
+    }
+    // ranges[i], ranges[i+1] bound range i; part_ids (optional) names its owner, default part i
+    static std::unique_ptr<Partition> build_from_contiguous(std::shared_ptr<const Executor> exec,
+                                                            const array<G>& ranges,
+                                                            const array<comm_index_type>& part_ids = {})
+    {
+        if (ranges.get_size() == 0) throw BadDimension("Partition: ranges needs at least one entry");
+        const size_type n = ranges.get_size() - 1;
+        if (part_ids.get_size() != 0 && part_ids.get_size() != n)
+            throw BadDimension("Partition: part_ids must have one entry per range");
+        auto p = std::unique_ptr<Partition>(new Partition(exec, (comm_index_type)n, n));
+        GKOB_CALL(gabi<G>::build_from_contiguous(exec->ctx(), (int64)n, ranges.get_const_data(),
+                                                 part_ids.get_size() ? part_ids.get_const_data() : nullptr,
+                                                 p->offsets_.get_data(), p->part_ids_.get_data()));
+        p->finalize_construction();
+        return p;
+    }
+    static std::unique_ptr<Partition> build_from_global_size_uniform(std::shared_ptr<const Executor> exec,
+                                                                     comm_index_type num_parts,
+                                                                     G global_size)
+    {
+        array<G> ranges(exec, (size_type)num_parts + 1);
+        // zero parts: the single bound is 0 whatever the size (partition.cpp:106-111)
+        GKOB_CALL(gabi<G>::build_ranges_from_global_size(exec->ctx(), num_parts,
+                                                         num_parts ? (int64)global_size : 0,
+                                                         ranges.get_data()));
+        return build_from_contiguous(exec, ranges);
+    }
+
+    size_type get_size() const { return size_; }
+    size_type get_num_ranges() const noexcept { return offsets_.get_size() - 1; }
+    comm_index_type get_num_parts() const noexcept { return num_parts_; }
+    comm_index_type get_num_empty_parts() const noexcept { return num_empty_parts_; }
+    // device pointers
+    const G* get_range_bounds() const noexcept { return offsets_.get_const_data(); }
+    const comm_index_type* get_part_ids() const noexcept { return part_ids_.get_const_data(); }
+    const L* get_range_starting_indices() const noexcept { return starting_indices_.get_const_data(); }
+    const L* get_part_sizes() const noexcept { return part_sizes_.get_const_data(); }
+    L get_part_size(comm_index_type part) const
+    {
+        if (part < 0 || part >= num_parts_) throw OutOfBounds("Partition::get_part_size");
+        return host_part_sizes_[part];
+    }
+    bool has_connected_parts() const
+    {
+        return (size_type)(num_parts_ - num_empty_parts_) == get_num_ranges();
+    }
+    bool has_ordered_parts() const
+    {
+        if (!has_connected_parts()) return false;
+        int32 res = 0;
+        GKOB_CALL(b200_partition_has_ordered_parts(exec_->ctx(), (int64)get_num_ranges(),
+                                                   part_ids_.get_const_data(), &res));
+        return res != 0;
+    }
+    std::shared_ptr<const Executor> get_executor() const { return exec_; }
+
+private:
+    Partition(std::shared_ptr<const Executor> exec, comm_index_type num_parts, size_type num_ranges)
+        : exec_(exec),
+          num_parts_(num_parts),
+          offsets_(exec, num_ranges + 1),
+          starting_indices_(exec, num_ranges),
+          part_sizes_(exec, (size_type)num_parts),
+          part_ids_(exec, num_ranges)
+    {}
+    void finalize_construction()
+    {
+        int32 empty = 0;
+        GKOB_CALL((lgabi<L, G>::build_starting_indices(
+            exec_->ctx(), (int64)get_num_ranges(), num_parts_, offsets_.get_const_data(),
+            part_ids_.get_const_data(), starting_indices_.get_data(), part_sizes_.get_data(), &empty)));
+        num_empty_parts_ = empty;
+        G last = 0;
+        exec_->copy_to_host(&last, offsets_.get_const_data() + get_num_ranges(), 1);
+        size_ = (size_type)last;
+        host_part_sizes_ = part_sizes_.to_host();
+    }
+    std::shared_ptr<const Executor> exec_;
+    comm_index_type num_parts_;
+    comm_index_type num_empty_parts_ = 0;
+    size_type size_ = 0;
+    array<G> offsets_;
+    array<L> starting_indices_;
+    array<L> part_sizes_;
+    array<comm_index_type> part_ids_;
+    std::vector<L> host_part_sizes_;
+};
+
+// experimental::distributed::index_map (include/ginkgo/core/distributed/index_map.hpp:60-200):
+// the remote indices a rank touches, ordered by (owning part, global index), and the maps
+// between the global and the local / non-local / combined index spaces.
+template <typename L = int32, typename G = int64>
+class index_map {
+public:
+    using partition_type = Partition<L, G>;
+    // `connections`: device array of global indices; entries owned by `rank` are ignored
+    index_map(std::shared_ptr<const Executor> exec, std::shared_ptr<const partition_type> part,
+              comm_index_type rank, const array<G>& connections)
+        : exec_(exec), part_(part), rank_(rank)
+    {
+        if (rank < 0 || rank >= part->get_num_parts()) throw OutOfBounds("index_map: rank");
+        const int64 gs = (int64)part->get_size(), nr = (int64)part->get_num_ranges();
+        const int64 words = (gs + 31) / 32;
+        bitmap_ = array<uint32>(exec, (size_type)words + 1);
+        word_rank_ = array<int64>(exec, (size_type)words + 1);
+        range_offsets_ = array<int64>(exec, (size_type)nr);
+        array<int64> sizes(exec, (size_type)part->get_num_parts());
+        auto ctx = exec->ctx();
+        GKOB_CALL(gabi<G>::index_map_mark(ctx, gs, nr, part->get_range_bounds(), part->get_part_ids(), rank,
+                                          (int64)connections.get_size(), connections.get_const_data(),
+                                          bitmap_.get_data()));
+        int64 num_remote = 0;
+        GKOB_CALL(gabi<G>::index_map_rank(ctx, gs, nr, part->get_num_parts(), part->get_range_bounds(),
+                                          part->get_part_ids(), bitmap_.get_const_data(),
+                                          word_rank_.get_data(), range_offsets_.get_data(), sizes.get_data(),
+                                          &num_remote));
+        remote_sizes_ = sizes.to_host();
+        remote_global_idxs_ = array<G>(exec, (size_type)num_remote);
+        remote_local_idxs_ = array<L>(exec, (size_type)num_remote);
+        GKOB_CALL((lgabi<L, G>::index_map_fill(
+            ctx, gs, nr, part->get_range_bounds(), part->get_part_ids(), part->get_range_starting_indices(),
+            bitmap_.get_const_data(), word_rank_.get_const_data(), range_offsets_.get_const_data(),
+            remote_global_idxs_.get_data(), remote_local_idxs_.get_data(), nullptr)));
+    }
+    size_type get_global_size() const { return part_->get_size(); }
+    size_type get_local_size() const { return (size_type)part_->get_part_size(rank_); }
+    size_type get_non_local_size() const { return remote_global_idxs_.get_size(); }
+    // flat device arrays ordered by (part, global index); segment p has get_remote_sizes()[p] entries
+    const array<G>& get_remote_global_idxs() const { return remote_global_idxs_; }
+    const array<L>& get_remote_local_idxs() const { return remote_local_idxs_; }
+    const std::vector<int64>& get_remote_sizes() const { return remote_sizes_; }
+    // the parts this rank receives from (the reference's get_remote_target_ids)
+    std::vector<comm_index_type> get_remote_target_ids() const
+    {
+        std::vector<comm_index_type> ids;
+        for (size_type p = 0; p < remote_sizes_.size(); ++p)
+            if (remote_sizes_[p]) ids.push_back((comm_index_type)p);
+        return ids;
+    }
+    // global -> local / non-local / combined index; invalid_index (-1) where not representable
+    array<L> map_to_local(const array<G>& global_ids, index_space is) const
+    {
+        array<L> out(exec_, global_ids.get_size());
+        map_to_local(global_ids.get_const_data(), global_ids.get_size(), is, out.get_data());
+        return out;
+    }
+    void map_to_local(const G* global_ids, size_type m, index_space is, L* local_ids) const
+    {
+        GKOB_CALL((lgabi<L, G>::index_map_map_to_local(
+            exec_->ctx(), (int64)part_->get_size(), (int64)part_->get_num_ranges(), part_->get_range_bounds(),
+            part_->get_part_ids(), part_->get_range_starting_indices(), bitmap_.get_const_data(),
+            word_rank_.get_const_data(), range_offsets_.get_const_data(), rank_,
+            (L)part_->get_part_size(rank_), (int32)is, (int64)m, global_ids, local_ids)));
+    }
+
+private:
+    std::shared_ptr<const Executor> exec_;
+    std::shared_ptr<const partition_type> part_;
+    comm_index_type rank_;
+    array<uint32> bitmap_;
+    array<int64> word_rank_, range_offsets_;
+    array<G> remote_global_idxs_;
+    array<L> remote_local_idxs_;
+    std::vector<int64> remote_sizes_;
+};
+
+// What one rank owns of a global matrix, in the combined index space of its columns
+// [local columns | remote columns ordered by (part, global index)]: the communication-free
+// part of Matrix::read_distributed (core/distributed/matrix.cpp:343-373).  `data` must be
+// sorted row-major like the reference requires of device_matrix_data handed to Csr::read.
+template <typename V, typename I, typename G>
+struct local_assembly {
+    std::unique_ptr<matrix::Csr<V, I>> local;  // n_local_rows x (n_local_cols + n_ghost)
+    size_type n_local_rows = 0, n_local_cols = 0, n_ghost = 0;
+    std::unique_ptr<index_map<I, G>> imap;     // remote columns of this rank
+};
+
+template <typename V, typename I, typename G>
+local_assembly<V, I, G> assemble_local(std::shared_ptr<const Executor> exec, const matrix_data<V, G>& data,
+                                       std::shared_ptr<const Partition<I, G>> row_part,
+                                       std::shared_ptr<const Partition<I, G>> col_part,
+                                       comm_index_type rank)
+{
+    if (data.size.rows != row_part->get_size() || data.size.cols != col_part->get_size())
+        throw DimensionMismatch("read_distributed: the partitions must cover the matrix");
+    if (row_part->get_num_parts() != col_part->get_num_parts())
+        throw DimensionMismatch("read_distributed: row and column partition need the same parts");
+    if (rank < 0 || rank >= row_part->get_num_parts()) throw OutOfBounds("read_distributed: rank");
+    auto ctx = exec->ctx();
+    const size_type nnz = data.nonzeros.size();
+    std::vector<G> hr(nnz), hc(nnz);
+    std::vector<V> hv(nnz);
+    for (size_type i = 0; i < nnz; ++i) {
+        hr[i] = data.nonzeros[i].row;
+        hc[i] = data.nonzeros[i].column;
+        hv[i] = data.nonzeros[i].value;
+    }
+    array<G> rows(exec, hr), cols(exec, hc);
+    array<V> vals(exec, hv);
+    array<uint8> cls(exec, nnz);
+    array<int64> lrank(exec, nnz + 1), nrank(exec, nnz + 1);
+    int64 n_loc = 0, n_non = 0;
+    GKOB_CALL(gabi<G>::classify_entries(
+        ctx, (int64)nnz, rows.get_const_data(), cols.get_const_data(), (int64)row_part->get_num_ranges(),
+        row_part->get_range_bounds(), row_part->get_part_ids(), (int64)col_part->get_num_ranges(),
+        col_part->get_range_bounds(), col_part->get_part_ids(), rank, cls.get_data(), lrank.get_data(),
+        nrank.get_data(), &n_loc, &n_non));
+    const size_type kept = (size_type)(n_loc + n_non);
+    array<I> krows(exec, kept);
+    array<G> kcols(exec, kept);
+    array<V> kvals(exec, kept);
+    GKOB_CALL((vlgabi<V, I, G>::kept_fill(
+        ctx, (int64)nnz, rows.get_const_data(), cols.get_const_data(), vals.get_const_data(),
+        (int64)row_part->get_num_ranges(), row_part->get_range_bounds(), row_part->get_range_starting_indices(),
+        cls.get_const_data(), lrank.get_const_data(), nrank.get_const_data(), krows.get_data(),
+        kcols.get_data(), kvals.get_data())));
+    local_assembly<V, I, G> out;
+    out.imap.reset(new index_map<I, G>(exec, col_part, rank, kcols));
+    out.n_local_rows = (size_type)row_part->get_part_size(rank);
+    out.n_local_cols = (size_type)col_part->get_part_size(rank);
+    out.n_ghost = out.imap->get_non_local_size();
+    array<I> lcols(exec, kept);
+    out.imap->map_to_local(kcols.get_const_data(), kept, index_space::combined, lcols.get_data());
+    array<I> row_ptrs(exec, out.n_local_rows + 1);
+    GKOB_CALL(iabi<I>::convert_idxs_to_ptrs(ctx, krows.get_const_data(), (int64)kept, (int64)out.n_local_rows,
+                                            row_ptrs.get_data()));
+    out.local = matrix::Csr<V, I>::create(exec, dim2{out.n_local_rows, out.n_local_cols + out.n_ghost},
+                                          std::move(kvals), std::move(lcols), std::move(row_ptrs));
+    return out;
+}
+
+// S[q * P + p] = entries rank q receives from rank p.  What `rank` sends: to peer q the
+// S[q][rank] entries that start at offset sum_{p < rank} S[q][p] of q's remote list.
+struct send_layout {
+    std::vector<int64> send_counts, source_offsets;
+};
+inline send_layout compute_send_layout(const std::vector<int64>& S, int P, int rank)
+{
+    send_layout l;
+    l.send_counts.resize(P);
+    l.source_offsets.resize(P);
+    for (int q = 0; q < P; ++q) {
+        l.send_counts[q] = S[(size_t)q * P + rank];
+        int64 off = 0;
+        for (int p = 0; p < rank; ++p) off += S[(size_t)q * P + p];
+        l.source_offsets[q] = off;
+    }
+    return l;
+}
+
 // distributed::Matrix: local rows, columns numbered into the extended vector
 // [n_local owned | n_ghost received]; apply = halo exchange + one local SpMV.
 template <typename V, typename I>
@@ -75,12 +409,14 @@ public:
     Matrix(std::shared_ptr<const Executor> exec, std::shared_ptr<communicator> comm,
            std::unique_ptr<matrix::Csr<V, I>> local, size_type n_ghost,
            const std::vector<int64>& send_counts, const std::vector<int64>& recv_counts,
-           const int32* send_idx_dev)
+           const int32* send_idx_dev, int64 n_local_cols = -1)
         : exec_(exec), comm_(comm), local_(std::move(local)), n_ghost_(n_ghost)
     {
-        if (local_->get_size().cols != local_->get_size().rows + n_ghost)
-            throw BadDimension("distributed::Matrix: local block must be n_local x (n_local+n_ghost)");
-        GKOB_CALL(b200_halo_create(exec->ctx(), comm->size(), local_->get_size().rows, n_ghost,
+        // square row/column partition unless told otherwise
+        n_local_cols_ = n_local_cols < 0 ? local_->get_size().rows : (size_type)n_local_cols;
+        if (local_->get_size().cols != n_local_cols_ + n_ghost)
+            throw BadDimension("distributed::Matrix: local block must be n_local x (n_local_cols+n_ghost)");
+        GKOB_CALL(b200_halo_create(exec->ctx(), comm->size(), (int64)n_local_cols_, n_ghost,
                                    send_counts.data(), recv_counts.data(), send_idx_dev,
                                    (int32)sizeof(V), &halo_));
         if (comm->use_p2p() &&
@@ -89,8 +425,69 @@ public:
                          comm->rank(), b200_last_error());
     }
     ~Matrix() { b200_halo_destroy(halo_); }
+
+    // experimental::distributed::Matrix::read_distributed (core/distributed/matrix.cpp:300-380):
+    // every rank passes the (row-major sorted) global matrix or at least its own rows; the rows
+    // of `row_part`'s part comm->rank() are kept, their columns renumbered into the combined
+    // index space, and the ranks exchange which of their entries the others need.  Collective.
+    template <typename G>
+    static std::shared_ptr<Matrix> read_distributed(std::shared_ptr<const Executor> exec,
+                                                    std::shared_ptr<communicator> comm,
+                                                    const matrix_data<V, G>& data,
+                                                    std::shared_ptr<const Partition<I, G>> row_part,
+                                                    std::shared_ptr<const Partition<I, G>> col_part = nullptr)
+    {
+        static_assert(sizeof(I) == 4, "the halo exchange indexes its send buffer with int32");
+        if (!col_part) col_part = row_part;
+        const int P = comm->size(), rank = comm->rank();
+        if (row_part->get_num_parts() != P)
+            throw DimensionMismatch("read_distributed: one part per rank of the communicator");
+        auto a = assemble_local<V, I, G>(exec, data, row_part, col_part, rank);
+        const auto& recv_counts = a.imap->get_remote_sizes();
+        std::vector<int64> send_counts(P, 0);
+        array<int32> send_idx(exec, 0);
+        if (P > 1) {
+            // S[q][p]: everyone's receive counts
+            array<int64> mine(exec, recv_counts), all(exec, (size_type)P * P);
+            GKOB_CALL(b200_comm_allgather_bytes(exec->ctx(), comm->get(), mine.get_const_data(),
+                                                all.get_data(), (int64)sizeof(int64) * P));
+            const auto S = all.to_host();
+            int64 max_remote = 0;
+            for (int q = 0; q < P; ++q)
+                max_remote = std::max(max_remote, std::accumulate(S.begin() + (size_t)q * P,
+                                                                  S.begin() + (size_t)(q + 1) * P, int64(0)));
+            // everyone's remote lists (local indices at their owners), padded to the longest
+            array<int32> padded(exec, (size_type)max_remote), lists(exec, (size_type)max_remote * P);
+            if (a.n_ghost)
+                exec->copy(padded.get_data(), a.imap->get_remote_local_idxs().get_const_data(), a.n_ghost);
+            GKOB_CALL(b200_comm_allgather_bytes(exec->ctx(), comm->get(), padded.get_const_data(),
+                                                lists.get_data(), (int64)sizeof(int32) * max_remote));
+            const auto lay = compute_send_layout(S, P, rank);
+            send_counts = lay.send_counts;
+            const int64 n_send = std::accumulate(send_counts.begin(), send_counts.end(), int64(0));
+            send_idx = array<int32>(exec, (size_type)n_send);
+            int64 at = 0;
+            for (int q = 0; q < P; ++q) {
+                if (send_counts[q])
+                    exec->copy(send_idx.get_data() + at,
+                               lists.get_const_data() + (size_t)q * max_remote + lay.source_offsets[q],
+                               (size_type)send_counts[q]);
+                at += send_counts[q];
+            }
+            exec->synchronize();
+        }
+        auto m = std::make_shared<Matrix>(exec, comm, std::move(a.local), a.n_ghost, send_counts, recv_counts,
+                                          send_idx.get_const_data(), (int64)a.n_local_cols);
+        const auto rg = a.imap->get_remote_global_idxs().to_host();
+        m->non_local_to_global_.assign(rg.begin(), rg.end());
+        return m;
+    }
+
     size_type n_local() const { return local_->get_size().rows; }
+    size_type n_local_cols() const { return n_local_cols_; }
     size_type n_ghost() const { return n_ghost_; }
+    // global column index of every ghost entry of the extended vector (read_distributed only)
+    const std::vector<int64>& get_non_local_to_global() const { return non_local_to_global_; }
     const matrix::Csr<V, I>* get_local_matrix() const { return local_.get(); }
     std::shared_ptr<communicator> get_communicator() const { return comm_; }
     b200_halo* get_halo() const { return halo_; }
@@ -107,7 +504,9 @@ private:
     std::shared_ptr<communicator> comm_;
     std::unique_ptr<matrix::Csr<V, I>> local_;
     size_type n_ghost_;
+    size_type n_local_cols_ = 0;
     b200_halo* halo_ = nullptr;
+    std::vector<int64> non_local_to_global_;  // read_distributed: global index of every ghost column
 };
 
 // Distributed CG with the fused device-resident iteration: per iteration

@@ -45,6 +45,9 @@ class BadDimension : public Error {
     using Error::Error;
 };
 
+class OutOfBounds : public Error {
+    using Error::Error;
+};
 class StreamError : public Error {
     using Error::Error;
 };

@@ -683,6 +683,9 @@ int32_t b200_comm_p2p_error(b200_ctx* ctx, const b200_comm* comm);
                                        VT* x_ext, const int32_t* ctl);
 B200_DECL_COMM(f64, double)
 B200_DECL_COMM(f32, float)
+/* all-gather of raw device bytes (set-up exchanges of counts and index lists) */
+b200_status b200_comm_allgather_bytes(b200_ctx* ctx, b200_comm* comm, const void* send, void* recv,
+                                      int64_t bytes_per_rank);
 
 /* ---------------------------------------------------------------------------
  * Distributed set-up on the device: what

@@ -31,7 +31,10 @@ def ksrc(tmp_path_factory):
     with open(src, "w") as f:
         f.write(open(os.path.join(ROOT, "ginkgo_b200", "csrc", "dist_assembly.cu")).read())
     so = os.path.join(d, "libdist_assembly_host.so")
-    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wno-unused-function",
+    # -Bsymbolic: the copy's own template instantiations, not the same-named ones of the CUDA
+    # library another test may have loaded into the process
+    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-Wl,-Bsymbolic", "-Wall",
+                    "-Wno-unused-function",
                     "-I" + os.path.join(ROOT, "tests", "mock", "host_cuda_shim"),
                     "-I" + os.path.join(ROOT, "include"), src, "-o", so], check=True)
     return KernelSourceBackend(ctypes.CDLL(so))

@@ -287,3 +287,162 @@ def test_host_advanced_solver_apply(host):
     expect = x0 * -0.5
     expect = expect + 2.0 * xs
     assert np.array_equal(tx.numpy(), expect)
+
+
+# ---------------------------------------------------------------- distributed set-up (8f rank 4)
+def _random_mapping(rng, n, num_parts, run):
+    out = []
+    while len(out) < n:
+        out += [int(rng.integers(num_parts))] * int(rng.integers(1, run + 1))
+    return np.array(out[:n], np.int32)
+
+
+def _ref_dist():
+    from oracle import ref
+    if not ref.available() or not hasattr(ref.lib(), "refshim_partition"):
+        pytest.skip("needs oracle/_ref with the distributed shim functions")
+    return ref
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_host_partition_is_the_reference_partition(host, seed):
+    from ginkgo_b200 import api
+    ref = _ref_dist()
+    rng = np.random.default_rng(seed)
+    num_parts = int(rng.integers(1, 7))
+    mapping = _random_mapping(rng, int(rng.integers(1, 300)), num_parts, 6)
+    nr = int(rng.integers(1, 10))
+    ranges = np.concatenate([[0], np.cumsum(rng.integers(0 if seed % 2 else 1, 9, nr))])
+    ids = rng.permutation(nr).astype(np.int32)
+    cases = [(api.HostPartition.from_mapping(host, mapping, num_parts), ref.partition(0, mapping, num_parts=num_parts)),
+             (api.HostPartition.from_contiguous(host, ranges), ref.partition(1, None, ranges)),
+             (api.HostPartition.from_contiguous(host, ranges, ids), ref.partition(1, ids, ranges)),
+             (api.HostPartition.uniform(host, num_parts, 1000 + seed), ref.partition(2, num_parts=num_parts, global_size=1000 + seed)),
+             (api.HostPartition.uniform(host, 0, 5), ref.partition(2, num_parts=0, global_size=5))]
+    for got, want in cases:
+        got = got.info()
+        for k in ("size", "num_ranges", "num_parts", "num_empty_parts", "connected", "ordered"):
+            assert got[k] == want[k], k
+        for k in ("range_bounds", "part_ids", "starting_indices", "part_sizes"):
+            np.testing.assert_array_equal(got[k], want[k])
+    with pytest.raises(api.DimensionMismatch):
+        api.HostPartition.from_contiguous(host, ranges, np.zeros(nr + 2, np.int32))
+
+
+def _dist_case(rng, square=True):
+    num_parts = int(rng.integers(2, 6))
+    nrows = int(rng.integers(30, 150))
+    ncols = nrows if square else int(rng.integers(30, 150))
+    row_map = _random_mapping(rng, nrows, num_parts, 8)
+    col_map = row_map if square else _random_mapping(rng, ncols, num_parts, 8)
+    nnz = int(rng.integers(50, 1200))
+    order = np.unique(rng.integers(0, nrows * ncols, nnz))  # row-major sorted, no duplicates
+    return num_parts, (nrows, ncols), row_map, col_map, order // ncols, order % ncols, rng.standard_normal(len(order))
+
+
+@pytest.mark.parametrize("seed", range(5))
+def test_host_assemble_local_is_the_reference_split(host, seed):
+    """rows/values = separate_local_nonlocal's kept entries, columns = index_map's combined space"""
+    from ginkgo_b200 import api
+    ref = _ref_dist()
+    rng = np.random.default_rng(40 + seed)
+    num_parts, shape, row_map, col_map, rows, cols, vals = _dist_case(rng, square=seed % 2 == 0)
+    rp = api.HostPartition.from_mapping(host, row_map, num_parts)
+    cp = api.HostPartition.from_mapping(host, col_map, num_parts)
+    for rank in range(num_parts):
+        a = api.HostAssembly(host, rp, rank, shape, rows, cols, vals, col_part=cp)
+        (lr, lc, lv), (nr_, nc, nv) = ref.separate_local_nonlocal(shape, rows, cols, vals, row_map, col_map,
+                                                                 num_parts, rank)
+        owned = row_map[rows] == rank
+        im = ref.index_map(col_map, num_parts, rank, nc, 2, cols[owned])
+        assert a.n_local_rows == int((row_map == rank).sum()) and a.n_local_cols == int((col_map == rank).sum())
+        assert a.n_ghost == len(im["remote_global"])
+        np.testing.assert_array_equal(a.remote_global, im["remote_global"])
+        np.testing.assert_array_equal(a.remote_local, im["remote_local"])
+        want_recv = np.zeros(num_parts, np.int64)
+        want_recv[im["target_ids"]] = im["remote_sizes"]
+        np.testing.assert_array_equal(a.recv_counts, want_recv)
+        np.testing.assert_array_equal(a.col_idxs, im["query_local"])
+        np.testing.assert_array_equal(a.values, vals[owned])
+        # row pointers = counts of the owned entries per local row
+        local_row_of = np.full(shape[0], -1)
+        local_row_of[row_map == rank] = np.arange(a.n_local_rows)  # one-range-per-run order == local order
+        info = rp.info()
+        for r in range(info["num_ranges"]):  # general: starting index + offset in range
+            if info["part_ids"][r] == rank:
+                b0, b1 = info["range_bounds"][r], info["range_bounds"][r + 1]
+                local_row_of[b0:b1] = info["starting_indices"][r] + np.arange(b1 - b0)
+        counts = np.bincount(local_row_of[rows[owned]], minlength=a.n_local_rows)
+        np.testing.assert_array_equal(a.row_ptrs, np.concatenate([[0], np.cumsum(counts)]))
+        for space in (0, 1, 2):
+            q = rng.integers(0, shape[1], 30)
+            np.testing.assert_array_equal(a.map_to_local(q, space),
+                                          ref.index_map(col_map, num_parts, rank, nc, space, q)["query_local"])
+    with pytest.raises(api.DimensionMismatch):
+        api.HostAssembly(host, rp, 0, (shape[0] + 1, shape[1]), rows, cols, vals, col_part=cp)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_host_send_layout_closes_the_halo_exchange(host, seed):
+    """all ranks' assemblies + compute_send_layout, with the exchange itself played in numpy:
+    every ghost slot receives the x entry of its global column and the local SpMVs add up to A x"""
+    from ginkgo_b200 import api
+    rng = np.random.default_rng(80 + seed)
+    num_parts, shape, row_map, _, rows, cols, vals = _dist_case(rng)
+    n = shape[0]
+    part = api.HostPartition.from_mapping(host, row_map, num_parts)
+    info = part.info()
+    local_of = np.zeros(n, np.int64)
+    for r in range(info["num_ranges"]):
+        b0, b1 = info["range_bounds"][r], info["range_bounds"][r + 1]
+        local_of[b0:b1] = info["starting_indices"][r] + np.arange(b1 - b0)
+    asm = [api.HostAssembly(host, part, q, shape, rows, cols, vals) for q in range(num_parts)]
+    S = np.array([a.recv_counts for a in asm])  # S[q][p]
+    x = rng.standard_normal(n)
+    x_local = []
+    for p in range(num_parts):
+        xl = np.zeros(asm[p].n_local_rows)
+        own = np.nonzero(row_map == p)[0]
+        xl[local_of[own]] = x[own]
+        x_local.append(xl)
+    # what every rank packs for every peer
+    packed = {}
+    for p in range(num_parts):
+        sc, so = api.host_send_layout(num_parts, p, S)
+        np.testing.assert_array_equal(sc, S[:, p])
+        for q in range(num_parts):
+            send_idx = asm[q].remote_local[so[q]:so[q] + sc[q]]  # read_distributed's device copy
+            packed[(p, q)] = x_local[p][send_idx]
+    y = np.zeros(n)
+    for q in range(num_parts):
+        ghosts = np.concatenate([packed[(p, q)] for p in range(num_parts)])
+        np.testing.assert_array_equal(ghosts, x[asm[q].remote_global])
+        x_ext = np.concatenate([x_local[q], ghosts])
+        a = asm[q]
+        yl = np.zeros(a.n_local_rows)
+        np.add.at(yl, np.repeat(np.arange(a.n_local_rows), np.diff(a.row_ptrs)), a.values * x_ext[a.col_idxs])
+        own = np.nonzero(row_map == q)[0]
+        y[own] = yl[local_of[own]]
+    want = np.zeros(n)
+    np.add.at(want, rows, vals * x[cols])
+    np.testing.assert_allclose(y, want, rtol=1e-12, atol=1e-12)
+
+
+def test_host_read_distributed_on_one_rank(host):
+    """world size 1 through the whole C++ path: communicator, read_distributed, Matrix::apply"""
+    from ginkgo_b200 import api
+    rng = np.random.default_rng(3)
+    n = 200
+    order = np.unique(rng.integers(0, n * n, 3000))
+    rows, cols, vals = order // n, order % n, rng.standard_normal(len(order))
+    part = api.HostPartition.uniform(host, 1, n)
+    A = api.DistMatrix.read(host, part, (n, n), rows, cols, vals)
+    assert (A.n_local, A.n_local_cols, A.n_ghost) == (n, n, 0)
+    x = _t(rng.standard_normal(n))
+    y = torch.zeros(n, dtype=torch.float64)
+    A.apply(x, y)
+    rp = np.concatenate([[0], np.cumsum(np.bincount(rows, minlength=n))]).astype(np.int32)
+    yo = np.zeros((n, 1))
+    H.Oracle()("csr_spmv_f64_i32", n, n, len(vals), rp, cols.astype(np.int32), vals,
+               x.numpy().reshape(n, 1).copy(), 1, 1, yo, 1)
+    assert np.array_equal(y.numpy(), yo[:, 0])

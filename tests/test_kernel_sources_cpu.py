@@ -63,7 +63,9 @@ def ksrc(tmp_path_factory):
     open(os.path.join(d, "krylov_steps.cpp"), "w").write(src)
     shutil.copy(os.path.join(ROOT, "tests", "mock", "host_cuda_shim", "elementwise.cuh"), d)
     so = os.path.join(d, "libkrylov_steps_host.so")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off",
+    # -Bsymbolic: the copy's own template instantiations, not the same-named ones of a CUDA
+    # library another test may have loaded into the process
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wl,-Bsymbolic", "-ffp-contract=off",
                     "-I" + os.path.join(ROOT, "include"), "-o", so, os.path.join(d, "krylov_steps.cpp")],
                    check=True)
     return KernelSourceBackend(ctypes.CDLL(so))
