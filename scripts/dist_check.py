@@ -68,6 +68,32 @@ for name, kw in [("lap3d_40", dict(grid=40, dims=3)), ("cfg2_small", dict(n=2000
     ex.synchronize()
     print("rank %d %s: n_local=%d n_ghost=%d p2p=%d spmv bit-equal=%s  %.1f us/apply"
           % (rank, name, A.n_local, A.n_ghost, A.p2p, same, e0.elapsed_time(e1) * 10), flush=True)
+    # the same matrix through read_distributed: split, renumbering and send lists built by the
+    # library's device kernels + its own all-gather (no torch.distributed in the set-up)
+    rp_h, ci_h, va_h = rp.cpu().numpy(), ci.cpu().numpy(), va.cpu().numpy()
+    rows_h = np.repeat(np.arange(n, dtype=np.int64), np.diff(rp_h))
+    part = api.HostPartition.uniform(ex, world, n)
+    pb = part.info()["range_bounds"]
+    q0, q1 = int(pb[rank]), int(pb[rank + 1])
+    mine = (rows_h >= q0) & (rows_h < q1)  # a rank only needs to pass its own rows
+    A2 = api.DistMatrix.read(ex, part, (n, n), rows_h[mine], ci_h[mine], va_h[mine])
+    with torch.cuda.stream(ex.stream):
+        x2 = torch.zeros(A2.n_local + A2.n_ghost, dtype=torch.float64, device=dev)
+        y2 = torch.zeros(A2.n_local, dtype=torch.float64, device=dev)
+    same2 = A2.n_local == q1 - q0
+    for k in range(3):
+        with torch.cuda.stream(ex.stream):
+            xk = W.vector(n, stream=40 + k, xp="torch", device=dev)
+            x2[:A2.n_local] = xk[q0:q1]
+            xdk = api.host_dense(ex, xk)
+        api._hcheck(_h.gkob_apply(A1.h, xdk.h, yd1.h))
+        A2.apply(x2, y2)
+        ex.synchronize()
+        same2 = same2 and torch.equal(y2, y1[q0:q1])
+        same2 = same2 and torch.equal(x2[A2.n_local:].cpu(), xk.cpu()[torch.from_numpy(A2.ghost_globals)])
+    ok &= same2
+    print("rank %d %s: read_distributed n_local=%d n_ghost=%d p2p=%d spmv bit-equal=%s"
+          % (rank, name, A2.n_local, A2.n_ghost, A2.p2p, same2), flush=True)
     if name.startswith("lap"):
         b = torch.ones(n, dtype=torch.float64, device=dev)
         s1 = api.HostSolver(ex, "cg", A1, precond_max_bs=1, max_iters=2000, reduction=1e-9, fused=True)

@@ -1,0 +1,115 @@
+"""GPU tests of the distributed set-up kernels (ginkgo_b200/csrc/dist_assembly.cu) and of
+distributed::{Partition, index_map, assemble_local, Matrix::read_distributed} on one GPU.
+Written after the round's GPU budget was spent: the oracle side, a host-compiled copy of the
+kernel source and the C++ host path are verified on the CPU (tests/test_dist_assembly_cpu.py,
+tests/test_host_cpu.py); this file sorts last so that a surprise here cannot hide another test.
+The world_size > 1 exchange of read_distributed is exercised by scripts/dist_check.py."""
+import numpy as np
+import pytest
+
+from tests import dist_driver as D
+from tests.test_dist_assembly_cpu import TYPES, eq, random_mapping
+from tests.test_solvers_gpu import hexec  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(orc, cuda, lt, gt, vt, n, num_parts, nnz, run, seed, local_part):
+    rng = np.random.default_rng(seed)
+    row_map = random_mapping(rng, n, num_parts, run)
+    order = np.unique(rng.integers(0, n * n, nnz))
+    rows, cols = order // n, order % n
+    vals = rng.standard_normal(len(order)).astype(D.NP[vt])
+    q = rng.integers(-2, n + 2, 200)
+    res = []
+    for be in (orc, cuda):
+        rp = D.partition_from_mapping(be, row_map, num_parts, lt, gt)
+        cp = D.partition_uniform(be, num_parts, n, lt, gt)
+        s = D.separate(be, rp, cp, rows, cols, vals, local_part, vt)
+        im = D.IndexMap(be, cp, local_part, s["kept"][1], skip_part=local_part)
+        maps = [im.map_to_local(be, q, sp) for sp in (0, 1, 2)]
+        comb = im.map_to_local(be, s["kept"][1], 2)
+        res.append((rp.as_dict(), cp.as_dict(), s, im, maps, comb))
+    (p0, c0, s0, i0, m0, k0), (p1, c1, s1, i1, m1, k1) = res
+    for a, b in ((p0, p1), (c0, c1)):
+        for k in a:
+            eq(a[k], b[k])
+    for k in ("local", "non_local", "kept"):
+        for a, b in zip(s0[k], s1[k]):
+            eq(a, b)
+    for k in ("cls", "local_rank", "non_local_rank"):
+        eq(s0[k], s1[k])
+    for k in ("bitmap", "word_rank", "range_offsets", "remote_sizes", "remote_global", "remote_local",
+              "remote_part_ids"):
+        eq(getattr(i0, k), getattr(i1, k))
+    for a, b in zip(m0, m1):
+        eq(a, b)
+    eq(k0, k1)
+
+
+@pytest.mark.parametrize("lt,gt", TYPES)
+@pytest.mark.parametrize("vt", ["f64", "f32"])
+def test_dist_assembly_kernels_match_oracle(orc, cuda, lt, gt, vt):
+    _compare(orc, cuda, lt, gt, vt, n=6000, num_parts=5, nnz=60000, run=150, seed=11, local_part=2)
+
+
+def test_dist_assembly_kernels_edge_cases(orc, cuda):
+    # a part without rows, single-row ranges, more parts than ranges, one part
+    _compare(orc, cuda, "i32", "i64", "f64", n=97, num_parts=9, nnz=900, run=1, seed=12, local_part=8)
+    _compare(orc, cuda, "i32", "i64", "f64", n=5000, num_parts=1, nnz=20000, run=40, seed=13, local_part=0)
+    for be in (orc, cuda):
+        p = D.partition_from_contiguous(be, [0])
+        assert (p.size, p.num_ranges, p.num_parts) == (0, 0, 0)
+        p = D.partition_uniform(be, 5, 3)
+        eq(p.range_bounds, [0, 1, 2, 3, 3, 3])
+        assert p.num_empty_parts == 2
+
+
+def test_host_assembly_large(hexec):
+    """n = 1M rows on 8 parts, 5M entries: properties of the assembled block of one part"""
+    from ginkgo_b200 import api
+    rng = np.random.default_rng(21)
+    n, num_parts, rank = 1_000_000, 8, 3
+    order = np.unique(rng.integers(0, n * n, 5_000_000))
+    rows, cols = order // n, order % n
+    vals = rng.standard_normal(len(order))
+    part = api.HostPartition.uniform(hexec, num_parts, n)
+    info = part.info()
+    lo, hi = int(info["range_bounds"][rank]), int(info["range_bounds"][rank + 1])
+    a = api.HostAssembly(hexec, part, rank, (n, n), rows, cols, vals)
+    owned = (rows >= lo) & (rows < hi)
+    assert (a.n_local_rows, a.n_local_cols) == (hi - lo, hi - lo)
+    remote = np.unique(cols[owned & ((cols < lo) | (cols >= hi))])
+    eq(a.remote_global, remote)  # contiguous parts: (part, global) order == global order
+    eq(a.recv_counts, np.histogram(remote, bins=info["range_bounds"])[0])
+    eq(a.values, vals[owned])
+    eq(a.row_ptrs, np.concatenate([[0], np.cumsum(np.bincount(rows[owned] - lo, minlength=hi - lo))]))
+    c = cols[owned]
+    is_local = (c >= lo) & (c < hi)
+    want = np.where(is_local, c - lo, (hi - lo) + np.searchsorted(remote, c))
+    eq(a.col_idxs, want)
+
+
+def test_read_distributed_on_one_gpu(hexec):
+    import torch
+    from ginkgo_b200 import api
+    rng = np.random.default_rng(22)
+    n = 50_000
+    order = np.unique(rng.integers(0, n * n, 600_000))
+    rows, cols, vals = order // n, order % n, rng.standard_normal(len(order))
+    part = api.HostPartition.uniform(hexec, 1, n)
+    A = api.DistMatrix.read(hexec, part, (n, n), rows, cols, vals)
+    assert (A.n_local, A.n_local_cols, A.n_ghost) == (n, n, 0)
+    with torch.cuda.stream(hexec.stream):
+        x = torch.from_numpy(rng.standard_normal(n)).to(hexec.device)
+        y = torch.zeros(n, dtype=torch.float64, device=hexec.device)
+        rp = torch.from_numpy(np.concatenate([[0], np.cumsum(np.bincount(rows, minlength=n))]).astype(np.int32)).to(hexec.device)
+        ci = torch.from_numpy(cols.astype(np.int32)).to(hexec.device)
+        va = torch.from_numpy(vals).to(hexec.device)
+        y2 = torch.zeros_like(y)
+    A.apply(x, y)
+    B = api.host_csr(hexec, (n, n), va, ci, rp)
+    xd, yd = api.host_dense(hexec, x), api.host_dense(hexec, y2)
+    api._hcheck(api._host().gkob_apply(B.h, xd.h, yd.h))
+    hexec.synchronize()
+    assert torch.equal(y, y2)
