@@ -226,6 +226,7 @@ def _configure_host_lib(h):
     h.gkob_csr_convert.argtypes = [vp, ctypes.c_char_p, ll, ll, d, d]
     h.gkob_csr_sort_by_column_index.restype = i
     h.gkob_csr_sort_by_column_index.argtypes = [vp]
+    h.gkob_csr_transpose.restype, h.gkob_csr_transpose.argtypes = vp, [vp]
     for s in ("f64", "f32"):
         f = getattr(h, "gkob_csr_view_%s_i32" % s)
         f.restype, f.argtypes = vp, [vp, ll, ll, ll, vp, vp, vp]
@@ -343,6 +344,13 @@ def host_sort_by_column_index(A):
     _hcheck(_host().gkob_csr_sort_by_column_index(A.h))
 
 
+def host_transpose(A):
+    """Transposable::transpose of a Csr handle -> a new (owning) handle"""
+    t = _HostObj(A.exec, _host().gkob_csr_transpose(A.h), keep=(A,))
+    t.vt = getattr(A, "vt", None)
+    return t
+
+
 class StagedApply:
     """gko_b200::staged_apply<V>: x_host = op(b_host) with HOST tensors (pinned to overlap),
     pipelined over two copy streams; apply() is asynchronous, wait() makes x_host valid."""
@@ -397,7 +405,7 @@ def host_dense(exec_, t, cols=None, stride=None):
 class HostSolver:
     """solver::Cg / Bicgstab / Gmres of the C++ host layer.
 
-    kind: "cg" | "bicgstab" | "gmres" | "fcg" | "cgs" | "pipe_cg" | "gcr" (krylov_dim) | "minres" | "ir" (relaxation_factor) | "chebyshev" (foci);  criteria: max_iters (None = no Iteration criterion),
+    kind: "cg" | "bicgstab" | "gmres" | "fcg" | "cgs" | "pipe_cg" | "gcr" (krylov_dim) | "minres" | "bicg" | "ir" (relaxation_factor) | "chebyshev" (foci);  criteria: max_iters (None = no Iteration criterion),
     res_kind 0 none / 1 ResidualNorm / 2 ImplicitResidualNorm, baseline 0 rhs_norm /
     1 initial_resnorm / 2 absolute, iter_first = order inside stop::Combined;
     precond_max_bs 0 = none, 1 = scalar Jacobi, k > 1 = block Jacobi (block_ptrs given, or
@@ -415,7 +423,7 @@ class HostSolver:
             self._bp = np.ascontiguousarray(block_ptrs, dtype=np.int32)
             bp, nb = self._bp.ctypes.data, len(self._bp) - 1
         fn = getattr(_host(), "gkob_solver_create_" + self.vt)
-        self.obj = _HostObj(exec_, fn(exec_.h, {"cg": 0, "bicgstab": 1, "gmres": 2, "fcg": 3, "cgs": 4, "ir": 5, "chebyshev": 6, "pipe_cg": 7, "gcr": 8, "minres": 9}[kind], A.h,
+        self.obj = _HostObj(exec_, fn(exec_.h, {"cg": 0, "bicgstab": 1, "gmres": 2, "fcg": 3, "cgs": 4, "ir": 5, "chebyshev": 6, "pipe_cg": 7, "gcr": 8, "minres": 9, "bicg": 10}[kind], A.h,
                                       precond_max_bs, bp, nb, -1 if max_iters is None else max_iters,
                                       res_kind, baseline, reduction, int(iter_first), krylov_dim,
                                       ortho, int(fused), check_every), (A,))

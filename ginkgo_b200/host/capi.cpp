@@ -84,6 +84,12 @@ std::unique_ptr<LinOp> make_solver(std::shared_ptr<Executor> exec, int kind,
         if (pre) f.with_preconditioner(pre);
         return f.on(exec)->generate(A);
     }
+    if (kind == 10) {
+        auto f = solver::Bicg<V>::build();
+        f.with_criteria(crit);
+        if (pre) f.with_preconditioner(pre);
+        return f.on(exec)->generate(A);
+    }
     if (kind == 9) {
         auto f = solver::Minres<V>::build();
         f.with_criteria(crit);
@@ -223,6 +229,22 @@ int gkob_csr_sort_by_column_index(void* csr)
         else
             throw NotSupported("gkob_csr_sort_by_column_index: not a Csr<double|float, int32>");
     });
+}
+
+// Transposable::transpose of a Csr<double|float, int32> handle -> new handle
+void* gkob_csr_transpose(void* csr)
+{
+    auto src = static_cast<Handle*>(csr);
+    auto h = new Handle{src->exec, nullptr};
+    if (guarded([&] {
+            auto t = dynamic_cast<const Transposable*>(src->op.get());
+            if (!t) throw NotSupported("gkob_csr_transpose: the operator is not Transposable");
+            h->op = t->transpose();
+        })) {
+        delete h;
+        return nullptr;
+    }
+    return h;
 }
 
 // staged_apply<V> over a LinOp handle: apply with HOST vectors, pipelined (gko_b200_staging.hpp)

@@ -82,6 +82,9 @@ struct viabi;
         static constexpr auto cgs_step_1 = b200_cgs_step_1_##S;                                 \
         static constexpr auto cgs_step_2 = b200_cgs_step_2_##S;                                 \
         static constexpr auto cgs_step_3 = b200_cgs_step_3_##S;                                 \
+        static constexpr auto bicg_initialize = b200_bicg_initialize_##S;                       \
+        static constexpr auto bicg_step_1 = b200_bicg_step_1_##S;                               \
+        static constexpr auto bicg_step_2 = b200_bicg_step_2_##S;                               \
         static constexpr auto pipe_cg_initialize_1 = b200_pipe_cg_initialize_1_##S;             \
         static constexpr auto pipe_cg_initialize_2 = b200_pipe_cg_initialize_2_##S;             \
         static constexpr auto pipe_cg_step_1 = b200_pipe_cg_step_1_##S;                         \
@@ -150,6 +153,8 @@ GKOB_V(float, f32)
         static constexpr auto jacobi_apply = b200_jacobi_apply_##S##_##T;                       \
         static constexpr auto jacobi_generate = b200_jacobi_generate_##S##_##T;                 \
         static constexpr auto jacobi_find_blocks = b200_jacobi_find_blocks_##T;                 \
+        static constexpr auto csr_transpose = b200_csr_transpose_##S##_##T;                     \
+        static constexpr auto jacobi_transpose = b200_jacobi_transpose_##S##_##T;               \
     };
 GKOB_VI(double, f64, int32, i32)
 GKOB_VI(double, f64, int64, i64)
@@ -323,6 +328,14 @@ protected:
     }
     std::shared_ptr<const Executor> exec_;
     dim2 size_;
+};
+
+// include/ginkgo/core/base/lin_op.hpp `Transposable` (real value types: conj_transpose == transpose)
+class Transposable {
+public:
+    virtual ~Transposable() = default;
+    virtual std::unique_ptr<LinOp> transpose() const = 0;
+    virtual std::unique_ptr<LinOp> conj_transpose() const { return transpose(); }
 };
 
 class LinOpFactory {
@@ -530,7 +543,7 @@ template <typename V, typename I>
 class Hybrid;
 
 template <typename V, typename I>
-class Csr : public LinOp {
+class Csr : public LinOp, public Transposable {
 public:
     using value_type = V;
     using index_type = I;
@@ -598,6 +611,18 @@ public:
     void convert_to(Coo<V, I>* result) const;
     void convert_to(Hybrid<V, I>* result) const;
     void sort_by_column_index();
+    // Csr::transpose (core/matrix/csr.cpp:1097-1107): rows of the result ordered like the
+    // reference's (by original row, then position), on the device
+    std::unique_ptr<LinOp> transpose() const override
+    {
+        const size_type nnz = get_num_stored_elements();
+        array<V> tv(exec_, nnz);
+        array<I> tc(exec_, nnz), tr(exec_, size_.cols + 1);
+        GKOB_CALL((viabi<V, I>::csr_transpose(exec_->ctx(), size_.rows, size_.cols, nnz, get_const_row_ptrs(),
+                                              get_const_col_idxs(), get_const_values(), tr.get_data(),
+                                              tc.get_data(), tv.get_data())));
+        return create(exec_, dim2{size_.cols, size_.rows}, std::move(tv), std::move(tc), std::move(tr));
+    }
     std::unique_ptr<Dense<V>> extract_diagonal() const
     {
         auto d = Dense<V>::create(exec_, dim2{std::min(size_.rows, size_.cols), 1});
@@ -941,12 +966,13 @@ private:
 
 // matrix::Identity: apply == copy (default preconditioner of the solvers)
 template <typename V>
-class Identity : public LinOp {
+class Identity : public LinOp, public Transposable {
 public:
     static std::unique_ptr<Identity> create(std::shared_ptr<const Executor> exec, size_type n)
     {
         return std::unique_ptr<Identity>(new Identity(exec, n));
     }
+    std::unique_ptr<LinOp> transpose() const override { return create(exec_, size_.rows); }
 
 protected:
     Identity(std::shared_ptr<const Executor> exec, size_type n) : LinOp(std::move(exec), dim2{n, n}) {}

@@ -264,7 +264,7 @@ struct block_interleaved_storage_scheme {
 };
 
 template <typename V, typename I>
-class Jacobi : public LinOp {
+class Jacobi : public LinOp, public Transposable {
 public:
     struct Factory : LinOpFactory {
         uint32 max_block_size_ = 32;
@@ -298,8 +298,34 @@ public:
     const V* get_blocks() const { return blocks_.get_const_data(); }
     const I* get_const_block_pointers() const { return block_pointers_.get_const_data(); }
     const block_interleaved_storage_scheme<I>& get_storage_scheme() const { return scheme_; }
+    // Jacobi::transpose (core/preconditioner/jacobi.cpp:261-283): same scheme and block
+    // pointers, every inverted block transposed (a scalar Jacobi is its own transpose)
+    std::unique_ptr<LinOp> transpose() const override
+    {
+        auto res = std::unique_ptr<Jacobi>(new Jacobi(exec_, size_, max_block_size_));
+        res->num_blocks_ = num_blocks_;
+        res->scheme_ = scheme_;
+        res->blocks_ = array<V>(exec_, blocks_.get_size());
+        if (max_block_size_ == 1) {
+            if (blocks_.get_size())
+                exec_->copy(res->blocks_.get_data(), blocks_.get_const_data(), blocks_.get_size());
+            return res;
+        }
+        res->block_pointers_ = array<I>(exec_, block_pointers_.get_size());
+        exec_->copy(res->block_pointers_.get_data(), block_pointers_.get_const_data(),
+                    block_pointers_.get_size());
+        GKOB_CALL(vabi<V>::fill(exec_->ctx(), blocks_.get_size(), 1, res->blocks_.get_data(), 1, V(0)));
+        GKOB_CALL((viabi<V, I>::jacobi_transpose(exec_->ctx(), num_blocks_, max_block_size_, scheme_.block_offset,
+                                                 scheme_.group_offset, scheme_.group_power,
+                                                 block_pointers_.get_const_data(), blocks_.get_const_data(),
+                                                 res->blocks_.get_data())));
+        return res;
+    }
 
 protected:
+    Jacobi(std::shared_ptr<const Executor> exec, dim2 size, uint32 max_block_size)
+        : LinOp(exec, size), max_block_size_(max_block_size)
+    {}
     Jacobi(std::shared_ptr<const Executor> exec, const Factory& f, std::shared_ptr<const LinOp> op)
         : LinOp(exec, op->get_size()), max_block_size_(f.max_block_size_)
     {
@@ -907,6 +933,84 @@ protected:
             GKOB_CALL(vabi<V>::cgs_step_3(ctx, sz.rows, nrhs, GKOB_CVS(t), GKOB_CVS(u_hat),
                                           GKOB_VS(r), GKOB_VS(x), alpha->get_const_values(),
                                           stop_status.get_const_data()));
+            std::swap(prev_rho, rho);
+        }
+        this->record(iter, stop_status);
+    }
+};
+// ---------------------------------------------------------------------------------------------
+// solver::Bicg (core/solver/bicg.cpp:113-232): two coupled recurrences, one with A and M, one
+// with their transposes (Transposable::conj_transpose of the system matrix and the
+// preconditioner, built once per apply like the reference does).
+// ---------------------------------------------------------------------------------------------
+template <typename V>
+class Bicg : public SolverBase<V> {
+    using Base = SolverBase<V>;
+    using Dense = matrix::Dense<V>;
+
+public:
+    struct Factory : SolverFactoryBase<Factory> {
+        std::unique_ptr<LinOp> generate(std::shared_ptr<const LinOp> op) const override
+        {
+            auto exec = this->exec_ ? this->exec_ : op->get_executor();
+            return std::unique_ptr<LinOp>(new Bicg(exec, *this, op));
+        }
+    };
+    static Factory build() { return Factory{}; }
+
+protected:
+    Bicg(std::shared_ptr<const Executor> exec, const Factory& f, std::shared_ptr<const LinOp> op)
+        : Base(exec, f, op)
+    {}
+    using Base::apply_impl;
+    void apply_impl(const LinOp* lb, LinOp* lx) const override
+    {
+        auto b = as<Dense>(lb);
+        auto x = as<Dense>(lx);
+        auto exec = this->exec_;
+        auto ctx = exec->ctx();
+        const dim2 sz = b->get_size();
+        const size_type nrhs = sz.cols;
+        auto mk = [&] { return Dense::create(exec, sz); };
+        auto sc = [&] { return Dense::create(exec, dim2{1, nrhs}); };
+        auto r = mk(), z = mk(), p = mk(), q = mk(), r2 = mk(), z2 = mk(), p2 = mk(), q2 = mk();
+        auto beta = sc(), prev_rho = sc(), rho = sc();
+        array<uint8> stop_status(exec, nrhs);
+        bool one_changed = false;
+        GKOB_CALL(vabi<V>::bicg_initialize(ctx, sz.rows, nrhs, GKOB_CVS(b), GKOB_VS(r), GKOB_VS(z), GKOB_VS(p),
+                                           GKOB_VS(q), prev_rho->get_values(), rho->get_values(), GKOB_VS(r2),
+                                           GKOB_VS(z2), GKOB_VS(p2), GKOB_VS(q2), stop_status.get_data()));
+        auto trans_A = dynamic_cast<const Transposable*>(this->system_matrix_.get());
+        auto trans_M = dynamic_cast<const Transposable*>(this->preconditioner_.get());
+        if (!trans_A) throw NotSupported("Bicg: the system matrix is not Transposable");
+        if (!trans_M) throw NotSupported("Bicg: the preconditioner is not Transposable");
+        auto conj_trans_A = trans_A->conj_transpose();
+        auto conj_trans_M = trans_M->conj_transpose();
+        this->system_matrix_->apply(this->neg_one_.get(), x, this->one_.get(), r.get());
+        r2->copy_from(r.get());
+        stop::CriterionArgs args{this->system_matrix_, b, x, r.get()};
+        auto crit = stop::combine_and_generate(this->criteria_, exec, args);
+        int64 iter = -1;
+        while (true) {
+            this->preconditioner_->apply(r.get(), z.get());
+            conj_trans_M->apply(r2.get(), z2.get());
+            z->compute_conj_dot(r2.get(), rho.get());
+            ++iter;
+            stop::Updater up;
+            up.num_iterations = iter;
+            up.residual = r.get();
+            up.implicit_sq_residual_norm = rho.get();
+            up.solution = x;
+            if (crit->check(1, true, &stop_status, &one_changed, up)) break;
+            GKOB_CALL(vabi<V>::bicg_step_1(ctx, sz.rows, nrhs, GKOB_VS(p), GKOB_CVS(z), GKOB_VS(p2), GKOB_CVS(z2),
+                                           rho->get_const_values(), prev_rho->get_const_values(),
+                                           stop_status.get_const_data()));
+            this->system_matrix_->apply(p.get(), q.get());
+            conj_trans_A->apply(p2.get(), q2.get());
+            p2->compute_conj_dot(q.get(), beta.get());
+            GKOB_CALL(vabi<V>::bicg_step_2(ctx, sz.rows, nrhs, GKOB_VS(x), GKOB_VS(r), GKOB_VS(r2), GKOB_CVS(p),
+                                           GKOB_CVS(q), GKOB_CVS(q2), beta->get_const_values(),
+                                           rho->get_const_values(), stop_status.get_const_data()));
             std::swap(prev_rho, rho);
         }
         this->record(iter, stop_status);

@@ -688,6 +688,47 @@ b200_status b200_comm_allgather_bytes(b200_ctx* ctx, b200_comm* comm, const void
                                       int64_t bytes_per_rank);
 
 /* ---------------------------------------------------------------------------
+ * BiCG and the transposes it applies:
+ *   bicg::initialize / step_1 / step_2   core/solver/bicg_kernels.hpp,
+ *                                        reference/solver/bicg_kernels.cpp:25-118
+ *   csr::transpose                       core/matrix/csr_kernels.hpp,
+ *                                        reference/matrix/csr_kernels.cpp:694-731 (inside a row of
+ *                                        the transpose: ordered by original row, then position)
+ *   jacobi::transpose_jacobi             core/preconditioner/jacobi_kernels.hpp,
+ *                                        reference/preconditioner/jacobi_kernels.cpp:597-627
+ *                                        (full-precision storage; out_blocks has the layout of blocks)
+ * ------------------------------------------------------------------------- */
+#define B200_DECL_BICG(V, VT)                                                                            \
+    b200_status b200_bicg_initialize_##V(                                                                \
+        b200_ctx* ctx, int64_t rows, int64_t cols, const VT* b, int64_t bs, VT* r, int64_t rs, VT* z,    \
+        int64_t zs, VT* p, int64_t ps, VT* q, int64_t qs, VT* prev_rho, VT* rho, VT* r2, int64_t r2s,    \
+        VT* z2, int64_t z2s, VT* p2, int64_t p2s, VT* q2, int64_t q2s, uint8_t* stop);                   \
+    b200_status b200_bicg_step_1_##V(b200_ctx* ctx, int64_t rows, int64_t cols, VT* p, int64_t ps,       \
+                                     const VT* z, int64_t zs, VT* p2, int64_t p2s, const VT* z2,         \
+                                     int64_t z2s, const VT* rho, const VT* prev_rho,                     \
+                                     const uint8_t* stop);                                               \
+    b200_status b200_bicg_step_2_##V(b200_ctx* ctx, int64_t rows, int64_t cols, VT* x, int64_t xs,       \
+                                     VT* r, int64_t rs, VT* r2, int64_t r2s, const VT* p, int64_t ps,    \
+                                     const VT* q, int64_t qs, const VT* q2, int64_t q2s,                 \
+                                     const VT* beta, const VT* rho, const uint8_t* stop);
+B200_DECL_BICG(f64, double)
+B200_DECL_BICG(f32, float)
+#define B200_DECL_TRANSPOSE(V, VT, I, IT)                                                                \
+    b200_status b200_csr_transpose_##V##_##I(b200_ctx* ctx, int64_t num_rows, int64_t num_cols,          \
+                                             int64_t nnz, const IT* row_ptrs, const IT* col_idxs,        \
+                                             const VT* values, IT* t_row_ptrs, IT* t_col_idxs,           \
+                                             VT* t_values);                                              \
+    b200_status b200_jacobi_transpose_##V##_##I(b200_ctx* ctx, int64_t num_blocks,                       \
+                                                int32_t max_block_size, int64_t block_offset,            \
+                                                int64_t group_offset, int32_t group_power,               \
+                                                const IT* block_ptrs, const VT* blocks,                  \
+                                                VT* out_blocks);
+B200_DECL_TRANSPOSE(f64, double, i32, int32_t)
+B200_DECL_TRANSPOSE(f64, double, i64, int64_t)
+B200_DECL_TRANSPOSE(f32, float, i32, int32_t)
+B200_DECL_TRANSPOSE(f32, float, i64, int64_t)
+
+/* ---------------------------------------------------------------------------
  * Distributed set-up on the device: what
  * experimental::distributed::Matrix::read_distributed runs before the first apply
  * (core/distributed/matrix.cpp:300-380).  G = global index type, L = local index type; the

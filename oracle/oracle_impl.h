@@ -282,6 +282,58 @@ void FN(cgs_step_3)(int64_t rows, int64_t cols, const V* t, int64_t ts, const V*
         }
 }
 
+/* reference/solver/bicg_kernels.cpp:25-118 */
+void FN(bicg_initialize)(int64_t rows, int64_t cols, const V* b, int64_t bs, V* r, int64_t rs, V* z,
+                         int64_t zs, V* p, int64_t ps, V* q, int64_t qs, V* prev_rho, V* rho, V* r2,
+                         int64_t r2s, V* z2, int64_t z2s, V* p2, int64_t p2s, V* q2, int64_t q2s,
+                         uint8_t* stop)
+{
+    for (int64_t j = 0; j < cols; ++j) {
+        rho[j] = 0;
+        prev_rho[j] = 1;
+        stop[j] = 0;
+    }
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) {
+            r[i * rs + j] = b[i * bs + j];
+            r2[i * r2s + j] = b[i * bs + j];
+            z[i * zs + j] = p[i * ps + j] = q[i * qs + j] = 0;
+            z2[i * z2s + j] = p2[i * p2s + j] = q2[i * q2s + j] = 0;
+        }
+}
+void FN(bicg_step_1)(int64_t rows, int64_t cols, V* p, int64_t ps, const V* z, int64_t zs, V* p2,
+                     int64_t p2s, const V* z2, int64_t z2s, const V* rho, const V* prev_rho,
+                     const uint8_t* stop)
+{
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) {
+            if (st_has_stopped(stop[j])) continue;
+            if (prev_rho[j] == 0) {
+                p[i * ps + j] = z[i * zs + j];
+                p2[i * p2s + j] = z2[i * z2s + j];
+            } else {
+                const V tmp = rho[j] / prev_rho[j];
+                p[i * ps + j] = z[i * zs + j] + tmp * p[i * ps + j];
+                p2[i * p2s + j] = z2[i * z2s + j] + tmp * p2[i * p2s + j];
+            }
+        }
+}
+void FN(bicg_step_2)(int64_t rows, int64_t cols, V* x, int64_t xs, V* r, int64_t rs, V* r2,
+                     int64_t r2s, const V* p, int64_t ps, const V* q, int64_t qs, const V* q2,
+                     int64_t q2s, const V* beta, const V* rho, const uint8_t* stop)
+{
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) {
+            if (st_has_stopped(stop[j])) continue;
+            if (beta[j] != 0) {
+                const V tmp = rho[j] / beta[j];
+                x[i * xs + j] += tmp * p[i * ps + j];
+                r[i * rs + j] -= tmp * q[i * qs + j];
+                r2[i * r2s + j] -= tmp * q2[i * q2s + j];
+            }
+        }
+}
+
 /* reference/solver/ir_kernels.cpp:17-24: reset every stopping status */
 #ifndef ORC_IR_INITIALIZE
 #define ORC_IR_INITIALIZE
@@ -1091,6 +1143,44 @@ void FNI(jacobi_simple_apply)(int64_t num_blocks, int32_t max_block_size, int64_
 {
     FNI(jacobi_apply)(num_blocks, max_block_size, block_offset, group_offset, group_power,
                       block_ptrs, blocks, NULL, b, bs, num_rhs, NULL, x, xs);
+}
+
+/* reference/matrix/csr_kernels.cpp:694-719 transpose_and_transform with the identity: count the
+ * columns, prefix sum, then walk the rows in order (convert_csr_to_csc) -- inside a row of the
+ * transpose the entries are ordered by (original row, position) */
+void FNI(csr_transpose)(int64_t num_rows, int64_t num_cols, int64_t nnz, const I* row_ptrs, const I* col_idxs,
+                        const V* values, I* t_row_ptrs, I* t_col_idxs, V* t_values)
+{
+    (void)nnz;
+    for (int64_t c = 0; c <= num_cols; ++c) t_row_ptrs[c] = 0;
+    for (int64_t k = 0; k < (int64_t)row_ptrs[num_rows]; ++k) t_row_ptrs[col_idxs[k] + 1]++;
+    for (int64_t c = 0; c < num_cols; ++c) t_row_ptrs[c + 1] += t_row_ptrs[c];
+    I* next = (I*)malloc(sizeof(I) * (size_t)(num_cols > 0 ? num_cols : 1));
+    for (int64_t c = 0; c < num_cols; ++c) next[c] = t_row_ptrs[c];
+    for (int64_t row = 0; row < num_rows; ++row)
+        for (int64_t k = row_ptrs[row]; k < (int64_t)row_ptrs[row + 1]; ++k) {
+            const I dest = next[col_idxs[k]]++;
+            t_col_idxs[dest] = (I)row;
+            t_values[dest] = values[k];
+        }
+    free(next);
+}
+
+/* reference/preconditioner/jacobi_kernels.cpp:208-218 transpose_block, :597-627 transpose_jacobi
+ * (full-precision storage): out(j, i) = in(i, j) inside every block, same storage scheme */
+void FNI(jacobi_transpose)(int64_t num_blocks, int32_t max_block_size, int64_t block_offset,
+                           int64_t group_offset, int32_t group_power, const I* block_ptrs, const V* blocks,
+                           V* out_blocks)
+{
+    (void)max_block_size;
+    const int64_t stride = block_offset << group_power;
+    for (int64_t k = 0; k < num_blocks; ++k) {
+        const int64_t ofs = group_offset * (k >> group_power) +
+                            block_offset * (k & (((int64_t)1 << group_power) - 1));
+        const int64_t n = (int64_t)block_ptrs[k + 1] - block_ptrs[k];
+        for (int64_t i = 0; i < n; ++i)
+            for (int64_t j = 0; j < n; ++j) out_blocks[ofs + i * stride + j] = blocks[ofs + i + j * stride];
+    }
 }
 
 #endif

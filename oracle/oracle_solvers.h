@@ -272,6 +272,66 @@ int64_t FN(cgs_solve)(int64_t n, int64_t cols, const int32_t* rp, const int32_t*
     return iter;
 }
 
+/* core/solver/bicg.cpp:113-232: A^T from csr::transpose, M^T from Jacobi::transpose (the
+ * scalar Jacobi and the identity are their own transposes) */
+int64_t FN(bicg_solve)(int64_t n, int64_t cols, const int32_t* rp, const int32_t* ci, const V* va,
+                       const V* b, V* x, const orc_solver_cfg* cfg, uint8_t* stop_out,
+                       V* resnorm_out)
+{
+    FN(sctx) s = {n, cols, rp, ci, va, cfg, NULL, NULL};
+    const int64_t nnz = rp[n];
+    int32_t* trp = malloc(sizeof(int32_t) * (n + 1));
+    int32_t* tci = malloc(sizeof(int32_t) * (nnz > 0 ? nnz : 1));
+    V* tva = malloc(sizeof(V) * (nnz > 0 ? nnz : 1));
+    CAT(FN(csr_transpose), i32)(n, n, nnz, rp, ci, va, trp, tci, tva);
+    orc_solver_cfg tcfg = *cfg;
+    V* tblocks = NULL;
+    if (cfg->precond == 2) {
+        const int64_t groups = (cfg->num_blocks + ((int64_t)1 << cfg->group_power) - 1) >> cfg->group_power;
+        tblocks = calloc((size_t)(groups * cfg->group_offset + 1), sizeof(V));
+        CAT(FN(jacobi_transpose), i32)(cfg->num_blocks, 32, cfg->block_offset, cfg->group_offset,
+                                       cfg->group_power, cfg->block_ptrs, (const V*)cfg->blocks, tblocks);
+        tcfg.blocks = tblocks;
+    }
+    FN(sctx) st = {n, cols, trp, tci, tva, &tcfg, NULL, NULL};
+    const size_t nb = sizeof(V) * n * cols;
+    V *r = malloc(nb), *z = malloc(nb), *p = malloc(nb), *q = malloc(nb), *r2 = malloc(nb),
+      *z2 = malloc(nb), *p2 = malloc(nb), *q2 = malloc(nb);
+    V* sc = malloc(sizeof(V) * cols * 3);
+    V *beta = sc, *prev_rho = sc + cols, *rho = sc + 2 * cols;
+    s.starting_tau = malloc(sizeof(V) * cols);
+    s.u_tau = malloc(sizeof(V) * cols);
+    uint8_t* stop = malloc(cols);
+    const V one = 1, neg_one = -1;
+    FN(bicg_initialize)(n, cols, b, cols, r, cols, z, cols, p, cols, q, cols, prev_rho, rho, r2, cols,
+                        z2, cols, p2, cols, q2, cols, stop);
+    FN(s_apply_A)(&s, &neg_one, x, &one, r);
+    memcpy(r2, r, nb);
+    FN(s_criterion_generate)(&s, b, r);
+    int64_t iter = -1;
+    int one_changed;
+    while (1) {
+        FN(s_apply_M)(&s, r, z);
+        FN(s_apply_M)(&st, r2, z2);
+        FN(dense_compute_dot)(n, cols, z, cols, r2, cols, rho);
+        ++iter;
+        if (FN(s_check)(&s, iter, r, NULL, rho, 1, stop, &one_changed)) break;
+        FN(bicg_step_1)(n, cols, p, cols, z, cols, p2, cols, z2, cols, rho, prev_rho, stop);
+        FN(s_apply_A)(&s, NULL, p, NULL, q);
+        FN(s_apply_A)(&st, NULL, p2, NULL, q2);
+        FN(dense_compute_dot)(n, cols, p2, cols, q, cols, beta);
+        FN(bicg_step_2)(n, cols, x, cols, r, cols, r2, cols, p, cols, q, cols, q2, cols, beta, rho, stop);
+        V* sw = prev_rho;
+        prev_rho = rho;
+        rho = sw;
+    }
+    if (stop_out) memcpy(stop_out, stop, cols);
+    if (resnorm_out) FN(dense_compute_norm2)(n, cols, r, cols, resnorm_out);
+    free(r); free(z); free(p); free(q); free(r2); free(z2); free(p2); free(q2); free(sc);
+    free(s.starting_tau); free(s.u_tau); free(stop); free(trp); free(tci); free(tva); free(tblocks);
+    return iter;
+}
+
 /* core/solver/update_residual.hpp:20-73 */
 static int FN(s_update_residual)(FN(sctx) * s, int64_t iter, const V* b, const V* x, V* residual,
                                  const V** residual_ptr, uint8_t* stop)

@@ -84,7 +84,7 @@ def solve(kind, rp, ci, va, b, x0, precond_max_bs=0, block_ptrs=None, max_iters=
     nb = 0 if block_ptrs is None else len(block_ptrs) - 1
     lib().refshim_solve_params(float(relaxation_factor), float(foci[0]), float(foci[1]))
     st = lib().refshim_solve(exec_kind, {"cg": 0, "bicgstab": 1, "gmres": 2, "fcg": 3, "cgs": 4, "ir": 5,
-                                         "chebyshev": 6, "pipe_cg": 7, "gcr": 8, "minres": 9}[kind], _vt(va), n,
+                                         "chebyshev": 6, "pipe_cg": 7, "gcr": 8, "minres": 9, "bicg": 10}[kind], _vt(va), n,
                              len(va), _p(rp), _p(ci), _p(va), _p(b2), _p(x), nrhs, precond_max_bs,
                              _p(block_ptrs), nb, max_iters, res_kind, baseline, reduction,
                              iter_first, krylov_dim, ortho, ctypes.byref(iters), _p(resn),
@@ -93,19 +93,33 @@ def solve(kind, rp, ci, va, b, x0, precond_max_bs=0, block_ptrs=None, max_iters=
     return x, iters.value, resn, sec.value
 
 
-def jacobi_generate(rp, ci, va, max_bs, block_ptrs=None):
+def jacobi_generate(rp, ci, va, max_bs, block_ptrs=None, transposed=False):
+    """transposed: the blocks of Jacobi::transpose() of the generated preconditioner"""
     n = len(rp) - 1
     nb = 0 if block_ptrs is None else len(block_ptrs) - 1
     cap = 32 * 32 * (n + 64) if max_bs > 1 else n
     blocks = np.zeros(cap, va.dtype)
     meta = np.zeros(5, np.int64)
     ptrs = np.zeros(n + 2, np.int32)
-    st = lib().refshim_jacobi_generate(_vt(va), n, len(va), _p(rp), _p(ci), _p(va), max_bs,
-                                       _p(block_ptrs), nb, _p(blocks), cap, _p(meta), _p(ptrs))
+    fn = lib().refshim_jacobi_generate_transposed if transposed else lib().refshim_jacobi_generate
+    st = fn(_vt(va), n, len(va), _p(rp), _p(ci), _p(va), max_bs, _p(block_ptrs), nb, _p(blocks), cap,
+            _p(meta), _p(ptrs))
     assert st == 0, st
     return dict(block_offset=int(meta[0]), group_offset=int(meta[1]), group_power=int(meta[2]),
                 num_blocks=int(meta[3]), blocks=blocks[:meta[4]].copy(),
                 block_ptrs=ptrs[:meta[3] + 1].copy())
+
+
+def csr_transpose(rp, ci, va, n_cols):
+    """Csr::transpose() of the real reference -> (row_ptrs, col_idxs, values) of the transpose"""
+    n = len(rp) - 1
+    trp = np.zeros(n_cols + 1, np.int32)
+    tci = np.zeros(max(len(va), 1), np.int32)
+    tva = np.zeros(max(len(va), 1), va.dtype)
+    st = lib().refshim_csr_transpose(_vt(va), n, n_cols, len(va), _p(rp), _p(ci), _p(va), _p(trp), _p(tci),
+                                     _p(tva))
+    assert st == 0, st
+    return trp, tci[:len(va)], tva[:len(va)]
 
 
 def convert(fmt, rp, ci, va, n_cols, slice_size=64, stride_factor=1, strategy=0, columns=0,

@@ -69,6 +69,7 @@ namespace b200 {
 using std::sqrt;
 
 inline void set_error(const char*, ...) {}
+inline int64_t ceildiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 constexpr uint8_t kFinalizedMask = 1u << 6;
 constexpr uint8_t kIdMask = (1u << 6) - 1u;

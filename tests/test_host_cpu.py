@@ -79,7 +79,7 @@ def host_solve(host, kind, vt, rp, ci, va, b, x0, precond_max_bs=0, block_ptrs=N
     return tx.numpy(), s.num_iterations, s.stop_status
 
 
-@pytest.mark.parametrize("kind", ["cg", "fcg", "cgs", "pipe_cg", "minres", "bicgstab", "gmres", "gcr"])
+@pytest.mark.parametrize("kind", ["cg", "fcg", "cgs", "pipe_cg", "minres", "bicgstab", "gmres", "gcr", "bicg"])
 @pytest.mark.parametrize("precond", [0, 1, 2, 3])
 @pytest.mark.parametrize("vt", ["f64", "f32"])
 def test_host_solver_loops_are_the_oracle_loops(host, kind, precond, vt):
@@ -446,3 +446,64 @@ def test_host_read_distributed_on_one_rank(host):
     H.Oracle()("csr_spmv_f64_i32", n, n, len(vals), rp, cols.astype(np.int32), vals,
                x.numpy().reshape(n, 1).copy(), 1, 1, yo, 1)
     assert np.array_equal(y.numpy(), yo[:, 0])
+
+
+# ------------------------------------------------------------------ transposes and BiCG (8f rank 3)
+@pytest.mark.parametrize("vt", ["f64", "f32"])
+def test_host_csr_transpose_applies_like_the_reference_transpose(host, vt):
+    from ginkgo_b200 import api
+    from tests.test_transpose_bicg_cpu import random_csr
+    rng = np.random.default_rng(17)
+    n, m = 300, 170
+    rp, ci, va = random_csr(rng, n, m, 14, vt)
+    A = api.host_csr(host, (n, m), _t(va), _t(ci), _t(rp))
+    A.vt = vt
+    T = api.host_transpose(A)
+    h = api._host()
+    assert (h.gkob_num_rows(T.h), h.gkob_num_cols(T.h)) == (m, n)
+    x = rng.uniform(-1, 1, (n, 2)).astype(VT[vt])
+    y = torch.zeros((m, 2), dtype=_t(va).dtype)
+    xd, yd = api.host_dense(host, _t(x)), api.host_dense(host, y)  # keep the handles alive
+    api._hcheck(h.gkob_apply(T.h, xd.h, yd.h))
+    o = H.Oracle()
+    trp, tci, tva = np.zeros(m + 1, np.int32), np.zeros(len(va), np.int32), np.zeros(len(va), VT[vt])
+    o("csr_transpose_%s_i32" % vt, n, m, len(va), rp, ci, va, trp, tci, tva)
+    yo = np.zeros((m, 2), VT[vt])
+    o("csr_spmv_%s_i32" % vt, m, n, len(va), trp, tci, tva, x, 2, 2, yo, 2)
+    assert np.array_equal(y.numpy(), yo)
+    # transposing twice: the same operator again
+    TT = api.host_transpose(T)
+    y2 = torch.zeros((n, 2), dtype=_t(va).dtype)
+    xm = rng.uniform(-1, 1, (m, 2)).astype(VT[vt])
+    xmd, y2d = api.host_dense(host, _t(xm)), api.host_dense(host, y2)
+    api._hcheck(h.gkob_apply(TT.h, xmd.h, y2d.h))
+    # (rows of A are unsorted, A^TT has them sorted: same sums up to the order of addition)
+    yo2 = np.zeros((n, 2), VT[vt])
+    o("csr_spmv_%s_i32" % vt, n, m, len(va), rp, ci, va, xm, 2, 2, yo2, 2)
+    np.testing.assert_allclose(y2.numpy(), yo2, rtol=1e-4 if vt == "f32" else 1e-12, atol=1e-5 if vt == "f32" else 1e-13)
+
+
+@pytest.mark.parametrize("vt", ["f64", "f32"])
+@pytest.mark.parametrize("precond", [0, 1, 2])
+def test_host_bicg_with_transposed_preconditioner(host, vt, precond):
+    """nonsymmetric values: the blocks of Jacobi::transpose differ from the blocks themselves"""
+    from oracle import ref
+    rp, ci, va = W.laplace(16, 2, vdtype=VT[vt])
+    rng = np.random.default_rng(31)
+    va = (va * rng.uniform(0.6, 1.4, len(va))).astype(VT[vt])
+    n = len(rp) - 1
+    b = rng.uniform(-1, 1, (n, 2)).astype(VT[vt])
+    x0 = np.zeros((n, 2), VT[vt])
+    max_bs = {0: 0, 1: 1, 2: 8}[precond]
+    bp = np.arange(0, n + 1, 8, dtype=np.int32) if precond == 2 else None
+    jac = None
+    if precond:
+        if not ref.available():
+            pytest.skip("needs oracle/_ref for the inverted blocks")
+        jac = ref.jacobi_generate(rp, ci, va, max_bs, bp)
+    red = 1e-9 if vt == "f64" else 1e-4
+    xo, ito, stop_o = H.orc_solve("bicg", vt, rp, ci, va, b, x0, precond, jac, max_iters=200, reduction=red)
+    xh, ith, stop_h = host_solve(host, "bicg", vt, rp, ci, va, b, x0, max_bs, bp, max_iters=200, reduction=red)
+    assert ith == ito and ito > 5
+    assert stop_h == stop_o[0]
+    assert np.array_equal(xh, xo)

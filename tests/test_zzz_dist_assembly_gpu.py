@@ -1,8 +1,9 @@
-"""GPU tests of the distributed set-up kernels (ginkgo_b200/csrc/dist_assembly.cu) and of
-distributed::{Partition, index_map, assemble_local, Matrix::read_distributed} on one GPU.
+"""GPU tests of the distributed set-up kernels (ginkgo_b200/csrc/dist_assembly.cu), of
+distributed::{Partition, index_map, assemble_local, Matrix::read_distributed} on one GPU, and
+of BiCG with its transposes (ginkgo_b200/csrc/bicg_transpose.cu).
 Written after the round's GPU budget was spent: the oracle side, a host-compiled copy of the
 kernel source and the C++ host path are verified on the CPU (tests/test_dist_assembly_cpu.py,
-tests/test_host_cpu.py); this file sorts last so that a surprise here cannot hide another test.
+tests/test_transpose_bicg_cpu.py, tests/test_host_cpu.py); this file sorts last so that a surprise here cannot hide another test.
 The world_size > 1 exchange of read_distributed is exercised by scripts/dist_check.py."""
 import numpy as np
 import pytest
@@ -113,3 +114,71 @@ def test_read_distributed_on_one_gpu(hexec):
     api._hcheck(api._host().gkob_apply(B.h, xd.h, yd.h))
     hexec.synchronize()
     assert torch.equal(y, y2)
+
+
+# ------------------------------------------------------- BiCG and its transposes (8f rank 3)
+from tests import helpers as H  # noqa: E402
+from tests.helpers import VT  # noqa: E402
+from tests.test_transpose_bicg_cpu import random_csr, transpose  # noqa: E402
+
+
+@pytest.mark.parametrize("vt", ["f64", "f32"])
+@pytest.mark.parametrize("it", ["i32", "i64"])
+@pytest.mark.parametrize("n,m,max_row", [(900, 300, 12), (500, 70000, 30), (3000, 256, 5), (40, 1, 3), (6, 6, 0),
+                                         (20000, 20000, 40)])
+def test_csr_transpose_matches_oracle(orc, cuda, vt, it, n, m, max_row):
+    rng = np.random.default_rng(n + 3 * m)
+    rp, ci, va = random_csr(rng, n, m, max_row, vt, it)
+    a = transpose(orc, rp, ci, va, m, vt, it)
+    b = transpose(cuda, rp, ci, va, m, vt, it)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("vt", ["f64", "f32"])
+@pytest.mark.parametrize("rows,cols", [(597, 43), (100001, 1), (0, 2)])
+def test_bicg_steps_match_oracle(orc, cuda, vt, rows, cols):
+    from tests.test_transpose_bicg_cpu import test_kernel_source_bicg_steps_match_oracle as body
+    body(orc, cuda, vt, rows, cols)
+
+
+@pytest.mark.parametrize("vt", ["f64", "f32"])
+def test_jacobi_transpose_matches_oracle(orc, cuda, vt):
+    rng = np.random.default_rng(4)
+    num_blocks, mbs = 300, 8
+    sizes = rng.integers(1, mbs + 1, num_blocks)
+    ptrs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    group_power = 2  # 32 / 8 = 4 blocks per group
+    block_offset, group_offset = mbs, mbs * 4 * mbs
+    space = group_offset * ((num_blocks + 3) // 4)
+    blocks = rng.standard_normal(space).astype(VT[vt])
+    outs = []
+    for be in (orc, cuda):
+        out = np.zeros(space, VT[vt])
+        be("jacobi_transpose_%s_i32" % vt, num_blocks, mbs, block_offset, group_offset, group_power, ptrs,
+           blocks, out)
+        outs.append(out)
+    assert np.array_equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("vt", ["f64", "f32"])
+@pytest.mark.parametrize("precond", [0, 1, 2])
+def test_bicg_solver_matches_oracle(hexec, vt, precond):
+    import workloads as W
+    from tests.test_solvers_gpu import device_solve, ref_jacobi
+    rp, ci, va = W.laplace(16, 2, vdtype=VT[vt])
+    rng = np.random.default_rng(31)
+    va = (va * rng.uniform(0.6, 1.4, len(va))).astype(VT[vt])
+    n = len(rp) - 1
+    b = rng.uniform(-1, 1, (n, 2)).astype(VT[vt])
+    x0 = np.zeros((n, 2), VT[vt])
+    max_bs = {0: 0, 1: 1, 2: 8}[precond]
+    bp = np.arange(0, n + 1, 8, dtype=np.int32) if precond == 2 else None
+    jac = ref_jacobi(vt, rp, ci, va, max_bs, bp) if precond else None
+    red = 1e-9 if vt == "f64" else 1e-4
+    xo, ito, stop_o = H.orc_solve("bicg", vt, rp, ci, va, b, x0, precond, jac, max_iters=200, reduction=red)
+    xd, itd, stop_d, _ = device_solve(hexec, "bicg", vt, rp, ci, va, b, x0, max_bs, bp, max_iters=200,
+                                      reduction=red)
+    assert abs(itd - ito) <= 2
+    tol = 1e-10 if vt == "f64" else 1e-5
+    assert np.linalg.norm(xd - xo) <= tol * 100 * np.linalg.norm(xo)
