@@ -507,3 +507,75 @@ def test_host_bicg_with_transposed_preconditioner(host, vt, precond):
     assert ith == ito and ito > 5
     assert stop_h == stop_o[0]
     assert np.array_equal(xh, xo)
+
+
+@pytest.mark.parametrize("world,seed", [(2, 0), (3, 1), (5, 2)])
+def test_host_read_distributed_multi_rank_in_threads(host, world, seed):
+    """`world` ranks as threads of this process on the mock's in-process communicator (barriers +
+    copies standing for NCCL): communicator::create, Matrix::read_distributed incl. the
+    all-gather of counts / remote lists and the send lists cut from them, halo_create and
+    Matrix::apply -- every rank's rows must equal the single-matrix SpMV bit for bit"""
+    import threading
+    from ginkgo_b200 import api
+    h = api._host()
+    api.DistMatrix._bind(h)
+    rng = np.random.default_rng(60 + seed)
+    n = int(rng.integers(200, 500))
+    nnz = int(rng.integers(2000, 6000))
+    order = np.unique(rng.integers(0, n * n, nnz))
+    rows, cols, vals = order // n, order % n, rng.standard_normal(len(order))
+    if seed == 1:  # one-directional coupling: strictly upper triangular + diagonal
+        keep = cols >= rows
+        rows, cols, vals = rows[keep], cols[keep], vals[keep]
+    row_map = _random_mapping(rng, n, world, 40) if seed else None
+    x = rng.standard_normal(n)
+    rp = np.concatenate([[0], np.cumsum(np.bincount(rows, minlength=n))]).astype(np.int32)
+    want = np.zeros((n, 1))
+    H.Oracle()("csr_spmv_f64_i32", n, n, len(vals), rp, cols.astype(np.int32), vals, x.reshape(n, 1).copy(), 1, 1,
+               want, 1)
+    idb = (ctypes.c_ubyte * 128)()
+    api._hcheck(h.gkob_dist_unique_id(idb))
+    results, errors = {}, []
+
+    def run(rank):
+        try:
+            ex = _CpuExec(h)
+            part = (api.HostPartition.from_mapping(ex, row_map, world) if row_map is not None
+                    else api.HostPartition.uniform(ex, world, n))
+            info = part.info()
+            r64, c64 = np.ascontiguousarray(rows, np.int64), np.ascontiguousarray(cols, np.int64)
+            d = h.gkob_dist_matrix_read_f64_i32(ex.h, idb, rank, world, part.h, n, n, len(vals), r64.ctypes.data,
+                                                c64.ctypes.data, vals.ctypes.data)
+            assert d, h.gkob_last_error().decode()
+            sz = np.zeros(3, np.int64)
+            api._hcheck(h.gkob_dist_matrix_sizes(d, sz.ctypes.data, None))
+            n_local, n_local_cols, n_ghost = (int(v) for v in sz)
+            ghosts = np.zeros(max(n_ghost, 1), np.int64)
+            api._hcheck(h.gkob_dist_matrix_sizes(d, sz.ctypes.data, ghosts.ctypes.data))
+            # local numbering of the owned global indices
+            owned = np.zeros(n_local, np.int64)
+            for r in range(info["num_ranges"]):
+                if info["part_ids"][r] == rank:
+                    b0, b1 = info["range_bounds"][r], info["range_bounds"][r + 1]
+                    owned[info["starting_indices"][r] + np.arange(b1 - b0)] = np.arange(b0, b1)
+            x_ext = np.zeros(n_local + n_ghost)
+            x_ext[:n_local] = x[owned]
+            y = np.zeros(n_local)
+            for _ in range(3):  # repeated exchanges
+                x_ext[n_local:] = -1
+                api._hcheck(h.gkob_dist_spmv_f64(d, x_ext.ctypes.data, y.ctypes.data))
+            results[rank] = (owned, y.copy(), x_ext[n_local:].copy(), ghosts[:n_ghost].copy())
+            h.gkob_dist_destroy(d)
+        except BaseException as e:  # noqa: BLE001
+            errors.append((rank, repr(e)))
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(120)
+    assert not errors, errors
+    assert sorted(results) == list(range(world))
+    for rank, (owned, y, ghost_vals, ghosts) in results.items():
+        assert np.array_equal(ghost_vals, x[ghosts])
+        assert np.array_equal(y, want[owned, 0])
