@@ -191,13 +191,38 @@ def run_gpu_arm(args, rank, world):
             api._hcheck(hl.gkob_apply(A.h, xg.h, yg.h))
         kernel_step = step
     else:
-        A = api.DistMatrix(ex, offs, rp, ci, va)
-        with torch.cuda.stream(ex.stream):
-            x_ext = torch.zeros(A.n_local + A.n_ghost, dtype=torch.float64, device=dev)
-            x_ext[:A.n_local] = x_full[r0:r1]
-            y_t = torch.empty(A.n_local, dtype=torch.float64, device=dev)
-        Aloc = api.host_csr(ex, (A.n_local, A.n_local + A.n_ghost), va, A.col_idxs, rp)
-        xe_h, y_h = api.host_dense(ex, x_ext), api.host_dense(ex, y_t)
+        def build_dist():
+            A_ = api.DistMatrix(ex, offs, rp, ci, va)
+            with torch.cuda.stream(ex.stream):
+                xe = torch.zeros(A_.n_local + A_.n_ghost, dtype=torch.float64, device=dev)
+                xe[:A_.n_local] = x_full[r0:r1]
+                yt = torch.empty(A_.n_local, dtype=torch.float64, device=dev)
+            Al = api.host_csr(ex, (A_.n_local, A_.n_local + A_.n_ghost), va, A_.col_idxs, rp)
+            return A_, xe, yt, Al, api.host_dense(ex, xe), api.host_dense(ex, yt)
+
+        def halo_delivers(A_, xe, yt):
+            """one exchange: every ghost slot must hold the x entry of its global column (all ranks)"""
+            A_.apply(xe, yt)
+            ex.synchronize()
+            with torch.cuda.stream(ex.stream):
+                good = A_.n_ghost == 0 or torch.equal(xe[A_.n_local:], x_full[A_.part["ghosts"].to(dev).long()])
+                t = torch.tensor([1 if good else 0], device=dev)
+            ex.synchronize()
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            return int(t.item()) == 1
+
+        A, x_ext, y_t, Aloc, xe_h, y_h = build_dist()
+        halo_path = "peer-memory halo exchange over NVLink" if A.p2p & 2 else "NCCL halo exchange"
+        if not halo_delivers(A, x_ext, y_t):
+            if not A.p2p:
+                raise RuntimeError("the halo exchange delivers wrong ghost values")
+            # same decision on every rank (all-reduced flag): rebuild on the NCCL path
+            os.environ["B200_P2P"] = "0"
+            del A, Aloc, xe_h, y_h
+            A, x_ext, y_t, Aloc, xe_h, y_h = build_dist()
+            halo_path = "NCCL halo exchange (the peer-memory exchange failed its validation on this box)"
+            if not halo_delivers(A, x_ext, y_t):
+                raise RuntimeError("the halo exchange delivers wrong ghost values")
 
         def step():  # halo exchange (referenced remote entries only) + local SpMV
             A.apply(x_ext, y_t)
@@ -299,8 +324,8 @@ def run_gpu_arm(args, rank, world):
         "config": {"workload": "%s: CSR SpMV fp64/int32, random n=%d nnz=%d (15 distinct uniform "
                                "cols/row), workloads.py seed 42" % (CFG, N_ROWS, nnz_total),
                    "parallelism": "1-D row split over %d GPU(s)%s" %
-                                  (world, ", NCCL halo exchange of the referenced x entries per "
-                                          "step" if world > 1 else ""),
+                                  (world, ", %s of the referenced x entries per step" % halo_path
+                                   if world > 1 else ""),
                    "l2": "inputs (2.0 GB/step) exceed the 126 MB L2; no flush between steps",
                    "gbs": alg_bytes * world / (ms_step * 1e-3) / 1e9},
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": cs.summary(),
