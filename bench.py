@@ -446,9 +446,28 @@ def run_cg(args, rank, world, ex, dev, timed_events=True):
         ms = wall(lambda: s.apply(bd, xd))
         done, ghosts = s.num_iterations, 0
     else:
-        A = api.DistMatrix(ex, offs, rp, ci, va)
-        A.make_cg(scalar_jacobi=False, max_iters=iters, reduction=1e-300, check_every=20)
-        A.cg_apply(b, x)
+        def warm_up():
+            """build + one untimed solve; every rank learns whether ALL ranks got through"""
+            A_ = api.DistMatrix(ex, offs, rp, ci, va)
+            A_.make_cg(scalar_jacobi=False, max_iters=iters, reduction=1e-300, check_every=20)
+            good, why = 1, ""
+            try:
+                good = 1 if A_.cg_apply(b, x)[0] > 0 else 0
+            except Exception as e:  # noqa: BLE001 (a peer-memory wait that timed out)
+                good, why = 0, repr(e)
+            t = torch.tensor([good], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            return A_, int(t.item()) == 1, why
+
+        A, good, why = warm_up()
+        if not good:
+            if not A.p2p:
+                raise RuntimeError("distributed CG failed: " + why)
+            os.environ["B200_P2P"] = "0"  # same decision on every rank: NCCL collectives
+            del A
+            A, good, why = warm_up()
+            if not good:
+                raise RuntimeError("distributed CG failed: " + why)
         x.zero_()
         res = {}
         ms = wall(lambda: res.update(it=A.cg_apply(b, x)[0]))
@@ -462,6 +481,8 @@ def run_cg(args, rank, world, ex, dev, timed_events=True):
                                "b=1, %d iterations, rows split in z-slabs over %d GPU(s)"
                                % (g, n, nnz, iters, world), "iterations": done, "ms": ms,
                    "iters_per_s": done / (ms * 1e-3), "ghosts_per_rank": ghosts,
+                   "collectives": ("single GPU" if world == 1 else
+                                   "peer memory over NVLink" if A.p2p else "NCCL"),
                    "algorithmic_gbs": bytes_it * done / (ms * 1e-3) / 1e9}
     return out
 
