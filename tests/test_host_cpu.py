@@ -45,15 +45,19 @@ def host(tmp_path_factory):
                     os.path.join(ROOT, "tests", "mock", "mock_base.c"), gen], check=True,
                    capture_output=True)
     objs = []
+    # B200_MOCK_SANITIZE=1: build the host layer + mock with ASan / UBSan; run pytest with
+    # LD_PRELOAD="$(g++ -print-file-name=libasan.so) $(g++ -print-file-name=libstdc++.so)"
+    san = (["-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-g"]
+           if os.environ.get("B200_MOCK_SANITIZE") == "1" else [])
     for src in (os.path.join(ROOT, "tests", "mock", "mock_base.c"), gen):
         o = os.path.join(d, os.path.basename(src) + ".o")
-        subprocess.run(["gcc", "-O1", "-fPIC", "-I" + inc, "-c", src, "-o", o], check=True)
+        subprocess.run(["gcc", "-O1", "-fPIC", "-I" + inc, "-c", src, "-o", o] + san, check=True)
         objs.append(o)
     so = os.path.join(d, "libgko_b200_host_mock.so")
     # one DSO, -Bsymbolic: the b200_* references of the host layer bind to the mock inside it,
     # whatever else the process has loaded
     subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-Wl,-Bsymbolic", "-o", so,
-                    os.path.join(ROOT, "ginkgo_b200", "host", "capi.cpp")] + objs +
+                    os.path.join(ROOT, "ginkgo_b200", "host", "capi.cpp")] + san + objs +
                    ["-L" + os.path.join(ROOT, "oracle"), "-loracle",
                     "-Wl,-rpath," + os.path.join(ROOT, "oracle")], check=True)
     lib = api._configure_host_lib(ctypes.CDLL(so))
