@@ -566,6 +566,9 @@ class DistMatrix:
         h.gkob_dist_cg_apply_f64.argtypes = [vp, vp, vp, ctypes.POINTER(ll),
                                              ctypes.POINTER(ctypes.c_ubyte)]
         h.gkob_dist_destroy.argtypes = [vp]
+        h.gkob_dist_solve_f64.restype = i
+        h.gkob_dist_solve_f64.argtypes = [vp, i, i, vp, vp, ll, ll, i, i, ctypes.c_double, i, i, i,
+                                          ctypes.POINTER(ll), ctypes.POINTER(ctypes.c_ubyte)]
 
     @staticmethod
     def _unique_id(exec_, rank, world, group):
@@ -645,6 +648,20 @@ class DistMatrix:
     def apply(self, x_ext, y_local):
         """y_local = A x; x_ext is [n_local owned | n_ghost] (ghosts filled by the exchange)"""
         _hcheck(_host().gkob_dist_spmv_f64(self.h, x_ext.data_ptr(), y_local.data_ptr()))
+
+    def solve(self, kind, b_local, x_local, global_rows, precond_max_bs=0, max_iters=None, res_kind=1,
+              baseline=0, reduction=1e-8, iter_first=True, krylov_dim=30, ortho=0):
+        """any host-layer solver (HostSolver's kinds) on the distributed matrix: b_local / x_local are
+        this rank's rows, wrapped as distributed::Vector (dots and norms sum over the ranks); the
+        preconditioner is generated from the local block.  Collective.  -> (iterations, status)"""
+        kinds = {"cg": 0, "bicgstab": 1, "gmres": 2, "fcg": 3, "cgs": 4, "ir": 5, "chebyshev": 6, "pipe_cg": 7,
+                 "gcr": 8, "minres": 9, "bicg": 10}
+        it, st = ctypes.c_longlong(0), ctypes.c_ubyte(0)
+        _hcheck(_host().gkob_dist_solve_f64(
+            self.h, kinds[kind], precond_max_bs, b_local.data_ptr(), x_local.data_ptr(), global_rows,
+            -1 if max_iters is None else max_iters, res_kind, baseline, reduction, int(iter_first), krylov_dim,
+            ortho, ctypes.byref(it), ctypes.byref(st)))
+        return it.value, st.value
 
     def make_cg(self, scalar_jacobi=False, max_iters=None, res_kind=1, baseline=0, reduction=1e-8,
                 iter_first=True, check_every=16):

@@ -482,7 +482,7 @@ int gkob_dist_spmv_f64(void* dist, double* x_ext, double* y_local)
         auto n = h->A->n_local(), ng = h->A->n_ghost();
         auto xe = matrix::Dense<double>::create_view(h->exec, dim2{n + ng, 1}, x_ext, 1);
         auto y = matrix::Dense<double>::create_view(h->exec, dim2{n, 1}, y_local, 1);
-        h->A->apply(xe.get(), y.get());
+        h->A->apply_extended(xe.get(), y.get());
     });
 }
 
@@ -509,6 +509,30 @@ int gkob_dist_cg_apply_f64(void* dist, const double* b_local, double* x_local, l
         h->cg->apply(b.get(), x.get());
         *iters = h->cg->get_num_iterations();
         *status = h->cg->get_stop_status();
+    });
+}
+
+// any solver of make_solver on the distributed matrix: b_local / x_local are this rank's rows
+// (device pointers), wrapped as distributed::Vector so that dots and norms sum over the ranks;
+// the preconditioner is generated from the local block.  Collective.
+int gkob_dist_solve_f64(void* dist, int kind, int precond_max_bs, const double* b_local, double* x_local,
+                        long long global_rows, long long max_iters, int res_kind, int baseline,
+                        double reduction, int iter_first, int krylov_dim, int ortho, long long* iters,
+                        unsigned char* status)
+{
+    return guarded([&] {
+        auto h = static_cast<DistHandle*>(dist);
+        const size_type n = h->A->n_local();
+        auto b = distributed::Vector<double>::create_view(h->exec, h->comm, dim2{(size_type)global_rows, 1},
+                                                          dim2{n, 1}, const_cast<double*>(b_local), 1);
+        auto x = distributed::Vector<double>::create_view(h->exec, h->comm, dim2{(size_type)global_rows, 1},
+                                                          dim2{n, 1}, x_local, 1);
+        auto solver = make_solver<double>(h->exec, kind, h->A, precond_max_bs, nullptr, 0, max_iters, res_kind,
+                                          baseline, reduction, iter_first, krylov_dim, ortho, 0, 1);
+        solver->apply(b.get(), x.get());
+        auto base = dynamic_cast<solver::SolverBase<double>*>(solver.get());
+        *iters = base ? (long long)base->get_num_iterations() : -1;
+        *status = base ? base->get_stop_status() : 0;
     });
 }
 

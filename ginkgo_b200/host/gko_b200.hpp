@@ -83,6 +83,7 @@ struct viabi;
         static constexpr auto cgs_step_2 = b200_cgs_step_2_##S;                                 \
         static constexpr auto cgs_step_3 = b200_cgs_step_3_##S;                                 \
         static constexpr auto bicg_initialize = b200_bicg_initialize_##S;                       \
+        static constexpr auto compute_sqrt = b200_dense_compute_sqrt_##S;                       \
         static constexpr auto bicg_step_1 = b200_bicg_step_1_##S;                               \
         static constexpr auto bicg_step_2 = b200_bicg_step_2_##S;                               \
         static constexpr auto pipe_cg_initialize_1 = b200_pipe_cg_initialize_1_##S;             \
@@ -280,6 +281,9 @@ public:
     // include/ginkgo/core/base/lin_op.hpp `apply_uses_initial_guess`: true for the iterative
     // solvers (x is read as the starting point), false for matrices and preconditioners
     virtual bool apply_uses_initial_guess() const { return false; }
+    // the operator whose rows this process holds: itself, or for a row-distributed operator its
+    // local block [owned columns | ghost columns] (what a local preconditioner is generated from)
+    virtual const LinOp* local_block() const { return this; }
     // x = op(b)
     void apply(const LinOp* b, LinOp* x) const
     {
@@ -361,11 +365,33 @@ T* as(From* p)
 
 namespace matrix {
 
+// Sum over the ranks of a row-distributed vector: attached to a Dense that holds the LOCAL rows
+// of a distributed vector (distributed::Vector), it completes compute_dot / compute_norm2 the way
+// experimental::distributed::Vector does (core/distributed/vector.cpp:510-534: local kernel,
+// all-reduce, square root).  Null for ordinary vectors.
+template <typename V>
+class reducer {
+public:
+    virtual ~reducer() = default;
+    // in-place sum over all ranks of `count` device values (stream ordered)
+    virtual void sum(V* device_values, size_type count) const = 0;
+};
+
 // ---- Dense (include/ginkgo/core/matrix/dense.hpp) ------------------------------------------
 template <typename V>
 class Dense : public LinOp {
 public:
     using value_type = V;
+    // a vector with `size` rows/cols on the same executor that reduces like this one
+    // (Dense::create_with_config_of / create_with_type_of)
+    std::unique_ptr<Dense> create_like(dim2 size) const
+    {
+        auto d = create(exec_, size);
+        d->reducer_ = reducer_;
+        return d;
+    }
+    void set_reducer(std::shared_ptr<const reducer<V>> r) { reducer_ = std::move(r); }
+    const std::shared_ptr<const reducer<V>>& get_reducer() const { return reducer_; }
     static std::unique_ptr<Dense> create(std::shared_ptr<const Executor> exec, dim2 size = {},
                                          size_type stride = 0)
     {
@@ -407,18 +433,23 @@ public:
     std::unique_ptr<Dense> clone() const
     {
         auto c = create(exec_, size_, stride_);
+        c->reducer_ = reducer_;
         c->copy_from(this);
         return c;
     }
     // rows [r0, r1) as a view (create_submatrix with a full column span)
     std::unique_ptr<Dense> create_submatrix_rows(size_type r0, size_type r1)
     {
-        return create_view(exec_, dim2{r1 - r0, size_.cols}, get_values() + r0 * stride_, stride_);
+        auto v = create_view(exec_, dim2{r1 - r0, size_.cols}, get_values() + r0 * stride_, stride_);
+        v->reducer_ = reducer_;
+        return v;
     }
     std::unique_ptr<const Dense> create_submatrix_rows(size_type r0, size_type r1) const
     {
-        return create_view(exec_, dim2{r1 - r0, size_.cols},
-                           const_cast<V*>(get_const_values()) + r0 * stride_, stride_);
+        auto v = create_view(exec_, dim2{r1 - r0, size_.cols},
+                             const_cast<V*>(get_const_values()) + r0 * stride_, stride_);
+        v->reducer_ = reducer_;
+        return v;
     }
     void copy_from(const Dense* o)
     {
@@ -461,6 +492,7 @@ public:
         require_row(result);
         GKOB_CALL(vabi<V>::dot(exec_->ctx(), size_.rows, size_.cols, get_const_values(), stride_,
                                b->get_const_values(), b->get_stride(), result->get_values()));
+        if (reducer_) reducer_->sum(result->get_values(), size_.cols);
     }
     void compute_conj_dot(const Dense* b, Dense* result) const
     {
@@ -469,10 +501,17 @@ public:
         GKOB_CALL(vabi<V>::conj_dot(exec_->ctx(), size_.rows, size_.cols, get_const_values(),
                                     stride_, b->get_const_values(), b->get_stride(),
                                     result->get_values()));
+        if (reducer_) reducer_->sum(result->get_values(), size_.cols);
     }
     void compute_norm2(Dense* result) const
     {
         require_row(result);
+        if (reducer_) {  // local squared norms, sum over the ranks, square root
+            compute_squared_norm2(result);
+            GKOB_CALL(vabi<V>::compute_sqrt(exec_->ctx(), 1, size_.cols, result->get_values(),
+                                            result->get_stride()));
+            return;
+        }
         GKOB_CALL(vabi<V>::norm2(exec_->ctx(), size_.rows, size_.cols, get_const_values(), stride_,
                                  result->get_values()));
     }
@@ -481,6 +520,7 @@ public:
         require_row(result);
         GKOB_CALL(vabi<V>::sqnorm2(exec_->ctx(), size_.rows, size_.cols, get_const_values(),
                                    stride_, result->get_values()));
+        if (reducer_) reducer_->sum(result->get_values(), size_.cols);
     }
 
 protected:
@@ -517,6 +557,7 @@ private:
     }
     array<V> values_;
     size_type stride_;
+    std::shared_ptr<const reducer<V>> reducer_;
 };
 
 template <typename V>

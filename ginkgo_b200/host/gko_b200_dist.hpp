@@ -70,6 +70,69 @@ struct cabi<float> {
     static constexpr auto halo_exchange = b200_halo_exchange_f32;
 };
 
+// the all-reduce behind a distributed vector's dots and norms
+template <typename V>
+class comm_reducer : public matrix::reducer<V> {
+public:
+    comm_reducer(std::shared_ptr<const Executor> exec, std::shared_ptr<communicator> comm)
+        : exec_(std::move(exec)), comm_(std::move(comm))
+    {}
+    void sum(V* device_values, size_type count) const override
+    {
+        if (comm_->size() > 1 && count)
+            GKOB_CALL(cabi<V>::allreduce(exec_->ctx(), comm_->get(), device_values, (int64)count));
+    }
+    const std::shared_ptr<communicator>& get_communicator() const { return comm_; }
+
+private:
+    std::shared_ptr<const Executor> exec_;
+    std::shared_ptr<communicator> comm_;
+};
+
+// experimental::distributed::Vector (include/ginkgo/core/distributed/vector.hpp): the rows a rank
+// owns of a global vector.  It IS the Dense of its local rows (get_local_vector() == this), so
+// every solver takes it as is; compute_dot / compute_conj_dot / compute_norm2 /
+// compute_squared_norm2 add the sum over the ranks (core/distributed/vector.cpp:480-534), and
+// the vectors a solver creates next to it reduce the same way (Dense::create_like).
+template <typename V>
+class Vector : public matrix::Dense<V> {
+    using Dense = matrix::Dense<V>;
+
+public:
+    static std::unique_ptr<Vector> create(std::shared_ptr<const Executor> exec, std::shared_ptr<communicator> comm,
+                                          dim2 global_size, dim2 local_size)
+    {
+        if (global_size.cols != local_size.cols)
+            throw DimensionMismatch("distributed::Vector: global and local column counts differ");
+        return std::unique_ptr<Vector>(new Vector(exec, comm, global_size, local_size,
+                                                  array<V>(exec, local_size.rows * local_size.cols),
+                                                  local_size.cols));
+    }
+    // non-owning view of the local rows in device memory
+    static std::unique_ptr<Vector> create_view(std::shared_ptr<const Executor> exec,
+                                               std::shared_ptr<communicator> comm, dim2 global_size,
+                                               dim2 local_size, V* device_ptr, size_type stride)
+    {
+        return std::unique_ptr<Vector>(new Vector(exec, comm, global_size, local_size,
+                                                  array<V>::view(exec, local_size.rows * stride, device_ptr),
+                                                  stride));
+    }
+    dim2 get_global_size() const { return global_size_; }
+    const Dense* get_local_vector() const { return this; }
+    Dense* get_local_vector() { return this; }
+    std::shared_ptr<communicator> get_communicator() const { return comm_; }
+
+private:
+    Vector(std::shared_ptr<const Executor> exec, std::shared_ptr<communicator> comm, dim2 global_size,
+           dim2 local_size, array<V> values, size_type stride)
+        : Dense(exec, local_size, std::move(values), stride), global_size_(global_size), comm_(comm)
+    {
+        this->set_reducer(std::make_shared<comm_reducer<V>>(exec, comm));
+    }
+    dim2 global_size_;
+    std::shared_ptr<communicator> comm_;
+};
+
 // C-ABI tables of the distributed set-up kernels, by global / (local, global) / (value, local,
 // global) types
 template <typename I>
@@ -404,16 +467,18 @@ inline send_layout compute_send_layout(const std::vector<int64>& S, int P, int r
 // distributed::Matrix: local rows, columns numbered into the extended vector
 // [n_local owned | n_ghost received]; apply = halo exchange + one local SpMV.
 template <typename V, typename I>
-class Matrix {
+class Matrix : public LinOp {
 public:
     Matrix(std::shared_ptr<const Executor> exec, std::shared_ptr<communicator> comm,
            std::unique_ptr<matrix::Csr<V, I>> local, size_type n_ghost,
            const std::vector<int64>& send_counts, const std::vector<int64>& recv_counts,
            const int32* send_idx_dev, int64 n_local_cols = -1)
-        : exec_(exec), comm_(comm), local_(std::move(local)), n_ghost_(n_ghost)
+        : LinOp(exec, dim2{local->get_size().rows,
+                           n_local_cols < 0 ? local->get_size().rows : (size_type)n_local_cols}),
+          comm_(comm), local_(std::move(local)), n_ghost_(n_ghost)
     {
         // square row/column partition unless told otherwise
-        n_local_cols_ = n_local_cols < 0 ? local_->get_size().rows : (size_type)n_local_cols;
+        n_local_cols_ = size_.cols;
         if (local_->get_size().cols != n_local_cols_ + n_ghost)
             throw BadDimension("distributed::Matrix: local block must be n_local x (n_local_cols+n_ghost)");
         GKOB_CALL(b200_halo_create(exec->ctx(), comm->size(), (int64)n_local_cols_, n_ghost,
@@ -489,18 +554,45 @@ public:
     // global column index of every ghost entry of the extended vector (read_distributed only)
     const std::vector<int64>& get_non_local_to_global() const { return non_local_to_global_; }
     const matrix::Csr<V, I>* get_local_matrix() const { return local_.get(); }
+    const LinOp* local_block() const override { return local_.get(); }
     std::shared_ptr<communicator> get_communicator() const { return comm_; }
     b200_halo* get_halo() const { return halo_; }
     // y_local = A x   (x_ext: owned part filled by the caller, ghosts by the exchange)
-    void apply(matrix::Dense<V>* x_ext, matrix::Dense<V>* y_local) const
+    void apply_extended(matrix::Dense<V>* x_ext, matrix::Dense<V>* y_local) const
     {
         GKOB_CALL(cabi<V>::halo_exchange(exec_->ctx(), comm_->get(), halo_, x_ext->get_values(),
                                          nullptr));
         local_->apply(x_ext, y_local);
     }
+    // a distributed::Vector of this matrix's row / column partition
+    std::unique_ptr<Vector<V>> create_row_vector(size_type global_rows) const
+    {
+        return Vector<V>::create(exec_, comm_, dim2{global_rows, 1}, dim2{n_local(), 1});
+    }
+
+protected:
+    // LinOp::apply on the LOCAL rows of distributed vectors (one column): b's rows are copied
+    // next to the ghost slots of an internal extended vector, then exchange + local SpMV
+    // (experimental::distributed::Matrix::apply_impl, core/distributed/matrix.cpp:450-509)
+    matrix::Dense<V>* gather(const LinOp* lb) const
+    {
+        auto b = as<matrix::Dense<V>>(lb);
+        if (b->get_size().cols != 1)
+            throw NotSupported("distributed::Matrix::apply: one right-hand side per call");
+        if (!x_ext_) x_ext_ = matrix::Dense<V>::create(exec_, dim2{n_local_cols_ + n_ghost_, 1});
+        auto owned = x_ext_->create_submatrix_rows(0, n_local_cols_);
+        owned->copy_from(b);
+        GKOB_CALL(cabi<V>::halo_exchange(exec_->ctx(), comm_->get(), halo_, x_ext_->get_values(), nullptr));
+        return x_ext_.get();
+    }
+    void apply_impl(const LinOp* b, LinOp* x) const override { local_->apply(gather(b), x); }
+    void apply_impl(const LinOp* alpha, const LinOp* b, const LinOp* beta, LinOp* x) const override
+    {
+        local_->apply(alpha, gather(b), beta, x);
+    }
 
 private:
-    std::shared_ptr<const Executor> exec_;
+    mutable std::unique_ptr<matrix::Dense<V>> x_ext_;
     std::shared_ptr<communicator> comm_;
     std::unique_ptr<matrix::Csr<V, I>> local_;
     size_type n_ghost_;

@@ -326,12 +326,16 @@ protected:
     Jacobi(std::shared_ptr<const Executor> exec, dim2 size, uint32 max_block_size)
         : LinOp(exec, size), max_block_size_(max_block_size)
     {}
+    // op: square, or the local block [owned columns | ghost columns] of a distributed matrix, whose
+    // diagonal blocks lie in the owned columns
     Jacobi(std::shared_ptr<const Executor> exec, const Factory& f, std::shared_ptr<const LinOp> op)
-        : LinOp(exec, op->get_size()), max_block_size_(f.max_block_size_)
+        : LinOp(exec, dim2{op->get_size().rows, op->get_size().rows}), max_block_size_(f.max_block_size_)
     {
+        if (op->local_block()->get_size().cols < op->get_size().rows)
+            throw BadDimension("Jacobi: the matrix has fewer columns than rows");
         if (max_block_size_ < 1 || max_block_size_ > 32)
             throw NotSupported("Jacobi: max_block_size must be in [1, 32]");
-        auto csr = as<matrix::Csr<V, I>>(op.get());
+        auto csr = as<matrix::Csr<V, I>>(op->local_block());
         const size_type n = size_.rows;
         if (max_block_size_ == 1) {
             auto diag = csr->extract_diagonal();
@@ -631,8 +635,7 @@ protected:
         auto exec = this->exec_;
         const dim2 sz = b->get_size();
         const size_type nrhs = sz.cols;
-        auto r = Dense::create(exec, sz), z = Dense::create(exec, sz), p = Dense::create(exec, sz),
-             q = Dense::create(exec, sz);
+        auto r = b->create_like(sz), z = b->create_like(sz), p = b->create_like(sz), q = b->create_like(sz);
         auto beta = Dense::create(exec, dim2{1, nrhs}), prev_rho = Dense::create(exec, dim2{1, nrhs}),
              rho = Dense::create(exec, dim2{1, nrhs});
         array<uint8> stop_status(exec, nrhs);
@@ -681,6 +684,7 @@ protected:
         using Csr = matrix::Csr<V, I>;
         auto A = dynamic_cast<const Csr*>(this->system_matrix_.get());
         if (!A || b->get_size().cols != 1 || b->get_stride() != 1 || x->get_stride() != 1) return false;
+        if (b->get_reducer()) return false;  // rows of a distributed vector: the loop with all-reduces
         const V* inv_diag = nullptr;
         if (auto J = dynamic_cast<const preconditioner::Jacobi<V, I>*>(this->preconditioner_.get())) {
             if (J->get_max_block_size() != 1) return false;
@@ -820,7 +824,7 @@ protected:
         auto ctx = exec->ctx();
         const dim2 sz = b->get_size();
         const size_type nrhs = sz.cols;
-        auto mk = [&] { return Dense::create(exec, sz); };
+        auto mk = [&] { return b->create_like(sz); };  // reduces like b (distributed vectors)
         auto sc = [&] { return Dense::create(exec, dim2{1, nrhs}); };
         auto r = mk(), z = mk(), p = mk(), q = mk(), t = mk();
         auto beta = sc(), prev_rho = sc(), rho = sc(), rho_t = sc();
@@ -891,7 +895,7 @@ protected:
         auto ctx = exec->ctx();
         const dim2 sz = b->get_size();
         const size_type nrhs = sz.cols;
-        auto mk = [&] { return Dense::create(exec, sz); };
+        auto mk = [&] { return b->create_like(sz); };  // reduces like b (distributed vectors)
         auto sc = [&] { return Dense::create(exec, dim2{1, nrhs}); };
         auto r = mk(), r_tld = mk(), p = mk(), q = mk(), u = mk(), u_hat = mk(), v_hat = mk(),
              t = mk();
@@ -971,7 +975,7 @@ protected:
         auto ctx = exec->ctx();
         const dim2 sz = b->get_size();
         const size_type nrhs = sz.cols;
-        auto mk = [&] { return Dense::create(exec, sz); };
+        auto mk = [&] { return b->create_like(sz); };  // reduces like b (distributed vectors)
         auto sc = [&] { return Dense::create(exec, dim2{1, nrhs}); };
         auto r = mk(), z = mk(), p = mk(), q = mk(), r2 = mk(), z2 = mk(), p2 = mk(), q2 = mk();
         auto beta = sc(), prev_rho = sc(), rho = sc();
@@ -1050,7 +1054,7 @@ protected:
         auto ctx = exec->ctx();
         const dim2 sz = b->get_size();
         const size_type nrhs = sz.cols;
-        auto mk = [&] { return Dense::create(exec, sz); };
+        auto mk = [&] { return b->create_like(sz); };  // reduces like b (distributed vectors)
         auto sc = [&] { return Dense::create(exec, dim2{1, nrhs}); };
         auto r = mk(), w = mk(), z1 = mk(), z2 = mk(), p = mk(), m = mk(), n = mk(), q = mk(), f = mk(),
              g = mk();
@@ -1144,10 +1148,10 @@ protected:
         auto ctx = exec->ctx();
         const dim2 sz = b->get_size();
         const size_type n = sz.rows, nrhs = sz.cols, kd = krylov_dim_;
-        auto residual = Dense::create(exec, sz), precon_residual = Dense::create(exec, sz),
-             a_precon_residual = Dense::create(exec, sz);
-        auto p_bases = Dense::create(exec, dim2{n * (kd + 1), nrhs});
-        auto ap_bases = Dense::create(exec, dim2{n * (kd + 1), nrhs});
+        auto residual = b->create_like(sz), precon_residual = b->create_like(sz),
+             a_precon_residual = b->create_like(sz);
+        auto p_bases = b->create_like(dim2{n * (kd + 1), nrhs});
+        auto ap_bases = b->create_like(dim2{n * (kd + 1), nrhs});
         auto tmp_rap = Dense::create(exec, dim2{1, nrhs}), tmp_minus_beta = Dense::create(exec, dim2{1, nrhs}),
              residual_norm = Dense::create(exec, dim2{1, nrhs});
         auto ap_norms = Dense::create(exec, dim2{kd + 1, nrhs});
@@ -1247,7 +1251,7 @@ protected:
         auto ctx = exec->ctx();
         const dim2 sz = b->get_size();
         const size_type nrhs = sz.cols;
-        auto mk = [&] { return Dense::create(exec, sz); };
+        auto mk = [&] { return b->create_like(sz); };  // reduces like b (distributed vectors)
         auto sc = [&] { return Dense::create(exec, dim2{1, nrhs}); };
         auto r = mk(), z = mk(), p = mk(), q = mk(), v = mk(), z_tilde = mk(), p_prev = mk(), q_prev = mk();
         auto alpha = sc(), beta = sc(), gamma = sc(), delta = sc(), eta_next = sc(), eta = sc(), tau = sc(),
@@ -1340,7 +1344,7 @@ protected:
         auto x = as<Dense>(lx);
         auto exec = this->exec_;
         const dim2 sz = b->get_size();
-        auto residual = Dense::create(exec, sz);
+        auto residual = b->create_like(sz);
         std::unique_ptr<Dense> inner_solution;
         array<uint8> stop_status(exec, sz.cols);
         GKOB_CALL(b200_ir_initialize(exec->ctx(), sz.cols, stop_status.get_data()));
@@ -1356,7 +1360,7 @@ protected:
             if (this->update_residual(crit.get(), iter, b, x, residual.get(), residual_ptr, &stop_status))
                 break;
             if (inner->apply_uses_initial_guess()) {
-                if (!inner_solution) inner_solution = Dense::create(exec, sz);
+                if (!inner_solution) inner_solution = b->create_like(sz);
                 inner_solution->copy_from(residual_ptr);
                 inner->apply(residual_ptr, inner_solution.get());
                 x->add_scaled(relaxation_.get(), inner_solution.get());
@@ -1418,8 +1422,8 @@ protected:
         auto exec = this->exec_;
         auto ctx = exec->ctx();
         const dim2 sz = b->get_size();
-        auto residual = Dense::create(exec, sz), inner_solution = Dense::create(exec, sz),
-             update_solution = Dense::create(exec, sz);
+        auto residual = b->create_like(sz), inner_solution = b->create_like(sz),
+             update_solution = b->create_like(sz);
         double alpha_host = 1.0 / center_;
         double beta_host = 0.5 * (foci_direction_ * alpha_host) * (foci_direction_ * alpha_host);
         array<uint8> stop_status(exec, sz.cols);
@@ -1487,7 +1491,7 @@ protected:
         auto ctx = exec->ctx();
         const dim2 sz = b->get_size();
         const size_type nrhs = sz.cols;
-        auto mk = [&] { return Dense::create(exec, sz); };
+        auto mk = [&] { return b->create_like(sz); };  // reduces like b (distributed vectors)
         auto sc = [&] { return Dense::create(exec, dim2{1, nrhs}); };
         auto r = mk(), z = mk(), y = mk(), v = mk(), s = mk(), t = mk(), p = mk(), rr = mk();
         auto alpha = sc(), beta = sc(), gamma = sc(), prev_rho = sc(), rho = sc(), omega = sc();
@@ -1593,9 +1597,9 @@ protected:
         auto ctx = exec->ctx();
         const dim2 sz = b->get_size();
         const size_type n = sz.rows, nrhs = sz.cols, kd = krylov_dim_;
-        auto residual = Dense::create(exec, sz), precv = Dense::create(exec, sz),
-             before = Dense::create(exec, sz), after = Dense::create(exec, sz);
-        auto krylov = Dense::create(exec, dim2{n * (kd + 1), nrhs});
+        auto residual = b->create_like(sz), precv = b->create_like(sz), before = b->create_like(sz),
+             after = b->create_like(sz);
+        auto krylov = b->create_like(dim2{n * (kd + 1), nrhs});
         auto hess = Dense::create(exec, dim2{kd, (kd + 1) * nrhs});
         hess->fill(V(0));
         std::unique_ptr<Dense> hess_aux;
@@ -1678,12 +1682,15 @@ protected:
             } else {
                 GKOB_CALL(vabi<V>::gmres_multi_dot(ctx, n, nrhs, restart_iter + 1, GKOB_CVS(krylov),
                                                    GKOB_CVS(next_k), GKOB_VS(hiter)));
+                if (b->get_reducer()) b->get_reducer()->sum(hiter->get_values(), (restart_iter + 1) * nrhs);
                 sub_all(hiter.get());
                 if (ortho_ == gmres::ortho_method::cgs2) {
                     auto haux = hess_aux->create_submatrix_rows(0, restart_iter + 2);
                     GKOB_CALL(vabi<V>::gmres_multi_dot(ctx, n, nrhs, restart_iter + 1,
                                                        GKOB_CVS(krylov), GKOB_CVS(next_k),
                                                        GKOB_VS(haux)));
+                    if (b->get_reducer())
+                        b->get_reducer()->sum(haux->get_values(), (restart_iter + 1) * nrhs);
                     sub_all(haux.get());
                     hiter->add_scaled(this->one_.get(), haux.get());
                 }

@@ -687,6 +687,14 @@ B200_DECL_COMM(f32, float)
 b200_status b200_comm_allgather_bytes(b200_ctx* ctx, b200_comm* comm, const void* send, void* recv,
                                       int64_t bytes_per_rank);
 
+/* dense::compute_sqrt (core/matrix/dense_kernels.hpp; reference/matrix/dense_kernels.cpp:440-448):
+ * data = sqrt(data) element-wise -- the last step of a distributed norm2
+ * (core/distributed/vector.cpp:520-534). */
+b200_status b200_dense_compute_sqrt_f64(b200_ctx* ctx, int64_t rows, int64_t cols, double* data,
+                                        int64_t stride);
+b200_status b200_dense_compute_sqrt_f32(b200_ctx* ctx, int64_t rows, int64_t cols, float* data,
+                                        int64_t stride);
+
 /* ---------------------------------------------------------------------------
  * BiCG and the transposes it applies:
  *   bicg::initialize / step_1 / step_2   core/solver/bicg_kernels.hpp,

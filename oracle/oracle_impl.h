@@ -282,6 +282,13 @@ void FN(cgs_step_3)(int64_t rows, int64_t cols, const V* t, int64_t ts, const V*
         }
 }
 
+/* reference/matrix/dense_kernels.cpp:440-448 */
+void FN(dense_compute_sqrt)(int64_t rows, int64_t cols, V* data, int64_t stride)
+{
+    for (int64_t i = 0; i < rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) data[i * stride + j] = SQRT(data[i * stride + j]);
+}
+
 /* reference/solver/bicg_kernels.cpp:25-118 */
 void FN(bicg_initialize)(int64_t rows, int64_t cols, const V* b, int64_t bs, V* r, int64_t rs, V* z,
                          int64_t zs, V* p, int64_t ps, V* q, int64_t qs, V* prev_rho, V* rho, V* r2,

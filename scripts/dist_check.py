@@ -95,6 +95,28 @@ for name, kw in [("lap3d_40", dict(grid=40, dims=3)), ("cfg2_small", dict(n=2000
     print("rank %d %s: read_distributed n_local=%d n_ghost=%d p2p=%d spmv bit-equal=%s"
           % (rank, name, A2.n_local, A2.n_ghost, A2.p2p, same2), flush=True)
     if name.startswith("lap"):
+        # every host-layer solver on distributed::Matrix / distributed::Vector (dots and norms
+        # all-reduced, Jacobi from the local block) against the same solver on one GPU
+        bfull = W.vector(n, stream=77, xp="torch", device=dev)
+        bd_full = api.host_dense(ex, bfull)
+        for kind, pre in (("cg", 1), ("bicgstab", 0), ("gmres", 1), ("fcg", 0), ("cgs", 1), ("pipe_cg", 0),
+                          ("minres", 0), ("gcr", 1)):
+            s1 = api.HostSolver(ex, kind, A1, precond_max_bs=pre, max_iters=600, reduction=1e-9, fused=False,
+                                krylov_dim=30)
+            with torch.cuda.stream(ex.stream):
+                xs = torch.zeros(n, dtype=torch.float64, device=dev)
+                xl = torch.zeros(A2.n_local, dtype=torch.float64, device=dev)
+                bl = bfull[q0:q1].contiguous()
+            xsd = api.host_dense(ex, xs)
+            s1.apply(bd_full, xsd)
+            it, st = A2.solve(kind, bl, xl, n, precond_max_bs=pre, max_iters=600, reduction=1e-9, krylov_dim=30)
+            ex.synchronize()
+            err = (xl - xs[q0:q1]).norm().item() / max(xs[q0:q1].norm().item(), 1e-300)
+            good = abs(it - s1.num_iterations) <= 2 and err < 1e-7
+            ok &= good
+            print("rank %d %s: distributed %s(precond %d) iters %d (1 GPU: %d) rel diff %.2e ok=%s"
+                  % (rank, name, kind, pre, it, s1.num_iterations, err, good), flush=True)
+    if name.startswith("lap"):
         b = torch.ones(n, dtype=torch.float64, device=dev)
         s1 = api.HostSolver(ex, "cg", A1, precond_max_bs=1, max_iters=2000, reduction=1e-9, fused=True)
         x1 = torch.zeros(n, dtype=torch.float64, device=dev)

@@ -583,3 +583,96 @@ def test_host_read_distributed_multi_rank_in_threads(host, world, seed):
     for rank, (owned, y, ghost_vals, ghosts) in results.items():
         assert np.array_equal(ghost_vals, x[ghosts])
         assert np.array_equal(y, want[owned, 0])
+
+
+DIST_KINDS = ["cg", "fcg", "cgs", "bicgstab", "pipe_cg", "minres", "gmres", "gmres_cgs", "gcr", "ir", "chebyshev"]
+
+
+@pytest.mark.parametrize("kind", DIST_KINDS)
+@pytest.mark.parametrize("precond", [0, 1, 4])
+def test_host_distributed_solvers_in_threads(host, kind, precond):
+    """every solver of the host layer on a distributed::Matrix with distributed::Vector operands,
+    3 ranks as threads: dots and norms are summed over the ranks, Jacobi comes from the local
+    block.  Same iteration count (+-1) and solution as the single-matrix solver."""
+    import threading
+    from ginkgo_b200 import api
+    h = api._host()
+    api.DistMatrix._bind(h)
+    world = 3
+    rp, ci, va = W.laplace(12, 2)
+    n = len(rp) - 1
+    rng = np.random.default_rng(8)
+    b = rng.uniform(-1, 1, n)
+    rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(rp))
+    cols = ci.astype(np.int64)
+    skind = "gmres" if kind == "gmres_cgs" else kind
+    extra = dict(ortho=1) if kind == "gmres_cgs" else {}
+    if kind == "ir":  # Richardson on a spectrum in (0.1, 8): relaxation < 2 / 8
+        extra = dict(relaxation_factor=0.2)
+    if kind == "chebyshev":
+        extra = dict(foci=(0.1, 8.0))
+    # uniform partition in blocks of 4 rows so that auto-detected 4x4 blocks cannot straddle ranks
+    max_bs = precond
+    x1, it1, st1 = host_solve(host, skind, "f64", rp, ci, va, b.reshape(n, 1), np.zeros((n, 1)), max_bs, None,
+                              max_iters=400, reduction=1e-10, krylov_dim=20, **extra)
+    api._host().gkob_solver_params(extra.get("relaxation_factor", 1.0), *extra.get("foci", (0.0, 1.0)))
+    idb = (ctypes.c_ubyte * 128)()
+    api._hcheck(h.gkob_dist_unique_id(idb))
+    out, errors = {}, []
+    kinds = {"cg": 0, "bicgstab": 1, "gmres": 2, "fcg": 3, "cgs": 4, "ir": 5, "chebyshev": 6, "pipe_cg": 7,
+             "gcr": 8, "minres": 9}
+
+    def run(rank):
+        try:
+            ex = _CpuExec(h)
+            part = api.HostPartition.from_contiguous(ex, [0, 48, 96, n])
+            pb = part.info()["range_bounds"]
+            q0, q1 = int(pb[rank]), int(pb[rank + 1])
+            d = h.gkob_dist_matrix_read_f64_i32(ex.h, idb, rank, world, part.h, n, n, len(va), rows.ctypes.data,
+                                                cols.ctypes.data, va.ctypes.data)
+            assert d, h.gkob_last_error().decode()
+            bl, xl = b[q0:q1].copy(), np.zeros(q1 - q0)
+            it, st = ctypes.c_longlong(0), ctypes.c_ubyte(0)
+            rc = h.gkob_dist_solve_f64(d, kinds[skind], max_bs, bl.ctypes.data, xl.ctypes.data, n, 400, 1, 0,
+                                       1e-10, 1, 20, extra.get("ortho", 0), ctypes.byref(it), ctypes.byref(st))
+            assert rc == 0, h.gkob_last_error().decode()
+            out[rank] = (q0, q1, xl, it.value, st.value)
+            h.gkob_dist_destroy(d)
+        except BaseException as e:  # noqa: BLE001
+            errors.append((rank, repr(e)))
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(300)
+    api._host().gkob_solver_params(1.0, 0.0, 1.0)
+    assert not errors, errors
+    x = np.zeros(n)
+    for rank, (q0, q1, xl, it, st) in out.items():
+        x[q0:q1] = xl
+        assert abs(it - it1) <= 1, (it, it1)
+        assert st == st1
+    assert np.isfinite(x1).all()
+    assert np.linalg.norm(x - x1[:, 0]) <= 1e-8 * np.linalg.norm(x1)
+
+
+def test_host_distributed_solve_python_wrapper(host):
+    """DistMatrix.read + DistMatrix.solve (the Python face) at world size 1: bit-identical to the
+    plain solver except for norm2 = sqrt(sum of squares) instead of the scaled nrm2 kernel"""
+    from ginkgo_b200 import api
+    rp, ci, va = W.laplace(10, 2)
+    n = len(rp) - 1
+    rng = np.random.default_rng(12)
+    b = rng.uniform(-1, 1, n)
+    x1, it1, st1 = host_solve(host, "cg", "f64", rp, ci, va, b.reshape(n, 1), np.zeros((n, 1)), 1, None,
+                              max_iters=300, reduction=1e-10)
+    rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(rp))
+    part = api.HostPartition.uniform(host, 1, n)
+    A = api.DistMatrix.read(host, part, (n, n), rows, ci.astype(np.int64), va)
+    bl, xl = _t(b), torch.zeros(n, dtype=torch.float64)
+    it, st = A.solve("cg", bl, xl, n, precond_max_bs=1, max_iters=300, reduction=1e-10)
+    assert abs(it - it1) <= 1 and st == st1
+    assert np.linalg.norm(xl.numpy() - x1[:, 0]) <= 1e-10 * np.linalg.norm(x1)
+    with pytest.raises(api.NotSupported):
+        A.solve("bicg", bl, xl, n)  # no transposed distributed apply

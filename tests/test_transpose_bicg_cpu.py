@@ -30,8 +30,9 @@ def orc():
 def ksrc(tmp_path_factory):
     d = str(tmp_path_factory.mktemp("bicg_ksrc"))
     src = os.path.join(d, "bicg_transpose.cpp")
-    with open(src, "w") as f:
+    with open(src, "w") as f:  # + dense::compute_sqrt (dist_vector.cu), one more element-wise file
         f.write(open(os.path.join(ROOT, "ginkgo_b200", "csrc", "bicg_transpose.cu")).read())
+        f.write(open(os.path.join(ROOT, "ginkgo_b200", "csrc", "dist_vector.cu")).read())
     so = os.path.join(d, "libbicg_transpose_host.so")
     subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-Wl,-Bsymbolic", "-Wall",
                     "-Wno-unused-function", "-ffp-contract=off",
@@ -198,3 +199,14 @@ def test_kernel_source_bicg_steps_match_oracle(orc, ksrc, vt, rows, cols):
         a, b = run(orc, name, args), run(ksrc, name, args)
         for x, y in zip(a, b):
             assert np.array_equal(x, y, equal_nan=True), name
+
+
+@pytest.mark.parametrize("vt", ["f64", "f32"])
+def test_kernel_source_compute_sqrt_matches_oracle(orc, ksrc, vt):
+    rng = np.random.default_rng(2)
+    data = H.dense(rng, 3, 17, 19, vt, fill=rng.uniform(0, 1e6, (3, 17)))
+    a, b = data.copy(), data.copy()
+    orc("dense_compute_sqrt_" + vt, 3, 17, a, 19)
+    ksrc("dense_compute_sqrt_" + vt, 3, 17, b, 19)
+    assert np.array_equal(a, b) and np.array_equal(a[:, :17], np.sqrt(data[:, :17]))
+    assert np.array_equal(a[:, 17:], data[:, 17:])  # padding untouched

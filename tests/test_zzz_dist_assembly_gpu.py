@@ -182,3 +182,37 @@ def test_bicg_solver_matches_oracle(hexec, vt, precond):
     assert abs(itd - ito) <= 2
     tol = 1e-10 if vt == "f64" else 1e-5
     assert np.linalg.norm(xd - xo) <= tol * 100 * np.linalg.norm(xo)
+
+
+# ------------------------------------------- distributed::Vector / generic distributed solvers
+@pytest.mark.parametrize("vt", ["f64", "f32"])
+def test_compute_sqrt_matches_oracle(orc, cuda, vt):
+    from tests.test_transpose_bicg_cpu import test_kernel_source_compute_sqrt_matches_oracle as body
+    body(orc, cuda, vt)
+
+
+@pytest.mark.parametrize("kind,pre", [("cg", 1), ("gmres", 1), ("bicgstab", 0), ("minres", 0)])
+def test_distributed_solver_on_one_gpu(hexec, kind, pre):
+    """world size 1: distributed::Matrix as LinOp + distributed::Vector operands must reproduce
+    the plain solver (the all-reduce is the identity, norm2 goes through sqnorm2 + sqrt)"""
+    import torch
+    import workloads as W
+    from ginkgo_b200 import api
+    from tests.test_solvers_gpu import device_solve
+    rp, ci, va = W.laplace(24, 2)
+    n = len(rp) - 1
+    rng = np.random.default_rng(9)
+    b = rng.uniform(-1, 1, n)
+    x1, it1, st1, _ = device_solve(hexec, kind, "f64", rp, ci, va, b.reshape(n, 1), np.zeros((n, 1)), pre, None,
+                                   max_iters=500, reduction=1e-10, fused=False)
+    rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(rp))
+    part = api.HostPartition.uniform(hexec, 1, n)
+    A = api.DistMatrix.read(hexec, part, (n, n), rows, ci.astype(np.int64), va)
+    with torch.cuda.stream(hexec.stream):
+        bl = torch.from_numpy(b).to(hexec.device)
+        xl = torch.zeros(n, dtype=torch.float64, device=hexec.device)
+    it, st = A.solve(kind, bl, xl, n, precond_max_bs=pre, max_iters=500, reduction=1e-10)
+    hexec.synchronize()
+    assert abs(it - it1) <= 1 and st == st1
+    x = xl.cpu().numpy()
+    assert np.linalg.norm(x - x1[:, 0]) <= 1e-9 * np.linalg.norm(x1)
