@@ -219,6 +219,8 @@ def _configure_host_lib(h):
     h.gkob_csr_read_f64_i32.restype, h.gkob_csr_read_f64_i32.argtypes = vp, [vp, ctypes.c_char_p]
     h.gkob_csr_write_f64_i32.restype = i
     h.gkob_csr_write_f64_i32.argtypes = [vp, ctypes.c_char_p, i]
+    h.gkob_read_f64_i32.restype, h.gkob_read_f64_i32.argtypes = vp, [vp, ctypes.c_char_p, ctypes.c_char_p]
+    h.gkob_write_f64_i32.restype, h.gkob_write_f64_i32.argtypes = i, [vp, ctypes.c_char_p, i]
     h.gkob_num_rows.restype, h.gkob_num_rows.argtypes = ll, [vp]
     h.gkob_num_cols.restype, h.gkob_num_cols.argtypes = ll, [vp]
     h.gkob_solver_params.restype, h.gkob_solver_params.argtypes = None, [d, d, d]
@@ -390,6 +392,19 @@ def host_write_csr(A, path, layout="coordinate"):
     """gko::write / gko::write_binary of a device Csr<double,int32>"""
     _hcheck(_host().gkob_csr_write_f64_i32(A.h, str(path).encode(),
                                            {"coordinate": 0, "array": 1, "binary": 2}[layout]))
+
+
+def host_read(exec_, path, fmt="csr"):
+    """gko::read_generic<Format<double,int32>>: fmt csr | ell | sellp | coo | hybrid"""
+    o = _HostObj(exec_, _host().gkob_read_f64_i32(exec_.h, str(path).encode(), fmt.encode()))
+    o.vt = "f64"
+    o.size = (_host().gkob_num_rows(o.h), _host().gkob_num_cols(o.h))
+    return o
+
+
+def host_write(A, path, layout="coordinate"):
+    """gko::write / gko::write_binary of any of the five formats (double, int32)"""
+    _hcheck(_host().gkob_write_f64_i32(A.h, str(path).encode(), {"coordinate": 0, "array": 1, "binary": 2}[layout]))
 
 
 def host_dense(exec_, t, cols=None, stride=None):

@@ -339,6 +339,61 @@ int gkob_csr_write_f64_i32(void* csr, const char* path, int layout)
             write(os, a, layout == 1 ? layout_type::array : layout_type::coordinate);
     });
 }
+// gko::read_generic<Format<double, int32>>(file): fmt "csr" | "ell" | "sellp" | "coo" | "hybrid"
+void* gkob_read_f64_i32(void* exec, const char* path, const char* fmt)
+{
+    auto e = static_cast<Handle*>(exec)->exec;
+    Handle* h = new Handle{e, nullptr};
+    if (guarded([&] {
+            std::ifstream is(path, std::ios::binary);
+            if (!is) throw StreamError(std::string("cannot open ") + path);
+            const std::string f(fmt);
+            if (f == "csr")
+                h->op = read_generic<matrix::Csr<double, int32>>(is, e);
+            else if (f == "ell")
+                h->op = read_generic<matrix::Ell<double, int32>>(is, e);
+            else if (f == "sellp")
+                h->op = read_generic<matrix::Sellp<double, int32>>(is, e);
+            else if (f == "coo")
+                h->op = read_generic<matrix::Coo<double, int32>>(is, e);
+            else if (f == "hybrid")
+                h->op = read_generic<matrix::Hybrid<double, int32>>(is, e);
+            else
+                throw NotSupported("gkob_read: unknown format " + f);
+        })) {
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+// gko::write / write_binary of any of the five formats (layout: 0 coordinate, 1 array, 2 binary)
+int gkob_write_f64_i32(void* op, const char* path, int layout)
+{
+    return guarded([&] {
+        auto p = static_cast<Handle*>(op)->op.get();
+        std::ofstream os(path, std::ios::binary);
+        if (!os) throw StreamError(std::string("cannot open ") + path);
+        os << std::setprecision(17);
+        auto put = [&](auto* a) {
+            if (layout == 2)
+                write_binary(os, a);
+            else
+                write(os, a, layout == 1 ? layout_type::array : layout_type::coordinate);
+        };
+        if (auto a = dynamic_cast<const matrix::Csr<double, int32>*>(p))
+            put(a);
+        else if (auto a = dynamic_cast<const matrix::Ell<double, int32>*>(p))
+            put(a);
+        else if (auto a = dynamic_cast<const matrix::Sellp<double, int32>*>(p))
+            put(a);
+        else if (auto a = dynamic_cast<const matrix::Coo<double, int32>*>(p))
+            put(a);
+        else if (auto a = dynamic_cast<const matrix::Hybrid<double, int32>*>(p))
+            put(a);
+        else
+            throw NotSupported("gkob_write: not a <double, int32> matrix format");
+    });
+}
 long long gkob_num_rows(void* op) { return (long long)static_cast<Handle*>(op)->op->get_size().rows; }
 long long gkob_num_cols(void* op) { return (long long)static_cast<Handle*>(op)->op->get_size().cols; }
 

@@ -717,6 +717,12 @@ private:
 template <typename V, typename I>
 class Ell : public LinOp {
 public:
+    using value_type = V;
+    using index_type = I;
+    // ReadableFromMatrixData / WritableToMatrixData (gko_b200_convert.hpp): read = Csr::read +
+    // Csr::convert_to on the device, write = the stored entries in row-major order
+    void read(const matrix_data<V, I>& data);
+    void write(matrix_data<V, I>& data) const;
     static std::unique_ptr<Ell> create(std::shared_ptr<const Executor> exec, dim2 size,
                                        size_type num_stored_per_row, size_type stride,
                                        array<V> values, array<I> col_idxs)
@@ -772,6 +778,12 @@ private:
 template <typename V, typename I>
 class Sellp : public LinOp {
 public:
+    using value_type = V;
+    using index_type = I;
+    // ReadableFromMatrixData / WritableToMatrixData (gko_b200_convert.hpp): read = Csr::read +
+    // Csr::convert_to on the device, write = the stored entries in row-major order
+    void read(const matrix_data<V, I>& data);
+    void write(matrix_data<V, I>& data) const;
     static std::unique_ptr<Sellp> create(std::shared_ptr<const Executor> exec, dim2 size,
                                          size_type slice_size, array<std::uint64_t> slice_sets,
                                          array<std::uint64_t> slice_lengths, array<V> values,
@@ -841,6 +853,12 @@ private:
 template <typename V, typename I>
 class Coo : public LinOp {
 public:
+    using value_type = V;
+    using index_type = I;
+    // ReadableFromMatrixData / WritableToMatrixData (gko_b200_convert.hpp): read = Csr::read +
+    // Csr::convert_to on the device, write = the stored entries in row-major order
+    void read(const matrix_data<V, I>& data);
+    void write(matrix_data<V, I>& data) const;
     static std::unique_ptr<Coo> create(std::shared_ptr<const Executor> exec, dim2 size,
                                        array<V> values, array<I> col_idxs, array<I> row_idxs)
     {
@@ -923,6 +941,12 @@ private:
 template <typename V, typename I>
 class Hybrid : public LinOp {
 public:
+    using value_type = V;
+    using index_type = I;
+    // ReadableFromMatrixData / WritableToMatrixData (gko_b200_convert.hpp): read = Csr::read +
+    // Csr::convert_to on the device, write = the stored entries in row-major order
+    void read(const matrix_data<V, I>& data);
+    void write(matrix_data<V, I>& data) const;
     static std::unique_ptr<Hybrid> create(std::shared_ptr<const Executor> exec,
                                           std::unique_ptr<Ell<V, I>> ell,
                                           std::unique_ptr<Coo<V, I>> coo)

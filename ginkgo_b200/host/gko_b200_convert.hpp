@@ -114,5 +114,102 @@ void Csr<V, I>::sort_by_column_index()
                                                      col_idxs_.get_data(), values_.get_data())));
 }
 
+// ---- ReadableFromMatrixData / WritableToMatrixData of the other formats ---------------------
+// read: through Csr (Csr::read, then the device conversion) -- the same layout the reference's
+// own read produces (core/matrix/{ell,sellp,coo,hybrid}.cpp `read`: widest row / slice sets /
+// strategy split computed from the row lengths).  write: the reference's loops
+// (core/matrix/ell.cpp `write`, sellp.cpp, coo.cpp, hybrid.cpp) over host copies of the arrays.
+template <typename V, typename I>
+void Ell<V, I>::read(const matrix_data<V, I>& data)
+{
+    auto tmp = Csr<V, I>::create(exec_);
+    tmp->read(data);
+    tmp->convert_to(this);
+}
+template <typename V, typename I>
+void Sellp<V, I>::read(const matrix_data<V, I>& data)
+{
+    auto tmp = Csr<V, I>::create(exec_);
+    tmp->read(data);
+    tmp->convert_to(this);
+}
+template <typename V, typename I>
+void Coo<V, I>::read(const matrix_data<V, I>& data)
+{
+    auto tmp = Csr<V, I>::create(exec_);
+    tmp->read(data);
+    tmp->convert_to(this);
+}
+template <typename V, typename I>
+void Hybrid<V, I>::read(const matrix_data<V, I>& data)
+{
+    auto tmp = Csr<V, I>::create(exec_);
+    tmp->read(data);
+    tmp->convert_to(this);
+}
+
+template <typename V, typename I>
+void Ell<V, I>::write(matrix_data<V, I>& data) const
+{
+    const auto vals = values_.to_host();
+    const auto cols = col_idxs_.to_host();
+    data = matrix_data<V, I>(size_);
+    for (size_type row = 0; row < size_.rows; ++row)
+        for (size_type i = 0; i < width_; ++i) {
+            const I col = cols[row + i * stride_];
+            if (col != I(-1)) data.nonzeros.push_back({(I)row, col, vals[row + i * stride_]});
+        }
+}
+template <typename V, typename I>
+void Sellp<V, I>::write(matrix_data<V, I>& data) const
+{
+    const auto vals = values_.to_host();
+    const auto cols = col_idxs_.to_host();
+    const auto sets = sets_.to_host();
+    const auto lens = lens_.to_host();
+    data = matrix_data<V, I>(size_);
+    const size_type num_slices = lens.size();
+    for (size_type slice = 0; slice < num_slices; ++slice)
+        for (size_type r = 0; r < slice_size_; ++r) {
+            const size_type row = slice * slice_size_ + r;
+            if (row >= size_.rows) break;
+            for (size_type i = 0; i < lens[slice]; ++i) {
+                const size_type at = (sets[slice] + i) * slice_size_ + r;
+                if (cols[at] != I(-1)) data.nonzeros.push_back({(I)row, cols[at], vals[at]});
+            }
+        }
+}
+template <typename V, typename I>
+void Coo<V, I>::write(matrix_data<V, I>& data) const
+{
+    const auto vals = values_.to_host();
+    const auto cols = col_idxs_.to_host();
+    const auto rows = row_idxs_.to_host();
+    data = matrix_data<V, I>(size_);
+    for (size_type k = 0; k < vals.size(); ++k) data.nonzeros.push_back({rows[k], cols[k], vals[k]});
+}
+template <typename V, typename I>
+void Hybrid<V, I>::write(matrix_data<V, I>& data) const
+{
+    const auto evals = ell_->values_.to_host();
+    const auto ecols = ell_->col_idxs_.to_host();
+    const auto cvals = coo_->values_.to_host();
+    const auto ccols = coo_->col_idxs_.to_host();
+    const auto crows = coo_->row_idxs_.to_host();
+    const size_type width = ell_->width_, stride = ell_->stride_;
+    data = matrix_data<V, I>(size_);
+    size_type coo_at = 0;
+    for (size_type row = 0; row < size_.rows; ++row) {
+        for (size_type i = 0; i < width; ++i) {
+            const I col = ecols[row + i * stride];
+            if (col != I(-1)) data.nonzeros.push_back({(I)row, col, evals[row + i * stride]});
+        }
+        while (coo_at < cvals.size() && (size_type)crows[coo_at] == row) {
+            data.nonzeros.push_back({(I)row, ccols[coo_at], cvals[coo_at]});
+            ++coo_at;
+        }
+    }
+}
+
 }  // namespace matrix
 }  // namespace gko_b200
