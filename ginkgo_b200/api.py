@@ -259,7 +259,7 @@ def _configure_host_lib(h):
     h.gkob_dist_assembly_destroy.restype, h.gkob_dist_assembly_destroy.argtypes = None, [vp]
     h.gkob_dist_send_layout.restype, h.gkob_dist_send_layout.argtypes = i, [i, i, vp, vp, vp]
     h.gkob_dist_matrix_read_f64_i32.restype = vp
-    h.gkob_dist_matrix_read_f64_i32.argtypes = [vp, vp, i, i, vp, ll, ll, ll, vp, vp, vp]
+    h.gkob_dist_matrix_read_f64_i32.argtypes = [vp, vp, i, i, vp, ll, ll, ll, vp, vp, vp, i]
     h.gkob_dist_matrix_sizes.restype, h.gkob_dist_matrix_sizes.argtypes = i, [vp, vp, vp]
     return h
 
@@ -582,7 +582,7 @@ class DistMatrix:
                                              ctypes.POINTER(ctypes.c_ubyte)]
         h.gkob_dist_destroy.argtypes = [vp]
         h.gkob_dist_solve_f64.restype = i
-        h.gkob_dist_solve_f64.argtypes = [vp, i, i, vp, vp, ll, ll, i, i, ctypes.c_double, i, i, i,
+        h.gkob_dist_solve_f64.argtypes = [vp, i, i, i, vp, vp, ll, ll, i, i, ctypes.c_double, i, i, i,
                                           ctypes.POINTER(ll), ctypes.POINTER(ctypes.c_ubyte)]
 
     @staticmethod
@@ -628,11 +628,12 @@ class DistMatrix:
             raise _lib.B200Error(h.gkob_last_error().decode())
 
     @classmethod
-    def read(cls, exec_, partition, shape, rows, cols, vals, group=None):
+    def read(cls, exec_, partition, shape, rows, cols, vals, group=None, keep_local_block=False):
         """experimental::distributed::Matrix::read_distributed: every rank passes the global
         (row-major sorted) triplets -- or at least its own rows -- and a HostPartition with one
         part per rank; the split, the column renumbering and the exchange of the send lists run
-        in the library (device kernels + its own communicator).  Collective."""
+        in the library (device kernels + its own communicator).  keep_local_block: also keep the
+        square block of the owned columns (needed by solve(..., schwarz != 0)).  Collective."""
         import torch.distributed as dist
         h = _host()
         cls._bind(h)
@@ -643,7 +644,8 @@ class DistMatrix:
         idb = cls._unique_id(exec_, self.rank, self.world, group)
         r, c, v = _np(rows, "int64"), _np(cols, "int64"), _np(vals, "float64")
         self.h = h.gkob_dist_matrix_read_f64_i32(exec_.h, idb, self.rank, self.world, partition.h, shape[0],
-                                                 shape[1], len(r), r.ctypes.data, c.ctypes.data, v.ctypes.data)
+                                                 shape[1], len(r), r.ctypes.data, c.ctypes.data, v.ctypes.data,
+                                                 int(keep_local_block))
         if not self.h:
             raise _lib.B200Error(h.gkob_last_error().decode())
         import numpy as np
@@ -665,15 +667,17 @@ class DistMatrix:
         _hcheck(_host().gkob_dist_spmv_f64(self.h, x_ext.data_ptr(), y_local.data_ptr()))
 
     def solve(self, kind, b_local, x_local, global_rows, precond_max_bs=0, max_iters=None, res_kind=1,
-              baseline=0, reduction=1e-8, iter_first=True, krylov_dim=30, ortho=0):
+              baseline=0, reduction=1e-8, iter_first=True, krylov_dim=30, ortho=0, schwarz=0):
         """any host-layer solver (HostSolver's kinds) on the distributed matrix: b_local / x_local are
         this rank's rows, wrapped as distributed::Vector (dots and norms sum over the ranks); the
-        preconditioner is generated from the local block.  Collective.  -> (iterations, status)"""
+        preconditioner is Jacobi(precond_max_bs) generated from the local block (schwarz=0), or
+        distributed::preconditioner::Schwarz around that Jacobi on the square local block (schwarz=-1)
+        or around `schwarz` Richardson sweeps preconditioned by it.  Collective.  -> (iterations, status)"""
         kinds = {"cg": 0, "bicgstab": 1, "gmres": 2, "fcg": 3, "cgs": 4, "ir": 5, "chebyshev": 6, "pipe_cg": 7,
                  "gcr": 8, "minres": 9, "bicg": 10}
         it, st = ctypes.c_longlong(0), ctypes.c_ubyte(0)
         _hcheck(_host().gkob_dist_solve_f64(
-            self.h, kinds[kind], precond_max_bs, b_local.data_ptr(), x_local.data_ptr(), global_rows,
+            self.h, kinds[kind], precond_max_bs, schwarz, b_local.data_ptr(), x_local.data_ptr(), global_rows,
             -1 if max_iters is None else max_iters, res_kind, baseline, reduction, int(iter_first), krylov_dim,
             ortho, ctypes.byref(it), ctypes.byref(st)))
         return it.value, st.value

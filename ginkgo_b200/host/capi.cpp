@@ -42,7 +42,8 @@ std::unique_ptr<LinOp> make_solver(std::shared_ptr<Executor> exec, int kind,
                                    std::shared_ptr<LinOp> A, int precond_max_bs,
                                    const int32* block_ptrs, int64 nblocks, int64 max_iters,
                                    int res_kind, int baseline, double reduction, int iter_first,
-                                   int krylov_dim, int ortho, int fused, int check_every)
+                                   int krylov_dim, int ortho, int fused, int check_every,
+                                   std::shared_ptr<const LinOp> generated_pre = nullptr)
 {
     std::vector<std::shared_ptr<const stop::CriterionFactory>> crit;
     std::shared_ptr<const stop::CriterionFactory> it_c, res_c;
@@ -72,40 +73,47 @@ std::unique_ptr<LinOp> make_solver(std::shared_ptr<Executor> exec, int kind,
             pb.with_block_pointers(std::vector<int32>(block_ptrs, block_ptrs + nblocks + 1));
         pre = pb.on(exec);
     }
+    auto set_pre = [&](auto& f) {
+        if (generated_pre)
+            f.with_generated_preconditioner(generated_pre);
+        else if (pre)
+            f.with_preconditioner(pre);
+    };
+    if (generated_pre && kind == 5) throw NotSupported("make_solver: Ir takes a solver factory");
     if (kind == 0) {
         auto f = solver::Cg<V>::build();
         f.with_criteria(crit).with_fused(fused != 0).with_check_every(check_every);
-        if (pre) f.with_preconditioner(pre);
+        set_pre(f);
         return f.on(exec)->generate(A);
     }
     if (kind == 1) {
         auto f = solver::Bicgstab<V>::build();
         f.with_criteria(crit);
-        if (pre) f.with_preconditioner(pre);
+        set_pre(f);
         return f.on(exec)->generate(A);
     }
     if (kind == 10) {
         auto f = solver::Bicg<V>::build();
         f.with_criteria(crit);
-        if (pre) f.with_preconditioner(pre);
+        set_pre(f);
         return f.on(exec)->generate(A);
     }
     if (kind == 9) {
         auto f = solver::Minres<V>::build();
         f.with_criteria(crit);
-        if (pre) f.with_preconditioner(pre);
+        set_pre(f);
         return f.on(exec)->generate(A);
     }
     if (kind == 8) {
         auto f = solver::Gcr<V>::build();
         f.with_criteria(crit).with_krylov_dim((size_type)krylov_dim);
-        if (pre) f.with_preconditioner(pre);
+        set_pre(f);
         return f.on(exec)->generate(A);
     }
     if (kind == 7) {
         auto f = solver::PipeCg<V>::build();
         f.with_criteria(crit);
-        if (pre) f.with_preconditioner(pre);
+        set_pre(f);
         return f.on(exec)->generate(A);
     }
     if (kind == 5) {
@@ -117,19 +125,19 @@ std::unique_ptr<LinOp> make_solver(std::shared_ptr<Executor> exec, int kind,
     if (kind == 6) {
         auto f = solver::Chebyshev<V>::build();
         f.with_criteria(crit).with_foci(g_foci_lo, g_foci_hi);
-        if (pre) f.with_preconditioner(pre);
+        set_pre(f);
         return f.on(exec)->generate(A);
     }
     if (kind == 3) {
         auto f = solver::Fcg<V>::build();
         f.with_criteria(crit);
-        if (pre) f.with_preconditioner(pre);
+        set_pre(f);
         return f.on(exec)->generate(A);
     }
     if (kind == 4) {
         auto f = solver::Cgs<V>::build();
         f.with_criteria(crit);
-        if (pre) f.with_preconditioner(pre);
+        set_pre(f);
         return f.on(exec)->generate(A);
     }
     auto f = solver::Gmres<V>::build();
@@ -137,7 +145,7 @@ std::unique_ptr<LinOp> make_solver(std::shared_ptr<Executor> exec, int kind,
     f.with_ortho_method(ortho == 0   ? solver::gmres::ortho_method::mgs
                         : ortho == 1 ? solver::gmres::ortho_method::cgs
                                      : solver::gmres::ortho_method::cgs2);
-    if (pre) f.with_preconditioner(pre);
+    set_pre(f);
     return f.on(exec)->generate(A);
 }
 }  // namespace
@@ -570,10 +578,13 @@ int gkob_dist_cg_apply_f64(void* dist, const double* b_local, double* x_local, l
 // any solver of make_solver on the distributed matrix: b_local / x_local are this rank's rows
 // (device pointers), wrapped as distributed::Vector so that dots and norms sum over the ranks;
 // the preconditioner is generated from the local block.  Collective.
-int gkob_dist_solve_f64(void* dist, int kind, int precond_max_bs, const double* b_local, double* x_local,
-                        long long global_rows, long long max_iters, int res_kind, int baseline,
-                        double reduction, int iter_first, int krylov_dim, int ortho, long long* iters,
-                        unsigned char* status)
+// schwarz_sweeps: 0 = Jacobi(precond_max_bs) generated from the local block; -1 = Schwarz whose
+// local solver is that Jacobi on the square local block; k > 0 = Schwarz whose local solver is k
+// Richardson sweeps (Ir, relaxation from gkob_solver_params) preconditioned by that Jacobi
+int gkob_dist_solve_f64(void* dist, int kind, int precond_max_bs, int schwarz_sweeps, const double* b_local,
+                        double* x_local, long long global_rows, long long max_iters, int res_kind,
+                        int baseline, double reduction, int iter_first, int krylov_dim, int ortho,
+                        long long* iters, unsigned char* status)
 {
     return guarded([&] {
         auto h = static_cast<DistHandle*>(dist);
@@ -582,8 +593,28 @@ int gkob_dist_solve_f64(void* dist, int kind, int precond_max_bs, const double* 
                                                           dim2{n, 1}, const_cast<double*>(b_local), 1);
         auto x = distributed::Vector<double>::create_view(h->exec, h->comm, dim2{(size_type)global_rows, 1},
                                                           dim2{n, 1}, x_local, 1);
-        auto solver = make_solver<double>(h->exec, kind, h->A, precond_max_bs, nullptr, 0, max_iters, res_kind,
-                                          baseline, reduction, iter_first, krylov_dim, ortho, 0, 1);
+        std::unique_ptr<LinOp> solver;
+        if (schwarz_sweeps == 0) {
+            solver = make_solver<double>(h->exec, kind, h->A, precond_max_bs, nullptr, 0, max_iters, res_kind,
+                                         baseline, reduction, iter_first, krylov_dim, ortho, 0, 1);
+        } else {
+            using jac = preconditioner::Jacobi<double, int32>;
+            std::shared_ptr<const LinOpFactory> local =
+                jac::build().with_max_block_size((uint32)std::max(precond_max_bs, 1)).on(h->exec);
+            if (schwarz_sweeps > 0)
+                local = solver::Ir<double>::build()
+                            .with_criteria(stop::Iteration::build().with_max_iters((size_type)schwarz_sweeps))
+                            .with_solver(local)
+                            .with_relaxation_factor(g_relaxation)
+                            .with_default_initial_guess(solver::initial_guess_mode::zero)
+                            .on(h->exec);
+            std::shared_ptr<const LinOp> schwarz = distributed::preconditioner::Schwarz<double, int32>::build()
+                                                       .with_local_solver(local)
+                                                       .on(h->exec)
+                                                       ->generate(h->A);
+            solver = make_solver<double>(h->exec, kind, h->A, 0, nullptr, 0, max_iters, res_kind, baseline,
+                                         reduction, iter_first, krylov_dim, ortho, 0, 1, schwarz);
+        }
         solver->apply(b.get(), x.get());
         auto base = dynamic_cast<solver::SolverBase<double>*>(solver.get());
         *iters = base ? (long long)base->get_num_iterations() : -1;
@@ -769,7 +800,8 @@ int gkob_dist_send_layout(int P, int rank, const long long* S, long long* send_c
 // collective: distributed::Matrix::read_distributed of the global triplets (row-major sorted)
 void* gkob_dist_matrix_read_f64_i32(void* exec, const unsigned char* id128, int rank, int nranks,
                                     void* row_part, long long nrows, long long ncols, long long nnz,
-                                    const long long* rows, const long long* cols, const double* vals)
+                                    const long long* rows, const long long* cols, const double* vals,
+                                    int keep_local_block)
 {
     auto e = static_cast<Handle*>(exec)->exec;
     auto h = new DistHandle();
@@ -778,7 +810,7 @@ void* gkob_dist_matrix_read_f64_i32(void* exec, const unsigned char* id128, int 
             h->comm = distributed::communicator::create(e, id128, rank, nranks);
             h->A = distributed::Matrix<double, int32>::read_distributed<int64>(
                 e, h->comm, triplets(nrows, ncols, nnz, rows, cols, vals),
-                static_cast<PartHandle*>(row_part)->part);
+                static_cast<PartHandle*>(row_part)->part, nullptr, keep_local_block != 0);
         })) {
         delete h;
         return nullptr;

@@ -389,13 +389,16 @@ struct local_assembly {
     std::unique_ptr<matrix::Csr<V, I>> local;  // n_local_rows x (n_local_cols + n_ghost)
     size_type n_local_rows = 0, n_local_cols = 0, n_ghost = 0;
     std::unique_ptr<index_map<I, G>> imap;     // remote columns of this rank
+    // optional: the square block of the owned columns alone (the reference's local_mtx), for
+    // local solvers (Schwarz)
+    std::shared_ptr<matrix::Csr<V, I>> local_only;
 };
 
 template <typename V, typename I, typename G>
 local_assembly<V, I, G> assemble_local(std::shared_ptr<const Executor> exec, const matrix_data<V, G>& data,
                                        std::shared_ptr<const Partition<I, G>> row_part,
                                        std::shared_ptr<const Partition<I, G>> col_part,
-                                       comm_index_type rank)
+                                       comm_index_type rank, bool keep_local_block = false)
 {
     if (data.size.rows != row_part->get_size() || data.size.cols != col_part->get_size())
         throw DimensionMismatch("read_distributed: the partitions must cover the matrix");
@@ -442,6 +445,24 @@ local_assembly<V, I, G> assemble_local(std::shared_ptr<const Executor> exec, con
                                             row_ptrs.get_data()));
     out.local = matrix::Csr<V, I>::create(exec, dim2{out.n_local_rows, out.n_local_cols + out.n_ghost},
                                           std::move(kvals), std::move(lcols), std::move(row_ptrs));
+    if (keep_local_block) {
+        // separate_local_nonlocal's local arrays (the non-local ones are not needed here)
+        array<I> lr(exec, (size_type)n_loc), lc(exec, (size_type)n_loc), nr(exec, (size_type)n_non);
+        array<G> nc(exec, (size_type)n_non);
+        array<V> lv(exec, (size_type)n_loc), nv(exec, (size_type)n_non);
+        GKOB_CALL((vlgabi<V, I, G>::separate_fill(
+            ctx, (int64)nnz, rows.get_const_data(), cols.get_const_data(), vals.get_const_data(),
+            (int64)row_part->get_num_ranges(), row_part->get_range_bounds(),
+            row_part->get_range_starting_indices(), (int64)col_part->get_num_ranges(),
+            col_part->get_range_bounds(), col_part->get_range_starting_indices(), cls.get_const_data(),
+            lrank.get_const_data(), nrank.get_const_data(), lr.get_data(), lc.get_data(), lv.get_data(),
+            nr.get_data(), nc.get_data(), nv.get_data())));
+        array<I> lptrs(exec, out.n_local_rows + 1);
+        GKOB_CALL(iabi<I>::convert_idxs_to_ptrs(ctx, lr.get_const_data(), n_loc, (int64)out.n_local_rows,
+                                                lptrs.get_data()));
+        out.local_only = matrix::Csr<V, I>::create(exec, dim2{out.n_local_rows, out.n_local_cols},
+                                                   std::move(lv), std::move(lc), std::move(lptrs));
+    }
     return out;
 }
 
@@ -500,14 +521,15 @@ public:
                                                     std::shared_ptr<communicator> comm,
                                                     const matrix_data<V, G>& data,
                                                     std::shared_ptr<const Partition<I, G>> row_part,
-                                                    std::shared_ptr<const Partition<I, G>> col_part = nullptr)
+                                                    std::shared_ptr<const Partition<I, G>> col_part = nullptr,
+                                                    bool keep_local_block = false)
     {
         static_assert(sizeof(I) == 4, "the halo exchange indexes its send buffer with int32");
         if (!col_part) col_part = row_part;
         const int P = comm->size(), rank = comm->rank();
         if (row_part->get_num_parts() != P)
             throw DimensionMismatch("read_distributed: one part per rank of the communicator");
-        auto a = assemble_local<V, I, G>(exec, data, row_part, col_part, rank);
+        auto a = assemble_local<V, I, G>(exec, data, row_part, col_part, rank, keep_local_block);
         const auto& recv_counts = a.imap->get_remote_sizes();
         std::vector<int64> send_counts(P, 0);
         array<int32> send_idx(exec, 0);
@@ -545,6 +567,7 @@ public:
                                           send_idx.get_const_data(), (int64)a.n_local_cols);
         const auto rg = a.imap->get_remote_global_idxs().to_host();
         m->non_local_to_global_.assign(rg.begin(), rg.end());
+        m->local_only_ = a.local_only;
         return m;
     }
 
@@ -555,6 +578,15 @@ public:
     const std::vector<int64>& get_non_local_to_global() const { return non_local_to_global_; }
     const matrix::Csr<V, I>* get_local_matrix() const { return local_.get(); }
     const LinOp* local_block() const override { return local_.get(); }
+    // the square block of the owned columns (experimental::distributed::Matrix::get_local_matrix);
+    // kept only when read_distributed was asked to (keep_local_block)
+    std::shared_ptr<const matrix::Csr<V, I>> get_local_diagonal_block() const
+    {
+        if (!local_only_)
+            throw NotSupported("distributed::Matrix: read_distributed(..., keep_local_block = true) keeps the "
+                               "square local block a local solver needs");
+        return local_only_;
+    }
     std::shared_ptr<communicator> get_communicator() const { return comm_; }
     b200_halo* get_halo() const { return halo_; }
     // y_local = A x   (x_ext: owned part filled by the caller, ghosts by the exchange)
@@ -599,7 +631,85 @@ private:
     size_type n_local_cols_ = 0;
     b200_halo* halo_ = nullptr;
     std::vector<int64> non_local_to_global_;  // read_distributed: global index of every ghost column
+    std::shared_ptr<matrix::Csr<V, I>> local_only_;
 };
+
+namespace preconditioner {
+
+// experimental::distributed::preconditioner::Schwarz, one level (core/distributed/preconditioner/
+// schwarz.cpp:88-140 without the coarse correction and the L1 smoother): a local solver,
+// generated from the square local block of the distributed matrix, applied to the local rows.
+template <typename V, typename I>
+class Schwarz : public LinOp {
+public:
+    struct Factory : LinOpFactory {
+        std::shared_ptr<const LinOpFactory> local_solver_;
+        std::shared_ptr<const LinOp> generated_local_solver_;
+        std::shared_ptr<const Executor> exec_;
+        Factory& with_local_solver(std::shared_ptr<const LinOpFactory> f)
+        {
+            local_solver_ = std::move(f);
+            return *this;
+        }
+        Factory& with_generated_local_solver(std::shared_ptr<const LinOp> s)
+        {
+            generated_local_solver_ = std::move(s);
+            return *this;
+        }
+        std::shared_ptr<const LinOpFactory> on(std::shared_ptr<const Executor> exec) const
+        {
+            auto f = std::make_shared<Factory>(*this);
+            f->exec_ = exec;
+            return f;
+        }
+        std::unique_ptr<LinOp> generate(std::shared_ptr<const LinOp> op) const override
+        {
+            return std::unique_ptr<LinOp>(new Schwarz(exec_ ? exec_ : op->get_executor(), *this, op));
+        }
+    };
+    static Factory build() { return Factory{}; }
+    std::shared_ptr<const LinOp> get_local_solver() const { return local_solver_; }
+    bool apply_uses_initial_guess() const override { return local_solver_->apply_uses_initial_guess(); }
+
+protected:
+    Schwarz(std::shared_ptr<const Executor> exec, const Factory& f, std::shared_ptr<const LinOp> op)
+        : LinOp(exec, dim2{op->get_size().rows, op->get_size().rows})
+    {
+        if (f.generated_local_solver_) {
+            local_solver_ = f.generated_local_solver_;
+        } else {
+            if (!f.local_solver_) throw NotSupported("Schwarz: a local solver (factory) is required");
+            auto dist = dynamic_cast<const Matrix<V, I>*>(op.get());
+            if (!dist) throw NotSupported("Schwarz: the operator is not a distributed::Matrix");
+            local_solver_ = f.local_solver_->generate(dist->get_local_diagonal_block());
+        }
+        if (local_solver_->get_size().rows != size_.rows)
+            throw DimensionMismatch("Schwarz: local solver and local rows differ in size");
+    }
+    // the local rows WITHOUT the sum over the ranks (gko::detail::get_local): a local solver's dots
+    // and norms are local
+    static std::unique_ptr<matrix::Dense<V>> local_view(const LinOp* v)
+    {
+        auto d = as<matrix::Dense<V>>(v);
+        return matrix::Dense<V>::create_view(d->get_executor(), d->get_size(),
+                                             const_cast<V*>(d->get_const_values()), d->get_stride());
+    }
+    void apply_impl(const LinOp* b, LinOp* x) const override
+    {
+        auto lb = local_view(b), lx = local_view(x);
+        local_solver_->apply(lb.get(), lx.get());
+    }
+    void apply_impl(const LinOp* alpha, const LinOp* b, const LinOp* beta, LinOp* x) const override
+    {
+        auto lb = local_view(b), lx = local_view(x);
+        local_solver_->apply(alpha, lb.get(), beta, lx.get());
+    }
+
+private:
+    std::shared_ptr<const LinOp> local_solver_;
+};
+
+}  // namespace preconditioner
 
 // Distributed CG with the fused device-resident iteration: per iteration
 //   step_p | halo exchange of p | spmv_dot | all-reduce(pq) | step_xr | all-reduce(rho, rr) | finish

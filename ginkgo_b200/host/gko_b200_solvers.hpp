@@ -440,6 +440,9 @@ namespace gmres {
 enum class ortho_method { mgs, cgs, cgs2 };
 }
 
+// include/ginkgo/core/solver/solver_base.hpp:33-46: what a solver assumes about the x it is given
+enum class initial_guess_mode { zero, rhs, provided };
+
 template <typename V>
 class SolverBase : public LinOp {
 public:
@@ -1313,9 +1316,17 @@ class Ir : public SolverBase<V> {
 public:
     struct Factory : SolverFactoryBase<Factory> {
         V relaxation_factor_ = V(1);
+        initial_guess_mode default_initial_guess_ = initial_guess_mode::provided;
         Factory& with_relaxation_factor(V w)
         {
             relaxation_factor_ = w;
+            return *this;
+        }
+        // zero / rhs: x is overwritten before the first iteration (needed when the Ir is itself a
+        // preconditioner or smoother: a fixed number of sweeps from a fixed start is a fixed operator)
+        Factory& with_default_initial_guess(initial_guess_mode m)
+        {
+            default_initial_guess_ = m;
             return *this;
         }
         // the reference's name for the inner-solver slot
@@ -1335,7 +1346,8 @@ public:
 
 protected:
     Ir(std::shared_ptr<const Executor> exec, const Factory& f, std::shared_ptr<const LinOp> op)
-        : Base(exec, f, op), relaxation_(matrix::scalar<V>(f.relaxation_factor_, exec))
+        : Base(exec, f, op), relaxation_(matrix::scalar<V>(f.relaxation_factor_, exec)),
+          guess_(f.default_initial_guess_)
     {}
     using Base::apply_impl;
     void apply_impl(const LinOp* lb, LinOp* lx) const override
@@ -1348,9 +1360,14 @@ protected:
         std::unique_ptr<Dense> inner_solution;
         array<uint8> stop_status(exec, sz.cols);
         GKOB_CALL(b200_ir_initialize(exec->ctx(), sz.cols, stop_status.get_data()));
-        residual->copy_from(b);
-        this->system_matrix_->apply(this->neg_one_.get(), x, this->one_.get(), residual.get());
-        const Dense* residual_ptr = residual.get();
+        // core/solver/ir.cpp:177-217: prepare the guess; from zero the first residual is b itself
+        if (guess_ == initial_guess_mode::zero) x->fill(V(0));
+        if (guess_ == initial_guess_mode::rhs) x->copy_from(b);
+        if (guess_ != initial_guess_mode::zero) {
+            residual->copy_from(b);
+            this->system_matrix_->apply(this->neg_one_.get(), x, this->one_.get(), residual.get());
+        }
+        const Dense* residual_ptr = guess_ == initial_guess_mode::zero ? b : residual.get();
         stop::CriterionArgs args{this->system_matrix_, b, x, residual_ptr};
         auto crit = stop::combine_and_generate(this->criteria_, exec, args);
         auto inner = this->preconditioner_.get();
@@ -1373,6 +1390,7 @@ protected:
 
 private:
     std::unique_ptr<Dense> relaxation_;
+    initial_guess_mode guess_;
 };
 
 // ---------------------------------------------------------------------------------------------
