@@ -1,8 +1,16 @@
-// gko_b200_dist.hpp -- multi-GPU host layer: the NCCL counterpart of the reference's
-// experimental::distributed::{Matrix, Vector} + distributed CG on this path
-// (core/distributed/matrix.cpp:450-509, core/distributed/vector.cpp:510-534,
-// core/solver/cg.cpp driven through precision_dispatch_real_complex_distributed).
-// One process per GPU; rank p owns rows [offsets[p], offsets[p+1]).
+// gko_b200_dist.hpp -- multi-GPU host layer: the NCCL / peer-memory counterpart of the reference's
+// experimental::distributed classes on this path, one process per GPU:
+//   communicator                      experimental::mpi::communicator (include/ginkgo/core/base/mpi.hpp)
+//   Partition<L, G>, index_map<L, G>  include/ginkgo/core/distributed/{partition,index_map}.hpp
+//   Vector<V>                         include/ginkgo/core/distributed/vector.hpp (core/distributed/vector.cpp:480-534)
+//   Matrix<V, I>                      core/distributed/matrix.cpp:300-380 (read_distributed), :450-509 (apply);
+//                                     a LinOp over the local rows, so every solver of gko_b200_solvers.hpp runs on it
+//   preconditioner::Schwarz<V, I>     core/distributed/preconditioner/schwarz.cpp (one level)
+//   Cg<V, I>                          the fused device-resident CG iteration with the exchange and the
+//                                     all-reduces inside the CUDA graph (core/solver/cg.cpp driven through
+//                                     precision_dispatch_real_complex_distributed)
+// Rank p owns the rows of part p of the row partition; its local block has the columns numbered
+// [owned columns | ghost columns ordered by (owner, global index)].
 #pragma once
 
 #include <algorithm>
