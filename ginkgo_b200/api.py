@@ -224,6 +224,7 @@ def _configure_host_lib(h):
     h.gkob_num_rows.restype, h.gkob_num_rows.argtypes = ll, [vp]
     h.gkob_num_cols.restype, h.gkob_num_cols.argtypes = ll, [vp]
     h.gkob_solver_params.restype, h.gkob_solver_params.argtypes = None, [d, d, d]
+    h.gkob_solver_guess.restype, h.gkob_solver_guess.argtypes = None, [i]
     h.gkob_csr_convert.restype = vp
     h.gkob_csr_convert.argtypes = [vp, ctypes.c_char_p, ll, ll, d, d]
     h.gkob_csr_sort_by_column_index.restype = i
@@ -428,9 +429,11 @@ class HostSolver:
 
     def __init__(self, exec_, kind, A, precond_max_bs=0, block_ptrs=None, max_iters=None,
                  res_kind=1, baseline=0, reduction=1e-8, iter_first=True, krylov_dim=30, ortho=0,
-                 fused=True, check_every=16, relaxation_factor=1.0, foci=(0.0, 1.0)):
+                 fused=True, check_every=16, relaxation_factor=1.0, foci=(0.0, 1.0), initial_guess="provided"):
         self.vt = A.vt
         _host().gkob_solver_params(float(relaxation_factor), float(foci[0]), float(foci[1]))
+        # "ir" only: solver::initial_guess_mode of with_default_initial_guess
+        _host().gkob_solver_guess({"provided": 0, "zero": 1, "rhs": 2}[initial_guess])
         bp = None
         nb = 0
         if block_ptrs is not None:

@@ -36,6 +36,7 @@ int guarded(F f)
 
 // extra parameters of solver kinds 5 (Ir) and 6 (Chebyshev), set by gkob_solver_params
 double g_relaxation = 1.0, g_foci_lo = 0.0, g_foci_hi = 1.0;
+int g_ir_guess = 0;  // kind 5: 0 provided, 1 zero, 2 rhs (gkob_solver_guess)
 
 template <typename V>
 std::unique_ptr<LinOp> make_solver(std::shared_ptr<Executor> exec, int kind,
@@ -119,6 +120,9 @@ std::unique_ptr<LinOp> make_solver(std::shared_ptr<Executor> exec, int kind,
     if (kind == 5) {
         auto f = solver::Ir<V>::build();
         f.with_criteria(crit).with_relaxation_factor((V)g_relaxation);
+        f.with_default_initial_guess(g_ir_guess == 1   ? solver::initial_guess_mode::zero
+                                     : g_ir_guess == 2 ? solver::initial_guess_mode::rhs
+                                                       : solver::initial_guess_mode::provided);
         if (pre) f.with_solver(pre);
         return f.on(exec)->generate(A);
     }
@@ -407,6 +411,7 @@ long long gkob_num_cols(void* op) { return (long long)static_cast<Handle*>(op)->
 
 // parameters for the next gkob_solver_create_* of kind 5 (Ir: relaxation_factor) or 6
 // (Chebyshev: foci)
+void gkob_solver_guess(int mode) { g_ir_guess = mode; }
 void gkob_solver_params(double relaxation_factor, double foci_lo, double foci_hi)
 {
     g_relaxation = relaxation_factor;

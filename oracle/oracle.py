@@ -23,7 +23,7 @@ class SolverCfg(ctypes.Structure):
         ("reduction_factor", ctypes.c_double), ("iter_first", ctypes.c_int32),
         ("krylov_dim", ctypes.c_int32), ("ortho", ctypes.c_int32),
         ("relaxation_factor", ctypes.c_double), ("foci_lo", ctypes.c_double),
-        ("foci_hi", ctypes.c_double),
+        ("foci_hi", ctypes.c_double), ("initial_guess", ctypes.c_int32),
     ]
 
 

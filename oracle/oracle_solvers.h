@@ -27,6 +27,7 @@ typedef struct {
     int32_t ortho;          /* GMRES: 0 mgs, 1 cgs, 2 cgs2 */
     double relaxation_factor; /* IR */
     double foci_lo, foci_hi;  /* Chebyshev */
+    int32_t initial_guess;    /* IR default_initial_guess: 0 provided, 1 zero, 2 rhs */
 } orc_solver_cfg;
 #endif
 
@@ -377,9 +378,14 @@ int64_t FN(ir_solve)(int64_t n, int64_t cols, const int32_t* rp, const int32_t* 
     uint8_t* stop = malloc(cols);
     const V one = 1, neg_one = -1, relax = (V)cfg->relaxation_factor;
     orc_ir_initialize(cols, stop);
-    memcpy(residual, b, nb);
-    FN(s_apply_A)(&s, &neg_one, x, &one, residual);
-    const V* residual_ptr = residual;
+    /* core/solver/ir.cpp:177-217: zero / rhs guesses overwrite x; from zero the first residual is b */
+    if (cfg->initial_guess == 1) memset(x, 0, nb);
+    if (cfg->initial_guess == 2) memcpy(x, b, nb);
+    if (cfg->initial_guess != 1) {
+        memcpy(residual, b, nb);
+        FN(s_apply_A)(&s, &neg_one, x, &one, residual);
+    }
+    const V* residual_ptr = cfg->initial_guess == 1 ? b : residual;
     FN(s_criterion_generate)(&s, b, residual_ptr);
     int64_t iter = -1;
     while (1) {
@@ -387,6 +393,7 @@ int64_t FN(ir_solve)(int64_t n, int64_t cols, const int32_t* rp, const int32_t* 
         if (FN(s_update_residual)(&s, iter, b, x, residual, &residual_ptr, stop)) break;
         FN(s_apply_M_adv)(&s, &relax, residual_ptr, &one, x);
     }
+    if (cfg->initial_guess == 1 && iter == 0) memcpy(residual, b, nb); /* for the norm reported below */
     if (stop_out) memcpy(stop_out, stop, cols);
     if (resnorm_out) FN(dense_compute_norm2)(n, cols, residual, cols, resnorm_out);
     free(residual); free(s.starting_tau); free(s.u_tau); free(stop);

@@ -73,7 +73,7 @@ def spmv(fmt, rp, ci, va, x, n_cols, alpha=None, beta=None, y=None, exec_kind=0,
 
 def solve(kind, rp, ci, va, b, x0, precond_max_bs=0, block_ptrs=None, max_iters=-1, res_kind=1,
           baseline=0, reduction=1e-8, iter_first=1, krylov_dim=30, ortho=0, exec_kind=0,
-          relaxation_factor=1.0, foci=(0.0, 1.0)):
+          relaxation_factor=1.0, foci=(0.0, 1.0), initial_guess="provided"):
     n = len(rp) - 1
     b2 = np.ascontiguousarray(b).reshape(n, -1)
     x = np.ascontiguousarray(x0).reshape(n, -1).copy()
@@ -83,6 +83,8 @@ def solve(kind, rp, ci, va, b, x0, precond_max_bs=0, block_ptrs=None, max_iters=
     resn = np.zeros(nrhs, va.dtype)
     nb = 0 if block_ptrs is None else len(block_ptrs) - 1
     lib().refshim_solve_params(float(relaxation_factor), float(foci[0]), float(foci[1]))
+    if hasattr(lib(), "refshim_solve_guess"):
+        lib().refshim_solve_guess({"provided": 0, "zero": 1, "rhs": 2}[initial_guess])
     st = lib().refshim_solve(exec_kind, {"cg": 0, "bicgstab": 1, "gmres": 2, "fcg": 3, "cgs": 4, "ir": 5,
                                          "chebyshev": 6, "pipe_cg": 7, "gcr": 8, "minres": 9, "bicg": 10}[kind], _vt(va), n,
                              len(va), _p(rp), _p(ci), _p(va), _p(b2), _p(x), nrhs, precond_max_bs,

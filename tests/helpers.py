@@ -226,6 +226,7 @@ def orc_solve(kind, vt, rp, ci, va, b, x0, precond=0, jac=None, **kw):
     cfg.ortho = kw.get("ortho", 0)
     cfg.relaxation_factor = kw.get("relaxation_factor", 1.0)
     cfg.foci_lo, cfg.foci_hi = kw.get("foci", (0.0, 1.0))
+    cfg.initial_guess = {"provided": 0, "zero": 1, "rhs": 2}[kw.get("initial_guess", "provided")]
     keep = []
     if jac is not None:
         keep.append(jac["blocks"])

@@ -807,3 +807,33 @@ def test_host_schwarz_needs_the_local_block(host):
     A2 = api.DistMatrix.read(host, part, (n, n), rows, ci.astype(np.int64), va, keep_local_block=True)
     it, st = A2.solve("cg", b, x, n, precond_max_bs=1, max_iters=100, reduction=1e-10, schwarz=-1)
     assert 0 < it < 100
+
+
+@pytest.mark.parametrize("guess", ["zero", "rhs", "provided"])
+@pytest.mark.parametrize("precond", [0, 1])
+def test_host_ir_default_initial_guess(host, guess, precond):
+    """Ir::with_default_initial_guess: reference == oracle == C++ host loop, bit for bit; x arrives
+    filled with garbage, which only `provided` may look at"""
+    from oracle import ref
+    rp, ci, va = W.laplace(10, 2)
+    n = len(rp) - 1
+    rng = np.random.default_rng(3)
+    b = rng.uniform(-1, 1, (n, 2))
+    x0 = rng.uniform(-1, 1, (n, 2))
+    jac = None
+    if precond:
+        if not ref.available():
+            pytest.skip("needs oracle/_ref")
+        jac = ref.jacobi_generate(rp, ci, va, 1, None)
+    kw = dict(max_iters=40, reduction=1e-12, relaxation_factor=0.2 if not precond else 0.9, initial_guess=guess)
+    xo, ito, so = H.orc_solve("ir", "f64", rp, ci, va, b, x0, precond, jac, **kw)
+    xh, ith, sh = host_solve(host, "ir", "f64", rp, ci, va, b, x0, precond, None, **kw)
+    assert ith == ito and sh == so[0] and np.array_equal(xh, xo)
+    if ref.available() and hasattr(ref.lib(), "refshim_solve_guess"):
+        xr, itr, _, _ = ref.solve("ir", rp, ci, va, b, x0, precond, None, max_iters=40, reduction=1e-12,
+                                  relaxation_factor=kw["relaxation_factor"], initial_guess=guess)
+        assert itr == ito and np.array_equal(xr, xo)
+    if guess == "zero":  # the same as a provided zero guess
+        xz, itz, _ = H.orc_solve("ir", "f64", rp, ci, va, b, np.zeros_like(x0), precond, jac,
+                                 **dict(kw, initial_guess="provided"))
+        assert itz == ito and np.array_equal(xz, xo)
