@@ -743,6 +743,17 @@ b200_status b200_halo_enable_p2p(b200_ctx* ctx, b200_comm* comm, b200_halo* h)
             b200::set_error("halo: send and receive counts of the ranks do not match");
             return B200_ERR_INVALID;
         }
+    // Two landing slots per halo are safe only when every exchanging pair of ranks sends in BOTH
+    // directions (a rank can then start epoch e+2 only after its peers finished reading epoch e).
+    // A one-directional coupling stays on the NCCL exchange; S is the same on every rank, so all
+    // ranks take this exit together, before the collective window set-up.
+    for (int q = 0; q < n; ++q)
+        for (int p = q + 1; p < n; ++p)
+            if ((S[(size_t)q * n + p] > 0) != (S[(size_t)p * n + q] > 0)) {
+                b200::set_error("halo: ranks %d and %d exchange in one direction only; keeping the NCCL "
+                                "exchange for this matrix", q, p);
+                return B200_ERR_COMM;
+            }
     const size_t flag_bytes = round256(2 * (size_t)n * sizeof(uint64_t));
     auto ghosts_of = [&](int p) {
         int64_t g = 0;

@@ -666,9 +666,8 @@ int64_t b200_halo_num_send(const b200_halo* halo);
  * Lifetime: the context outlives the communicator, the communicator outlives its halos
  * (exported blocks are only freed in b200_comm_destroy, after a barrier).
  * Slot reuse (two landing slots per halo) is safe when every exchanging pair of ranks sends in
- * both directions or a collective separates consecutive exchanges (true for symmetric patterns
- * and inside the solvers); a purely one-directional coupling in a bare loop of exchanges needs
- * the NCCL path (B200_P2P=0) for now. */
+ * both directions; b200_halo_enable_p2p checks the all-gathered counts and returns B200_ERR_COMM
+ * (on every rank alike, the halo stays on NCCL) when some pair is coupled in one direction only. */
 b200_status b200_comm_enable_p2p(b200_ctx* ctx, b200_comm* comm);
 b200_status b200_halo_enable_p2p(b200_ctx* ctx, b200_comm* comm, b200_halo* halo);
 int32_t b200_comm_p2p_enabled(const b200_comm* comm);
