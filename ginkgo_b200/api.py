@@ -584,6 +584,8 @@ class DistMatrix:
         h.gkob_dist_cg_apply_f64.argtypes = [vp, vp, vp, ctypes.POINTER(ll),
                                              ctypes.POINTER(ctypes.c_ubyte)]
         h.gkob_dist_destroy.argtypes = [vp]
+        h.gkob_dist_vector_read_f64.restype = i
+        h.gkob_dist_vector_read_f64.argtypes = [vp, vp, ll, ll, ll, vp, vp, vp, vp]
         h.gkob_dist_solve_f64.restype = i
         h.gkob_dist_solve_f64.argtypes = [vp, i, i, i, vp, vp, ll, ll, i, i, ctypes.c_double, i, i, i,
                                           ctypes.POINTER(ll), ctypes.POINTER(ctypes.c_ubyte)]

@@ -276,6 +276,28 @@ b200_status kept_fill(b200_ctx* ctx, int64_t nnz, const G* row_idxs, const G* co
     });
 }
 
+// distributed_vector::build_local (reference/distributed/vector_kernels.cpp:15-40): scatter the
+// entries of the owned rows into the pre-zeroed row-major local block.  Like the reference's device
+// backends this is a plain scatter: (row, column) pairs must be unique (sum_duplicates first).
+template <typename V, typename L, typename G>
+b200_status vector_build_local(b200_ctx* ctx, int64_t nnz, const G* row_idxs, const G* col_idxs, const V* values,
+                               int64_t num_ranges, const G* bounds, const int32_t* part_ids, const L* starting,
+                               int32_t local_part, V* local_values, int64_t local_stride)
+{
+    B200_REQUIRE(ctx, "null argument");
+    B200_REQUIRE(nnz >= 0 && num_ranges >= 0 && local_stride >= 0, "negative size");
+    B200_REQUIRE(nnz == 0 || (row_idxs && col_idxs && values && bounds && part_ids && starting && local_values &&
+                              num_ranges > 0),
+                 "null argument");
+    return launch_ew(ctx, nnz, 1, [=] __device__(int64_t i, int64_t) {
+        const G row = row_idxs[i];
+        const int64_t r = find_range(bounds, num_ranges, row);
+        if (part_ids[r] != local_part) return;
+        const int64_t lrow = (int64_t)((L)(row - bounds[r]) + starting[r]);
+        local_values[lrow * local_stride + (int64_t)col_idxs[i]] = values[i];
+    });
+}
+
 // --------------------------------------------------------------------------------- index map
 inline int64_t num_words(int64_t global_size) { return (global_size + 31) / 32; }
 
@@ -513,6 +535,16 @@ B200_DEF_DIST_LG(i64, int64_t, i64, int64_t)
             ctx, nnz, row_idxs, col_idxs, values, row_num_ranges, row_bounds, row_starting,              \
             col_num_ranges, col_bounds, col_starting, cls, local_rank, non_local_rank, local_rows,       \
             local_cols, local_vals, non_local_rows, non_local_cols, non_local_vals);                     \
+    }                                                                                                    \
+    b200_status b200_dist_vector_build_local_##V##_##L##_##G(                                            \
+        b200_ctx* ctx, int64_t nnz, const GT* row_idxs, const GT* col_idxs, const VT* values,            \
+        int64_t num_ranges, const GT* bounds, const int32_t* part_ids, const LT* starting,               \
+        int32_t local_part, VT* local_values, int64_t local_stride)                                      \
+    {                                                                                                    \
+        return b200::dist_assembly::vector_build_local<VT, LT, GT>(ctx, nnz, row_idxs, col_idxs, values, \
+                                                                   num_ranges, bounds, part_ids,         \
+                                                                   starting, local_part, local_values,   \
+                                                                   local_stride);                        \
     }                                                                                                    \
     b200_status b200_dist_kept_fill_##V##_##L##_##G(                                                     \
         b200_ctx* ctx, int64_t nnz, const GT* row_idxs, const GT* col_idxs, const VT* values,            \

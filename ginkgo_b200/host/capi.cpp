@@ -838,6 +838,22 @@ int gkob_dist_matrix_sizes(void* dist, long long* out, long long* ghost_globals)
     });
 }
 
+// distributed::read_distributed_vector on the communicator of `dist`: the local rows (row-major,
+// n_local x ncols) are copied to out_host
+int gkob_dist_vector_read_f64(void* dist, void* row_part, long long nrows, long long ncols, long long nnz,
+                              const long long* rows, const long long* cols, const double* vals, double* out_host)
+{
+    return guarded([&] {
+        auto h = static_cast<DistHandle*>(dist);
+        auto v = distributed::read_distributed_vector<double, int32, int64>(
+            h->exec, h->comm, triplets(nrows, ncols, nnz, rows, cols, vals),
+            static_cast<PartHandle*>(row_part)->part);
+        const auto host = v->to_host();
+        std::copy(host.begin(), host.end(), out_host);
+    });
+}
+
+
 
 // bit 0: all-reduces run on peer memory, bit 1: the halo exchange does
 int gkob_dist_p2p(void* dist)

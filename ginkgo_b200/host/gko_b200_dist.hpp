@@ -187,6 +187,7 @@ GKOB_LG(int64, i64, int64, i64)
     struct vlgabi<V, L, G> {                                                                          \
         static constexpr auto separate_fill = b200_dist_separate_fill_##VS##_##LS##_##GS;             \
         static constexpr auto kept_fill = b200_dist_kept_fill_##VS##_##LS##_##GS;                     \
+        static constexpr auto vector_build_local = b200_dist_vector_build_local_##VS##_##LS##_##GS;   \
     };
 GKOB_VLG(double, f64, int32, i32, int32, i32)
 GKOB_VLG(double, f64, int32, i32, int64, i64)
@@ -472,6 +473,38 @@ local_assembly<V, I, G> assemble_local(std::shared_ptr<const Executor> exec, con
                                                    std::move(lv), std::move(lc), std::move(lptrs));
     }
     return out;
+}
+
+// experimental::distributed::Vector::read_distributed (core/distributed/vector.cpp:250-275): the
+// rows of `partition`'s part comm->rank() of a global multi-vector given as (unique) triplets
+template <typename V, typename L, typename G>
+std::unique_ptr<Vector<V>> read_distributed_vector(std::shared_ptr<const Executor> exec,
+                                                   std::shared_ptr<communicator> comm,
+                                                   const matrix_data<V, G>& data,
+                                                   std::shared_ptr<const Partition<L, G>> partition)
+{
+    if (data.size.rows != partition->get_size())
+        throw DimensionMismatch("read_distributed: the partition must cover the rows of the vector");
+    if (partition->get_num_parts() != comm->size())
+        throw DimensionMismatch("read_distributed: one part per rank of the communicator");
+    const size_type nnz = data.nonzeros.size(), cols = data.size.cols;
+    std::vector<G> hr(nnz), hc(nnz);
+    std::vector<V> hv(nnz);
+    for (size_type i = 0; i < nnz; ++i) {
+        hr[i] = data.nonzeros[i].row;
+        hc[i] = data.nonzeros[i].column;
+        hv[i] = data.nonzeros[i].value;
+    }
+    array<G> rows(exec, hr), cs(exec, hc);
+    array<V> vals(exec, hv);
+    const size_type n_local = (size_type)partition->get_part_size(comm->rank());
+    auto v = Vector<V>::create(exec, comm, data.size, dim2{n_local, cols});
+    v->fill(V(0));
+    GKOB_CALL((vlgabi<V, L, G>::vector_build_local(
+        exec->ctx(), (int64)nnz, rows.get_const_data(), cs.get_const_data(), vals.get_const_data(),
+        (int64)partition->get_num_ranges(), partition->get_range_bounds(), partition->get_part_ids(),
+        partition->get_range_starting_indices(), comm->rank(), v->get_values(), (int64)v->get_stride())));
+    return v;
 }
 
 // S[q * P + p] = entries rank q receives from rank p.  What `rank` sends: to peer q the

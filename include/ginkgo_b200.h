@@ -829,7 +829,14 @@ B200_DECL_DIST_LG(i64, int64_t, i64, int64_t)
     b200_status b200_dist_kept_fill_##V##_##L##_##G(                                                     \
         b200_ctx* ctx, int64_t nnz, const GT* row_idxs, const GT* col_idxs, const VT* values,            \
         int64_t row_num_ranges, const GT* row_bounds, const LT* row_starting, const uint8_t* cls,        \
-        const int64_t* local_rank, const int64_t* non_local_rank, LT* rows, GT* cols, VT* vals);
+        const int64_t* local_rank, const int64_t* non_local_rank, LT* rows, GT* cols, VT* vals);                                                                                                         \
+    /* distributed_vector::build_local (reference/distributed/vector_kernels.cpp:15-40): scatter */     \
+    /* the entries of local_part's rows into the pre-zeroed row-major local block; unique (row, */      \
+    /* column) pairs, as for the reference's device backends */                                         \
+    b200_status b200_dist_vector_build_local_##V##_##L##_##G(                                            \
+        b200_ctx* ctx, int64_t nnz, const GT* row_idxs, const GT* col_idxs, const VT* values,            \
+        int64_t num_ranges, const GT* bounds, const int32_t* part_ids, const LT* starting,               \
+        int32_t local_part, VT* local_values, int64_t local_stride);
 #define B200_DECL_DIST_VLG_ALL(V, VT)                     \
     B200_DECL_DIST_VLG(V, VT, i32, int32_t, i32, int32_t) \
     B200_DECL_DIST_VLG(V, VT, i32, int32_t, i64, int64_t) \

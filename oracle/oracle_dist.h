@@ -350,6 +350,21 @@ void ORC_VLGN(orc_dist_kept_fill)(int64_t nnz, const G* row_idxs, const G* col_i
         vals[k] = values[i];
     }
 }
+
+/* distributed_vector::build_local (reference/distributed/vector_kernels.cpp:15-40): the entries
+ * of the owned rows into the (pre-zeroed) row-major local block; later duplicates win */
+void ORC_VLGN(orc_dist_vector_build_local)(int64_t nnz, const G* row_idxs, const G* col_idxs, const V* values,
+                                           int64_t num_ranges, const G* bounds, const int32_t* part_ids,
+                                           const L* starting, int32_t local_part, V* local_values,
+                                           int64_t local_stride)
+{
+    for (int64_t i = 0; i < nnz; ++i) {
+        const int64_t r = ORC_GN(orc_find_range)(bounds, num_ranges, row_idxs[i]);
+        if (part_ids[r] != local_part) continue;
+        const int64_t lrow = (int64_t)((L)(row_idxs[i] - bounds[r]) + starting[r]);
+        local_values[lrow * local_stride + (int64_t)col_idxs[i]] = values[i];
+    }
+}
 #undef ORC_VLGN
 #undef ORC_VLGN2
 #undef ORC_CAT7

@@ -249,3 +249,17 @@ def index_map(mapping, num_parts, rank, conns, index_space=0, query=None):
     a, b = int(meta[0]), int(meta[1])
     return dict(remote_global=rg[:a].copy(), remote_local=rl[:a].copy(), target_ids=ids[:b].copy(),
                 remote_sizes=sizes[:b].copy(), query_local=ql[:k].copy())
+
+
+def vector_build_local(shape, rows, cols, vals, mapping, num_parts, local_part):
+    """distributed_vector::build_local into a zeroed n_local x ncols block"""
+    rows = np.ascontiguousarray(rows, np.int64)
+    cols = np.ascontiguousarray(cols, np.int64)
+    vals = np.ascontiguousarray(vals, np.float64)
+    mp = np.ascontiguousarray(mapping, np.int32)
+    n_local = int((mp == local_part).sum())
+    local = np.zeros((max(n_local, 1), shape[1]))
+    st = lib().refshim_vector_build_local(shape[0], shape[1], len(rows), _p(rows), _p(cols), _p(vals), _p(mp),
+                                          num_parts, local_part, n_local, _p(local))
+    assert st == 0, st
+    return local[:n_local]

@@ -154,3 +154,17 @@ class IndexMap:
            _pad(part.part_ids), _pad(part.starting_indices), self.bitmap, self.word_rank, self.range_offsets,
            self.rank, local_size, index_space, len(g), _pad(g), out)
         return out[:len(g)]
+
+
+def vector_build_local(be, part, rows, cols, vals, ncols, local_part, vt="f64"):
+    """distributed_vector::build_local -> the n_local x ncols block of part local_part"""
+    lt, gt = part.lt, part.gt
+    rows = np.ascontiguousarray(rows, NP[gt])
+    cols = np.ascontiguousarray(cols, NP[gt])
+    vals = np.ascontiguousarray(vals, NP[vt])
+    n_local = int(part.part_sizes[local_part])
+    local = np.zeros(max(n_local * ncols, 1), NP[vt])
+    be("dist_vector_build_local_%s_%s_%s" % (vt, lt, gt), len(rows), _pad(rows), _pad(cols), _pad(vals),
+       part.num_ranges, part.range_bounds, _pad(part.part_ids), _pad(part.starting_indices), local_part, local,
+       ncols)
+    return local[:n_local * ncols].reshape(n_local, ncols)

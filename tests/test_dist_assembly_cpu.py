@@ -327,3 +327,28 @@ def test_kernel_source_matches_oracle(orc, ksrc, lt, gt, vt):
               "remote_part_ids"):
         eq(getattr(i0, k), getattr(i1, k))
     eq(c0, c1)
+
+
+@pytest.mark.parametrize("lt,gt", TYPES)
+@pytest.mark.parametrize("seed", range(3))
+def test_vector_build_local_matches_reference(be, lt, gt, seed):
+    """distributed_vector::build_local (unique (row, column) pairs)"""
+    rng = np.random.default_rng(200 + seed)
+    num_parts, nrows, ncols = int(rng.integers(1, 6)), int(rng.integers(5, 120)), int(rng.integers(1, 5))
+    mapping = random_mapping(rng, nrows, num_parts, 6)
+    order = np.unique(rng.integers(0, nrows * ncols, int(rng.integers(1, 300))))
+    rows, cols, vals = order // ncols, order % ncols, rng.standard_normal(len(order))
+    part = D.partition_from_mapping(be, mapping, num_parts, lt, gt)
+    for p in range(num_parts):
+        got = D.vector_build_local(be, part, rows, cols, vals, ncols, p)
+        want = np.zeros((int((mapping == p).sum()), ncols))
+        own = np.nonzero(mapping == p)[0]
+        local_of = {g: i for i, g in enumerate(own)}  # mapping-built partition: local order = global order
+        for r, c, v in zip(rows, cols, vals):
+            if mapping[r] == p:
+                want[local_of[r], c] = v
+        eq(got, want)
+        if (lt, gt) == ("i32", "i64"):
+            ref = ref_or_skip()
+            if hasattr(ref.lib(), "refshim_vector_build_local"):
+                eq(got, ref.vector_build_local((nrows, ncols), rows, cols, vals, mapping, num_parts, p))

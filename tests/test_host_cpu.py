@@ -568,6 +568,17 @@ def test_host_read_distributed_multi_rank_in_threads(host, world, seed):
             for _ in range(3):  # repeated exchanges
                 x_ext[n_local:] = -1
                 api._hcheck(h.gkob_dist_spmv_f64(d, x_ext.ctypes.data, y.ctypes.data))
+            # distributed::read_distributed_vector of a 2-column global vector (every 3rd row set)
+            vr = np.arange(0, n, 3, dtype=np.int64)
+            vrows, vcols = np.repeat(vr, 2), np.tile(np.array([0, 1], np.int64), len(vr))
+            vvals = (vrows * 10 + vcols).astype(np.float64)
+            vout = np.zeros(max(n_local, 1) * 2)
+            api._hcheck(h.gkob_dist_vector_read_f64(d, part.h, n, 2, len(vvals), vrows.ctypes.data,
+                                                    vcols.ctypes.data, vvals.ctypes.data, vout.ctypes.data))
+            want_v = np.zeros((n_local, 2))
+            sel = owned % 3 == 0
+            want_v[sel, 0], want_v[sel, 1] = owned[sel] * 10, owned[sel] * 10 + 1
+            assert np.array_equal(vout[:n_local * 2].reshape(n_local, 2), want_v)
             results[rank] = (owned, y.copy(), x_ext[n_local:].copy(), ghosts[:n_ghost].copy())
             h.gkob_dist_destroy(d)
         except BaseException as e:  # noqa: BLE001
