@@ -216,3 +216,18 @@ def test_distributed_solver_on_one_gpu(hexec, kind, pre):
     assert abs(it - it1) <= 1 and st == st1
     x = xl.cpu().numpy()
     assert np.linalg.norm(x - x1[:, 0]) <= 1e-9 * np.linalg.norm(x1)
+
+
+@pytest.mark.parametrize("lt,gt", TYPES)
+def test_vector_build_local_matches_oracle(orc, cuda, lt, gt):
+    rng = np.random.default_rng(33)
+    num_parts, nrows, ncols = 5, 20000, 3
+    mapping = random_mapping(rng, nrows, num_parts, 300)
+    order = np.unique(rng.integers(0, nrows * ncols, 30000))
+    rows, cols, vals = order // ncols, order % ncols, rng.standard_normal(len(order))
+    res = []
+    for be in (orc, cuda):
+        part = D.partition_from_mapping(be, mapping, num_parts, lt, gt)
+        res.append([D.vector_build_local(be, part, rows, cols, vals, ncols, p) for p in range(num_parts)])
+    for a, b in zip(*res):
+        eq(a, b)
