@@ -20,47 +20,14 @@ from tests.helpers import VT
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-class _CpuExec:
-    """stands where api.HostExecutor stands: a gkob executor handle on the mock"""
-
-    def __init__(self, lib):
-        self.h = lib.gkob_exec_create(0, None)
-        assert self.h
-        self.device = torch.device("cpu")
-        self.stream = None
-        self._lib = lib
-
-    def synchronize(self):
-        pass
+from tests.mock_build import CpuExec as _CpuExec  # noqa: E402
 
 
 @pytest.fixture(scope="module")
 def host(tmp_path_factory):
     from ginkgo_b200 import api
-    d = str(tmp_path_factory.mktemp("mock"))
-    inc = os.path.join(ROOT, "include")
-    gen = os.path.join(d, "mock_gen.c")
-    subprocess.run(["python", os.path.join(ROOT, "tests", "mock", "gen_mock.py"),
-                    os.path.join(inc, "ginkgo_b200.h"), os.path.join(ROOT, "oracle", "liboracle.so"),
-                    os.path.join(ROOT, "tests", "mock", "mock_base.c"), gen], check=True,
-                   capture_output=True)
-    objs = []
-    # B200_MOCK_SANITIZE=1: build the host layer + mock with ASan / UBSan; run pytest with
-    # LD_PRELOAD="$(g++ -print-file-name=libasan.so) $(g++ -print-file-name=libstdc++.so)"
-    san = (["-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-g"]
-           if os.environ.get("B200_MOCK_SANITIZE") == "1" else [])
-    for src in (os.path.join(ROOT, "tests", "mock", "mock_base.c"), gen):
-        o = os.path.join(d, os.path.basename(src) + ".o")
-        subprocess.run(["gcc", "-O1", "-fPIC", "-I" + inc, "-c", src, "-o", o] + san, check=True)
-        objs.append(o)
-    so = os.path.join(d, "libgko_b200_host_mock.so")
-    # one DSO, -Bsymbolic: the b200_* references of the host layer bind to the mock inside it,
-    # whatever else the process has loaded
-    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-Wl,-Bsymbolic", "-o", so,
-                    os.path.join(ROOT, "ginkgo_b200", "host", "capi.cpp")] + san + objs +
-                   ["-L" + os.path.join(ROOT, "oracle"), "-loracle",
-                    "-Wl,-rpath," + os.path.join(ROOT, "oracle")], check=True)
-    lib = api._configure_host_lib(ctypes.CDLL(so))
+    from tests.mock_build import build_mock_host
+    lib = build_mock_host(str(tmp_path_factory.mktemp("mock")))
     saved = api._HOST_LIB
     api._HOST_LIB = lib
     yield _CpuExec(lib)

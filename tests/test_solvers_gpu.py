@@ -3,6 +3,8 @@ drop-in kernels, and the fused device-resident CG) against the oracle's restatem
 reference's host loops (which is bit-identical to the real reference, see
 tests/test_oracle_vs_ref.py).  Bar: same iteration count +-2 and the
 final TRUE relative residual within 1e-10 (fp64) / 1e-5 (fp32) of the oracle's."""
+import os
+
 import numpy as np
 import pytest
 
@@ -14,8 +16,15 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")
-def hexec():
+def hexec(tmp_path_factory):
     from ginkgo_b200 import api
+    if os.environ.get("B200_TEST_SELFCHECK") == "1":
+        # harness self-check (no GPU): the C++ host layer on the host-memory mock stands in for
+        # the device, to debug the TEST BODIES themselves.  Never set on the GPU box.
+        from tests.mock_build import CpuExec, build_mock_host
+        lib = build_mock_host(str(tmp_path_factory.mktemp("mock_selfcheck")))
+        api._HOST_LIB = lib
+        return CpuExec(lib)
     return api.HostExecutor(0)
 
 
