@@ -54,3 +54,20 @@ def test_product_does_not_touch_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")) or f == "Makefile":
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "oracle" not in txt.lower().replace("test oracle", ""), os.path.join(dp, f)
+
+
+def test_host_library_exports_every_handle_the_python_face_binds():
+    # ginkgo_b200/lib/libgko_b200_host.so (the C++ host layer's C handles): api._configure_host_lib
+    # and DistMatrix._bind set argtypes on every gkob_* they use, which fails on a missing export
+    from ginkgo_b200 import api
+    h = api._host()
+    api.DistMatrix._bind(h)
+    out = subprocess.run(["nm", "-D", "--defined-only", os.path.join(os.path.dirname(_lib.LIB_PATH),
+                                                                     "libgko_b200_host.so")],
+                         capture_output=True, text=True, check=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T gkob_" in l}
+    assert len(exported) > 50
+    import re
+    used = set(re.findall(r"\bgkob_\w+", open(os.path.join(ROOT, "ginkgo_b200", "api.py")).read()))
+    used = {u for u in used if not u.endswith("_")}  # name prefixes completed with a value type
+    assert used <= exported, sorted(used - exported)
