@@ -10,7 +10,7 @@ import pytest
 from tests import helpers as H
 from tests.helpers import IT, R, VT, rel_err
 
-BACKENDS = ["oracle", pytest.param("cuda", marks=pytest.mark.gpu)]
+BACKENDS = ["oracle", pytest.param("cuda", marks=H.first_gpu_run_marks())]
 VTS = ["f64", "f32"]
 ITS = ["i32", "i64"]
 

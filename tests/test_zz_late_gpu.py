@@ -12,7 +12,7 @@ from tests.helpers import VT
 from tests.test_parity_gpu import VTS, _all_equal, both
 from tests.test_solvers_gpu import device_solve, hexec, ref_jacobi, true_rel_res  # noqa: F401
 
-pytestmark = pytest.mark.gpu
+pytestmark = H.first_gpu_run_marks()
 
 
 @pytest.mark.parametrize("vt", VTS)

@@ -8,11 +8,13 @@ The world_size > 1 exchange of read_distributed is exercised by scripts/dist_che
 import numpy as np
 import pytest
 
+from tests import helpers as H  # noqa: E402
+
 from tests import dist_driver as D
 from tests.test_dist_assembly_cpu import TYPES, eq, random_mapping
 from tests.test_solvers_gpu import hexec  # noqa: F401
 
-pytestmark = pytest.mark.gpu
+pytestmark = H.first_gpu_run_marks()
 
 
 def _compare(orc, cuda, lt, gt, vt, n, num_parts, nnz, run, seed, local_part):
