@@ -815,3 +815,99 @@ def test_host_ir_default_initial_guess(host, guess, precond):
         xz, itz, _ = H.orc_solve("ir", "f64", rp, ci, va, b, np.zeros_like(x0), precond, jac,
                                  **dict(kw, initial_guess="provided"))
         assert itz == ito and np.array_equal(xz, xo)
+
+
+# ------------------------------------------------------------ fused CG and the distributed fused CG
+@pytest.mark.parametrize("vt", ["f64", "f32"])
+@pytest.mark.parametrize("precond", [0, 1])
+@pytest.mark.parametrize("res_kind,baseline,iter_first", [(1, 0, True), (2, 1, False), (1, 2, True)])
+def test_host_fused_cg_path_on_the_mock(host, vt, precond, res_kind, baseline, iter_first):
+    """solver::Cg::try_fused (graph of check_every iterations, control block polling) with the
+    mock's sequential restatement of the fused kernels and its recorded graphs: same iteration
+    count as the kernel-by-kernel loop (+-1), same solution"""
+    from ginkgo_b200 import api
+    rp, ci, va = W.laplace(14, 2, vdtype=VT[vt])
+    n = len(rp) - 1
+    rng = np.random.default_rng(4)
+    b = rng.uniform(-1, 1, n).astype(VT[vt])
+    red = 1e-9 if vt == "f64" else 1e-4
+    if baseline == 2:
+        red *= 10  # absolute threshold
+    x1, it1, st1 = host_solve(host, "cg", vt, rp, ci, va, b.reshape(n, 1), np.zeros((n, 1), VT[vt]), precond, None,
+                              max_iters=300, reduction=red, res_kind=res_kind, baseline=baseline,
+                              iter_first=iter_first)
+    t = [_t(va), _t(ci), _t(rp)]
+    tb, tx = _t(b), torch.zeros(n, dtype=_t(va).dtype)
+    A = api.host_csr(host, (n, n), *t)
+    s = api.HostSolver(host, "cg", A, precond_max_bs=precond, max_iters=300, reduction=red, res_kind=res_kind,
+                       baseline=baseline, iter_first=iter_first, fused=True, check_every=7)
+    bd, xd = api.host_dense(host, tb), api.host_dense(host, tx)
+    s.apply(bd, xd)
+    assert s.used_fused
+    assert abs(s.num_iterations - it1) <= 1 and s.stop_status == st1
+    tol = 1e-10 if vt == "f64" else 1e-4
+    assert np.linalg.norm(tx.numpy() - x1[:, 0]) <= tol * 10 * np.linalg.norm(x1)
+    # a second apply replays the captured graph with a new right-hand side
+    tb2 = _t(rng.uniform(-1, 1, n).astype(VT[vt]))
+    tx.zero_()
+    bd2 = api.host_dense(host, tb2)
+    s.apply(bd2, xd)
+    x2, it2, _ = host_solve(host, "cg", vt, rp, ci, va, tb2.numpy().reshape(n, 1), np.zeros((n, 1), VT[vt]), precond,
+                            None, max_iters=300, reduction=red, res_kind=res_kind, baseline=baseline,
+                            iter_first=iter_first)
+    assert abs(s.num_iterations - it2) <= 1
+    assert np.linalg.norm(tx.numpy() - x2[:, 0]) <= tol * 10 * np.linalg.norm(x2)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("scalar_jacobi", [False, True])
+def test_host_distributed_fused_cg_in_threads(host, world, scalar_jacobi):
+    """distributed::Cg (the fused iteration with the halo exchange and the two all-reduces inside
+    the graph) on the torch-free set-up path, ranks as threads"""
+    import threading
+    from ginkgo_b200 import api
+    h = api._host()
+    api.DistMatrix._bind(h)
+    rp, ci, va = W.laplace(12, 2)
+    n = len(rp) - 1
+    rng = np.random.default_rng(21)
+    b = rng.uniform(-1, 1, n)
+    rows, cols = np.repeat(np.arange(n, dtype=np.int64), np.diff(rp)), ci.astype(np.int64)
+    x1, it1, st1 = host_solve(host, "cg", "f64", rp, ci, va, b.reshape(n, 1), np.zeros((n, 1)),
+                              1 if scalar_jacobi else 0, None, max_iters=300, reduction=1e-10)
+    idb = (ctypes.c_ubyte * 128)()
+    api._hcheck(h.gkob_dist_unique_id(idb))
+    out, errors = {}, []
+
+    def run(rank):
+        try:
+            ex = _CpuExec(h)
+            part = api.HostPartition.uniform(ex, world, n)
+            pb = part.info()["range_bounds"]
+            q0, q1 = int(pb[rank]), int(pb[rank + 1])
+            d = h.gkob_dist_matrix_read_f64_i32(ex.h, idb, rank, world, part.h, n, n, len(va), rows.ctypes.data,
+                                                cols.ctypes.data, va.ctypes.data, 0)
+            assert d, h.gkob_last_error().decode()
+            api._hcheck(h.gkob_dist_cg_create_f64(d, int(scalar_jacobi), 300, 1, 0, 1e-10, 1, 5))
+            bl, xl = b[q0:q1].copy(), np.zeros(q1 - q0)
+            it, st = ctypes.c_longlong(0), ctypes.c_ubyte(0)
+            for _ in range(2):  # the second apply replays the captured graph
+                xl[:] = 0
+                api._hcheck(h.gkob_dist_cg_apply_f64(d, bl.ctypes.data, xl.ctypes.data, ctypes.byref(it),
+                                                     ctypes.byref(st)))
+            out[rank] = (q0, q1, xl, it.value, st.value)
+            h.gkob_dist_destroy(d)
+        except BaseException as e:  # noqa: BLE001
+            errors.append((rank, repr(e)))
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(300)
+    assert not errors, errors
+    x = np.zeros(n)
+    for rank, (q0, q1, xl, it, st) in out.items():
+        x[q0:q1] = xl
+        assert abs(it - it1) <= 1 and st == st1, (it, it1, st, st1)
+    assert np.linalg.norm(x - x1[:, 0]) <= 1e-8 * np.linalg.norm(x1)
