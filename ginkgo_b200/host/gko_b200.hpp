@@ -1058,6 +1058,77 @@ protected:
 template <typename V>
 using Vec = matrix::Dense<V>;
 
+// ---- small conveniences of the reference's user code -------------------------------------------
+// gko::share (include/ginkgo/core/base/utils_helper.hpp): unique -> shared ownership
+template <typename T>
+std::shared_ptr<T> share(std::unique_ptr<T>&& p)
+{
+    return std::shared_ptr<T>(std::move(p));
+}
+// gko::clone of a vector
+template <typename V>
+std::unique_ptr<matrix::Dense<V>> clone(const matrix::Dense<V>* v)
+{
+    return v->clone();
+}
+template <typename V>
+std::unique_ptr<matrix::Dense<V>> clone(const std::unique_ptr<matrix::Dense<V>>& v)
+{
+    return v->clone();
+}
+// gko::initialize<Matrix>({...}, exec) (include/ginkgo/core/matrix/dense.hpp `initialize`): a column
+// vector from a flat list, a matrix from a list of rows; sparse formats drop the zeros like the
+// reference's Dense -> format conversion does
+namespace detail {
+template <typename M>
+struct is_dense : std::false_type {};
+template <typename V>
+struct is_dense<matrix::Dense<V>> : std::true_type {};
+template <typename M>
+struct index_of {
+    using type = typename M::index_type;
+};
+template <typename V>
+struct index_of<matrix::Dense<V>> {
+    using type = int32;
+};
+}  // namespace detail
+template <typename Matrix>
+std::unique_ptr<Matrix> initialize(
+    std::initializer_list<std::initializer_list<typename Matrix::value_type>> rows,
+    std::shared_ptr<const Executor> exec)
+{
+    using V = typename Matrix::value_type;
+    const size_type nr = rows.size(), nc = nr ? rows.begin()->size() : 0;
+    std::vector<V> flat;
+    flat.reserve(nr * nc);
+    for (const auto& r : rows) {
+        if (r.size() != nc) throw BadDimension("initialize: rows of different length");
+        flat.insert(flat.end(), r.begin(), r.end());
+    }
+    if constexpr (detail::is_dense<Matrix>::value) {
+        return Matrix::create_from_host(exec, dim2{nr, nc}, flat.data());
+    } else {
+        using I = typename detail::index_of<Matrix>::type;
+        matrix_data<V, I> data(dim2{nr, nc});
+        for (size_type i = 0; i < nr; ++i)
+            for (size_type j = 0; j < nc; ++j)
+                if (flat[i * nc + j] != V(0)) data.nonzeros.push_back({(I)i, (I)j, flat[i * nc + j]});
+        auto m = Matrix::create(exec);
+        m->read(data);
+        return m;
+    }
+}
+template <typename Matrix>
+std::unique_ptr<Matrix> initialize(std::initializer_list<typename Matrix::value_type> column,
+                                   std::shared_ptr<const Executor> exec)
+{
+    using V = typename Matrix::value_type;
+    static_assert(detail::is_dense<Matrix>::value, "a flat list initialises a column vector");
+    std::vector<V> h(column);
+    return Matrix::create_from_host(exec, dim2{h.size(), 1}, h.data());
+}
+
 // gko::read / read_binary / read_generic / write / write_binary
 // (include/ginkgo/core/base/mtx_io.hpp:150-320) for matrix::Csr
 template <typename MatrixType, typename StreamType>

@@ -911,3 +911,26 @@ def test_host_distributed_fused_cg_in_threads(host, world, scalar_jacobi):
         x[q0:q1] = xl
         assert abs(it - it1) <= 1 and st == st1, (it, it1, st, st1)
     assert np.linalg.norm(x - x1[:, 0]) <= 1e-8 * np.linalg.norm(x1)
+
+
+def test_cpp_user_idioms_on_the_mock(tmp_path):
+    """tests/cpp/host_api_check.cpp: gko::initialize<Format> / share / clone and the reference's
+    3 x 3 stencil solves (x = [1, 3, 2]) written like the reference's own tests, linked against
+    the mock"""
+    d = str(tmp_path)
+    inc = os.path.join(ROOT, "include")
+    gen = os.path.join(d, "mock_gen.c")
+    subprocess.run(["python", os.path.join(ROOT, "tests", "mock", "gen_mock.py"),
+                    os.path.join(inc, "ginkgo_b200.h"), os.path.join(ROOT, "oracle", "liboracle.so"),
+                    os.path.join(ROOT, "tests", "mock", "mock_base.c"), gen], check=True, capture_output=True)
+    objs = []
+    for src in (os.path.join(ROOT, "tests", "mock", "mock_base.c"), gen):
+        o = os.path.join(d, os.path.basename(src) + ".o")
+        subprocess.run(["gcc", "-O1", "-fPIC", "-I" + inc, "-c", src, "-o", o], check=True)
+        objs.append(o)
+    exe = os.path.join(d, "host_api_check")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-Wall", os.path.join(ROOT, "tests", "cpp", "host_api_check.cpp")] +
+                   objs + ["-L" + os.path.join(ROOT, "oracle"), "-loracle", "-lpthread", "-lm",
+                           "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout + r.stderr
