@@ -934,3 +934,28 @@ def test_cpp_user_idioms_on_the_mock(tmp_path):
                            "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-o", exe], check=True)
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout + r.stderr
+
+
+MALFORMED_FILES = {
+    "empty": b"",
+    "header_only": b"%%MatrixMarket matrix coordinate real general\n",
+    "truncated": b"%%MatrixMarket matrix coordinate real general\n3 3 4\n1 1 1.0\n2 2",
+    "bad_index": b"%%MatrixMarket matrix coordinate real general\n2 2 1\n3 1 1.0\n",
+    "zero_index": b"%%MatrixMarket matrix coordinate real general\n2 2 1\n0 1 1.0\n",
+    "negative_size": b"%%MatrixMarket matrix coordinate real general\n-2 2 1\n1 1 1.0\n",
+    "garbage": b"\x00\x01\x02 not a matrix",
+    "bad_banner": b"%%MatrixMarket matrix coordinate quaternion general\n1 1 1\n1 1 1.0\n",
+    "binary_truncated": b"GINKGODI" + b"\x03\x00\x00\x00\x00\x00\x00\x00",
+    "huge_nnz": b"%%MatrixMarket matrix coordinate real general\n2 2 99999999999\n1 1 1.0\n",
+}
+
+
+@pytest.mark.parametrize("name", sorted(MALFORMED_FILES))
+def test_host_readers_reject_malformed_files(host, tmp_path, name):
+    """every malformed file ends in an exception of the host layer (never a crash, never a matrix)"""
+    from ginkgo_b200 import _lib, api
+    p = tmp_path / "m.mtx"
+    p.write_bytes(MALFORMED_FILES[name])
+    for fmt in ("csr", "ell"):
+        with pytest.raises(_lib.B200Error):
+            api.host_read(host, p, fmt)
