@@ -661,21 +661,9 @@ def test_distributed_example_runs_on_the_mock(tmp_path, solver):
     """examples/distributed_solver.cpp (the reference's distributed-solver flow) linked against
     the host-memory mock instead of the CUDA library, one rank: read_distributed, distributed
     vectors, solver + Jacobi from the local block, residual check"""
-    d = str(tmp_path)
-    inc = os.path.join(ROOT, "include")
-    gen = os.path.join(d, "mock_gen.c")
-    subprocess.run(["python", os.path.join(ROOT, "tests", "mock", "gen_mock.py"),
-                    os.path.join(inc, "ginkgo_b200.h"), os.path.join(ROOT, "oracle", "liboracle.so"),
-                    os.path.join(ROOT, "tests", "mock", "mock_base.c"), gen], check=True, capture_output=True)
-    objs = []
-    for src in (os.path.join(ROOT, "tests", "mock", "mock_base.c"), gen):
-        o = os.path.join(d, os.path.basename(src) + ".o")
-        subprocess.run(["gcc", "-O1", "-fPIC", "-I" + inc, "-c", src, "-o", o], check=True)
-        objs.append(o)
-    exe = os.path.join(d, "distributed_solver")
-    subprocess.run(["g++", "-O1", "-std=c++17", os.path.join(ROOT, "examples", "distributed_solver.cpp")] + objs +
-                   ["-L" + os.path.join(ROOT, "oracle"), "-loracle", "-lpthread",
-                    "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-o", exe], check=True)
+    from tests.mock_build import build_mock_executable
+    exe = build_mock_executable(str(tmp_path), os.path.join(ROOT, "examples", "distributed_solver.cpp"),
+                                "distributed_solver")
     env = dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK="0")
     r = subprocess.run([exe, "10", solver], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
@@ -917,21 +905,9 @@ def test_cpp_user_idioms_on_the_mock(tmp_path):
     """tests/cpp/host_api_check.cpp: gko::initialize<Format> / share / clone and the reference's
     3 x 3 stencil solves (x = [1, 3, 2]) written like the reference's own tests, linked against
     the mock"""
-    d = str(tmp_path)
-    inc = os.path.join(ROOT, "include")
-    gen = os.path.join(d, "mock_gen.c")
-    subprocess.run(["python", os.path.join(ROOT, "tests", "mock", "gen_mock.py"),
-                    os.path.join(inc, "ginkgo_b200.h"), os.path.join(ROOT, "oracle", "liboracle.so"),
-                    os.path.join(ROOT, "tests", "mock", "mock_base.c"), gen], check=True, capture_output=True)
-    objs = []
-    for src in (os.path.join(ROOT, "tests", "mock", "mock_base.c"), gen):
-        o = os.path.join(d, os.path.basename(src) + ".o")
-        subprocess.run(["gcc", "-O1", "-fPIC", "-I" + inc, "-c", src, "-o", o], check=True)
-        objs.append(o)
-    exe = os.path.join(d, "host_api_check")
-    subprocess.run(["g++", "-O1", "-std=c++17", "-Wall", os.path.join(ROOT, "tests", "cpp", "host_api_check.cpp")] +
-                   objs + ["-L" + os.path.join(ROOT, "oracle"), "-loracle", "-lpthread", "-lm",
-                           "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-o", exe], check=True)
+    from tests.mock_build import build_mock_executable
+    exe = build_mock_executable(str(tmp_path), os.path.join(ROOT, "tests", "cpp", "host_api_check.cpp"),
+                                "host_api_check")
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout + r.stderr
 
