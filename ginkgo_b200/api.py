@@ -587,8 +587,9 @@ class DistMatrix:
         h.gkob_dist_vector_read_f64.restype = i
         h.gkob_dist_vector_read_f64.argtypes = [vp, vp, ll, ll, ll, vp, vp, vp, vp]
         h.gkob_dist_solve_f64.restype = i
-        h.gkob_dist_solve_f64.argtypes = [vp, i, i, i, vp, vp, ll, ll, i, i, ctypes.c_double, i, i, i,
+        h.gkob_dist_solve_f64.argtypes = [vp, i, i, i, vp, vp, ll, ll, i, i, ctypes.c_double, i, i, i, i,
                                           ctypes.POINTER(ll), ctypes.POINTER(ctypes.c_ubyte)]
+        h.gkob_dist_apply_f64.restype, h.gkob_dist_apply_f64.argtypes = i, [vp, vp, vp, i]
 
     @staticmethod
     def _unique_id(exec_, rank, world, group):
@@ -684,8 +685,14 @@ class DistMatrix:
         _hcheck(_host().gkob_dist_solve_f64(
             self.h, kinds[kind], precond_max_bs, schwarz, b_local.data_ptr(), x_local.data_ptr(), global_rows,
             -1 if max_iters is None else max_iters, res_kind, baseline, reduction, int(iter_first), krylov_dim,
-            ortho, ctypes.byref(it), ctypes.byref(st)))
+            ortho, 1 if b_local.dim() == 1 else b_local.shape[1], ctypes.byref(it), ctypes.byref(st)))
         return it.value, st.value
+
+    def apply_local(self, b_local, x_local):
+        """LinOp::apply on the local rows of distributed vectors (n_local [x nrhs] tensors): the owned
+        entries are copied next to the ghost slots of an internal extended vector"""
+        _hcheck(_host().gkob_dist_apply_f64(self.h, b_local.data_ptr(), x_local.data_ptr(),
+                                            1 if b_local.dim() == 1 else b_local.shape[1]))
 
     def make_cg(self, scalar_jacobi=False, max_iters=None, res_kind=1, baseline=0, reduction=1e-8,
                 iter_first=True, check_every=16):

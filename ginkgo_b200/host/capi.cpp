@@ -586,18 +586,20 @@ int gkob_dist_cg_apply_f64(void* dist, const double* b_local, double* x_local, l
 // schwarz_sweeps: 0 = Jacobi(precond_max_bs) generated from the local block; -1 = Schwarz whose
 // local solver is that Jacobi on the square local block; k > 0 = Schwarz whose local solver is k
 // Richardson sweeps (Ir, relaxation from gkob_solver_params) preconditioned by that Jacobi
+// b_local / x_local: n_local x nrhs, row-major
 int gkob_dist_solve_f64(void* dist, int kind, int precond_max_bs, int schwarz_sweeps, const double* b_local,
                         double* x_local, long long global_rows, long long max_iters, int res_kind,
-                        int baseline, double reduction, int iter_first, int krylov_dim, int ortho,
+                        int baseline, double reduction, int iter_first, int krylov_dim, int ortho, int nrhs,
                         long long* iters, unsigned char* status)
 {
     return guarded([&] {
         auto h = static_cast<DistHandle*>(dist);
         const size_type n = h->A->n_local();
-        auto b = distributed::Vector<double>::create_view(h->exec, h->comm, dim2{(size_type)global_rows, 1},
-                                                          dim2{n, 1}, const_cast<double*>(b_local), 1);
-        auto x = distributed::Vector<double>::create_view(h->exec, h->comm, dim2{(size_type)global_rows, 1},
-                                                          dim2{n, 1}, x_local, 1);
+        const size_type k = (size_type)nrhs;
+        auto b = distributed::Vector<double>::create_view(h->exec, h->comm, dim2{(size_type)global_rows, k},
+                                                          dim2{n, k}, const_cast<double*>(b_local), k);
+        auto x = distributed::Vector<double>::create_view(h->exec, h->comm, dim2{(size_type)global_rows, k},
+                                                          dim2{n, k}, x_local, k);
         std::unique_ptr<LinOp> solver;
         if (schwarz_sweeps == 0) {
             solver = make_solver<double>(h->exec, kind, h->A, precond_max_bs, nullptr, 0, max_iters, res_kind,
@@ -624,6 +626,20 @@ int gkob_dist_solve_f64(void* dist, int kind, int precond_max_bs, int schwarz_sw
         auto base = dynamic_cast<solver::SolverBase<double>*>(solver.get());
         *iters = base ? (long long)base->get_num_iterations() : -1;
         *status = base ? base->get_stop_status() : 0;
+    });
+}
+
+// LinOp::apply of the distributed matrix on the local rows of distributed vectors
+// (n_local_cols x nrhs -> n_local x nrhs, row-major)
+int gkob_dist_apply_f64(void* dist, const double* b_local, double* x_local, int nrhs)
+{
+    return guarded([&] {
+        auto h = static_cast<DistHandle*>(dist);
+        const size_type k = (size_type)nrhs;
+        auto b = matrix::Dense<double>::create_view(h->exec, dim2{h->A->n_local_cols(), k},
+                                                    const_cast<double*>(b_local), k);
+        auto x = matrix::Dense<double>::create_view(h->exec, dim2{h->A->n_local(), k}, x_local, k);
+        static_cast<const LinOp*>(h->A.get())->apply(b.get(), x.get());
     });
 }
 

@@ -644,24 +644,41 @@ public:
     }
 
 protected:
-    // LinOp::apply on the LOCAL rows of distributed vectors (one column): b's rows are copied
-    // next to the ghost slots of an internal extended vector, then exchange + local SpMV
+    // LinOp::apply on the LOCAL rows of distributed vectors: column by column, b's rows are
+    // copied next to the ghost slots of an internal extended vector, then exchange + local SpMV
     // (experimental::distributed::Matrix::apply_impl, core/distributed/matrix.cpp:450-509)
-    matrix::Dense<V>* gather(const LinOp* lb) const
+    matrix::Dense<V>* gather(const matrix::Dense<V>* b, size_type col) const
     {
-        auto b = as<matrix::Dense<V>>(lb);
-        if (b->get_size().cols != 1)
-            throw NotSupported("distributed::Matrix::apply: one right-hand side per call");
         if (!x_ext_) x_ext_ = matrix::Dense<V>::create(exec_, dim2{n_local_cols_ + n_ghost_, 1});
         auto owned = x_ext_->create_submatrix_rows(0, n_local_cols_);
-        owned->copy_from(b);
+        auto bcol = matrix::Dense<V>::create_view(exec_, dim2{b->get_size().rows, 1},
+                                                  const_cast<V*>(b->get_const_values()) + col, b->get_stride());
+        owned->copy_from(bcol.get());
         GKOB_CALL(cabi<V>::halo_exchange(exec_->ctx(), comm_->get(), halo_, x_ext_->get_values(), nullptr));
         return x_ext_.get();
     }
-    void apply_impl(const LinOp* b, LinOp* x) const override { local_->apply(gather(b), x); }
-    void apply_impl(const LinOp* alpha, const LinOp* b, const LinOp* beta, LinOp* x) const override
+    static std::unique_ptr<matrix::Dense<V>> column_of(matrix::Dense<V>* x, size_type col)
     {
-        local_->apply(alpha, gather(b), beta, x);
+        return matrix::Dense<V>::create_view(x->get_executor(), dim2{x->get_size().rows, 1},
+                                             x->get_values() + col, x->get_stride());
+    }
+    void apply_impl(const LinOp* lb, LinOp* lx) const override
+    {
+        auto b = as<matrix::Dense<V>>(lb);
+        auto x = as<matrix::Dense<V>>(lx);
+        for (size_type j = 0; j < b->get_size().cols; ++j) {
+            auto xe = gather(b, j);
+            local_->apply(xe, column_of(x, j).get());
+        }
+    }
+    void apply_impl(const LinOp* alpha, const LinOp* lb, const LinOp* beta, LinOp* lx) const override
+    {
+        auto b = as<matrix::Dense<V>>(lb);
+        auto x = as<matrix::Dense<V>>(lx);
+        for (size_type j = 0; j < b->get_size().cols; ++j) {
+            auto xe = gather(b, j);
+            local_->apply(alpha, xe, beta, column_of(x, j).get());
+        }
     }
 
 private:

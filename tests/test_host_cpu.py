@@ -612,7 +612,7 @@ def test_host_distributed_solvers_in_threads(host, kind, precond, schwarz=0):
             bl, xl = b[q0:q1].copy(), np.zeros(q1 - q0)
             it, st = ctypes.c_longlong(0), ctypes.c_ubyte(0)
             rc = h.gkob_dist_solve_f64(d, kinds[skind], max_bs, schwarz, bl.ctypes.data, xl.ctypes.data, n, 400, 1,
-                                       0, 1e-10, 1, 20, extra.get("ortho", 0), ctypes.byref(it), ctypes.byref(st))
+                                       0, 1e-10, 1, 20, extra.get("ortho", 0), 1, ctypes.byref(it), ctypes.byref(st))
             assert rc == 0, h.gkob_last_error().decode()
             out[rank] = (q0, q1, xl, it.value, st.value)
             h.gkob_dist_destroy(d)
@@ -738,7 +738,7 @@ def test_host_schwarz_with_local_richardson_sweeps(host):
             assert d, h.gkob_last_error().decode()
             bl, xl = b[q0:q1].copy(), np.zeros(q1 - q0)
             it, st = ctypes.c_longlong(0), ctypes.c_ubyte(0)
-            rc = h.gkob_dist_solve_f64(d, 0, 1, 3, bl.ctypes.data, xl.ctypes.data, n, 400, 1, 0, 1e-10, 1, 20, 0,
+            rc = h.gkob_dist_solve_f64(d, 0, 1, 3, bl.ctypes.data, xl.ctypes.data, n, 400, 1, 0, 1e-10, 1, 20, 0, 1,
                                        ctypes.byref(it), ctypes.byref(st))
             assert rc == 0, h.gkob_last_error().decode()
             out[rank] = (q0, q1, xl, it.value)
@@ -935,3 +935,61 @@ def test_host_readers_reject_malformed_files(host, tmp_path, name):
     for fmt in ("csr", "ell"):
         with pytest.raises(_lib.B200Error):
             api.host_read(host, p, fmt)
+
+
+@pytest.mark.parametrize("kind", ["cg", "gmres", "bicgstab"])
+def test_host_distributed_multiple_right_hand_sides(host, kind):
+    """distributed apply and solve with 3 right-hand sides (column by column through the halo),
+    3 ranks as threads, against the single-matrix multi-rhs solver"""
+    import threading
+    from ginkgo_b200 import api
+    h = api._host()
+    api.DistMatrix._bind(h)
+    world, k = 3, 3
+    rp, ci, va = W.laplace(12, 2)
+    n = len(rp) - 1
+    rng = np.random.default_rng(15)
+    b = rng.uniform(-1, 1, (n, k))
+    rows, cols = np.repeat(np.arange(n, dtype=np.int64), np.diff(rp)), ci.astype(np.int64)
+    x1, it1, st1 = host_solve(host, kind, "f64", rp, ci, va, b, np.zeros((n, k)), 1, None, max_iters=400,
+                              reduction=1e-10, krylov_dim=20)
+    y1 = np.zeros((n, k))
+    H.Oracle()("csr_spmv_f64_i32", n, n, len(va), rp, ci, va, b.copy(), k, k, y1, k)
+    idb = (ctypes.c_ubyte * 128)()
+    api._hcheck(h.gkob_dist_unique_id(idb))
+    out, errors = {}, []
+    kinds = {"cg": 0, "bicgstab": 1, "gmres": 2}
+
+    def run(rank):
+        try:
+            ex = _CpuExec(h)
+            part = api.HostPartition.uniform(ex, world, n)
+            pb = part.info()["range_bounds"]
+            q0, q1 = int(pb[rank]), int(pb[rank + 1])
+            d = h.gkob_dist_matrix_read_f64_i32(ex.h, idb, rank, world, part.h, n, n, len(va), rows.ctypes.data,
+                                                cols.ctypes.data, va.ctypes.data, 0)
+            assert d, h.gkob_last_error().decode()
+            bl = np.ascontiguousarray(b[q0:q1])
+            yl, xl = np.zeros((q1 - q0, k)), np.zeros((q1 - q0, k))
+            api._hcheck(h.gkob_dist_apply_f64(d, bl.ctypes.data, yl.ctypes.data, k))
+            it, st = ctypes.c_longlong(0), ctypes.c_ubyte(0)
+            rc = h.gkob_dist_solve_f64(d, kinds[kind], 1, 0, bl.ctypes.data, xl.ctypes.data, n, 400, 1, 0, 1e-10, 1,
+                                       20, 0, k, ctypes.byref(it), ctypes.byref(st))
+            assert rc == 0, h.gkob_last_error().decode()
+            out[rank] = (q0, q1, yl, xl, it.value)
+            h.gkob_dist_destroy(d)
+        except BaseException as e:  # noqa: BLE001
+            errors.append((rank, repr(e)))
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(300)
+    assert not errors, errors
+    x = np.zeros((n, k))
+    for rank, (q0, q1, yl, xl, it) in out.items():
+        assert np.array_equal(yl, y1[q0:q1])  # the SpMV rows are bit-identical
+        x[q0:q1] = xl
+        assert abs(it - it1) <= 1
+    assert np.linalg.norm(x - x1) <= 1e-8 * np.linalg.norm(x1)
