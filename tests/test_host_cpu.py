@@ -656,14 +656,19 @@ def test_host_distributed_solve_python_wrapper(host):
         A.solve("bicg", bl, xl, n)  # no transposed distributed apply
 
 
+@pytest.fixture(scope="module")
+def dist_example_exe(tmp_path_factory):
+    from tests.mock_build import build_mock_executable
+    return build_mock_executable(str(tmp_path_factory.mktemp("dist_example")),
+                                 os.path.join(ROOT, "examples", "distributed_solver.cpp"), "distributed_solver")
+
+
 @pytest.mark.parametrize("solver", ["cg", "gmres", "bicgstab"])
-def test_distributed_example_runs_on_the_mock(tmp_path, solver):
+def test_distributed_example_runs_on_the_mock(dist_example_exe, solver):
     """examples/distributed_solver.cpp (the reference's distributed-solver flow) linked against
     the host-memory mock instead of the CUDA library, one rank: read_distributed, distributed
     vectors, solver + Jacobi from the local block, residual check"""
-    from tests.mock_build import build_mock_executable
-    exe = build_mock_executable(str(tmp_path), os.path.join(ROOT, "examples", "distributed_solver.cpp"),
-                                "distributed_solver")
+    exe = dist_example_exe
     env = dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK="0")
     r = subprocess.run([exe, "10", solver], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
