@@ -233,3 +233,28 @@ def test_vector_build_local_matches_oracle(orc, cuda, lt, gt):
         res.append([D.vector_build_local(be, part, rows, cols, vals, ncols, p) for p in range(num_parts)])
     for a, b in zip(*res):
         eq(a, b)
+
+
+def test_distributed_apply_with_several_right_hand_sides(hexec):
+    """world size 1: distributed::Matrix::apply on a 3-column vector (column by column through the
+    internal extended vector) equals the plain Csr apply, bit for bit"""
+    import torch
+    import workloads as W
+    from ginkgo_b200 import api
+    rp, ci, va = W.laplace(20, 2)
+    n, k = len(rp) - 1, 3
+    rng = np.random.default_rng(10)
+    rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(rp))
+    part = api.HostPartition.uniform(hexec, 1, n)
+    A = api.DistMatrix.read(hexec, part, (n, n), rows, ci.astype(np.int64), va)
+    with torch.cuda.stream(hexec.stream):
+        t = [torch.from_numpy(a).to(hexec.device) for a in (va, ci, rp)]
+        b = torch.from_numpy(rng.uniform(-1, 1, (n, k))).to(hexec.device)
+        y1 = torch.zeros((n, k), dtype=torch.float64, device=hexec.device)
+        y2 = torch.zeros((n, k), dtype=torch.float64, device=hexec.device)
+    A.apply_local(b, y1)
+    B = api.host_csr(hexec, (n, n), *t)
+    bd, yd = api.host_dense(hexec, b), api.host_dense(hexec, y2)
+    api._hcheck(api._host().gkob_apply(B.h, bd.h, yd.h))
+    hexec.synchronize()
+    assert torch.equal(y1, y2)
