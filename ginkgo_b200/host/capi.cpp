@@ -370,6 +370,8 @@ void* gkob_read_f64_i32(void* exec, const char* path, const char* fmt)
                 h->op = read_generic<matrix::Coo<double, int32>>(is, e);
             else if (f == "hybrid")
                 h->op = read_generic<matrix::Hybrid<double, int32>>(is, e);
+            else if (f == "dense")
+                h->op = read_generic<matrix::Dense<double>>(is, e);
             else
                 throw NotSupported("gkob_read: unknown format " + f);
         })) {
@@ -401,6 +403,8 @@ int gkob_write_f64_i32(void* op, const char* path, int layout)
         else if (auto a = dynamic_cast<const matrix::Coo<double, int32>*>(p))
             put(a);
         else if (auto a = dynamic_cast<const matrix::Hybrid<double, int32>*>(p))
+            put(a);
+        else if (auto a = dynamic_cast<const matrix::Dense<double>*>(p))
             put(a);
         else
             throw NotSupported("gkob_write: not a <double, int32> matrix format");

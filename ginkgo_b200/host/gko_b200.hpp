@@ -421,6 +421,31 @@ public:
     V* get_values() { return values_.get_data(); }
     const V* get_const_values() const { return values_.get_const_data(); }
     size_type get_stride() const { return stride_; }
+    // ReadableFromMatrixData / WritableToMatrixData (core/matrix/dense.cpp `read`, :1074-1087
+    // `write_impl`): zero-filled, entries scattered (later duplicates win); write lists the nonzeros
+    template <typename I>
+    void read(const matrix_data<V, I>& data)
+    {
+        std::vector<V> h(data.size.rows * data.size.cols, V(0));
+        for (const auto& e : data.nonzeros) {
+            if (e.row < 0 || (size_type)e.row >= data.size.rows || e.column < 0 ||
+                (size_type)e.column >= data.size.cols)
+                throw OutOfBounds("Dense::read: entry outside the matrix");
+            h[(size_type)e.row * data.size.cols + (size_type)e.column] = e.value;
+        }
+        size_ = data.size;
+        stride_ = data.size.cols;
+        values_ = array<V>(exec_, h);
+    }
+    template <typename I>
+    void write(matrix_data<V, I>& data) const
+    {
+        const auto h = to_host();
+        data = matrix_data<V, I>(size_);
+        for (size_type r = 0; r < size_.rows; ++r)
+            for (size_type c = 0; c < size_.cols; ++c)
+                if (h[r * size_.cols + c] != V(0)) data.nonzeros.push_back({(I)r, (I)c, h[r * size_.cols + c]});
+    }
     std::vector<V> to_host() const
     {  // compact row-major copy
         std::vector<V> raw = values_.to_host();
@@ -1130,39 +1155,39 @@ std::unique_ptr<Matrix> initialize(std::initializer_list<typename Matrix::value_
 }
 
 // gko::read / read_binary / read_generic / write / write_binary
-// (include/ginkgo/core/base/mtx_io.hpp:150-320) for matrix::Csr
+// (include/ginkgo/core/base/mtx_io.hpp:150-320) for Dense and the five sparse formats
 template <typename MatrixType, typename StreamType>
 std::unique_ptr<MatrixType> read(StreamType&& is, std::shared_ptr<const Executor> exec)
 {
     auto mtx = MatrixType::create(std::move(exec));
-    mtx->read(read_raw<typename MatrixType::value_type, typename MatrixType::index_type>(is));
+    mtx->read(read_raw<typename MatrixType::value_type, typename detail::index_of<MatrixType>::type>(is));
     return mtx;
 }
 template <typename MatrixType, typename StreamType>
 std::unique_ptr<MatrixType> read_binary(StreamType&& is, std::shared_ptr<const Executor> exec)
 {
     auto mtx = MatrixType::create(std::move(exec));
-    mtx->read(read_binary_raw<typename MatrixType::value_type, typename MatrixType::index_type>(is));
+    mtx->read(read_binary_raw<typename MatrixType::value_type, typename detail::index_of<MatrixType>::type>(is));
     return mtx;
 }
 template <typename MatrixType, typename StreamType>
 std::unique_ptr<MatrixType> read_generic(StreamType&& is, std::shared_ptr<const Executor> exec)
 {
     auto mtx = MatrixType::create(std::move(exec));
-    mtx->read(read_generic_raw<typename MatrixType::value_type, typename MatrixType::index_type>(is));
+    mtx->read(read_generic_raw<typename MatrixType::value_type, typename detail::index_of<MatrixType>::type>(is));
     return mtx;
 }
 template <typename MatrixType, typename StreamType>
 void write(StreamType&& os, const MatrixType* mtx, layout_type layout = layout_type::coordinate)
 {
-    matrix_data<typename MatrixType::value_type, typename MatrixType::index_type> data;
+    matrix_data<typename MatrixType::value_type, typename detail::index_of<MatrixType>::type> data;
     mtx->write(data);
     write_raw(os, data, layout);
 }
 template <typename MatrixType, typename StreamType>
 void write_binary(StreamType&& os, const MatrixType* mtx)
 {
-    matrix_data<typename MatrixType::value_type, typename MatrixType::index_type> data;
+    matrix_data<typename MatrixType::value_type, typename detail::index_of<MatrixType>::type> data;
     mtx->write(data);
     write_binary_raw(os, data);
 }
