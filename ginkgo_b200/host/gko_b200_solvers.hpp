@@ -2,6 +2,8 @@
 // Included by gko_b200.hpp.
 #pragma once
 
+#include <chrono>
+
 namespace gko_b200 {
 
 // =============================================================================================
@@ -89,6 +91,51 @@ private:
     Iteration(std::shared_ptr<const Executor> exec, size_type n) : exec_(exec), max_iters_(n) {}
     std::shared_ptr<const Executor> exec_;
     size_type max_iters_;
+};
+
+// core/stop/time.cpp:17-27, include/ginkgo/core/stop/time.hpp:24-58: wall-clock limit, the clock
+// starts when the criterion is generated (i.e. at the beginning of a solve)
+class Time : public Criterion {
+public:
+    using clock = std::chrono::steady_clock;
+    struct Factory : CriterionFactory {
+        std::chrono::nanoseconds time_limit_{10000000000LL};
+        Factory& with_time_limit(std::chrono::nanoseconds t)
+        {
+            time_limit_ = t;
+            return *this;
+        }
+        std::shared_ptr<const CriterionFactory> on(std::shared_ptr<const Executor>) const
+        {
+            return std::make_shared<Factory>(*this);
+        }
+        std::unique_ptr<Criterion> generate(std::shared_ptr<const Executor> exec,
+                                            const CriterionArgs&) const override
+        {
+            return std::unique_ptr<Criterion>(new Time(exec, time_limit_));
+        }
+        int kind() const override { return 3; }  // host-side only: keeps the solver off the fused path
+    };
+    static Factory build() { return Factory{}; }
+    bool check(uint8 id, bool set_finalized, array<uint8>* stop_status, bool* one_changed,
+               const Updater&) override
+    {
+        const bool result = clock::now() - start_ >= time_limit_;
+        if (result) {
+            GKOB_CALL(b200_set_all_statuses(exec_->ctx(), stop_status->get_size(), id, set_finalized,
+                                            stop_status->get_data()));
+            *one_changed = true;
+        }
+        return result;
+    }
+
+private:
+    Time(std::shared_ptr<const Executor> exec, std::chrono::nanoseconds limit)
+        : exec_(exec), time_limit_(limit), start_(clock::now())
+    {}
+    std::shared_ptr<const Executor> exec_;
+    std::chrono::nanoseconds time_limit_;
+    clock::time_point start_;
 };
 
 // core/stop/residual_norm.cpp:91-228
@@ -701,6 +748,7 @@ protected:
         if (this->criteria_.empty() || this->criteria_.size() > 2) return false;
         for (size_type k = 0; k < this->criteria_.size(); ++k) {
             auto& c = this->criteria_[k];
+            if (c->kind() < 0 || c->kind() > 2) return false;  // e.g. stop::Time: host-side criterion
             if (c->kind() == 0) {
                 if (max_iters >= 0) return false;
                 max_iters = (int64)c->max_iters();
