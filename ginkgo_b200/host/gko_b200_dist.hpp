@@ -102,6 +102,8 @@ private:
 // every solver takes it as is; compute_dot / compute_conj_dot / compute_norm2 /
 // compute_squared_norm2 add the sum over the ranks (core/distributed/vector.cpp:480-534), and
 // the vectors a solver creates next to it reduce the same way (Dense::create_like).
+// A solver on a distributed::Matrix must be given distributed::Vector operands: with plain Dense
+// operands its dots and norms would stay local to each rank.
 template <typename V>
 class Vector : public matrix::Dense<V> {
     using Dense = matrix::Dense<V>;
