@@ -81,12 +81,36 @@ inline bool is_finalized(uint8_t s) { return (s & kFinalizedMask) != 0; }
         if (!(cond)) return B200_ERR_INVALID;   \
     } while (0)
 
+// The host loop may visit the (row, col) pairs in any order -- a GPU does.  -DB200_SHIM_ORDER=1 runs
+// them backwards, =2 in a scrambled order (a stride coprime to the count), so that a kernel body
+// which silently relies on ascending execution order fails on the CPU already.
+#ifndef B200_SHIM_ORDER
+#define B200_SHIM_ORDER 0
+#endif
 template <typename F>
 inline b200_status launch_ew(b200_ctx* ctx, int64_t rows, int64_t cols, F f)
 {
-    if (rows * cols <= 0) return B200_OK;
-    for (int64_t i = 0; i < rows; ++i)
-        for (int64_t j = 0; j < cols; ++j) f(i, j);
+    const int64_t total = rows * cols;
+    if (total <= 0) return B200_OK;
+    int64_t stride = 1;
+    if (B200_SHIM_ORDER == 2) {
+        stride = total / 2 + 1;
+        auto gcd = [](int64_t a, int64_t b) {
+            while (b) {
+                const int64_t t = a % b;
+                a = b;
+                b = t;
+            }
+            return a;
+        };
+        while (gcd(stride, total) != 1) ++stride;
+    }
+    for (int64_t k = 0; k < total; ++k) {
+        int64_t t = k;
+        if (B200_SHIM_ORDER == 1) t = total - 1 - k;
+        if (B200_SHIM_ORDER == 2) t = (int64_t)(((__int128)k * stride + 7) % total);
+        f(t / cols, t % cols);
+    }
     ctx->launches++;
     return B200_OK;
 }

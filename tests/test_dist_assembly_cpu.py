@@ -24,8 +24,9 @@ def orc():
     return H.Oracle()
 
 
-@pytest.fixture(scope="module")
-def ksrc(tmp_path_factory):
+# execution order of the host loop that stands for the grid: ascending, descending, scrambled
+@pytest.fixture(scope="module", params=[0, 1, 2], ids=["fwd", "rev", "scrambled"])
+def ksrc(tmp_path_factory, request):
     d = str(tmp_path_factory.mktemp("dist_ksrc"))
     src = os.path.join(d, "dist_assembly.cpp")
     with open(src, "w") as f:
@@ -34,7 +35,7 @@ def ksrc(tmp_path_factory):
     # -Bsymbolic: the copy's own template instantiations, not the same-named ones of the CUDA
     # library another test may have loaded into the process
     subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-Wl,-Bsymbolic", "-Wall",
-                    "-Wno-unused-function",
+                    "-Wno-unused-function", "-DB200_SHIM_ORDER=%d" % request.param,
                     "-I" + os.path.join(ROOT, "tests", "mock", "host_cuda_shim"),
                     "-I" + os.path.join(ROOT, "include"), src, "-o", so], check=True)
     return KernelSourceBackend(ctypes.CDLL(so))

@@ -46,8 +46,9 @@ class KernelSourceBackend:
             a.value = b.value
 
 
-@pytest.fixture(scope="module")
-def ksrc(tmp_path_factory):
+# execution order of the host loop that stands for the grid: ascending, descending, scrambled
+@pytest.fixture(scope="module", params=[0, 1, 2], ids=["fwd", "rev", "scrambled"])
+def ksrc(tmp_path_factory, request):
     d = str(tmp_path_factory.mktemp("ksrc"))
     src = open(os.path.join(ROOT, "ginkgo_b200", "csrc", "krylov_steps.cu")).read()
     # the one hand-written __global__ kernel of the file (bicgstab's status flip) and its <<<>>>
@@ -65,7 +66,7 @@ def ksrc(tmp_path_factory):
     so = os.path.join(d, "libkrylov_steps_host.so")
     # -Bsymbolic: the copy's own template instantiations, not the same-named ones of a CUDA
     # library another test may have loaded into the process
-    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wl,-Bsymbolic", "-ffp-contract=off",
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wl,-Bsymbolic", "-ffp-contract=off", "-DB200_SHIM_ORDER=%d" % request.param,
                     "-I" + os.path.join(ROOT, "include"), "-o", so, os.path.join(d, "krylov_steps.cpp")],
                    check=True)
     return KernelSourceBackend(ctypes.CDLL(so))

@@ -26,8 +26,9 @@ def orc():
     return H.Oracle()
 
 
-@pytest.fixture(scope="module")
-def ksrc(tmp_path_factory):
+# execution order of the host loop that stands for the grid: ascending, descending, scrambled
+@pytest.fixture(scope="module", params=[0, 1, 2], ids=["fwd", "rev", "scrambled"])
+def ksrc(tmp_path_factory, request):
     d = str(tmp_path_factory.mktemp("bicg_ksrc"))
     src = os.path.join(d, "bicg_transpose.cpp")
     with open(src, "w") as f:  # + dense::compute_sqrt (dist_vector.cu), one more element-wise file
@@ -35,7 +36,7 @@ def ksrc(tmp_path_factory):
         f.write(open(os.path.join(ROOT, "ginkgo_b200", "csrc", "dist_vector.cu")).read())
     so = os.path.join(d, "libbicg_transpose_host.so")
     subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-Wl,-Bsymbolic", "-Wall",
-                    "-Wno-unused-function", "-ffp-contract=off",
+                    "-Wno-unused-function", "-DB200_SHIM_ORDER=%d" % request.param, "-ffp-contract=off",
                     "-I" + os.path.join(ROOT, "tests", "mock", "host_cuda_shim"),
                     "-I" + os.path.join(ROOT, "include"), src, "-o", so], check=True)
     return KernelSourceBackend(ctypes.CDLL(so))
