@@ -181,7 +181,7 @@ inline b200_status has_ordered_parts(b200_ctx* ctx, int64_t num_ranges, const in
     b200_status st = launch_ew(ctx, 1, 1, [=] __device__(int64_t, int64_t) { *unordered = 0; });
     if (st != B200_OK) return st;
     st = launch_ew(ctx, num_ranges - 1, 1, [=] __device__(int64_t i, int64_t) {
-        if (part_ids[i + 1] < part_ids[i]) *unordered = 1;  // every writer stores the same value
+        if (part_ids[i + 1] < part_ids[i]) atomicAdd(unordered, 1);
     });
     if (st != B200_OK) return st;
     int32_t u = 0;

@@ -11,6 +11,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#ifdef B200_SHIM_THREADS
+#include <thread>
+#include <vector>
+#endif
 
 #include "ginkgo_b200.h"
 
@@ -51,18 +55,8 @@ inline int cudaStreamSynchronize(int) { return 0; }
     } while (0)
 inline int __popc(unsigned int w) { return __builtin_popcount(w); }
 inline int __ffs(unsigned int w) { return __builtin_ffs((int)w); }
-inline unsigned int atomicOr(unsigned int* p, unsigned int v)
-{
-    const unsigned int old = *p;
-    *p = old | v;
-    return old;
-}
-inline int atomicAdd(int* p, int v)
-{
-    const int old = *p;
-    *p = old + v;
-    return old;
-}
+inline unsigned int atomicOr(unsigned int* p, unsigned int v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 
 namespace b200 {
 
@@ -105,6 +99,19 @@ inline b200_status launch_ew(b200_ctx* ctx, int64_t rows, int64_t cols, F f)
         };
         while (gcd(stride, total) != 1) ++stride;
     }
+#ifdef B200_SHIM_THREADS
+    // real concurrency (for ThreadSanitizer runs): the index space is dealt round-robin to threads
+    {
+        std::vector<std::thread> pool;
+        for (int w = 0; w < B200_SHIM_THREADS; ++w)
+            pool.emplace_back([=] {
+                for (int64_t k = w; k < total; k += B200_SHIM_THREADS) f(k / cols, k % cols);
+            });
+        for (auto& th : pool) th.join();
+        ctx->launches++;
+        return B200_OK;
+    }
+#endif
     for (int64_t k = 0; k < total; ++k) {
         int64_t t = k;
         if (B200_SHIM_ORDER == 1) t = total - 1 - k;

@@ -353,3 +353,31 @@ def test_vector_build_local_matches_reference(be, lt, gt, seed):
             ref = ref_or_skip()
             if hasattr(ref.lib(), "refshim_vector_build_local"):
                 eq(got, ref.vector_build_local((nrows, ncols), rows, cols, vals, mapping, num_parts, p))
+
+
+def test_kernel_sources_are_race_free_under_real_threads(tmp_path):
+    """ThreadSanitizer on host-compiled copies of dist_assembly.cu and bicg_transpose.cu (+
+    dist_vector.cu) whose launches run on 4 real threads: no conflicting accesses inside a launch"""
+    import sys
+    tsan = subprocess.run(["g++", "-print-file-name=libtsan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(tsan) or not os.path.exists(tsan):
+        pytest.skip("libtsan not available")
+    libs = []
+    for name, files in (("da", ["dist_assembly.cu"]), ("bt", ["bicg_transpose.cu", "dist_vector.cu"])):
+        src = str(tmp_path / (name + ".cpp"))
+        with open(src, "w") as f:
+            for cu in files:
+                f.write(open(os.path.join(ROOT, "ginkgo_b200", "csrc", cu)).read())
+        so = str(tmp_path / ("lib%s_tsan.so" % name))
+        subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-fsanitize=thread",
+                        "-DB200_SHIM_THREADS=4", "-ffp-contract=off", "-Wl,-Bsymbolic",
+                        "-I" + os.path.join(ROOT, "tests", "mock", "host_cuda_shim"),
+                        "-I" + os.path.join(ROOT, "include"), src, "-o", so, "-lpthread"], check=True)
+        libs.append(so)
+    env = dict(os.environ, LD_PRELOAD=tsan, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tsan_runner.py")] + libs, env=env,
+                       capture_output=True, text=True, timeout=900)
+    if "FATAL: ThreadSanitizer" in r.stderr and "TSAN_RUNNER_DONE" not in r.stdout:
+        pytest.skip("ThreadSanitizer cannot start in this environment: " + r.stderr[-200:])
+    assert "TSAN_RUNNER_DONE" in r.stdout, r.stdout[-500:] + r.stderr[-2000:]
+    assert "WARNING: ThreadSanitizer" not in r.stderr, r.stderr[-4000:]
