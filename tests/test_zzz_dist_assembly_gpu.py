@@ -168,7 +168,11 @@ def test_jacobi_transpose_matches_oracle(orc, cuda, vt):
 def test_bicg_solver_matches_oracle(hexec, vt, precond):
     import workloads as W
     from tests.test_solvers_gpu import device_solve, ref_jacobi
-    rp, ci, va = W.laplace(16, 2, vdtype=VT[vt])
+    # unpreconditioned fp32 BiCG stagnates above 1e-4 on the 16x16 grid (the REFERENCE too: 200
+    # iterations, true residual 3e-3 / 8e-2 -- first B200 log), where comparing two chaotic
+    # non-converged runs means nothing; the 12x12 grid converges in ~65 iterations
+    grid = 12 if (vt == "f32" and precond == 0) else 16
+    rp, ci, va = W.laplace(grid, 2, vdtype=VT[vt])
     rng = np.random.default_rng(31)
     va = (va * rng.uniform(0.6, 1.4, len(va))).astype(VT[vt])
     n = len(rp) - 1
