@@ -54,10 +54,49 @@ __global__ void extract_diagonal_kernel(int64_t n, const I* __restrict__ rp,
     diag[row] = d;
 }
 
+// components::fill_array for any trivially copyable element of 1, 2, 4, 8 or 16 bytes
+template <typename T>
+__global__ void fill_array_kernel(T* __restrict__ data, int64_t n, T value)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        data[i] = value;
+}
+
 }  // namespace convert
 }  // namespace b200
 
 extern "C" {
+
+/* components::fill_array (core/components/fill_array_kernels.hpp:22-25;
+ * reference/components/fill_array_kernels.cpp:17-24): data[i] = value, element size 1..16 */
+b200_status b200_fill_array(b200_ctx* ctx, void* data, int64_t n, const void* value_host,
+                            int32_t elem_bytes)
+{
+    B200_REQUIRE(ctx != nullptr, "ctx is null");
+    B200_REQUIRE(n >= 0, "negative size");
+    if (n == 0) return B200_OK;
+    B200_REQUIRE(data && value_host, "null pointer");
+    const int grid = b200::grid_for(n, 256, ctx->num_sms, 16);
+#define B200_FILL(T)                                                                          \
+    {                                                                                         \
+        T v;                                                                                  \
+        memcpy(&v, value_host, sizeof(T));                                                    \
+        b200::convert::fill_array_kernel<T><<<grid, 256, 0, ctx->stream>>>((T*)data, n, v);   \
+    }
+    switch (elem_bytes) {
+    case 1: B200_FILL(uint8_t) break;
+    case 2: B200_FILL(uint16_t) break;
+    case 4: B200_FILL(uint32_t) break;
+    case 8: B200_FILL(uint64_t) break;
+    case 16: B200_FILL(ulonglong2) break;
+    default: B200_REQUIRE(false, "fill_array: element size must be 1, 2, 4, 8 or 16 bytes");
+    }
+#undef B200_FILL
+    B200_LAUNCH_CHECK(ctx);
+    return B200_OK;
+}
+
 
 #define B200_DEF_CONVERT_I(I, IT)                                                              \
     b200_status b200_convert_ptrs_to_idxs_##I(b200_ctx* ctx, const IT* ptrs, int64_t num_rows, \

@@ -34,17 +34,23 @@
 namespace b200 {
 namespace csr {
 
-constexpr int kRCap = 3584;                      // staged nonzeros per stage
-constexpr int kRItemsMax = 3072;                 // largest tile (merge items) the kernel accepts
-constexpr int kRRpCap = kRItemsMax / kRowW + 8;  // staged row pointers per stage
-
-template <typename V, typename I>
+// Stage geometry: CAP staged nonzeros; tiles of at most CAP - 512 merge items (so rows up to
+// 512 entries ride along with their tile), hence at most (CAP - 512) / kRowW rows.
+// Two shapes are shipped (launch_ring_auto): a deep ring (CAP 3584 x 4 stages = 197 KB in
+// flight per SM) for matrices whose gathers are local, and a shallow one (CAP 1792 x 2 stages =
+// 49 KB) for scattered gathers: the number of outstanding L1 misses is bounded by the L1 data
+// capacity (one 128-byte line per pending gather), and L1 is what shared memory leaves of the
+// SM's 228 KB -- with the deep ring every kernel of this family ran 3x slower on uniformly
+// random columns (profiles/r02c_lab_ring_first.txt).
+template <typename V, typename I, int CAP>
 struct RingStage {
-    static constexpr size_t vals_off = 0;
-    static constexpr size_t cols_off = sizeof(V) * kRCap;
-    static constexpr size_t rp_off = cols_off + sizeof(I) * kRCap;
-    static constexpr size_t bytes = (rp_off + sizeof(I) * kRRpCap + 127) & ~size_t(127);
-    static constexpr int stages = (bytes * 4 <= 200 * 1024) ? 4 : ((bytes * 3 <= 210 * 1024) ? 3 : 2);
+    static constexpr int items_max = CAP - 512;
+    static constexpr int rp_cap = items_max / kRowW + 8;
+    static constexpr size_t hdr_off = 0;  // int64 r0, p0, r1, p1 of the staged tile (r1 < 0: end)
+    static constexpr size_t vals_off = 64;
+    static constexpr size_t cols_off = vals_off + sizeof(V) * CAP;
+    static constexpr size_t rp_off = cols_off + sizeof(I) * CAP;
+    static constexpr size_t bytes = (rp_off + sizeof(I) * rp_cap + 127) & ~size_t(127);
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
@@ -99,7 +105,7 @@ __device__ __forceinline__ void dot_epilogue_any(V dot_acc, const DotArgs<V>& do
     }
 }
 
-template <typename V, typename I, int LANES, bool ADVANCED, bool DOT, int NW, int KB, bool GNA>
+template <typename V, typename I, int LANES, bool ADVANCED, bool DOT, int NW, int KB, bool GNA, int CAP, int STAGES>
 __global__ void __launch_bounds__((NW + 1) * 32, 1)
     ring_kernel(const int64_t* __restrict__ tiles, int64_t num_tiles, int64_t nnz, int64_t num_rows,
                 const I* __restrict__ row_ptrs, const I* __restrict__ col_idxs,
@@ -107,8 +113,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
                 const V* __restrict__ b, int64_t b_stride, const V* __restrict__ beta_p,
                 V* __restrict__ c, int64_t c_stride, DotArgs<V> dot)
 {
-    using S = RingStage<V, I>;
-    constexpr int STAGES = S::stages;
+    using S = RingStage<V, I, CAP>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint64_t full_bar[STAGES];
     __shared__ uint64_t empty_bar[STAGES];
@@ -134,58 +139,102 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
     V dot_acc = V(0);
 
     if (warp == NW) {
-        // ------------------------------------------------------------------ producer
-        if (lane == 0) {
-            const int64_t floor4 = nnz & ~int64_t(3);
-            const int64_t rfloor4 = (num_rows + 1) & ~int64_t(3);
-            int stage = 0;
-            uint32_t ph = 0;
-            for (int64_t t = blockIdx.x; t < num_tiles; t += G) {
+        // ------------------------------------------------------------------ producer warp
+        // The 32 lanes fetch the extents of the CTA's next 32 tiles in one go (and the batch
+        // after that while the current one is issued), lane 0 fills the stages: no dependent
+        // global load sits between two bulk copies (with one per tile the producer could not
+        // issue more than ~one tile per microsecond, profiles/r02d_lab_ring_shapes.txt).
+        const int64_t nmine = num_tiles > (int64_t)blockIdx.x ? (num_tiles - 1 - blockIdx.x) / G + 1 : 0;
+        auto load_ext = [&](int64_t k, long long (&e)[4]) {
+            e[0] = e[1] = e[2] = e[3] = 0;
+            if (k < nmine) {
+                const int64_t t = blockIdx.x + k * G;
                 const longlong2 ea = *reinterpret_cast<const longlong2*>(tiles + 2 * t);
                 const longlong2 eb = *reinterpret_cast<const longlong2*>(tiles + 2 * t + 2);
-                const int64_t r0 = ea.x, p0 = ea.y, r1 = eb.x, p1 = eb.y;
-                if (r1 <= r0) continue;
-                const int64_t a0 = p0 & ~int64_t(3);
-                int64_t pend = p1, rows_end = r1;
-                if (p1 - a0 > kRCap) {
-                    rows_end = r1 - 1;
-                    pend = (int64_t)row_ptrs[rows_end];
-                }
-                if (rows_end <= r0) continue;  // the tile is one long row: nothing is staged
-                mbar_wait(&empty_bar[stage], ph ^ 1u);
-                unsigned char* sp = smem_raw + (size_t)stage * S::bytes;
-                V* vals_s = reinterpret_cast<V*>(sp + S::vals_off);
-                I* cols_s = reinterpret_cast<I*>(sp + S::cols_off);
-                I* rp_s = reinterpret_cast<I*>(sp + S::rp_off);
-                int64_t be = (pend + 3) & ~int64_t(3);
-                if (be > floor4) be = floor4;
-                int64_t cnt = be - a0;
-                if (cnt < 0) cnt = 0;
-                // the <= 3 trailing entries of the arrays cannot be bulk-copied (16-byte units)
-                for (int64_t i = (be > a0 ? be : a0); i < pend; ++i) {
-                    vals_s[i - a0] = values[i];
-                    cols_s[i - a0] = col_idxs[i];
-                }
-                const int64_t ra0 = r0 & ~int64_t(3);
-                int64_t rbe = (rows_end + 1 + 3) & ~int64_t(3);
-                if (rbe > rfloor4) rbe = rfloor4;
-                int64_t rcnt = rbe - ra0;
-                if (rcnt < 0) rcnt = 0;
-                for (int64_t i = (rbe > ra0 ? rbe : ra0); i <= rows_end; ++i) rp_s[i - ra0] = row_ptrs[i];
-                fence_proxy_async();
-                mbar_arrive_expect_tx(&full_bar[stage],
-                                      (uint32_t)(cnt * (sizeof(V) + sizeof(I)) + rcnt * sizeof(I)));
-                if (cnt > 0) {
-                    tma_load_1d(vals_s, values + a0, (uint32_t)(cnt * sizeof(V)), &full_bar[stage], pol_first);
-                    tma_load_1d(cols_s, col_idxs + a0, (uint32_t)(cnt * sizeof(I)), &full_bar[stage], pol_first);
-                }
-                if (rcnt > 0)
-                    tma_load_1d(rp_s, row_ptrs + ra0, (uint32_t)(rcnt * sizeof(I)), &full_bar[stage], pol_first);
-                if (++stage == STAGES) {
-                    stage = 0;
-                    ph ^= 1u;
+                e[0] = ea.x;
+                e[1] = ea.y;
+                e[2] = eb.x;
+                e[3] = eb.y;
+            }
+        };
+        const int64_t floor4 = nnz & ~int64_t(3);
+        const int64_t rfloor4 = (num_rows + 1) & ~int64_t(3);
+        int stage = 0;
+        uint32_t ph = 0;
+        long long ext[4], nxt[4];
+        load_ext(lane, ext);
+        for (int64_t k0 = 0; k0 < nmine; k0 += 32) {
+            load_ext(k0 + 32 + lane, nxt);
+            const int nb = (int)((nmine - k0) < 32 ? (nmine - k0) : 32);
+            for (int i = 0; i < nb; ++i) {
+                const int64_t r0 = __shfl_sync(0xffffffffu, ext[0], i);
+                const int64_t p0 = __shfl_sync(0xffffffffu, ext[1], i);
+                const int64_t r1 = __shfl_sync(0xffffffffu, ext[2], i);
+                const int64_t p1 = __shfl_sync(0xffffffffu, ext[3], i);
+                if (r1 <= r0) continue;  // empty tile (inside a row longer than a tile)
+                if (lane == 0) {
+                    const int64_t a0 = p0 & ~int64_t(3);
+                    int64_t pend = p1, rows_end = r1;
+                    if (p1 - a0 > CAP) {  // the last row does not fit: staged without it
+                        rows_end = r1 - 1;
+                        pend = (int64_t)row_ptrs[rows_end];
+                    }
+                    mbar_wait(&empty_bar[stage], ph ^ 1u);
+                    unsigned char* sp = smem_raw + (size_t)stage * S::bytes;
+                    int64_t* hdr = reinterpret_cast<int64_t*>(sp + S::hdr_off);
+                    V* vals_s = reinterpret_cast<V*>(sp + S::vals_off);
+                    I* cols_s = reinterpret_cast<I*>(sp + S::cols_off);
+                    I* rp_s = reinterpret_cast<I*>(sp + S::rp_off);
+                    hdr[0] = r0;
+                    hdr[1] = p0;
+                    hdr[2] = r1;
+                    hdr[3] = p1;
+                    int64_t cnt = 0, rcnt = 0;
+                    const int64_t ra0 = r0 & ~int64_t(3);
+                    if (rows_end > r0) {
+                        int64_t be = (pend + 3) & ~int64_t(3);
+                        if (be > floor4) be = floor4;
+                        cnt = be - a0;
+                        if (cnt < 0) cnt = 0;
+                        // the <= 3 trailing entries of the arrays cannot be bulk-copied (16-byte units)
+                        for (int64_t q = (be > a0 ? be : a0); q < pend; ++q) {
+                            vals_s[q - a0] = values[q];
+                            cols_s[q - a0] = col_idxs[q];
+                        }
+                        int64_t rbe = (rows_end + 1 + 3) & ~int64_t(3);
+                        if (rbe > rfloor4) rbe = rfloor4;
+                        rcnt = rbe - ra0;
+                        if (rcnt < 0) rcnt = 0;
+                        for (int64_t q = (rbe > ra0 ? rbe : ra0); q <= rows_end; ++q) rp_s[q - ra0] = row_ptrs[q];
+                    }
+                    fence_proxy_async();
+                    mbar_arrive_expect_tx(&full_bar[stage],
+                                          (uint32_t)(cnt * (sizeof(V) + sizeof(I)) + rcnt * sizeof(I)));
+                    if (cnt > 0) {
+                        tma_load_1d(vals_s, values + a0, (uint32_t)(cnt * sizeof(V)), &full_bar[stage], pol_first);
+                        tma_load_1d(cols_s, col_idxs + a0, (uint32_t)(cnt * sizeof(I)), &full_bar[stage],
+                                    pol_first);
+                    }
+                    if (rcnt > 0)
+                        tma_load_1d(rp_s, row_ptrs + ra0, (uint32_t)(rcnt * sizeof(I)), &full_bar[stage],
+                                    pol_first);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        ph ^= 1u;
+                    }
                 }
             }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ext[q] = nxt[q];
+        }
+        if (lane == 0) {  // end marker
+            mbar_wait(&empty_bar[stage], ph ^ 1u);
+            int64_t* hdr = reinterpret_cast<int64_t*>(smem_raw + (size_t)stage * S::bytes + S::hdr_off);
+            hdr[0] = 0;
+            hdr[1] = 0;
+            hdr[2] = -1;
+            hdr[3] = 0;
+            mbar_arrive(&full_bar[stage]);
         }
     } else {
         // ------------------------------------------------------------------ consumers
@@ -200,17 +249,16 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
         int stage = 0;
         uint32_t ph = 0;
         int base = 0;  // passes dealt so far, modulo NW (identical in all consumer warps)
-        for (int64_t t = blockIdx.x; t < num_tiles; t += G) {
-            const longlong2 ea = *reinterpret_cast<const longlong2*>(tiles + 2 * t);
-            const longlong2 eb = *reinterpret_cast<const longlong2*>(tiles + 2 * t + 2);
-            const int64_t r0 = ea.x, p0 = ea.y, r1 = eb.x, p1 = eb.y;
-            if (r1 <= r0) continue;
+        for (;;) {
+            mbar_wait(&full_bar[stage], ph);
+            const unsigned char* sp = smem_raw + (size_t)stage * S::bytes;
+            const int64_t* hdr = reinterpret_cast<const int64_t*>(sp + S::hdr_off);
+            const int64_t r0 = hdr[0], p0 = hdr[1], r1 = hdr[2], p1 = hdr[3];
+            if (r1 < 0) break;
             const int64_t a0 = p0 & ~int64_t(3);
-            const bool long_last = (p1 - a0) > kRCap;
+            const bool long_last = (p1 - a0) > CAP;
             const int64_t rows_end = long_last ? r1 - 1 : r1;
             if (rows_end > r0) {
-                mbar_wait(&full_bar[stage], ph);
-                const unsigned char* sp = smem_raw + (size_t)stage * S::bytes;
                 const V* vals_s = reinterpret_cast<const V*>(sp + S::vals_off);
                 const I* cols_s = reinterpret_cast<const I*>(sp + S::cols_off);
                 const I* rp_l = reinterpret_cast<const I*>(sp + S::rp_off) + (r0 & int64_t(3));
@@ -266,12 +314,12 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
                     }
                 }
                 base = (base + npass) % NW;
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty_bar[stage]);
-                if (++stage == STAGES) {
-                    stage = 0;
-                    ph ^= 1u;
-                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[stage]);
+            if (++stage == STAGES) {
+                stage = 0;
+                ph ^= 1u;
             }
             if (long_last) {
                 // the tile's last row does not fit a stage: all consumer warps stream it from
@@ -304,16 +352,32 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
     if (DOT) dot_epilogue_any(dot_acc, dot, red, &is_last);
 }
 
-template <typename V, typename I, int LANES, bool ADVANCED, bool DOT, int NW, int KB, bool GNA>
+// shared-memory size + a carve-out that leaves the rest of the SM's 228 KB to L1
+template <typename K>
+b200_status set_smem_exact(K kernel, size_t bytes)
+{
+    static thread_local const void* done = nullptr;
+    if (done != (const void*)kernel) {
+        B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        int pct = (int)((bytes + 4096) * 100 / (228 * 1024)) + 1;
+        if (pct > 100) pct = 100;
+        B200_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+        done = (const void*)kernel;
+    }
+    return B200_OK;
+}
+
+template <typename V, typename I, int LANES, bool ADVANCED, bool DOT, int NW, int KB, bool GNA, int CAP, int STAGES>
 b200_status launch_ring(b200_ctx* ctx, int64_t num_tiles, const int64_t* tiles, int64_t nnz,
                         int64_t num_rows, const I* row_ptrs, const I* col_idxs, const V* values,
                         const V* alpha, const V* b, int64_t b_stride, const V* beta, V* c,
                         int64_t c_stride, DotArgs<V> dot, int grid)
 {
-    using S = RingStage<V, I>;
-    constexpr size_t smem = S::bytes * S::stages;
-    auto k = ring_kernel<V, I, LANES, ADVANCED, DOT, NW, KB, GNA>;
-    b200_status st = set_smem(k, smem);
+    using S = RingStage<V, I, CAP>;
+    constexpr size_t smem = S::bytes * STAGES;
+    static_assert(smem <= 227 * 1024, "ring does not fit the SM's shared memory");
+    auto k = ring_kernel<V, I, LANES, ADVANCED, DOT, NW, KB, GNA, CAP, STAGES>;
+    b200_status st = set_smem_exact(k, smem);
     if (st != B200_OK) return st;
     k<<<grid, (NW + 1) * 32, smem, ctx->stream>>>(tiles, num_tiles, nnz, num_rows, row_ptrs, col_idxs,
                                                   values, alpha, b, b_stride, beta, c, c_stride, dot);

@@ -564,6 +564,11 @@ B200_DECL_SPMV_DOT(f32, float, i64, int64_t)
  * (reference/components/format_conversion_kernels.cpp) and csr::extract_diagonal
  * (core/matrix/csr_kernels.hpp, reference/matrix/csr_kernels.cpp).
  * ------------------------------------------------------------------------- */
+/* components::fill_array (core/components/fill_array_kernels.hpp:22-25): data[i] = *value_host
+ * for n elements of elem_bytes (1, 2, 4, 8 or 16) bytes each; the value is read on the host
+ * at call time. */
+b200_status b200_fill_array(b200_ctx* ctx, void* data, int64_t n, const void* value_host,
+                            int32_t elem_bytes);
 #define B200_DECL_CONVERT_I(I, IT)                                                             \
     b200_status b200_convert_ptrs_to_idxs_##I(b200_ctx* ctx, const IT* ptrs, int64_t num_rows, \
                                               IT* idxs);                                       \
