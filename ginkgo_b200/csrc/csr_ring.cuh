@@ -47,7 +47,7 @@ struct RingStage {
     static constexpr int items_max = CAP - 512;
     static constexpr int rp_cap = items_max / kRowW + 8;
     static constexpr size_t hdr_off = 0;  // int64 r0, p0, r1, p1 of the staged tile (r1 < 0: end)
-    static constexpr size_t vals_off = 64;
+    static constexpr size_t vals_off = 128;
     static constexpr size_t cols_off = vals_off + sizeof(V) * CAP;
     static constexpr size_t rp_off = cols_off + sizeof(I) * CAP;
     static constexpr size_t bytes = (rp_off + sizeof(I) * rp_cap + 127) & ~size_t(127);
@@ -105,8 +105,9 @@ __device__ __forceinline__ void dot_epilogue_any(V dot_acc, const DotArgs<V>& do
     }
 }
 
-template <typename V, typename I, int LANES, bool ADVANCED, bool DOT, int NW, int KB, bool GNA, int CAP, int STAGES>
-__global__ void __launch_bounds__((NW + 1) * 32, 1)
+template <typename V, typename I, int LANES, bool ADVANCED, bool DOT, int NW, int KB, bool GNA, int CAP, int STAGES,
+          int NP>
+__global__ void __launch_bounds__((NW + NP) * 32, 1)
     ring_kernel(const int64_t* __restrict__ tiles, int64_t num_tiles, int64_t nnz, int64_t num_rows,
                 const I* __restrict__ row_ptrs, const I* __restrict__ col_idxs,
                 const V* __restrict__ values, const V* __restrict__ alpha_p,
@@ -138,103 +139,90 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
     const uint64_t pol_first = policy_evict_first();
     V dot_acc = V(0);
 
-    if (warp == NW) {
-        // ------------------------------------------------------------------ producer warp
-        // The 32 lanes fetch the extents of the CTA's next 32 tiles in one go (and the batch
-        // after that while the current one is issued), lane 0 fills the stages: no dependent
-        // global load sits between two bulk copies (with one per tile the producer could not
-        // issue more than ~one tile per microsecond, profiles/r02d_lab_ring_shapes.txt).
-        const int64_t nmine = num_tiles > (int64_t)blockIdx.x ? (num_tiles - 1 - blockIdx.x) / G + 1 : 0;
-        auto load_ext = [&](int64_t k, long long (&e)[4]) {
-            e[0] = e[1] = e[2] = e[3] = 0;
-            if (k < nmine) {
-                const int64_t t = blockIdx.x + k * G;
-                const longlong2 ea = *reinterpret_cast<const longlong2*>(tiles + 2 * t);
-                const longlong2 eb = *reinterpret_cast<const longlong2*>(tiles + 2 * t + 2);
-                e[0] = ea.x;
-                e[1] = ea.y;
-                e[2] = eb.x;
-                e[3] = eb.y;
-            }
-        };
-        const int64_t floor4 = nnz & ~int64_t(3);
-        const int64_t rfloor4 = (num_rows + 1) & ~int64_t(3);
-        int stage = 0;
-        uint32_t ph = 0;
-        long long ext[4], nxt[4];
-        load_ext(lane, ext);
-        for (int64_t k0 = 0; k0 < nmine; k0 += 32) {
-            load_ext(k0 + 32 + lane, nxt);
-            const int nb = (int)((nmine - k0) < 32 ? (nmine - k0) : 32);
-            for (int i = 0; i < nb; ++i) {
-                const int64_t r0 = __shfl_sync(0xffffffffu, ext[0], i);
-                const int64_t p0 = __shfl_sync(0xffffffffu, ext[1], i);
-                const int64_t r1 = __shfl_sync(0xffffffffu, ext[2], i);
-                const int64_t p1 = __shfl_sync(0xffffffffu, ext[3], i);
-                if (r1 <= r0) continue;  // empty tile (inside a row longer than a tile)
-                if (lane == 0) {
-                    const int64_t a0 = p0 & ~int64_t(3);
-                    int64_t pend = p1, rows_end = r1;
-                    if (p1 - a0 > CAP) {  // the last row does not fit: staged without it
-                        rows_end = r1 - 1;
-                        pend = (int64_t)row_ptrs[rows_end];
-                    }
-                    mbar_wait(&empty_bar[stage], ph ^ 1u);
-                    unsigned char* sp = smem_raw + (size_t)stage * S::bytes;
-                    int64_t* hdr = reinterpret_cast<int64_t*>(sp + S::hdr_off);
-                    V* vals_s = reinterpret_cast<V*>(sp + S::vals_off);
-                    I* cols_s = reinterpret_cast<I*>(sp + S::cols_off);
-                    I* rp_s = reinterpret_cast<I*>(sp + S::rp_off);
-                    hdr[0] = r0;
-                    hdr[1] = p0;
-                    hdr[2] = r1;
-                    hdr[3] = p1;
-                    int64_t cnt = 0, rcnt = 0;
-                    const int64_t ra0 = r0 & ~int64_t(3);
-                    if (rows_end > r0) {
-                        int64_t be = (pend + 3) & ~int64_t(3);
+    static_assert(STAGES % NP == 0, "every producer warp owns STAGES / NP stages");
+    // tiles of this CTA, in order: t = blockIdx.x + j * G; tile j lives in stage j % STAGES
+    const int64_t nmine = num_tiles > (int64_t)blockIdx.x ? (num_tiles - 1 - blockIdx.x) / G + 1 : 0;
+
+    if (warp >= NW) {
+        // ------------------------------------------------------------------ producer warps
+        // Producer w fills the stages of tiles j = w, w + NP, ... (one elected lane; the extents
+        // of its next two tiles are already in registers, so no dependent global load sits between
+        // two bulk copies).  The first measurements had ONE lane walk all tiles with a dependent
+        // extent load per tile and ~300 instructions per tile: 1.4 us per tile whatever its size,
+        // consumers starved on the full barrier (profiles/r02f_ring_banded.txt).
+        if (lane == 0) {
+            const int w = warp - NW;
+            const int64_t floor4 = nnz & ~int64_t(3);
+            const int64_t rfloor4 = (num_rows + 1) & ~int64_t(3);
+            auto load_ext = [&](int64_t j, longlong2& ea, longlong2& eb) {
+                if (j < nmine) {
+                    const int64_t t = blockIdx.x + j * G;
+                    ea = *reinterpret_cast<const longlong2*>(tiles + 2 * t);
+                    eb = *reinterpret_cast<const longlong2*>(tiles + 2 * t + 2);
+                }
+            };
+            longlong2 a0e = {0, 0}, b0e = {0, 0}, a1e = {0, 0}, b1e = {0, 0}, a2e = {0, 0}, b2e = {0, 0};
+            load_ext(w, a0e, b0e);
+            load_ext(w + NP, a1e, b1e);
+            int stage = w % STAGES;
+            uint32_t ph = 0;
+            for (int64_t j = w; j < nmine; j += NP) {
+                load_ext(j + 2 * NP, a2e, b2e);
+                const int64_t r0 = a0e.x, p0 = a0e.y, r1 = b0e.x, p1 = b0e.y;
+                const int64_t a0 = p0 & ~int64_t(3);
+                const int64_t ra0 = r0 & ~int64_t(3);
+                int64_t pend = p1, rows_end = r1;
+                if (r1 > r0 && p1 - a0 > CAP) {  // the last row does not fit: staged without it
+                    rows_end = r1 - 1;
+                    pend = (int64_t)row_ptrs[rows_end];
+                }
+                mbar_wait(&empty_bar[stage], ph ^ 1u);
+                unsigned char* sp = smem_raw + (size_t)stage * S::bytes;
+                longlong2* hdr = reinterpret_cast<longlong2*>(sp + S::hdr_off);
+                hdr[0] = a0e;
+                hdr[1] = b0e;
+                uint32_t cnt = 0, rcnt = 0;
+                if (rows_end > r0) {
+                    int64_t be = (pend + 3) & ~int64_t(3);
+                    int64_t rbe = (rows_end + 4) & ~int64_t(3);
+                    if (be > floor4 || rbe > rfloor4) {
+                        // the <= 3 trailing entries of the arrays cannot be bulk-copied (16-byte
+                        // units): copied by hand (last tile of the matrix only)
+                        V* vals_s = reinterpret_cast<V*>(sp + S::vals_off);
+                        I* cols_s = reinterpret_cast<I*>(sp + S::cols_off);
+                        I* rp_s = reinterpret_cast<I*>(sp + S::rp_off);
                         if (be > floor4) be = floor4;
-                        cnt = be - a0;
-                        if (cnt < 0) cnt = 0;
-                        // the <= 3 trailing entries of the arrays cannot be bulk-copied (16-byte units)
+                        if (rbe > rfloor4) rbe = rfloor4;
                         for (int64_t q = (be > a0 ? be : a0); q < pend; ++q) {
                             vals_s[q - a0] = values[q];
                             cols_s[q - a0] = col_idxs[q];
                         }
-                        int64_t rbe = (rows_end + 1 + 3) & ~int64_t(3);
-                        if (rbe > rfloor4) rbe = rfloor4;
-                        rcnt = rbe - ra0;
-                        if (rcnt < 0) rcnt = 0;
                         for (int64_t q = (rbe > ra0 ? rbe : ra0); q <= rows_end; ++q) rp_s[q - ra0] = row_ptrs[q];
                     }
-                    fence_proxy_async();
-                    mbar_arrive_expect_tx(&full_bar[stage],
-                                          (uint32_t)(cnt * (sizeof(V) + sizeof(I)) + rcnt * sizeof(I)));
-                    if (cnt > 0) {
-                        tma_load_1d(vals_s, values + a0, (uint32_t)(cnt * sizeof(V)), &full_bar[stage], pol_first);
-                        tma_load_1d(cols_s, col_idxs + a0, (uint32_t)(cnt * sizeof(I)), &full_bar[stage],
-                                    pol_first);
-                    }
-                    if (rcnt > 0)
-                        tma_load_1d(rp_s, row_ptrs + ra0, (uint32_t)(rcnt * sizeof(I)), &full_bar[stage],
-                                    pol_first);
-                    if (++stage == STAGES) {
-                        stage = 0;
-                        ph ^= 1u;
-                    }
+                    cnt = be > a0 ? (uint32_t)(be - a0) : 0u;
+                    rcnt = rbe > ra0 ? (uint32_t)(rbe - ra0) : 0u;
                 }
+                fence_proxy_async();
+                mbar_arrive_expect_tx(&full_bar[stage],
+                                      cnt * (uint32_t)(sizeof(V) + sizeof(I)) + rcnt * (uint32_t)sizeof(I));
+                if (cnt > 0) {
+                    tma_load_1d(sp + S::vals_off, values + a0, cnt * (uint32_t)sizeof(V), &full_bar[stage], pol_first);
+                    tma_load_1d(sp + S::cols_off, col_idxs + a0, cnt * (uint32_t)sizeof(I), &full_bar[stage],
+                                pol_first);
+                }
+                if (rcnt > 0)
+                    tma_load_1d(sp + S::rp_off, row_ptrs + ra0, rcnt * (uint32_t)sizeof(I), &full_bar[stage],
+                                pol_first);
+                stage += NP;
+                if (stage >= STAGES) {
+                    stage -= STAGES;
+                    ph ^= 1u;
+                }
+                a0e = a1e;
+                b0e = b1e;
+                a1e = a2e;
+                b1e = b2e;
             }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) ext[q] = nxt[q];
-        }
-        if (lane == 0) {  // end marker
-            mbar_wait(&empty_bar[stage], ph ^ 1u);
-            int64_t* hdr = reinterpret_cast<int64_t*>(smem_raw + (size_t)stage * S::bytes + S::hdr_off);
-            hdr[0] = 0;
-            hdr[1] = 0;
-            hdr[2] = -1;
-            hdr[3] = 0;
-            mbar_arrive(&full_bar[stage]);
         }
     } else {
         // ------------------------------------------------------------------ consumers
@@ -249,14 +237,13 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
         int stage = 0;
         uint32_t ph = 0;
         int base = 0;  // passes dealt so far, modulo NW (identical in all consumer warps)
-        for (;;) {
+        for (int64_t j = 0; j < nmine; ++j) {
             mbar_wait(&full_bar[stage], ph);
             const unsigned char* sp = smem_raw + (size_t)stage * S::bytes;
             const int64_t* hdr = reinterpret_cast<const int64_t*>(sp + S::hdr_off);
             const int64_t r0 = hdr[0], p0 = hdr[1], r1 = hdr[2], p1 = hdr[3];
-            if (r1 < 0) break;
             const int64_t a0 = p0 & ~int64_t(3);
-            const bool long_last = (p1 - a0) > CAP;
+            const bool long_last = r1 > r0 && (p1 - a0) > CAP;
             const int64_t rows_end = long_last ? r1 - 1 : r1;
             if (rows_end > r0) {
                 const V* vals_s = reinterpret_cast<const V*>(sp + S::vals_off);
@@ -367,7 +354,8 @@ b200_status set_smem_exact(K kernel, size_t bytes)
     return B200_OK;
 }
 
-template <typename V, typename I, int LANES, bool ADVANCED, bool DOT, int NW, int KB, bool GNA, int CAP, int STAGES>
+template <typename V, typename I, int LANES, bool ADVANCED, bool DOT, int NW, int KB, bool GNA, int CAP, int STAGES,
+          int NP>
 b200_status launch_ring(b200_ctx* ctx, int64_t num_tiles, const int64_t* tiles, int64_t nnz,
                         int64_t num_rows, const I* row_ptrs, const I* col_idxs, const V* values,
                         const V* alpha, const V* b, int64_t b_stride, const V* beta, V* c,
@@ -376,10 +364,10 @@ b200_status launch_ring(b200_ctx* ctx, int64_t num_tiles, const int64_t* tiles, 
     using S = RingStage<V, I, CAP>;
     constexpr size_t smem = S::bytes * STAGES;
     static_assert(smem <= 227 * 1024, "ring does not fit the SM's shared memory");
-    auto k = ring_kernel<V, I, LANES, ADVANCED, DOT, NW, KB, GNA, CAP, STAGES>;
+    auto k = ring_kernel<V, I, LANES, ADVANCED, DOT, NW, KB, GNA, CAP, STAGES, NP>;
     b200_status st = set_smem_exact(k, smem);
     if (st != B200_OK) return st;
-    k<<<grid, (NW + 1) * 32, smem, ctx->stream>>>(tiles, num_tiles, nnz, num_rows, row_ptrs, col_idxs,
+    k<<<grid, (NW + NP) * 32, smem, ctx->stream>>>(tiles, num_tiles, nnz, num_rows, row_ptrs, col_idxs,
                                                   values, alpha, b, b_stride, beta, c, c_stride, dot);
     B200_LAUNCH_CHECK(ctx);
     return B200_OK;

@@ -394,6 +394,38 @@ b200_status plan_tune(b200_ctx* ctx, b200_csr_plan* plan, int64_t num_rows, int6
 
 extern "C" {
 
+/* csr::is_sorted_by_column_index (core/matrix/csr_kernels.hpp; reference/matrix/csr_kernels.cpp
+ * `is_sorted_by_column_index`): 1 iff every row's column indices are non-decreasing.  Blocking
+ * (the reference returns the flag through a host bool as well). */
+#define B200_DEF_IS_SORTED(I, IT)                                                                \
+    b200_status b200_csr_is_sorted_by_column_index_##I(b200_ctx* ctx, int64_t num_rows,          \
+                                                       const IT* row_ptrs, const IT* col_idxs,   \
+                                                       int32_t* is_sorted_host)                  \
+    {                                                                                            \
+        B200_REQUIRE(ctx && is_sorted_host, "null argument");                                    \
+        *is_sorted_host = 1;                                                                     \
+        if (num_rows <= 0) return B200_OK;                                                       \
+        B200_REQUIRE(row_ptrs != nullptr, "null pointer");                                       \
+        int* flag = (int*)ctx->scratch(sizeof(int));                                             \
+        if (!flag) {                                                                             \
+            b200::set_error("scratch allocation failed");                                        \
+            return B200_ERR_ALLOC;                                                               \
+        }                                                                                        \
+        B200_CUDA_CHECK(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));                     \
+        b200::csr::unsorted_rows_kernel<IT><<<(unsigned)b200::ceildiv(num_rows, 256), 256, 0,    \
+                                              ctx->stream>>>(num_rows, row_ptrs, col_idxs, flag); \
+        B200_LAUNCH_CHECK(ctx);                                                                  \
+        int unsorted = 0;                                                                        \
+        B200_CUDA_CHECK(cudaMemcpyAsync(&unsorted, flag, sizeof(int), cudaMemcpyDeviceToHost,    \
+                                        ctx->stream));                                           \
+        B200_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));                                     \
+        *is_sorted_host = unsorted ? 0 : 1;                                                      \
+        return B200_OK;                                                                          \
+    }
+B200_DEF_IS_SORTED(i32, int32_t)
+B200_DEF_IS_SORTED(i64, int64_t)
+#undef B200_DEF_IS_SORTED
+
 int b200_csr_plan_variant(const b200_csr_plan* plan) { return plan ? plan->variant : -1; }
 int b200_csr_plan_parts(const b200_csr_plan* plan) { return plan ? plan->parts : 0; }
 

@@ -391,9 +391,25 @@ GKO_DECLARE_CSR_EXTRACT_DIAGONAL(ValueType, IndexType)
     B2(B2_SELECT_VI(ValueType, IndexType, b200_csr_extract_diagonal, ctx_of(exec), n, orig->get_const_row_ptrs(),
                     orig->get_const_col_idxs(), orig->get_const_values(), diag->get_values()));
 }
+template <typename ValueType, typename IndexType>
+GKO_DECLARE_CSR_SORT_BY_COLUMN_INDEX(ValueType, IndexType)
+{
+    B2(B2_SELECT_VI(ValueType, IndexType, b200_csr_sort_by_column_index, ctx_of(exec), rows(to_sort),
+                    to_sort->get_const_row_ptrs(), to_sort->get_col_idxs(), to_sort->get_values()));
+}
+template <typename ValueType, typename IndexType>
+GKO_DECLARE_CSR_IS_SORTED_BY_COLUMN_INDEX(ValueType, IndexType)
+{
+    int32_t flag = 1;
+    B2(B2_SELECT_I(IndexType, b200_csr_is_sorted_by_column_index, ctx_of(exec), rows(to_check),
+                   to_check->get_const_row_ptrs(), to_check->get_const_col_idxs(), &flag));
+    *is_sorted = flag != 0;
+}
 #define B2_INST_CSR(V, I)                                       \
     template GKO_DECLARE_CSR_SPMV_KERNEL(V, V, V, I);           \
     template GKO_DECLARE_CSR_ADVANCED_SPMV_KERNEL(V, V, V, I);  \
+    template GKO_DECLARE_CSR_SORT_BY_COLUMN_INDEX(V, I);        \
+    template GKO_DECLARE_CSR_IS_SORTED_BY_COLUMN_INDEX(V, I);   \
     template GKO_DECLARE_CSR_EXTRACT_DIAGONAL(V, I)
 B2_INST_CSR(double, int32);
 B2_INST_CSR(double, int64);

@@ -633,6 +633,14 @@ B200_DECL_EXTRACT_DIAG(f32, float, i64, int64_t)
                                                         VT* values);
 B200_DECL_CONVERT_FMT_I(i32, int32_t)
 B200_DECL_CONVERT_FMT_I(i64, int64_t)
+/* csr::is_sorted_by_column_index (core/matrix/csr_kernels.hpp; reference/matrix/csr_kernels.cpp):
+ * *is_sorted_host = 1 iff every row's column indices are non-decreasing; blocking. */
+b200_status b200_csr_is_sorted_by_column_index_i32(b200_ctx* ctx, int64_t num_rows,
+                                                   const int32_t* row_ptrs, const int32_t* col_idxs,
+                                                   int32_t* is_sorted_host);
+b200_status b200_csr_is_sorted_by_column_index_i64(b200_ctx* ctx, int64_t num_rows,
+                                                   const int64_t* row_ptrs, const int64_t* col_idxs,
+                                                   int32_t* is_sorted_host);
 B200_DECL_CONVERT_FMT(f64, double, i32, int32_t)
 B200_DECL_CONVERT_FMT(f64, double, i64, int64_t)
 B200_DECL_CONVERT_FMT(f32, float, i32, int32_t)

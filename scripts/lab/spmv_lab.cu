@@ -66,6 +66,36 @@ __global__ void gen_random(int64_t n, int64_t ncols, int64_t col0, int* rp, int*
         va[r * PR + k] = (V)unit(hash3(101, r, k));
     }
 }
+// cfg2a: the rows of cfg2 restricted to the columns [0, ncols/2): what the first launch of the
+// 2-block column-blocked copy streams (variable row lengths, 40 MB of x)
+template <typename V, int PR>
+__global__ void gen_random_half(int64_t n, int64_t ncols, const int* rp, int* cnt, int* ci, V* va)
+{
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    int64_t c[PR];
+    const int64_t span = ncols - PR + 1;
+    for (int k = 0; k < PR; ++k) c[k] = (int64_t)(hash3(1, r, k) % (uint64_t)span);
+    for (int i = 1; i < PR; ++i) {
+        int64_t v = c[i];
+        int j = i - 1;
+        while (j >= 0 && c[j] > v) {
+            c[j + 1] = c[j];
+            --j;
+        }
+        c[j + 1] = v;
+    }
+    int m = 0;
+    for (int k = 0; k < PR; ++k)
+        if (c[k] + k < ncols / 2) {
+            if (rp) {
+                ci[rp[r] + m] = (int)(c[k] + k);
+                va[rp[r] + m] = (V)unit(hash3(101, r, k));
+            }
+            ++m;
+        }
+    if (cnt) cnt[r] = m;
+}
 template <typename V>
 __global__ void gen_band_fill(int64_t n, int hb, const int* rp, int* ci, V* va)
 {
@@ -136,6 +166,26 @@ Mat<V> make_matrix(const std::string& name)
         if (pr == 15) gen_random<V, 15><<<grid, T>>>(m.n, m.ncols, 0, m.rp, m.ci, m.va, false);
         if (pr == 8) gen_random<V, 8><<<grid, T>>>(m.n, m.ncols / 2, 0, m.rp, m.ci, m.va, false);
         if (pr == 20) gen_random<V, 20><<<grid, T>>>(m.n, m.ncols, 0, m.rp, m.ci, m.va, false);
+    } else if (name == "cfg2a") {
+        m.n = m.ncols = 10000000;
+        int* cnt;
+        CK(cudaMalloc(&cnt, m.n * sizeof(int)));
+        gen_random_half<V, 15><<<(int)((m.n + T - 1) / T), T>>>(m.n, m.ncols, nullptr, cnt, nullptr, nullptr);
+        std::vector<int> h(m.n), rp(m.n + 1);
+        CK(cudaMemcpy(h.data(), cnt, m.n * sizeof(int), cudaMemcpyDeviceToHost));
+        int64_t p = 0;
+        for (int64_t r = 0; r < m.n; ++r) {
+            rp[r] = (int)p;
+            p += h[r];
+        }
+        rp[m.n] = (int)p;
+        m.nnz = p;
+        CK(cudaMalloc(&m.rp, (m.n + 1) * sizeof(int)));
+        CK(cudaMalloc(&m.ci, m.nnz * sizeof(int)));
+        CK(cudaMalloc(&m.va, m.nnz * sizeof(V)));
+        CK(cudaMemcpy(m.rp, rp.data(), (m.n + 1) * sizeof(int), cudaMemcpyHostToDevice));
+        gen_random_half<V, 15><<<(int)((m.n + T - 1) / T), T>>>(m.n, m.ncols, m.rp, nullptr, m.ci, m.va);
+        CK(cudaFree(cnt));
     } else if (name == "banded") {
         m.n = m.ncols = 10000000;
         const int hb = 7;
@@ -254,6 +304,8 @@ struct Bench {
     template <typename F>
     void run(const char* label, F f)
     {
+        if (const char* only = getenv("LAB_ONLY"))
+            if (!strstr(label, only)) return;
         CK(cudaMemset(y, 0xff, m.n * sizeof(V)));
         CK(cudaMemset(cnt, 0, 8));
         f();
@@ -299,7 +351,7 @@ void group_base(const std::string& name)
 }
 
 // ------------------------------------------------------------------------------ group: ring
-template <typename V, int NW, int KB, bool GNA, int CAP, int STAGES>
+template <typename V, int NW, int KB, bool GNA, int CAP, int STAGES, int NP>
 void ring_case(Bench<V>& B, int64_t items = CAP - 512)
 {
     auto& m = B.m;
@@ -309,11 +361,11 @@ void ring_case(Bench<V>& B, int64_t items = CAP - 512)
     fill_plan<int>(B.ctx, m.n, m.nnz, m.rp, nt, tiles, items);
     CK(cudaDeviceSynchronize());
     char label[128];
-    snprintf(label, sizeof label, "ring NW=%d KB=%d GNA=%d CAP=%d x%d items=%lld", NW, KB, (int)GNA, CAP, STAGES,
-             (long long)items);
+    snprintf(label, sizeof label, "ring NW=%d NP=%d KB=%d GNA=%d CAP=%d x%d items=%lld", NW, NP, KB, (int)GNA, CAP,
+             STAGES, (long long)items);
     const int grid = (int)std::min<int64_t>(nt, B.ctx->num_sms);
     B.run(label, [&] {
-        launch_ring<V, int, 1, false, false, NW, KB, GNA, CAP, STAGES>(
+        launch_ring<V, int, 1, false, false, NW, KB, GNA, CAP, STAGES, NP>(
             B.ctx, nt, tiles, m.nnz, m.n, m.rp, m.ci, m.va, (const V*)nullptr, B.x, 1, (const V*)nullptr, B.y, 1,
             DotArgs<V>{}, grid);
     });
@@ -325,26 +377,27 @@ void group_ring(const std::string& name)
 {
     Bench<V> B;
     B.init(name);
-    // deep ring (structured matrices)
-    ring_case<V, 16, 8, false, 3584, 4>(B);
-    ring_case<V, 24, 8, false, 3584, 4>(B);
-    ring_case<V, 30, 8, false, 3584, 4>(B);
-    ring_case<V, 16, 8, false, 3584, 3>(B);
-    ring_case<V, 16, 8, false, 2560, 4>(B);
-    ring_case<V, 24, 8, false, 2560, 5>(B);
-    ring_case<V, 24, 8, false, 1792, 6>(B);
-    // shallow ring (scattered gathers: leave the SM's memory to L1)
-    ring_case<V, 16, 8, false, 1792, 2>(B);
-    ring_case<V, 16, 8, true, 1792, 2>(B);
-    ring_case<V, 24, 8, true, 1792, 2>(B);
-    ring_case<V, 16, 16, true, 1792, 2>(B);
-    ring_case<V, 16, 8, true, 1792, 3>(B);
-    ring_case<V, 24, 8, true, 1792, 3>(B);
-    ring_case<V, 16, 8, true, 1024, 3>(B);
-    ring_case<V, 16, 8, true, 1024, 4>(B);
-    ring_case<V, 16, 8, true, 2560, 2>(B);
-    ring_case<V, 24, 8, true, 2560, 2>(B);
-    ring_case<V, 16, 8, true, 3584, 2>(B);
+    // deep rings (structured matrices)
+    ring_case<V, 16, 8, false, 3584, 4, 1>(B);
+    ring_case<V, 16, 8, false, 3584, 4, 2>(B);
+    ring_case<V, 16, 8, false, 3584, 4, 4>(B);
+    ring_case<V, 24, 8, false, 3584, 4, 2>(B);
+    ring_case<V, 24, 8, false, 3584, 4, 4>(B);
+    ring_case<V, 28, 8, false, 3584, 4, 4>(B);
+    ring_case<V, 24, 8, false, 2560, 4, 4>(B);
+    ring_case<V, 24, 8, false, 1792, 8, 4>(B);
+    ring_case<V, 24, 8, false, 1792, 6, 2>(B);
+    // shallower rings (scattered gathers: leave the SM's memory to L1)
+    ring_case<V, 16, 8, true, 3584, 2, 2>(B);
+    ring_case<V, 16, 8, false, 3584, 2, 2>(B);
+    ring_case<V, 16, 8, true, 2560, 2, 2>(B);
+    ring_case<V, 16, 8, true, 1792, 2, 2>(B);
+    ring_case<V, 16, 8, true, 1792, 4, 4>(B);
+    ring_case<V, 24, 8, true, 1792, 4, 4>(B);
+    ring_case<V, 16, 16, true, 1792, 4, 4>(B);
+    ring_case<V, 16, 8, true, 1024, 4, 4>(B);
+    ring_case<V, 16, 8, true, 1024, 8, 4>(B);
+    ring_case<V, 24, 8, true, 1024, 8, 4>(B);
 }
 
 // ------------------------------------------------------------------------------ group: micro
