@@ -28,7 +28,7 @@ def preprocess(path, include_dirs=()):
 
 
 _DECL = re.compile(
-    r"(?:^|(?<=[;}]))\s*((?:const\s+)?(?:void|char|int64_t|int32_t|b200_status|int)\s*\**)\s*(\w+)\s*\(([^()]*)\)\s*(;|\{)",
+    r"(?:^|(?<=[;}]))\s*((?:const\s+)?(?:void|char|int64_t|int32_t|b200_status|int|double)\s*\**)\s*(\w+)\s*\(([^()]*)\)\s*(;|\{)",
     re.M)
 
 

@@ -168,9 +168,18 @@ class Csr(_SparseBase):
             _lib.check(fn(self.exec.ctx, self.size[0], self.nnz, self.row_ptrs.data_ptr(),
                           ctypes.byref(p)))
             self._plan = p
+            # this object owns the values tensor: callers that write into it call values_changed()
+            self.exec._l.b200_csr_plan_allow_value_copy(p, 1)
             self.exec.run("b200_csr_plan_tune_%s_%s" % (self.vt, self.it), p, self.size[0],
                           self.size[1], self.nnz, self.row_ptrs, self.col_idxs, self.values)
         return self._plan
+
+    def values_changed(self):
+        """call after writing into .values in place: refreshes the plan's column-blocked value copy
+        (b200_csr_plan_refresh_values_*; a no-op when the plan holds no copy)"""
+        if self._plan is not None:
+            self.exec.run("b200_csr_plan_refresh_values_%s_%s" % (self.vt, self.it), self._plan,
+                          self.size[0], self.row_ptrs, self.values)
 
     def _apply_impl(self, alpha, b, beta, x):
         sfx = "_%s_%s" % (self.vt, self.it)

@@ -1,5 +1,5 @@
 // C-ABI entry points of the CSR (and COO-on-CSR) SpMV; kernels in csr_kernels.cuh.
-#include "csr_kernels.cuh"
+#include "csr_launch.cuh"
 #include "scan.cuh"
 
 namespace b200 {
@@ -34,33 +34,32 @@ b200_status spmv_impl(b200_ctx* ctx, const b200_csr_plan* plan, int64_t num_rows
         for (int p = 0; p < plan->parts; ++p) {
             const b200_csr_plan* sub = plan->part_plan[p];
             const Variant v = pick_variant(plan->part_cols[p], plan->part_vals[p], sub);
-            const bool w = v != kSlab && v != kTma;
+            int64_t nt = 0;
+            const int64_t* pt = plan_tiles(sub, v, &nt);
             b200_status st;
             if (p == 0 && !ADVANCED)
                 st = launch_slab<V, I, false, false>(
-                    ctx, sub->lanes, v, w ? sub->num_wtiles : sub->num_tiles,
-                    w ? sub->wtiles : sub->tiles, plan->part_nnz[p], (const I*)plan->part_row_ptrs[p],
+                    ctx, sub->lanes, v, nt, pt, plan->part_nnz[p], (const I*)plan->part_row_ptrs[p],
                     (const I*)plan->part_cols[p], (const V*)plan->part_vals[p], nullptr, b, b_stride,
-                    nullptr, c, c_stride);
+                    nullptr, c, c_stride, DotArgs<V>{}, num_rows);
             else
                 st = launch_slab<V, I, true, false>(
-                    ctx, sub->lanes, v, w ? sub->num_wtiles : sub->num_tiles,
-                    w ? sub->wtiles : sub->tiles, plan->part_nnz[p], (const I*)plan->part_row_ptrs[p],
+                    ctx, sub->lanes, v, nt, pt, plan->part_nnz[p], (const I*)plan->part_row_ptrs[p],
                     (const I*)plan->part_cols[p], (const V*)plan->part_vals[p],
                     ADVANCED ? alpha : ones, b, b_stride, (ADVANCED && p == 0) ? beta : ones + 1, c,
-                    c_stride);
+                    c_stride, DotArgs<V>{}, num_rows);
             if (st != B200_OK) return st;
         }
         return B200_OK;
     }
     const Variant variant = pick_variant(col_idxs, values, plan);
-    const int64_t num_tiles = variant_tiles(variant, num_rows, nnz);
+    int64_t num_tiles = variant_tiles(variant, num_rows, nnz);
     const int64_t* tiles = nullptr;
     int lanes;
     if (plan) {
         B200_REQUIRE(plan->num_rows == num_rows && plan->nnz == nnz,
                      "plan does not match the matrix");
-        tiles = (variant != kSlab && variant != kTma) ? plan->wtiles : plan->tiles;
+        tiles = plan_tiles(plan, variant, &num_tiles);
         lanes = plan->lanes;
     } else {
         int64_t* tr = (int64_t*)ctx->scratch(2 * (num_tiles + 1) * sizeof(int64_t));
@@ -69,14 +68,14 @@ b200_status spmv_impl(b200_ctx* ctx, const b200_csr_plan* plan, int64_t num_rows
             return B200_ERR_ALLOC;
         }
         b200_status st = fill_plan<I>(ctx, num_rows, nnz, row_ptrs, num_tiles, tr,
-                                      (variant != kSlab && variant != kTma) ? kWTile : kTile);
+                                      variant != kSlab ? kWTile : kTile);
         if (st != B200_OK) return st;
         tiles = tr;
         lanes = pick_lanes(num_rows, nnz);
     }
     return launch_slab<V, I, ADVANCED, false>(ctx, lanes, variant, num_tiles, tiles, nnz, row_ptrs,
                                               col_idxs, values, alpha, b, b_stride, beta, c,
-                                              c_stride);
+                                              c_stride, DotArgs<V>{}, num_rows);
 }
 
 template <typename I>
@@ -90,20 +89,24 @@ b200_status plan_create(b200_ctx* ctx, int64_t num_rows, int64_t nnz, const I* r
     p->nnz = nnz;
     p->num_tiles = num_tiles_for(num_rows, nnz);
     p->num_wtiles = num_wtiles_for(num_rows, nnz);
+    p->num_rtiles = num_rtiles_for(num_rows, nnz);
     p->lanes = pick_lanes(num_rows, nnz);
     p->device = ctx->device;
     cudaError_t e = cudaMalloc((void**)&p->tiles,
-                               2 * (p->num_tiles + p->num_wtiles + 2) * sizeof(int64_t));
+                               2 * (p->num_tiles + p->num_wtiles + p->num_rtiles + 3) * sizeof(int64_t));
     if (e != cudaSuccess) {
         delete p;
         set_error("cudaMalloc failed for csr plan: %s", cudaGetErrorString(e));
         return B200_ERR_ALLOC;
     }
     p->wtiles = p->tiles + 2 * (p->num_tiles + 1);
+    p->rtiles = p->wtiles + 2 * (p->num_wtiles + 1);
     if (num_rows > 0) {
         b200_status st = fill_plan<I>(ctx, num_rows, nnz, row_ptrs, p->num_tiles, p->tiles, kTile);
         if (st == B200_OK)
             st = fill_plan<I>(ctx, num_rows, nnz, row_ptrs, p->num_wtiles, p->wtiles, kWTile);
+        if (st == B200_OK)
+            st = fill_plan<I>(ctx, num_rows, nnz, row_ptrs, p->num_rtiles, p->rtiles, kRingItems);
         if (st != B200_OK) {
             cudaFree(p->tiles);
             delete p;
@@ -185,6 +188,8 @@ inline void plan_drop_parts(b200_csr_plan* plan)
     }
     cudaFree(plan->ones);
     plan->ones = nullptr;
+    cudaFree(plan->pos);
+    plan->pos = nullptr;
     plan->parts = 0;
 }
 
@@ -255,24 +260,94 @@ b200_status plan_reblock(b200_ctx* ctx, b200_csr_plan* plan, int64_t num_rows, i
         st = plan_create<I>(ctx, num_rows, plan->part_nnz[p], prp, &plan->part_plan[p]);
     }
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(pos);
     cudaFree(sums);
     if (!ok || st != B200_OK) {
         cudaGetLastError();
+        cudaFree(pos);
         plan_drop_parts(plan);
         return st;
     }
+    plan->pos = pos;
     plan->parts = parts;
     plan->src_cols = ci;
     plan->src_vals = va;
     return B200_OK;
 }
 
-// Set-up time choice between the two warp kernels: the pipelined one wins where the gathers
-// of b are local (stencils, banded matrices: +10-14 %), the plain one where they are not
-// (uniformly random columns: +10 %) and on matrices too small to pipeline.  Both sum every
-// row in the same order, so the choice never changes a result bit.  Measured, not guessed:
-// each candidate runs `reps` times on the real matrix against a zero vector.
+// ---- locality of the gathers --------------------------------------------------------------
+// For a sample of groups of 32 consecutive rows (= one pass of the ring kernel's lane <-> row
+// schedule): how many distinct 128-byte lines of b does the j-th gather instruction touch, per
+// gathered element?  Stencils / bands: 32 neighbouring rows at the same offset = 2-3 lines per 32
+// elements (~0.08); uniformly random columns: one line per element (1.0).
+template <typename V, typename I>
+__global__ void gather_lines_kernel(int64_t num_rows, const I* __restrict__ rp, const I* __restrict__ ci,
+                                    int64_t groups, int64_t group_stride, unsigned long long* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t g = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (g >= groups) return;
+    const int64_t row = g * group_stride + lane;
+    int64_t s = 0, len = 0;
+    if (row < num_rows) {
+        s = rp[row];
+        len = (int64_t)rp[row + 1] - s;
+    }
+    if (len > 64) len = 64;  // the head of long rows is representative
+    const int64_t maxlen = __reduce_max_sync(0xffffffffu, (int)len);
+    unsigned long long lines = 0, elems = 0;
+    constexpr int kPerLine = 128 / (int)sizeof(V);
+    for (int64_t j = 0; j < maxlen; ++j) {
+        const bool act = j < len;
+        const unsigned mask = __ballot_sync(0xffffffffu, act);
+        if (act) {
+            const long long line = (long long)ci[s + j] / kPerLine;
+            const unsigned same = __match_any_sync(mask, line);
+            if ((__ffs(same) - 1) == lane) ++lines;  // one leader per distinct line
+            ++elems;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lines += __shfl_xor_sync(0xffffffffu, lines, o);
+        elems += __shfl_xor_sync(0xffffffffu, elems, o);
+    }
+    if (lane == 0) {
+        atomicAdd(out, lines);
+        atomicAdd(out + 1, elems);
+    }
+}
+
+template <typename V, typename I>
+b200_status plan_gather_lines(b200_ctx* ctx, b200_csr_plan* plan, int64_t num_rows, const I* rp, const I* ci)
+{
+    plan->gather_lines = 0.f;
+    if (num_rows == 0 || plan->nnz == 0) return B200_OK;
+    const int64_t all = ceildiv(num_rows, 32);
+    const int64_t groups = all < 4096 ? all : 4096;
+    const int64_t stride = (all / groups) * 32;  // evenly spread over the matrix
+    unsigned long long* cnt = (unsigned long long*)ctx->scratch(2 * sizeof(unsigned long long));
+    if (!cnt) return B200_ERR_ALLOC;
+    B200_CUDA_CHECK(cudaMemsetAsync(cnt, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    gather_lines_kernel<V, I><<<(unsigned)ceildiv(groups * 32, 256), 256, 0, ctx->stream>>>(num_rows, rp, ci, groups,
+                                                                                          stride, cnt);
+    B200_LAUNCH_CHECK(ctx);
+    unsigned long long h[2] = {0, 0};
+    B200_CUDA_CHECK(cudaMemcpyAsync(h, cnt, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    plan->gather_lines = h[1] ? (float)((double)h[0] / (double)h[1]) : 0.f;
+    return B200_OK;
+}
+
+// Set-up time choice of the kernel variant and of the column-blocked copy -- the analogue of the
+// reference's `automatical` strategy, which picks from nnz statistics (include/ginkgo/core/matrix/
+// csr.hpp).  A function of the matrix, reproducible run to run and under a profiler:
+//   gathers local (<= 0.5 line per element) and >= 2 ring tiles per SM, 16-byte aligned arrays  -> kCtaRing
+//   gathers local, smaller matrix                                                               -> kPipe
+//   gathers scattered                                                                           -> kWarp,
+//       plus the column-blocked copy when b exceeds 48 MB (parts of <= 40 MB of b each) and the
+//       rows are column-sorted
+// Every variant sums a row in the same order, so the choice never changes a result bit.
+// B200_CSR_TUNE_TIMING=1 (opt-in) times the candidates on the matrix instead, as round 1 did.
 template <typename V, typename I>
 b200_status plan_tune(b200_ctx* ctx, b200_csr_plan* plan, int64_t num_rows, int64_t num_cols,
                       int64_t nnz, const I* row_ptrs, const I* col_idxs, const V* values)
@@ -280,113 +355,116 @@ b200_status plan_tune(b200_ctx* ctx, b200_csr_plan* plan, int64_t num_rows, int6
     B200_REQUIRE(ctx && plan, "null argument");
     B200_REQUIRE(plan->num_rows == num_rows && plan->nnz == nnz, "plan does not match the matrix");
     plan->variant = kWarp;
-    const int64_t warps = (int64_t)ctx->num_sms * kWCtasPerSm * kWarpsPerCta;
-    if (num_rows == 0 || nnz == 0 || plan->num_wtiles < 4 * warps) return B200_OK;
+    if (num_rows == 0 || nnz == 0) return B200_OK;
     B200_REQUIRE(row_ptrs && col_idxs && values, "null pointer");
-    // Tuning decisions are timing based, so a run under a profiler (serialised, cold-cache
-    // launches) can decide differently from the run it is meant to explain.  B200_TUNE_RECORD
-    // appends every decision ("variant parts") to a file, B200_TUNE_REPLAY applies the
-    // decisions of such a file in call order instead of measuring.
-    static int tune_call = 0;
-    const int this_call = tune_call++;
-    if (const char* rp = getenv("B200_TUNE_REPLAY")) {
-        int v = -1, parts = 0, line = 0;
-        if (FILE* f = fopen(rp, "r")) {
-            int fv, fp;
-            while (fscanf(f, "%d %d", &fv, &fp) == 2) {
-                if (line++ == this_call) {
-                    v = fv;
-                    parts = fp;
-                    break;
-                }
-            }
-            fclose(f);
-        }
-        if (v >= 0) {
-            plan->variant = v;
-            if (parts >= 2)
-                return plan_reblock<V, I>(ctx, plan, num_rows, num_cols, nnz, row_ptrs, col_idxs,
-                                          values, parts);
-            return B200_OK;
-        }
-    }
-    V *b = nullptr, *c = nullptr;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    b200_status st = B200_OK;
-    if (cudaMalloc((void**)&b, (size_t)num_cols * sizeof(V)) != cudaSuccess ||
-        cudaMalloc((void**)&c, (size_t)num_rows * sizeof(V)) != cudaSuccess ||
-        cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) {
-        cudaGetLastError();
-        cudaFree(b);
-        cudaFree(c);
-        if (e0) cudaEventDestroy(e0);
-        if (e1) cudaEventDestroy(e1);
-        return B200_OK;  // no room to measure: keep the default, this is only a tuning step
-    }
-    cudaMemsetAsync(b, 0, (size_t)num_cols * sizeof(V), ctx->stream);
-    const Variant cand[2] = {kWarp, kPipe};
-    float best = 0.f;
-    const int reps = 3;
-    for (int k = 0; k < 2 && st == B200_OK; ++k) {
-        float ms = 0.f;
-        for (int r = 0; r <= reps && st == B200_OK; ++r) {  // r == 0 warms up
-            if (r == 1) cudaEventRecord(e0, ctx->stream);
-            st = launch_slab<V, I, false, false>(ctx, plan->lanes, cand[k], plan->num_wtiles,
-                                                 plan->wtiles, nnz, row_ptrs, col_idxs, values,
-                                                 nullptr, b, 1, nullptr, c, 1);
-        }
-        cudaEventRecord(e1, ctx->stream);
-        if (cudaEventSynchronize(e1) != cudaSuccess) st = B200_ERR_CUDA;
-        if (st == B200_OK) cudaEventElapsedTime(&ms, e0, e1);
-        if (st == B200_OK && (k == 0 || ms < 0.97f * best)) {
-            best = ms;
-            plan->variant = cand[k];
-        }
-    }
-    // third candidate: the column-blocked copy, when b is too large to stay in L2 next to
-    // the matrix stream (B200: 126 MB L2 on two dies; gathers of a 40 MB slice stay resident)
+    b200_status st = plan_gather_lines<V, I>(ctx, plan, num_rows, row_ptrs, col_idxs);
+    if (st != B200_OK) return st;
+    const bool local = plan->gather_lines <= 0.5f;
+    const bool aligned = (((uintptr_t)col_idxs | (uintptr_t)values | (uintptr_t)row_ptrs) & 15u) == 0;
+    const bool big = plan->num_rtiles >= 2 * (int64_t)ctx->num_sms;
+    const int64_t warps = (int64_t)ctx->num_sms * kWCtasPerSm * kWarpsPerCta;
+    if (local)
+        plan->variant = (big && aligned) ? kCtaRing : (plan->num_wtiles >= 4 * warps ? kPipe : kWarp);
+    // column-blocked copy: scattered gathers into a b that does not stay in L2 next to the stream
+    // (B200: 126 MB L2 on two dies, a 40 MB slice of b stays resident)
     const size_t b_bytes = (size_t)num_cols * sizeof(V);
     const char* rb = getenv("B200_CSR_REBLOCK");  // "0" never, "N" force N parts
     int parts = 0;
     if (rb)
         parts = atoi(rb);
-    else if (b_bytes > (size_t)48 << 20 && nnz >= 4 * num_rows)
+    else if (plan->allow_copy && !local && b_bytes > (size_t)48 << 20 && nnz >= 4 * num_rows)
         parts = (int)((b_bytes + ((size_t)40 << 20) - 1) / ((size_t)40 << 20));
     if (parts > b200_csr_plan::kMaxParts) parts = b200_csr_plan::kMaxParts;
-    float t_parts = 0.f;
-    if (st == B200_OK && parts >= 2) {
+    if (parts >= 2) {
         st = plan_reblock<V, I>(ctx, plan, num_rows, num_cols, nnz, row_ptrs, col_idxs, values, parts);
-        if (st == B200_OK && plan->parts > 1) {
-            for (int r = 0; r <= reps && st == B200_OK; ++r) {
-                if (r == 1) cudaEventRecord(e0, ctx->stream);
-                st = spmv_impl<V, I, false>(ctx, plan, num_rows, num_cols, nnz, row_ptrs, col_idxs,
-                                            values, nullptr, b, 1, 1, nullptr, c, 1);
-            }
-            cudaEventRecord(e1, ctx->stream);
-            if (cudaEventSynchronize(e1) != cudaSuccess) st = B200_ERR_CUDA;
-            if (st == B200_OK) cudaEventElapsedTime(&t_parts, e0, e1);
-            if (st != B200_OK || (!rb && t_parts > 0.96f * best)) plan_drop_parts(plan);
+        if (st != B200_OK) return st;
+        for (int p = 0; p < plan->parts; ++p) {
+            plan->part_plan[p]->variant = plan->variant;
+            plan->part_plan[p]->gather_lines = plan->gather_lines;
         }
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFree(b);
-    cudaFree(c);
+    static const bool timing = getenv("B200_CSR_TUNE_TIMING") && atoi(getenv("B200_CSR_TUNE_TIMING")) != 0;
+    if (timing) {
+        // opt-in: time every applicable variant on the matrix itself and keep the fastest
+        V *b = nullptr, *c = nullptr;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (cudaMalloc((void**)&b, (size_t)num_cols * sizeof(V)) == cudaSuccess &&
+            cudaMalloc((void**)&c, (size_t)num_rows * sizeof(V)) == cudaSuccess &&
+            cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess) {
+            cudaMemsetAsync(b, 0, (size_t)num_cols * sizeof(V), ctx->stream);
+            const Variant cand[3] = {kWarp, kPipe, kCtaRing};
+            float best = 0.f;
+            int best_v = plan->variant;
+            for (int k = 0; k < 3 && st == B200_OK; ++k) {
+                if (cand[k] == kCtaRing && !aligned) continue;
+                plan->variant = cand[k];
+                for (int p = 0; p < plan->parts; ++p) plan->part_plan[p]->variant = cand[k];
+                float ms = 0.f;
+                for (int r = 0; r <= 3 && st == B200_OK; ++r) {  // r == 0 warms up
+                    if (r == 1) cudaEventRecord(e0, ctx->stream);
+                    st = spmv_impl<V, I, false>(ctx, plan, num_rows, num_cols, nnz, row_ptrs, col_idxs, values,
+                                                nullptr, b, 1, 1, nullptr, c, 1);
+                }
+                cudaEventRecord(e1, ctx->stream);
+                if (cudaEventSynchronize(e1) != cudaSuccess) st = B200_ERR_CUDA;
+                if (st == B200_OK) cudaEventElapsedTime(&ms, e0, e1);
+                if (st == B200_OK && (best == 0.f || ms < 0.97f * best)) {
+                    best = ms;
+                    best_v = cand[k];
+                }
+            }
+            plan->variant = best_v;
+            for (int p = 0; p < plan->parts; ++p) plan->part_plan[p]->variant = best_v;
+        }
+        cudaGetLastError();
+        cudaFree(b);
+        cudaFree(c);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    }
     if (getenv("B200_DEBUG"))
         fprintf(stderr,
-                "[b200] csr plan tuned: rows %lld nnz %lld -> %s (%.3f ms / %d launches)%s parts=%d "
-                "(%.3f ms)\n",
-                (long long)num_rows, (long long)nnz,
-                plan->variant == kPipe ? "warp_pipe" : "warp_stream", best, reps,
-                plan->parts > 1 ? ", column-blocked copy kept" : "", plan->parts, t_parts);
-    if (const char* rec = getenv("B200_TUNE_RECORD")) {
-        if (FILE* f = fopen(rec, "a")) {
-            fprintf(f, "%d %d\n", plan->variant, plan->parts);
-            fclose(f);
-        }
-    }
+                "[b200] csr plan tuned: rows %lld nnz %lld, %.3f lines of b per gathered element -> %s, "
+                "column-blocked parts=%d\n",
+                (long long)num_rows, (long long)nnz, plan->gather_lines,
+                plan->variant == kCtaRing ? "cta_ring" : (plan->variant == kPipe ? "warp_pipe" : "warp_stream"),
+                plan->parts);
     if (st != B200_OK) set_error("csr plan tuning failed: %s", cudaGetErrorString(cudaGetLastError()));
     return st;
+}
+
+// values of the column-blocked copy again from the caller's (changed) values array
+template <typename V, typename I>
+__global__ void split_values_kernel(int64_t num_rows, const I* __restrict__ rp, const V* __restrict__ va, int parts,
+                                    const I* __restrict__ pos, int part, const I* __restrict__ prp,
+                                    V* __restrict__ pva)
+{
+    const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (row >= num_rows) return;
+    const int64_t s = part == 0 ? (int64_t)rp[row] : (int64_t)pos[(int64_t)(part - 1) * num_rows + row];
+    const int64_t e = part == parts - 1 ? (int64_t)rp[row + 1] : (int64_t)pos[(int64_t)part * num_rows + row];
+    int64_t out = prp[row];
+    for (int64_t k = s; k < e; ++k, ++out) pva[out] = va[k];
+}
+
+template <typename V, typename I>
+b200_status plan_refresh_values(b200_ctx* ctx, b200_csr_plan* plan, int64_t num_rows, const I* row_ptrs,
+                                const V* values)
+{
+    B200_REQUIRE(ctx && plan, "null argument");
+    B200_REQUIRE(plan->num_rows == num_rows, "plan does not match the matrix");
+    if (plan->parts < 2) return B200_OK;  // no copy: nothing can be stale
+    B200_REQUIRE(row_ptrs && values && plan->pos, "null pointer");
+    const unsigned grid = (unsigned)ceildiv(num_rows, 256);
+    for (int p = 0; p < plan->parts; ++p) {
+        split_values_kernel<V, I><<<grid, 256, 0, ctx->stream>>>(num_rows, row_ptrs, values, plan->parts,
+                                                                 (const I*)plan->pos, p,
+                                                                 (const I*)plan->part_row_ptrs[p],
+                                                                 (V*)plan->part_vals[p]);
+        B200_LAUNCH_CHECK(ctx);
+    }
+    plan->src_vals = values;
+    return B200_OK;
 }
 
 }  // namespace csr
@@ -427,6 +505,17 @@ B200_DEF_IS_SORTED(i64, int64_t)
 #undef B200_DEF_IS_SORTED
 
 int b200_csr_plan_variant(const b200_csr_plan* plan) { return plan ? plan->variant : -1; }
+/* overrides the tuned choice (0 slab, 2 warp_stream, 4 warp_pipe, 5 cta_ring): parity tests and
+ * experiments run every variant on the same matrix; results are the same bits whatever is set */
+void b200_csr_plan_set_variant(b200_csr_plan* plan, int variant)
+{
+    if (plan && (variant == 0 || variant == 2 || variant == 4 || variant == 5)) plan->variant = variant;
+}
+void b200_csr_plan_allow_value_copy(b200_csr_plan* plan, int allow)
+{
+    if (plan) plan->allow_copy = allow != 0;
+}
+double b200_csr_plan_gather_lines(const b200_csr_plan* plan) { return plan ? (double)plan->gather_lines : -1.0; }
 int b200_csr_plan_parts(const b200_csr_plan* plan) { return plan ? plan->parts : 0; }
 
 void b200_csr_plan_destroy(b200_csr_plan* plan)
@@ -452,6 +541,12 @@ void b200_csr_plan_destroy(b200_csr_plan* plan)
     {                                                                                          \
         return b200::csr::plan_tune<VT, IT>(ctx, plan, num_rows, num_cols, nnz, row_ptrs,      \
                                             col_idxs, values);                                 \
+    }                                                                                          \
+    b200_status b200_csr_plan_refresh_values_##V##_##I(b200_ctx* ctx, b200_csr_plan* plan,     \
+                                                       int64_t num_rows, const IT* row_ptrs,   \
+                                                       const VT* values)                       \
+    {                                                                                          \
+        return b200::csr::plan_refresh_values<VT, IT>(ctx, plan, num_rows, row_ptrs, values);  \
     }                                                                                          \
     b200_status b200_csr_spmv_##V##_##I(                                                       \
         b200_ctx* ctx, const b200_csr_plan* plan, int64_t num_rows, int64_t num_cols,          \
@@ -611,7 +706,7 @@ b200_status apply(b200_ctx* ctx, const b200_coo_plan* plan, int mode, int64_t nu
         if (st != B200_OK) return st;
         if (num_rhs == 1) {
             st = csr::fill_plan<I>(ctx, num_rows, nnz, rp, num_tiles, tiles,
-                                   (variant != csr::kSlab && variant != csr::kTma) ? csr::kWTile : csr::kTile);
+                                   variant != csr::kSlab ? csr::kWTile : csr::kTile);
             if (st != B200_OK) return st;
             const csr::Variant tma = variant;
             const int lanes = csr::pick_lanes(num_rows, nnz);

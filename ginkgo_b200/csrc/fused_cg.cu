@@ -25,7 +25,7 @@
 // Control  ctl[8] (int32): 0 stopping_status byte (0 = running), 1 iterations done,
 //                 2 max_iters (-1 none), 3 res_kind (0 none, 1 ResidualNorm,
 //                 2 ImplicitResidualNorm), 4 iter_first
-#include "csr_kernels.cuh"
+#include "csr_launch.cuh"
 
 namespace b200 {
 namespace fcg {
@@ -309,11 +309,11 @@ B200_DEF_FCG(f32, float)
         const b200::csr::Variant v = b200::csr::pick_variant(col_idxs, values, plan);            \
         B200_REQUIRE(v != b200::csr::kSlab, "col_idxs/values must be 32-byte aligned");          \
         b200::csr::DotArgs<VT> dot{work, ctx->counters + 1, dot_out, ctl};                       \
-        const bool w = v != b200::csr::kTma;                                                    \
+        int64_t nt = 0;                                                                          \
+        const int64_t* pt = b200::csr::plan_tiles(plan, v, &nt);                                 \
         return b200::csr::launch_slab<VT, IT, false, true>(                                      \
-            ctx, plan->lanes, v, w ? plan->num_wtiles : plan->num_tiles,                         \
-            w ? plan->wtiles : plan->tiles, nnz, row_ptrs, col_idxs, values, nullptr, b, 1,      \
-            nullptr, c, 1, dot);                                                                 \
+            ctx, plan->lanes, v, nt, pt, nnz, row_ptrs, col_idxs, values, nullptr, b, 1,         \
+            nullptr, c, 1, dot, num_rows);                                                       \
     }
 
 B200_DEF_SPMV_DOT(f64, double, i32, int32_t)

@@ -9,7 +9,7 @@
 // `GKO_NOT_COMPILED`).  This translation unit defines the SAME symbols for the hot path --
 // executor glue and the SpMV / Krylov / BLAS-1 / stopping / Jacobi kernels -- as thin wrappers
 // that unpack the Ginkgo objects into pointers, sizes, strides and the executor's stream and call
-// the C ABI of include/ginkgo_b200.h.  Build (ginkgo_b200/dropin/Makefile): the stub object is kept
+// the C ABI of include/ginkgo_b200.h.  Proof build (tests/dropin/Makefile): the stub object is kept
 // with all its symbols weakened (objcopy --weaken), so everything this file does not define still
 // resolves to the reference's own NotCompiled stub, and every symbol it does define wins.
 //

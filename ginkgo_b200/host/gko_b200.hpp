@@ -127,6 +127,7 @@ GKOB_V(float, f32)
     struct viabi<V, I> {                                                                        \
         static constexpr auto csr_plan_create = b200_csr_plan_create_##S##_##T;                 \
         static constexpr auto csr_plan_tune = b200_csr_plan_tune_##S##_##T;                     \
+        static constexpr auto csr_plan_refresh_values = b200_csr_plan_refresh_values_##S##_##T; \
         static constexpr auto csr_spmv = b200_csr_spmv_##S##_##T;                               \
         static constexpr auto csr_advanced_spmv = b200_csr_advanced_spmv_##S##_##T;             \
         static constexpr auto csr_spmv_dot = b200_csr_spmv_dot_##S##_##T;                       \
@@ -629,6 +630,12 @@ public:
     }
     ~Csr() override { b200_csr_plan_destroy(plan_); }
     const V* get_const_values() const { return values_.get_const_data(); }
+    // mutable access: the plan may hold a column-blocked copy of the values, refreshed on the next use
+    V* get_values()
+    {
+        values_dirty_ = true;
+        return values_.get_data();
+    }
     const I* get_const_col_idxs() const { return col_idxs_.get_const_data(); }
     const I* get_const_row_ptrs() const { return row_ptrs_.get_const_data(); }
     size_type get_num_stored_elements() const { return values_.get_size(); }
@@ -638,10 +645,19 @@ public:
         if (!plan_) {
             GKOB_CALL((viabi<V, I>::csr_plan_create(exec_->ctx(), size_.rows, values_.get_size(),
                                                     row_ptrs_.get_const_data(), &plan_)));
-            // strategy selection (reference: csr.hpp `automatical`), measured on the matrix
+            // this class sees every mutable access to the values (get_values), so the plan may keep
+            // its column-blocked value copy
+            b200_csr_plan_allow_value_copy(plan_, 1);
+            // strategy selection (reference: csr.hpp `automatical`), a function of the matrix
             GKOB_CALL((viabi<V, I>::csr_plan_tune(
                 exec_->ctx(), plan_, size_.rows, size_.cols, values_.get_size(),
                 row_ptrs_.get_const_data(), col_idxs_.get_const_data(), values_.get_const_data())));
+            values_dirty_ = false;
+        } else if (values_dirty_) {
+            GKOB_CALL((viabi<V, I>::csr_plan_refresh_values(exec_->ctx(), plan_, size_.rows,
+                                                            row_ptrs_.get_const_data(),
+                                                            values_.get_const_data())));
+            values_dirty_ = false;
         }
         return plan_;
     }
@@ -736,6 +752,7 @@ private:
     array<I> col_idxs_;
     array<I> row_ptrs_;
     mutable b200_csr_plan* plan_ = nullptr;
+    mutable bool values_dirty_ = false;
 };
 
 // ---- Ell / Sellp / Coo / Hybrid: device arrays in the reference's layouts ---------------------

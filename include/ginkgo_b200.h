@@ -114,13 +114,17 @@ b200_status b200_pipe_join(b200_pipe* pipe);
  * of the reference's strategy selection (include/ginkgo/core/matrix/csr.hpp `automatical`,
  * which picks from nnz statistics); every variant sums rows in the same order, so the
  * choice never changes a result.  plan_variant returns the recorded choice (-1 untuned).
- * When b is larger than L2 can hold next to the matrix stream (> 48 MB) and the rows are
- * column-sorted, tune also tries a COLUMN-BLOCKED COPY of col_idxs/values held by the plan
- * (2-4 parts of <= 40 MB of b each, applied in order: the row sums keep their exact
- * left-to-right order, so the bits do not change) and keeps it if it is >= 4 % faster.
- * The copy is only used for calls that pass the same col_idxs / values pointers; after
- * changing the values in place, tune again (the reference's `srow` has the same contract
- * for structural changes, csr.hpp `make_srow`).  B200_CSR_REBLOCK=0 disables it.
+ * plan_tune decides from the matrix, not from a timing: the locality of its gathers (distinct
+ * 128-byte lines of b per gathered element on a sample of row groups, plan_gather_lines), its size
+ * and the size of b against L2 (B200_CSR_TUNE_TIMING=1 times the candidates instead).
+ * COLUMN-BLOCKED COPY: for scattered gathers into a b larger than L2 keeps (> 48 MB) with
+ * column-sorted rows, tune can keep a copy of col_idxs / values split into parts of <= 40 MB of b,
+ * applied in order (the row sums keep their exact left-to-right order: same bits).  The copy holds
+ * VALUES, so it is built only for plans whose owner opted in with b200_csr_plan_allow_value_copy(plan, 1)
+ * and thereby promises to call b200_csr_plan_refresh_values_* after changing values in place (the
+ * C++ host layer and the Python harness do; a raw caller that never opts in cannot see stale
+ * values).  It is used only for calls that pass the col_idxs / values pointers it was made from.
+ * B200_CSR_REBLOCK=0 disables it, =N forces N parts.
  * ------------------------------------------------------------------------- */
 #define B200_DECL_CSR(V, VT, I, IT)                                                          \
     b200_status b200_csr_plan_create_##V##_##I(b200_ctx* ctx, int64_t num_rows, int64_t nnz, \
@@ -129,6 +133,9 @@ b200_status b200_pipe_join(b200_pipe* pipe);
                                              int64_t num_rows, int64_t num_cols,             \
                                              int64_t nnz, const IT* row_ptrs,                \
                                              const IT* col_idxs, const VT* values);          \
+    b200_status b200_csr_plan_refresh_values_##V##_##I(b200_ctx* ctx, b200_csr_plan* plan,   \
+                                                       int64_t num_rows, const IT* row_ptrs, \
+                                                       const VT* values);                    \
     b200_status b200_csr_spmv_##V##_##I(                                                     \
         b200_ctx* ctx, const b200_csr_plan* plan, int64_t num_rows, int64_t num_cols,        \
         int64_t nnz, const IT* row_ptrs, const IT* col_idxs, const VT* values, const VT* b,  \
@@ -140,6 +147,9 @@ b200_status b200_pipe_join(b200_pipe* pipe);
         VT* c, int64_t c_stride);
 void b200_csr_plan_destroy(b200_csr_plan* plan);
 int b200_csr_plan_variant(const b200_csr_plan* plan);
+void b200_csr_plan_set_variant(b200_csr_plan* plan, int variant); /* 0 slab, 2 warp_stream, 4 warp_pipe, 5 cta_ring */
+void b200_csr_plan_allow_value_copy(b200_csr_plan* plan, int allow);
+double b200_csr_plan_gather_lines(const b200_csr_plan* plan); /* -1 before tune */
 int b200_csr_plan_parts(const b200_csr_plan* plan); /* > 1: a column-blocked copy is in use */
 
 /* ---------------------------------------------------------------------------

@@ -13,7 +13,7 @@
 #include <string>
 #include <vector>
 
-#include "../../ginkgo_b200/csrc/csr_ring.cuh"
+#include "../../ginkgo_b200/csrc/csr_launch.cuh"
 
 using namespace b200;
 using namespace b200::csr;

@@ -1,7 +1,7 @@
 // dropin_check.cpp -- runs the REFERENCE's own host code (gko::matrix::Csr::apply,
 // gko::solver::{Cg,Bicgstab,Gmres}::build()...on(exec)->generate(A)->apply(b, x),
 // gko::preconditioner::Jacobi, gko::stop::*) on a gko::CudaExecutor whose kernels are the B200
-// library (ginkgo_b200/dropin/cuda_backend.cpp linked in place of the reference's
+// library (ginkgo_b200/dropin/cuda_backend.cpp, built by tests/dropin/Makefile, linked in place of the reference's
 // core/device_hooks/cuda_hooks.cpp stub) and compares every result with the same code on
 // gko::ReferenceExecutor.  Written against the reference's public headers only.
 //

@@ -162,8 +162,9 @@ def test_cfg4_full_size_gmres_block_jacobi(hexec):
 
 @pytest.mark.parametrize("kind", ["stencil", "random"])
 def test_plan_tune_keeps_results_bit_identical(kind):
-    """b200_csr_plan_tune_* may pick either warp kernel; the result must not change by a bit
-    against the untuned (plan = NULL) launch, and the recorded choice must be a warp variant."""
+    """b200_csr_plan_tune_* decides from the matrix (locality of the gathers, size): the 7-pt stencil
+    gets the bulk-copy ring (variant 5), uniformly random columns the warp-stream kernel (2); the
+    result must not change by a bit against the untuned (plan = NULL) launch."""
     import ctypes
     import torch
     from ginkgo_b200 import api, _lib
@@ -184,7 +185,45 @@ def test_plan_tune_keeps_results_bit_identical(kind):
     ex.run("b200_csr_spmv_f64_i32", None, n, n, A.nnz, rp, ci, va, x, 1, 1, y0, 1)
     ex.synchronize()
     variant = _lib.lib().b200_csr_plan_variant(A.plan())
-    assert variant in (2, 4)
+    lines = _lib.lib().b200_csr_plan_gather_lines(A.plan())
+    print("%s: variant %d, %.3f lines of b per gathered element" % (kind, variant, lines))
+    assert variant == (5 if kind == "stencil" else 2)
+    assert (lines < 0.2) if kind == "stencil" else (lines > 0.9)
+    assert torch.equal(Y.values.reshape(-1), y0)
+
+
+def test_value_copy_is_refreshed_after_in_place_changes(monkeypatch):
+    """ADVICE r01: the column-blocked copy holds values.  A raw C-ABI plan never builds it (no opt-in);
+    api.Csr opts in and refreshes through values_changed()."""
+    import ctypes
+    import torch
+    from ginkgo_b200 import api, _lib
+    monkeypatch.setenv("B200_CSR_REBLOCK", "2")
+    ex = api.B200Executor.create(0)
+    dev = ex.device
+    n = 300_000
+    with torch.cuda.stream(ex.stream):
+        rp, ci, va = W.random_csr(n, 9, xp="torch", device=dev, stream=21)
+        x = W.vector(n, xp="torch", device=dev)
+        y0 = torch.zeros(n, dtype=torch.float64, device=dev)
+    # raw plan: tune without the opt-in keeps no copy even when forced by size rules
+    monkeypatch.delenv("B200_CSR_REBLOCK")
+    raw = ctypes.c_void_p()
+    l = _lib.lib()
+    _lib.check(l.b200_csr_plan_create_f64_i32(ex.ctx, n, va.numel(), rp.data_ptr(), ctypes.byref(raw)))
+    ex.run("b200_csr_plan_tune_f64_i32", raw, n, n, va.numel(), rp, ci, va)
+    assert l.b200_csr_plan_parts(raw) == 0
+    l.b200_csr_plan_destroy(raw)
+    monkeypatch.setenv("B200_CSR_REBLOCK", "2")
+    A = api.Csr(ex, (n, n), va, ci, rp)
+    assert l.b200_csr_plan_parts(A.plan()) == 2
+    Y = api.Dense(ex, torch.zeros_like(y0))
+    with torch.cuda.stream(ex.stream):
+        va.mul_(-3.0)          # in-place change of the matrix values
+    A.values_changed()
+    A.apply(api.Dense(ex, x), Y)
+    ex.run("b200_csr_spmv_f64_i32", None, n, n, A.nnz, rp, ci, va, x, 1, 1, y0, 1)
+    ex.synchronize()
     assert torch.equal(Y.values.reshape(-1), y0)
 
 

@@ -69,12 +69,16 @@ EXACT_KINDS = {"ref_common", "empty_rows", "laplace_like", "all_empty"}  # LANES
 @pytest.mark.parametrize("kind", CSR_KINDS)
 @pytest.mark.parametrize("vt", VTS)
 @pytest.mark.parametrize("it", ITS)
-@pytest.mark.parametrize("use_plan", [False, True])
+@pytest.mark.parametrize("use_plan", [False, True, "pipe", "ring"])
 def test_csr_spmv_vector(orc, cuda, kind, vt, it, use_plan):
     rng = np.random.default_rng(42)
     n, m, rp, ci, va = csr_case(rng, kind, vt, it)
     nnz = len(va)
     plan = cuda.make_csr_plan(vt, it, n, nnz, rp) if use_plan else None
+    if use_plan in ("pipe", "ring") and plan is not None:
+        # every kernel variant on every case: the bulk-copy ring (csr_ring.cuh) incl. its tails (nnz and
+        # num_rows + 1 not multiples of 4), rows longer than a stage, empty tiles inside long rows
+        cuda.l.b200_csr_plan_set_variant(plan, {"pipe": 4, "ring": 5}[use_plan])
     x = H.dense(rng, m, 1, vt=vt)
     tol = R[vt] * max(1.0, np.sqrt(np.diff(rp.astype(np.int64)).max(initial=1)))
 
