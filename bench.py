@@ -25,6 +25,11 @@ import sys
 import threading
 import time
 
+# Thread binding of the CPU arm (the reference's OmpExecutor): must be in the environment BEFORE
+# anything loads libgomp (numpy / torch do), otherwise it is ignored and the 64 threads float.
+os.environ.setdefault("OMP_PROC_BIND", "close")
+os.environ.setdefault("OMP_PLACES", "cores")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -35,7 +40,6 @@ import workloads as W  # noqa: E402
 CFG = "cfg2"
 N_ROWS = W.CONFIGS[CFG]["n"]
 PER_ROW = W.CONFIGS[CFG]["per_row"]
-CPU_SAMPLE_ROWS = 2_000_000  # bounded CPU sample: first 2M rows (30M nnz), full-width x
 
 
 def peaks():
@@ -91,48 +95,69 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ CPU arm (reference OMP)
-def cpu_reference_spmv(sample_rows, reps):
-    """the reference's OMP executor (oracle/_ref) or, if that was not built, the oracle port"""
-    rp, ci, va = W.build(CFG, 0, sample_rows, xp="np")
-    x = W.vector(N_ROWS)
+def cfg2_on_host():
+    """the FULL cfg2 matrix + x as numpy arrays (generated on the GPU when there is one: the
+    counter-based hash of workloads.py gives the same bits on both, and 150 M entries take ~1 s there)"""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+            rp, ci, va = W.build(CFG, xp="torch", device=dev)
+            x = W.vector(N_ROWS, xp="torch", device=dev)
+            out = tuple(t.cpu().numpy() for t in (rp, ci, va, x))
+            del rp, ci, va, x
+            torch.cuda.empty_cache()
+            return out
+    except Exception:
+        pass
+    rp, ci, va = W.build(CFG, xp="np")
+    return rp, ci, va, W.vector(N_ROWS)
+
+
+def cpu_reference_spmv(mat, min_reps, min_seconds=2.0):
+    """the reference's OMP executor (oracle/_ref) on the full cfg2 -- same config as the GPU arm --
+    or, if that was not built, the oracle port.  Reference methodology (benchmark/utils/timer):
+    warm-up, then >= min_reps repetitions and >= min_seconds."""
+    rp, ci, va, x = mat
     nnz = len(va)
-    os.environ.setdefault("OMP_PROC_BIND", "close")
-    os.environ.setdefault("OMP_PLACES", "cores")
+    n = len(rp) - 1
     from oracle import ref
     if ref.available():
         cores = ref.use_physical_cores()
+        _, sec1 = ref.spmv("csr", rp, ci, va, x, N_ROWS, exec_kind=1, reps=2)  # warm-up, first touch
+        reps = int(max(min_reps, min(200, min_seconds / max(sec1, 1e-6))))
         _, sec = ref.spmv("csr", rp, ci, va, x, N_ROWS, exec_kind=1, reps=reps)
         kind = "reference"
     else:
         from oracle import oracle
-        y = np.zeros(sample_rows)
+        y = np.zeros(n)
+        reps = max(1, min_reps // 4)
         t0 = time.perf_counter()
         for _ in range(reps):
-            oracle.call("orc_csr_spmv_f64_i32", sample_rows, N_ROWS, nnz, rp, ci, va, x, 1, 1, y, 1)
+            oracle.call("orc_csr_spmv_f64_i32", n, N_ROWS, nnz, rp, ci, va, x, 1, 1, y, 1)
         sec = (time.perf_counter() - t0) / reps
         cores, kind = 1, "port"
     return {"value": 2.0 * nnz / sec / 1e9, "unit": "GFLOP/s", "cores": cores, "kind": kind,
-            "sample": "first %d rows (nnz=%d) of %s against the full %d-entry x; %s; %d reps, "
-                      "%.3f ms/SpMV" % (sample_rows, nnz, CFG, N_ROWS,
-                                        "gko::OmpExecutor Csr(classical)::apply" if kind == "reference"
-                                        else "oracle C port, 1 thread", reps, sec * 1e3),
+            "sample": "the full %s (n=%d, nnz=%d) against the full x; %s; %d reps, %.3f ms/SpMV; "
+                      "OMP_PROC_BIND=%s OMP_PLACES=%s (set before libgomp loads), nproc=%d"
+                      % (CFG, n, nnz, "gko::OmpExecutor Csr(classical)::apply, %d threads" % cores
+                         if kind == "reference" else "oracle C port, 1 thread", reps, sec * 1e3,
+                         os.environ.get("OMP_PROC_BIND"), os.environ.get("OMP_PLACES"), os.cpu_count() or 0),
             "ms": sec * 1e3, "nnz": nnz}
 
 
 def run_reference_arm(args, rank):
     if rank != 0:
         return
-    reps = max(1, args.steps)
-    # keep the whole run within minutes whatever K is: cap the timed repetitions
-    reps = min(reps, 200)
-    b = cpu_reference_spmv(CPU_SAMPLE_ROWS, reps)
+    b = cpu_reference_spmv(cfg2_on_host(), max(1, min(args.steps, 200)))
     line = {
         "impl": "reference", "metric": "csr_spmv_fp64_gflops", "value": b["value"],
         "unit": "GFLOP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": b["ms"], "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "%s: random CSR n=%d nnz=%d (15/row) fp64/int32; CPU sample = %s"
-                               % (CFG, N_ROWS, N_ROWS * PER_ROW, b["sample"])},
+        "config": {"workload": "%s: CSR SpMV fp64/int32, random n=%d nnz=%d (15 distinct uniform "
+                               "cols/row), workloads.py seed 42" % (CFG, N_ROWS, N_ROWS * PER_ROW),
+                   "cpu_arm": b["sample"]},
         "cpu_baseline": {k: b[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": b["value"], "unit": "GFLOP/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
@@ -230,7 +255,7 @@ def run_gpu_arm(args, rank, world):
         def kernel_step():
             api._hcheck(hl.gkob_apply(Aloc.h, xe_h.h, y_h.h))
     ex.synchronize()
-    kernel_name = {2: "warp_stream_kernel", 4: "warp_pipe_kernel"}.get(
+    kernel_name = {2: "warp_stream_kernel", 4: "warp_pipe_kernel", 5: "ring_kernel"}.get(
         hl.gkob_csr_kernel_variant((A if world == 1 else Aloc).h), "warp_stream_kernel")
     plan_parts = hl.gkob_csr_plan_parts((A if world == 1 else Aloc).h)
     for _ in range(max(args.warmup, 3)):
@@ -291,31 +316,65 @@ def run_gpu_arm(args, rank, world):
     ncols_loc = N_ROWS if world == 1 else A.n_local + A.n_ghost
     alg_bytes = W.spmv_bytes(r1 - r0, ncols_loc, nnz_loc)
     achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
+    n_launch = max(plan_parts, 1)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                 "kernel": "b200::csr::%s<double,int,1,...>" % kernel_name + (
                     " x %d launches (column-blocked copy, parts applied in order)" % plan_parts
                     if plan_parts > 1 else ""),
-                "launches_per_step": max(plan_parts, 1),
-                "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": ms_kernel}
-    prof = os.path.join(ROOT, "profiles", "r01_csr_spmv_cfg2.json")
-    if os.path.exists(prof) and world == 1:  # the capture is of the 1-GPU workload
+                # one SpMV = `launches_per_step` launches of the kernel; bytes and time are per STEP
+                "launches_per_step": n_launch,
+                "algorithmic_bytes_per_step": alg_bytes, "kernel_ms_per_step": ms_kernel,
+                "algorithmic_bytes_per_launch": alg_bytes / n_launch, "ms_per_launch": ms_kernel / n_launch,
+                "gather_lines_per_element": hl.gkob_csr_gather_lines((A if world == 1 else Aloc).h)
+                if hasattr(hl, "gkob_csr_gather_lines") else None}
+    prof = os.path.join(ROOT, "profiles", "r02_csr_spmv_cfg2.json")
+    if os.path.exists(prof) and world == 1:  # ncu --set full capture of THIS build's bench command
         try:
             pj = json.load(open(prof))
-            # the capture is of the column-blocked SpMV (2 launches); without the copy one
-            # launch moves what profiles/r01g_spmv_cfg2_random.json shows
-            roofline["traffic"] = pj.get("dram_bytes_per_launch") if plan_parts > 1 else 4518669040.0
+            if int(pj.get("launches_per_step", -1)) == n_launch:
+                roofline["traffic"] = pj.get("dram_bytes_per_step")
+                roofline["traffic_source"] = "profiles/r02_csr_spmv_cfg2.json (dram__bytes_read.sum + " \
+                                             "dram__bytes_write.sum of the step's launches, ncu --set full)"
         except Exception:
             pass
-    del A, rp, ci, va, x_full
+    host_mat = None
+    if world == 1 and not args.no_cpu:  # the CPU arm times the SAME matrix
+        host_mat = tuple(t.cpu().numpy() for t in (rp, ci, va, x_full))
+    del A, rp, ci, va
     torch.cuda.empty_cache()
+
+    # ------------------------------------------ banded twin of cfg2 (same n, nnz/row; local gathers)
+    twin = None
+    if world == 1 and not args.no_twin:
+        with torch.cuda.stream(ex.stream):
+            brp, bci, bva = W.build("cfg2_banded", xp="torch", device=dev)
+            yb = torch.empty(N_ROWS, dtype=torch.float64, device=dev)
+        B = api.host_csr(ex, (N_ROWS, N_ROWS), bva, bci, brp)
+        xb, ybh = api.host_dense(ex, x_full), api.host_dense(ex, yb)
+
+        def bstep():
+            api._hcheck(hl.gkob_apply(B.h, xb.h, ybh.h))
+        for _ in range(3):
+            bstep()
+        ms_b = timed(bstep, args.steps) / args.steps
+        bbytes = W.spmv_bytes(N_ROWS, N_ROWS, bva.numel())
+        twin = {"workload": "banded twin of cfg2: n=%d, columns row-7..row+7, nnz=%d" % (N_ROWS, bva.numel()),
+                "ms_per_step": ms_b, "gflops": 2.0 * bva.numel() / (ms_b * 1e-3) / 1e9,
+                "achieved": bbytes / (ms_b * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": bbytes / (ms_b * 1e-3) / 1e9 / peak,
+                "kernel_variant": hl.gkob_csr_kernel_variant(B.h)}
+        del B, brp, bci, bva, yb
+        torch.cuda.empty_cache()
+    roofline["banded_twin"] = twin
+    del x_full
 
     # ------------------------------------------------------------------------------ CG
     cg = run_cg(args, rank, world, ex, dev, timed_events=True)
 
     if rank != 0:
         return
-    cpu = cpu_reference_spmv(CPU_SAMPLE_ROWS, 10) if world == 1 and not args.no_cpu else None
+    cpu = cpu_reference_spmv(host_mat, 10) if host_mat is not None else None
     line = {
         "metric": "csr_spmv_fp64_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
@@ -331,6 +390,10 @@ def run_gpu_arm(args, rank, world):
         "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": cs.summary(),
         "cg": cg,
     }
+    # the solver legs also under `config` (a key every consumer of the line keeps)
+    line["config"]["solver_legs"] = {k: {kk: v[kk] for kk in ("iterations", "iters_per_s", "true_rel_residual",
+                                                               "roofline") if kk in v}
+                                     for k, v in cg.items()}
     if cpu:
         line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line))
@@ -388,7 +451,12 @@ def run_cg(args, rank, world, ex, dev, timed_events=True):
                        "ms": ms, "iters_per_s": s.num_iterations / (ms * 1e-3),
                        "true_rel_residual": (r.norm() / b.norm()).item(),
                        "fused": s.used_fused, "stop_status": s.stop_status,
-                       "algorithmic_gbs": bytes_it * s.num_iterations / (ms * 1e-3) / 1e9}
+                       "algorithmic_gbs": bytes_it * s.num_iterations / (ms * 1e-3) / 1e9,
+                       "roofline": {"bound": "hbm", "unit": "GB/s", "peak": peaks()[0],
+                                    "achieved": bytes_it * s.num_iterations / (ms * 1e-3) / 1e9,
+                                    "frac": bytes_it * s.num_iterations / (ms * 1e-3) / 1e9 / peaks()[0],
+                                    "bytes_model": "fused minimum per iteration: nnz*12 + (n+1)*4 + 13*n*8 "
+                                                   "(SURVEY 8d; the reference's unfused count is +6*n*8)"}}
         del A, s, rp, ci, va, b, x, r
         torch.cuda.empty_cache()
     if args.no_cg:
@@ -424,6 +492,17 @@ def run_cg(args, rank, world, ex, dev, timed_events=True):
                        "iters_per_s": s.num_iterations / (ms * 1e-3),
                        "true_rel_residual": (r.double().norm() / b.double().norm()).item(),
                        "stop_status": s.stop_status, "first_apply_incl_generate_s": setup_s}
+        # byte model of the reference (core/solver/gmres.cpp:427-443) with d = Krylov vectors actually
+        # built before the stop: (5d/2 + 21/2 + 14/d) n V + (1 + 1/d) (B_matrix + B_blocks)
+        d_ = max(1, min(30, s.num_iterations))
+        nnz4 = va.numel()
+        bmat = nnz4 * 8 + (n + 1) * 4
+        bblk = (n // 16) * 256 * 4 + (n // 16 + 1) * 4
+        bytes_it4 = (2.5 * d_ + 10.5 + 14.0 / d_) * n * 4 + (1 + 1.0 / d_) * (bmat + bblk)
+        gbs4 = bytes_it4 * s.num_iterations / (ms * 1e-3) / 1e9
+        out["cfg4"]["roofline"] = {"bound": "hbm", "unit": "GB/s", "peak": peaks()[0], "achieved": gbs4,
+                                   "frac": gbs4 / peaks()[0],
+                                   "bytes_model": "reference formula core/solver/gmres.cpp:427-443 with d=%d" % d_}
         del A, s, rp, ci, va, b, x, r
         torch.cuda.empty_cache()
     # configs[4]: 400^3, fixed 200 iterations (reduction 0 never triggers), strong scaling
@@ -472,18 +551,55 @@ def run_cg(args, rank, world, ex, dev, timed_events=True):
         res = {}
         ms = wall(lambda: res.update(it=A.cg_apply(b, x)[0]))
         done, ghosts = res["it"], A.n_ghost
+    # TRUE residual ||b - A x|| / ||b|| of the timed solve, identical code path for every N
+    # (a wrong halo inside the CG graph would show here); compared with the reference's
+    # 200-iteration value (tests/golden/fullsize_reference.json) at the full size
+    with torch.cuda.stream(ex.stream):
+        yt = torch.empty(r1 - r0, dtype=torch.float64, device=dev)
+        if world == 1:
+            xe = x
+        else:
+            xe = torch.zeros(A.n_local + A.n_ghost, dtype=torch.float64, device=dev)
+            xe[:A.n_local] = x
+    if world == 1:
+        api._hcheck(api._host().gkob_apply(A.h, api.host_dense(ex, xe).h, (ytd := api.host_dense(ex, yt)).h))
+    else:
+        A.apply(xe, yt)
+    ex.synchronize()
+    with torch.cuda.stream(ex.stream):
+        sq = torch.stack([((b - yt) ** 2).sum(), (b ** 2).sum()])
+    ex.synchronize()
+    if world > 1:
+        dist.all_reduce(sq)
+    true_res = float((sq[0] / sq[1]).sqrt().item())
+    ref_res = None
+    try:
+        gj = json.load(open(os.path.join(ROOT, "tests", "golden", "fullsize_reference.json")))
+        if not args.small_cg and "cfg5" in gj:
+            ref_res = gj["cfg5"]["true_rel_residual"]
+    except Exception:
+        pass
+    if ref_res is not None and done == iters and abs(true_res - ref_res) > 1e-10 + 1e-6 * ref_res:
+        raise RuntimeError("cfg5 CG on %d GPU(s): true residual %.12e after %d iterations, the reference "
+                           "has %.12e" % (world, true_res, done, ref_res))
     nnz_t = torch.tensor([nnz_loc], device=dev, dtype=torch.int64)
     if world > 1:
         dist.all_reduce(nnz_t)
     nnz = int(nnz_t.item())
     bytes_it = nnz * 12 + (n + world) * 4 + 13 * n * 8
+    peak, _ = peaks()
+    gbs = bytes_it * done / (ms * 1e-3) / 1e9
     out["cfg5"] = {"workload": "cfg5: CG fp64 (unpreconditioned), 7-pt Laplacian %d^3 n=%d nnz=%d, "
                                "b=1, %d iterations, rows split in z-slabs over %d GPU(s)"
                                % (g, n, nnz, iters, world), "iterations": done, "ms": ms,
                    "iters_per_s": done / (ms * 1e-3), "ghosts_per_rank": ghosts,
                    "collectives": ("single GPU" if world == 1 else
                                    "peer memory over NVLink" if A.p2p else "NCCL"),
-                   "algorithmic_gbs": bytes_it * done / (ms * 1e-3) / 1e9}
+                   "true_rel_residual": true_res, "reference_true_rel_residual": ref_res,
+                   "algorithmic_gbs": gbs,
+                   "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak * world, "unit": "GB/s",
+                                "frac": gbs / (peak * world),
+                                "bytes_model": "fused minimum per iteration: nnz*12 + (n+1)*4 + 13*n*8 (SURVEY 8d)"}}
     return out
 
 
@@ -496,6 +612,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-cg", action="store_true", help="skip the CG legs")
     ap.add_argument("--no-gmres", action="store_true", help="skip the GMRES + block-Jacobi leg")
+    ap.add_argument("--no-twin", action="store_true", help="skip the banded twin of cfg2")
     ap.add_argument("--small-cg", action="store_true", help="160^3 instead of 400^3 for the cfg5 leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

@@ -220,6 +220,7 @@ def _configure_host_lib(h):
     h.gkob_launch_count.argtypes = [vp]
     h.gkob_csr_kernel_variant.restype, h.gkob_csr_kernel_variant.argtypes = i, [vp]
     h.gkob_csr_plan_parts.restype, h.gkob_csr_plan_parts.argtypes = i, [vp]
+    h.gkob_csr_gather_lines.restype, h.gkob_csr_gather_lines.argtypes = ctypes.c_double, [vp]
     h.gkob_staged_create.restype, h.gkob_staged_create.argtypes = vp, [vp, i, ll]
     h.gkob_staged_apply.restype, h.gkob_staged_apply.argtypes = i, [vp, vp, vp]
     h.gkob_staged_join.restype, h.gkob_staged_join.argtypes = i, [vp]

@@ -423,7 +423,21 @@ void gkob_solver_params(double relaxation_factor, double foci_lo, double foci_hi
     g_foci_hi = foci_hi;
 }
 
-// kernel variant the tuned plan of a Csr handle uses (2 = warp_stream, 4 = warp_pipe); -1 if
+// locality of the gathers the tuned plan measured (distinct 128-byte lines of b per gathered element)
+double gkob_csr_gather_lines(void* csr)
+{
+    double v = -1.0;
+    guarded([&] {
+        auto op = static_cast<Handle*>(csr)->op.get();
+        if (auto a = dynamic_cast<const matrix::Csr<double, int32>*>(op))
+            v = b200_csr_plan_gather_lines(a->get_plan());
+        else if (auto a = dynamic_cast<const matrix::Csr<float, int32>*>(op))
+            v = b200_csr_plan_gather_lines(a->get_plan());
+    });
+    return v;
+}
+
+// kernel variant the tuned plan of a Csr handle uses (2 = warp_stream, 4 = warp_pipe, 5 = cta ring); -1 if
 // the handle is not a double/int32 or float/int32 Csr
 int gkob_csr_kernel_variant(void* csr)
 {

@@ -2,7 +2,7 @@
 """Generates tests/golden/fullsize_reference.json: iteration counts and residuals of the REAL
 reference (oracle/_ref = /root/reference's core + Reference/OMP executors compiled in place,
 driven through its public API by oracle/ref_shim.cpp) on BASELINE.json's full-size solver
-configurations.  Run once here (CPU only, ~2 min on 8 cores); the GPU tests
+configurations.  Run once here (CPU only, ~2 min on 8 cores for cfg3/cfg4, ~10 min more for cfg5); the GPU tests
 (tests/test_fullsize_gpu.py) and bench.py compare against the committed numbers.
 
   cfg3  CG + Jacobi(max_block_size=1) fp64, 7-pt Laplacian 200^3, b = 1, x0 = 0,
@@ -68,7 +68,23 @@ def main():
                                      exec_kind=0)
         out["cfg4"]["reference_after_%d_iterations" % its] = {"true_rel_residual": true_rel(rp, ci, va, b, x)}
         print("cfg4 after", its, out["cfg4"]["reference_after_%d_iterations" % its], flush=True)
-    with open(os.path.join(ROOT, "tests", "golden", "fullsize_reference.json"), "w") as f:
+    path = os.path.join(ROOT, "tests", "golden", "fullsize_reference.json")
+    with open(path, "w") as f:
+        json.dump(out, f, indent=1)
+    del rp, ci, va, b, x
+    # ---- cfg5: CG fp64 unpreconditioned, 7-pt Laplacian 400^3, b = 1, exactly 200 iterations
+    # (what bench.py times at 1/2/4/8 GPUs): the true residual every rank count must reproduce
+    g = W.CONFIGS["cfg5"]["grid"]
+    rp, ci, va = W.laplace(g, 3)
+    n = len(rp) - 1
+    b = np.ones(n)
+    t = time.time()
+    x, it, resn, sec = ref.solve("cg", rp, ci, va, b, np.zeros(n), precond_max_bs=0, max_iters=200,
+                                 reduction=1e-300, exec_kind=1)
+    out["cfg5"] = {"executor": "omp", "iterations": int(it), "implicit_residual_norm": float(resn[0]),
+                   "true_rel_residual": true_rel(rp, ci, va, b, x), "seconds": round(time.time() - t, 1)}
+    print("cfg5", out["cfg5"], flush=True)
+    with open(path, "w") as f:
         json.dump(out, f, indent=1)
 
 

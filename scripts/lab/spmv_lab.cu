@@ -340,14 +340,13 @@ void group_base(const std::string& name)
     fill_plan<int>(B.ctx, m.n, m.nnz, m.rp, nwt, wtiles, kWTile);
     CK(cudaDeviceSynchronize());
     auto go = [&](Variant v) {
-        const bool w = (v == csr::kWarp || v == kRingV || v == kPipe);
-        launch_slab<V, int, false, false>(B.ctx, 1, v, w ? nwt : nt, w ? wtiles : tiles, m.nnz, m.rp, m.ci, m.va,
-                                          (const V*)nullptr, B.x, 1, (const V*)nullptr, B.y, 1);
+        launch_slab<V, int, false, false>(B.ctx, 1, v, nwt, wtiles, m.nnz, m.rp, m.ci, m.va, (const V*)nullptr, B.x,
+                                          1, (const V*)nullptr, B.y, 1);
     };
     B.run("r01 warp_stream", [&] { go(csr::kWarp); });
     B.run("r01 warp_pipe", [&] { go(kPipe); });
-    B.run("r01 warp_ring (per-warp bulk ring)", [&] { go(kRingV); });
-    B.run("r01 slab_tma (CTA bulk, block barriers)", [&] { go(kTma); });
+    (void)nt;
+    (void)tiles;
 }
 
 // ------------------------------------------------------------------------------ group: ring
