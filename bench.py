@@ -230,7 +230,7 @@ def run_gpu_arm(args, rank, world):
             A_.apply(xe, yt)
             ex.synchronize()
             with torch.cuda.stream(ex.stream):
-                good = A_.n_ghost == 0 or torch.equal(xe[A_.n_local:], x_full[A_.part["ghosts"].to(dev).long()])
+                good = A_.n_ghost == 0 or torch.equal(A_.last_ghosts(), x_full[A_.part["ghosts"].to(dev).long()])
                 t = torch.tensor([1 if good else 0], device=dev)
             ex.synchronize()
             dist.all_reduce(t, op=dist.ReduceOp.MIN)

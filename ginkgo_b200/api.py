@@ -587,6 +587,7 @@ class DistMatrix:
         h.gkob_dist_matrix_create_f64_i32.restype = vp
         h.gkob_dist_matrix_create_f64_i32.argtypes = [vp, vp, i, i, ll, ll, ll, vp, vp, vp, vp, vp, vp]
         h.gkob_dist_spmv_f64.restype, h.gkob_dist_spmv_f64.argtypes = i, [vp, vp, vp]
+        h.gkob_dist_last_ghosts_f64.restype, h.gkob_dist_last_ghosts_f64.argtypes = i, [vp, vp]
         h.gkob_dist_p2p.restype, h.gkob_dist_p2p.argtypes = i, [vp]
         h.gkob_dist_cg_create_f64.restype = i
         h.gkob_dist_cg_create_f64.argtypes = [vp, i, ll, i, i, ctypes.c_double, i, i]
@@ -679,8 +680,16 @@ class DistMatrix:
         return _host().gkob_dist_p2p(self.h)
 
     def apply(self, x_ext, y_local):
-        """y_local = A x; x_ext is [n_local owned | n_ghost] (ghosts filled by the exchange)"""
+        """y_local = A x; x_ext is [n_local owned | n_ghost].  The ghosts are exchanged; on the
+        peer-memory path the SpMV reads them in place from the landing slot (last_ghosts() returns
+        them), otherwise they are written into the tail of x_ext"""
         _hcheck(_host().gkob_dist_spmv_f64(self.h, x_ext.data_ptr(), y_local.data_ptr()))
+
+    def last_ghosts(self):
+        """the ghost values the last apply() gathered from (device tensor of n_ghost entries)"""
+        out = torch.empty(max(self.n_ghost, 1), dtype=torch.float64, device=self.exec.device)
+        _hcheck(_host().gkob_dist_last_ghosts_f64(self.h, out.data_ptr()))
+        return out[:self.n_ghost]
 
     def solve(self, kind, b_local, x_local, global_rows, precond_max_bs=0, max_iters=None, res_kind=1,
               baseline=0, reduction=1e-8, iter_first=True, krylov_dim=30, ortho=0, schwarz=0):

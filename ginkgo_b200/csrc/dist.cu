@@ -149,8 +149,18 @@ struct b200_halo {
     // owner-side landing slots of the peers, no NCCL call on the data path
     bool p2p = false;
     int rank = 0;
-    b200_peer_window win;           // [flags 2 x nranks u64 | landing slot 0 | landing slot 1]
-    size_t slot_off[2] = {0, 0};
+    // window: [flags 2 x nranks u64 | extended vector 0 | extended vector 1]; an extended vector is
+    // [n_local owned | n_ghost landing slot], so a kernel can gather straight from it
+    // (b200_halo_exchange_inplace_*) -- or the slot is copied into the caller's ghost tail
+    b200_peer_window win;
+    size_t buf_off[2] = {0, 0};     // the two extended vectors
+    size_t slot_off[2] = {0, 0};    // their ghost tails (= landing slots)
+    // every peer's send list is one contiguous run of owned entries (a matrix whose ghosts are
+    // (nearly) all of x, e.g. uniformly random columns): pushed with 16-byte remote stores
+    bool runs = false;
+    int64_t* run_base_dev = nullptr;  // device: first owned index of the run, per peer
+    uint64_t host_epoch = 0;          // exchanges issued from the host outside stream capture
+    bool captured = false;            // an exchange was captured into a graph: host_epoch is unreliable
     int64_t* meta_dev = nullptr;    // device: send_off[nranks+1] | send_cnt[nranks] | recv_cnt[nranks]
     void** peer_slot_dev = nullptr;  // device: [2][nranks] where my segment starts on peer p
     uint64_t** peer_flag_dev = nullptr;  // device: [nranks] &flags[0][rank] on peer p
@@ -300,6 +310,87 @@ __global__ void __launch_bounds__(256) halo_wait_kernel(HaloDev h, V* __restrict
             h.ticket[1] = 0;
             *(volatile uint64_t*)h.epoch = e;
         }
+    }
+}
+
+// Contiguous runs: peer p receives x[run_base[p] .. + send_cnt[p]) -- stored with 16-byte remote
+// stores where the destination is 16-byte aligned (8-byte head / tail otherwise).  blockIdx.y
+// selects the peer; y == nranks copies the owned entries into this rank's own extended vector
+// (own != nullptr), so the consumer kernel can read [owned | ghosts] from one base pointer.
+template <typename V>
+__global__ void __launch_bounds__(256) halo_push_runs_kernel(HaloDev h, const V* __restrict__ x,
+                                                            const int64_t* __restrict__ run_base, V* own)
+{
+    const uint64_t e = *(volatile uint64_t*)h.epoch + 1;
+    const int par = (int)(e & 1);
+    const int p = blockIdx.y;
+    const int64_t* send_cnt = h.meta + h.nranks + 1;
+    const V* src;
+    V* dst;
+    int64_t cnt;
+    if (p == h.nranks) {
+        src = x;
+        dst = own;
+        cnt = own ? h.n_local : 0;
+    } else {
+        src = x + run_base[p];
+        dst = (V*)h.peer_slot[par * h.nranks + p];
+        cnt = send_cnt[p];
+    }
+    if (cnt > 0) {
+        constexpr int kPer = 16 / (int)sizeof(V);  // elements per 16-byte store
+        int64_t head = (int64_t)(((16 - ((uintptr_t)dst & 15)) & 15) / sizeof(V));
+        if (head > cnt) head = cnt;
+        const int64_t body = (cnt - head) / kPer;
+        const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+        const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+        if (tid < head) dst[tid] = src[tid];
+        const V* s2 = src + head;
+        V* d2 = dst + head;
+        for (int64_t i = tid; i < body; i += stride) {
+            V v[kPer];
+#pragma unroll
+            for (int k = 0; k < kPer; ++k) v[k] = s2[i * kPer + k];
+            if (sizeof(V) == 8) {
+                double2 w = make_double2((double)v[0], (double)v[kPer - 1]);
+                *reinterpret_cast<double2*>(d2 + i * kPer) = w;
+            } else {
+                float4 w = make_float4((float)v[0], (float)v[1 % kPer], (float)v[2 % kPer], (float)v[3 % kPer]);
+                *reinterpret_cast<float4*>(d2 + i * kPer) = w;
+            }
+        }
+        const int64_t done = head + body * kPer;
+        if (tid < cnt - done) dst[done + tid] = src[done + tid];
+    }
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        last = atomicAdd(h.ticket, 1u) == gridDim.x * gridDim.y - 1;
+    }
+    __syncthreads();
+    if (last) {
+        if (threadIdx.x == 0) *h.ticket = 0;
+        if ((int)threadIdx.x < h.nranks && send_cnt[threadIdx.x] > 0) {
+            __threadfence_system();
+            st_release_sys(h.peer_flag[threadIdx.x] + par * h.nranks, e);
+        }
+    }
+}
+
+// wait only: acquire the epoch flag of every rank this one receives from; the consumer reads the
+// landing slot in place.  One CTA; advances the epoch.
+__global__ void __launch_bounds__(256) halo_wait_inplace_kernel(HaloDev h)
+{
+    const uint64_t e = *(volatile uint64_t*)h.epoch + 1;
+    const int par = (int)(e & 1);
+    const int64_t* recv_cnt = h.meta + 2 * h.nranks + 1;
+    if ((int)threadIdx.x < h.nranks && recv_cnt[threadIdx.x] > 0)
+        wait_flag(h.my_flags + par * h.nranks + threadIdx.x, e, h.err);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        *(volatile uint64_t*)h.epoch = e;
     }
 }
 
@@ -570,6 +661,7 @@ void b200_halo_destroy(b200_halo* h)
         cudaFree(h->peer_flag_dev);
         cudaFree(h->epoch_dev);
         cudaFree(h->ticket_dev);
+        cudaFree(h->run_base_dev);
     }
     delete h;
 }
@@ -611,6 +703,12 @@ int64_t b200_halo_num_send(const b200_halo* h) { return h->n_send; }
         auto& a = b200::nccl::api();                                                           \
         if (h->nranks == 1 || (h->n_send == 0 && h->n_ghost == 0)) return B200_OK;             \
         if (h->p2p) {                                                                          \
+            cudaStreamCaptureStatus cap_st = cudaStreamCaptureStatusNone;                      \
+            cudaStreamIsCapturing(ctx->stream, &cap_st);                                       \
+            if (cap_st != cudaStreamCaptureStatusNone)                                         \
+                h->captured = true;                                                            \
+            else                                                                               \
+                h->host_epoch++;                                                               \
             b200::dist::HaloDev d{h->nranks, h->rank, h->n_local, h->n_ghost, h->n_send,       \
                                   h->send_idx, h->meta_dev, h->peer_slot_dev,                  \
                                   h->peer_flag_dev, (uint64_t*)h->win.local,                   \
@@ -618,9 +716,15 @@ int64_t b200_halo_num_send(const b200_halo* h) { return h->n_send; }
                                    (char*)h->win.local + h->slot_off[1]},                      \
                                   h->epoch_dev, h->ticket_dev, h->err_dev};                    \
             const int64_t cap = (int64_t)ctx->num_sms * 4;                                     \
-            int64_t gs = b200::ceildiv(h->n_send, 256 * 4);                                    \
-            gs = gs < 1 ? 1 : (gs > cap ? cap : gs);                                           \
-            b200::dist::halo_push_kernel<VT><<<(unsigned)gs, 256, 0, ctx->stream>>>(d, x_ext); \
+            if (h->runs) {                                                                     \
+                dim3 grid(32, (unsigned)h->nranks);                                            \
+                b200::dist::halo_push_runs_kernel<VT><<<grid, 256, 0, ctx->stream>>>(          \
+                    d, x_ext, h->run_base_dev, nullptr);                                       \
+            } else {                                                                           \
+                int64_t gs = b200::ceildiv(h->n_send, 256 * 4);                                \
+                gs = gs < 1 ? 1 : (gs > cap ? cap : gs);                                       \
+                b200::dist::halo_push_kernel<VT><<<(unsigned)gs, 256, 0, ctx->stream>>>(d, x_ext); \
+            }                                                                                  \
             B200_LAUNCH_CHECK(ctx);                                                            \
             int64_t gr = b200::ceildiv(h->n_ghost, 256 * 4);                                   \
             gr = gr < 1 ? 1 : (gr > cap ? cap : gr);                                           \
@@ -646,6 +750,51 @@ int64_t b200_halo_num_send(const b200_halo* h) { return h->n_send; }
                                        comm->comm, ctx->stream));                              \
         }                                                                                      \
         B200_NCCL_CHECK(a.GroupEnd());                                                         \
+        return B200_OK;                                                                        \
+    }                                                                                          \
+    /* The exchange without the landing -> ghost copy: the owned entries x_owned[0 .. n_local) go  */ \
+    /* to the peers AND into this rank's own extended vector inside the peer window; *x_ext_out is */ \
+    /* that vector [owned | ghosts], valid until the exchange after the next one.  Peer memory     */ \
+    /* only, not capturable (the buffer alternates with the epoch): returns B200_ERR_UNSUPPORTED   */ \
+    /* otherwise and the caller uses b200_halo_exchange_*.                                         */ \
+    b200_status b200_halo_exchange_inplace_##V(b200_ctx* ctx, b200_comm* comm, b200_halo* h,   \
+                                               const VT* x_owned, VT** x_ext_out)              \
+    {                                                                                          \
+        (void)comm;                                                                            \
+        B200_REQUIRE(ctx && h && x_owned && x_ext_out, "null argument");                       \
+        cudaStreamCaptureStatus cap_st = cudaStreamCaptureStatusNone;                          \
+        cudaStreamIsCapturing(ctx->stream, &cap_st);                                           \
+        if (!h->p2p || h->captured || cap_st != cudaStreamCaptureStatusNone) {                 \
+            b200::set_error("in-place halo exchange needs the peer-memory path outside graphs"); \
+            return B200_ERR_UNSUPPORTED;                                                       \
+        }                                                                                      \
+        const int par = (int)((h->host_epoch + 1) & 1);                                        \
+        VT* own = (VT*)((char*)h->win.local + h->buf_off[par]);                                \
+        b200::dist::HaloDev d{h->nranks, h->rank, h->n_local, h->n_ghost, h->n_send,           \
+                              h->send_idx, h->meta_dev, h->peer_slot_dev,                      \
+                              h->peer_flag_dev, (uint64_t*)h->win.local,                       \
+                              {(char*)h->win.local + h->slot_off[0],                           \
+                               (char*)h->win.local + h->slot_off[1]},                          \
+                              h->epoch_dev, h->ticket_dev, h->err_dev};                        \
+        if (h->runs) {                                                                         \
+            /* ~16 CTAs per destination keep every NVLink direction busy without taking the SMs */ \
+            dim3 grid(32, (unsigned)h->nranks + 1);                                            \
+            b200::dist::halo_push_runs_kernel<VT><<<grid, 256, 0, ctx->stream>>>(d, x_owned,   \
+                                                                                 h->run_base_dev, own); \
+            B200_LAUNCH_CHECK(ctx);                                                            \
+        } else {                                                                               \
+            B200_CUDA_CHECK(cudaMemcpyAsync(own, x_owned, (size_t)h->n_local * sizeof(VT),     \
+                                            cudaMemcpyDeviceToDevice, ctx->stream));           \
+            const int64_t cap = (int64_t)ctx->num_sms * 4;                                     \
+            int64_t gs = b200::ceildiv(h->n_send, 256 * 4);                                    \
+            gs = gs < 1 ? 1 : (gs > cap ? cap : gs);                                           \
+            b200::dist::halo_push_kernel<VT><<<(unsigned)gs, 256, 0, ctx->stream>>>(d, x_owned); \
+            B200_LAUNCH_CHECK(ctx);                                                            \
+        }                                                                                      \
+        b200::dist::halo_wait_inplace_kernel<<<1, 256, 0, ctx->stream>>>(d);                   \
+        B200_LAUNCH_CHECK(ctx);                                                                \
+        h->host_epoch++;                                                                       \
+        *x_ext_out = own;                                                                      \
         return B200_OK;                                                                        \
     }
 B200_DEF_COMM(f64, double)
@@ -760,10 +909,17 @@ b200_status b200_halo_enable_p2p(b200_ctx* ctx, b200_comm* comm, b200_halo* h)
         for (int q = 0; q < n; ++q) g += S[(size_t)q * n + p];
         return g;
     };
-    auto slot_bytes_of = [&](int p) { return round256((size_t)ghosts_of(p) * h->elem + 16); };
-    h->slot_off[0] = flag_bytes;
-    h->slot_off[1] = flag_bytes + slot_bytes_of(me);
-    st = window_open(ctx, comm, flag_bytes + 2 * slot_bytes_of(me), &h->win);
+    // every rank's number of owned entries: the landing slot of rank p is the ghost tail of its
+    // extended vectors [n_local_p owned | ghosts_p]
+    std::vector<int64_t> NL(n);
+    st = allgather_host(ctx, comm, &h->n_local, sizeof(int64_t), NL.data());
+    if (st != B200_OK) return st;
+    auto buf_bytes_of = [&](int p) { return round256((size_t)(NL[p] + ghosts_of(p)) * h->elem + 16); };
+    h->buf_off[0] = flag_bytes;
+    h->buf_off[1] = flag_bytes + buf_bytes_of(me);
+    h->slot_off[0] = h->buf_off[0] + (size_t)NL[me] * h->elem;
+    h->slot_off[1] = h->buf_off[1] + (size_t)NL[me] * h->elem;
+    st = window_open(ctx, comm, flag_bytes + 2 * buf_bytes_of(me), &h->win);
     if (st != B200_OK) return st;
     std::vector<void*> peer_slot(2 * (size_t)n);
     std::vector<uint64_t*> peer_flag(n);
@@ -771,9 +927,35 @@ b200_status b200_halo_enable_p2p(b200_ctx* ctx, b200_comm* comm, b200_halo* h)
         int64_t off = 0;  // where my segment starts in p's ghost numbering
         for (int q = 0; q < me; ++q) off += S[(size_t)q * n + p];
         char* base = (char*)h->win.mapped[p];
-        peer_slot[p] = base + flag_bytes + (size_t)off * h->elem;
-        peer_slot[n + p] = base + flag_bytes + slot_bytes_of(p) + (size_t)off * h->elem;
+        peer_slot[p] = base + flag_bytes + (size_t)(NL[p] + off) * h->elem;
+        peer_slot[n + p] = base + flag_bytes + buf_bytes_of(p) + (size_t)(NL[p] + off) * h->elem;
         peer_flag[p] = (uint64_t*)base + me;
+    }
+    // contiguous runs?  (host check of the send list, once)
+    {
+        std::vector<int32_t> idx((size_t)h->n_send);
+        if (h->n_send > 0)
+            B200_CUDA_CHECK(cudaMemcpy(idx.data(), h->send_idx, sizeof(int32_t) * (size_t)h->n_send,
+                                       cudaMemcpyDeviceToHost));
+        std::vector<int64_t> base(n, 0);
+        bool runs = h->n_send > 0;
+        for (int p = 0; p < n && runs; ++p) {
+            const int64_t o = h->send_off[p], c = h->send_count[p];
+            if (c == 0) continue;
+            base[p] = idx[(size_t)o];
+            for (int64_t k = 1; k < c; ++k)
+                if (idx[(size_t)(o + k)] != idx[(size_t)o] + k) {
+                    runs = false;
+                    break;
+                }
+        }
+        if (const char* env = getenv("B200_HALO_RUNS"))
+            if (atoi(env) == 0) runs = false;
+        if (runs) {
+            B200_CUDA_CHECK(cudaMalloc((void**)&h->run_base_dev, sizeof(int64_t) * n));
+            B200_CUDA_CHECK(cudaMemcpy(h->run_base_dev, base.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice));
+        }
+        h->runs = runs;
     }
     std::vector<int64_t> meta(3 * (size_t)n + 1);
     for (int p = 0; p < n; ++p) {

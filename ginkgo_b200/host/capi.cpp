@@ -572,6 +572,19 @@ int gkob_dist_spmv_f64(void* dist, double* x_ext, double* y_local)
     });
 }
 
+// ghosts_out[0 .. n_ghost) = the ghost entries the last gkob_dist_spmv_f64 gathered from (the peer-memory
+// path reads them in place from the landing slot instead of copying them into the caller's x_ext)
+int gkob_dist_last_ghosts_f64(void* dist, double* ghosts_out)
+{
+    return guarded([&] {
+        auto h = static_cast<DistHandle*>(dist);
+        auto n = h->A->n_local(), ng = h->A->n_ghost();
+        const double* src = h->A->last_extended();
+        if (!src) throw NotSupported("no distributed apply yet");
+        if (ng) h->exec->copy(ghosts_out, src + n, ng);
+    });
+}
+
 int gkob_dist_cg_create_f64(void* dist, int scalar_jacobi, long long max_iters, int res_kind,
                             int baseline, double reduction, int iter_first, int check_every)
 {

@@ -71,11 +71,13 @@ template <>
 struct cabi<double> {
     static constexpr auto allreduce = b200_comm_allreduce_sum_f64;
     static constexpr auto halo_exchange = b200_halo_exchange_f64;
+    static constexpr auto halo_exchange_inplace = b200_halo_exchange_inplace_f64;
 };
 template <>
 struct cabi<float> {
     static constexpr auto allreduce = b200_comm_allreduce_sum_f32;
     static constexpr auto halo_exchange = b200_halo_exchange_f32;
+    static constexpr auto halo_exchange_inplace = b200_halo_exchange_inplace_f32;
 };
 
 // the all-reduce behind a distributed vector's dots and norms
@@ -635,10 +637,24 @@ public:
     // y_local = A x   (x_ext: owned part filled by the caller, ghosts by the exchange)
     void apply_extended(matrix::Dense<V>* x_ext, matrix::Dense<V>* y_local) const
     {
+        // peer memory: the local SpMV gathers straight from the landing slots (no ghost copy; the
+        // ghosts of this call are then in last_extended(), not in x_ext)
+        V* in_place = nullptr;
+        if (b200_halo_p2p_enabled(halo_) && x_ext->get_stride() == 1 &&
+            cabi<V>::halo_exchange_inplace(exec_->ctx(), comm_->get(), halo_, x_ext->get_const_values(),
+                                           &in_place) == B200_OK) {
+            last_ext_ = in_place;
+            auto view = matrix::Dense<V>::create_view(exec_, x_ext->get_size(), in_place, 1);
+            local_->apply(view.get(), y_local);
+            return;
+        }
+        last_ext_ = x_ext->get_values();
         GKOB_CALL(cabi<V>::halo_exchange(exec_->ctx(), comm_->get(), halo_, x_ext->get_values(),
                                          nullptr));
         local_->apply(x_ext, y_local);
     }
+    // the extended vector [owned | ghosts] the last apply_extended gathered from
+    const V* last_extended() const { return last_ext_; }
     // a distributed::Vector of this matrix's row / column partition
     std::unique_ptr<Vector<V>> create_row_vector(size_type global_rows) const
     {
@@ -685,6 +701,7 @@ protected:
 
 private:
     mutable std::unique_ptr<matrix::Dense<V>> x_ext_;
+    mutable const V* last_ext_ = nullptr;
     std::shared_ptr<communicator> comm_;
     std::unique_ptr<matrix::Csr<V, I>> local_;
     size_type n_ghost_;

@@ -702,7 +702,14 @@ int32_t b200_comm_p2p_error(b200_ctx* ctx, const b200_comm* comm);
     b200_status b200_comm_allgather_##V(b200_ctx* ctx, b200_comm* comm, const VT* send,        \
                                         VT* recv, int64_t count_per_rank);                     \
     b200_status b200_halo_exchange_##V(b200_ctx* ctx, b200_comm* comm, b200_halo* halo,        \
-                                       VT* x_ext, const int32_t* ctl);
+                                       VT* x_ext, const int32_t* ctl);                         \
+    /* the exchange without the landing-slot -> ghost-tail copy (peer memory, not capturable): */ \
+    /* x_owned[0 .. n_local) goes to the peers (16-byte remote stores when every peer's send   */ \
+    /* list is one contiguous run) and into this rank's extended vector inside the peer        */ \
+    /* window; *x_ext_out = [owned | ghosts], valid until the exchange after the next one.     */ \
+    /* B200_ERR_UNSUPPORTED without peer memory or after a captured exchange: use the call above */ \
+    b200_status b200_halo_exchange_inplace_##V(b200_ctx* ctx, b200_comm* comm, b200_halo* halo, \
+                                               const VT* x_owned, VT** x_ext_out);
 B200_DECL_COMM(f64, double)
 B200_DECL_COMM(f32, float)
 /* all-gather of raw device bytes (set-up exchanges of counts and index lists) */

@@ -2,7 +2,7 @@
 mkdir -p gpurun_out
 echo "== solver tests"; timeout 600 python -m pytest tests/test_solvers_gpu.py -q -m gpu --timeout 120 2>&1 | tail -8
 echo "== dist check (2 GPUs)"
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 scripts/dist_check.py 2>&1 | grep -v "^W\|warn" | tail -12
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/multi_gpu_check.py 2>&1 | grep -v "^W\|warn" | tail -12
 echo "== bench 2 GPUs"
 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 50 --warmup 3 2>gpurun_out/bench2.err | tee gpurun_out/bench2.json | python -c "
 import sys,json

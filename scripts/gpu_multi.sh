@@ -4,7 +4,7 @@ N=$1
 mkdir -p gpurun_out
 for P2P in 1 0; do
 echo "== dist check ($N GPUs, B200_P2P=$P2P)"
-B200_P2P=$P2P timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$P2P scripts/dist_check.py 2>&1 | grep -E "rank|DIST_CHECK|Error|error|gko_b200" | sort | tail -24
+B200_P2P=$P2P timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$P2P tests/multi_gpu_check.py 2>&1 | grep -E "rank|DIST_CHECK|Error|error|gko_b200" | sort | tail -24
 done
 for P2P in 1 0; do
 echo "== bench $N GPUs B200_P2P=$P2P"

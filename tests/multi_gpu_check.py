@@ -1,4 +1,4 @@
-"""torchrun --nproc-per-node N scripts/dist_check.py : multi-GPU parity check (harness).
+"""torchrun --nproc-per-node N tests/multi_gpu_check.py : multi-GPU parity check (run by tests/test_multi_gpu.py).
 Distributed SpMV rows must be bit-identical to the single-GPU rows; distributed fused CG must
 match the single-GPU fused CG (same iteration count +-1, x to 1e-10)."""
 import os
@@ -90,7 +90,7 @@ for name, kw in [("lap3d_40", dict(grid=40, dims=3)), ("cfg2_small", dict(n=2000
         A2.apply(x2, y2)
         ex.synchronize()
         same2 = same2 and torch.equal(y2, y1[q0:q1])
-        same2 = same2 and torch.equal(x2[A2.n_local:].cpu(), xk.cpu()[torch.from_numpy(A2.ghost_globals)])
+        same2 = same2 and torch.equal(A2.last_ghosts().cpu(), xk.cpu()[torch.from_numpy(A2.ghost_globals)])
     ok &= same2
     print("rank %d %s: read_distributed n_local=%d n_ghost=%d p2p=%d spmv bit-equal=%s"
           % (rank, name, A2.n_local, A2.n_ghost, A2.p2p, same2), flush=True)
