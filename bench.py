@@ -367,6 +367,34 @@ def run_gpu_arm(args, rank, world):
         del B, brp, bci, bva, yb
         torch.cuda.empty_cache()
     roofline["banded_twin"] = twin
+    # ------------------------------------------ skewed twin: Zipf row lengths, the nnz of cfg2
+    skew = None
+    if world == 1 and not args.no_twin:
+        with torch.cuda.stream(ex.stream):
+            zrp, zci, zva = W.build("cfg2_zipf", xp="torch", device=dev)
+            yz = torch.empty(N_ROWS, dtype=torch.float64, device=dev)
+        Z = api.host_csr(ex, (N_ROWS, N_ROWS), zva, zci, zrp)
+        xz, yzh = api.host_dense(ex, x_full), api.host_dense(ex, yz)
+
+        def zstep():
+            api._hcheck(hl.gkob_apply(Z.h, xz.h, yzh.h))
+        for _ in range(3):
+            zstep()
+        ms_z = timed(zstep, args.steps) / args.steps
+        zbytes = W.spmv_bytes(N_ROWS, N_ROWS, zva.numel())
+        with torch.cuda.stream(ex.stream):
+            zl = (zrp[1:] - zrp[:-1])
+            zmax, zlong = int(zl.max().item()), int((zl >= 16384).sum().item())
+        skew = {"workload": "skewed twin of cfg2: n=%d, Zipf row lengths (longest row %d entries, %d rows >= 16384 "
+                            "split over CTAs), nnz=%d, columns spread over all of x"
+                            % (N_ROWS, zmax, zlong, zva.numel()),
+                "ms_per_step": ms_z, "gflops": 2.0 * zva.numel() / (ms_z * 1e-3) / 1e9,
+                "achieved": zbytes / (ms_z * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": zbytes / (ms_z * 1e-3) / 1e9 / peak, "kernel_variant": hl.gkob_csr_kernel_variant(Z.h),
+                "vs_uniform_random_cfg2": (zbytes / ms_z) / (alg_bytes / ms_kernel)}
+        del Z, zrp, zci, zva, yz
+        torch.cuda.empty_cache()
+    roofline["skewed_twin"] = skew
     del x_full
 
     # ------------------------------------------------------------------------------ CG

@@ -77,6 +77,9 @@ struct DotArgs {
     unsigned int* counter;  // self-resetting ticket
     V* result;
     const int32_t* ctl;
+    // rows with at least this many entries are NOT computed by these kernels (0: none): the plan
+    // splits them over CTAs (long_rows_kernel); such a row is always the last row of its tile
+    int64_t skip_from;
 };
 
 template <typename V>
@@ -327,7 +330,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kWCtasPerSm)
                 }
             }
             // ---- a last row that does not fit the strip: the whole warp sums it
-            if (long_last) {
+            if (long_last && !(dot.skip_from > 0 && p1 - sl >= dot.skip_from)) {
                 V acc = V(0);
                 for (int64_t i = sl + lane; i < p1; i += 32) {
                     const I col = ld_stream(col_idxs + i, pol_first);
@@ -500,7 +503,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kWCtasPerSm)
                 const V x = ld_gather(b + (int64_t)col * b_stride, pol_last);
                 prod[i - p0] = ADVANCED ? (alpha * val) * x : val * x;
             }
-            if (long_last) {
+            if (long_last && !(dot.skip_from > 0 && p1 - sl >= dot.skip_from)) {
                 V acc = V(0);
                 for (int64_t i = sl + lane; i < p1; i += 32) {
                     const I col = ld_stream(col_idxs + i, pol_first);
@@ -612,7 +615,7 @@ __global__ void __launch_bounds__(kThreads, 3)
         row_phase<V, LANES, ADVANCED, DOT>(
             r0, rows_end, a0, prod, [&](int64_t r) { return (int64_t)row_ptrs[r]; }, beta, b, b_stride,
             c, c_stride, dot_acc);
-        if (long_last)
+        if (long_last && !(dot.skip_from > 0 && p1 - sl >= dot.skip_from))
             long_row<V, I, ADVANCED, DOT>(rl, sl, p1, col_idxs, values, alpha, beta, b, b_stride, c,
                                           c_stride, red, dot_acc, pol_first, pol_last);
     }
@@ -647,6 +650,93 @@ __global__ void __launch_bounds__(256)
         }
         c[row * c_stride + j] = acc;
     }
+}
+
+// --------------------------------------------------------------------------
+// rows split over CTAs (skewed matrices): the plan lists every row with >= kLongRow entries and
+// cuts it into chunks of kLongChunk; one CTA per chunk adds its products (thread t takes entries
+// t, t + 256, ... in order, then a fixed tree), the CTA that finishes a row last adds the row's
+// chunk sums IN CHUNK ORDER and writes c.  Deterministic, no floating-point atomics.  Replaces the
+// carry fix-up of the reference's merge-path / load-balance kernels
+// (common/cuda_hip/matrix/csr_kernels.template.cpp:208-505), which use atomic_add.
+// --------------------------------------------------------------------------
+constexpr int64_t kLongRow = 16384;
+constexpr int64_t kLongChunk = 8192;
+
+struct LongRows {
+    int64_t num_rows;             // long rows
+    int64_t num_chunks;
+    const int64_t* row;           // [num_rows] row index, ascending
+    const int64_t* chunk_first;   // [num_rows + 1] first chunk of a row
+    const int32_t* chunk_row;     // [num_chunks] position of the chunk's row in `row`
+    unsigned int* tickets;        // [num_rows] self-resetting
+    void* partials;               // [num_chunks] value type
+};
+
+template <typename V, typename I, bool ADVANCED>
+__global__ void __launch_bounds__(256) long_rows_kernel(LongRows lr, const I* __restrict__ row_ptrs,
+                                                       const I* __restrict__ col_idxs,
+                                                       const V* __restrict__ values,
+                                                       const V* __restrict__ alpha_p,
+                                                       const V* __restrict__ b, int64_t b_stride,
+                                                       const V* __restrict__ beta_p, V* __restrict__ c,
+                                                       int64_t c_stride, const int32_t* ctl)
+{
+    __shared__ V red[32];
+    __shared__ bool last;
+    if (ctl && ctl[0] != 0) return;
+    const int tid = threadIdx.x;
+    const int64_t chunk = blockIdx.x;
+    const int k = lr.chunk_row[chunk];
+    const int64_t row = lr.row[k];
+    const int64_t s = (int64_t)row_ptrs[row] + (chunk - lr.chunk_first[k]) * kLongChunk;
+    int64_t e = s + kLongChunk;
+    const int64_t row_end = row_ptrs[row + 1];
+    if (e > row_end) e = row_end;
+    V alpha = V(1), beta = V(0);
+    if (ADVANCED) {
+        alpha = *alpha_p;
+        beta = *beta_p;
+    }
+    const uint64_t pol_last = policy_evict_last();
+    const uint64_t pol_first = policy_evict_first();
+    V acc = V(0);
+    for (int64_t i = s + tid; i < e; i += 256) {
+        const I col = ld_stream(col_idxs + i, pol_first);
+        const V val = ld_stream(values + i, pol_first);
+        const V x = ld_gather(b + (int64_t)col * b_stride, pol_last);
+        acc += ADVANCED ? (alpha * val) * x : val * x;
+    }
+    acc = block_sum(acc, red);
+    V* partials = (V*)lr.partials;
+    if (tid == 0) {
+        partials[chunk] = acc;
+        __threadfence();
+        const unsigned nchunks = (unsigned)(lr.chunk_first[k + 1] - lr.chunk_first[k]);
+        last = atomicAdd(lr.tickets + k, 1u) == nchunks - 1;
+    }
+    __syncthreads();
+    if (last && tid == 0) {
+        __threadfence();
+        lr.tickets[k] = 0u;
+        V sum = V(0);
+        for (int64_t q = lr.chunk_first[k]; q < lr.chunk_first[k + 1]; ++q) sum += __ldcg(partials + q);
+        if (ADVANCED && beta != V(0)) sum = c[row * c_stride] * beta + sum;
+        c[row * c_stride] = sum;
+    }
+}
+
+// fused dot: the long rows' share of b.c, added in row order after the main kernel has written
+// the dot of all other rows
+template <typename V>
+__global__ void long_rows_dot_fix_kernel(LongRows lr, const V* __restrict__ b, int64_t b_stride,
+                                         const V* __restrict__ c, int64_t c_stride, V* result,
+                                         const int32_t* ctl)
+{
+    if (ctl && ctl[0] != 0) return;
+    V t = *result;
+    for (int64_t k = 0; k < lr.num_rows; ++k) t += b[lr.row[k] * b_stride] * c[lr.row[k] * c_stride];
+    *result = t;
 }
 
 }  // namespace csr

@@ -58,6 +58,14 @@ struct b200_csr_plan {
     int device = 0;
     int variant = -1;  // kernel variant chosen by b200_csr_plan_tune_*, -1 = not tuned
     float gather_lines = -1.f;  // distinct 128-byte lines of b per gathered element (tune), -1 = unknown
+    // rows with >= kLongRow entries (skewed matrices): computed by long_rows_kernel, one CTA per chunk
+    // of kLongChunk entries, chunk sums combined in chunk order (csr_kernels.cuh)
+    int64_t num_long = 0, num_long_chunks = 0;
+    int64_t* long_row = nullptr;          // device [num_long]
+    int64_t* long_chunk_first = nullptr;  // device [num_long + 1]
+    int32_t* long_chunk_row = nullptr;    // device [num_long_chunks]
+    unsigned int* long_tickets = nullptr; // device [num_long], zero, self-resetting
+    void* long_partials = nullptr;        // device [num_long_chunks] values (8 bytes each)
     // Column-blocked copy of the matrix (b200_csr_plan_tune_* builds it for scattered gathers into a b
     // larger than L2 keeps): part p holds, row by row, the entries with column in
     // [p * col_block, (p+1) * col_block).  Rows are column-sorted (checked), so applying the parts in
@@ -229,6 +237,32 @@ b200_status launch_slab(b200_ctx* ctx, int lanes, Variant v, int64_t num_tiles,
     default: B200_SLAB(32);
     }
 #undef B200_SLAB
+}
+
+// one SpMV through a plan: the chosen variant on its tiles, then -- for plans with rows split over
+// CTAs -- the long-row kernel (and the long rows' share of the fused dot)
+template <typename V, typename I, bool ADVANCED, bool DOT>
+b200_status launch_planned(b200_ctx* ctx, const b200_csr_plan* plan, Variant v, int64_t nnz, const I* row_ptrs,
+                           const I* col_idxs, const V* values, const V* alpha, const V* b, int64_t b_stride,
+                           const V* beta, V* c, int64_t c_stride, DotArgs<V> dot = DotArgs<V>{})
+{
+    int64_t nt = 0;
+    const int64_t* tiles = plan_tiles(plan, v, &nt);
+    const bool has_long = plan->num_long > 0;
+    if (has_long) dot.skip_from = kLongRow;
+    b200_status st = launch_slab<V, I, ADVANCED, DOT>(ctx, plan->lanes, v, nt, tiles, nnz, row_ptrs, col_idxs, values,
+                                                     alpha, b, b_stride, beta, c, c_stride, dot, plan->num_rows);
+    if (st != B200_OK || !has_long) return st;
+    LongRows lr{plan->num_long,      plan->num_long_chunks, plan->long_row,     plan->long_chunk_first,
+                plan->long_chunk_row, plan->long_tickets,    plan->long_partials};
+    long_rows_kernel<V, I, ADVANCED><<<(unsigned)plan->num_long_chunks, 256, 0, ctx->stream>>>(
+        lr, row_ptrs, col_idxs, values, alpha, b, b_stride, beta, c, c_stride, DOT ? dot.ctl : nullptr);
+    B200_LAUNCH_CHECK(ctx);
+    if (DOT) {
+        long_rows_dot_fix_kernel<V><<<1, 1, 0, ctx->stream>>>(lr, b, b_stride, c, c_stride, dot.result, dot.ctl);
+        B200_LAUNCH_CHECK(ctx);
+    }
+    return B200_OK;
 }
 
 }  // namespace csr

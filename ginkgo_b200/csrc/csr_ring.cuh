@@ -308,9 +308,10 @@ __global__ void __launch_bounds__((NW + NP) * 32, 1)
                 stage = 0;
                 ph ^= 1u;
             }
-            if (long_last) {
+            if (long_last && !(dot.skip_from > 0 && p1 - (int64_t)row_ptrs[r1 - 1] >= dot.skip_from)) {
                 // the tile's last row does not fit a stage: all consumer warps stream it from
-                // global memory, fixed reduction tree (deterministic)
+                // global memory, fixed reduction tree (deterministic); rows the plan splits over
+                // CTAs (dot.skip_from) are left to long_rows_kernel
                 const int64_t rl = r1 - 1;
                 const int64_t sl = (int64_t)row_ptrs[rl];
                 V acc = V(0);

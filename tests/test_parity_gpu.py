@@ -49,6 +49,10 @@ def csr_case(rng, kind, vt, it):
         n, m = 40, 20000
         lens = rng.integers(0, 30, size=n)
         lens[3], lens[17], lens[18], lens[39] = 2500, 5000, 9000, 4200
+    elif kind == "split_rows":  # rows >= 16384 entries: split over CTAs by the plan (long_rows_kernel)
+        n, m = 300, 70000
+        lens = rng.integers(0, 12, size=n)
+        lens[0], lens[5], lens[6], lens[150], lens[299] = 16384, 16383, 50000, 24577, 33000
     elif kind == "one_row":
         n, m = 1, 7000
         lens = np.array([6500])
@@ -61,7 +65,7 @@ def csr_case(rng, kind, vt, it):
     return n, m, rp, ci, va
 
 
-CSR_KINDS = ["ref_common", "empty_rows", "laplace_like", "wide_rows", "long_rows", "one_row",
+CSR_KINDS = ["ref_common", "empty_rows", "laplace_like", "wide_rows", "long_rows", "split_rows", "one_row",
              "all_empty"]
 EXACT_KINDS = {"ref_common", "empty_rows", "laplace_like", "all_empty"}  # LANES == 1, rows fit
 

@@ -176,6 +176,57 @@ def banded_csr(n, half_bw, r0=0, r1=None, xp="np", vdtype=None, device=None, str
     return rp.to(torch.int32), cols[ok].to(torch.int32), vals[ok]
 
 
+# ---------------------------------------------------------------- skewed rows (power law)
+def zipf_lengths(n, nnz_target, xp="np", device=None):
+    """row lengths ~ c / rank (Zipf, exponent 1), ranks scattered over the rows by the bijection
+    rank(r) = (r * A + B) mod n; c is chosen so that the total is ~ nnz_target.  For n = 10 M and
+    nnz = 150 M the longest row has ~9 M entries, ~550 rows have >= 16384, ~1 M rows have one."""
+    import math
+    c = nnz_target / (math.log(n) + 0.5772156649)
+    A = 2_654_435_761 % n
+    while math.gcd(A, n) != 1:
+        A += 1
+    if xp == "np":
+        r = np.arange(n, dtype=np.int64)
+        rank = (r * A + 12345) % n
+        return np.clip(np.rint(c / (rank + 1.0)), 1, n).astype(np.int64)
+    import torch
+    r = torch.arange(n, dtype=torch.int64, device=device)
+    rank = (r * A + 12345) % n
+    return torch.clamp(torch.round(c / (rank + 1.0).double()), 1, n).to(torch.int64)
+
+
+def zipf_csr(n, nnz_target, xp="np", vdtype=None, device=None, stream=5):
+    """n x n CSR with Zipf row lengths; the L columns of a row are one uniformly jittered pick out of
+    each of L equal bins of [0, n) (sorted, distinct, spread over all of x).  Values U(-1,1).
+    Returns (row_ptrs int32/int64, col_idxs int32, values)."""
+    lens = zipf_lengths(n, nnz_target, xp, device)
+    if xp == "np":
+        rp = np.zeros(n + 1, dtype=np.int64)
+        rp[1:] = np.cumsum(lens)
+        nnz = int(rp[-1])
+        row = np.repeat(np.arange(n, dtype=np.int64), lens)
+        k = np.arange(nnz, dtype=np.int64) - rp[row]
+        L = lens[row]
+        u = (hash_np(stream, row, k) >> np.uint64(11)).astype(np.float64) / 9007199254740992.0
+        lo, hi = k * n // L, (k + 1) * n // L  # integer bins of [0, n): never empty (L <= n), disjoint
+        cols = lo + np.minimum((u * (hi - lo)).astype(np.int64), hi - lo - 1)
+        vals = _unit_np(hash_np(stream + 100, row, k), vdtype or np.float64)
+        return rp.astype(np.int32 if nnz < 2**31 else np.int64), cols.astype(np.int32), vals
+    import torch
+    rp = torch.zeros(n + 1, dtype=torch.int64, device=device)
+    rp[1:] = torch.cumsum(lens, 0)
+    nnz = int(rp[-1].item())
+    row = torch.repeat_interleave(torch.arange(n, dtype=torch.int64, device=device), lens)
+    k = torch.arange(nnz, dtype=torch.int64, device=device) - rp[row]
+    L = lens[row]
+    u = _lsr_t(hash_t(stream, row, k), 11).double() / 9007199254740992.0
+    lo, hi = k * n // L, (k + 1) * n // L
+    cols = lo + torch.minimum((u * (hi - lo).double()).to(torch.int64), hi - lo - 1)
+    vals = _unit_t(hash_t(stream + 100, row, k), vdtype or torch.float64)
+    return rp.to(torch.int32 if nnz < 2**31 else torch.int64), cols.to(torch.int32), vals
+
+
 # ------------------------------------------------------------------------ stencils
 def laplace(grid, dims, r0=0, r1=None, xp="np", vdtype=None, device=None):
     """5-pt (dims=2) / 7-pt (dims=3) Laplacian on a grid^dims box, natural ordering, diag =
@@ -215,6 +266,7 @@ CONFIGS = {
     "cfg1": dict(kind="laplace", grid=316, dims=2, n=99856, nnz=498016, dtype="f64"),
     "cfg2": dict(kind="random", n=10_000_000, per_row=15, nnz=150_000_000, dtype="f64"),
     "cfg2_banded": dict(kind="banded", n=10_000_000, half_bw=7, dtype="f64"),
+    "cfg2_zipf": dict(kind="zipf", n=10_000_000, nnz=150_000_000, dtype="f64"),
     "cfg3": dict(kind="laplace", grid=200, dims=3, n=8_000_000, nnz=55_760_000, dtype="f64"),
     "cfg4": dict(kind="random", n=4_000_000, per_row=20, nnz=80_000_000, dtype="f32",
                  diag_dominant=True),
@@ -237,6 +289,8 @@ def build(name, r0=0, r1=None, xp="np", device=None, n=None):
         return laplace(c["grid"], c["dims"], r0, r1, xp, vd, device)
     if c["kind"] == "banded":
         return banded_csr(c["n"], c["half_bw"], r0, r1, xp, vd, device)
+    if c["kind"] == "zipf":
+        return zipf_csr(c["n"], c["nnz"] * c["n"] // CONFIGS["cfg2_zipf"]["n"], xp, vd, device)
     return random_csr(c["n"], c["per_row"], r0, r1, xp, vd, device, c.get("diag_dominant", False))
 
 
