@@ -313,60 +313,79 @@ __global__ void __launch_bounds__(256) halo_wait_kernel(HaloDev h, V* __restrict
     }
 }
 
-// Contiguous runs: peer p receives x[run_base[p] .. + send_cnt[p]) -- stored with 16-byte remote
-// stores where the destination is 16-byte aligned (8-byte head / tail otherwise).  blockIdx.y
-// selects the peer; y == nranks copies the owned entries into this rank's own extended vector
-// (own != nullptr), so the consumer kernel can read [owned | ghosts] from one base pointer.
+// Contiguous runs: peer p receives x[run_base[p] .. + send_cnt[p]).  The work of all destinations
+// (plus, with own != nullptr, the copy of the owned entries into this rank's own extended vector,
+// so the consumer kernel can read [owned | ghosts] from one base pointer) is cut into blocks of
+// kRunBlock elements dealt round-robin to the CTAs; a thread keeps 4 independent 16-byte stores in
+// flight (two 8-byte local loads each), 8-byte stores only at unaligned segment ends.  First
+// version: 32 CTAs per destination, one load -> store chain per thread = 278 GB/s on one NVLink
+// peer (profiles/r02i_multi_gpu.txt); this one keeps every link busy.
+constexpr int kRunBlock = 2048;
+
 template <typename V>
 __global__ void __launch_bounds__(256) halo_push_runs_kernel(HaloDev h, const V* __restrict__ x,
                                                             const int64_t* __restrict__ run_base, V* own)
 {
     const uint64_t e = *(volatile uint64_t*)h.epoch + 1;
     const int par = (int)(e & 1);
-    const int p = blockIdx.y;
     const int64_t* send_cnt = h.meta + h.nranks + 1;
-    const V* src;
-    V* dst;
-    int64_t cnt;
-    if (p == h.nranks) {
-        src = x;
-        dst = own;
-        cnt = own ? h.n_local : 0;
-    } else {
-        src = x + run_base[p];
-        dst = (V*)h.peer_slot[par * h.nranks + p];
-        cnt = send_cnt[p];
-    }
-    if (cnt > 0) {
-        constexpr int kPer = 16 / (int)sizeof(V);  // elements per 16-byte store
-        int64_t head = (int64_t)(((16 - ((uintptr_t)dst & 15)) & 15) / sizeof(V));
-        if (head > cnt) head = cnt;
-        const int64_t body = (cnt - head) / kPer;
-        const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-        const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-        if (tid < head) dst[tid] = src[tid];
-        const V* s2 = src + head;
-        V* d2 = dst + head;
-        for (int64_t i = tid; i < body; i += stride) {
-            V v[kPer];
+    const int ndst = h.nranks + (own ? 1 : 0);
+    // blocks per destination (destination nranks = the own copy)
+    int64_t total = 0;
+    for (int p = 0; p < ndst; ++p) total += ceildiv(p < h.nranks ? send_cnt[p] : h.n_local, (int64_t)kRunBlock);
+    constexpr int kPer = 16 / (int)sizeof(V);  // elements per 16-byte store
+    for (int64_t blk = blockIdx.x; blk < total; blk += gridDim.x) {
+        int p = 0;
+        int64_t first = 0;
+        for (;; ++p) {
+            const int64_t nb = ceildiv(p < h.nranks ? send_cnt[p] : h.n_local, (int64_t)kRunBlock);
+            if (blk < first + nb) break;
+            first += nb;
+        }
+        const int64_t cnt = p < h.nranks ? send_cnt[p] : h.n_local;
+        const V* src = p < h.nranks ? x + run_base[p] : x;
+        V* dst = p < h.nranks ? (V*)h.peer_slot[par * h.nranks + p] : own;
+        const int64_t lo = (blk - first) * kRunBlock;
+        int64_t hi = lo + kRunBlock;
+        if (hi > cnt) hi = cnt;
+        // 16-byte aligned body of [lo, hi) in destination space
+        int64_t head = (int64_t)(((16 - ((uintptr_t)(dst + lo) & 15)) & 15) / sizeof(V));
+        if (head > hi - lo) head = hi - lo;
+        const int64_t body = (hi - lo - head) / kPer;
+        const int tid = threadIdx.x;
+        if (tid < head) dst[lo + tid] = src[lo + tid];
+        const V* s2 = src + lo + head;
+        V* d2 = dst + lo + head;
+        // kRunBlock / kPer <= 1024 stores per block = 4 per thread, all loads first
+        V v[4][kPer];
 #pragma unroll
-            for (int k = 0; k < kPer; ++k) v[k] = s2[i * kPer + k];
-            if (sizeof(V) == 8) {
-                double2 w = make_double2((double)v[0], (double)v[kPer - 1]);
-                *reinterpret_cast<double2*>(d2 + i * kPer) = w;
-            } else {
-                float4 w = make_float4((float)v[0], (float)v[1 % kPer], (float)v[2 % kPer], (float)v[3 % kPer]);
-                *reinterpret_cast<float4*>(d2 + i * kPer) = w;
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = tid + 256 * u;
+            if (i < body) {
+#pragma unroll
+                for (int k = 0; k < kPer; ++k) v[u][k] = s2[i * kPer + k];
             }
         }
-        const int64_t done = head + body * kPer;
-        if (tid < cnt - done) dst[done + tid] = src[done + tid];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = tid + 256 * u;
+            if (i < body) {
+                if (sizeof(V) == 8) {
+                    *reinterpret_cast<double2*>(d2 + i * kPer) = make_double2((double)v[u][0], (double)v[u][kPer - 1]);
+                } else {
+                    *reinterpret_cast<float4*>(d2 + i * kPer) =
+                        make_float4((float)v[u][0], (float)v[u][1 % kPer], (float)v[u][2 % kPer], (float)v[u][3 % kPer]);
+                }
+            }
+        }
+        const int64_t done = lo + head + body * kPer;
+        if (tid < hi - done) dst[done + tid] = src[done + tid];
     }
     __shared__ bool last;
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence_system();
-        last = atomicAdd(h.ticket, 1u) == gridDim.x * gridDim.y - 1;
+        last = atomicAdd(h.ticket, 1u) == gridDim.x - 1;
     }
     __syncthreads();
     if (last) {
@@ -717,8 +736,7 @@ int64_t b200_halo_num_send(const b200_halo* h) { return h->n_send; }
                                   h->epoch_dev, h->ticket_dev, h->err_dev};                    \
             const int64_t cap = (int64_t)ctx->num_sms * 4;                                     \
             if (h->runs) {                                                                     \
-                dim3 grid(32, (unsigned)h->nranks);                                            \
-                b200::dist::halo_push_runs_kernel<VT><<<grid, 256, 0, ctx->stream>>>(          \
+                b200::dist::halo_push_runs_kernel<VT><<<2 * ctx->num_sms, 256, 0, ctx->stream>>>( \
                     d, x_ext, h->run_base_dev, nullptr);                                       \
             } else {                                                                           \
                 int64_t gs = b200::ceildiv(h->n_send, 256 * 4);                                \
@@ -777,10 +795,8 @@ int64_t b200_halo_num_send(const b200_halo* h) { return h->n_send; }
                                (char*)h->win.local + h->slot_off[1]},                          \
                               h->epoch_dev, h->ticket_dev, h->err_dev};                        \
         if (h->runs) {                                                                         \
-            /* ~16 CTAs per destination keep every NVLink direction busy without taking the SMs */ \
-            dim3 grid(32, (unsigned)h->nranks + 1);                                            \
-            b200::dist::halo_push_runs_kernel<VT><<<grid, 256, 0, ctx->stream>>>(d, x_owned,   \
-                                                                                 h->run_base_dev, own); \
+            b200::dist::halo_push_runs_kernel<VT><<<2 * ctx->num_sms, 256, 0, ctx->stream>>>(  \
+                d, x_owned, h->run_base_dev, own);                                             \
             B200_LAUNCH_CHECK(ctx);                                                            \
         } else {                                                                               \
             B200_CUDA_CHECK(cudaMemcpyAsync(own, x_owned, (size_t)h->n_local * sizeof(VT),     \
