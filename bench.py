@@ -590,7 +590,8 @@ def run_cg(args, rank, world, ex, dev, timed_events=True):
             xe = torch.zeros(A.n_local + A.n_ghost, dtype=torch.float64, device=dev)
             xe[:A.n_local] = x
     if world == 1:
-        api._hcheck(api._host().gkob_apply(A.h, api.host_dense(ex, xe).h, (ytd := api.host_dense(ex, yt)).h))
+        xed, ytd = api.host_dense(ex, xe), api.host_dense(ex, yt)  # the handles must outlive the call
+        api._hcheck(api._host().gkob_apply(A.h, xed.h, ytd.h))
     else:
         A.apply(xe, yt)
     ex.synchronize()

@@ -653,6 +653,54 @@ __global__ void __launch_bounds__(256)
 }
 
 // --------------------------------------------------------------------------
+// several right-hand sides: P = 2..32 lanes per row, lane j owns right-hand side j0 + j
+// (grid.y walks j0 in steps of P), 32 / P rows per warp.  Per nonzero the P lanes read the same
+// (col, value) -- a broadcast -- and gather P CONSECUTIVE entries of the row-major b: one
+// coalesced access serves all right-hand sides.  Every (row, rhs) sum is left to right = the
+// reference's order.  The reference runs its vector kernel once per right-hand side (grid.y = #rhs,
+// common/cuda_hip/matrix/csr_kernels.template.cpp:2103-2109), i.e. streams the matrix nrhs times.
+// --------------------------------------------------------------------------
+template <typename V, typename I, bool ADVANCED, int P>
+__global__ void __launch_bounds__(256)
+    multi_rhs_rows_kernel(int64_t num_rows, int64_t num_rhs, const I* __restrict__ row_ptrs,
+                          const I* __restrict__ col_idxs, const V* __restrict__ values,
+                          const V* __restrict__ alpha_p, const V* __restrict__ b, int64_t b_stride,
+                          const V* __restrict__ beta_p, V* __restrict__ c, int64_t c_stride)
+{
+    constexpr int kRowsPerWarp = 32 / P;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t row = warp * kRowsPerWarp + lane / P;
+    const int64_t j = (int64_t)blockIdx.y * P + lane % P;
+    if (row >= num_rows) return;
+    const bool jv = j < num_rhs;
+    V alpha = V(1), beta = V(0);
+    if (ADVANCED) {
+        alpha = *alpha_p;
+        beta = *beta_p;
+    }
+    const int64_t s = row_ptrs[row], e = row_ptrs[row + 1];
+    V acc = V(0);
+    if (ADVANCED && jv && beta != V(0)) acc = c[row * c_stride + j] * beta;
+    constexpr int kB = 4;
+    for (int64_t k = s; k < e; k += kB) {
+        I cc[kB];
+        V vv[kB], xx[kB];
+#pragma unroll
+        for (int q = 0; q < kB; ++q) {
+            cc[q] = k + q < e ? col_idxs[k + q] : I(0);
+            vv[q] = k + q < e ? values[k + q] : V(0);
+        }
+#pragma unroll
+        for (int q = 0; q < kB; ++q) xx[q] = (k + q < e && jv) ? b[(int64_t)cc[q] * b_stride + j] : V(0);
+#pragma unroll
+        for (int q = 0; q < kB; ++q)
+            if (k + q < e) acc += ADVANCED ? (alpha * vv[q]) * xx[q] : vv[q] * xx[q];
+    }
+    if (jv) c[row * c_stride + j] = acc;
+}
+
+// --------------------------------------------------------------------------
 // rows split over CTAs (skewed matrices): the plan lists every row with >= kLongRow entries and
 // cuts it into chunks of kLongChunk; one CTA per chunk adds its products (thread t takes entries
 // t, t + 256, ... in order, then a fixed tree), the CTA that finishes a row last adds the row's

@@ -23,9 +23,22 @@ b200_status spmv_impl(b200_ctx* ctx, const b200_csr_plan* plan, int64_t num_rows
     if (ADVANCED) B200_REQUIRE(alpha && beta, "alpha/beta must be device pointers");
 
     if (num_rhs > 1) {
-        const int grid = grid_for(num_rows * num_rhs, 256, ctx->num_sms, 16);
-        multi_rhs_kernel<V, I, ADVANCED><<<grid, 256, 0, ctx->stream>>>(
-            num_rows, num_rhs, row_ptrs, col_idxs, values, alpha, b, b_stride, beta, c, c_stride);
+        // P lanes per row (next power of two >= num_rhs, at most 32), grid.y chunks of P right-hand sides
+        int P = 2;
+        while (P < num_rhs && P < 32) P *= 2;
+        const int64_t rows_per_block = 256 / P;
+        dim3 grid((unsigned)ceildiv(num_rows, rows_per_block), (unsigned)ceildiv(num_rhs, (int64_t)P));
+#define B200_MRHS(PP)                                                                             \
+    multi_rhs_rows_kernel<V, I, ADVANCED, PP><<<grid, 256, 0, ctx->stream>>>(                     \
+        num_rows, num_rhs, row_ptrs, col_idxs, values, alpha, b, b_stride, beta, c, c_stride)
+        switch (P) {
+        case 2: B200_MRHS(2); break;
+        case 4: B200_MRHS(4); break;
+        case 8: B200_MRHS(8); break;
+        case 16: B200_MRHS(16); break;
+        default: B200_MRHS(32); break;
+        }
+#undef B200_MRHS
         B200_LAUNCH_CHECK(ctx);
         return B200_OK;
     }

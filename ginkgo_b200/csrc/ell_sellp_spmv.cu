@@ -21,9 +21,10 @@
 namespace b200 {
 
 // acc += sum_i val_i * b[col_i] over `len` stored entries spaced `step` apart, in storage
-// order, skipping padding (col == -1) exactly like the reference loops.  The loads of four
+// order, skipping padding (col == -1) exactly like the reference loops.  The loads of kRowBatch
 // entries are issued together (predicated off for padding and for positions past `len`), so
-// a row of 7 entries costs two memory latencies instead of seven.
+// a row of 7 entries costs ONE round of (column, value) loads and one of gathers instead of seven
+// (round 1 batched four: two rounds for the 7-pt stencil, SELL-P at 53 % of the HBM roofline).
 template <typename V, typename I, bool ADVANCED>
 __device__ __forceinline__ V strided_row_sum(V acc, const I* __restrict__ cols,
                                              const V* __restrict__ vals, int64_t step, int64_t len,
@@ -31,24 +32,25 @@ __device__ __forceinline__ V strided_row_sum(V acc, const I* __restrict__ cols,
                                              const V* __restrict__ b, int64_t b_stride,
                                              uint64_t pol_first, uint64_t pol_last)
 {
-    for (int64_t i = lane_first; i < len; i += 4 * lane_step) {
-        I c[4];
-        V v[4], x[4];
+    constexpr int kRowBatch = 8;
+    for (int64_t i = lane_first; i < len; i += kRowBatch * lane_step) {
+        I c[kRowBatch];
+        V v[kRowBatch], x[kRowBatch];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < kRowBatch; ++k) {
             const int64_t ik = i + k * lane_step;
             c[k] = ik < len ? ld_stream(cols + ik * step, pol_first) : I(-1);
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < kRowBatch; ++k) {
             const int64_t ik = i + k * lane_step;
             v[k] = ik < len ? ld_stream(vals + ik * step, pol_first) : V(0);
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < kRowBatch; ++k)
             x[k] = c[k] >= I(0) ? ld_gather(b + (int64_t)c[k] * b_stride, pol_last) : V(0);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < kRowBatch; ++k)
             if (c[k] != I(-1)) acc += ADVANCED ? (alpha * v[k]) * x[k] : v[k] * x[k];
     }
     return acc;

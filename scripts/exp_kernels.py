@@ -84,8 +84,33 @@ def formats(name, rp, ci, va):
 with torch.cuda.stream(hx.stream):
     rp, ci, va = W.build("cfg3", xp="torch", device=dev)
 formats("cfg3", rp, ci, va)
-del rp, ci, va
+# several right-hand sides (Missing #6 of VERDICT r01): b is n x 8 row-major
+with torch.cuda.stream(hx.stream):
+    n3 = rp.numel() - 1
+    xb = torch.rand(n3, 8, dtype=torch.float64, device=dev)
+    yb = torch.zeros(n3, 8, dtype=torch.float64, device=dev)
+report("csr (a1)", "csr SpMV, 8 right-hand sides, on cfg3", int(va.numel()) * 12 + (n3 + 1) * 4 + 2 * n3 * 8 * 8,
+       timeit(lambda: ex.run("b200_csr_spmv_f64_i32", None, n3, n3, va.numel(), rp, ci, va, xb, 8, 8, yb, 8)))
+del rp, ci, va, xb, yb
 torch.cuda.empty_cache()
+
+# CSR on the other input classes: banded twin (ring kernel), cfg2 (warp_stream x 2 column blocks),
+# skewed twin (rows split over CTAs)
+for cfg in ("cfg2_banded", "cfg2", "cfg2_zipf"):
+    with torch.cuda.stream(hx.stream):
+        rp, ci, va = W.build(cfg, xp="torch", device=dev)
+        n2 = rp.numel() - 1
+        x2 = W.vector(n2, xp="torch", device=dev)
+        y2 = torch.zeros(n2, dtype=torch.float64, device=dev)
+    A2 = api.host_csr(hx, (n2, n2), va, ci, rp)
+    xd2, yd2 = api.host_dense(hx, x2), api.host_dense(hx, y2)
+    h2 = api._host()
+    ms = timeit(lambda: api._hcheck(h2.gkob_apply(A2.h, xd2.h, yd2.h)), stream=hx.stream)
+    report("csr (a1)", "csr SpMV on %s (n=%d nnz=%d, kernel variant %d, %d column blocks)"
+           % (cfg, n2, va.numel(), h2.gkob_csr_kernel_variant(A2.h), max(1, h2.gkob_csr_plan_parts(A2.h))),
+           W.spmv_bytes(n2, n2, va.numel()), ms)
+    del A2, rp, ci, va, x2, y2, xd2, yd2
+    torch.cuda.empty_cache()
 
 # ------------------------------------------------------------------ a7-a13: vector kernels
 n = 32_000_000
@@ -158,4 +183,4 @@ with torch.cuda.stream(ex.stream):
 report("8f-1", "csr::convert_to_ell cfg4 (fp32)", int(va.numel()) * 8 + width * n * 8,
        timeit(lambda: ex.run("b200_csr_convert_to_ell_f32_i32", n, rp, ci, va, width, n, ecols, evals), reps=10))
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(dict(peak_gbs=PEAK, rows=rows), open("gpurun_out/exp_kernels.json", "w"), indent=1)
+json.dump(dict(peak_gbs=PEAK, rows=rows), open(os.environ.get("EXP_KERNELS_OUT", "gpurun_out/exp_kernels.json"), "w"), indent=1)

@@ -711,11 +711,89 @@ void group_tma4()
     }
 }
 
+// ------------------------------------------------------------------------------ group: san
+// small matrices for compute-sanitizer (racecheck / memcheck / synccheck): every shipped CSR variant through
+// a plan, incl. rows longer than a stage, rows split over CTAs, the fused dot and the advanced form
+__global__ void gen_small(int64_t n, int64_t m, const int* rp, int* ci, double* va)
+{
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int64_t len = rp[r + 1] - rp[r];
+    for (int64_t k = 0; k < len; ++k) {
+        const int64_t lo = k * m / len, hi = (k + 1) * m / len;
+        ci[rp[r] + k] = (int)(lo + (int64_t)(hash3(5, r, k) % (uint64_t)(hi - lo)));
+        va[rp[r] + k] = unit(hash3(6, r, k));
+    }
+}
+void group_san()
+{
+    const int64_t n = 20011, m = 40000;
+    std::vector<int> rp(n + 1);
+    int64_t p = 0;
+    for (int64_t r = 0; r < n; ++r) {
+        rp[r] = (int)p;
+        int64_t len = 3 + (r * 7) % 11;
+        if (r == 17) len = 5000;      // longer than a stage
+        if (r == 4242) len = 20000;   // split over CTAs (>= 16384)
+        if (r == n - 1) len = 17001;  // split, last row
+        if (r % 500 == 3) len = 0;
+        p += len;
+    }
+    rp[n] = (int)p;
+    const int64_t nnz = p;
+    int *d_rp, *d_ci;
+    double *d_va, *x, *y, *yref, *scal, *work;
+    CK(cudaMalloc(&d_rp, (n + 1) * 4));
+    CK(cudaMalloc(&d_ci, nnz * 4));
+    CK(cudaMalloc(&d_va, nnz * 8));
+    CK(cudaMalloc(&x, m * 8));
+    CK(cudaMalloc(&y, n * 8));
+    CK(cudaMalloc(&yref, n * 8));
+    CK(cudaMalloc(&scal, 64));
+    CK(cudaMemcpy(d_rp, rp.data(), (n + 1) * 4, cudaMemcpyHostToDevice));
+    gen_small<<<(int)((n + 255) / 256), 256>>>(n, m, d_rp, d_ci, d_va);
+    gen_vec<double><<<(int)((m + 255) / 256), 256>>>(m, x);
+    ref_spmv<double><<<(int)((n + 255) / 256), 256>>>(n, d_rp, d_ci, d_va, x, yref);
+    CK(cudaDeviceSynchronize());
+    b200_ctx* ctx;
+    if (b200_ctx_create(0, nullptr, &ctx) != B200_OK) exit(2);
+    CK(cudaMalloc(&work, 8 * (size_t)b200_cg_fused_work_size_f64(ctx)));
+    b200_csr_plan* plan;
+    if (b200_csr_plan_create_f64_i32(ctx, n, nnz, d_rp, &plan) != B200_OK) exit(2);
+    printf("san: n=%lld nnz=%lld long rows %lld\n", (long long)n, (long long)nnz,
+           (long long)b200_csr_plan_num_long_rows(plan));
+    const double ab[2] = {-1.5, 0.25};
+    CK(cudaMemcpy(scal, ab, 16, cudaMemcpyHostToDevice));
+    std::vector<double> h(n), hr(n);
+    CK(cudaMemcpy(hr.data(), yref, n * 8, cudaMemcpyDeviceToHost));
+    for (int v : {2, 4, 5}) {
+        b200_csr_plan_set_variant(plan, v);
+        CK(cudaMemset(y, 0, n * 8));
+        if (b200_csr_spmv_f64_i32(ctx, plan, n, m, nnz, d_rp, d_ci, d_va, x, 1, 1, y, 1) != B200_OK) exit(3);
+        if (b200_csr_advanced_spmv_f64_i32(ctx, plan, n, m, nnz, d_rp, d_ci, d_va, scal, x, 1, 1, scal + 1, y, 1) !=
+            B200_OK)
+            exit(3);
+        if (b200_csr_spmv_dot_f64_i32(ctx, plan, n, n, nnz, d_rp, d_ci, d_va, x, y, scal + 4, work, nullptr) != B200_OK)
+            exit(3);
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(h.data(), y, n * 8, cudaMemcpyDeviceToHost));
+        double worst = 0;
+        for (int64_t r = 0; r < n; ++r) {
+            const double d = fabs(h[r] - hr[r]) / (fabs(hr[r]) + 1e-300);
+            if (d > worst && fabs(hr[r]) > 1e-12) worst = d;
+        }
+        printf("san: variant %d done, worst relative row difference to the reference kernel %.3e\n", v, worst);
+    }
+    b200_csr_plan_destroy(plan);
+    printf("san: finished\n");
+}
+
 int main(int argc, char** argv)
 {
     const std::string group = argc > 1 ? argv[1] : "micro";
     const std::string name = argc > 2 ? argv[2] : "cfg2";
     if (group == "micro") group_micro();
+    if (group == "san") group_san();
     if (group == "tma4") group_tma4();
     if (group == "base") {
         if (name == "cfg4")
