@@ -588,6 +588,8 @@ class DistMatrix:
         h.gkob_dist_matrix_create_f64_i32.argtypes = [vp, vp, i, i, ll, ll, ll, vp, vp, vp, vp, vp, vp]
         h.gkob_dist_spmv_f64.restype, h.gkob_dist_spmv_f64.argtypes = i, [vp, vp, vp]
         h.gkob_dist_last_ghosts_f64.restype, h.gkob_dist_last_ghosts_f64.argtypes = i, [vp, vp]
+        h.gkob_dist_set_overlap.restype, h.gkob_dist_set_overlap.argtypes = i, [vp, i]
+        h.gkob_dist_pipelined.restype, h.gkob_dist_pipelined.argtypes = i, [vp]
         h.gkob_dist_p2p.restype, h.gkob_dist_p2p.argtypes = i, [vp]
         h.gkob_dist_cg_create_f64.restype = i
         h.gkob_dist_cg_create_f64.argtypes = [vp, i, ll, i, i, ctypes.c_double, i, i]
@@ -684,6 +686,15 @@ class DistMatrix:
         peer-memory path the SpMV reads them in place from the landing slot (last_ghosts() returns
         them), otherwise they are written into the tail of x_ext"""
         _hcheck(_host().gkob_dist_spmv_f64(self.h, x_ext.data_ptr(), y_local.data_ptr()))
+
+    def set_overlap(self, on):
+        """opt into the pipelined exchange: owner blocks applied in arrival order while the rest of x is
+        still in flight (row sums re-associated: 1e-13-equal, not bit-equal, to one GPU)"""
+        _hcheck(_host().gkob_dist_set_overlap(self.h, int(bool(on))))
+
+    @property
+    def pipelined(self):
+        return bool(_host().gkob_dist_pipelined(self.h))
 
     def last_ghosts(self):
         """the ghost values the last apply() gathered from (device tensor of n_ghost entries)"""

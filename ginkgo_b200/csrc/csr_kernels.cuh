@@ -80,7 +80,25 @@ struct DotArgs {
     // rows with at least this many entries are NOT computed by these kernels (0: none): the plan
     // splits them over CTAs (long_rows_kernel); such a row is always the last row of its tile
     int64_t skip_from;
+    // multi-GPU pipelining: before touching b, wait until *wait_flag >= wait_epoch (system scope): the
+    // owner block this launch gathers from has landed (dist.cu, b200_halo_*_staged); nullptr: no wait
+    const unsigned long long* wait_flag;
+    unsigned long long wait_epoch;
 };
+
+// every CTA's thread 0 polls the flag; the barrier publishes the acquire to the block
+template <typename V>
+__device__ __forceinline__ void wait_for_block(const DotArgs<V>& dot)
+{
+    if (dot.wait_flag == nullptr) return;
+    if (threadIdx.x == 0) {
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(dot.wait_flag) : "memory");
+        } while (v < dot.wait_epoch);
+    }
+    __syncthreads();
+}
 
 template <typename V>
 __device__ __forceinline__ void dot_epilogue(V dot_acc, const DotArgs<V>& dot, V* red, bool* is_last)
@@ -198,6 +216,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kWCtasPerSm)
     __shared__ V red[32];
     __shared__ bool is_last;
     if (DOT && dot.ctl && dot.ctl[0] != 0) return;
+    wait_for_block(dot);
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -372,6 +391,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kWCtasPerSm)
     __shared__ V red[32];
     __shared__ bool is_last;
     if (DOT && dot.ctl && dot.ctl[0] != 0) return;
+    wait_for_block(dot);
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;

@@ -73,17 +73,18 @@ struct b200_csr_plan {
     // the original order: same bits, but the gathers of one launch stay inside a slice of b that fits
     // in L2.  The copy holds VALUES: after changing the matrix values in place the caller refreshes it
     // (b200_csr_plan_refresh_values_*); `pos` keeps the split positions for that.
-    static constexpr int kMaxParts = 4;
+    static constexpr int kMaxParts = 16;
     bool allow_copy = false;  // b200_csr_plan_allow_value_copy: the owner promises to refresh after value changes
     int parts = 0;
     const void* src_cols = nullptr;  // the arrays the copy was made from (identity check)
     const void* src_vals = nullptr;
     void* pos = nullptr;             // I[(parts-1) * num_rows]: first entry of a row in part p+1
-    void* part_row_ptrs[kMaxParts] = {nullptr, nullptr, nullptr, nullptr};
-    void* part_cols[kMaxParts] = {nullptr, nullptr, nullptr, nullptr};
-    void* part_vals[kMaxParts] = {nullptr, nullptr, nullptr, nullptr};
-    int64_t part_nnz[kMaxParts] = {0, 0, 0, 0};
-    b200_csr_plan* part_plan[kMaxParts] = {nullptr, nullptr, nullptr, nullptr};
+    void* part_row_ptrs[kMaxParts] = {};
+    void* part_cols[kMaxParts] = {};
+    void* part_vals[kMaxParts] = {};
+    int64_t part_nnz[kMaxParts] = {};
+    int64_t part_bound[kMaxParts + 1] = {};  // part p holds the columns [part_bound[p], part_bound[p+1])
+    b200_csr_plan* part_plan[kMaxParts] = {};
     void* ones = nullptr;  // device {1, 1} in the value type
 };
 

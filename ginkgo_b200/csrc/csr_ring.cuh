@@ -121,6 +121,7 @@ __global__ void __launch_bounds__((NW + NP) * 32, 1)
     __shared__ V red[32];
     __shared__ bool is_last;
     if (DOT && dot.ctl && dot.ctl[0] != 0) return;
+    wait_for_block(dot);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;

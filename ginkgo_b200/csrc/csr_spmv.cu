@@ -226,9 +226,12 @@ __global__ void unsorted_rows_kernel(int64_t num_rows, const I* __restrict__ rp,
 }
 
 // pos[(p - 1) * num_rows + row] = first entry of `row` with column >= bounds[p], p = 1..parts-1
+struct PartBounds {
+    int64_t b[b200_csr_plan::kMaxParts + 1];
+};
 template <typename I>
 __global__ void split_positions_kernel(int64_t num_rows, const I* __restrict__ rp,
-                                       const I* __restrict__ ci, int parts, int64_t col_block,
+                                       const I* __restrict__ ci, int parts, PartBounds bounds,
                                        I* __restrict__ pos)
 {
     const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -236,7 +239,7 @@ __global__ void split_positions_kernel(int64_t num_rows, const I* __restrict__ r
     const int64_t s = rp[row], e = rp[row + 1];
     int64_t k = s;
     for (int p = 1; p < parts; ++p) {
-        const int64_t bound = p * col_block;
+        const int64_t bound = bounds.b[p];
         while (k < e && (int64_t)ci[k] < bound) ++k;
         pos[(int64_t)(p - 1) * num_rows + row] = (I)k;
     }
@@ -294,13 +297,19 @@ b200_status plan_create(b200_ctx* ctx, int64_t num_rows, int64_t nnz, const I* r
 
 // Builds the copy; returns B200_OK with plan->parts == 0 when the matrix does not qualify
 // (unsorted rows, no memory): the caller then simply keeps the original arrays.
+// bounds_host (optional): parts + 1 ascending column boundaries, bounds[0] = 0, bounds[parts] = num_cols;
+// nullptr: parts equal column blocks
 template <typename V, typename I>
 b200_status plan_reblock(b200_ctx* ctx, b200_csr_plan* plan, int64_t num_rows, int64_t num_cols,
-                         int64_t nnz, const I* rp, const I* ci, const V* va, int parts)
+                         int64_t nnz, const I* rp, const I* ci, const V* va, int parts,
+                         const int64_t* bounds_host = nullptr)
 {
     plan_drop_parts(plan);
     if (parts < 2 || num_rows == 0 || nnz == 0) return B200_OK;
-    if (parts > b200_csr_plan::kMaxParts) parts = b200_csr_plan::kMaxParts;
+    if (parts > b200_csr_plan::kMaxParts) {
+        if (bounds_host) return B200_OK;  // cannot honour the requested boundaries
+        parts = b200_csr_plan::kMaxParts;
+    }
     const unsigned grid = (unsigned)ceildiv(num_rows, 256);
     int* flag = (int*)ctx->scratch(sizeof(int));
     if (!flag) return B200_OK;
@@ -317,11 +326,16 @@ b200_status plan_reblock(b200_ctx* ctx, b200_csr_plan* plan, int64_t num_rows, i
               cudaMalloc((void**)&sums, sizeof(I) * (size_t)scan::num_tiles(num_rows + 1)) == cudaSuccess &&
               cudaMalloc(&plan->ones, 2 * sizeof(V)) == cudaSuccess;
     const int64_t col_block = ceildiv(num_cols, (int64_t)parts);
+    PartBounds pb;
+    for (int p = 0; p <= parts; ++p) {
+        pb.b[p] = bounds_host ? bounds_host[p] : (p == parts ? num_cols : p * col_block);
+        plan->part_bound[p] = pb.b[p];
+    }
     b200_status st = B200_OK;
     if (ok) {
         plan_ones_kernel<V><<<1, 1, 0, ctx->stream>>>((V*)plan->ones);
         ctx->launches++;
-        split_positions_kernel<I><<<grid, 256, 0, ctx->stream>>>(num_rows, rp, ci, parts, col_block, pos);
+        split_positions_kernel<I><<<grid, 256, 0, ctx->stream>>>(num_rows, rp, ci, parts, pb, pos);
         ctx->launches++;
     }
     for (int p = 0; p < parts && ok && st == B200_OK; ++p) {
@@ -528,6 +542,39 @@ b200_status plan_tune(b200_ctx* ctx, b200_csr_plan* plan, int64_t num_rows, int6
     return st;
 }
 
+// one part of the column-blocked copy: c = A_p b (accumulate == 0) or c += A_p b.  Parts applied in
+// ascending order reproduce the row sums of the whole matrix bit for bit; any other order (the
+// multi-GPU pipeline applies owner blocks in arrival order) changes the association of the sums.
+template <typename V, typename I>
+b200_status spmv_part(b200_ctx* ctx, const b200_csr_plan* plan, int part, int accumulate, const V* b,
+                      int64_t b_stride, V* c, int64_t c_stride, const unsigned long long* wait_flag,
+                      unsigned long long wait_epoch)
+{
+    B200_REQUIRE(ctx && plan && b && c, "null argument");
+    B200_REQUIRE(part >= 0 && part < plan->parts, "no such part");
+    const b200_csr_plan* sub = plan->part_plan[part];
+    if (plan->part_nnz[part] == 0) {  // empty block: only the first one has something to do (c = 0)
+        if (!accumulate) {
+            B200_REQUIRE(c_stride == 1, "empty first block needs a contiguous c");
+            B200_CUDA_CHECK(cudaMemsetAsync(c, 0, sizeof(V) * (size_t)plan->num_rows, ctx->stream));
+        }
+        return B200_OK;
+    }
+    const Variant v = pick_variant(plan->part_cols[part], plan->part_vals[part], sub);
+    DotArgs<V> dot{};
+    dot.wait_flag = wait_flag;
+    dot.wait_epoch = wait_epoch;
+    const V* ones = (const V*)plan->ones;
+    if (!accumulate)
+        return launch_planned<V, I, false, false>(ctx, sub, v, plan->part_nnz[part],
+                                                  (const I*)plan->part_row_ptrs[part], (const I*)plan->part_cols[part],
+                                                  (const V*)plan->part_vals[part], nullptr, b, b_stride, nullptr, c,
+                                                  c_stride, dot);
+    return launch_planned<V, I, true, false>(ctx, sub, v, plan->part_nnz[part], (const I*)plan->part_row_ptrs[part],
+                                             (const I*)plan->part_cols[part], (const V*)plan->part_vals[part], ones, b,
+                                             b_stride, ones + 1, c, c_stride, dot);
+}
+
 // values of the column-blocked copy again from the caller's (changed) values array
 template <typename V, typename I>
 __global__ void split_values_kernel(int64_t num_rows, const I* __restrict__ rp, const V* __restrict__ va, int parts,
@@ -644,6 +691,31 @@ void b200_csr_plan_destroy(b200_csr_plan* plan)
                                                        const VT* values)                       \
     {                                                                                          \
         return b200::csr::plan_refresh_values<VT, IT>(ctx, plan, num_rows, row_ptrs, values);  \
+    }                                                                                          \
+    b200_status b200_csr_plan_split_columns_##V##_##I(                                         \
+        b200_ctx* ctx, b200_csr_plan* plan, int64_t num_rows, int64_t num_cols, int64_t nnz,   \
+        const IT* row_ptrs, const IT* col_idxs, const VT* values, int32_t parts,               \
+        const int64_t* bounds_host)                                                            \
+    {                                                                                          \
+        B200_REQUIRE(ctx && plan && bounds_host, "null argument");                             \
+        B200_REQUIRE(plan->num_rows == num_rows && plan->nnz == nnz, "plan does not match");   \
+        for (int p = 0; p < parts; ++p)                                                        \
+            B200_REQUIRE(bounds_host[p] <= bounds_host[p + 1], "bounds must ascend");          \
+        B200_REQUIRE(bounds_host[0] == 0 && bounds_host[parts] == num_cols, "bounds must cover the columns"); \
+        b200_status st = b200::csr::plan_reblock<VT, IT>(ctx, plan, num_rows, num_cols, nnz, row_ptrs, col_idxs,    \
+                                                        values, parts, bounds_host);           \
+        if (st == B200_OK)                                                                     \
+            for (int p = 0; p < plan->parts; ++p) plan->part_plan[p]->variant = plan->variant; \
+        return st;                                                                             \
+    }                                                                                          \
+    b200_status b200_csr_spmv_part_##V##_##I(b200_ctx* ctx, const b200_csr_plan* plan, int32_t part,      \
+                                             int32_t accumulate, const VT* b, int64_t b_stride, VT* c,    \
+                                             int64_t c_stride, const uint64_t* wait_flag,      \
+                                             uint64_t wait_epoch)                              \
+    {                                                                                          \
+        return b200::csr::spmv_part<VT, IT>(ctx, plan, part, accumulate, b, b_stride, c, c_stride,        \
+                                            (const unsigned long long*)wait_flag,              \
+                                            (unsigned long long)wait_epoch);                   \
     }                                                                                          \
     b200_status b200_csr_spmv_##V##_##I(                                                       \
         b200_ctx* ctx, const b200_csr_plan* plan, int64_t num_rows, int64_t num_cols,          \

@@ -159,6 +159,11 @@ struct b200_halo {
     // (nearly) all of x, e.g. uniformly random columns): pushed with 16-byte remote stores
     bool runs = false;
     int64_t* run_base_dev = nullptr;  // device: first owned index of the run, per peer
+    // pipelined exchange (b200_halo_exchange_staged_*): the push runs on its own stream, destinations
+    // in ring order (rank + 1, rank + 2, ...), one arrival flag per source
+    cudaStream_t push_stream = nullptr;
+    cudaEvent_t ev_ready = nullptr, ev_pushed = nullptr;
+    unsigned* dst_ticket_dev = nullptr;  // device [nranks], zero, self-resetting
     uint64_t host_epoch = 0;          // exchanges issued from the host outside stream capture
     bool captured = false;            // an exchange was captured into a graph: host_epoch is unreliable
     int64_t* meta_dev = nullptr;    // device: send_off[nranks+1] | send_cnt[nranks] | recv_cnt[nranks]
@@ -395,6 +400,88 @@ __global__ void __launch_bounds__(256) halo_push_runs_kernel(HaloDev h, const V*
             st_release_sys(h.peer_flag[threadIdx.x] + par * h.nranks, e);
         }
     }
+}
+
+// Pipelined variant of the run push: destinations in RING order (rank + 1, rank + 2, ...; every rank
+// sends to a different peer in every step, so the first block a rank needs -- from rank - 1 -- is
+// complete after 1 / (P - 1) of the exchange), blocks dealt step-major, and the CTA that completes a
+// destination releases that destination's flag at once.  Runs on its own stream next to the SpMV
+// launches that consume the blocks in arrival order (few CTAs: NVLink is saturated by ~100).
+template <typename V>
+__global__ void __launch_bounds__(256) halo_push_staged_kernel(HaloDev h, const V* __restrict__ x,
+                                                              const int64_t* __restrict__ run_base,
+                                                              unsigned* __restrict__ dst_ticket)
+{
+    const uint64_t e = *(volatile uint64_t*)h.epoch + 1;
+    const int par = (int)(e & 1);
+    const int64_t* send_cnt = h.meta + h.nranks + 1;
+    int64_t total = 0;
+    for (int p = 0; p < h.nranks; ++p) total += ceildiv(send_cnt[p], (int64_t)kRunBlock);
+    constexpr int kPer = 16 / (int)sizeof(V);
+    __shared__ bool last;
+    for (int64_t blk = blockIdx.x; blk < total; blk += gridDim.x) {
+        int p = 0;
+        int64_t first = 0, nb = 0;
+        for (int s = 1; s < h.nranks; ++s) {  // ring order
+            p = (h.rank + s) % h.nranks;
+            nb = ceildiv(send_cnt[p], (int64_t)kRunBlock);
+            if (blk < first + nb) break;
+            first += nb;
+        }
+        const int64_t cnt = send_cnt[p];
+        const V* src = x + run_base[p];
+        V* dst = (V*)h.peer_slot[par * h.nranks + p];
+        const int64_t lo = (blk - first) * kRunBlock;
+        int64_t hi = lo + kRunBlock;
+        if (hi > cnt) hi = cnt;
+        int64_t head = (int64_t)(((16 - ((uintptr_t)(dst + lo) & 15)) & 15) / sizeof(V));
+        if (head > hi - lo) head = hi - lo;
+        const int64_t body = (hi - lo - head) / kPer;
+        const int tid = threadIdx.x;
+        if (tid < head) dst[lo + tid] = src[lo + tid];
+        const V* s2 = src + lo + head;
+        V* d2 = dst + lo + head;
+        V v[4][kPer];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = tid + 256 * u;
+            if (i < body) {
+#pragma unroll
+                for (int k = 0; k < kPer; ++k) v[u][k] = s2[i * kPer + k];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = tid + 256 * u;
+            if (i < body) {
+                if (sizeof(V) == 8) {
+                    *reinterpret_cast<double2*>(d2 + i * kPer) = make_double2((double)v[u][0], (double)v[u][kPer - 1]);
+                } else {
+                    *reinterpret_cast<float4*>(d2 + i * kPer) =
+                        make_float4((float)v[u][0], (float)v[u][1 % kPer], (float)v[u][2 % kPer], (float)v[u][3 % kPer]);
+                }
+            }
+        }
+        const int64_t done = lo + head + body * kPer;
+        if (tid < hi - done) dst[done + tid] = src[done + tid];
+        // destination p complete?  (the CTA that stores its last block releases p's flag)
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence_system();
+            last = atomicAdd(dst_ticket + p, 1u) == (unsigned)nb - 1;
+            if (last) {
+                dst_ticket[p] = 0;
+                __threadfence_system();
+                st_release_sys(h.peer_flag[p] + par * h.nranks, e);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void halo_epoch_advance_kernel(HaloDev h)
+{
+    *(volatile uint64_t*)h.epoch = *(volatile uint64_t*)h.epoch + 1;
 }
 
 // wait only: acquire the epoch flag of every rank this one receives from; the consumer reads the
@@ -681,6 +768,10 @@ void b200_halo_destroy(b200_halo* h)
         cudaFree(h->epoch_dev);
         cudaFree(h->ticket_dev);
         cudaFree(h->run_base_dev);
+        cudaFree(h->dst_ticket_dev);
+        if (h->push_stream) cudaStreamDestroy(h->push_stream);
+        if (h->ev_ready) cudaEventDestroy(h->ev_ready);
+        if (h->ev_pushed) cudaEventDestroy(h->ev_pushed);
     }
     delete h;
 }
@@ -812,9 +903,84 @@ int64_t b200_halo_num_send(const b200_halo* h) { return h->n_send; }
         h->host_epoch++;                                                                       \
         *x_ext_out = own;                                                                      \
         return B200_OK;                                                                        \
+    }                                                                                          \
+    /* Pipelined exchange for matrices whose ghosts are contiguous runs of every peer (dense      */ \
+    /* ghosts): begin() copies the owned entries into the rank's extended vector, starts the ring- */ \
+    /* ordered push on a second stream and returns the extended vector, the per-source arrival    */ \
+    /* flags (device, index = source rank) and the epoch to wait for; the caller gathers from the  */ \
+    /* owner blocks as they arrive (b200_csr_spmv_part_* with wait_flag = flags + src) and calls    */ \
+    /* end() after the last block.  B200_ERR_UNSUPPORTED when the halo does not qualify.           */ \
+    b200_status b200_halo_exchange_staged_begin_##V(b200_ctx* ctx, b200_comm* comm, b200_halo* h, \
+                                                    const VT* x_owned, VT** x_ext_out,         \
+                                                    const uint64_t** flags_out,                \
+                                                    uint64_t* epoch_out)                       \
+    {                                                                                          \
+        (void)comm;                                                                            \
+        B200_REQUIRE(ctx && h && x_owned && x_ext_out && flags_out && epoch_out, "null argument"); \
+        cudaStreamCaptureStatus cap_st = cudaStreamCaptureStatusNone;                          \
+        cudaStreamIsCapturing(ctx->stream, &cap_st);                                           \
+        if (!h->p2p || !h->runs || h->captured || cap_st != cudaStreamCaptureStatusNone) {     \
+            b200::set_error("staged halo exchange needs peer memory, contiguous runs, no graphs"); \
+            return B200_ERR_UNSUPPORTED;                                                       \
+        }                                                                                      \
+        if (!h->push_stream) {                                                                 \
+            B200_CUDA_CHECK(cudaStreamCreateWithFlags(&h->push_stream, cudaStreamNonBlocking)); \
+            B200_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));   \
+            B200_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_pushed, cudaEventDisableTiming));  \
+            B200_CUDA_CHECK(cudaMalloc((void**)&h->dst_ticket_dev, sizeof(unsigned) * h->nranks)); \
+            B200_CUDA_CHECK(cudaMemset(h->dst_ticket_dev, 0, sizeof(unsigned) * h->nranks));   \
+        }                                                                                      \
+        const uint64_t e = h->host_epoch + 1;                                                  \
+        const int par = (int)(e & 1);                                                          \
+        VT* own = (VT*)((char*)h->win.local + h->buf_off[par]);                                \
+        b200::dist::HaloDev d{h->nranks, h->rank, h->n_local, h->n_ghost, h->n_send,           \
+                              h->send_idx, h->meta_dev, h->peer_slot_dev,                      \
+                              h->peer_flag_dev, (uint64_t*)h->win.local,                       \
+                              {(char*)h->win.local + h->slot_off[0],                           \
+                               (char*)h->win.local + h->slot_off[1]},                          \
+                              h->epoch_dev, h->ticket_dev, h->err_dev};                        \
+        B200_CUDA_CHECK(cudaEventRecord(h->ev_ready, ctx->stream));                            \
+        B200_CUDA_CHECK(cudaStreamWaitEvent(h->push_stream, h->ev_ready, 0));                  \
+        b200::dist::halo_push_staged_kernel<VT><<<96, 256, 0, h->push_stream>>>(               \
+            d, x_owned, h->run_base_dev, h->dst_ticket_dev);                                   \
+        B200_LAUNCH_CHECK(ctx);                                                                \
+        B200_CUDA_CHECK(cudaEventRecord(h->ev_pushed, h->push_stream));                        \
+        B200_CUDA_CHECK(cudaMemcpyAsync(own, x_owned, (size_t)h->n_local * sizeof(VT),         \
+                                        cudaMemcpyDeviceToDevice, ctx->stream));               \
+        *x_ext_out = own;                                                                      \
+        *flags_out = (const uint64_t*)h->win.local + (size_t)par * h->nranks;                  \
+        *epoch_out = e;                                                                        \
+        return B200_OK;                                                                        \
     }
 B200_DEF_COMM(f64, double)
 B200_DEF_COMM(f32, float)
+
+/* after the last owner block has been consumed: advance the epoch on the compute stream and make
+ * that stream wait for the push (it reads the caller's x_owned) */
+b200_status b200_halo_exchange_staged_end(b200_ctx* ctx, b200_halo* h)
+{
+    B200_REQUIRE(ctx && h && h->push_stream, "no staged exchange in flight");
+    b200::dist::HaloDev d{h->nranks, h->rank, h->n_local, h->n_ghost, h->n_send,
+                          h->send_idx, h->meta_dev, h->peer_slot_dev,
+                          h->peer_flag_dev, (uint64_t*)h->win.local,
+                          {(char*)h->win.local + h->slot_off[0], (char*)h->win.local + h->slot_off[1]},
+                          h->epoch_dev, h->ticket_dev, h->err_dev};
+    b200::dist::halo_epoch_advance_kernel<<<1, 1, 0, ctx->stream>>>(d);
+    B200_LAUNCH_CHECK(ctx);
+    B200_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, h->ev_pushed, 0));
+    h->host_epoch++;
+    return B200_OK;
+}
+/* counts of the halo (host arrays of nranks entries): what this rank receives from / sends to each peer */
+b200_status b200_halo_counts(const b200_halo* h, int64_t* recv_counts, int64_t* send_counts)
+{
+    B200_REQUIRE(h != nullptr, "null halo");
+    for (int p = 0; p < h->nranks; ++p) {
+        if (recv_counts) recv_counts[p] = h->recv_count[p];
+        if (send_counts) send_counts[p] = h->send_count[p];
+    }
+    return B200_OK;
+}
 
 // all-gather of `bytes_per_rank` raw device bytes per rank (set-up exchanges of index lists
 // and counts: distributed::Matrix::read_distributed)

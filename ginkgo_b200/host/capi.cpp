@@ -572,6 +572,14 @@ int gkob_dist_spmv_f64(void* dist, double* x_ext, double* y_local)
     });
 }
 
+// pipelined (owner-block, arrival-order) exchange on / off; returns through *active whether the next
+// gkob_dist_spmv_f64 will use it (collective decisions are local: every rank qualifies alike)
+int gkob_dist_set_overlap(void* dist, int on)
+{
+    return guarded([&] { static_cast<DistHandle*>(dist)->A->set_overlap(on != 0); });
+}
+int gkob_dist_pipelined(void* dist) { return static_cast<DistHandle*>(dist)->A->pipelined() ? 1 : 0; }
+
 // ghosts_out[0 .. n_ghost) = the ghost entries the last gkob_dist_spmv_f64 gathered from (the peer-memory
 // path reads them in place from the landing slot instead of copying them into the caller's x_ext)
 int gkob_dist_last_ghosts_f64(void* dist, double* ghosts_out)

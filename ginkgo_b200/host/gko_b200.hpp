@@ -128,6 +128,8 @@ GKOB_V(float, f32)
         static constexpr auto csr_plan_create = b200_csr_plan_create_##S##_##T;                 \
         static constexpr auto csr_plan_tune = b200_csr_plan_tune_##S##_##T;                     \
         static constexpr auto csr_plan_refresh_values = b200_csr_plan_refresh_values_##S##_##T; \
+        static constexpr auto csr_plan_split_columns = b200_csr_plan_split_columns_##S##_##T;   \
+        static constexpr auto csr_spmv_part = b200_csr_spmv_part_##S##_##T;                     \
         static constexpr auto csr_spmv = b200_csr_spmv_##S##_##T;                               \
         static constexpr auto csr_advanced_spmv = b200_csr_advanced_spmv_##S##_##T;             \
         static constexpr auto csr_spmv_dot = b200_csr_spmv_dot_##S##_##T;                       \

@@ -72,12 +72,14 @@ struct cabi<double> {
     static constexpr auto allreduce = b200_comm_allreduce_sum_f64;
     static constexpr auto halo_exchange = b200_halo_exchange_f64;
     static constexpr auto halo_exchange_inplace = b200_halo_exchange_inplace_f64;
+    static constexpr auto halo_exchange_staged_begin = b200_halo_exchange_staged_begin_f64;
 };
 template <>
 struct cabi<float> {
     static constexpr auto allreduce = b200_comm_allreduce_sum_f32;
     static constexpr auto halo_exchange = b200_halo_exchange_f32;
     static constexpr auto halo_exchange_inplace = b200_halo_exchange_inplace_f32;
+    static constexpr auto halo_exchange_staged_begin = b200_halo_exchange_staged_begin_f32;
 };
 
 // the all-reduce behind a distributed vector's dots and norms
@@ -555,7 +557,11 @@ public:
             std::fprintf(stderr, "[gko_b200] rank %d: peer-memory halo unavailable (%s), using NCCL\n",
                          comm->rank(), b200_last_error());
     }
-    ~Matrix() { b200_halo_destroy(halo_); }
+    ~Matrix()
+    {
+        b200_csr_plan_destroy(owner_plan_);
+        b200_halo_destroy(halo_);
+    }
 
     // experimental::distributed::Matrix::read_distributed (core/distributed/matrix.cpp:300-380):
     // every rank passes the (row-major sorted) global matrix or at least its own rows; the rows
@@ -637,6 +643,7 @@ public:
     // y_local = A x   (x_ext: owned part filled by the caller, ghosts by the exchange)
     void apply_extended(matrix::Dense<V>* x_ext, matrix::Dense<V>* y_local) const
     {
+        if (apply_pipelined(x_ext, y_local)) return;
         // peer memory: the local SpMV gathers straight from the landing slots (no ghost copy; the
         // ghosts of this call are then in last_extended(), not in x_ext)
         V* in_place = nullptr;
@@ -655,6 +662,80 @@ public:
     }
     // the extended vector [owned | ghosts] the last apply_extended gathered from
     const V* last_extended() const { return last_ext_; }
+    // 1 once apply_extended runs the pipelined exchange (B200_DIST_OVERLAP=1 / set_overlap(true) and a
+    // qualifying halo)
+    bool pipelined() const { return owner_plan_ != nullptr && overlap_want_ == 1 && !overlap_failed_; }
+    void set_overlap(bool on) const { overlap_want_ = on ? 1 : 0; }
+
+protected:
+    // Opt-in (B200_DIST_OVERLAP=1): exchange and SpMV pipelined by OWNER BLOCK.  The local matrix is kept
+    // a second time split by the owner of the column ([owned | ghosts of rank 0 | ...] are contiguous
+    // column ranges of the local numbering); the push runs on its own stream in ring order, and this
+    // rank applies its own block first, then the block of rank-1, rank-2, ... as each lands (the SpMV of
+    // a block waits for that block's arrival flag itself).  The reference overlaps the local block with
+    // the exchange the same way (core/distributed/matrix.cpp:450-509: local_mtx_ / non_local_mtx_).
+    // Row sums are associated in ARRIVAL order, not left to right: results agree with the single-GPU
+    // ones to rounding (1e-13 relative), not bit for bit -- hence opt-in.
+    bool apply_pipelined(matrix::Dense<V>* x_ext, matrix::Dense<V>* y_local) const
+    {
+        if (overlap_want_ < 0)
+            overlap_want_ = (getenv("B200_DIST_OVERLAP") && atoi(getenv("B200_DIST_OVERLAP")) != 0) ? 1 : 0;
+        const int P = comm_->size(), r = comm_->rank();
+        if (overlap_want_ != 1 || overlap_failed_ || P < 2 || P > 16 || !b200_halo_p2p_enabled(halo_) ||
+            x_ext->get_stride() != 1 || y_local->get_size().cols != 1)
+            return false;
+        auto ctx = exec_->ctx();
+        std::vector<int64> recv(P, 0);
+        if (!owner_plan_) {
+            GKOB_CALL(b200_halo_counts(halo_, recv.data(), nullptr));
+            std::vector<int64> bounds(P + 1, 0);
+            bounds[1] = (int64)n_local_cols_;
+            int k = 1;
+            for (int q = 0; q < P; ++q) {
+                if (q == r) continue;
+                bounds[k + 1] = bounds[k] + recv[q];
+                ++k;
+            }
+            const auto nnz = local_->get_num_stored_elements();
+            b200_csr_plan* p = nullptr;
+            GKOB_CALL((viabi<V, I>::csr_plan_create(ctx, local_->get_size().rows, nnz, local_->get_const_row_ptrs(), &p)));
+            b200_csr_plan_allow_value_copy(p, 1);
+            b200_status st = viabi<V, I>::csr_plan_tune(ctx, p, local_->get_size().rows, local_->get_size().cols, nnz,
+                                                       local_->get_const_row_ptrs(), local_->get_const_col_idxs(),
+                                                       local_->get_const_values());
+            if (st == B200_OK)
+                st = viabi<V, I>::csr_plan_split_columns(ctx, p, local_->get_size().rows, local_->get_size().cols, nnz,
+                                                         local_->get_const_row_ptrs(), local_->get_const_col_idxs(),
+                                                         local_->get_const_values(), P, bounds.data());
+            if (st != B200_OK || b200_csr_plan_parts(p) != P) {
+                b200_csr_plan_destroy(p);
+                overlap_failed_ = true;
+                return false;
+            }
+            owner_plan_ = p;
+            recv_counts_ = recv;
+        }
+        V* b = nullptr;
+        const uint64_t* flags = nullptr;
+        uint64_t epoch = 0;
+        if (cabi<V>::halo_exchange_staged_begin(ctx, comm_->get(), halo_, x_ext->get_const_values(), &b, &flags,
+                                                &epoch) != B200_OK) {
+            overlap_failed_ = true;
+            return false;
+        }
+        for (int s = 0; s < P; ++s) {
+            const int src = (r - s + P) % P;
+            if (s > 0 && recv_counts_[src] == 0) continue;  // nothing comes from there: no flag either
+            const int part = s == 0 ? 0 : (src < r ? src + 1 : src);
+            GKOB_CALL((viabi<V, I>::csr_spmv_part(ctx, owner_plan_, part, s > 0 ? 1 : 0, b, 1, y_local->get_values(),
+                                                  y_local->get_stride(), s == 0 ? nullptr : flags + src, epoch)));
+        }
+        GKOB_CALL(b200_halo_exchange_staged_end(ctx, halo_));
+        last_ext_ = b;
+        return true;
+    }
+
+public:
     // a distributed::Vector of this matrix's row / column partition
     std::unique_ptr<Vector<V>> create_row_vector(size_type global_rows) const
     {
@@ -702,6 +783,10 @@ protected:
 private:
     mutable std::unique_ptr<matrix::Dense<V>> x_ext_;
     mutable const V* last_ext_ = nullptr;
+    mutable b200_csr_plan* owner_plan_ = nullptr;  // the local matrix split by column owner (pipelined apply)
+    mutable std::vector<int64> recv_counts_;
+    mutable bool overlap_failed_ = false;
+    mutable int overlap_want_ = -1;  // -1: take B200_DIST_OVERLAP
     std::shared_ptr<communicator> comm_;
     std::unique_ptr<matrix::Csr<V, I>> local_;
     size_type n_ghost_;

@@ -136,6 +136,21 @@ b200_status b200_pipe_join(b200_pipe* pipe);
     b200_status b200_csr_plan_refresh_values_##V##_##I(b200_ctx* ctx, b200_csr_plan* plan,   \
                                                        int64_t num_rows, const IT* row_ptrs, \
                                                        const VT* values);                    \
+    /* column-blocked copy with GIVEN boundaries (parts + 1 ascending host values, 0 .. num_cols;  \
+     * needs b200_csr_plan_allow_value_copy, at most 16 parts, column-sorted rows; plan parts == 0 \
+     * afterwards if the matrix did not qualify) and the apply of ONE part: c = A_p b              \
+     * (accumulate 0) or c += A_p b, optionally after *wait_flag >= wait_epoch (system-scope        \
+     * acquire: the multi-GPU pipeline passes the arrival flag of the owner block the part         \
+     * gathers from).  Parts applied in ascending order give the bits of the whole matrix; any     \
+     * other order re-associates the row sums. */                                                  \
+    b200_status b200_csr_plan_split_columns_##V##_##I(                                       \
+        b200_ctx* ctx, b200_csr_plan* plan, int64_t num_rows, int64_t num_cols, int64_t nnz, \
+        const IT* row_ptrs, const IT* col_idxs, const VT* values, int32_t parts,             \
+        const int64_t* bounds_host);                                                         \
+    b200_status b200_csr_spmv_part_##V##_##I(b200_ctx* ctx, const b200_csr_plan* plan,       \
+                                             int32_t part, int32_t accumulate, const VT* b,  \
+                                             int64_t b_stride, VT* c, int64_t c_stride,      \
+                                             const uint64_t* wait_flag, uint64_t wait_epoch); \
     b200_status b200_csr_spmv_##V##_##I(                                                     \
         b200_ctx* ctx, const b200_csr_plan* plan, int64_t num_rows, int64_t num_cols,        \
         int64_t nnz, const IT* row_ptrs, const IT* col_idxs, const VT* values, const VT* b,  \
@@ -699,6 +714,8 @@ b200_status b200_comm_enable_p2p(b200_ctx* ctx, b200_comm* comm);
 b200_status b200_halo_enable_p2p(b200_ctx* ctx, b200_comm* comm, b200_halo* halo);
 int32_t b200_comm_p2p_enabled(const b200_comm* comm);
 int32_t b200_halo_p2p_enabled(const b200_halo* halo);
+b200_status b200_halo_exchange_staged_end(b200_ctx* ctx, b200_halo* halo);
+b200_status b200_halo_counts(const b200_halo* halo, int64_t* recv_counts, int64_t* send_counts);
 int32_t b200_comm_p2p_error(b200_ctx* ctx, const b200_comm* comm);
 #define B200_DECL_COMM(V, VT)                                                                  \
     b200_status b200_comm_allreduce_sum_##V(b200_ctx* ctx, b200_comm* comm, VT* buf,           \
@@ -713,7 +730,14 @@ int32_t b200_comm_p2p_error(b200_ctx* ctx, const b200_comm* comm);
     /* window; *x_ext_out = [owned | ghosts], valid until the exchange after the next one.     */ \
     /* B200_ERR_UNSUPPORTED without peer memory or after a captured exchange: use the call above */ \
     b200_status b200_halo_exchange_inplace_##V(b200_ctx* ctx, b200_comm* comm, b200_halo* halo, \
-                                               const VT* x_owned, VT** x_ext_out);
+                                               const VT* x_owned, VT** x_ext_out);             \
+    /* pipelined exchange (dense ghosts in contiguous runs, peer memory, not capturable): the push \
+     * runs on its own stream in ring order (rank+1, rank+2, ...), flags[src] (device) reaches     \
+     * *epoch_out when source src has landed in *x_ext_out; consume the owner blocks in arrival    \
+     * order with b200_csr_spmv_part_*, then call b200_halo_exchange_staged_end */                 \
+    b200_status b200_halo_exchange_staged_begin_##V(b200_ctx* ctx, b200_comm* comm, b200_halo* halo, \
+                                                    const VT* x_owned, VT** x_ext_out,         \
+                                                    const uint64_t** flags_out, uint64_t* epoch_out);
 B200_DECL_COMM(f64, double)
 B200_DECL_COMM(f32, float)
 /* all-gather of raw device bytes (set-up exchanges of counts and index lists) */

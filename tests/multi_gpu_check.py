@@ -17,6 +17,15 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ex = api.HostExecutor(local)
 dev = ex.device
 ok = True
+OVERLAP = os.environ.get("B200_DIST_OVERLAP", "0") == "1"
+
+
+def rows_equal(y, yref):
+    """bit-equal on the default paths; the pipelined exchange re-associates the row sums"""
+    if not OVERLAP:
+        return torch.equal(y, yref)
+    return bool(((y - yref).abs().max() <= 1e-13 * yref.abs().max()).item())
+
 for name, kw in [("lap3d_40", dict(grid=40, dims=3)), ("cfg2_small", dict(n=200000))]:
     with torch.cuda.stream(ex.stream):
         if name.startswith("lap"):
@@ -44,7 +53,7 @@ for name, kw in [("lap3d_40", dict(grid=40, dims=3)), ("cfg2_small", dict(n=2000
         y = torch.zeros(A.n_local, dtype=torch.float64, device=dev)
     A.apply(x_ext, y)
     ex.synchronize()
-    same = torch.equal(y, y1[r0:r1])
+    same = rows_equal(y, y1[r0:r1])
     # repeated exchanges with changing data (epochs / double-buffered landing slots)
     for k in range(1, 6):
         with torch.cuda.stream(ex.stream):
@@ -54,7 +63,7 @@ for name, kw in [("lap3d_40", dict(grid=40, dims=3)), ("cfg2_small", dict(n=2000
         api._hcheck(_h.gkob_apply(A1.h, xdk.h, yd1.h))
         A.apply(x_ext, y)
         ex.synchronize()
-        same = same and torch.equal(y, y1[r0:r1])
+        same = same and rows_equal(y, y1[r0:r1])
     ok &= same
     with torch.cuda.stream(ex.stream):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -66,8 +75,9 @@ for name, kw in [("lap3d_40", dict(grid=40, dims=3)), ("cfg2_small", dict(n=2000
             A.apply(x_ext, y)
         e1.record(ex.stream)
     ex.synchronize()
-    print("rank %d %s: n_local=%d n_ghost=%d p2p=%d spmv bit-equal=%s  %.1f us/apply"
-          % (rank, name, A.n_local, A.n_ghost, A.p2p, same, e0.elapsed_time(e1) * 10), flush=True)
+    print("rank %d %s: n_local=%d n_ghost=%d p2p=%d pipelined=%s spmv %s=%s  %.1f us/apply"
+          % (rank, name, A.n_local, A.n_ghost, A.p2p, A.pipelined, "1e-13-equal" if OVERLAP else "bit-equal", same,
+             e0.elapsed_time(e1) * 10), flush=True)
     # the same matrix through read_distributed: split, renumbering and send lists built by the
     # library's device kernels + its own all-gather (no torch.distributed in the set-up)
     rp_h, ci_h, va_h = rp.cpu().numpy(), ci.cpu().numpy(), va.cpu().numpy()
@@ -89,7 +99,7 @@ for name, kw in [("lap3d_40", dict(grid=40, dims=3)), ("cfg2_small", dict(n=2000
         api._hcheck(_h.gkob_apply(A1.h, xdk.h, yd1.h))
         A2.apply(x2, y2)
         ex.synchronize()
-        same2 = same2 and torch.equal(y2, y1[q0:q1])
+        same2 = same2 and rows_equal(y2, y1[q0:q1])
         same2 = same2 and torch.equal(A2.last_ghosts().cpu(), xk.cpu()[torch.from_numpy(A2.ghost_globals)])
     ok &= same2
     print("rank %d %s: read_distributed n_local=%d n_ghost=%d p2p=%d spmv bit-equal=%s"

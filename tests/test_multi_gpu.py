@@ -2,7 +2,7 @@
 distributed SpMV rows bit-identical to the single-GPU rows (torch-built partition and read_distributed),
 every host-layer solver on distributed::Matrix against the same solver on one GPU, the fused distributed CG --
 once per exchange path: peer memory with 16-byte run pushes + in-place ghosts, peer memory with the indexed
-push, NCCL send/recv."""
+push, NCCL send/recv, and the opt-in pipelined exchange (owner blocks in arrival order, 1e-13-equal)."""
 import os
 import subprocess
 import sys
@@ -21,14 +21,14 @@ def _ngpu():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("path", ["p2p_runs", "p2p_indexed", "nccl"])
+@pytest.mark.parametrize("path", ["p2p_runs", "p2p_indexed", "nccl", "p2p_overlap"])
 def test_two_gpu_parity(path):
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
     env = dict(os.environ)
     env.update({"p2p_runs": {"B200_P2P": "1"}, "p2p_indexed": {"B200_P2P": "1", "B200_HALO_RUNS": "0"},
-                "nccl": {"B200_P2P": "0"}}[path])
-    port = {"p2p_runs": 29611, "p2p_indexed": 29612, "nccl": 29613}[path]
+                "nccl": {"B200_P2P": "0"}, "p2p_overlap": {"B200_P2P": "1", "B200_DIST_OVERLAP": "1"}}[path])
+    port = {"p2p_runs": 29611, "p2p_indexed": 29612, "nccl": 29613, "p2p_overlap": 29614}[path]
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", str(port),
                         os.path.join(ROOT, "tests", "multi_gpu_check.py")], capture_output=True, text=True,
