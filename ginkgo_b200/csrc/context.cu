@@ -197,6 +197,18 @@ b200_status b200_pipe_create(b200_ctx* ctx, b200_pipe** out)
         B200_CUDA_CHECK(cudaEventCreateWithFlags(&p->computed[i], cudaEventDisableTiming));
         B200_CUDA_CHECK(cudaEventCreateWithFlags(&p->downloaded[i], cudaEventDisableTiming));
     }
+    // Staging buffers come from the stream-ordered pool of ctx->stream: a block handed to the owner of
+    // this pipe may still be in use by earlier work on ctx->stream (plan tuning, solver workspaces freed
+    // with b200_free).  Order both copy streams after everything enqueued on ctx->stream so far, and
+    // pre-record `computed` on ctx->stream so the first upload / download of every slot has a real
+    // dependency instead of waiting on a never-recorded event (a no-op).
+    cudaEvent_t born;
+    B200_CUDA_CHECK(cudaEventCreateWithFlags(&born, cudaEventDisableTiming));
+    B200_CUDA_CHECK(cudaEventRecord(born, ctx->stream));
+    B200_CUDA_CHECK(cudaStreamWaitEvent(p->in, born, 0));
+    B200_CUDA_CHECK(cudaStreamWaitEvent(p->out, born, 0));
+    for (int i = 0; i < b200_pipe::kSlots; ++i) B200_CUDA_CHECK(cudaEventRecord(p->computed[i], ctx->stream));
+    B200_CUDA_CHECK(cudaEventDestroy(born));
     *out = p;
     return B200_OK;
 }
@@ -205,6 +217,8 @@ void b200_pipe_destroy(b200_pipe* p)
 {
     if (!p) return;
     cudaSetDevice(p->ctx->device);
+    // the owner frees its staging buffers on ctx->stream after this call: nothing of the copy streams
+    // may still touch them (host-synchronous, so the stream-ordered frees that follow are safe)
     cudaStreamSynchronize(p->in);
     cudaStreamSynchronize(p->out);
     for (int i = 0; i < b200_pipe::kSlots; ++i) {

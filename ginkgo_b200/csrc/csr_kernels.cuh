@@ -162,6 +162,41 @@ __device__ __forceinline__ void row_phase(int64_t r0, int64_t rows_end, int64_t 
     }
 }
 
+// Products of the entries start, start + step, ... (< end) of one row, added to ONE accumulator in
+// that order.  Four entries per round: the four (col, val) loads and the four gathers of a round
+// are issued before the first add, so a thread keeps 4 gathers in flight instead of 1 -- the sum is
+// the same sequence of additions as the plain loop.  (Zipf twin of cfg2: 23 % of the nonzeros sit
+// in rows that a single warp sums with this loop.)
+template <typename V, typename I, bool ADVANCED>
+__device__ __forceinline__ V strided_row_sum(int64_t start, int64_t end, int64_t step,
+                                             const I* __restrict__ col_idxs,
+                                             const V* __restrict__ values, V alpha,
+                                             const V* __restrict__ b, int64_t b_stride,
+                                             uint64_t pol_first, uint64_t pol_last, V acc = V(0))
+{
+    int64_t i = start;
+    for (; i + 3 * step < end; i += 4 * step) {
+        I col[4];
+        V val[4], x[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            col[k] = ld_stream(col_idxs + i + k * step, pol_first);
+            val[k] = ld_stream(values + i + k * step, pol_first);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) x[k] = ld_gather(b + (int64_t)col[k] * b_stride, pol_last);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc += ADVANCED ? (alpha * val[k]) * x[k] : val[k] * x[k];
+    }
+    for (; i < end; i += step) {
+        const I col = ld_stream(col_idxs + i, pol_first);
+        const V val = ld_stream(values + i, pol_first);
+        const V x = ld_gather(b + (int64_t)col * b_stride, pol_last);
+        acc += ADVANCED ? (alpha * val) * x : val * x;
+    }
+    return acc;
+}
+
 // last row of a tile that does not fit the staging buffer: whole-CTA sum
 template <typename V, typename I, bool ADVANCED, bool DOT>
 __device__ __forceinline__ void long_row(int64_t rl, int64_t sl, int64_t p1,
@@ -172,13 +207,8 @@ __device__ __forceinline__ void long_row(int64_t rl, int64_t sl, int64_t p1,
                                          uint64_t pol_first, uint64_t pol_last)
 {
     const int tid = threadIdx.x;
-    V acc = V(0);
-    for (int64_t i = sl + tid; i < p1; i += kThreads) {
-        const I col = ld_stream(col_idxs + i, pol_first);
-        const V val = ld_stream(values + i, pol_first);
-        const V x = ld_gather(b + (int64_t)col * b_stride, pol_last);
-        acc += ADVANCED ? (alpha * val) * x : val * x;
-    }
+    V acc = strided_row_sum<V, I, ADVANCED>(sl + tid, p1, kThreads, col_idxs, values, alpha, b, b_stride,
+                                            pol_first, pol_last);
     acc = block_sum(acc, red);
     if (tid == 0) {
         if (ADVANCED && beta != V(0)) acc = c[rl * c_stride] * beta + acc;
@@ -350,13 +380,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kWCtasPerSm)
             }
             // ---- a last row that does not fit the strip: the whole warp sums it
             if (long_last && !(dot.skip_from > 0 && p1 - sl >= dot.skip_from)) {
-                V acc = V(0);
-                for (int64_t i = sl + lane; i < p1; i += 32) {
-                    const I col = ld_stream(col_idxs + i, pol_first);
-                    const V val = ld_stream(values + i, pol_first);
-                    const V x = ld_gather(b + (int64_t)col * b_stride, pol_last);
-                    acc += ADVANCED ? (alpha * val) * x : val * x;
-                }
+                V acc = strided_row_sum<V, I, ADVANCED>(sl + lane, p1, 32, col_idxs, values, alpha, b,
+                                                        b_stride, pol_first, pol_last);
                 acc = warp_sum(acc);
                 if (lane == 0) {
                     if (ADVANCED && beta != V(0)) acc = c[rl * c_stride] * beta + acc;
@@ -524,13 +549,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kWCtasPerSm)
                 prod[i - p0] = ADVANCED ? (alpha * val) * x : val * x;
             }
             if (long_last && !(dot.skip_from > 0 && p1 - sl >= dot.skip_from)) {
-                V acc = V(0);
-                for (int64_t i = sl + lane; i < p1; i += 32) {
-                    const I col = ld_stream(col_idxs + i, pol_first);
-                    const V val = ld_stream(values + i, pol_first);
-                    const V x = ld_gather(b + (int64_t)col * b_stride, pol_last);
-                    acc += ADVANCED ? (alpha * val) * x : val * x;
-                }
+                V acc = strided_row_sum<V, I, ADVANCED>(sl + lane, p1, 32, col_idxs, values, alpha, b,
+                                                        b_stride, pol_first, pol_last);
                 acc = warp_sum(acc);
                 if (lane == 0) {
                     if (ADVANCED && beta != V(0)) acc = c[rl * c_stride] * beta + acc;
@@ -728,8 +748,11 @@ __global__ void __launch_bounds__(256)
 // carry fix-up of the reference's merge-path / load-balance kernels
 // (common/cuda_hip/matrix/csr_kernels.template.cpp:208-505), which use atomic_add.
 // --------------------------------------------------------------------------
-constexpr int64_t kLongRow = 16384;
-constexpr int64_t kLongChunk = 8192;
+// 4096: a row below the threshold is at most 128 rounds of 32 entries for the one warp that owns it
+// (16384 / 8192 until r02j: the Zipf twin of cfg2 ran at 55 % of the uniform matrix's rate, the tail
+// being single warps with 16 K-entry rows)
+constexpr int64_t kLongRow = 4096;
+constexpr int64_t kLongChunk = 4096;
 
 struct LongRows {
     int64_t num_rows;             // long rows
@@ -768,13 +791,8 @@ __global__ void __launch_bounds__(256) long_rows_kernel(LongRows lr, const I* __
     }
     const uint64_t pol_last = policy_evict_last();
     const uint64_t pol_first = policy_evict_first();
-    V acc = V(0);
-    for (int64_t i = s + tid; i < e; i += 256) {
-        const I col = ld_stream(col_idxs + i, pol_first);
-        const V val = ld_stream(values + i, pol_first);
-        const V x = ld_gather(b + (int64_t)col * b_stride, pol_last);
-        acc += ADVANCED ? (alpha * val) * x : val * x;
-    }
+    V acc = strided_row_sum<V, I, ADVANCED>(s + tid, e, 256, col_idxs, values, alpha, b, b_stride, pol_first,
+                                            pol_last);
     acc = block_sum(acc, red);
     V* partials = (V*)lr.partials;
     if (tid == 0) {

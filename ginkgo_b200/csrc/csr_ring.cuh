@@ -315,13 +315,8 @@ __global__ void __launch_bounds__((NW + NP) * 32, 1)
                 // CTAs (dot.skip_from) are left to long_rows_kernel
                 const int64_t rl = r1 - 1;
                 const int64_t sl = (int64_t)row_ptrs[rl];
-                V acc = V(0);
-                for (int64_t i = sl + tid; i < p1; i += NW * 32) {
-                    const I col = ld_stream(col_idxs + i, pol_first);
-                    const V val = ld_stream(values + i, pol_first);
-                    const V x = ld_gather(b + (int64_t)col * b_stride, pol_last);
-                    acc += ADVANCED ? (alpha * val) * x : val * x;
-                }
+                V acc = strided_row_sum<V, I, ADVANCED>(sl + tid, p1, NW * 32, col_idxs, values, alpha, b,
+                                                        b_stride, pol_first, pol_last);
                 acc = warp_sum(acc);
                 named_bar_sync<NW * 32>();
                 if (lane == 0) red[warp] = acc;

@@ -936,6 +936,11 @@ public:
         GKOB_CALL(cabi<V>::allreduce(ctx, comm, sc + 6, 2));
         GKOB_CALL(vabi<V>::fused_finish(ctx, sc, ctl, 1, baseline_ == 0 ? 3 : baseline_,
                                         (V)reduction_));
+        // After the stop (ctl[0] != 0) the remaining iterations of a check_every_ batch are no-op
+        // KERNELS, but their all-reduces still run on the already-global sc[2] and sc[6..7]: those
+        // three cells are scratch between two finishes and UNDEFINED after a stop (they are re-summed
+        // once per left-over iteration).  Nothing reads them then: the results of the solve are
+        // x, ctl[0..1] and sc[0], sc[1], sc[3..5], which the all-reduces never touch.
         auto enqueue_iteration = [&]() {
             GKOB_CALL(vabi<V>::fused_step_p(ctx, n, p_ext, z, sc, ctl));
             GKOB_CALL(cabi<V>::halo_exchange(ctx, comm, A_->get_halo(), p_ext, ctl));

@@ -18,13 +18,18 @@ public:
     staged_apply(std::shared_ptr<const LinOp> op, size_type num_rhs = 1)
         : op_(std::move(op)), exec_(op_->get_executor()), nrhs_(num_rhs)
     {
-        GKOB_CALL(b200_pipe_create(exec_->ctx(), &pipe_));
         const auto sz = op_->get_size();
         for (int s = 0; s < b200_pipe_num_slots(); ++s) {
             b_.push_back(Dense::create(exec_, dim2{sz.cols, nrhs_}));
             x_.push_back(Dense::create(exec_, dim2{sz.rows, nrhs_}));
         }
+        // created AFTER the staging buffers: b200_pipe_create orders both copy streams behind
+        // everything enqueued on the executor's stream so far, i.e. behind whatever used the
+        // pool blocks these buffers were carved from
+        GKOB_CALL(b200_pipe_create(exec_->ctx(), &pipe_));
     }
+    // the destructor body runs before the members die: the copy streams are drained
+    // (b200_pipe_destroy synchronises them) before b_ / x_ are returned to the pool
     ~staged_apply() { b200_pipe_destroy(pipe_); }
     staged_apply(const staged_apply&) = delete;
     staged_apply& operator=(const staged_apply&) = delete;

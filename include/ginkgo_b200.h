@@ -166,7 +166,7 @@ void b200_csr_plan_set_variant(b200_csr_plan* plan, int variant); /* 0 slab, 2 w
 void b200_csr_plan_allow_value_copy(b200_csr_plan* plan, int allow);
 double b200_csr_plan_gather_lines(const b200_csr_plan* plan); /* -1 before tune */
 int b200_csr_plan_parts(const b200_csr_plan* plan); /* > 1: a column-blocked copy is in use */
-/* rows with >= 16384 entries: the plan splits them over CTAs (8192-entry chunks, chunk sums combined
+/* rows with >= 4096 entries: the plan splits them over CTAs (4096-entry chunks, chunk sums combined
  * in chunk order: deterministic) instead of leaving each to one warp / CTA -- the reference's
  * load-balance / merge-path kernels (common/cuda_hip/matrix/csr_kernels.template.cpp:208-505) */
 int64_t b200_csr_plan_num_long_rows(const b200_csr_plan* plan);

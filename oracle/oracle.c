@@ -9,6 +9,24 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "oracle_precision.h"
+
+/* jacobi::initialize_precisions, reference/preconditioner/jacobi_kernels.cpp:453-461 */
+void orc_jacobi_initialize_precisions(const uint8_t* source, int64_t source_size, uint8_t* precisions,
+                                      int64_t size)
+{
+    orc_jacobi_initialize_precisions_impl(source, source_size, precisions, size);
+}
+/* conversions of the adaptive block-Jacobi storage types, exported for the tests */
+void orc_float_to_gko_half(const float* in, int64_t n, uint16_t* out)
+{
+    for (int64_t i = 0; i < n; ++i) out[i] = orc_float_to_half(in[i]);
+}
+void orc_gko_half_to_float(const uint16_t* in, int64_t n, float* out)
+{
+    for (int64_t i = 0; i < n; ++i) out[i] = orc_half_to_float(in[i]);
+}
+
 /* reference/components/format_conversion_kernels.cpp: convert_ptrs_to_idxs / convert_idxs_to_ptrs */
 #define ORC_CONVERT(IS, I)                                                                  \
     void orc_convert_ptrs_to_idxs_##IS(const I* ptrs, int64_t num_rows, I* idxs)            \

@@ -1190,4 +1190,7 @@ void FNI(jacobi_transpose)(int64_t num_blocks, int32_t max_block_size, int64_t b
     }
 }
 
+/* adaptive-precision block-Jacobi (storage_optimization): generate / apply / transpose */
+#include "oracle_jacobi_adaptive.h"
+
 #endif

@@ -112,6 +112,47 @@ def jacobi_generate(rp, ci, va, max_bs, block_ptrs=None, transposed=False):
                 block_ptrs=ptrs[:meta[3] + 1].copy())
 
 
+def jacobi_adaptive(rp, ci, va, max_bs, block_ptrs=None, storage=None, accuracy=0.1, transposed=False,
+                    b=None, x=None, alpha=None, beta=None):
+    """gko::preconditioner::Jacobi with storage_optimization of the real reference.
+    storage: None | one byte (0xff = autodetect, else preserving << 4 | nonpreserving) | uint8 array
+    (block-wise).  b (n x nrhs): also apply; x = J b, or x = alpha J b + beta x when alpha is given.
+    Returns the storage scheme, the raw block storage (as the value type), the per-block precisions
+    and condition numbers, and x."""
+    n = len(rp) - 1
+    nb = 0 if block_ptrs is None else len(block_ptrs) - 1
+    cap = 32 * 32 * (n + 64)
+    blocks = np.zeros(cap, va.dtype)
+    meta = np.zeros(6, np.int64)
+    ptrs = np.zeros(n + 2, np.int32)
+    prec = np.zeros(n + 1, np.uint8)
+    cond = np.zeros(n + 1, va.dtype)
+    if storage is None:
+        so_kind, so = 0, np.zeros(1, np.uint8)
+    elif np.isscalar(storage):
+        so_kind, so = 1, np.array([storage], np.uint8)
+    else:
+        so_kind, so = 2, np.ascontiguousarray(storage, dtype=np.uint8)
+    nrhs = 0
+    xo = None
+    if b is not None:
+        b2 = np.ascontiguousarray(b.reshape(n, -1))
+        nrhs = b2.shape[1]
+        xo = np.zeros((n, nrhs), va.dtype) if x is None else np.ascontiguousarray(x.reshape(n, -1)).copy()
+    al = None if alpha is None else np.array([alpha], va.dtype)
+    be = None if beta is None else np.array([beta], va.dtype)
+    st = lib().refshim_jacobi_adaptive(_vt(va), n, len(va), _p(rp), _p(ci), _p(va), max_bs, _p(block_ptrs), nb,
+                                       so_kind, _p(so), len(so), float(accuracy), _p(blocks), cap, _p(meta),
+                                       _p(ptrs), _p(prec), _p(cond), int(transposed), nrhs,
+                                       _p(b2) if b is not None else None, _p(xo) if b is not None else None,
+                                       _p(al), _p(be))
+    assert st == 0, st
+    nblk = int(meta[3])
+    return dict(block_offset=int(meta[0]), group_offset=int(meta[1]), group_power=int(meta[2]),
+                num_blocks=nblk, blocks=blocks[:meta[4]].copy(), block_ptrs=ptrs[:nblk + 1].copy(),
+                precisions=prec[:nblk].copy() if meta[5] else None, conditioning=cond[:nblk].copy(), x=xo)
+
+
 def csr_transpose(rp, ci, va, n_cols):
     """Csr::transpose() of the real reference -> (row_ptrs, col_idxs, values) of the transpose"""
     n = len(rp) - 1

@@ -8,7 +8,7 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader > $O
 for g in $GROUPS_; do
   case $g in
-    micro|tma4) timeout 120 $L $g >> $O 2>&1; echo "$g rc=$?" >> $O;;
+    micro|tma4|l1cap) timeout 120 $L $g >> $O 2>&1; echo "$g rc=$?" >> $O;;
     *) for m in ${MATS:-cfg2 cfg2a cfg2h banded cfg3 cfg4}; do timeout 180 $L $g $m >> $O 2>&1; echo "rc=$?" >> $O; done;;
   esac
 done

@@ -573,6 +573,41 @@ void group_micro()
     }
 }
 
+
+// ------------------------------------------------------------------------------ group: l1cap
+// M4: the 8-byte gather rate against the shared-memory carve-out.  A pending L1 miss holds a 128-byte
+// line of the unified L1 / shared-memory array, so every KB given to shared memory takes 8 outstanding
+// gathers away: the budget a staging ring has on matrices with scattered columns.
+void group_l1cap()
+{
+    Timer tm;
+    const int64_t n = 75000000, M = 5000000;
+    int* idx;
+    double *x, *dout;
+    CK(cudaMalloc(&idx, n * 4));
+    CK(cudaMalloc(&x, M * 8));
+    CK(cudaMalloc(&dout, 8));
+    gen_xint<<<(int)((M + 255) / 256), 256>>>(M, x);
+    gen_idx<<<(int)((n + 255) / 256), 256>>>(n, M, idx);
+    CK(cudaDeviceSynchronize());
+    auto k8 = gather_ldg<8, true>;
+    auto k16 = gather_ldg<16, true>;
+    CK(cudaFuncSetAttribute(k8, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(k16, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    for (int kb : {0, 16, 32, 48, 64, 96, 128, 160, 192}) {
+        for (int thr : {512, 1024}) {
+            const double t8 = tm.ms([&] { k8<<<148, thr, (size_t)kb * 1024>>>(idx, n, x, dout); });
+            const double t16 = tm.ms([&] { k16<<<148, thr, (size_t)kb * 1024>>>(idx, n, x, dout); });
+            printf("micro l1cap  smem %3d KB/SM, 1 CTA x %4d thr: U=8 %.4f ms %.3f gathers/clk/SM | U=16 %.4f ms %.3f "
+                   "gathers/clk/SM   (x = 40 MB, no_allocate)\n",
+                   kb, thr, t8, n / t8 / 1e6 / 148 / 1.965, t16, n / t16 / 1e6 / 148 / 1.965);
+            fflush(stdout);
+        }
+    }
+    CK(cudaFree(idx));
+    CK(cudaFree(x));
+}
+
 // ------------------------------------------------------------------------------ group: tma4
 // M3: the same gathers through the TMA gather4 path: x viewed as a 2-D tensor of 16-byte rows
 // {x[2i], x[2i+1]}; one cp.async.bulk.tensor.2d...tile::gather4 brings 4 rows (= 4 gathered
@@ -795,6 +830,7 @@ int main(int argc, char** argv)
     if (group == "micro") group_micro();
     if (group == "san") group_san();
     if (group == "tma4") group_tma4();
+    if (group == "l1cap") group_l1cap();
     if (group == "base") {
         if (name == "cfg4")
             group_base<float>(name);
