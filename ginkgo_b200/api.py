@@ -251,6 +251,10 @@ def _configure_host_lib(h):
         f = getattr(h, "gkob_solver_info_" + s)
         f.restype, f.argtypes = i, [vp, ctypes.POINTER(ll), ctypes.POINTER(ctypes.c_ubyte),
                                     ctypes.POINTER(i)]
+    h.gkob_jacobi_create.restype = vp
+    h.gkob_jacobi_create.argtypes = [vp, i, vp, i, vp, ll, i, vp, ll, d]
+    h.gkob_jacobi_get.restype, h.gkob_jacobi_get.argtypes = i, [vp, i, vp, vp, vp, vp, vp]
+    h.gkob_jacobi_transpose.restype, h.gkob_jacobi_transpose.argtypes = vp, [vp]
     h.gkob_apply.restype, h.gkob_apply.argtypes = i, [vp, vp, vp]
     h.gkob_apply4.restype, h.gkob_apply4.argtypes = i, [vp, vp, vp, vp, vp]
     h.gkob_synchronize.restype, h.gkob_synchronize.argtypes = i, [vp]
@@ -362,6 +366,71 @@ def host_transpose(A):
     t = _HostObj(A.exec, _host().gkob_csr_transpose(A.h), keep=(A,))
     t.vt = getattr(A, "vt", None)
     return t
+
+
+AUTODETECT = 0xff  # gko::precision_reduction::autodetect()
+
+
+def precision_reduction(preserving, nonpreserving):
+    """the byte of gko::precision_reduction(preserving, nonpreserving)"""
+    return (preserving << 4) | nonpreserving
+
+
+def host_jacobi(A, max_block_size, block_ptrs=None, storage_optimization=None, accuracy=0.1):
+    """gko_b200::preconditioner::Jacobi<V,int32>::build().with_max_block_size(..)
+    [.with_block_pointers(..)] [.with_storage_optimization(..)] [.with_accuracy(..)].on(exec)->generate(A).
+    storage_optimization: None | one precision_reduction byte (AUTODETECT = 0xff) | a sequence of bytes
+    (block-wise, replicated cyclically).  Returns a LinOp handle (host_apply / host_jacobi_get)."""
+    import numpy as _np
+    bp = None if block_ptrs is None else _np.ascontiguousarray(block_ptrs, dtype=_np.int32)
+    if storage_optimization is None:
+        kind, so = 0, _np.zeros(1, _np.uint8)
+    elif _np.isscalar(storage_optimization):
+        kind, so = 1, _np.array([storage_optimization], _np.uint8)
+    else:
+        kind, so = 2, _np.ascontiguousarray(storage_optimization, dtype=_np.uint8)
+    o = _HostObj(A.exec, _host().gkob_jacobi_create(
+        A.exec.h, 0 if A.vt == "f64" else 1, A.h, int(max_block_size),
+        None if bp is None else bp.ctypes.data, 0 if bp is None else len(bp) - 1, kind, so.ctypes.data, len(so),
+        float(accuracy)), keep=(A,))
+    o.vt = A.vt
+    return o
+
+
+def host_jacobi_get(J):
+    """storage scheme, raw block storage (as the value type), block pointers, the precision_reduction
+    byte of every block (None without storage optimisation) and the condition numbers, on the host"""
+    import numpy as _np
+    vt = 0 if J.vt == "f64" else 1
+    dt = _np.float64 if vt == 0 else _np.float32
+    meta = _np.zeros(6, _np.int64)
+    _hcheck(_host().gkob_jacobi_get(J.h, vt, meta.ctypes.data, None, None, None, None))
+    nb, stored = int(meta[3]), int(meta[4])
+    blocks = _np.zeros(max(stored, 1), dt)
+    ptrs = _np.zeros(nb + 1, _np.int32)
+    prec = _np.zeros(max(nb, 1), _np.uint8)
+    cond = _np.zeros(max(nb, 1), dt)
+    J.exec.synchronize()
+    _hcheck(_host().gkob_jacobi_get(J.h, vt, meta.ctypes.data, blocks.ctypes.data, ptrs.ctypes.data,
+                                    prec.ctypes.data, cond.ctypes.data))
+    return dict(block_offset=int(meta[0]), group_offset=int(meta[1]), group_power=int(meta[2]), num_blocks=nb,
+                blocks=blocks[:stored], block_ptrs=ptrs, precisions=prec[:nb] if meta[5] else None,
+                conditioning=cond[:nb] if meta[5] else None)
+
+
+def host_jacobi_transpose(J):
+    """Jacobi::transpose()"""
+    t = _HostObj(J.exec, _host().gkob_jacobi_transpose(J.h), keep=(J,))
+    t.vt = J.vt
+    return t
+
+
+def host_apply(op, b, x, alpha=None, beta=None):
+    """x = op(b)  or  x = alpha op(b) + beta x   (handles of host_dense; alpha / beta 1x1)"""
+    if alpha is None:
+        _hcheck(_host().gkob_apply(op.h, b.h, x.h))
+    else:
+        _hcheck(_host().gkob_apply4(op.h, alpha.h, b.h, beta.h, x.h))
 
 
 class StagedApply:

@@ -13,6 +13,7 @@
 // common/cuda_hip/preconditioner/jacobi_{simple,advanced}_apply_kernels
 // (contract reference/preconditioner/jacobi_kernels.cpp:419-592).
 #include "elementwise.cuh"
+#include "jacobi_precision.cuh"
 
 namespace b200 {
 namespace stop {
@@ -104,8 +105,9 @@ namespace jacobi {
 template <typename V, typename I, int MBS, bool ADVANCED>
 __global__ void __launch_bounds__(256)
     block_apply_kernel(int64_t num_blocks, int64_t block_offset, int64_t group_offset,
-                       int32_t group_power, const I* __restrict__ block_ptrs,
-                       const V* __restrict__ blocks, const V* __restrict__ alpha_p,
+                       int32_t group_power, const uint8_t* __restrict__ block_precisions,
+                       const I* __restrict__ block_ptrs, const V* __restrict__ blocks,
+                       const V* __restrict__ alpha_p,
                        const V* __restrict__ b, int64_t bs_, int64_t num_rhs,
                        const V* __restrict__ beta_p, V* __restrict__ x, int64_t xs)
 {
@@ -125,11 +127,15 @@ __global__ void __launch_bounds__(256)
     }
     const bool valid = r < bsz;
     const int64_t stride = block_offset << group_power;
-    const V* col0 = blocks + group_offset * group + lane;
+    // adaptive precision (jacobi_precision.cuh): the block is stored as the type its precision_reduction
+    // byte names, addressed in elements of THAT type from the group's base, and widened on load
+    const int kind =
+        storage_kind<V>((block_precisions && sub < group_size && k < num_blocks) ? block_precisions[k] : uint8_t(0));
+    const void* gbase = blocks + group_offset * group;
     V a[MBS];
 #pragma unroll
     for (int inner = 0; inner < MBS; ++inner)
-        a[inner] = (valid && inner < bsz) ? col0[inner * stride] : V(0);
+        a[inner] = (valid && inner < bsz) ? load_elem(gbase, lane + inner * stride, kind, V(0)) : V(0);
     V alpha = V(1), beta = V(0);
     if (ADVANCED) {
         alpha = *alpha_p;
@@ -152,8 +158,9 @@ __global__ void __launch_bounds__(256)
 template <typename V, typename I, bool ADVANCED>
 b200_status block_apply(b200_ctx* ctx, int64_t num_blocks, int32_t max_block_size,
                         int64_t block_offset, int64_t group_offset, int32_t group_power,
-                        const I* block_ptrs, const V* blocks, const V* alpha, const V* b,
-                        int64_t bs, int64_t num_rhs, const V* beta, V* x, int64_t xs)
+                        const uint8_t* block_precisions, const I* block_ptrs, const V* blocks,
+                        const V* alpha, const V* b, int64_t bs, int64_t num_rhs, const V* beta, V* x,
+                        int64_t xs)
 {
     B200_REQUIRE(ctx != nullptr, "ctx is null");
     B200_REQUIRE(max_block_size >= 1 && max_block_size <= 32, "max_block_size must be in [1,32]");
@@ -164,8 +171,8 @@ b200_status block_apply(b200_ctx* ctx, int64_t num_blocks, int32_t max_block_siz
     const unsigned grid = (unsigned)ceildiv(groups * 32, (int64_t)256);
 #define B200_BJ(M)                                                                              \
     block_apply_kernel<V, I, M, ADVANCED><<<grid, 256, 0, ctx->stream>>>(                       \
-        num_blocks, block_offset, group_offset, group_power, block_ptrs, blocks, alpha, b, bs,  \
-        num_rhs, beta, x, xs)
+        num_blocks, block_offset, group_offset, group_power, block_precisions, block_ptrs,      \
+        blocks, alpha, b, bs, num_rhs, beta, x, xs)
     if (block_offset <= 4)
         B200_BJ(4);
     else if (block_offset <= 8)
@@ -250,8 +257,29 @@ B200_DEF_STOP_JACOBI(f32, float)
         const VT* blocks, const VT* b, int64_t bs, int64_t num_rhs, VT* x, int64_t xs)         \
     {                                                                                          \
         return b200::jacobi::block_apply<VT, IT, false>(                                       \
-            ctx, num_blocks, max_block_size, block_offset, group_offset, group_power,          \
+            ctx, num_blocks, max_block_size, block_offset, group_offset, group_power, nullptr, \
             block_pointers, blocks, nullptr, b, bs, num_rhs, nullptr, x, xs);                  \
+    }                                                                                          \
+    b200_status b200_jacobi_simple_apply_adaptive_##V##_##I(                                   \
+        b200_ctx* ctx, int64_t num_blocks, int32_t max_block_size, int64_t block_offset,       \
+        int64_t group_offset, int32_t group_power, const uint8_t* block_precisions,            \
+        const IT* block_pointers, const VT* blocks, const VT* b, int64_t bs, int64_t num_rhs,  \
+        VT* x, int64_t xs)                                                                     \
+    {                                                                                          \
+        return b200::jacobi::block_apply<VT, IT, false>(                                       \
+            ctx, num_blocks, max_block_size, block_offset, group_offset, group_power,          \
+            block_precisions, block_pointers, blocks, nullptr, b, bs, num_rhs, nullptr, x,     \
+            xs);                                                                               \
+    }                                                                                          \
+    b200_status b200_jacobi_apply_adaptive_##V##_##I(                                          \
+        b200_ctx* ctx, int64_t num_blocks, int32_t max_block_size, int64_t block_offset,       \
+        int64_t group_offset, int32_t group_power, const uint8_t* block_precisions,            \
+        const IT* block_pointers, const VT* blocks, const VT* alpha, const VT* b, int64_t bs,  \
+        int64_t num_rhs, const VT* beta, VT* x, int64_t xs)                                    \
+    {                                                                                          \
+        return b200::jacobi::block_apply<VT, IT, true>(                                        \
+            ctx, num_blocks, max_block_size, block_offset, group_offset, group_power,          \
+            block_precisions, block_pointers, blocks, alpha, b, bs, num_rhs, beta, x, xs);     \
     }                                                                                          \
     b200_status b200_jacobi_apply_##V##_##I(                                                   \
         b200_ctx* ctx, int64_t num_blocks, int32_t max_block_size, int64_t block_offset,       \
@@ -260,7 +288,7 @@ B200_DEF_STOP_JACOBI(f32, float)
         const VT* beta, VT* x, int64_t xs)                                                     \
     {                                                                                          \
         return b200::jacobi::block_apply<VT, IT, true>(                                        \
-            ctx, num_blocks, max_block_size, block_offset, group_offset, group_power,          \
+            ctx, num_blocks, max_block_size, block_offset, group_offset, group_power, nullptr, \
             block_pointers, blocks, alpha, b, bs, num_rhs, beta, x, xs);                       \
     }
 

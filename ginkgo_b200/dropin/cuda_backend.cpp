@@ -843,35 +843,64 @@ GKO_DECLARE_JACOBI_FIND_BLOCKS_KERNEL(ValueType, IndexType)
                    block_pointers.get_data(), &nb));
     num_blocks = (size_type)nb;
 }
+// gko::precision_reduction is one byte (include/ginkgo/core/base/types.hpp:239-350): the C ABI takes the
+// array<precision_reduction> as bytes (nullptr when the preconditioner has no storage optimisation)
+static_assert(sizeof(precision_reduction) == 1, "precision_reduction is expected to be one byte");
+inline uint8_t* prec_bytes(array<precision_reduction>& a) { return reinterpret_cast<uint8_t*>(a.get_data()); }
+inline const uint8_t* prec_bytes(const array<precision_reduction>& a)
+{
+    return reinterpret_cast<const uint8_t*>(a.get_const_data());
+}
+
 template <typename ValueType, typename IndexType>
 GKO_DECLARE_JACOBI_GENERATE_KERNEL(ValueType, IndexType)
 {
-    // adaptive block precision (storage_optimization) is outside the path: full precision only
-    if (block_precisions.get_const_data() != nullptr) GKO_NOT_SUPPORTED(block_precisions);
-    B2(B2_SELECT_VI(ValueType, IndexType, b200_jacobi_generate, ctx_of(exec), rows(system_matrix),
+    B2(B2_SELECT_VI(ValueType, IndexType, b200_jacobi_generate_adaptive, ctx_of(exec), rows(system_matrix),
                     system_matrix->get_const_row_ptrs(), system_matrix->get_const_col_idxs(),
                     system_matrix->get_const_values(), (int64_t)num_blocks, (int32_t)max_block_size,
-                    (int64_t)storage_scheme.block_offset, (int64_t)storage_scheme.group_offset,
-                    (int32_t)storage_scheme.group_power, block_pointers.get_const_data(), blocks.get_data()));
+                    (double)accuracy, (int64_t)storage_scheme.block_offset, (int64_t)storage_scheme.group_offset,
+                    (int32_t)storage_scheme.group_power, conditioning.get_data(), prec_bytes(block_precisions),
+                    block_pointers.get_const_data(), blocks.get_data()));
 }
 template <typename ValueType, typename IndexType>
 GKO_DECLARE_JACOBI_SIMPLE_APPLY_KERNEL(ValueType, IndexType)
 {
-    if (block_precisions.get_const_data() != nullptr) GKO_NOT_SUPPORTED(block_precisions);
-    B2(B2_SELECT_VI(ValueType, IndexType, b200_jacobi_simple_apply, ctx_of(exec), (int64_t)num_blocks,
+    B2(B2_SELECT_VI(ValueType, IndexType, b200_jacobi_simple_apply_adaptive, ctx_of(exec), (int64_t)num_blocks,
                     (int32_t)max_block_size, (int64_t)storage_scheme.block_offset, (int64_t)storage_scheme.group_offset,
-                    (int32_t)storage_scheme.group_power, block_pointers.get_const_data(), blocks.get_const_data(),
-                    b->get_const_values(), ld(b), cols(b), x->get_values(), ld(x)));
+                    (int32_t)storage_scheme.group_power, prec_bytes(block_precisions),
+                    block_pointers.get_const_data(), blocks.get_const_data(), b->get_const_values(), ld(b), cols(b),
+                    x->get_values(), ld(x)));
 }
 template <typename ValueType, typename IndexType>
 GKO_DECLARE_JACOBI_APPLY_KERNEL(ValueType, IndexType)
 {
-    if (block_precisions.get_const_data() != nullptr) GKO_NOT_SUPPORTED(block_precisions);
-    B2(B2_SELECT_VI(ValueType, IndexType, b200_jacobi_apply, ctx_of(exec), (int64_t)num_blocks, (int32_t)max_block_size,
-                    (int64_t)storage_scheme.block_offset, (int64_t)storage_scheme.group_offset,
-                    (int32_t)storage_scheme.group_power, block_pointers.get_const_data(), blocks.get_const_data(),
-                    alpha->get_const_values(), b->get_const_values(), ld(b), cols(b), beta->get_const_values(),
-                    x->get_values(), ld(x)));
+    B2(B2_SELECT_VI(ValueType, IndexType, b200_jacobi_apply_adaptive, ctx_of(exec), (int64_t)num_blocks,
+                    (int32_t)max_block_size, (int64_t)storage_scheme.block_offset, (int64_t)storage_scheme.group_offset,
+                    (int32_t)storage_scheme.group_power, prec_bytes(block_precisions),
+                    block_pointers.get_const_data(), blocks.get_const_data(), alpha->get_const_values(),
+                    b->get_const_values(), ld(b), cols(b), beta->get_const_values(), x->get_values(), ld(x)));
+}
+template <typename ValueType, typename IndexType>
+GKO_DECLARE_JACOBI_TRANSPOSE_KERNEL(ValueType, IndexType)
+{
+    B2(B2_SELECT_VI(ValueType, IndexType, b200_jacobi_transpose_adaptive, ctx_of(exec), (int64_t)num_blocks,
+                    (int32_t)max_block_size, (int64_t)storage_scheme.block_offset, (int64_t)storage_scheme.group_offset,
+                    (int32_t)storage_scheme.group_power, prec_bytes(block_precisions),
+                    block_pointers.get_const_data(), blocks.get_const_data(), out_blocks.get_data()));
+}
+// real value types: the conjugate transpose is the transpose
+template <typename ValueType, typename IndexType>
+GKO_DECLARE_JACOBI_CONJ_TRANSPOSE_KERNEL(ValueType, IndexType)
+{
+    B2(B2_SELECT_VI(ValueType, IndexType, b200_jacobi_transpose_adaptive, ctx_of(exec), (int64_t)num_blocks,
+                    (int32_t)max_block_size, (int64_t)storage_scheme.block_offset, (int64_t)storage_scheme.group_offset,
+                    (int32_t)storage_scheme.group_power, prec_bytes(block_precisions),
+                    block_pointers.get_const_data(), blocks.get_const_data(), out_blocks.get_data()));
+}
+GKO_DECLARE_JACOBI_INITIALIZE_PRECISIONS_KERNEL
+{
+    B2(b200_jacobi_initialize_precisions(ctx_of(exec), prec_bytes(source), (int64_t)source.get_size(),
+                                         prec_bytes(precisions), (int64_t)precisions.get_size()));
 }
 template <typename ValueType>
 GKO_DECLARE_JACOBI_INVERT_DIAGONAL_KERNEL(ValueType)
@@ -896,7 +925,9 @@ GKO_DECLARE_JACOBI_SCALAR_APPLY_KERNEL(ValueType)
     template GKO_DECLARE_JACOBI_FIND_BLOCKS_KERNEL(V, I);      \
     template GKO_DECLARE_JACOBI_GENERATE_KERNEL(V, I);         \
     template GKO_DECLARE_JACOBI_SIMPLE_APPLY_KERNEL(V, I);     \
-    template GKO_DECLARE_JACOBI_APPLY_KERNEL(V, I)
+    template GKO_DECLARE_JACOBI_APPLY_KERNEL(V, I);            \
+    template GKO_DECLARE_JACOBI_TRANSPOSE_KERNEL(V, I);        \
+    template GKO_DECLARE_JACOBI_CONJ_TRANSPOSE_KERNEL(V, I)
 B2_INST_JACOBI_VI(double, int32);
 B2_INST_JACOBI_VI(double, int64);
 B2_INST_JACOBI_VI(float, int32);

@@ -192,6 +192,95 @@ static std::shared_ptr<LinOp> convert_csr(const matrix::Csr<V, int32>* a, const 
 }
 
 
+// preconditioner::Jacobi as an object of its own (generate, storage optimisation, transpose):
+//   so_kind 0 none, 1 one precision_reduction byte for all blocks (so[0]), 2 block-wise so[0 .. so_len);
+//   a byte 0xff is autodetect().  vt 0 double, 1 float.
+template <typename V>
+static std::shared_ptr<LinOp> make_jacobi(std::shared_ptr<Executor> exec, std::shared_ptr<LinOp> A, int max_bs,
+                                          const int32* block_ptrs, long long nblocks, int so_kind,
+                                          const unsigned char* so, long long so_len, double accuracy)
+{
+    auto pb = preconditioner::Jacobi<V, int32>::build();
+    pb.with_max_block_size((uint32)max_bs);
+    pb.with_accuracy(accuracy);
+    if (block_ptrs && max_bs > 1) pb.with_block_pointers(std::vector<int32>(block_ptrs, block_ptrs + nblocks + 1));
+    if (so_kind == 1) pb.with_storage_optimization(precision_reduction::from_byte(so[0]));
+    if (so_kind == 2) {
+        std::vector<precision_reduction> v;
+        for (long long i = 0; i < so_len; ++i) v.push_back(precision_reduction::from_byte(so[i]));
+        pb.with_storage_optimization(v);
+    }
+    return std::shared_ptr<LinOp>(pb.on(exec)->generate(A));
+}
+template <typename V>
+static int jacobi_get(Handle* h, long long* meta, void* blocks, int32* ptrs, unsigned char* prec, void* cond)
+{
+    auto J = dynamic_cast<const preconditioner::Jacobi<V, int32>*>(h->op.get());
+    if (!J) throw NotSupported("gkob_jacobi_get: not a Jacobi of this value type");
+    auto e = J->get_executor();
+    const auto& sch = J->get_storage_scheme();
+    const long long nb = (long long)J->get_num_blocks();
+    meta[0] = sch.block_offset;
+    meta[1] = sch.group_offset;
+    meta[2] = sch.group_power;
+    meta[3] = nb;
+    meta[4] = (long long)J->get_num_stored_elements();
+    meta[5] = J->get_block_precisions() ? 1 : 0;
+    if (blocks && meta[4]) e->copy_to_host((V*)blocks, J->get_blocks(), (size_type)meta[4]);
+    if (ptrs && J->get_max_block_size() > 1) e->copy_to_host(ptrs, J->get_const_block_pointers(), (size_type)nb + 1);
+    if (prec && J->get_block_precisions()) e->copy_to_host(prec, J->get_block_precisions(), (size_type)nb);
+    if (cond && J->get_conditioning()) e->copy_to_host((V*)cond, J->get_conditioning(), (size_type)nb);
+    return 0;
+}
+
+extern "C" {
+
+void* gkob_jacobi_create(void* exec, int vt, void* matrix, int max_bs, const int* block_ptrs, long long nblocks,
+                         int so_kind, const unsigned char* so, long long so_len, double accuracy)
+{
+    Handle* h = new Handle();
+    auto e = static_cast<Handle*>(exec)->exec;
+    auto A = static_cast<Handle*>(matrix)->op;
+    if (guarded([&] {
+            h->exec = e;
+            h->op = vt == 0 ? make_jacobi<double>(e, A, max_bs, block_ptrs, nblocks, so_kind, so, so_len, accuracy)
+                            : make_jacobi<float>(e, A, max_bs, block_ptrs, nblocks, so_kind, so, so_len, accuracy);
+        })) {
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+// meta: block_offset, group_offset, group_power, num_blocks, stored elements, has precisions;
+// blocks (raw storage as the value type) / block pointers / precisions / condition numbers -> host
+int gkob_jacobi_get(void* jacobi, int vt, long long* meta, void* blocks, int* ptrs, unsigned char* prec, void* cond)
+{
+    return guarded([&] {
+        auto h = static_cast<Handle*>(jacobi);
+        vt == 0 ? jacobi_get<double>(h, meta, blocks, ptrs, prec, cond)
+                : jacobi_get<float>(h, meta, blocks, ptrs, prec, cond);
+    });
+}
+// Jacobi::transpose()
+void* gkob_jacobi_transpose(void* jacobi)
+{
+    Handle* src = static_cast<Handle*>(jacobi);
+    Handle* h = new Handle();
+    if (guarded([&] {
+            auto t = dynamic_cast<const Transposable*>(src->op.get());
+            if (!t) throw NotSupported("gkob_jacobi_transpose: not transposable");
+            h->exec = src->exec;
+            h->op = std::shared_ptr<LinOp>(t->transpose());
+        })) {
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+
+}  // extern "C"
+
+
 extern "C" {
 
 const char* gkob_last_error() { return g_err.c_str(); }

@@ -159,6 +159,12 @@ GKOB_V(float, f32)
         static constexpr auto jacobi_find_blocks = b200_jacobi_find_blocks_##T;                 \
         static constexpr auto csr_transpose = b200_csr_transpose_##S##_##T;                     \
         static constexpr auto jacobi_transpose = b200_jacobi_transpose_##S##_##T;               \
+        static constexpr auto jacobi_generate_adaptive = b200_jacobi_generate_adaptive_##S##_##T; \
+        static constexpr auto jacobi_simple_apply_adaptive =                                    \
+            b200_jacobi_simple_apply_adaptive_##S##_##T;                                        \
+        static constexpr auto jacobi_apply_adaptive = b200_jacobi_apply_adaptive_##S##_##T;     \
+        static constexpr auto jacobi_transpose_adaptive =                                       \
+            b200_jacobi_transpose_adaptive_##S##_##T;                                           \
     };
 GKOB_VI(double, f64, int32, i32)
 GKOB_VI(double, f64, int64, i64)

@@ -291,6 +291,30 @@ inline std::unique_ptr<Criterion> combine_and_generate(
 // operation order); block pointers are user-supplied or detected by b200_jacobi_find_blocks_*
 // (reference/preconditioner/jacobi_kernels.cpp:36-123).
 // =============================================================================================
+// gko::precision_reduction (include/ginkgo/core/base/types.hpp:239-350): how far the storage of a
+// Jacobi block may be reduced -- `preserving` steps keep the exponent range (truncation), `nonpreserving`
+// steps switch to the next smaller IEEE type; one byte, preserving << 4 | nonpreserving.
+class precision_reduction {
+public:
+    constexpr precision_reduction() noexcept : data_(0) {}
+    constexpr precision_reduction(uint8 preserving, uint8 nonpreserving) noexcept
+        : data_((uint8)((preserving << 4) | nonpreserving))
+    {}
+    constexpr operator uint8() const noexcept { return data_; }
+    constexpr uint8 get_preserving() const noexcept { return (uint8)(data_ >> 4); }
+    constexpr uint8 get_nonpreserving() const noexcept { return (uint8)(data_ & 0xf); }
+    static constexpr precision_reduction autodetect() noexcept { return from_byte(0xff); }
+    static constexpr precision_reduction from_byte(uint8 b) noexcept
+    {
+        precision_reduction p;
+        p.data_ = b;
+        return p;
+    }
+
+private:
+    uint8 data_;
+};
+
 namespace preconditioner {
 
 template <typename I>
@@ -316,7 +340,30 @@ public:
     struct Factory : LinOpFactory {
         uint32 max_block_size_ = 32;
         std::vector<I> block_pointers_;
+        // storage_optimization (jacobi.hpp:391-485): one reduction for all blocks, or block-wise
+        // (replicated cyclically over the blocks, jacobi::initialize_precisions)
+        bool so_block_wise_ = false;
+        precision_reduction so_all_{};
+        std::vector<precision_reduction> so_blocks_;
+        double accuracy_ = 1e-1;  // jacobi.hpp:513
         std::shared_ptr<const Executor> exec_;
+        Factory& with_storage_optimization(precision_reduction p)
+        {
+            so_block_wise_ = false;
+            so_all_ = p;
+            return *this;
+        }
+        Factory& with_storage_optimization(std::vector<precision_reduction> block_wise)
+        {
+            so_block_wise_ = true;
+            so_blocks_ = std::move(block_wise);
+            return *this;
+        }
+        Factory& with_accuracy(double a)
+        {
+            accuracy_ = a;
+            return *this;
+        }
         Factory& with_max_block_size(uint32 s)
         {
             max_block_size_ = s;
@@ -345,6 +392,14 @@ public:
     const V* get_blocks() const { return blocks_.get_const_data(); }
     const I* get_const_block_pointers() const { return block_pointers_.get_const_data(); }
     const block_interleaved_storage_scheme<I>& get_storage_scheme() const { return scheme_; }
+    // adaptive precision: condition numbers (device, num_blocks; nullptr without storage
+    // optimisation, jacobi.hpp:254) and the precision every block was stored in (device bytes)
+    const V* get_conditioning() const { return conditioning_.get_size() ? conditioning_.get_const_data() : nullptr; }
+    const uint8* get_block_precisions() const
+    {
+        return precisions_.get_size() ? precisions_.get_const_data() : nullptr;
+    }
+    size_type get_num_stored_elements() const { return blocks_.get_size(); }
     // Jacobi::transpose (core/preconditioner/jacobi.cpp:261-283): same scheme and block
     // pointers, every inverted block transposed (a scalar Jacobi is its own transpose)
     std::unique_ptr<LinOp> transpose() const override
@@ -362,6 +417,17 @@ public:
         exec_->copy(res->block_pointers_.get_data(), block_pointers_.get_const_data(),
                     block_pointers_.get_size());
         GKOB_CALL(vabi<V>::fill(exec_->ctx(), blocks_.get_size(), 1, res->blocks_.get_data(), 1, V(0)));
+        if (precisions_.get_size()) {
+            res->precisions_ = array<uint8>(exec_, precisions_.get_size());
+            exec_->copy(res->precisions_.get_data(), precisions_.get_const_data(), precisions_.get_size());
+            res->conditioning_ = array<V>(exec_, conditioning_.get_size());
+            exec_->copy(res->conditioning_.get_data(), conditioning_.get_const_data(), conditioning_.get_size());
+            GKOB_CALL((viabi<V, I>::jacobi_transpose_adaptive(
+                exec_->ctx(), num_blocks_, max_block_size_, scheme_.block_offset, scheme_.group_offset,
+                scheme_.group_power, precisions_.get_const_data(), block_pointers_.get_const_data(),
+                blocks_.get_const_data(), res->blocks_.get_data())));
+            return res;
+        }
         GKOB_CALL((viabi<V, I>::jacobi_transpose(exec_->ctx(), num_blocks_, max_block_size_, scheme_.block_offset,
                                                  scheme_.group_offset, scheme_.group_power,
                                                  block_pointers_.get_const_data(), blocks_.get_const_data(),
@@ -424,6 +490,27 @@ protected:
         blocks_ = array<V>(exec, space);
         GKOB_CALL(vabi<V>::fill(exec->ctx(), space, 1, blocks_.get_data(), 1, V(0)));
         block_pointers_ = array<I>(exec, ptrs);
+        // adaptive variant (core/preconditioner/jacobi.cpp:380-401): the precision array is replicated
+        // to one entry per block and the condition numbers are kept
+        if (f.so_block_wise_ || (uint8)f.so_all_ != 0) {
+            std::vector<uint8> src;
+            if (f.so_block_wise_)
+                for (auto p : f.so_blocks_) src.push_back((uint8)p);
+            else
+                src.push_back((uint8)f.so_all_);
+            if (src.empty()) throw BadDimension("Jacobi: empty block-wise storage optimization");
+            array<uint8> dsrc(exec, src);
+            precisions_ = array<uint8>(exec, num_blocks_);
+            GKOB_CALL(b200_jacobi_initialize_precisions(exec->ctx(), dsrc.get_const_data(), (int64)src.size(),
+                                                        precisions_.get_data(), (int64)num_blocks_));
+            conditioning_ = array<V>(exec, num_blocks_);
+            GKOB_CALL((viabi<V, I>::jacobi_generate_adaptive(
+                exec->ctx(), n, csr->get_const_row_ptrs(), csr->get_const_col_idxs(), csr->get_const_values(),
+                num_blocks_, max_block_size_, f.accuracy_, scheme_.block_offset, scheme_.group_offset,
+                scheme_.group_power, conditioning_.get_data(), precisions_.get_data(),
+                block_pointers_.get_const_data(), blocks_.get_data())));
+            return;
+        }
         GKOB_CALL((viabi<V, I>::jacobi_generate(
             exec->ctx(), n, csr->get_const_row_ptrs(), csr->get_const_col_idxs(),
             csr->get_const_values(), num_blocks_, max_block_size_, scheme_.block_offset,
@@ -440,6 +527,12 @@ protected:
                                                    blocks_.get_const_data(), db->get_const_values(),
                                                    db->get_stride(), dx->get_values(),
                                                    dx->get_stride()));
+        } else if (precisions_.get_size()) {
+            GKOB_CALL((viabi<V, I>::jacobi_simple_apply_adaptive(
+                exec_->ctx(), num_blocks_, max_block_size_, scheme_.block_offset, scheme_.group_offset,
+                scheme_.group_power, precisions_.get_const_data(), block_pointers_.get_const_data(),
+                blocks_.get_const_data(), db->get_const_values(), db->get_stride(), db->get_size().cols,
+                dx->get_values(), dx->get_stride())));
         } else {
             GKOB_CALL((viabi<V, I>::jacobi_simple_apply(
                 exec_->ctx(), num_blocks_, max_block_size_, scheme_.block_offset,
@@ -459,6 +552,12 @@ protected:
                                             blocks_.get_const_data(), al, db->get_const_values(),
                                             db->get_stride(), be, dx->get_values(),
                                             dx->get_stride()));
+        } else if (precisions_.get_size()) {
+            GKOB_CALL((viabi<V, I>::jacobi_apply_adaptive(
+                exec_->ctx(), num_blocks_, max_block_size_, scheme_.block_offset, scheme_.group_offset,
+                scheme_.group_power, precisions_.get_const_data(), block_pointers_.get_const_data(),
+                blocks_.get_const_data(), al, db->get_const_values(), db->get_stride(), db->get_size().cols, be,
+                dx->get_values(), dx->get_stride())));
         } else {
             GKOB_CALL((viabi<V, I>::jacobi_apply(
                 exec_->ctx(), num_blocks_, max_block_size_, scheme_.block_offset,
@@ -474,6 +573,8 @@ private:
     block_interleaved_storage_scheme<I> scheme_;
     array<V> blocks_;
     array<I> block_pointers_;
+    array<uint8> precisions_;  // adaptive variant only: one precision_reduction byte per block
+    array<V> conditioning_;    // adaptive variant only
 };
 
 }  // namespace preconditioner

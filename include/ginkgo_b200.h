@@ -245,7 +245,8 @@ void b200_coo_plan_destroy(b200_coo_plan* plan);
  * jacobi.hpp:37-141): element (r,c) of block k at
  *   group_offset*(k >> group_power) + block_offset*(k & (2^group_power-1))
  *   + r + c*(block_offset << group_power).
- * Only full-precision storage (block_precisions == NULL in the reference).
+ * The plain entry points read full-precision storage (block_precisions == NULL in the reference);
+ * the *_adaptive ones take the reference's array<precision_reduction> (one byte per block).
  * ------------------------------------------------------------------------- */
 #define B200_DECL_JACOBI_BLOCK(V, VT, I, IT)                                                  \
     b200_status b200_jacobi_simple_apply_##V##_##I(                                           \
@@ -266,7 +267,48 @@ void b200_coo_plan_destroy(b200_coo_plan* plan);
     b200_status b200_jacobi_generate_##V##_##I(                                               \
         b200_ctx* ctx, int64_t num_rows, const IT* row_ptrs, const IT* col_idxs,              \
         const VT* values, int64_t num_blocks, int32_t max_block_size, int64_t block_offset,   \
-        int64_t group_offset, int32_t group_power, const IT* block_pointers, VT* blocks);
+        int64_t group_offset, int32_t group_power, const IT* block_pointers, VT* blocks);     \
+    /* ---- adaptive precision (Jacobi `storage_optimization`, include/ginkgo/core/            \
+     * preconditioner/jacobi.hpp:315-513).  block_precisions: gko::precision_reduction per     \
+     * block, one byte = preserving << 4 | nonpreserving, 0xff = autodetect(); in/out for      \
+     * generate.  jacobi::generate with conditioning + block_precisions                        \
+     * (core/preconditioner/jacobi_kernels.hpp:28-40, reference/preconditioner/                \
+     * jacobi_kernels.cpp:281-410): condition numbers (1-norm of block times 1-norm of its     \
+     * inverse, the reference's compute_inf_norm on the row-major block), per-block detection  \
+     * of the storage types that keep `accuracy` (core/preconditioner/jacobi_utils.hpp:        \
+     * 100-189; reductions that narrow the exponent range are verified by inverting the        \
+     * rounded inverse), ONE precision per storage group, blocks stored converted: float /     \
+     * gko::half / truncated<double,2> / truncated<float,2> / truncated<double,4> for double,  \
+     * gko::half / truncated<float,2> for float.  conditioning == NULL or block_precisions ==  \
+     * NULL behave as in the reference (no detection / full precision).  Precisions,           \
+     * condition numbers and stored bits are identical to the reference executor's. */        \
+    b200_status b200_jacobi_generate_adaptive_##V##_##I(                                      \
+        b200_ctx* ctx, int64_t num_rows, const IT* row_ptrs, const IT* col_idxs,              \
+        const VT* values, int64_t num_blocks, int32_t max_block_size, double accuracy,        \
+        int64_t block_offset, int64_t group_offset, int32_t group_power, VT* conditioning,    \
+        uint8_t* block_precisions, const IT* block_pointers, VT* blocks);                     \
+    /* jacobi::simple_apply / apply reading every block in its stored precision                \
+     * (reference/preconditioner/jacobi_kernels.cpp:415-520) */                               \
+    b200_status b200_jacobi_simple_apply_adaptive_##V##_##I(                                  \
+        b200_ctx* ctx, int64_t num_blocks, int32_t max_block_size, int64_t block_offset,      \
+        int64_t group_offset, int32_t group_power, const uint8_t* block_precisions,           \
+        const IT* block_pointers, const VT* blocks, const VT* b, int64_t b_stride,            \
+        int64_t num_rhs, VT* x, int64_t x_stride);                                            \
+    b200_status b200_jacobi_apply_adaptive_##V##_##I(                                         \
+        b200_ctx* ctx, int64_t num_blocks, int32_t max_block_size, int64_t block_offset,      \
+        int64_t group_offset, int32_t group_power, const uint8_t* block_precisions,           \
+        const IT* block_pointers, const VT* blocks, const VT* alpha, const VT* b,             \
+        int64_t b_stride, int64_t num_rhs, const VT* beta, VT* x, int64_t x_stride);          \
+    /* jacobi::transpose_jacobi with stored precisions (reference/...:597-627) */             \
+    b200_status b200_jacobi_transpose_adaptive_##V##_##I(                                     \
+        b200_ctx* ctx, int64_t num_blocks, int32_t max_block_size, int64_t block_offset,      \
+        int64_t group_offset, int32_t group_power, const uint8_t* block_precisions,           \
+        const IT* block_pointers, const VT* blocks, VT* out_blocks);
+
+/* jacobi::initialize_precisions (reference/preconditioner/jacobi_kernels.cpp:453-461):
+ * precisions[i] = source[i % source_size] */
+b200_status b200_jacobi_initialize_precisions(b200_ctx* ctx, const uint8_t* source, int64_t source_size,
+                                              uint8_t* precisions, int64_t size);
 
 /* jacobi::find_blocks (core/preconditioner/jacobi_kernels.hpp:19-26; reference/preconditioner/
  * jacobi_kernels.cpp:36-123): natural blocks = maximal runs of rows with identical column

@@ -208,6 +208,89 @@ void solver_case(std::shared_ptr<gko::Executor> ref, std::shared_ptr<gko::Execut
     report(what, rel_diff(x_dev.get(), x_ref.get()), sizeof(V) == 8 ? 1e-7 : 2e-3, it_dev, it_ref);
 }
 
+// the reference's own adaptive-precision block-Jacobi (storage_optimization = autodetect) generated and
+// applied on the device executor: chosen precisions and condition numbers must be IDENTICAL to the
+// ReferenceExecutor's, the stored blocks bit-identical, the apply within tolerance
+template <typename V>
+void adaptive_jacobi_case(std::shared_ptr<gko::Executor> ref, std::shared_ptr<gko::Executor> dev,
+                          const gko::matrix_data<V, gko::int32>& data, unsigned max_block_size, bool transposed)
+{
+    using Dense = gko::matrix::Dense<V>;
+    using Csr = gko::matrix::Csr<V, gko::int32>;
+    using Jacobi = gko::preconditioner::Jacobi<V, gko::int32>;
+    const auto n = data.size[0];
+    struct Out {
+        std::unique_ptr<Dense> x;
+        std::vector<unsigned char> prec, bytes;
+        std::vector<double> cond;
+    };
+    auto run = [&](std::shared_ptr<gko::Executor> exec, Out& o) {
+        auto A_host = Csr::create(exec->get_master());
+        A_host->read(data);
+        auto A = gko::share(gko::clone(exec, A_host));
+        gko::array<gko::int32> ptrs(exec->get_master(), (n + max_block_size - 1) / max_block_size + 1);
+        for (gko::size_type k = 0; k < ptrs.get_size(); ++k)
+            ptrs.get_data()[k] = (gko::int32)std::min<gko::size_type>(k * max_block_size, n);
+        std::shared_ptr<Jacobi> J = Jacobi::build()
+                                        .with_max_block_size(max_block_size)
+                                        .with_block_pointers(gko::array<gko::int32>(exec, ptrs))
+                                        .with_storage_optimization(gko::precision_reduction::autodetect())
+                                        .with_accuracy((gko::remove_complex<V>)0.1)
+                                        .on(exec)
+                                        ->generate(A);
+        if (transposed) J = gko::as<Jacobi>(J->transpose());
+        auto b = Dense::create(exec, gko::dim<2>(n, 2));
+        b->fill(V(1));
+        o.x = Dense::create(exec, gko::dim<2>(n, 2));
+        o.x->fill(V(0));
+        J->apply(b, o.x);
+        exec->synchronize();
+        const auto nb = J->get_num_blocks();
+        gko::array<gko::precision_reduction> pr(exec->get_master(), J->get_parameters().storage_optimization.block_wise);
+        for (gko::size_type k = 0; k < nb; ++k) o.prec.push_back((unsigned char)pr.get_const_data()[k]);
+        gko::array<gko::remove_complex<V>> cond(exec, nb);
+        exec->copy(nb, J->get_conditioning(), cond.get_data());
+        cond.set_executor(exec->get_master());
+        for (gko::size_type k = 0; k < nb; ++k) o.cond.push_back((double)cond.get_const_data()[k]);
+        // stored bits of the blocks actually written: position (r, c) of block k in its precision
+        gko::array<V> blocks(exec, J->get_num_stored_elements());
+        exec->copy(J->get_num_stored_elements(), J->get_blocks(), blocks.get_data());
+        blocks.set_executor(exec->get_master());
+        const auto sch = J->get_storage_scheme();
+        for (gko::size_type k = 0; k < nb; ++k) {
+            const auto p = o.prec[k];
+            const int w = sizeof(V) == 8 ? (p == 0x01 || p == 0x10 ? 4 : (p == 0x00 ? 8 : 2)) : (p == 0x00 ? 4 : 2);
+            const auto* base = reinterpret_cast<const unsigned char*>(blocks.get_const_data() + sch.get_group_offset(k));
+            const int bs = ptrs.get_const_data()[k + 1] - ptrs.get_const_data()[k];
+            for (int c = 0; c < bs; ++c)
+                for (int r = 0; r < bs; ++r) {
+                    const std::size_t idx = sch.get_block_offset(k) + r + c * sch.get_stride();
+                    for (int q = 0; q < w; ++q) o.bytes.push_back(base[idx * w + q]);
+                }
+        }
+    };
+    Out a, d;
+    run(ref, a);
+    run(dev, d);
+    char what[160];
+    std::snprintf(what, sizeof what, "preconditioner::Jacobi(%u, autodetect)%s chosen precisions (%s)", max_block_size,
+                  transposed ? "^T" : "", sizeof(V) == 8 ? "f64" : "f32");
+    report(what, a.prec == d.prec ? 0.0 : 1.0, 0.0);
+    std::snprintf(what, sizeof what, "preconditioner::Jacobi(%u, autodetect)%s condition numbers", max_block_size,
+                  transposed ? "^T" : "");
+    report(what, a.cond == d.cond ? 0.0 : 1.0, 0.0);
+    std::snprintf(what, sizeof what, "preconditioner::Jacobi(%u, autodetect)%s stored block bits", max_block_size,
+                  transposed ? "^T" : "");
+    report(what, a.bytes == d.bytes ? 0.0 : 1.0, 0.0);
+    std::snprintf(what, sizeof what, "preconditioner::Jacobi(%u, autodetect)%s::apply (2 rhs)", max_block_size,
+                  transposed ? "^T" : "");
+    report(what, rel_diff(d.x.get(), a.x.get()), sizeof(V) == 8 ? 1e-14 : 1e-6);
+    int hist[256] = {};
+    for (auto p : d.prec) hist[p]++;
+    std::printf("#   precisions on the device: (0,0) %d  (0,1) %d  (0,2) %d  (1,0) %d  (1,1) %d  (2,0) %d\n", hist[0x00],
+                hist[0x01], hist[0x02], hist[0x10], hist[0x11], hist[0x20]);
+}
+
 }  // namespace
 
 int main(int argc, char** argv)
@@ -247,6 +330,10 @@ int main(int argc, char** argv)
         solver_case<double, gko::solver::Bicgstab<double>>(ref, dev, ns, "Bicgstab", 1, 1e-10);
         solver_case<double, gko::solver::Gmres<double>>(ref, dev, ns, "Gmres", 1, 1e-10);
         solver_case<float, gko::solver::Gmres<float>>(ref, dev, ns_f, "Gmres", 8, 1e-5);
+        adaptive_jacobi_case<double>(ref, dev, ns, 16, false);
+        adaptive_jacobi_case<double>(ref, dev, lap, 7, false);
+        adaptive_jacobi_case<double>(ref, dev, ns, 32, true);
+        adaptive_jacobi_case<float>(ref, dev, ns_f, 16, false);
     } catch (const std::exception& e) {
         std::printf("EXCEPTION: %s\n", e.what());
         ++failures;
