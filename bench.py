@@ -419,8 +419,8 @@ def run_gpu_arm(args, rank, world):
         zbytes = W.spmv_bytes(N_ROWS, N_ROWS, zva.numel())
         with torch.cuda.stream(ex.stream):
             zl = (zrp[1:] - zrp[:-1])
-            zmax, zlong = int(zl.max().item()), int((zl >= 4096).sum().item())
-        skew = {"workload": "skewed twin of cfg2: n=%d, Zipf row lengths (longest row %d entries, %d rows >= 4096 "
+            zmax, zlong = int(zl.max().item()), int((zl >= 1024).sum().item())
+        skew = {"workload": "skewed twin of cfg2: n=%d, Zipf row lengths (longest row %d entries, %d rows >= 1024 "
                             "split over CTAs), nnz=%d, columns spread over all of x"
                             % (N_ROWS, zmax, zlong, zva.numel()),
                 "ms_per_step": ms_z, "gflops": 2.0 * zva.numel() / (ms_z * 1e-3) / 1e9,

@@ -33,6 +33,11 @@ struct b200_ctx {
     unsigned int* counters = nullptr;  // zero-initialised, self-resetting block counters
     uint8_t* pinned = nullptr;    // small pinned host mailbox (stop flags)
     void* dev_mailbox = nullptr;  // small device mailbox
+    // fork / join of independent kernels of ONE operation (csr: the rows split over CTAs next to the
+    // main kernel): aux waits for `fork` recorded on stream, stream waits for `join` recorded on aux.
+    // Plain event dependencies, so they are captured into CUDA graphs like any other launch.
+    cudaStream_t aux = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
 
     // returns a scratch pointer of at least `bytes` (stream ordered re-use)
     void* scratch(size_t bytes);

@@ -71,6 +71,9 @@ b200_status b200_ctx_create(int32_t device_id, void* cuda_stream, b200_ctx** out
         B200_CUDA_CHECK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->owns_stream = true;
     }
+    B200_CUDA_CHECK(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
+    B200_CUDA_CHECK(cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming));
+    B200_CUDA_CHECK(cudaEventCreateWithFlags(&c->join, cudaEventDisableTiming));
     {
         // keep released blocks in the device pool instead of returning them to the driver
         cudaMemPool_t pool;
@@ -96,6 +99,12 @@ void b200_ctx_destroy(b200_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->aux) {
+        cudaStreamSynchronize(ctx->aux);
+        cudaStreamDestroy(ctx->aux);
+    }
+    if (ctx->fork) cudaEventDestroy(ctx->fork);
+    if (ctx->join) cudaEventDestroy(ctx->join);
     if (ctx->ws.ptr) cudaFree(ctx->ws.ptr);
     if (ctx->counters) cudaFree(ctx->counters);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);

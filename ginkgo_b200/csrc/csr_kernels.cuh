@@ -130,7 +130,7 @@ template <typename V, int LANES, bool ADVANCED, bool DOT, typename RowPtr>
 __device__ __forceinline__ void row_phase(int64_t r0, int64_t rows_end, int64_t a0, const V* prod,
                                           RowPtr rp, V beta, const V* __restrict__ b,
                                           int64_t b_stride, V* __restrict__ c, int64_t c_stride,
-                                          V& dot_acc)
+                                          V& dot_acc, int64_t skip_from = 0)
 {
     constexpr int kRowsPerPass = kThreads / LANES;
     const int tid = threadIdx.x;
@@ -139,11 +139,17 @@ __device__ __forceinline__ void row_phase(int64_t r0, int64_t rows_end, int64_t 
     const int64_t passes = (nrows + kRowsPerPass - 1) / kRowsPerPass;
     for (int64_t ps = 0; ps < passes; ++ps) {
         const int64_t r = r0 + ps * kRowsPerPass + tid / LANES;
-        const bool rv = r < rows_end;
+        bool rv = r < rows_end;
         int64_t s = 0, e = 0;
         if (rv) {
             s = rp(r);
             e = rp(r + 1);
+        }
+        // rows the plan splits over CTAs (long_rows_kernel) are not this kernel's: with a tile larger
+        // than the split threshold such a row can sit anywhere in the tile, not only at its end
+        if (skip_from > 0 && e - s >= skip_from) {
+            rv = false;
+            s = e = 0;
         }
         V acc = V(0);
         if (LANES == 1) {
@@ -233,6 +239,7 @@ constexpr int kWTile = 256;
 constexpr int kWCap = kWTile + 64 + 8;   // staged nonzeros per warp tile
 constexpr int kWarpsPerCta = 8;
 constexpr int kWCtasPerSm = 2;  // 128 registers: the register-resident prefetch must not spill
+constexpr int kWideRow = 64;    // LANES == 1: rows of this many entries or more are summed by the whole warp
 
 template <typename V, typename I, int LANES, bool ADVANCED, bool DOT>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, kWCtasPerSm)
@@ -362,9 +369,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kWCtasPerSm)
                 }
                 if (!rv) s = e = 0;
                 V acc = V(0);
+                // LANES == 1 plans (average row <= 32) on skewed matrices: a row of kWideRow or more
+                // entries is not left to one lane (300 dependent adds while 31 lanes idle: the Zipf
+                // twin of cfg2 spent a quarter of its time there) but summed by the whole warp below
+                const bool wide = LANES == 1 && (e - s) >= kWideRow;
                 if (LANES == 1) {
-                    if (ADVANCED && rv && beta != V(0)) acc = c[(r0 + rloc) * c_stride] * beta;
-                    for (int64_t i = s; i < e; ++i) acc += prod[i - p0];
+                    if (!wide) {
+                        if (ADVANCED && rv && beta != V(0)) acc = c[(r0 + rloc) * c_stride] * beta;
+                        for (int64_t i = s; i < e; ++i) acc += prod[i - p0];
+                    }
                 } else {
                     for (int64_t i = s + sub; i < e; i += LANES) acc += prod[i - p0];
 #pragma unroll
@@ -373,9 +386,26 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, kWCtasPerSm)
                     if (ADVANCED && rv && sub == 0 && beta != V(0))
                         acc = c[(r0 + rloc) * c_stride] * beta + acc;
                 }
-                if (rv && sub == 0) {
+                if (rv && sub == 0 && !wide) {
                     c[(r0 + rloc) * c_stride] = acc;
                     if (DOT) dot_acc += b[(r0 + rloc) * b_stride] * acc;
+                }
+                if (LANES == 1) {
+                    unsigned wm = __ballot_sync(0xffffffffu, wide);
+                    while (wm) {
+                        const int src = __ffs(wm) - 1;
+                        wm &= wm - 1;
+                        const int64_t ws = __shfl_sync(0xffffffffu, s, src);
+                        const int64_t we = __shfl_sync(0xffffffffu, e, src);
+                        V part = V(0);
+                        for (int64_t i = ws + lane; i < we; i += 32) part += prod[i - p0];
+                        part = warp_sum(part);  // fixed tree: deterministic
+                        if (lane == src) {
+                            if (ADVANCED && beta != V(0)) part = c[(r0 + rloc) * c_stride] * beta + part;
+                            c[(r0 + rloc) * c_stride] = part;
+                            if (DOT) dot_acc += b[(r0 + rloc) * b_stride] * part;
+                        }
+                    }
                 }
             }
             // ---- a last row that does not fit the strip: the whole warp sums it
@@ -654,7 +684,7 @@ __global__ void __launch_bounds__(kThreads, 3)
         __syncthreads();
         row_phase<V, LANES, ADVANCED, DOT>(
             r0, rows_end, a0, prod, [&](int64_t r) { return (int64_t)row_ptrs[r]; }, beta, b, b_stride,
-            c, c_stride, dot_acc);
+            c, c_stride, dot_acc, dot.skip_from);
         if (long_last && !(dot.skip_from > 0 && p1 - sl >= dot.skip_from))
             long_row<V, I, ADVANCED, DOT>(rl, sl, p1, col_idxs, values, alpha, beta, b, b_stride, c,
                                           c_stride, red, dot_acc, pol_first, pol_last);
@@ -748,10 +778,12 @@ __global__ void __launch_bounds__(256)
 // carry fix-up of the reference's merge-path / load-balance kernels
 // (common/cuda_hip/matrix/csr_kernels.template.cpp:208-505), which use atomic_add.
 // --------------------------------------------------------------------------
-// 4096: a row below the threshold is at most 128 rounds of 32 entries for the one warp that owns it
-// (16384 / 8192 until r02j: the Zipf twin of cfg2 ran at 55 % of the uniform matrix's rate, the tail
-// being single warps with 16 K-entry rows)
-constexpr int64_t kLongRow = 4096;
+// 1024: a row below the threshold is at most 32 rounds of 32 entries for the one warp that owns it, so
+// the static deal of tiles to warps stays balanced; everything longer goes to long_rows_kernel, which
+// runs at the gather rate of the memory system (16384 / 8192 until r02j, 4096 / 4096 in r02k: the Zipf
+// twin of cfg2 at 55 % / 65 % of the uniform matrix's rate, single warps with multi-thousand-entry
+// rows being the tail of the main kernel -- profiles/r02l_zipf_launches_before.csv)
+constexpr int64_t kLongRow = 1024;
 constexpr int64_t kLongChunk = 4096;
 
 struct LongRows {
@@ -771,11 +803,19 @@ __global__ void __launch_bounds__(256) long_rows_kernel(LongRows lr, const I* __
                                                        const V* __restrict__ alpha_p,
                                                        const V* __restrict__ b, int64_t b_stride,
                                                        const V* __restrict__ beta_p, V* __restrict__ c,
-                                                       int64_t c_stride, const int32_t* ctl)
+                                                       int64_t c_stride, const int32_t* ctl,
+                                                       const unsigned long long* wait_flag,
+                                                       unsigned long long wait_epoch)
 {
     __shared__ V red[32];
     __shared__ bool last;
     if (ctl && ctl[0] != 0) return;
+    {  // multi-GPU pipelining: the owner block this launch gathers from must have landed (see DotArgs)
+        DotArgs<V> w{};
+        w.wait_flag = wait_flag;
+        w.wait_epoch = wait_epoch;
+        wait_for_block(w);
+    }
     const int tid = threadIdx.x;
     const int64_t chunk = blockIdx.x;
     const int k = lr.chunk_row[chunk];

@@ -262,10 +262,14 @@ __global__ void __launch_bounds__((NW + NP) * 32, 1)
                         s = (int)((int64_t)rp_l[rloc] - a0);
                         len = (int)((int64_t)rp_l[rloc + 1] - a0) - s;
                     }
+                    // rows the plan splits over CTAs are long_rows_kernel's, wherever they sit in the
+                    // stage (the split threshold is below the ring's tile size)
+                    const bool mine = rv && !(dot.skip_from > 0 && len >= dot.skip_from);
+                    if (!mine) len = 0;
                     const int mylen = (len - sub + LANES - 1) / LANES;
                     const int maxlen = __reduce_max_sync(0xffffffffu, mylen);
                     V acc = V(0);
-                    if (LANES == 1 && ADVANCED && rv && beta != V(0)) acc = c[(r0 + rloc) * c_stride] * beta;
+                    if (LANES == 1 && ADVANCED && mine && beta != V(0)) acc = c[(r0 + rloc) * c_stride] * beta;
                     const int i0 = s + sub;
                     for (int j = 0; j < maxlen; j += KB) {
                         I cc[KB];
@@ -293,10 +297,10 @@ __global__ void __launch_bounds__((NW + NP) * 32, 1)
                     if (LANES > 1) {
 #pragma unroll
                         for (int o = LANES / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-                        if (ADVANCED && rv && sub == 0 && beta != V(0))
+                        if (ADVANCED && mine && sub == 0 && beta != V(0))
                             acc = c[(r0 + rloc) * c_stride] * beta + acc;
                     }
-                    if (rv && sub == 0) {
+                    if (mine && sub == 0) {
                         c[(r0 + rloc) * c_stride] = acc;
                         if (DOT) dot_acc += b[(r0 + rloc) * b_stride] * acc;
                     }

@@ -22,9 +22,11 @@ namespace b200 {
 
 // acc += sum_i val_i * b[col_i] over `len` stored entries spaced `step` apart, in storage
 // order, skipping padding (col == -1) exactly like the reference loops.  The loads of kRowBatch
-// entries are issued together (predicated off for padding and for positions past `len`), so
-// a row of 7 entries costs ONE round of (column, value) loads and one of gathers instead of seven
-// (round 1 batched four: two rounds for the 7-pt stencil, SELL-P at 53 % of the HBM roofline).
+// entries are issued together (predicated off for padding and for positions past `len`): a row of
+// 7 entries costs two rounds of (column, value) loads and gathers instead of seven.  Batches of 8
+// (one round for the 7-pt stencil) were measured and REJECTED: 80 instead of 46 registers per
+// thread take a third of the resident warps away and with them the bytes in flight -- ELL 77 % ->
+// 63 %, SELL-P 53 % -> 41 % of the HBM roofline (profiles/r01h_ vs r02l_kernels_roofline.json).
 template <typename V, typename I, bool ADVANCED>
 __device__ __forceinline__ V strided_row_sum(V acc, const I* __restrict__ cols,
                                              const V* __restrict__ vals, int64_t step, int64_t len,
@@ -32,7 +34,7 @@ __device__ __forceinline__ V strided_row_sum(V acc, const I* __restrict__ cols,
                                              const V* __restrict__ b, int64_t b_stride,
                                              uint64_t pol_first, uint64_t pol_last)
 {
-    constexpr int kRowBatch = 8;
+    constexpr int kRowBatch = 4;
     for (int64_t i = lane_first; i < len; i += kRowBatch * lane_step) {
         I c[kRowBatch];
         V v[kRowBatch], x[kRowBatch];

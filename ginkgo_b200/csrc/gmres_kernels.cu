@@ -228,8 +228,22 @@ b200_status multi_dot(b200_ctx* ctx, int64_t rows, int64_t cols, int64_t num_bas
     constexpr int kVW = 16 / (int)sizeof(V);
     const bool vec_ok = cols == 1 && ks == 1 && ws == 1 && rows % kVW == 0 &&
                         ((uintptr_t)krylov % 16) == 0 && ((uintptr_t)w % 16) == 0;
+    // exactly one resident wave: the kernel keeps 16 accumulators + 17 vector loads per thread (128
+    // registers -> 2 CTAs per SM); the old cap of 3 CTAs per SM left a half-empty second wave behind
+    // the first -- 49 % of the HBM roofline on cfg4's 30 x 4M basis (profiles/r02l_kernels_roofline.json)
+    static thread_local int per_sm[2] = {0, 0};
+    int& occ = per_sm[vec_ok ? 1 : 0];
+    if (occ == 0) {
+        if (vec_ok)
+            B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, multi_dot_kernel<V, kVW>,
+                                                                          kMdThreads, 0));
+        else
+            B200_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, multi_dot_kernel<V, 1>,
+                                                                          kMdThreads, 0));
+        if (occ < 1) occ = 1;
+    }
     int grid = (int)ceildiv(rows, (int64_t)kMdThreads * (vec_ok ? kVW : 1) * 2);
-    if (grid > ctx->num_sms * 3) grid = ctx->num_sms * 3;
+    if (grid > ctx->num_sms * occ) grid = ctx->num_sms * occ;
     if (grid < 1) grid = 1;
     V* partials = (V*)ctx->scratch(sizeof(V) * grid * num_bases * cols);
     if (!partials) return B200_ERR_ALLOC;

@@ -64,14 +64,14 @@ __device__ __forceinline__ uint16_t float_to_gko_half(float f)
     const uint32_t tail = d & 0x1fffu;
     return (uint16_t)(result + ((tail > 0x1000u || (tail == 0x1000u && (result & 1u))) ? 1u : 0u));
 }
-// half.hpp:434-448 (half2float)
+// half.hpp:434-448 (half2float), branch-free
 __device__ __forceinline__ float gko_half_to_float(uint16_t h)
 {
     const uint32_t sign = ((uint32_t)h & 0x8000u) << 16;
-    if ((h & 0x7c00u) == 0x7c00u) return __uint_as_float(sign | 0x7f800000u | ((h & 0x03ffu) ? 0x007fffffu : 0u));
-    if ((h & 0x7c00u) == 0) return __uint_as_float(sign);
-    const uint32_t e = ((uint32_t)(h & 0x7c00u) << 13) + (0x3f800000u - (0x3c00u << 13));
-    return __uint_as_float(sign | e | ((uint32_t)(h & 0x03ffu) << 13));
+    const uint32_t ex = h & 0x7c00u, sig = h & 0x03ffu;
+    const uint32_t normal = sign | (((uint32_t)ex << 13) + (0x3f800000u - (0x3c00u << 13))) | ((uint32_t)sig << 13);
+    const uint32_t special = sign | 0x7f800000u | (sig ? 0x007fffffu : 0u);  // inf / nan
+    return __uint_as_float(ex == 0x7c00u ? special : (ex == 0 ? sign : normal));
 }
 
 __device__ __forceinline__ void store_elem(void* base, int64_t idx, int kind, double v)

@@ -12,6 +12,8 @@
 // common/unified/preconditioner/jacobi_kernels.cpp:39-105; block apply replaces
 // common/cuda_hip/preconditioner/jacobi_{simple,advanced}_apply_kernels
 // (contract reference/preconditioner/jacobi_kernels.cpp:419-592).
+#include <stdlib.h>
+
 #include "elementwise.cuh"
 #include "jacobi_precision.cuh"
 
@@ -102,7 +104,7 @@ namespace jacobi {
 // l / block_offset, so every load of a block column is a single coalesced run for the whole
 // warp.  All MBS columns are fetched before the first multiply (no chain of dependent
 // latencies) and stay in registers for every right-hand side.
-template <typename V, typename I, int MBS, bool ADVANCED>
+template <typename V, typename I, int MBS, bool ADVANCED, bool ADAPTIVE>
 __global__ void __launch_bounds__(256)
     block_apply_kernel(int64_t num_blocks, int64_t block_offset, int64_t group_offset,
                        int32_t group_power, const uint8_t* __restrict__ block_precisions,
@@ -128,14 +130,58 @@ __global__ void __launch_bounds__(256)
     const bool valid = r < bsz;
     const int64_t stride = block_offset << group_power;
     // adaptive precision (jacobi_precision.cuh): the block is stored as the type its precision_reduction
-    // byte names, addressed in elements of THAT type from the group's base, and widened on load
+    // byte names, addressed in elements of THAT type from the group's base, and widened on load.
+    // ADAPTIVE == false (no precision array) is the round-1 kernel unchanged: cfg4's GMRES applies it
+    // every iteration.
     const int kind =
-        storage_kind<V>((block_precisions && sub < group_size && k < num_blocks) ? block_precisions[k] : uint8_t(0));
+        ADAPTIVE ? storage_kind<V>((sub < group_size && k < num_blocks) ? block_precisions[k] : uint8_t(0))
+                 : (sizeof(V) == 8 ? (int)kF64 : (int)kF32);
     const void* gbase = blocks + group_offset * group;
     V a[MBS];
+    // Two phases: ALL raw loads of the column set first (by storage width), then the conversions.  With
+    // the conversion next to each load the branches of gko::half's inf / nan / denormal handling kept
+    // the compiler from hoisting the loads: 16 dependent round trips per warp, 0.24 ms instead of
+    // 0.07 ms on cfg4's blocks (profiles/r02n_jacobi_probe.txt).
+    const int64_t e0 = lane;
+    if (!ADAPTIVE) {
+        const V* col0 = blocks + group_offset * group + lane;
 #pragma unroll
-    for (int inner = 0; inner < MBS; ++inner)
-        a[inner] = (valid && inner < bsz) ? load_elem(gbase, lane + inner * stride, kind, V(0)) : V(0);
+        for (int inner = 0; inner < MBS; ++inner)
+            a[inner] = (valid && inner < bsz) ? col0[inner * stride] : V(0);
+    } else
+    switch (storage_bytes(kind)) {
+    case 8: {
+#pragma unroll
+        for (int inner = 0; inner < MBS; ++inner)
+            a[inner] = (valid && inner < bsz) ? (V) reinterpret_cast<const double*>(gbase)[e0 + inner * stride] : V(0);
+        break;
+    }
+    case 4: {
+        uint32_t raw[MBS];
+#pragma unroll
+        for (int inner = 0; inner < MBS; ++inner)
+            raw[inner] = (valid && inner < bsz) ? reinterpret_cast<const uint32_t*>(gbase)[e0 + inner * stride] : 0u;
+#pragma unroll
+        for (int inner = 0; inner < MBS; ++inner)
+            a[inner] = kind == kF32 ? (V)__uint_as_float(raw[inner]) : (V)__hiloint2double((int)raw[inner], 0);
+        break;
+    }
+    default: {
+        uint16_t raw[MBS];
+#pragma unroll
+        for (int inner = 0; inner < MBS; ++inner)
+            raw[inner] = (valid && inner < bsz) ? reinterpret_cast<const uint16_t*>(gbase)[e0 + inner * stride]
+                                                : uint16_t(0);
+#pragma unroll
+        for (int inner = 0; inner < MBS; ++inner) {
+            const uint32_t w = (uint32_t)raw[inner] << 16;
+            a[inner] = kind == kF16     ? (V)gko_half_to_float(raw[inner])
+                       : kind == kT32_16 ? (V)__uint_as_float(w)
+                                         : (V)__hiloint2double((int)w, 0);
+        }
+        break;
+    }
+    }
     V alpha = V(1), beta = V(0);
     if (ADVANCED) {
         alpha = *alpha_p;
@@ -155,6 +201,126 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// --------------------------------------------------------------------------------------------
+// Many right-hand sides: the block apply is a batch of small dense GEMMs  X_k = Binv_k B_k
+// (bs x bs times bs x nrhs) -- the one place of the path where tensor cores apply (SURVEY.md 8d,
+// north_star).  The reference loops the right-hand sides inside apply_block
+// (reference/preconditioner/jacobi_kernels.cpp:415-447; its CUDA backend launches one GEMV kernel
+// per block row, common/cuda_hip/preconditioner/jacobi_simple_apply_kernels.cpp:41-55).
+// Here: one warp per block, the block's inverse is loaded ONCE into DMMA A-fragments (in its
+// stored precision, widened to fp64), then for every tile of 8 right-hand sides
+// MT x KS  mma.sync.m8n8k4.f64  (SASS DMMA) accumulate in fp64; fp32 operands are widened, so
+// products are exact and only the final store rounds.  Summation order differs from the
+// reference's sequential inner loop (k in chunks of 4 inside the tensor core): results agree to
+// r<T>, not bit for bit -- the SIMT kernel above stays the path for fewer than 8 (fp32: 16) right-hand sides.
+// Roofline: per block bs^2 + 2 bs nrhs values of traffic against 2 bs^2 nrhs flops -- 16 x 16 fp64
+// with 32 right-hand sides is 1.6 flop/B, i.e. 10 TFLOP/s at the HBM peak: far beyond issuing one
+// DFMA per product from shuffled operands (the SIMT kernel: 3 instructions per product and lane),
+// well inside the 40 TFLOP/s of the fp64 tensor pipe.
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+constexpr int kMmaWarps = 8;
+
+template <typename V, typename I, int MT, bool ADVANCED>
+__global__ void __launch_bounds__(kMmaWarps * 32)
+    block_apply_mma_kernel(int64_t num_blocks, int64_t block_offset, int64_t group_offset, int32_t group_power,
+                           const uint8_t* __restrict__ block_precisions, const I* __restrict__ block_ptrs,
+                           const V* __restrict__ blocks, const V* __restrict__ alpha_p,
+                           const V* __restrict__ b, int64_t bs_, int64_t num_rhs,
+                           const V* __restrict__ beta_p, V* __restrict__ x, int64_t xs)
+{
+    constexpr int KS = 2 * MT;  // k-steps of 4 covering 8 * MT columns
+    const int lane = threadIdx.x & 31;
+    const int64_t k = (int64_t)blockIdx.x * kMmaWarps + (threadIdx.x >> 5);
+    if (k >= num_blocks) return;
+    const int64_t first = block_ptrs[k];
+    const int bsz = (int)((int64_t)block_ptrs[k + 1] - first);
+    const int gid = lane >> 2, tig = lane & 3;
+    const int64_t stride = block_offset << group_power;
+    const void* gbase = blocks + group_offset * (k >> group_power);
+    const int64_t bo = block_offset * (k & (((int64_t)1 << group_power) - 1));
+    const int kind = storage_kind<V>(block_precisions ? block_precisions[k] : uint8_t(0));
+    // A fragments: element (row, col) of the inverse, row = 8 mt + gid, col = 4 ks + tig
+    double a[MT][KS];
+    auto load_frags = [&](auto get) {
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                const int row = 8 * mt + gid, col = 4 * ks + tig;
+                a[mt][ks] = (row < bsz && col < bsz) ? get(bo + row + col * stride) : 0.0;
+            }
+    };
+    switch (kind) {  // outside the loops: one branch, then MT * KS independent loads
+    case kF64: load_frags([&](int64_t i) { return reinterpret_cast<const double*>(gbase)[i]; }); break;
+    case kF32: load_frags([&](int64_t i) { return (double)reinterpret_cast<const float*>(gbase)[i]; }); break;
+    default: load_frags([&](int64_t i) { return (double)load_elem(gbase, i, kind, V(0)); }); break;
+    }
+    double alpha = 1.0, beta = 0.0;
+    if (ADVANCED) {
+        alpha = (double)*alpha_p;
+        beta = (double)*beta_p;
+    }
+    for (int64_t j0 = 0; j0 < num_rhs; j0 += 8) {
+        // B fragments: element (kk, n) of the right-hand-side block, kk = 4 ks + tig, n = gid
+        double bf[KS];
+        const bool ncol = j0 + gid < num_rhs;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            const int kk = 4 * ks + tig;
+            bf[ks] = (ncol && kk < bsz) ? (double)b[(first + kk) * bs_ + j0 + gid] : 0.0;
+        }
+        double c[MT][2];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            c[mt][0] = c[mt][1] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) dmma_m8n8k4(c[mt][0], c[mt][1], a[mt][ks], bf[ks]);
+        }
+        // D fragments: row = 8 mt + gid, columns 2 tig, 2 tig + 1 of the tile
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+            const int row = 8 * mt + gid;
+            if (row >= bsz) continue;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int64_t col = j0 + 2 * tig + q;
+                if (col >= num_rhs) continue;
+                V* dst = x + (first + row) * xs + col;
+                double v = c[mt][q];
+                if (ADVANCED) v = beta != 0.0 ? alpha * v + beta * (double)*dst : alpha * v;
+                *dst = (V)v;
+            }
+        }
+    }
+}
+
+// which kernel applies the blocks: -1 (default) tensor cores from 8 right-hand sides on, 0 always the SIMT
+// kernel (bit-identical to the reference for any number of right-hand sides), 1 always the tensor cores.
+// B200_JACOBI_MMA in the environment sets the initial value, b200_jacobi_apply_mode changes it.
+inline int& mma_mode()
+{
+    static int mode = [] {
+        const char* env = getenv("B200_JACOBI_MMA");
+        return env ? (env[0] == '0' ? 0 : (env[0] == '1' ? 1 : -1)) : -1;
+    }();
+    return mode;
+}
+// fp64: 8 right-hand sides fill one DMMA tile -- 97 % of the HBM roofline against 46 % for the SIMT kernel;
+// fp32 operands are widened to fp64, the DMMA pipe (not HBM) bounds that path and it overtakes the
+// SIMT kernel between 8 and 16 right-hand sides (profiles/r02l_kernels_roofline.json)
+inline bool use_mma(int64_t num_rhs, size_t value_bytes)
+{
+    const int m = mma_mode();
+    return m == 1 || (m < 0 && num_rhs >= (value_bytes == 8 ? 8 : 16));
+}
+
 template <typename V, typename I, bool ADVANCED>
 b200_status block_apply(b200_ctx* ctx, int64_t num_blocks, int32_t max_block_size,
                         int64_t block_offset, int64_t group_offset, int32_t group_power,
@@ -167,12 +333,35 @@ b200_status block_apply(b200_ctx* ctx, int64_t num_blocks, int32_t max_block_siz
     B200_REQUIRE(block_offset >= 1 && (block_offset << group_power) <= 32 && group_power >= 0,
                  "storage scheme does not fit a warp");
     if (num_blocks <= 0 || num_rhs <= 0) return B200_OK;
+    if (use_mma(num_rhs, sizeof(V))) {
+        const unsigned mgrid = (unsigned)ceildiv(num_blocks, (int64_t)kMmaWarps);
+#define B200_BJM(M)                                                                               \
+    block_apply_mma_kernel<V, I, M, ADVANCED><<<mgrid, kMmaWarps * 32, 0, ctx->stream>>>(         \
+        num_blocks, block_offset, group_offset, group_power, block_precisions, block_ptrs, blocks, \
+        alpha, b, bs, num_rhs, beta, x, xs)
+        if (max_block_size <= 8)
+            B200_BJM(1);
+        else if (max_block_size <= 16)
+            B200_BJM(2);
+        else
+            B200_BJM(4);
+#undef B200_BJM
+        B200_LAUNCH_CHECK(ctx);
+        return B200_OK;
+    }
     const int64_t groups = ceildiv(num_blocks, int64_t(1) << group_power);
     const unsigned grid = (unsigned)ceildiv(groups * 32, (int64_t)256);
 #define B200_BJ(M)                                                                              \
-    block_apply_kernel<V, I, M, ADVANCED><<<grid, 256, 0, ctx->stream>>>(                       \
-        num_blocks, block_offset, group_offset, group_power, block_precisions, block_ptrs,      \
-        blocks, alpha, b, bs, num_rhs, beta, x, xs)
+    do {                                                                                        \
+        if (block_precisions)                                                                   \
+            block_apply_kernel<V, I, M, ADVANCED, true><<<grid, 256, 0, ctx->stream>>>(         \
+                num_blocks, block_offset, group_offset, group_power, block_precisions,          \
+                block_ptrs, blocks, alpha, b, bs, num_rhs, beta, x, xs);                        \
+        else                                                                                    \
+            block_apply_kernel<V, I, M, ADVANCED, false><<<grid, 256, 0, ctx->stream>>>(        \
+                num_blocks, block_offset, group_offset, group_power, nullptr, block_ptrs,       \
+                blocks, alpha, b, bs, num_rhs, beta, x, xs);                                    \
+    } while (0)
     if (block_offset <= 4)
         B200_BJ(4);
     else if (block_offset <= 8)
@@ -190,6 +379,8 @@ b200_status block_apply(b200_ctx* ctx, int64_t num_blocks, int32_t max_block_siz
 }  // namespace b200
 
 extern "C" {
+
+void b200_jacobi_apply_mode(int mode) { b200::jacobi::mma_mode() = mode < 0 ? -1 : (mode ? 1 : 0); }
 
 b200_status b200_set_all_statuses(b200_ctx* ctx, int64_t cols, uint8_t stopping_id,
                                   int32_t set_finalized, uint8_t* stop_status)

@@ -166,7 +166,7 @@ void b200_csr_plan_set_variant(b200_csr_plan* plan, int variant); /* 0 slab, 2 w
 void b200_csr_plan_allow_value_copy(b200_csr_plan* plan, int allow);
 double b200_csr_plan_gather_lines(const b200_csr_plan* plan); /* -1 before tune */
 int b200_csr_plan_parts(const b200_csr_plan* plan); /* > 1: a column-blocked copy is in use */
-/* rows with >= 4096 entries: the plan splits them over CTAs (4096-entry chunks, chunk sums combined
+/* rows with >= 1024 entries: the plan splits them over CTAs (4096-entry chunks, chunk sums combined
  * in chunk order: deterministic) instead of leaving each to one warp / CTA -- the reference's
  * load-balance / merge-path kernels (common/cuda_hip/matrix/csr_kernels.template.cpp:208-505) */
 int64_t b200_csr_plan_num_long_rows(const b200_csr_plan* plan);
@@ -304,6 +304,13 @@ void b200_coo_plan_destroy(b200_coo_plan* plan);
         b200_ctx* ctx, int64_t num_blocks, int32_t max_block_size, int64_t block_offset,      \
         int64_t group_offset, int32_t group_power, const uint8_t* block_precisions,           \
         const IT* block_pointers, const VT* blocks, VT* out_blocks);
+
+/* Block apply with many right-hand sides = a batch of small dense GEMMs: from 8 (fp32: 16) right-hand
+ * sides on the blocks are applied on the fp64 tensor cores (mma.sync.m8n8k4.f64, fp32 operands widened;
+ * agrees with the reference to r<T>), below that by the SIMT kernel whose sums have the reference's
+ * order (bit-identical).  mode: -1 that default, 0 always SIMT, 1 always tensor cores.  Process-wide;
+ * initial value from B200_JACOBI_MMA. */
+void b200_jacobi_apply_mode(int mode);
 
 /* jacobi::initialize_precisions (reference/preconditioner/jacobi_kernels.cpp:453-461):
  * precisions[i] = source[i % source_size] */

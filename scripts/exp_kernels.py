@@ -173,6 +173,49 @@ report("8f-2", "jacobi::generate 250k x 16x16 fp32 (reads the block rows of A)",
 report("a13", "jacobi::simple_apply 250k x 16x16 fp32", nb * bs * bs * 4 + 2 * n4 * 4,
        timeit(lambda: ex.run("b200_jacobi_simple_apply_f32_i32", nb, bs, bs, bs * 2 * bs, gp, bp, blocks, b,
                              1, 1, x, 1)))
+# adaptive-precision generate (autodetect: conditioning + verification inversions) and apply of the result
+with torch.cuda.stream(ex.stream):
+    prec = torch.full((nb,), 0xFF, dtype=torch.uint8, device=dev)
+    cond = torch.zeros(nb, dtype=torch.float32, device=dev)
+    ablocks = torch.zeros(nb * bs * bs, dtype=torch.float32, device=dev)
+
+
+def gen_adaptive():
+    prec.fill_(0xFF)
+    ex.run("b200_jacobi_generate_adaptive_f32_i32", n4, rp, ci, va, nb, bs, 0.1, bs, bs * 2 * bs, gp, cond, prec,
+           bp, ablocks)
+
+
+report("8f-2", "jacobi::generate adaptive (autodetect) 250k x 16x16 fp32",
+       int(va.numel()) * 8 + (n4 + 1) * 4 + nb * bs * bs * 2, timeit(gen_adaptive, reps=10))
+ex.synchronize()
+hist = torch.bincount(prec.long(), minlength=256)
+stored = int(hist[0].item()) * 4 + int((hist.sum() - hist[0]).item()) * 2
+print("# adaptive precisions chosen: " + ", ".join("0x%02x: %d" % (i, int(c)) for i, c in enumerate(hist.tolist()) if c),
+      flush=True)
+report("a13", "jacobi::simple_apply_adaptive 250k x 16x16 fp32 (stored %.0f %% of full)" % (100.0 * stored / (4 * nb)),
+       stored * bs * bs + 2 * n4 * 4,
+       timeit(lambda: ex.run("b200_jacobi_simple_apply_adaptive_f32_i32", nb, bs, bs, bs * 2 * bs, gp, prec, bp,
+                             ablocks, b, 1, 1, x, 1)))
+# many right-hand sides: the block apply as a batch of small GEMMs, SIMT kernel vs fp64 tensor cores
+from ginkgo_b200 import _lib as _L
+for vt_name, tdt, vb in (("f32", torch.float32, 4), ("f64", torch.float64, 8)):
+    for nrhs in (8, 32):
+        with torch.cuda.stream(ex.stream):
+            blk = torch.rand(nb * bs * bs, dtype=tdt, device=dev)
+            bm = torch.rand(n4 * nrhs, dtype=tdt, device=dev)
+            xm = torch.zeros(n4 * nrhs, dtype=tdt, device=dev)
+        nbytes = nb * bs * bs * vb + 2 * n4 * nrhs * vb
+        flops = 2.0 * nb * bs * bs * nrhs
+        for mode, label in ((0, "SIMT"), (1, "fp64 tensor cores")):
+            _L.lib().b200_jacobi_apply_mode(mode)
+            ms = timeit(lambda: ex.run("b200_jacobi_simple_apply_%s_i32" % vt_name, nb, bs, bs, bs * 2 * bs, gp, bp,
+                                       blk, bm, nrhs, nrhs, xm, nrhs), reps=10)
+            report("a13", "jacobi::simple_apply 250k x 16x16 %s, %d rhs, %s (%.1f TFLOP/s)" % (
+                vt_name, nrhs, label, flops / ms / 1e9), nbytes, ms)
+        _L.lib().b200_jacobi_apply_mode(-1)
+        del blk, bm, xm
+        torch.cuda.empty_cache()
 # conversions on cfg4
 n = n4
 with torch.cuda.stream(ex.stream):

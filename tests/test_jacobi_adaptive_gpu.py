@@ -148,3 +148,44 @@ def test_host_layer_jacobi_on_the_device(orc, hexec, vt, max_bs, storage):
         orc("jacobi_transpose_adaptive_%s_i32" % vt, nb, max_bs, O["block_offset"], O["group_offset"],
             O["group_power"], O["precisions"], ptrs, O["blocks"], bt)
         assert np.array_equal(GT["blocks"].view(np.uint8), bt.view(np.uint8))
+
+
+# ------------------------------------------------------------------ many right-hand sides: tensor cores
+@pytest.mark.parametrize("vt", ["f64", "f32"])
+@pytest.mark.parametrize("max_bs", [5, 8, 13, 16, 32])
+@pytest.mark.parametrize("nrhs", [8, 13, 32, 64])
+@pytest.mark.parametrize("storage", [None, JC.AUTODETECT])
+def test_many_rhs_apply_on_the_fp64_tensor_cores(orc, cuda, vt, max_bs, nrhs, storage):
+    """num_rhs >= 8: block_apply_mma_kernel (mma.sync.m8n8k4.f64, fp64 accumulation).  The inner
+    products are summed in another order than the reference's sequential loop: r<T>-scaled tolerance."""
+    n = 999
+    rp, ci, va, ptrs = JC.make(n, max_bs, 300 + max_bs, VT[vt])
+    nb = len(ptrs) - 1
+    O = generate(orc, vt, "i32", rp, ci, va, ptrs, max_bs, storage, 0.1)
+    args = (nb, max_bs, O["block_offset"], O["group_offset"], O["group_power"], O["precisions"], ptrs, O["blocks"])
+    b = np.random.default_rng(19).uniform(-1, 1, (n, nrhs)).astype(VT[vt])
+    ld = nrhs + 3  # strided operands
+    bpad = np.zeros((n, ld), VT[vt])
+    bpad[:, :nrhs] = b
+    xo = np.zeros((n, nrhs), VT[vt])
+    orc("jacobi_simple_apply_adaptive_%s_i32" % vt, *args, b, nrhs, nrhs, xo, nrhs)
+    xc = np.full((n, ld), 7.0, VT[vt])
+    cuda("jacobi_simple_apply_adaptive_%s_i32" % vt, *args, bpad, ld, nrhs, xc, ld)
+    assert H.rel_err(xc[:, :nrhs], xo) <= 4 * H.R[vt]
+    assert np.all(xc[:, nrhs:] == 7.0)  # nothing written past the last right-hand side
+    x0 = np.random.default_rng(20).uniform(-1, 1, (n, nrhs)).astype(VT[vt])
+    al, be = np.array([-0.75], VT[vt]), np.array([1.5], VT[vt])
+    xo2, xc2 = x0.copy(), x0.copy()
+    orc("jacobi_apply_adaptive_%s_i32" % vt, *args, al, b, nrhs, nrhs, be, xo2, nrhs)
+    cuda("jacobi_apply_adaptive_%s_i32" % vt, *args, al, b, nrhs, nrhs, be, xc2, nrhs)
+    assert H.rel_err(xc2, xo2) <= 4 * H.R[vt]
+    if storage is None:  # the plain entry points take the same kernel
+        xc3 = np.zeros((n, nrhs), VT[vt])
+        cuda("jacobi_simple_apply_%s_i32" % vt, nb, max_bs, O["block_offset"], O["group_offset"], O["group_power"],
+             ptrs, O["blocks"], b, nrhs, nrhs, xc3, nrhs)
+        assert np.array_equal(xc3, xc[:, :nrhs])
+        # beta == 0 never reads x (NaN in, clean out)
+        xn = np.full((n, nrhs), np.nan, VT[vt])
+        cuda("jacobi_apply_%s_i32" % vt, nb, max_bs, O["block_offset"], O["group_offset"], O["group_power"], ptrs,
+             O["blocks"], al, b, nrhs, nrhs, np.array([0.0], VT[vt]), xn, nrhs)
+        assert np.all(np.isfinite(xn))

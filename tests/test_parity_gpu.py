@@ -49,11 +49,12 @@ def csr_case(rng, kind, vt, it):
         n, m = 40, 20000
         lens = rng.integers(0, 30, size=n)
         lens[3], lens[17], lens[18], lens[39] = 2500, 5000, 9000, 4200
-    elif kind == "split_rows":  # rows >= 4096 entries (16384 until r02j): split over CTAs by the plan (long_rows_kernel)
+    elif kind == "split_rows":  # rows >= 1024 entries (16384 until r02j): split over CTAs by the plan (long_rows_kernel)
         n, m = 300, 70000
         lens = rng.integers(0, 12, size=n)
         lens[0], lens[5], lens[6], lens[150], lens[299] = 16384, 16383, 50000, 24577, 33000
-        lens[10], lens[11], lens[12] = 4096, 4095, 8193  # the threshold, one below, one entry into a third chunk
+        lens[10], lens[11], lens[12] = 4096, 4095, 8193  # chunk size, one below, one entry into a third chunk
+        lens[13], lens[14], lens[15], lens[16] = 1024, 1023, 64, 63  # split threshold; warp-summed rows (>= 64)
     elif kind == "one_row":
         n, m = 1, 7000
         lens = np.array([6500])
