@@ -38,6 +38,12 @@ struct b200_ctx {
     // Plain event dependencies, so they are captured into CUDA graphs like any other launch.
     cudaStream_t aux = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
+    // b200_snapshot_*: two slots of a stream-ordered "what did this look like at THIS point of the
+    // stream" read-back that does not wait for work enqueued afterwards
+    void* snap_dev = nullptr;      // 2 x kSnapBytes device
+    uint8_t* snap_host = nullptr;  // 2 x kSnapBytes pinned host
+    cudaEvent_t snap_ev[2] = {nullptr, nullptr};
+    static constexpr size_t kSnapBytes = 256;
 
     // returns a scratch pointer of at least `bytes` (stream ordered re-use)
     void* scratch(size_t bytes);

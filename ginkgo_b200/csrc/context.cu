@@ -74,6 +74,9 @@ b200_status b200_ctx_create(int32_t device_id, void* cuda_stream, b200_ctx** out
     B200_CUDA_CHECK(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
     B200_CUDA_CHECK(cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming));
     B200_CUDA_CHECK(cudaEventCreateWithFlags(&c->join, cudaEventDisableTiming));
+    B200_CUDA_CHECK(cudaMalloc(&c->snap_dev, 2 * b200_ctx::kSnapBytes));
+    B200_CUDA_CHECK(cudaMallocHost((void**)&c->snap_host, 2 * b200_ctx::kSnapBytes));
+    for (int i = 0; i < 2; ++i) B200_CUDA_CHECK(cudaEventCreateWithFlags(&c->snap_ev[i], cudaEventDisableTiming));
     {
         // keep released blocks in the device pool instead of returning them to the driver
         cudaMemPool_t pool;
@@ -105,12 +108,47 @@ void b200_ctx_destroy(b200_ctx* ctx)
     }
     if (ctx->fork) cudaEventDestroy(ctx->fork);
     if (ctx->join) cudaEventDestroy(ctx->join);
+    for (int i = 0; i < 2; ++i)
+        if (ctx->snap_ev[i]) cudaEventDestroy(ctx->snap_ev[i]);
+    if (ctx->snap_dev) cudaFree(ctx->snap_dev);
+    if (ctx->snap_host) cudaFreeHost(ctx->snap_host);
     if (ctx->ws.ptr) cudaFree(ctx->ws.ptr);
     if (ctx->counters) cudaFree(ctx->counters);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->dev_mailbox) cudaFree(ctx->dev_mailbox);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+/* Stream-ordered snapshot: the bytes at src_dev AS THEY ARE when the stream reaches this point are
+ * copied into slot `slot` (device to device, on the stream) and from there to pinned host memory on
+ * the auxiliary stream; b200_snapshot_end waits for that copy only -- work enqueued on the stream
+ * after the begin keeps running.  The fused solvers poll their control block this way: the next
+ * batch of iterations is already queued when the host looks at the previous one, so the GPU never
+ * idles for a host round trip (and the ranks of a distributed solve all see the state at the SAME
+ * batch boundary, i.e. take the same decision). */
+b200_status b200_snapshot_begin(b200_ctx* ctx, int32_t slot, const void* src_dev, size_t bytes)
+{
+    B200_REQUIRE(ctx && src_dev, "null argument");
+    B200_REQUIRE(slot >= 0 && slot < 2 && bytes <= b200_ctx::kSnapBytes, "bad snapshot slot / size");
+    B200_CUDA_CHECK(cudaSetDevice(ctx->device));
+    char* d = (char*)ctx->snap_dev + (size_t)slot * b200_ctx::kSnapBytes;
+    B200_CUDA_CHECK(cudaMemcpyAsync(d, src_dev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    B200_CUDA_CHECK(cudaEventRecord(ctx->snap_ev[slot], ctx->stream));
+    B200_CUDA_CHECK(cudaStreamWaitEvent(ctx->aux, ctx->snap_ev[slot], 0));
+    B200_CUDA_CHECK(cudaMemcpyAsync(ctx->snap_host + (size_t)slot * b200_ctx::kSnapBytes, d, bytes,
+                                    cudaMemcpyDeviceToHost, ctx->aux));
+    B200_CUDA_CHECK(cudaEventRecord(ctx->snap_ev[slot], ctx->aux));
+    return B200_OK;
+}
+
+b200_status b200_snapshot_end(b200_ctx* ctx, int32_t slot, void* dst_host, size_t bytes)
+{
+    B200_REQUIRE(ctx && dst_host, "null argument");
+    B200_REQUIRE(slot >= 0 && slot < 2 && bytes <= b200_ctx::kSnapBytes, "bad snapshot slot / size");
+    B200_CUDA_CHECK(cudaEventSynchronize(ctx->snap_ev[slot]));
+    memcpy(dst_host, ctx->snap_host + (size_t)slot * b200_ctx::kSnapBytes, bytes);
+    return B200_OK;
 }
 
 void* b200_ctx_stream(const b200_ctx* ctx) { return (void*)ctx->stream; }

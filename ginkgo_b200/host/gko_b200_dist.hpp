@@ -708,6 +708,9 @@ protected:
                                                          local_->get_const_row_ptrs(), local_->get_const_col_idxs(),
                                                          local_->get_const_values(), P, bounds.data());
             if (st != B200_OK || b200_csr_plan_parts(p) != P) {
+                std::fprintf(stderr, "[gko_b200] rank %d: pipelined exchange unavailable: owner split gave %d parts, "
+                                     "status %d (%s)\n",
+                             r, (int)b200_csr_plan_parts(p), (int)st, b200_last_error());
                 b200_csr_plan_destroy(p);
                 overlap_failed_ = true;
                 return false;
@@ -720,6 +723,7 @@ protected:
         uint64_t epoch = 0;
         if (cabi<V>::halo_exchange_staged_begin(ctx, comm_->get(), halo_, x_ext->get_const_values(), &b, &flags,
                                                 &epoch) != B200_OK) {
+            std::fprintf(stderr, "[gko_b200] rank %d: pipelined exchange unavailable: %s\n", r, b200_last_error());
             overlap_failed_ = true;
             return false;
         }
@@ -965,12 +969,26 @@ public:
         }
         int32 h[8] = {0};
         exec_->copy_to_host(h, ctl_.get_const_data(), 8);
-        while (h[0] == 0) {
-            const int32 before = h[1];
+        if (h[0] == 0) {
+            // One batch of iterations is always queued AHEAD of the one the host looks at: the control
+            // block is read through a stream-ordered snapshot taken at the batch boundary
+            // (b200_snapshot_*), so neither the GPU nor -- distributed -- the other ranks' GPUs wait for
+            // this host's round trip, and every rank sees the state of the same boundary.  After the
+            // stop the kernels of the batch queued ahead are no-ops.
+            int slot = 0;
+            int32 before = h[1];
             GKOB_CALL(b200_graph_launch(ctx, graph_));
-            exec_->copy_to_host(h, ctl_.get_const_data(), 8);
-            if (h[0] == 0 && h[1] == before)
-                throw Error("fused CG: the device iteration made no progress");
+            GKOB_CALL(b200_snapshot_begin(ctx, slot, ctl_.get_const_data(), sizeof(h)));
+            for (;;) {
+                GKOB_CALL(b200_graph_launch(ctx, graph_));
+                GKOB_CALL(b200_snapshot_begin(ctx, slot ^ 1, ctl_.get_const_data(), sizeof(h)));
+                GKOB_CALL(b200_snapshot_end(ctx, slot, h, sizeof(h)));
+                if (h[0] != 0) break;
+                if (h[1] == before) throw Error("fused CG: the device iteration made no progress");
+                before = h[1];
+                slot ^= 1;
+            }
+            exec_->copy_to_host(h, ctl_.get_const_data(), 8);  // drains the batch queued ahead
         }
         num_iterations_ = h[1];
         status_ = (uint8)h[0];

@@ -80,6 +80,12 @@ b200_status b200_copy_h2d(b200_ctx* ctx, void* dst_dev, const void* src_host, si
 b200_status b200_copy_d2h(b200_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes); /* blocking */
 b200_status b200_copy_d2d(b200_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes);  /* async */
 b200_status b200_synchronize(b200_ctx* ctx);
+/* Stream-ordered snapshot of a few bytes (<= 256) of device memory: begin copies them, in stream order,
+ * into slot 0 / 1 and on to pinned host memory on an auxiliary stream; end waits for THAT copy only and
+ * hands the bytes out -- kernels enqueued after the begin keep running.  The fused device-resident
+ * solvers poll their control block with it (one batch of iterations always queued ahead). */
+b200_status b200_snapshot_begin(b200_ctx* ctx, int32_t slot, const void* src_dev, size_t bytes);
+b200_status b200_snapshot_end(b200_ctx* ctx, int32_t slot, void* dst_host, size_t bytes);
 
 /* Staging pipe for HOST-resident operands (the reference clones them onto the device inside
  * LinOp::apply: include/ginkgo/core/base/lin_op.hpp:129-215, make_temporary_clone).  Two

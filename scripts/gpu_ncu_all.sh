@@ -7,6 +7,9 @@
 TAG=${1:-r02}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_gpu.txt 2>&1
+echo "== pytest"; timeout 1500 python -m pytest tests -q -m gpu --timeout 180 2>&1 | tail -4 | tee gpurun_out/${TAG}_pytest_gpu.txt
+echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+echo "== dropin"; timeout 300 tests/dropin/_build/dropin_check cuda > gpurun_out/${TAG}_dropin_check.txt 2>&1; tail -1 gpurun_out/${TAG}_dropin_check.txt
 echo "== bench"; timeout 900 python bench.py --steps 100 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; tail -2 gpurun_out/${TAG}_bench.err; cut -c1-300 gpurun_out/${TAG}_bench.json
 echo "== bench reference arm"; timeout 600 python bench.py --impl reference --steps 20 --warmup 2 > gpurun_out/${TAG}_bench_ref.json 2>gpurun_out/${TAG}_bench_ref.err; cut -c1-400 gpurun_out/${TAG}_bench_ref.json
 echo "== launch list"; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name-base demangled -k regex:'b200::' -c 600 --csv --log-file gpurun_out/${TAG}_launches_bench.csv python bench.py --steps 20 --warmup 3 --no-cpu --small-cg --no-twin > gpurun_out/${TAG}_ncu_launches.log 2>&1; tail -1 gpurun_out/${TAG}_ncu_launches.log | cut -c1-200

@@ -22,7 +22,11 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
         "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
         "launch__shared_mem_per_block_static", "launch__shared_mem_per_block_dynamic",
-        "l1tex__m_xbar2l1tex_read_bytes.sum", "sm__cycles_elapsed.avg.per_second"]
+        "l1tex__m_xbar2l1tex_read_bytes.sum", "sm__cycles_elapsed.avg.per_second",
+        "l1tex__m_l1tex2xbar_req_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "lts__t_requests_srcunit_tex.sum",
+        "smsp__inst_executed.sum"]
 res = []
 for d in data:
     k = {"kernel": d[hdr.index("Kernel Name")][:160]}
