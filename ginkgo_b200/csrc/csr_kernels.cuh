@@ -771,92 +771,6 @@ __global__ void __launch_bounds__(256)
 }
 
 // --------------------------------------------------------------------------
-// several right-hand sides, vectorised (aligned row-major b / c): one lane owns VEC = 16 / sizeof(V)
-// consecutive right-hand sides of one row (a 16-byte gather / store), PL lanes cover the right-hand
-// sides of a tile, 32 / PL consecutive rows per warp.  The (column, value) pairs of the warp's rows are
-// one contiguous run of the matrix: it is read with COALESCED loads, 32 entries per round, and every
-// lane fetches its row's entries from the lane that holds them with shuffles -- the thread-per-(row,
-// rhs) kernel above issues one tiny uncoalesced load pair per row and entry (8 right-hand sides on the
-// 7-pt stencil: 33 % of the HBM roofline).  Every (row, rhs) sum is still left to right.
-// --------------------------------------------------------------------------
-template <typename V>
-struct alignas(16) rhs_vec {
-    V v[16 / sizeof(V)];
-};
-
-template <typename V, typename I, bool ADVANCED, int PL>
-__global__ void __launch_bounds__(256)
-    multi_rhs_vec_kernel(int64_t num_rows, int64_t num_rhs, const I* __restrict__ row_ptrs,
-                         const I* __restrict__ col_idxs, const V* __restrict__ values,
-                         const V* __restrict__ alpha_p, const V* __restrict__ b, int64_t b_stride,
-                         const V* __restrict__ beta_p, V* __restrict__ c, int64_t c_stride)
-{
-    constexpr int VEC = 16 / (int)sizeof(V);
-    constexpr int kRowsPerWarp = 32 / PL;
-    using vec = rhs_vec<V>;
-    const int lane = threadIdx.x & 31;
-    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t row0 = warp * kRowsPerWarp;
-    if (row0 >= num_rows) return;
-    const int rr = lane / PL;
-    const int64_t row = row0 + rr;
-    const int64_t j = ((int64_t)blockIdx.y * PL + lane % PL) * VEC;  // first right-hand side of this lane
-    const bool rv = row < num_rows;
-    const bool jv = rv && j < num_rhs;  // num_rhs % VEC == 0 (host checks): all VEC columns or none
-    V alpha = V(1), beta = V(0);
-    if (ADVANCED) {
-        alpha = *alpha_p;
-        beta = *beta_p;
-    }
-    const int64_t last_row = row0 + kRowsPerWarp < num_rows ? row0 + kRowsPerWarp : num_rows;
-    const int64_t s0 = row_ptrs[row0], e_all = row_ptrs[last_row];
-    const int64_t s = rv ? (int64_t)row_ptrs[row] : e_all;
-    const int64_t e = rv ? (int64_t)row_ptrs[row + 1] : e_all;
-    vec acc;
-#pragma unroll
-    for (int q = 0; q < VEC; ++q) acc.v[q] = V(0);
-    if (ADVANCED && jv && beta != V(0)) {
-        const vec old = *reinterpret_cast<const vec*>(c + row * c_stride + j);
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) acc.v[q] = old.v[q] * beta;
-    }
-    for (int64_t base = s0; base < e_all; base += 32) {
-        // one coalesced round: lane l holds entry base + l
-        const bool ok = base + lane < e_all;
-        const I cl = ok ? col_idxs[base + lane] : I(0);
-        const V vl = ok ? values[base + lane] : V(0);
-        // this lane's row owns [lo, hi) of the round
-        const int64_t lo = s > base ? s : base;
-        const int64_t hi = e < base + 32 ? e : base + 32;
-        const int cnt = hi > lo ? (int)(hi - lo) : 0;
-        const int maxcnt = __reduce_max_sync(0xffffffffu, cnt);
-        constexpr int kB = 4;
-        for (int k0 = 0; k0 < maxcnt; k0 += kB) {
-            I cc[kB];
-            V vv[kB];
-            vec xx[kB];
-#pragma unroll
-            for (int q = 0; q < kB; ++q) {
-                const int src = (k0 + q < cnt) ? (int)(lo - base) + k0 + q : 0;
-                cc[q] = __shfl_sync(0xffffffffu, cl, src);
-                vv[q] = __shfl_sync(0xffffffffu, vl, src);
-            }
-#pragma unroll
-            for (int q = 0; q < kB; ++q)
-                if (k0 + q < cnt && jv) xx[q] = *reinterpret_cast<const vec*>(b + (int64_t)cc[q] * b_stride + j);
-#pragma unroll
-            for (int q = 0; q < kB; ++q)
-                if (k0 + q < cnt && jv) {
-                    const V av = ADVANCED ? alpha * vv[q] : vv[q];
-#pragma unroll
-                    for (int w = 0; w < VEC; ++w) acc.v[w] += av * xx[q].v[w];
-                }
-        }
-    }
-    if (jv) *reinterpret_cast<vec*>(c + row * c_stride + j) = acc;
-}
-
-// --------------------------------------------------------------------------
 // rows split over CTAs (skewed matrices): the plan lists every row with >= kLongRow entries and
 // cuts it into chunks of kLongChunk; one CTA per chunk adds its products (thread t takes entries
 // t, t + 256, ... in order, then a fixed tree), the CTA that finishes a row last adds the row's

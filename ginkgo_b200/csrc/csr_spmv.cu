@@ -22,31 +22,6 @@ b200_status spmv_impl(b200_ctx* ctx, const b200_csr_plan* plan, int64_t num_rows
     B200_REQUIRE(nnz == 0 || (col_idxs && values && b), "null pointer");
     if (ADVANCED) B200_REQUIRE(alpha && beta, "alpha/beta must be device pointers");
 
-    constexpr int kVec = 16 / (int)sizeof(V);
-    if (num_rhs >= 2 * kVec && num_rhs % kVec == 0 && b_stride % kVec == 0 && c_stride % kVec == 0 &&
-        (((uintptr_t)b | (uintptr_t)c) & 15u) == 0) {
-        // aligned row-major operands: 16-byte gathers, coalesced matrix rounds + shuffles
-        // (multi_rhs_vec_kernel); PL lanes cover min(32, num_rhs / kVec) vectors of right-hand sides
-        const int64_t vecs = num_rhs / kVec;
-        int PL = 1;
-        while (PL < vecs && PL < 32) PL *= 2;
-        const int64_t rows_per_block = 8 * (32 / PL);
-        dim3 grid((unsigned)ceildiv(num_rows, rows_per_block), (unsigned)ceildiv(vecs, (int64_t)PL));
-#define B200_MRV(PP)                                                                              \
-    multi_rhs_vec_kernel<V, I, ADVANCED, PP><<<grid, 256, 0, ctx->stream>>>(                      \
-        num_rows, num_rhs, row_ptrs, col_idxs, values, alpha, b, b_stride, beta, c, c_stride)
-        switch (PL) {
-        case 1: B200_MRV(1); break;
-        case 2: B200_MRV(2); break;
-        case 4: B200_MRV(4); break;
-        case 8: B200_MRV(8); break;
-        case 16: B200_MRV(16); break;
-        default: B200_MRV(32); break;
-        }
-#undef B200_MRV
-        B200_LAUNCH_CHECK(ctx);
-        return B200_OK;
-    }
     if (num_rhs > 1) {
         // P lanes per row (next power of two >= num_rhs, at most 32), grid.y chunks of P right-hand sides
         int P = 2;

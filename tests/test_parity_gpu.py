@@ -116,8 +116,7 @@ def test_csr_spmv_multi_rhs_strided(orc, cuda, vt, it):
     rng = np.random.default_rng(7)
     n, m, rp, ci, va = csr_case(rng, "ref_common", vt, it)
     nnz = len(va)
-    # (8, 8, 8) ... : aligned row-major operands take multi_rhs_vec_kernel (16-byte gathers, coalesced matrix
-    # rounds + shuffles); odd strides / counts stay on the thread-per-(row, rhs) kernel.  Same sums either way.
+    # aligned and odd strides / counts: P lanes per row, grid.y tiles of P right-hand sides
     for nrhs, bs, cs in [(3, 3, 3), (3, 5, 4), (43, 45, 46), (8, 8, 8), (8, 12, 10), (12, 12, 16), (64, 64, 64),
                          (4, 4, 4), (136, 136, 140)]:
         x = H.dense(rng, m, nrhs, bs, vt)
