@@ -33,6 +33,11 @@ void* b200_ctx::scratch(size_t bytes)
     return np;
 }
 
+__global__ void snapshot_copy_kernel(const unsigned char* __restrict__ src, unsigned char* __restrict__ dst, int bytes)
+{
+    for (int i = threadIdx.x; i < bytes; i += blockDim.x) dst[i] = src[i];
+}
+
 extern "C" {
 
 const char* b200_last_error(void) { return b200::g_err; }
@@ -133,7 +138,10 @@ b200_status b200_snapshot_begin(b200_ctx* ctx, int32_t slot, const void* src_dev
     B200_REQUIRE(slot >= 0 && slot < 2 && bytes <= b200_ctx::kSnapBytes, "bad snapshot slot / size");
     B200_CUDA_CHECK(cudaSetDevice(ctx->device));
     char* d = (char*)ctx->snap_dev + (size_t)slot * b200_ctx::kSnapBytes;
-    B200_CUDA_CHECK(cudaMemcpyAsync(d, src_dev, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    // a 64-thread kernel, not cudaMemcpyAsync: the copy stays on the compute engine (no hand-over to a
+    // copy engine and back between two graph launches)
+    snapshot_copy_kernel<<<1, 64, 0, ctx->stream>>>((const unsigned char*)src_dev, (unsigned char*)d, (int)bytes);
+    B200_CUDA_CHECK(cudaGetLastError());
     B200_CUDA_CHECK(cudaEventRecord(ctx->snap_ev[slot], ctx->stream));
     B200_CUDA_CHECK(cudaStreamWaitEvent(ctx->aux, ctx->snap_ev[slot], 0));
     B200_CUDA_CHECK(cudaMemcpyAsync(ctx->snap_host + (size_t)slot * b200_ctx::kSnapBytes, d, bytes,
