@@ -775,3 +775,26 @@ def test_cgs_steps(orc, cuda, vt, rows, cols):
                 lambda: [rows, cols, v["t"], st["t"], v["u_hat"], st["u_hat"], v["r"].copy(), st["r"],
                          v["x"].copy(), st["x"], sc["alpha"], stop])
     _all_equal(a, b)
+
+
+def test_snapshot_reads_the_state_at_its_point_of_the_stream(cuda):
+    """b200_snapshot_begin / end (the fused solvers' control-block poll): the bytes are taken IN STREAM
+    ORDER at the begin, work enqueued afterwards neither delays nor changes what end hands out"""
+    if not hasattr(cuda, "ctx"):
+        pytest.skip("harness self-check: no device")
+    import torch
+    with torch.cuda.stream(cuda.stream):
+        t = torch.arange(8, dtype=torch.int32, device="cuda")
+        cuda._libmod.check(cuda.l.b200_snapshot_begin(cuda.ctx, 0, t.data_ptr(), 32))
+        t.add_(100)
+        big = torch.zeros(1 << 26, dtype=torch.float32, device="cuda")
+        for _ in range(8):  # keep the stream busy behind the first snapshot
+            big.add_(1.0)
+        cuda._libmod.check(cuda.l.b200_snapshot_begin(cuda.ctx, 1, t.data_ptr(), 32))
+        t.add_(100)
+    a, b = np.zeros(8, np.int32), np.zeros(8, np.int32)
+    cuda._libmod.check(cuda.l.b200_snapshot_end(cuda.ctx, 0, a.ctypes.data, 32))
+    cuda._libmod.check(cuda.l.b200_snapshot_end(cuda.ctx, 1, b.ctypes.data, 32))
+    assert np.array_equal(a, np.arange(8)) and np.array_equal(b, np.arange(8) + 100)
+    cuda.stream.synchronize()
+    assert int(t[0].item()) == 200
