@@ -80,3 +80,50 @@ def written_mask(block_ptrs, prec, value_is_double, block_offset, group_offset, 
         for b in range(w):
             mask[base + idx * w + b] = True
     return mask
+
+
+def load_golden():
+    """tests/golden/jacobi_adaptive_reference.json (scripts/gen_jacobi_adaptive_golden.py): outputs of the
+    REAL reference for deterministic inputs of make(); returns a list of dicts with decoded arrays"""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "jacobi_adaptive_reference.json")
+    cases = json.load(open(path))["cases"]
+    for c in cases:
+        dt = np.float64 if c["vt"] == "f64" else np.float32
+        c["dtype"] = dt
+        c["precisions"] = np.array(c["precisions"], np.uint8)
+        c["conditioning"] = np.frombuffer(bytes.fromhex(c["conditioning_hex"]), dt)
+        c["stored_bytes"] = np.frombuffer(bytes.fromhex(c["stored_bytes_hex"]), np.uint8)
+        c["x"] = np.frombuffer(bytes.fromhex(c["x_hex"]), dt).reshape(c["n"], 2)
+        c["x_advanced"] = np.frombuffer(bytes.fromhex(c["x_advanced_hex"]), dt).reshape(c["n"], 2)
+    return cases
+
+
+def check_against_golden(backend, c):
+    """run generate + apply + advanced apply on `backend` (tests.helpers Oracle / Cuda) for golden case c
+    and compare with the reference's committed outputs bit for bit"""
+    vt, n, max_bs, dt = c["vt"], c["n"], c["max_block_size"], c["dtype"]
+    rp, ci, va, ptrs = make(n, max_bs, c["seed"], dt)
+    nb = len(ptrs) - 1
+    assert nb == c["num_blocks"]
+    storage = c["storage"]
+    prec = storage_request(storage, nb, c["seed"]) if storage == "mixed" else np.full(nb, storage, np.uint8)
+    cond = np.zeros(nb, dt)
+    bo, go, gp, space = scheme(max_bs, nb)
+    blocks = np.zeros(space, dt)
+    backend("jacobi_generate_adaptive_%s_i32" % vt, n, rp, ci, va, nb, max_bs, float(c["accuracy"]), bo, go, gp, cond,
+            prec, ptrs, blocks)
+    assert np.array_equal(prec, c["precisions"])
+    assert np.array_equal(cond.view(np.uint8), c["conditioning"].view(np.uint8))
+    mask = written_mask(ptrs, prec, vt == "f64", bo, go, gp, space, dt().itemsize)
+    assert np.array_equal(blocks.view(np.uint8)[mask], c["stored_bytes"])
+    b = np.random.default_rng(c["seed"] + 100).uniform(-1, 1, (n, 2)).astype(dt)
+    x0 = np.random.default_rng(c["seed"] + 200).uniform(-1, 1, (n, 2)).astype(dt)
+    x = np.zeros((n, 2), dt)
+    backend("jacobi_simple_apply_adaptive_%s_i32" % vt, nb, max_bs, bo, go, gp, prec, ptrs, blocks, b, 2, 2, x, 2)
+    assert np.array_equal(x.view(np.uint8), c["x"].view(np.uint8))
+    x2 = x0.copy()
+    backend("jacobi_apply_adaptive_%s_i32" % vt, nb, max_bs, bo, go, gp, prec, ptrs, blocks, np.array([-0.75], dt), b, 2,
+            2, np.array([1.5], dt), x2, 2)
+    assert np.array_equal(x2.view(np.uint8), c["x_advanced"].view(np.uint8))

@@ -65,6 +65,13 @@ def test_generate_apply_transpose_match_the_oracle(orc, cuda, vt, it, max_bs, st
         assert np.array_equal(tc.view(np.uint8), to.view(np.uint8))
 
 
+@pytest.mark.parametrize("case", range(8))
+def test_device_matches_the_committed_reference_outputs(cuda, case):
+    """the device against tests/golden/jacobi_adaptive_reference.json (outputs of the REAL reference for
+    deterministic inputs): precisions, condition numbers, stored bytes, apply and advanced apply bit for bit"""
+    JC.check_against_golden(cuda, JC.load_golden()[case])
+
+
 @pytest.mark.parametrize("vt", ["f64", "f32"])
 def test_no_conditioning_means_no_detection(orc, cuda, vt):
     """reference/preconditioner/jacobi_kernels.cpp:357: autodetect() without a conditioning array
