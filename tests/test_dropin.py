@@ -40,6 +40,10 @@ HOT = [
     "gko::kernels::cuda::jacobi::simple_scalar_apply<double>",
     "gko::kernels::cuda::jacobi::simple_apply<float, int>",
     "gko::kernels::cuda::jacobi::generate<double, int>",
+    "gko::kernels::cuda::jacobi::apply<double, int>",
+    "gko::kernels::cuda::jacobi::transpose_jacobi<double, int>",
+    "gko::kernels::cuda::jacobi::conj_transpose_jacobi<float, long>",
+    "gko::kernels::cuda::jacobi::initialize_precisions",
 ]
 
 
