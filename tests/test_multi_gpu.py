@@ -2,7 +2,11 @@
 distributed SpMV rows bit-identical to the single-GPU rows (torch-built partition and read_distributed),
 every host-layer solver on distributed::Matrix against the same solver on one GPU, the fused distributed CG --
 once per exchange path: peer memory with 16-byte run pushes + in-place ghosts, peer memory with the indexed
-push, NCCL send/recv, and the opt-in pipelined exchange (owner blocks in arrival order, 1e-13-equal)."""
+push, NCCL send/recv, and with the opt-in pipelined exchange REQUESTED (owner blocks in arrival order,
+1e-13-equal).  Round 2 on B200s: the request falls back to the exact exchange -- the owner split needs
+column-sorted local rows, which ranks > 0 do not have, and the staged push needs contiguous runs
+(profiles/r02w_bench_2gpu.err) -- so that path currently proves the fallback, not
+the pipelined kernels."""
 import os
 import subprocess
 import sys
